@@ -1,0 +1,567 @@
+// TEST INFRASTRUCTURE ONLY (oracle) -- never linked or executed by the product path.
+//
+// Driver around the UNMODIFIED reference library (pavelsevecek/OpenSPH core/, compiled by oracle/Makefile into
+// oracle/_ref/libopensph_core*.a). It only calls the reference's public API:
+//   InitialConditions::addMonolithicBody (core/sph/initial/Initial.cpp:100-125), Tests::getSolidStorage
+//   (core/tests/Setup.cpp:57-88), getStandardEquations (core/sph/solvers/StandardSets.cpp:14-95),
+//   AsymmetricSolver / SymmetricSolver<3> ::create/integrate (core/sph/solvers/AsymmetricSolver.cpp:71-102),
+//   Factory::getTimeStepping / ITimeStepping::step (core/timestepping/TimeStepping.cpp:34-75),
+//   Factory::getFinder + IBasicFinder::findAll (core/objects/finders/NeighborFinder.h:39-133).
+//
+// Commands
+//   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
+//                    [--neighbours] [--steps K] [--integrator pc|euler] --in IN.snap --out OUT.snap
+//       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
+//       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
+//   sph_ref bench    --config C --n N --steps K --warmup W [--threads T] [--finder kd|grid] [--integrate-only]
+//       prints one JSON line with seconds per step of the reference CPU path.
+//
+// Snapshot format "SPHSNAP1": u32 count, then per array {char name[32]; u32 dtype(0=f64,1=u32); u32 ncomp;
+// u64 rows; payload}. All particle arrays are in the reference's own particle order.
+#include "Sph.h"
+#include "tests/Setup.h"
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace Sph;
+
+namespace {
+
+struct SnapWriter {
+    struct Item {
+        std::string name;
+        uint32_t dtype, ncomp;
+        uint64_t rows;
+        std::vector<char> data;
+    };
+    std::vector<Item> items;
+
+    void addF64(const std::string& name, const std::vector<double>& v, uint32_t ncomp) {
+        Item it{ name, 0, ncomp, v.size() / ncomp, {} };
+        it.data.resize(v.size() * 8);
+        memcpy(it.data.data(), v.data(), it.data.size());
+        items.push_back(std::move(it));
+    }
+    void addU32(const std::string& name, const std::vector<uint32_t>& v, uint32_t ncomp) {
+        Item it{ name, 1, ncomp, v.size() / ncomp, {} };
+        it.data.resize(v.size() * 4);
+        memcpy(it.data.data(), v.data(), it.data.size());
+        items.push_back(std::move(it));
+    }
+    void write(const std::string& path) {
+        std::ofstream f(path, std::ios::binary);
+        f.write("SPHSNAP1", 8);
+        uint32_t cnt = items.size();
+        f.write((char*)&cnt, 4);
+        for (auto& it : items) {
+            char name[32] = { 0 };
+            strncpy(name, it.name.c_str(), 31);
+            f.write(name, 32);
+            f.write((char*)&it.dtype, 4);
+            f.write((char*)&it.ncomp, 4);
+            f.write((char*)&it.rows, 8);
+            f.write(it.data.data(), it.data.size());
+        }
+    }
+};
+
+std::vector<double> vec4(ArrayView<const Vector> a) {
+    std::vector<double> out(a.size() * 4);
+    for (Size i = 0; i < a.size(); ++i) {
+        out[4 * i + 0] = a[i][X];
+        out[4 * i + 1] = a[i][Y];
+        out[4 * i + 2] = a[i][Z];
+        out[4 * i + 3] = a[i][H];
+    }
+    return out;
+}
+std::vector<double> scal(ArrayView<const Float> a) {
+    return std::vector<double>(a.begin(), a.end());
+}
+std::vector<uint32_t> uscal(ArrayView<const Size> a) {
+    return std::vector<uint32_t>(a.begin(), a.end());
+}
+std::vector<double> tt5(ArrayView<const TracelessTensor> a) {
+    std::vector<double> out(a.size() * 5);
+    for (Size i = 0; i < a.size(); ++i) {
+        out[5 * i + 0] = a[i](0, 0);
+        out[5 * i + 1] = a[i](1, 1);
+        out[5 * i + 2] = a[i](0, 1);
+        out[5 * i + 3] = a[i](0, 2);
+        out[5 * i + 4] = a[i](1, 2);
+    }
+    return out;
+}
+std::vector<double> st6(ArrayView<const SymmetricTensor> a) {
+    std::vector<double> out(a.size() * 6);
+    for (Size i = 0; i < a.size(); ++i) {
+        out[6 * i + 0] = a[i](0, 0);
+        out[6 * i + 1] = a[i](1, 1);
+        out[6 * i + 2] = a[i](2, 2);
+        out[6 * i + 3] = a[i](0, 1);
+        out[6 * i + 4] = a[i](0, 2);
+        out[6 * i + 5] = a[i](1, 2);
+    }
+    return out;
+}
+
+struct Args {
+    std::map<std::string, std::string> kv;
+    bool has(const std::string& k) const {
+        return kv.count(k) > 0;
+    }
+    std::string str(const std::string& k, const std::string& def = "") const {
+        auto it = kv.find(k);
+        return it == kv.end() ? def : it->second;
+    }
+    long num(const std::string& k, long def) const {
+        auto it = kv.find(k);
+        return it == kv.end() ? def : atol(it->second.c_str());
+    }
+};
+
+/// Run settings of the named config.
+RunSettings makeSettings(const std::string& config, const Args& args) {
+    RunSettings settings; // library defaults (core/system/Settings.cpp:486-715)
+    if (config == "preset" || config == "preset_const_h" || config == "fluid" || config == "collision_preset") {
+        // GUI "collision" preset, SphJob::getDefaultSettings (core/run/jobs/SimulationJobs.cpp:195-232),
+        // SELF_GRAVITY removed (out of scope), adaptive h per BASELINE.json configs 3-4.
+        settings.set(RunSettingsId::TIMESTEPPING_INTEGRATOR, TimesteppingEnum::PREDICTOR_CORRECTOR)
+            .set(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP, 0.01_f)
+            .set(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP, 10._f)
+            .set(RunSettingsId::TIMESTEPPING_COURANT_NUMBER, 0.2_f)
+            .set(RunSettingsId::SPH_SOLVER_TYPE, SolverEnum::ASYMMETRIC_SOLVER)
+            .set(RunSettingsId::SPH_SOLVER_FORCES, ForceEnum::PRESSURE | ForceEnum::SOLID_STRESS)
+            .set(RunSettingsId::SPH_DISCRETIZATION, DiscretizationEnum::STANDARD)
+            .set(RunSettingsId::SPH_FINDER, FinderEnum::KD_TREE)
+            .set(RunSettingsId::SPH_AV_TYPE, ArtificialViscosityEnum::STANDARD)
+            .set(RunSettingsId::SPH_AV_ALPHA, 1.5_f)
+            .set(RunSettingsId::SPH_AV_BETA, 3._f)
+            .set(RunSettingsId::SPH_KERNEL, KernelEnum::CUBIC_SPLINE)
+            .set(RunSettingsId::FINDER_LEAF_SIZE, 20)
+            .set(RunSettingsId::RUN_THREAD_GRANULARITY, 1000)
+            .set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH, SmoothingLengthEnum::CONTINUITY_EQUATION)
+            .set(RunSettingsId::SPH_ASYMMETRIC_COMPUTE_RADII_HASH_MAP, false)
+            .set(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR, true)
+            // Presets::makeAsteroidCollision (core/run/jobs/Presets.cpp:96-99)
+            .set(RunSettingsId::TIMESTEPPING_CRITERION,
+                TimeStepCriterionEnum::COURANT | TimeStepCriterionEnum::DIVERGENCE);
+        if (config == "preset_const_h") {
+            settings.set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH, EMPTY_FLAGS);
+        }
+        if (config == "fluid") {
+            settings.set(RunSettingsId::SPH_SOLVER_FORCES, ForceEnum::PRESSURE)
+                .set(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR, false);
+        }
+    } else if (config == "collision") {
+        // examples/04_simple_collision/SimpleCollision.cpp:12-41
+        settings.set(RunSettingsId::TIMESTEPPING_CRITERION, TimeStepCriterionEnum::COURANT)
+            .set(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP, 0.1_f);
+    }
+    // "hello", "solid_test": library defaults (examples/01_hello_asteroid/HelloAsteroid.cpp:11-36)
+    if (args.str("solver") == "asym") {
+        settings.set(RunSettingsId::SPH_SOLVER_TYPE, SolverEnum::ASYMMETRIC_SOLVER);
+    } else if (args.str("solver") == "sym") {
+        settings.set(RunSettingsId::SPH_SOLVER_TYPE, SolverEnum::SYMMETRIC_SOLVER);
+    }
+    if (args.str("finder") == "grid") {
+        settings.set(RunSettingsId::SPH_FINDER, FinderEnum::UNIFORM_GRID);
+    } else if (args.str("finder") == "kd") {
+        settings.set(RunSettingsId::SPH_FINDER, FinderEnum::KD_TREE);
+    }
+    if (args.has("corrected")) {
+        settings.set(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR, args.num("corrected", 1) != 0);
+    }
+    if (args.has("const-h")) {
+        settings.set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH, EMPTY_FLAGS);
+    }
+    if (args.str("integrator") == "euler") {
+        settings.set(RunSettingsId::TIMESTEPPING_INTEGRATOR, TimesteppingEnum::EULER_EXPLICIT);
+    } else if (args.str("integrator") == "pc") {
+        settings.set(RunSettingsId::TIMESTEPPING_INTEGRATOR, TimesteppingEnum::PREDICTOR_CORRECTOR);
+    }
+    if (args.has("criteria")) {
+        settings.set(RunSettingsId::TIMESTEPPING_CRITERION, Flags<TimeStepCriterionEnum>::fromValue(args.num("criteria", 0)));
+    }
+    settings.set(RunSettingsId::RUN_THREAD_CNT, int(args.num("threads", 0)));
+    return settings;
+}
+
+/// Builds the particle storage of the named config using the reference's own initial conditions.
+void makeStorage(const std::string& config, const Size n, const RunSettings& settings, Storage& storage) {
+    if (config == "solid_test") {
+        // core/sph/solvers/benchmark/Solvers.cpp:20 -- the author's own benchmark input
+        storage = Tests::getSolidStorage(n, BodySettings::getDefaults(), 1.e3_f);
+        return;
+    }
+    InitialConditions ic(settings);
+    BodySettings body;
+    if (config == "hello") {
+        body.set(BodySettingsId::PARTICLE_COUNT, int(n));
+        ic.addMonolithicBody(storage, SphericalDomain(Vector(0._f), 1.e3_f), body);
+    } else if (config == "collision" || config == "collision_preset") {
+        body.set(BodySettingsId::PARTICLE_COUNT, int(n));
+        ic.addMonolithicBody(storage, SphericalDomain(Vector(0._f), 1.e5_f), body);
+        body.set(BodySettingsId::PARTICLE_COUNT, int(max<Size>(n / 100, 10)));
+        BodyView impactor =
+            ic.addMonolithicBody(storage, SphericalDomain(Vector(1.4e5_f, 0._f, 0._f), 2.e4_f), body);
+        impactor.addVelocity(Vector(-5.e3_f, 0._f, 0._f));
+    } else if (config == "preset" || config == "preset_const_h") {
+        body.set(BodySettingsId::PARTICLE_COUNT, int(n));
+        if (n >= 5000000) {
+            body.set(BodySettingsId::WEIBULL_SAMPLE_DISTRIBUTIONS, true);
+        }
+        ic.addMonolithicBody(storage, SphericalDomain(Vector(0._f), 5.e4_f), body);
+    } else if (config == "fluid") {
+        body.set(BodySettingsId::PARTICLE_COUNT, int(n))
+            .set(BodySettingsId::RHEOLOGY_YIELDING, YieldingEnum::NONE)
+            .set(BodySettingsId::RHEOLOGY_DAMAGE, FractureEnum::NONE);
+        ic.addMonolithicBody(storage, SphericalDomain(Vector(0._f), 5.e4_f), body);
+    } else {
+        throw std::runtime_error("unknown config " + config);
+    }
+}
+
+/// Smooth analytic velocity field so that AV / stress / continuity terms are non-trivial.
+void seedVelocity(Storage& storage, const Float scale) {
+    ArrayView<Vector> r, v, dv;
+    tie(r, v, dv) = storage.getAll<Vector>(QuantityId::POSITION);
+    Float rmax = 0._f;
+    for (Size i = 0; i < r.size(); ++i) {
+        rmax = max(rmax, getLength(r[i]));
+    }
+    for (Size i = 0; i < r.size(); ++i) {
+        const Float x = r[i][X] / rmax, y = r[i][Y] / rmax, z = r[i][Z] / rmax;
+        Vector w(-0.8_f * x + 0.3_f * y * z, 0.5_f * std::sin(3._f * x) - 0.6_f * y, 0.4_f * z * x - 0.7_f * z + 0.2_f * y);
+        const Float hOld = v[i][H];
+        v[i] += scale * w;
+        v[i][H] = hOld;
+    }
+}
+
+/// Random perturbation of the state to exercise every branch (EoS phases, yielding, damage, undamaged filter).
+void jitter(Storage& storage, const unsigned seed) {
+    std::mt19937_64 gen(seed);
+    std::uniform_real_distribution<double> uni(0., 1.);
+    ArrayView<Vector> r, v, dv;
+    tie(r, v, dv) = storage.getAll<Vector>(QuantityId::POSITION);
+    ArrayView<Float> rho = storage.getValue<Float>(QuantityId::DENSITY);
+    ArrayView<Float> u = storage.getValue<Float>(QuantityId::ENERGY);
+    Float cs0 = 3000._f;
+    for (Size i = 0; i < r.size(); ++i) {
+        const Float h = r[i][H];
+        r[i][X] += 0.25_f * h * (2 * uni(gen) - 1);
+        r[i][Y] += 0.25_f * h * (2 * uni(gen) - 1);
+        r[i][Z] += 0.25_f * h * (2 * uni(gen) - 1);
+        r[i][H] = h * (0.85_f + 0.3_f * uni(gen));
+        const Float vh = v[i][H];
+        v[i] += Vector(0.02_f * cs0 * (2 * uni(gen) - 1), 0.02_f * cs0 * (2 * uni(gen) - 1), 0.02_f * cs0 * (2 * uni(gen) - 1));
+        v[i][H] = vh;
+        rho[i] *= 0.9_f + 0.2_f * uni(gen);
+        const Float c = uni(gen);
+        u[i] = c < 0.5 ? 1.e5_f * uni(gen) : (c < 0.8 ? 5.e6_f * uni(gen) : 3.e7_f * uni(gen));
+    }
+    if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
+        ArrayView<TracelessTensor> s = storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS);
+        for (Size i = 0; i < s.size(); ++i) {
+            const Float a = (uni(gen) < 0.3 ? 4.e9_f : 4.e8_f);
+            s[i] = TracelessTensor(a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1));
+        }
+    }
+    if (storage.has(QuantityId::DAMAGE)) {
+        ArrayView<Float> d = storage.getValue<Float>(QuantityId::DAMAGE);
+        for (Size i = 0; i < d.size(); ++i) {
+            const Float c = uni(gen);
+            d[i] = c < 0.4 ? 0._f : (c < 0.47 ? 1._f : uni(gen));
+        }
+    }
+}
+
+void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& w) {
+    ArrayView<const Vector> r, v, dv;
+    tie(r, v, dv) = storage.getAll<Vector>(QuantityId::POSITION);
+    w.addF64("pos", vec4(r), 4);
+    w.addF64("vel", vec4(v), 4);
+    w.addF64("acc", vec4(dv), 4);
+    w.addF64("mass", scal(storage.getValue<Float>(QuantityId::MASS)), 1);
+    auto first = [&](const char* name, const char* dname, QuantityId id) {
+        if (storage.has(id)) {
+            w.addF64(name, scal(storage.getValue<Float>(id)), 1);
+            if (dname && storage.getQuantity(id).getOrderEnum() != OrderEnum::ZERO) {
+                w.addF64(dname, scal(storage.getDt<Float>(id)), 1);
+            }
+        }
+    };
+    first("rho", "drho", QuantityId::DENSITY);
+    first("u", "du", QuantityId::ENERGY);
+    first("p", nullptr, QuantityId::PRESSURE);
+    first("cs", nullptr, QuantityId::SOUND_SPEED);
+    first("reduce", nullptr, QuantityId::STRESS_REDUCING);
+    first("damage", "ddamage", QuantityId::DAMAGE);
+    first("eps_min", nullptr, QuantityId::EPS_MIN);
+    first("m_zero", nullptr, QuantityId::M_ZERO);
+    first("growth", nullptr, QuantityId::EXPLICIT_GROWTH);
+    first("divv", nullptr, QuantityId::VELOCITY_DIVERGENCE);
+    if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
+        w.addF64("S", tt5(storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)), 5);
+        w.addF64("dS", tt5(storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)), 5);
+    }
+    if (storage.has(QuantityId::VELOCITY_GRADIENT)) {
+        w.addF64("gradv", st6(storage.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT)), 6);
+    }
+    if (storage.has(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)) {
+        w.addF64("corr", st6(storage.getValue<SymmetricTensor>(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)), 6);
+    }
+    auto uq = [&](const char* name, QuantityId id) {
+        if (storage.has(id)) {
+            w.addU32(name, uscal(storage.getValue<Size>(id)), 1);
+        }
+    };
+    uq("flag", QuantityId::FLAG);
+    uq("n_flaws", QuantityId::N_FLAWS);
+    uq("ncnt", QuantityId::NEIGHBOR_CNT);
+
+    // materials: index ranges + every constant the device path needs
+    std::vector<uint32_t> matRange;
+    std::vector<double> matParams;
+    for (Size i = 0; i < storage.getMaterialCnt(); ++i) {
+        MaterialView mat = storage.getMaterial(i);
+        IndexSequence seq = mat.sequence();
+        matRange.push_back(*seq.begin());
+        matRange.push_back(*seq.end());
+        const BodySettings& b = mat->getParams();
+        auto f = [&](BodySettingsId id) { return double(b.get<Float>(id)); };
+        const Interval rhoRange = mat->range(QuantityId::DENSITY);
+        const Interval uRange = mat->range(QuantityId::ENERGY);
+        const Interval dRange = mat->range(QuantityId::DAMAGE);
+        const double row[32] = {
+            double(int(b.get<EosEnum>(BodySettingsId::EOS))),
+            f(BodySettingsId::TILLOTSON_SUBLIMATION), f(BodySettingsId::TILLOTSON_ENERGY_IV),
+            f(BodySettingsId::TILLOTSON_ENERGY_CV), f(BodySettingsId::TILLOTSON_SMALL_A),
+            f(BodySettingsId::TILLOTSON_SMALL_B), f(BodySettingsId::DENSITY), f(BodySettingsId::BULK_MODULUS),
+            f(BodySettingsId::TILLOTSON_NONLINEAR_B), f(BodySettingsId::TILLOTSON_ALPHA),
+            f(BodySettingsId::TILLOTSON_BETA), f(BodySettingsId::ADIABATIC_INDEX),
+            double(int(b.get<YieldingEnum>(BodySettingsId::RHEOLOGY_YIELDING))),
+            double(int(b.get<FractureEnum>(BodySettingsId::RHEOLOGY_DAMAGE))),
+            f(BodySettingsId::SHEAR_MODULUS), f(BodySettingsId::ELASTICITY_LIMIT), f(BodySettingsId::MELT_ENERGY),
+            f(BodySettingsId::YOUNG_MODULUS),
+            rhoRange.lower(), rhoRange.upper(), uRange.lower(), uRange.upper(), dRange.lower(), dRange.upper(),
+            mat->minimal(QuantityId::DENSITY), mat->minimal(QuantityId::ENERGY), mat->minimal(QuantityId::DAMAGE),
+            mat->minimal(QuantityId::DEVIATORIC_STRESS), 0, 0, 0, 0 };
+        matParams.insert(matParams.end(), row, row + 32);
+    }
+    w.addU32("mat_range", matRange, 2);
+    w.addF64("mat_params", matParams, 32);
+
+    LutKernel<3> kernel = Factory::getKernel<3>(settings);
+    const Flags<SmoothingLengthEnum> hflags =
+        settings.getFlags<SmoothingLengthEnum>(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH);
+    const Flags<ForceEnum> forces = settings.getFlags<ForceEnum>(RunSettingsId::SPH_SOLVER_FORCES);
+    const Interval hRange = settings.get<Interval>(RunSettingsId::SPH_SMOOTHING_LENGTH_RANGE);
+    const Interval nRange = settings.get<Interval>(RunSettingsId::SPH_NEIGHBOR_RANGE);
+    std::vector<double> run = {
+        kernel.radius(),
+        settings.get<Float>(RunSettingsId::SPH_AV_ALPHA),
+        settings.get<Float>(RunSettingsId::SPH_AV_BETA),
+        double(forces.has(ForceEnum::PRESSURE)),
+        double(forces.has(ForceEnum::SOLID_STRESS)),
+        double(settings.get<bool>(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR)),
+        double(settings.get<bool>(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED)),
+        double(hflags.has(SmoothingLengthEnum::CONTINUITY_EQUATION)),
+        double(hflags.has(SmoothingLengthEnum::SOUND_SPEED_ENFORCING)),
+        double(int(settings.get<ContinuityEnum>(RunSettingsId::SPH_CONTINUITY_MODE))),
+        double(int(settings.get<DiscretizationEnum>(RunSettingsId::SPH_DISCRETIZATION))),
+        hRange.lower(), hRange.upper(),
+        settings.get<Float>(RunSettingsId::SPH_NEIGHBOR_ENFORCING), nRange.lower(), nRange.upper(),
+        settings.get<Float>(RunSettingsId::TIMESTEPPING_COURANT_NUMBER),
+        settings.get<Float>(RunSettingsId::TIMESTEPPING_DERIVATIVE_FACTOR),
+        settings.get<Float>(RunSettingsId::TIMESTEPPING_DIVERGENCE_FACTOR),
+        double(settings.getFlags<TimeStepCriterionEnum>(RunSettingsId::TIMESTEPPING_CRITERION).value()),
+        settings.get<Float>(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP),
+        settings.get<Float>(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP),
+        settings.get<Float>(RunSettingsId::TIMESTEPPING_MAX_INCREASE),
+        double(int(settings.get<SolverEnum>(RunSettingsId::SPH_SOLVER_TYPE))),
+        double(int(settings.get<TimesteppingEnum>(RunSettingsId::TIMESTEPPING_INTEGRATOR))),
+    };
+    w.addF64("run_params", run, 1);
+
+    // the LUT exactly as the reference builds it (core/sph/kernel/Kernel.h:85-101)
+    const Size entries = 40000;
+    const Float qSqrToIdx = Float(entries) / sqr(kernel.radius());
+    std::vector<double> lutGrad(entries + 1), lutVal(entries + 1);
+    for (Size i = 0; i <= entries; ++i) {
+        const Float qSqr = Float(i) / qSqrToIdx;
+        // exact node values: at the nodes the linear interpolation returns the table entries themselves
+        lutGrad[i] = (i < entries) ? kernel.gradImpl(qSqr) : 0.;
+        lutVal[i] = (i < entries) ? kernel.valueImpl(qSqr) : 0.;
+    }
+    w.addF64("lut_grad", lutGrad, 1);
+    w.addF64("lut_val", lutVal, 1);
+}
+
+/// Neighbour lists exactly as AsymmetricSolver::loop selects them (core/sph/solvers/AsymmetricSolver.cpp:174-199),
+/// obtained from the reference finder; sorted by index for set comparison.
+void dumpNeighbours(const Storage& storage, const RunSettings& settings, IScheduler& scheduler, SnapWriter& w) {
+    ArrayView<const Vector> r = storage.getValue<Vector>(QuantityId::POSITION);
+    AutoPtr<ISymmetricFinder> finder = Factory::getFinder(settings);
+    finder->build(scheduler, r);
+    LutKernel<3> kernel = Factory::getKernel<3>(settings);
+    Float maxH = 0._f;
+    for (Size i = 0; i < r.size(); ++i) {
+        maxH = max(maxH, r[i][H]);
+    }
+    const Float maxRadius = maxH * kernel.radius();
+    std::vector<uint32_t> offsets(2 * (r.size() + 1)); // u64 stored as two u32 (little endian)
+    std::vector<uint32_t> idxs;
+    Array<NeighborRecord> neighs;
+    uint64_t total = 0;
+    for (Size i = 0; i < r.size(); ++i) {
+        offsets[2 * i] = uint32_t(total & 0xffffffffu);
+        offsets[2 * i + 1] = uint32_t(total >> 32);
+        const Float radius = 0.5_f * (r[i][H] * kernel.radius() + maxRadius);
+        finder->findAll(i, radius, neighs);
+        std::vector<uint32_t> mine;
+        for (auto& n : neighs) {
+            const Size j = n.index;
+            const Float hbar = 0.5_f * (r[i][H] + r[j][H]);
+            if (i == j || n.distanceSqr >= sqr(kernel.radius() * hbar)) {
+                continue;
+            }
+            mine.push_back(j);
+        }
+        std::sort(mine.begin(), mine.end());
+        idxs.insert(idxs.end(), mine.begin(), mine.end());
+        total += mine.size();
+    }
+    offsets[2 * r.size()] = uint32_t(total & 0xffffffffu);
+    offsets[2 * r.size() + 1] = uint32_t(total >> 32);
+    w.addU32("nbr_offsets", offsets, 2);
+    w.addU32("nbr_idx", idxs, 1);
+}
+
+double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        std::cerr << "usage: sph_ref snapshot|bench --config C --n N ..." << std::endl;
+        return 2;
+    }
+    const std::string cmd = argv[1];
+    Args args;
+    for (int i = 2; i < argc; ++i) {
+        std::string k = argv[i];
+        if (k.rfind("--", 0) != 0) {
+            continue;
+        }
+        k = k.substr(2);
+        if (i + 1 < argc && std::string(argv[i + 1]).rfind("--", 0) != 0) {
+            args.kv[k] = argv[++i];
+        } else {
+            args.kv[k] = "1";
+        }
+    }
+    try {
+        const std::string config = args.str("config", "hello");
+        const Size n = Size(args.num("n", 10000));
+        RunSettings settings = makeSettings(config, args);
+        SharedPtr<IScheduler> scheduler = Factory::getScheduler(settings);
+        SharedPtr<Storage> storage = makeShared<Storage>();
+        makeStorage(config, n, settings, *storage);
+
+        AutoPtr<ISolver> solver = Factory::getSolver(*scheduler, settings);
+        for (Size i = 0; i < storage->getMaterialCnt(); ++i) {
+            solver->create(*storage, storage->getMaterial(i));
+        }
+        if (args.num("velocity", 1) != 0) {
+            seedVelocity(*storage, Float(args.num("vscale", 50)));
+        }
+        if (args.has("jitter")) {
+            jitter(*storage, unsigned(args.num("jitter", 1)));
+        }
+        const Size N = storage->getParticleCnt();
+
+        if (cmd == "snapshot") {
+            if (args.has("in")) {
+                SnapWriter w;
+                dumpState(*storage, settings, w);
+                w.write(args.str("in"));
+            }
+            Statistics stats;
+            stats.set(StatisticsId::RUN_TIME, 0._f);
+            const long steps = args.num("steps", 0);
+            std::vector<double> dts;
+            if (steps == 0) {
+                storage->zeroHighestDerivatives(*scheduler);
+                solver->integrate(*storage, stats);
+            } else {
+                AutoPtr<ITimeStepping> stepping = Factory::getTimeStepping(settings, storage);
+                for (long s = 0; s < steps; ++s) {
+                    dts.push_back(stepping->getTimeStep());
+                    stepping->step(*scheduler, *solver, stats);
+                }
+                dts.push_back(stepping->getTimeStep());
+            }
+            SnapWriter w;
+            dumpState(*storage, settings, w);
+            if (!dts.empty()) {
+                w.addF64("dt_history", dts, 1);
+            }
+            if (args.has("neighbours")) {
+                dumpNeighbours(*storage, settings, *scheduler, w);
+            }
+            w.write(args.str("out", "out.snap"));
+            std::cout << "{\"particles\": " << N << ", \"materials\": " << storage->getMaterialCnt() << "}"
+                      << std::endl;
+        } else if (cmd == "bench") {
+            const long steps = args.num("steps", 3), warmup = args.num("warmup", 1);
+            Statistics stats;
+            stats.set(StatisticsId::RUN_TIME, 0._f);
+            double total = 0.;
+            if (args.has("integrate-only")) {
+                for (long s = 0; s < warmup + steps; ++s) {
+                    storage->zeroHighestDerivatives(*scheduler);
+                    const double t0 = now();
+                    solver->integrate(*storage, stats);
+                    if (s >= warmup) {
+                        total += now() - t0;
+                    }
+                }
+            } else {
+                // tiny fixed dt keeps the lattice intact so every step does the same work
+                settings.set(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP, 1.e-6_f)
+                    .set(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP, 1.e-6_f);
+                AutoPtr<ITimeStepping> stepping = Factory::getTimeStepping(settings, storage);
+                for (long s = 0; s < warmup + steps; ++s) {
+                    const double t0 = now();
+                    stepping->step(*scheduler, *solver, stats);
+                    if (s >= warmup) {
+                        total += now() - t0;
+                    }
+                }
+            }
+            const MinMaxMean nc = stats.get<MinMaxMean>(StatisticsId::NEIGHBOR_COUNT);
+            printf("{\"particles\": %u, \"steps\": %ld, \"seconds_per_step\": %.6f, \"particle_updates_per_s\": %.6e, "
+                   "\"threads\": %d, \"neigh_mean\": %.2f, \"neigh_max\": %.0f, \"mode\": \"%s\"}\n",
+                N, steps, total / steps, double(N) * steps / total, int(scheduler->getThreadCnt()), nc.mean(), nc.max(),
+                args.has("integrate-only") ? "integrate" : "full_step");
+        } else {
+            std::cerr << "unknown command " << cmd << std::endl;
+            return 2;
+        }
+    } catch (const std::exception& e) {
+        std::cerr << "sph_ref error: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}
