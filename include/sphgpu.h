@@ -1,0 +1,225 @@
+/*
+ * sphgpu.h -- C ABI of the B200-native SPH evaluation engine (libsphgpu.so).
+ *
+ * This is the drop-in boundary for OpenSPH's per-step hot path. The reference has no C ABI (it is one C++
+ * address space); each entry point below names the reference interface it replaces (paths relative to the
+ * reference root). The reference-side binding (a C++ `GpuSolver : ISolver` that forwards to these calls) is
+ * in opensph_b200/host/GpuSolver.{h,cpp} and described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SPHGPU_E_* code otherwise; sphgpu_last_error() returns a
+ *    human-readable message for the calling thread (reference convention: C++ exceptions such as InvalidSetup,
+ *    core/sph/solvers/AsymmetricSolver.cpp:228-234 -- the C++ wrapper turns non-zero into those exceptions);
+ *  - one context per device, calls on one context are serialised by the caller (ISolver::integrate is not
+ *    re-entrant, core/timestepping/ISolver.h:28-31);
+ *  - plain pointers and sizes only; no CUDA or torch types. Pointers are HOST pointers unless the name says
+ *    `_device`;
+ *  - there is NO CPU fallback: if no CUDA device is usable, sphgpu_create fails with SPHGPU_E_NO_DEVICE.
+ */
+#ifndef SPHGPU_H
+#define SPHGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHGPU_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------------------- */
+enum {
+    SPHGPU_OK = 0,
+    SPHGPU_E_INVALID = -1,     /* bad argument / unsupported setup  (reference: InvalidSetup)              */
+    SPHGPU_E_NO_DEVICE = -2,   /* no usable CUDA device -- there is no CPU path                            */
+    SPHGPU_E_CUDA = -3,        /* a CUDA runtime call or kernel failed                                      */
+    SPHGPU_E_OOM = -4,         /* device allocation failed                                                  */
+    SPHGPU_E_STATE = -5        /* call order violated (e.g. integrate before the state was uploaded)       */
+};
+
+/* ---- enumerations mirroring the reference's settings (core/system/Settings.h) ------------------------ */
+enum { SPHGPU_FORCE_PRESSURE = 1u << 0, SPHGPU_FORCE_SOLID_STRESS = 1u << 1 }; /* ForceEnum subset         */
+enum {
+    SPHGPU_FLAG_CORRECTION_TENSOR = 1u << 0,    /* RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR          */
+    SPHGPU_FLAG_SUM_ONLY_UNDAMAGED = 1u << 1,   /* RunSettingsId::SPH_SUM_ONLY_UNDAMAGED                     */
+    SPHGPU_FLAG_ADAPTIVE_H = 1u << 2,           /* SmoothingLengthEnum::CONTINUITY_EQUATION                  */
+    SPHGPU_FLAG_SOUND_SPEED_ENFORCING = 1u << 3 /* SmoothingLengthEnum::SOUND_SPEED_ENFORCING                */
+};
+enum { SPHGPU_DISCR_STANDARD = 0, SPHGPU_DISCR_BENZ_ASPHAUG = 1 };        /* DiscretizationEnum            */
+enum { SPHGPU_CONTINUITY_STANDARD = 0, SPHGPU_CONTINUITY_SUM_ONLY_UNDAMAGED = 1 }; /* ContinuityEnum       */
+enum { SPHGPU_EOS_NONE = 0, SPHGPU_EOS_IDEAL_GAS = 1, SPHGPU_EOS_TILLOTSON = 4 };  /* EosEnum values       */
+enum { SPHGPU_YIELD_NONE = 0, SPHGPU_YIELD_ELASTIC = 1, SPHGPU_YIELD_VON_MISES = 2, SPHGPU_YIELD_DUST = 4 };
+enum { SPHGPU_FRACTURE_NONE = 0, SPHGPU_FRACTURE_SCALAR_GRADY_KIPP = 1 };
+/* TimeStepCriterionEnum bit values (core/system/Settings.h:577-592) */
+enum {
+    SPHGPU_CRIT_COURANT = 1u << 1,
+    SPHGPU_CRIT_DERIVATIVES = 1u << 2,
+    SPHGPU_CRIT_ACCELERATION = 1u << 3,
+    SPHGPU_CRIT_DIVERGENCE = 1u << 4
+};
+/* CriterionId (core/timestepping/TimeStepCriterion.h:18-26) */
+enum {
+    SPHGPU_CRITID_INITIAL_VALUE = 0,
+    SPHGPU_CRITID_MAXIMAL_VALUE = 1,
+    SPHGPU_CRITID_DERIVATIVE = 2,
+    SPHGPU_CRITID_CFL_CONDITION = 3,
+    SPHGPU_CRITID_ACCELERATION = 4,
+    SPHGPU_CRITID_DIVERGENCE = 5,
+    SPHGPU_CRITID_MAX_CHANGE = 6
+};
+
+/* Quantities of the Storage schema the path touches (QuantityId in
+ * core/quantities/QuantityIds.h). `order` selects value (0), first (1) or second (2) time derivative. */
+enum {
+    SPHGPU_Q_POSITION = 0,            /* Vector {x,y,z,h}; order 1 = {v, dh/dt}; order 2 = {a, 0}           */
+    SPHGPU_Q_MASS = 1,                /* f64                                                                 */
+    SPHGPU_Q_DENSITY = 2,             /* f64, orders 0..1                                                    */
+    SPHGPU_Q_ENERGY = 3,              /* f64, orders 0..1                                                    */
+    SPHGPU_Q_PRESSURE = 4,            /* f64                                                                 */
+    SPHGPU_Q_SOUND_SPEED = 5,         /* f64                                                                 */
+    SPHGPU_Q_DEVIATORIC_STRESS = 6,   /* TracelessTensor {xx,yy,xy,xz,yz}, orders 0..1                       */
+    SPHGPU_Q_DAMAGE = 7,              /* f64, orders 0..1                                                    */
+    SPHGPU_Q_STRESS_REDUCING = 8,     /* f64                                                                 */
+    SPHGPU_Q_VELOCITY_DIVERGENCE = 9, /* f64                                                                 */
+    SPHGPU_Q_VELOCITY_GRADIENT = 10,  /* SymmetricTensor {xx,yy,zz,xy,xz,yz}                                 */
+    SPHGPU_Q_CORRECTION_TENSOR = 11,  /* SymmetricTensor (STRAIN_RATE_CORRECTION_TENSOR)                     */
+    SPHGPU_Q_EPS_MIN = 12,            /* f64                                                                 */
+    SPHGPU_Q_M_ZERO = 13,             /* f64                                                                 */
+    SPHGPU_Q_EXPLICIT_GROWTH = 14,    /* f64                                                                 */
+    SPHGPU_Q_N_FLAWS = 15,            /* u32                                                                 */
+    SPHGPU_Q_FLAG = 16,               /* u32  body index                                                     */
+    SPHGPU_Q_NEIGHBOR_CNT = 17,       /* u32                                                                 */
+    SPHGPU_Q_COUNT = 18
+};
+
+/* Host memory layouts understood by upload/download. */
+enum {
+    SPHGPU_LAYOUT_PACKED = 0, /* components tightly packed: Vector 4 f64, TracelessTensor 5 f64 {xx,yy,xy,xz,yz},
+                                 SymmetricTensor 6 f64 {xx,yy,zz,xy,xz,yz}, scalars 1 f64 / 1 u32              */
+    SPHGPU_LAYOUT_OPENSPH = 1 /* the reference's in-memory AoS: Vector 32 B {x,y,z,h} (geometry/Vector.h:378-395),
+                                 TracelessTensor 64 B {xx,yy,xy,xz|yz,pad} (TracelessTensor.h:36-45),
+                                 SymmetricTensor 64 B {xx,yy,zz,pad|xy,xz,yz,pad} (SymmetricTensor.h:18-21)    */
+};
+
+/* ---- configuration ------------------------------------------------------------------------------------ */
+
+/* Run-level configuration: what AsymmetricSolver's constructor reads from RunSettings
+ * (core/sph/solvers/AsymmetricSolver.cpp:58-69,124-136; core/sph/solvers/StandardSets.cpp:14-95). */
+typedef struct sphgpu_config {
+    uint32_t abi_version;        /* SPHGPU_ABI_VERSION                                                        */
+    uint32_t forces;             /* SPHGPU_FORCE_*                                                            */
+    uint32_t flags;              /* SPHGPU_FLAG_*                                                             */
+    uint32_t discretization;     /* SPHGPU_DISCR_*  (only STANDARD is implemented)                            */
+    uint32_t continuity_mode;    /* SPHGPU_CONTINUITY_*                                                       */
+    uint32_t lut_entries;        /* LutKernel::NEntries = 40000 (tables hold lut_entries+1 values)            */
+    const double* lut_grad;      /* (dW/dq)/q sampled in q^2, core/sph/kernel/Kernel.h:85-101                 */
+    const double* lut_value;     /* W sampled in q^2 (only W(0) is needed: density floor); may be NULL        */
+    double kernel_radius;        /* LutKernel::radius(), 2 for the cubic spline                               */
+    double av_alpha, av_beta;    /* StandardAV, core/sph/equations/av/Standard.h:44-46                        */
+    double h_min, h_max;         /* SPH_SMOOTHING_LENGTH_RANGE, EquationTerm.cpp:349,356-364                  */
+    double neigh_enforcing;      /* SPH_NEIGHBOR_ENFORCING (used only with SOUND_SPEED_ENFORCING)             */
+    double neigh_lower, neigh_upper; /* SPH_NEIGHBOR_RANGE                                                    */
+    /* time-step criteria, core/timestepping/TimeStepCriterion.cpp:117-419 */
+    uint32_t criteria;           /* SPHGPU_CRIT_* mask                                                        */
+    uint32_t reserved0;
+    double courant;              /* TIMESTEPPING_COURANT_NUMBER                                               */
+    double derivative_factor;    /* TIMESTEPPING_DERIVATIVE_FACTOR                                            */
+    double divergence_factor;    /* TIMESTEPPING_DIVERGENCE_FACTOR                                            */
+    double max_change;           /* TIMESTEPPING_MAX_INCREASE (>= 1e300 means unlimited)                      */
+} sphgpu_config;
+
+/* Per-material constants (one per body; materials own contiguous particle index ranges,
+ * MaterialView::sequence(), core/quantities/IMaterial.h:110-194). */
+typedef struct sphgpu_material {
+    uint32_t begin, end;         /* particle index range [begin,end)                                          */
+    uint32_t eos;                /* SPHGPU_EOS_*                                                              */
+    uint32_t yielding;           /* SPHGPU_YIELD_*                                                            */
+    uint32_t fracture;           /* SPHGPU_FRACTURE_*                                                         */
+    uint32_t reserved0;
+    /* TillotsonEos (core/physics/Eos.cpp:184-238) */
+    double til_u0, til_uiv, til_ucv, til_a, til_b, rho0, til_A, til_B, til_alpha, til_beta;
+    double gamma;                /* IdealGasEos (Eos.cpp:42-45)                                               */
+    double shear_modulus;        /* mu, SolidStressForce::finalize (EquationTerm.cpp:190-201)                 */
+    double elasticity_limit;     /* von Mises Y0 (Rheology.cpp:47)                                            */
+    double melt_energy;          /* u_melt (Rheology.cpp:50)                                                  */
+    double young_modulus;        /* set by ScalarGradyKippModel::setFlaws (Damage.cpp:44-48)                  */
+    /* ranges / minimals used by the integrators and the derivative criterion (IMaterial::range/minimal) */
+    double rho_min, rho_max, u_min, u_max, d_min, d_max;
+    double rho_small, u_small, d_small, s_small;
+} sphgpu_material;
+
+typedef struct sphgpu_stats {
+    uint32_t neigh_min, neigh_max; /* StatisticsId::NEIGHBOR_COUNT (AsymmetricSolver.cpp:218-225)            */
+    double neigh_mean;
+    uint64_t pair_count;           /* sum of NEIGHBOR_CNT                                                    */
+    double gpu_ms;                 /* device time of the call, CUDA events                                   */
+    uint32_t kernel_launches;      /* kernels launched by this call                                          */
+    uint32_t reserved0;
+} sphgpu_stats;
+
+typedef struct sphgpu_timestep {
+    double dt;                 /* new time step                                                              */
+    uint32_t criterion;        /* SPHGPU_CRITID_*                                                            */
+    uint32_t reserved0;
+} sphgpu_timestep;
+
+typedef struct sphgpu_ctx sphgpu_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+
+/* Replaces AsymmetricSolver::AsymmetricSolver + Factory::getKernel/getFinder (AsymmetricSolver.cpp:58-69,124-136).
+ * `capacity` >= n_particles reserves room for ghost (halo) particles appended after the owned ones. */
+int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, uint32_t n_materials,
+    uint32_t n_particles, uint32_t capacity, int device, sphgpu_ctx** out);
+int sphgpu_destroy(sphgpu_ctx* ctx);
+const char* sphgpu_last_error(void);
+uint32_t sphgpu_abi_version(void);
+
+/* ---- state transfer (replaces Storage::getValue/getDt/getD2t array access, core/quantities/Storage.h:291-608) */
+
+/* Copies `count` particles starting at particle index `first` of quantity `q`/`order` between host memory in
+ * `layout` and the device-resident SoA mirror. */
+int sphgpu_upload(sphgpu_ctx* ctx, int q, int order, int layout, const void* host, uint32_t first, uint32_t count);
+int sphgpu_download(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count);
+/* Same, PACKED layout only, with a DEVICE pointer on the context's device (used by the multi-GPU halo plumbing). */
+int sphgpu_upload_device(sphgpu_ctx* ctx, int q, int order, const void* dev, uint32_t first, uint32_t count);
+int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_t first, uint32_t count);
+/* Number of particles that take part as neighbours: owned + ghosts (ghosts occupy [n_particles, n_active)). */
+int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
+
+/* ---- the hot path --------------------------------------------------------------------------------------- */
+
+/* Replaces IAsymmetricSolver::integrate (AsymmetricSolver.cpp:71-96): material->initialize (EoS + rheology),
+ * equations.initialize (h clamp), finder build + findAll, derivatives.eval over all pairs, accumulated.store,
+ * equations.finalize, material->finalize (damage growth). Highest derivatives are OVERWRITTEN, i.e. the call
+ * behaves as the reference does after Storage::zeroHighestDerivatives (TimeStepping.cpp:238,334). */
+int sphgpu_integrate(sphgpu_ctx* ctx, double t, sphgpu_stats* stats);
+
+/* Replaces PredictorCorrector::makePredictions + swap + zeroHighestDerivatives (TimeStepping.cpp:286-300,331-334). */
+int sphgpu_step_predict(sphgpu_ctx* ctx, double dt);
+/* Replaces PredictorCorrector::makeCorrections (TimeStepping.cpp:302-322). */
+int sphgpu_step_correct(sphgpu_ctx* ctx, double dt);
+/* Replaces EulerExplicit::stepParticles after solver.integrate (TimeStepping.cpp:243-264). */
+int sphgpu_step_euler(sphgpu_ctx* ctx, double dt);
+/* Replaces MultiCriterion::compute (TimeStepCriterion.cpp:389-419). */
+int sphgpu_compute_timestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out);
+/* One whole PredictorCorrector step on the device (ITimeStepping::step, TimeStepping.cpp:34-75):
+ * predict(dt) -> integrate -> correct(dt) -> criteria. No host<->device traffic except the returned scalars. */
+int sphgpu_step_pc(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
+
+/* ---- inspection (tests) --------------------------------------------------------------------------------- */
+
+/* Neighbour lists exactly as AsymmetricSolver::loop selects them (AsymmetricSolver.cpp:174-199), CSR:
+ * offsets[n_particles+1], indices ascending per particle. Pass idx == NULL to obtain only offsets. */
+int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_t* idx, uint64_t idx_capacity);
+/* Device-time breakdown of the last integrate call in milliseconds: [0] grid build + sort, [1] prologue + pack,
+ * [2] pair kernel, [3] rest. */
+int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4);
+/* Selects the pair-kernel variant (0 = default). For A/B measurements only. */
+int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHGPU_H */

@@ -1,0 +1,131 @@
+"""ctypes wrapper of the plain-C oracle (oracle/liboracle_port.so). Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+from opensph_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "oracle", "liboracle_port.so")
+
+_D = C.POINTER(C.c_double)
+_U = C.POINTER(C.c_uint32)
+
+
+class OrcState(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("pad0", C.c_uint32)] + [(k, _D) for k in (
+        "pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
+        "eps_min", "m_zero", "growth")] + [(k, _U) for k in ("n_flaws", "flag", "ncnt")] + [(k, _D) for k in (
+        "divv", "gradv", "corr", "acc_pred", "drho_pred", "du_pred", "dS_pred", "ddamage_pred")]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_find_neighbours.restype = C.c_uint64
+        _lib.orc_timestep.restype = C.c_double
+    return _lib
+
+
+_F64 = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
+        "eps_min", "m_zero", "growth", "divv", "gradv", "corr")
+_U32 = ("n_flaws", "flag", "ncnt")
+_PRED = {"acc_pred": "acc", "drho_pred": "drho", "du_pred": "du", "dS_pred": "dS", "ddamage_pred": "ddamage"}
+
+
+class OraclePort:
+    """Holds one particle state (copied from a snapshot dict) and runs the C restatement on it."""
+
+    def __init__(self, snap: Dict[str, np.ndarray], setup: Optional[abi.RunSetup] = None):
+        self.setup = setup or abi.setup_from_snapshot(snap)
+        self.a: Dict[str, np.ndarray] = {}
+        n = len(snap["mass"])
+        for k in _F64:
+            if k in snap:
+                self.a[k] = np.ascontiguousarray(snap[k], dtype=np.float64).copy()
+        for k in _U32:
+            if k in snap:
+                self.a[k] = np.ascontiguousarray(snap[k], dtype=np.uint32).copy()
+        if "ncnt" not in self.a:
+            self.a["ncnt"] = np.zeros(n, np.uint32)
+        if "flag" not in self.a:
+            self.a["flag"] = np.zeros(n, np.uint32)
+        if "divv" not in self.a:
+            self.a["divv"] = np.zeros(n)
+        if self.setup.solid:
+            self.a.setdefault("gradv", np.zeros((n, 6)))
+            self.a.setdefault("corr", np.tile(np.array([1., 1., 1., 0., 0., 0.]), (n, 1)))
+        for pk, k in _PRED.items():
+            if k in self.a:
+                self.a[pk] = np.zeros_like(self.a[k])
+        self.n = n
+        self.state = OrcState()
+        self.state.n = n
+        for name, _ in OrcState._fields_[2:]:
+            arr = self.a.get(name)
+            if arr is None:
+                setattr(self.state, name, None)
+            elif arr.dtype == np.uint32:
+                setattr(self.state, name, arr.ctypes.data_as(_U))
+            else:
+                setattr(self.state, name, arr.ctypes.data_as(_D))
+        self.last_dt = C.c_double(0.0)
+
+    def _args(self):
+        return C.byref(self.state), C.byref(self.setup.cfg), self.setup.materials, C.c_uint32(self.setup.n_materials)
+
+    def integrate(self) -> None:
+        lib().orc_integrate(*self._args())
+
+    def predict(self, dt: float) -> None:
+        lib().orc_predict(*self._args(), C.c_double(dt))
+
+    def correct(self, dt: float) -> None:
+        lib().orc_correct(*self._args(), C.c_double(dt))
+
+    def euler(self, dt: float) -> None:
+        lib().orc_euler(*self._args(), C.c_double(dt))
+
+    def timestep(self, max_dt: float):
+        crit = C.c_uint32(0)
+        dt = lib().orc_timestep(*self._args(), C.c_double(max_dt), C.byref(self.last_dt), C.byref(crit))
+        return float(dt), int(crit.value)
+
+    def step_pc(self, dt: float, max_dt: float):
+        """ITimeStepping::step with PredictorCorrector (core/timestepping/TimeStepping.cpp:34-75,324-346)."""
+        self.predict(dt)
+        self.integrate()
+        self.correct(dt)
+        return self.timestep(max_dt)
+
+    def step_euler(self, dt: float, max_dt: float):
+        self.integrate()
+        self.euler(dt)
+        return self.timestep(max_dt)
+
+    def neighbours(self):
+        off = np.zeros(self.n + 1, np.uint64)
+        total = lib().orc_find_neighbours(C.byref(self.state), C.byref(self.setup.cfg),
+                                          off.ctypes.data_as(C.POINTER(C.c_uint64)), None, C.c_uint64(0))
+        idx = np.zeros(int(total), np.uint32)
+        lib().orc_find_neighbours(C.byref(self.state), C.byref(self.setup.cfg),
+                                  off.ctypes.data_as(C.POINTER(C.c_uint64)), idx.ctypes.data_as(_U), C.c_uint64(int(total)))
+        return off, idx
+
+
+def build_lut(entries: int = 40000, radius: float = 2.0):
+    grad = np.zeros(entries + 1)
+    val = np.zeros(entries + 1)
+    lib().orc_build_lut(grad.ctypes.data_as(_D), val.ctypes.data_as(_D), C.c_uint32(entries), C.c_double(radius))
+    return grad, val
