@@ -28,6 +28,12 @@ extern "C" {
 
 #define SPHGPU_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define SPHGPU_API __attribute__((visibility("default")))
+#else
+#define SPHGPU_API
+#endif
+
 /* ---- status codes ------------------------------------------------------------------------------------- */
 enum {
     SPHGPU_OK = 0,
@@ -90,7 +96,9 @@ enum {
     SPHGPU_Q_N_FLAWS = 15,            /* u32                                                                 */
     SPHGPU_Q_FLAG = 16,               /* u32  body index                                                     */
     SPHGPU_Q_NEIGHBOR_CNT = 17,       /* u32                                                                 */
-    SPHGPU_Q_COUNT = 18
+    SPHGPU_Q_MATERIAL_ID = 18,        /* u32  index into the materials passed to sphgpu_create; initialised from
+                                         their [begin,end) ranges, must be uploaded for ghost particles      */
+    SPHGPU_Q_COUNT = 19
 };
 
 /* Host memory layouts understood by upload/download. */
@@ -170,23 +178,23 @@ typedef struct sphgpu_ctx sphgpu_ctx;
 
 /* Replaces AsymmetricSolver::AsymmetricSolver + Factory::getKernel/getFinder (AsymmetricSolver.cpp:58-69,124-136).
  * `capacity` >= n_particles reserves room for ghost (halo) particles appended after the owned ones. */
-int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, uint32_t n_materials,
+SPHGPU_API int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, uint32_t n_materials,
     uint32_t n_particles, uint32_t capacity, int device, sphgpu_ctx** out);
-int sphgpu_destroy(sphgpu_ctx* ctx);
-const char* sphgpu_last_error(void);
-uint32_t sphgpu_abi_version(void);
+SPHGPU_API int sphgpu_destroy(sphgpu_ctx* ctx);
+SPHGPU_API const char* sphgpu_last_error(void);
+SPHGPU_API uint32_t sphgpu_abi_version(void);
 
 /* ---- state transfer (replaces Storage::getValue/getDt/getD2t array access, core/quantities/Storage.h:291-608) */
 
 /* Copies `count` particles starting at particle index `first` of quantity `q`/`order` between host memory in
  * `layout` and the device-resident SoA mirror. */
-int sphgpu_upload(sphgpu_ctx* ctx, int q, int order, int layout, const void* host, uint32_t first, uint32_t count);
-int sphgpu_download(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count);
+SPHGPU_API int sphgpu_upload(sphgpu_ctx* ctx, int q, int order, int layout, const void* host, uint32_t first, uint32_t count);
+SPHGPU_API int sphgpu_download(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count);
 /* Same, PACKED layout only, with a DEVICE pointer on the context's device (used by the multi-GPU halo plumbing). */
-int sphgpu_upload_device(sphgpu_ctx* ctx, int q, int order, const void* dev, uint32_t first, uint32_t count);
-int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_t first, uint32_t count);
+SPHGPU_API int sphgpu_upload_device(sphgpu_ctx* ctx, int q, int order, const void* dev, uint32_t first, uint32_t count);
+SPHGPU_API int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_t first, uint32_t count);
 /* Number of particles that take part as neighbours: owned + ghosts (ghosts occupy [n_particles, n_active)). */
-int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
+SPHGPU_API int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
 
 /* ---- the hot path --------------------------------------------------------------------------------------- */
 
@@ -194,30 +202,37 @@ int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
  * equations.initialize (h clamp), finder build + findAll, derivatives.eval over all pairs, accumulated.store,
  * equations.finalize, material->finalize (damage growth). Highest derivatives are OVERWRITTEN, i.e. the call
  * behaves as the reference does after Storage::zeroHighestDerivatives (TimeStepping.cpp:238,334). */
-int sphgpu_integrate(sphgpu_ctx* ctx, double t, sphgpu_stats* stats);
+SPHGPU_API int sphgpu_integrate(sphgpu_ctx* ctx, double t, sphgpu_stats* stats);
 
 /* Replaces PredictorCorrector::makePredictions + swap + zeroHighestDerivatives (TimeStepping.cpp:286-300,331-334). */
-int sphgpu_step_predict(sphgpu_ctx* ctx, double dt);
+SPHGPU_API int sphgpu_step_predict(sphgpu_ctx* ctx, double dt);
 /* Replaces PredictorCorrector::makeCorrections (TimeStepping.cpp:302-322). */
-int sphgpu_step_correct(sphgpu_ctx* ctx, double dt);
+SPHGPU_API int sphgpu_step_correct(sphgpu_ctx* ctx, double dt);
 /* Replaces EulerExplicit::stepParticles after solver.integrate (TimeStepping.cpp:243-264). */
-int sphgpu_step_euler(sphgpu_ctx* ctx, double dt);
+SPHGPU_API int sphgpu_step_euler(sphgpu_ctx* ctx, double dt);
 /* Replaces MultiCriterion::compute (TimeStepCriterion.cpp:389-419). */
-int sphgpu_compute_timestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out);
+SPHGPU_API int sphgpu_compute_timestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out);
+/* Seeds MultiCriterion::lastStep (TimeStepCriterion.cpp:387) used when max_change limits the growth of dt. */
+SPHGPU_API int sphgpu_set_last_timestep(sphgpu_ctx* ctx, double dt);
 /* One whole PredictorCorrector step on the device (ITimeStepping::step, TimeStepping.cpp:34-75):
  * predict(dt) -> integrate -> correct(dt) -> criteria. No host<->device traffic except the returned scalars. */
-int sphgpu_step_pc(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
+SPHGPU_API int sphgpu_step_pc(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
 
 /* ---- inspection (tests) --------------------------------------------------------------------------------- */
 
 /* Neighbour lists exactly as AsymmetricSolver::loop selects them (AsymmetricSolver.cpp:174-199), CSR:
  * offsets[n_particles+1], indices ascending per particle. Pass idx == NULL to obtain only offsets. */
-int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_t* idx, uint64_t idx_capacity);
+SPHGPU_API int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_t* idx, uint64_t idx_capacity);
 /* Device-time breakdown of the last integrate call in milliseconds: [0] grid build + sort, [1] prologue + pack,
  * [2] pair kernel, [3] rest. */
-int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4);
-/* Selects the pair-kernel variant (0 = default). For A/B measurements only. */
-int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
+SPHGPU_API int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4);
+/* Selects the pair-kernel variant (0 = default tiled kernel, 1 = direct per-thread kernel). For A/B checks only. */
+SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
+/* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*), so that
+ * the caller can bracket calls with its own events (e.g. torch.cuda.Event). NULL restores the private stream. */
+SPHGPU_API int sphgpu_set_stream(sphgpu_ctx* ctx, void* cuda_stream);
+/* Blocks until all work queued on the context's stream has finished. */
+SPHGPU_API int sphgpu_synchronize(sphgpu_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ QUANTITIES: Dict[str, Tuple[int, int, type]] = {
     "N_FLAWS": (15, 1, np.uint32),
     "FLAG": (16, 1, np.uint32),
     "NEIGHBOR_CNT": (17, 1, np.uint32),
+    "MATERIAL_ID": (18, 1, np.uint32),
 }
 
 # snapshot array name -> (quantity, order)
@@ -125,8 +126,12 @@ def _clip_inf(x: float) -> float:
     return float(x)
 
 
-def setup_from_snapshot(snap: Dict[str, np.ndarray]) -> RunSetup:
-    """Builds the engine configuration from the constants the reference driver stored (oracle/ref_driver.cpp:dumpState)."""
+def setup_from_snapshot(snap: Dict[str, np.ndarray], lut: Dict[str, np.ndarray] = None) -> RunSetup:
+    """Builds the engine configuration from the constants the reference driver stored (oracle/ref_driver.cpp:dumpState).
+
+    `lut` supplies lut_grad / lut_val when the snapshot was written without the kernel tables."""
+    if lut is None:
+        lut = snap
     rp = snap["run_params"]
     cfg = Config()
     cfg.abi_version = ABI_VERSION
@@ -155,7 +160,7 @@ def setup_from_snapshot(snap: Dict[str, np.ndarray]) -> RunSetup:
         if m.yielding == YIELD_NONE:
             m.fracture = FRACTURE_NONE  # Factory::getMaterial: no rheology => EosMaterial (core/system/Factory.cpp:544-564)
         mats.append(m)
-    return RunSetup(cfg, mats, snap["lut_grad"], snap["lut_val"])
+    return RunSetup(cfg, mats, lut["lut_grad"], lut["lut_val"])
 
 
 def run_constants(snap: Dict[str, np.ndarray]) -> Dict[str, float]:

@@ -1,0 +1,310 @@
+// Cell-list build: bounds reduction -> grid parameters (on device, no host round trip) -> cell histogram ->
+// exclusive scan -> scatter -> per-cell ordering. Replaces the finder build of the reference
+// (ISymmetricFinder::build, core/objects/finders/NeighborFinder.cpp:7-26; KdTree::buildImpl,
+// core/objects/finders/KdTree.inl.h:10-41; LookupMap::update, core/objects/containers/LookupMap.h:31-45) and
+// IAsymmetricSolver::getMaxSearchRadius (core/sph/solvers/AsymmetricSolver.cpp:104-111).
+//
+// The cell edge is R * h_max (x 1+1e-6), so every neighbour j of i (|r_i - r_j| < R (h_i + h_j)/2 <= R h_max)
+// lies in the 3x3x3 block of cells around i. If that would need more than maxCells cells the edge is enlarged,
+// like the reference's UniformGridFinder caps its grid at (cbrt(N)+1)^3 cells (UniformGrid.cpp:16).
+#include "sphgpu_internal.h"
+
+namespace sph {
+
+__device__ __forceinline__ double warpMin(double v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+__device__ __forceinline__ double warpMax(double v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+
+// AdaptiveSmoothingLength::initialize (h clamp, EquationTerm.cpp:356-364) fused with the bounding-box / h_max pass.
+__global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax) {
+    double lo[3] = { INFTY_REF, INFTY_REF, INFTY_REF }, hi[3] = { -INFTY_REF, -INFTY_REF, -INFTY_REF }, hm = 0.;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nActive; i += gridDim.x * blockDim.x) {
+        double h = d.f[F_H][i];
+        if (clampH) {
+            const double hc = fmax(hMin, fmin(h, hMax));
+            if (hc != h) {
+                d.f[F_H][i] = hc;
+            }
+            h = hc;
+        }
+        const double x = d.f[F_X][i], y = d.f[F_Y][i], z = d.f[F_Z][i];
+        lo[0] = fmin(lo[0], x);
+        lo[1] = fmin(lo[1], y);
+        lo[2] = fmin(lo[2], z);
+        hi[0] = fmax(hi[0], x);
+        hi[1] = fmax(hi[1], y);
+        hi[2] = fmax(hi[2], z);
+        hm = fmax(hm, h);
+    }
+    __shared__ double sm[8][7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[7] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm) };
+    if (lane == 0) {
+        for (int k = 0; k < 7; ++k) {
+            sm[warp][k] = v[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int k = threadIdx.x;
+        double r = sm[0][k];
+        for (int w = 1; w < 8; ++w) {
+            r = (k < 3) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
+        }
+        d.boundsPartial[blockIdx.x * 8 + k] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPartials, double kernelRadius, uint32_t maxCells) {
+    __shared__ double sm[8][7];
+    double v[7] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0. };
+    for (int b = threadIdx.x; b < nPartials; b += blockDim.x) {
+        for (int k = 0; k < 7; ++k) {
+            const double p = d.boundsPartial[b * 8 + k];
+            v[k] = (k < 3) ? fmin(v[k], p) : fmax(v[k], p);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 7; ++k) {
+        v[k] = (k < 3) ? warpMin(v[k]) : warpMax(v[k]);
+    }
+    if (lane == 0) {
+        for (int k = 0; k < 7; ++k) {
+            sm[warp][k] = v[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 7; ++k) {
+            double r = sm[0][k];
+            for (int w = 1; w < 8; ++w) {
+                r = (k < 3) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
+            }
+            v[k] = r;
+        }
+        GridDev g;
+        g.hmax = v[6];
+        double cell = kernelRadius * v[6] * (1. + 1.e-6);
+        if (!(cell > 0.)) {
+            cell = 1.;
+        }
+        double ext[3];
+        for (int k = 0; k < 3; ++k) {
+            g.lo[k] = v[k];
+            ext[k] = fmax(v[3 + k] - v[k], 0.);
+        }
+        for (int iter = 0; iter < 64; ++iter) {
+            double total = 1.;
+            for (int k = 0; k < 3; ++k) {
+                total *= floor(ext[k] / cell) + 1.;
+            }
+            if (total <= (double)maxCells) {
+                break;
+            }
+            cell *= fmax(cbrt(total / (double)maxCells), 1.0) * 1.02;
+        }
+        g.cell = cell;
+        g.cellInv = 1. / cell;
+        uint32_t n = 1;
+        for (int k = 0; k < 3; ++k) {
+            g.dim[k] = (int)floor(ext[k] / cell) + 1;
+            n *= (uint32_t)g.dim[k];
+        }
+        g.ncells = n;
+        *d.grid = g;
+    }
+}
+
+__device__ __forceinline__ uint32_t cellIndex(const GridDev& g, double x, double y, double z) {
+    int cx = (int)floor((x - g.lo[0]) * g.cellInv);
+    int cy = (int)floor((y - g.lo[1]) * g.cellInv);
+    int cz = (int)floor((z - g.lo[2]) * g.cellInv);
+    cx = min(max(cx, 0), g.dim[0] - 1);
+    cy = min(max(cy, 0), g.dim[1] - 1);
+    cz = min(max(cz, 0), g.dim[2] - 1);
+    return (uint32_t)((cz * g.dim[1] + cy) * g.dim[0] + cx);
+}
+
+__global__ void __launch_bounds__(256) k_cell_count(DevicePointers d, uint32_t nActive) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nActive) {
+        return;
+    }
+    const GridDev g = *d.grid;
+    const uint32_t c = cellIndex(g, d.f[F_X][i], d.f[F_Y][i], d.f[F_Z][i]);
+    d.cellOf[i] = c;
+    d.rank[i] = atomicAdd(&d.cellCount[c], 1u);
+}
+
+// ---- exclusive scan of cellCount[0..total) into cellStart, three passes -----------------------------------
+__global__ void __launch_bounds__(512) k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+    uint32_t* __restrict__ blockSums, uint32_t total) {
+    // each thread owns 8 consecutive items
+    __shared__ uint32_t warpSums[16];
+    const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
+    uint32_t v[8];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = (base + k < total) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) {
+            incl += t;
+        }
+    }
+    if (lane == 31) {
+        warpSums[warp] = incl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < 16) ? warpSums[lane] : 0u;
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) {
+                w += t;
+            }
+        }
+        if (lane < 16) {
+            warpSums[lane] = w; // inclusive over warps
+        }
+    }
+    __syncthreads();
+    uint32_t excl = incl - sum + (warp > 0 ? warpSums[warp - 1] : 0u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < total) {
+            out[base + k] = excl;
+        }
+        excl += v[k];
+    }
+    if (threadIdx.x == 511) {
+        blockSums[blockIdx.x] = warpSums[15];
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* blockSums, uint32_t nBlocks) {
+    // single block, sequential over chunks of 1024
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) {
+        carry = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nBlocks; base += 1024) {
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t val = idx < nBlocks ? blockSums[idx] : 0u;
+        uint32_t incl = val;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) {
+                incl += t;
+            }
+        }
+        if (lane == 31) {
+            warpSums[warp] = incl;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warpSums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) {
+                    w += t;
+                }
+            }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t excl = incl - val + (warp > 0 ? warpSums[warp - 1] : 0u) + carry;
+        if (idx < nBlocks) {
+            blockSums[idx] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry = excl + val;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(512) k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ blockSums, uint32_t total) {
+    const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
+    const uint32_t add = blockSums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < total) {
+            out[base + k] += add;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter(DevicePointers d, uint32_t nActive) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nActive) {
+        return;
+    }
+    d.order[d.cellStart[d.cellOf[i]] + d.rank[i]] = i;
+}
+
+// The histogram ranks come from atomics and are not reproducible; order every cell by slot index so that the
+// summation order (and therefore every bit of the result) is the same from run to run.
+__global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t maxCells) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= maxCells || c >= d.grid->ncells) {
+        return;
+    }
+    const uint32_t s = d.cellStart[c], e = d.cellStart[c + 1];
+    if (e - s < 2 || e - s > 4096) {
+        return;
+    }
+    for (uint32_t a = s + 1; a < e; ++a) {
+        const uint32_t key = d.order[a];
+        uint32_t b = a;
+        while (b > s && d.order[b - 1] > key) {
+            d.order[b] = d.order[b - 1];
+            --b;
+        }
+        d.order[b] = key;
+    }
+}
+
+int launchGridBuild(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->nActive;
+    cudaStream_t st = ctx->stream;
+    const bool clampH = (ctx->prm.flags & SPHGPU_FLAG_ADAPTIVE_H) != 0;
+    k_bounds<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n, clampH, ctx->prm.h_min, ctx->prm.h_max);
+    k_grid_params<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, ctx->prm.kernel_radius, ctx->maxCells);
+    SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.cellCount, 0, sizeof(uint32_t) * (ctx->maxCells + 1), st));
+    const uint32_t blocks = (n + 255) / 256;
+    if (blocks > 0) {
+        k_cell_count<<<blocks, 256, 0, st>>>(ctx->d, n);
+    }
+    const uint32_t total = ctx->maxCells + 1;
+    k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.cellStart, ctx->d.scanBlock, total);
+    k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks);
+    k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellStart, ctx->d.scanBlock, total);
+    if (blocks > 0) {
+        k_scatter<<<blocks, 256, 0, st>>>(ctx->d, n);
+    }
+    k_sort_cells<<<(ctx->maxCells + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
+    ctx->launches += 8;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+} // namespace sph

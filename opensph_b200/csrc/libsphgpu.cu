@@ -1,0 +1,8 @@
+// Single translation unit of libsphgpu.so: the kernels share __constant__ run/material parameters, so the sources
+// are compiled together (no relocatable device code needed).
+#include "api.cu"
+#include "grid.cu"
+#include "pair.cu"
+#include "pair_tiled.cu"
+#include "stepping.cu"
+#include "transfer.cu"

@@ -1,0 +1,339 @@
+// The fused neighbour-search + pair-sum kernels. Replaces the hot loop of the reference
+// (AsymmetricSolver::loop functor, core/sph/solvers/AsymmetricSolver.cpp:174-201: finder.findAll, the neighbour
+// filter, kernel.grad, derivatives.eval) together with material->initialize (AsymmetricSolver.cpp:75-79),
+// accumulated.store + equations.finalize (:204-216) and material->finalize (:90-95).
+#include "sphgpu_internal.h"
+
+namespace sph {
+
+__constant__ ParamsDev c_prm;
+__constant__ MaterialDev c_mats[MAX_MATERIALS];
+
+int uploadConstants(const sphgpu_ctx* ctx) {
+    SPH_CUDA_CHECK(cudaMemcpyToSymbol(c_prm, &ctx->prm, sizeof(ParamsDev)));
+    SPH_CUDA_CHECK(cudaMemcpyToSymbol(c_mats, ctx->matsHost, sizeof(MaterialDev) * MAX_MATERIALS));
+    return SPHGPU_OK;
+}
+
+// ---- prologue: EoS + rheology + damage growth, and packing of the sorted neighbour-input planes -----------
+// One thread per SORTED position t; slot i = order[t]. Reads the slot state once, writes p, cs, reduce, yielded S
+// and dD/dt back to the slot planes and the neighbour inputs (with p/rho^2, S/rho^2, m/rho precomputed) to the
+// sorted planes.
+template <bool SOLID>
+__global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_t nActive, uint32_t nOwned, bool hasReduce,
+    bool hasDamage) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nActive) {
+        return;
+    }
+    const uint32_t i = d.order[t];
+    const MaterialDev& mat = c_mats[d.u[U_MATID][i]];
+    const double rho = d.f[F_RHO][i], u = d.f[F_U][i];
+    double p = d.f[F_P][i], cs = d.f[F_CS][i];
+    evalEos(mat, rho, u, p, cs);
+    double S[5] = { 0., 0., 0., 0., 0. };
+    double reduce = 1.;
+    if (SOLID) {
+        for (int k = 0; k < 5; ++k) {
+            S[k] = d.f[F_S0 + k][i];
+        }
+    }
+    if (hasReduce) {
+        reduce = d.f[F_REDUCE][i];
+    }
+    if (mat.yielding == SPHGPU_YIELD_VON_MISES) {
+        const bool dmg = hasDamage && mat.fracture != SPHGPU_FRACTURE_NONE;
+        const double D = dmg ? d.f[F_D][i] : 0.;
+        reduce = vonMises(mat, u, D, dmg, p, S);
+        d.f[F_REDUCE][i] = reduce;
+        if (SOLID) {
+            for (int k = 0; k < 5; ++k) {
+                d.f[F_S0 + k][i] = S[k];
+            }
+        }
+        if (dmg && mat.fracture == SPHGPU_FRACTURE_SCALAR_GRADY_KIPP && i < nOwned) {
+            d.f[F_DD][i] = damageRate(mat, p, S, D, d.f[F_EPSMIN][i], d.f[F_MZERO][i], d.f[F_GROWTH][i], d.u[U_NFLAWS][i]);
+        }
+    }
+    d.f[F_P][i] = p;
+    d.f[F_CS][i] = cs;
+
+    const double rhoInv2 = 1. / (rho * rho);
+    const double m = d.f[F_M][i];
+    d.s[S_X][t] = d.f[F_X][i];
+    d.s[S_Y][t] = d.f[F_Y][i];
+    d.s[S_Z][t] = d.f[F_Z][i];
+    d.s[S_H][t] = d.f[F_H][i];
+    d.s[S_VX][t] = d.f[F_VX][i];
+    d.s[S_VY][t] = d.f[F_VY][i];
+    d.s[S_VZ][t] = d.f[F_VZ][i];
+    d.s[S_M][t] = m;
+    d.s[S_RHO][t] = rho;
+    d.s[S_P][t] = p * rhoInv2;
+    d.s[S_CS][t] = cs;
+    if (SOLID) {
+        d.s[S_VOL][t] = m / rho;
+        for (int k = 0; k < 5; ++k) {
+            d.s[S_S0 + k][t] = S[k] * rhoInv2;
+        }
+        d.sGrp[t] = (hasReduce && reduce == 0.) ? -1 : (int)d.u[U_FLAG][i];
+    }
+    d.sCell[t] = d.cellOf[i];
+}
+
+// Sorted positions only (neighbour-list inspection; does not touch the particle state).
+__global__ void __launch_bounds__(256) k_pack_positions(DevicePointers d, uint32_t nActive) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nActive) {
+        return;
+    }
+    const uint32_t i = d.order[t];
+    d.s[S_X][t] = d.f[F_X][i];
+    d.s[S_Y][t] = d.f[F_Y][i];
+    d.s[S_Z][t] = d.f[F_Z][i];
+    d.s[S_H][t] = d.f[F_H][i];
+    d.sCell[t] = d.cellOf[i];
+}
+
+template <bool SOLID>
+__device__ __forceinline__ void loadSorted(const DevicePointers& d, uint32_t t, Particle& p) {
+    p.x = d.s[S_X][t];
+    p.y = d.s[S_Y][t];
+    p.z = d.s[S_Z][t];
+    p.h = d.s[S_H][t];
+    p.vx = d.s[S_VX][t];
+    p.vy = d.s[S_VY][t];
+    p.vz = d.s[S_VZ][t];
+    p.m = d.s[S_M][t];
+    p.rho = d.s[S_RHO][t];
+    p.P = d.s[S_P][t];
+    p.cs = d.s[S_CS][t];
+    if (SOLID) {
+        p.vol = d.s[S_VOL][t];
+        for (int k = 0; k < 5; ++k) {
+            p.Sr[k] = d.s[S_S0 + k][t];
+        }
+        p.grp = d.sGrp[t];
+    } else {
+        p.vol = 0.;
+        p.grp = 0;
+    }
+}
+
+template <bool SOLID, bool CORRECTED>
+__device__ __forceinline__ void storeDerivs(const DevicePointers& d, uint32_t i, const Derivs& o) {
+    d.f[F_AX][i] = o.ax;
+    d.f[F_AY][i] = o.ay;
+    d.f[F_AZ][i] = o.az;
+    d.f[F_VH][i] = o.vh;
+    d.f[F_DU][i] = o.du;
+    d.f[F_DRHO][i] = o.drho;
+    d.f[F_DIVV][i] = o.divv;
+    d.u[U_NCNT][i] = o.ncnt;
+    if (SOLID) {
+        for (int k = 0; k < 5; ++k) {
+            d.f[F_DS0 + k][i] = o.dS[k];
+        }
+        for (int k = 0; k < 6; ++k) {
+            d.f[F_GV0 + k][i] = o.gradv[k];
+        }
+        if (CORRECTED) {
+            for (int k = 0; k < 6; ++k) {
+                d.f[F_C0 + k][i] = o.corr[k];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void neighbourStats(const DevicePointers& d, uint32_t cnt, bool valid) {
+    // warp-aggregated min / max / sum of NEIGHBOR_CNT (AsymmetricSolver.cpp:218-225)
+    const unsigned mask = __activemask();
+    uint32_t mn = valid ? cnt : 0xffffffffu, mx = valid ? cnt : 0u, sm = valid ? cnt : 0u;
+    mn = __reduce_min_sync(mask, mn);
+    mx = __reduce_max_sync(mask, mx);
+    sm = __reduce_add_sync(mask, sm);
+    if ((threadIdx.x & 31) == (__ffs(mask) - 1)) {
+        atomicMin(&d.stats->neighMin, mn);
+        atomicMax(&d.stats->neighMax, mx);
+        atomicAdd(&d.stats->pairCount, (unsigned long long)sm);
+    }
+}
+
+// ---- variant 1: one thread per target, candidates streamed from the sorted planes through L1 -----------------
+// Simple and obviously correct; kept as the cross-check for the tiled variants.
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__global__ void __launch_bounds__(128) k_pair_direct(DevicePointers d, uint32_t nActive, uint32_t nOwned) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < nActive;
+    const uint32_t i = live ? d.order[t] : 0xffffffffu;
+    const bool target = live && i < nOwned; // ghosts are neighbours only
+    Accum acc;
+    accumZero(acc);
+    if (target) {
+        const GridDev g = *d.grid;
+        Particle pi;
+        loadSorted<SOLID>(d, t, pi);
+        const uint32_t c = d.sCell[t];
+        const int cx = (int)(c % (uint32_t)g.dim[0]);
+        const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+        const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+                const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
+                for (uint32_t k = s; k < e; ++k) {
+                    if (k == t) {
+                        continue;
+                    }
+                    const double dx = pi.x - d.s[S_X][k], dy = pi.y - d.s[S_Y][k], dz = pi.z - d.s[S_Z][k];
+                    double d2, hbar;
+                    if (!isNeighbour(dx, dy, dz, pi.h, d.s[S_H][k], c_prm.kernel_radius, d2, hbar)) {
+                        continue;
+                    }
+                    Particle pj;
+                    loadSorted<SOLID>(d, k, pj);
+                    pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+                }
+            }
+        }
+        const MaterialDev& mat = c_mats[d.u[U_MATID][i]];
+        double S[5] = { 0., 0., 0., 0., 0. };
+        if (SOLID) {
+            for (int k = 0; k < 5; ++k) {
+                S[k] = d.f[F_S0 + k][i];
+            }
+        }
+        Derivs out;
+        finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][i], pi.cs, SOLID ? d.f[F_REDUCE][i] : 1., S, out);
+        storeDerivs<SOLID, CORRECTED>(d, i, out);
+    }
+    neighbourStats(d, acc.cnt, target);
+}
+
+// ---- neighbour lists for the tests ---------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint32_t nActive, uint32_t nOwned, uint32_t* counts,
+    const unsigned long long* offsets, uint32_t* idx) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nActive) {
+        return;
+    }
+    const uint32_t i = d.order[t];
+    if (i >= nOwned) {
+        return;
+    }
+    const GridDev g = *d.grid;
+    const double xi = d.s[S_X][t], yi = d.s[S_Y][t], zi = d.s[S_Z][t], hi = d.s[S_H][t];
+    const uint32_t c = d.sCell[t];
+    const int cx = (int)(c % (uint32_t)g.dim[0]);
+    const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+    const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    uint32_t cnt = 0;
+    const unsigned long long base = FILL ? offsets[i] : 0ull;
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+            const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+            const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
+            for (uint32_t k = s; k < e; ++k) {
+                if (k == t) {
+                    continue;
+                }
+                double d2, hbar;
+                if (!isNeighbour(xi - d.s[S_X][k], yi - d.s[S_Y][k], zi - d.s[S_Z][k], hi, d.s[S_H][k], c_prm.kernel_radius, d2, hbar)) {
+                    continue;
+                }
+                if (FILL) {
+                    idx[base + cnt] = d.order[k];
+                }
+                cnt++;
+            }
+        }
+    }
+    if (!FILL) {
+        counts[i] = cnt;
+    }
+}
+
+int launchProloguePack(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->nActive;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = (n + 255) / 256;
+    if (ctx->solid) {
+        k_prologue_pack<true><<<blocks, 256, 0, ctx->stream>>>(ctx->d, n, ctx->n, ctx->hasReduce, ctx->hasDamage);
+    } else {
+        k_prologue_pack<false><<<blocks, 256, 0, ctx->stream>>>(ctx->d, n, ctx->n, ctx->hasReduce, ctx->hasDamage);
+    }
+    ctx->launches += 1;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchProloguePackPositionsOnly(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->nActive;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    k_pack_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchPairTiled(sphgpu_ctx* ctx); // pair_tiled.cu
+
+int launchPair(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->nActive;
+    const StatsDev init = { 0xffffffffu, 0u, 0ull };
+    SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->d.stats, &init, sizeof(StatsDev), cudaMemcpyHostToDevice, ctx->stream));
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    if (ctx->variant != 1) {
+        return launchPairTiled(ctx);
+    }
+    const uint32_t blocks = (n + 127) / 128;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->solid) {
+        k_pair_direct<false, false, false><<<blocks, 128, 0, st>>>(ctx->d, n, ctx->n);
+    } else if (ctx->corrected) {
+        if (ctx->filter) {
+            k_pair_direct<true, true, true><<<blocks, 128, 0, st>>>(ctx->d, n, ctx->n);
+        } else {
+            k_pair_direct<true, true, false><<<blocks, 128, 0, st>>>(ctx->d, n, ctx->n);
+        }
+    } else {
+        if (ctx->filter) {
+            k_pair_direct<true, false, true><<<blocks, 128, 0, st>>>(ctx->d, n, ctx->n);
+        } else {
+            k_pair_direct<true, false, false><<<blocks, 128, 0, st>>>(ctx->d, n, ctx->n);
+        }
+    }
+    ctx->launches += 1;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchNeighbourCount(sphgpu_ctx* ctx, uint32_t* countsDev) {
+    const uint32_t n = ctx->nActive;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    k_neighbour_lists<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, countsDev, nullptr, nullptr);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, uint32_t* idxDev) {
+    const uint32_t n = ctx->nActive;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    k_neighbour_lists<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, nullptr, offsetsDev, idxDev);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+} // namespace sph

@@ -1,0 +1,455 @@
+// Per-particle and per-pair arithmetic of the SPH hot path, shared by every kernel variant.
+// All functions are __host__ __device__ so that tests/csrc/host_math_check.cu can run the very same code on the
+// CPU against the oracle (a compile-time check of the formulas, NOT a product path).
+//
+// Reference formulas (paths relative to the reference root):
+//   kernel gradient      core/sph/kernel/Kernel.h:32-36,129-144,640-643
+//   VelocityDivergence   core/sph/equations/DerivativeHelpers.h:292-304,355-371
+//   VelocityGradient     core/sph/equations/DerivativeHelpers.h:100-146,382-398
+//   CorrectionTensor     core/sph/equations/Derivative.cpp:36-74
+//   PressureGradient     core/sph/equations/EquationTerm.cpp:12-24,41-67
+//   StressDivergence     core/sph/equations/EquationTerm.cpp:113-140
+//   StandardAV           core/sph/equations/av/Standard.h:63-83
+//   finalizers           core/sph/equations/EquationTerm.cpp:90-99,177-203,289-316,366-434
+//   Tillotson / ideal gas core/physics/Eos.cpp:42-45,198-238
+//   von Mises            core/physics/Rheology.cpp:36-83
+//   Grady-Kipp           core/physics/Damage.cpp:128-170, core/objects/geometry/SymmetricTensor.h:377-399
+#pragma once
+#include "../../include/sphgpu.h"
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define SPH_HD __host__ __device__ __forceinline__
+#else
+#define SPH_HD inline
+#endif
+
+namespace sph {
+
+constexpr double EPS_REF = (double)1.e-12f;  // math/MathUtils.h:26-30 (float literal)
+constexpr double LARGE_REF = (double)1.e20f; // math/MathUtils.h:33
+constexpr double INFTY_REF = 1.7976931348623157e308;
+
+/// Per-material constants in the form the kernels consume.
+struct MaterialDev {
+    uint32_t eos, yielding, fracture, pad;
+    double til_u0, til_uiv, til_ucv, til_a, til_b, rho0, til_A, til_B, til_alpha, til_beta, gamma;
+    double shear_modulus, elasticity_limit, melt_energy, young_modulus;
+    double rho_min, rho_max, u_min, u_max, d_min, d_max;
+    double rho_small, u_small, d_small, s_small;
+};
+
+constexpr int MAX_MATERIALS = 32;
+
+/// Run-level constants.
+struct ParamsDev {
+    uint32_t forces, flags, continuity_mode, lut_entries;
+    double kernel_radius, radius_sqr, q_sqr_to_idx;
+    double av_alpha, av_beta;
+    double h_min, h_max, neigh_enforcing, neigh_lower, neigh_upper;
+    uint32_t criteria, n_materials;
+    double courant, derivative_factor, divergence_factor;
+};
+
+SPH_HD double sqr(double x) {
+    return x * x;
+}
+
+// ---- equation of state ---------------------------------------------------------------------------------
+
+SPH_HD void eosTillotson(const MaterialDev& m, double rho, double u, double& pOut, double& csOut) {
+    const double eta = rho / m.rho0;
+    const double mu = eta - 1.;
+    const double denom = u / (m.til_u0 * eta * eta) + 1.;
+    const double denom2 = sqr(denom);
+    const double rho2 = rho * rho;
+    // compressed phase
+    const double pc = (m.til_a + m.til_b / denom) * rho * u + m.til_A * mu + m.til_B * mu * mu;
+    double dpdu = m.til_a * rho + m.til_b * rho / denom2;
+    double dpdrho = m.til_a * u + m.til_b * u * (3. * denom - 2.) / denom2 + m.til_A / m.rho0 + 2. * m.til_B * mu / m.rho0;
+    const double csc = dpdrho + dpdu * pc / rho2;
+    // expanded phase
+    const double rhoExp = m.rho0 / rho - 1.;
+    const double betaExp = exp(-fmin(m.til_beta * rhoExp, 70.));
+    const double alphaExp = exp(-fmin(m.til_alpha * sqr(rhoExp), 70.));
+    const double pe = m.til_a * rho * u + (m.til_b * rho * u / denom + m.til_A * mu * betaExp) * alphaExp;
+    dpdu = m.til_a * rho + alphaExp * m.til_b * rho / denom2;
+    dpdrho = m.til_a * u + alphaExp * (m.til_b * u * (3. * denom - 2.) / denom2) +
+             alphaExp * (m.til_b * u * rho / denom) * m.rho0 * (2. * m.til_alpha * rhoExp) / rho2 +
+             alphaExp * m.til_A * betaExp * (1. / m.rho0 + m.rho0 * mu / rho2 * (2. * m.til_alpha * rhoExp + m.til_beta));
+    double cse = dpdrho + dpdu * pe / rho2;
+    cse = fmax(cse, 0.);
+    double p = pc, cs = csc;
+    if (rho <= m.rho0 && u > m.til_ucv) {
+        p = pe;
+        cs = cse;
+    } else if (rho <= m.rho0 && u > m.til_uiv && u <= m.til_ucv) {
+        p = ((u - m.til_uiv) * pe + (m.til_ucv - u) * pc) / (m.til_ucv - m.til_uiv);
+        cs = ((u - m.til_uiv) * cse + (m.til_ucv - u) * csc) / (m.til_ucv - m.til_uiv);
+    }
+    cs = fmax(cs, 0.25 * m.til_A / m.rho0);
+    pOut = p;
+    csOut = sqrt(cs);
+}
+
+SPH_HD void evalEos(const MaterialDev& m, double rho, double u, double& p, double& cs) {
+    if (m.eos == SPHGPU_EOS_TILLOTSON) {
+        eosTillotson(m, rho, u, p, cs);
+    } else if (m.eos == SPHGPU_EOS_IDEAL_GAS) {
+        p = (m.gamma - 1.) * u * rho;
+        cs = sqrt(m.gamma * p / rho);
+    }
+}
+
+// ---- rheology + damage ---------------------------------------------------------------------------------
+
+/// VonMisesRheology::initialize for one particle. S = {xx,yy,xy,xz,yz} is scaled in place; returns the reducing factor.
+SPH_HD double vonMises(const MaterialDev& m, double u, double D, bool hasDamage, double& p, double S[5]) {
+    const double d = hasDamage ? D * D * D : 0.;
+    if (p < 0.) {
+        p = (1. - d) * p;
+    }
+    const double unorm = u / m.melt_energy;
+    double Y = unorm < 1.e-5 ? m.elasticity_limit : m.elasticity_limit * fmax(1. - unorm, 0.);
+    Y = (1. - d) * Y;
+    if (Y < EPS_REF) {
+        S[0] = S[1] = S[2] = S[3] = S[4] = 0.;
+        return 0.;
+    }
+    const double szz = -S[0] - S[1];
+    const double ddot = (S[0] * S[0] + S[1] * S[1] + szz * szz) + 2. * (S[2] * S[2] + S[3] * S[3] + S[4] * S[4]);
+    const double J2 = 0.5 * ddot + 1.e-15;
+    const double red = fmin(Y / sqrt(3. * J2), 1.);
+    for (int k = 0; k < 5; ++k) {
+        S[k] = S[k] * red;
+    }
+    return red;
+}
+
+/// sqrtApprox (math/MathUtils.h:40-62): float bit trick + one Newton iteration. Only scales the eigenvalue problem.
+SPH_HD double sqrtApproxRef(double f) {
+    if (f == 0.) {
+        return 0.;
+    }
+    float y = (float)f;
+    const float x2 = y * 0.5f;
+#ifdef __CUDA_ARCH__
+    int i = __float_as_int(y);
+    i = 0x5f3759df - (i >> 1);
+    y = __int_as_float(i);
+#else
+    int i;
+    memcpy(&i, &y, sizeof(float));
+    i = 0x5f3759df - (i >> 1);
+    memcpy(&y, &i, sizeof(float));
+#endif
+    const float r = y * (1.5f - (x2 * y * y));
+    return (double)(1.f / r);
+}
+
+/// Largest eigenvalue of the symmetric tensor t = {xx,yy,zz,xy,xz,yz} as findEigenvalues computes it.
+SPH_HD double maxEigenvalue(const double t[6]) {
+    const double v0 = fmax(t[0], t[3]), v1 = fmax(t[1], t[4]), v2 = fmax(t[2], t[5]);
+    const double n = sqrtApproxRef(v0 * v0 + v1 * v1 + v2 * v2);
+    if (n < 1.e-12) {
+        return 0.;
+    }
+    const double inv1 = t[0] + t[1] + t[2];
+    const double inv2 = (t[3] * t[3] + t[4] * t[4] + t[5] * t[5]) - (t[1] * t[2] + t[2] * t[0] + t[0] * t[1]);
+    const double inv3 = t[0] * t[1] * t[2] + 2. * t[3] * t[4] * t[5] - (t[3] * t[3] * t[2] + t[4] * t[4] * t[1] + t[5] * t[5] * t[0]);
+    const double p = -inv1 / n;
+    const double q = -inv2 / sqr(n);
+    const double r = -inv3 / (n * n * n);
+    const double a = q - p * p / 3.;
+    const double b = (2. * p * p * p - 9. * p * q + 27. * r) / 27.;
+    const double aCub = a * a * a / 27.;
+    if (0.25 * b * b + aCub >= 0.) {
+        return 0.;
+    }
+    const double t1 = 2. * sqrt(-a / 3.);
+    const double phi = acos(-0.5 * b / sqrt(-aCub));
+    const double PI = 3.14159265358979323846;
+    const double s0 = (t1 * cos(phi / 3.) - p / 3.) * n;
+    const double s1 = (t1 * cos((phi + 2 * PI) / 3.) - p / 3.) * n;
+    const double s2 = (t1 * cos((phi + 4 * PI) / 3.) - p / 3.) * n;
+    return fmax(fmax(s0, s1), s2);
+}
+
+/// ScalarGradyKippModel::integrate for one particle; returns dD/dt (0 when the flaw is not activated).
+SPH_HD double damageRate(const MaterialDev& m, double p, const double S[5], double D, double epsMin, double mZero,
+    double growth, uint32_t nFlaws) {
+    if (D >= m.d_max) {
+        return LARGE_REF;
+    }
+    const double sigma[6] = { S[0] - p, S[1] - p, (-S[0] - S[1]) - p, S[2], S[3], S[4] };
+    const double sigMax = maxEigenvalue(sigma);
+    const double youngRed = fmax((1. - D * D * D) * m.young_modulus, 1.e-20);
+    const double strain = sigMax / youngRed;
+    const double ratio = strain / epsMin;
+    if (ratio <= 1.) {
+        return 0.;
+    }
+    return growth * cbrt(fmin(pow(ratio, mZero), (double)nFlaws));
+}
+
+// ---- pair interaction ------------------------------------------------------------------------------------
+
+/// What one particle contributes as a neighbour. P = p/rho^2, Sr = S/rho^2, vol = m/rho, grp = body flag or -1 if the
+/// particle is fully damaged (reduce == 0), i.e. excluded by the SUM_ONLY_UNDAMAGED filter.
+struct Particle {
+    double x, y, z, h;
+    double vx, vy, vz;
+    double m, rho, P, cs, vol;
+    double Sr[5];
+    int grp;
+};
+
+/// Per-target running sums. T = sum m_j (v_j - v_i) (x) gradW (full 3x3, row-major), Cm = sum V_j (r_j - r_i) (x) gradW.
+struct Accum {
+    double ax, ay, az, du, divv;
+    double T[9];
+    double Cm[6];
+    uint32_t cnt;
+};
+
+SPH_HD void accumZero(Accum& a) {
+    a.ax = a.ay = a.az = a.du = a.divv = 0.;
+    for (int k = 0; k < 9; ++k) {
+        a.T[k] = 0.;
+    }
+    for (int k = 0; k < 6; ++k) {
+        a.Cm[k] = 0.;
+    }
+    a.cnt = 0;
+}
+
+/// Exact neighbour predicate of AsymmetricSolver::loop (AsymmetricSolver.cpp:186-191): d^2 < (R * hbar)^2, evaluated
+/// without FMA contraction and in the reference's operation order so that the neighbour SETS are bit-identical.
+SPH_HD bool isNeighbour(double dx, double dy, double dz, double hi, double hj, double R, double& d2, double& hbar) {
+#ifdef __CUDA_ARCH__
+    d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    hbar = __dmul_rn(0.5, __dadd_rn(hi, hj));
+    const double rh = __dmul_rn(R, hbar);
+    return d2 < __dmul_rn(rh, rh);
+#else
+    d2 = dx * dx + dy * dy + dz * dz;
+    hbar = 0.5 * (hi + hj);
+    const double rh = R * hbar;
+    return d2 < rh * rh;
+#endif
+}
+
+/// One directed pair i <- j. `lut` is the (dW/dq)/q table. SOLID adds velocity gradient + stress divergence (with the
+/// undamaged filter when FILTER), CORRECTED adds the correction-tensor sums.
+template <bool SOLID, bool CORRECTED, bool FILTER>
+SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut, const Particle& pi, const Particle& pj,
+    double dx, double dy, double dz, double d2, double hbar, Accum& acc) {
+    acc.cnt++;
+    const double hInv = 1. / hbar;
+    const double hInv2 = hInv * hInv;
+    const double qSqr = d2 * hInv2;
+    double G = 0.;
+    if (qSqr < prm.radius_sqr) {
+        const double fidx = prm.q_sqr_to_idx * qSqr;
+        const uint32_t k = (uint32_t)fidx;
+        const double ratio = fidx - (double)k;
+#ifdef __CUDA_ARCH__
+        const double g0 = __ldg(lut + k), g1 = __ldg(lut + k + 1);
+#else
+        const double g0 = lut[k], g1 = lut[k + 1];
+#endif
+        G = g0 * (1. - ratio) + g1 * ratio;
+    }
+    const double s = hInv2 * hInv2 * hInv * G; // h^-5 * (dW/dq)/q
+    const double gx = dx * s, gy = dy * s, gz = dz * s;
+    const double dvx = pj.vx - pi.vx, dvy = pj.vy - pi.vy, dvz = pj.vz - pi.vz;
+    const double dvg = dvx * gx + dvy * gy + dvz * gz;
+    const double mgx = pj.m * gx, mgy = pj.m * gy, mgz = pj.m * gz;
+    acc.divv += pj.m * dvg;
+
+    // artificial viscosity: w = (v_i - v_j).(r_i - r_j) = -(dv.d)
+    const double w = -(dvx * dx + dvy * dy + dvz * dz);
+    double Pi = 0.;
+    if (w < 0.) {
+        const double rhobar = 0.5 * (pi.rho + pj.rho);
+        const double csbar = 0.5 * (pi.cs + pj.cs);
+        const double mu = hbar * w / (d2 + 1.e-2 * hbar * hbar);
+        Pi = (-prm.av_alpha * csbar * mu + prm.av_beta * mu * mu) / rhobar;
+        acc.du += 0.5 * Pi * (-pj.m * dvg); // m_j * 0.5 * Pi * (v_i - v_j).gradW
+    }
+    // pressure gradient + AV: dv_i -= m_j (P_i + P_j + Pi) gradW
+    const double c = pi.P + pj.P + Pi;
+    acc.ax -= c * mgx;
+    acc.ay -= c * mgy;
+    acc.az -= c * mgz;
+
+    if (SOLID) {
+        bool ok = true;
+        if (FILTER) {
+            ok = (pi.grp == pj.grp) && (pi.grp >= 0);
+        }
+        if (ok) {
+            // stress divergence: dv_i += m_j (S_i/rho_i^2 + S_j/rho_j^2) gradW
+            const double sxx = pi.Sr[0] + pj.Sr[0], syy = pi.Sr[1] + pj.Sr[1], sxy = pi.Sr[2] + pj.Sr[2],
+                         sxz = pi.Sr[3] + pj.Sr[3], syz = pi.Sr[4] + pj.Sr[4];
+            const double szz = -sxx - syy;
+            acc.ax += sxx * mgx + sxy * mgy + sxz * mgz;
+            acc.ay += sxy * mgx + syy * mgy + syz * mgz;
+            acc.az += sxz * mgx + syz * mgy + szz * mgz;
+            // velocity gradient (uncorrected outer product; C_i is applied once in the epilogue)
+            acc.T[0] += dvx * mgx;
+            acc.T[1] += dvx * mgy;
+            acc.T[2] += dvx * mgz;
+            acc.T[3] += dvy * mgx;
+            acc.T[4] += dvy * mgy;
+            acc.T[5] += dvy * mgz;
+            acc.T[6] += dvz * mgx;
+            acc.T[7] += dvz * mgy;
+            acc.T[8] += dvz * mgz;
+            if (CORRECTED) {
+                // (r_j - r_i) (x) gradW = -s d (x) d  (symmetric)
+                const double vs = -pj.vol * s;
+                const double vdx = vs * dx, vdy = vs * dy, vdz = vs * dz;
+                acc.Cm[0] += vdx * dx;
+                acc.Cm[1] += vdy * dy;
+                acc.Cm[2] += vdz * dz;
+                acc.Cm[3] += vdx * dy;
+                acc.Cm[4] += vdx * dz;
+                acc.Cm[5] += vdy * dz;
+            }
+        }
+    }
+}
+
+/// Derivatives of one particle (everything IAsymmetricSolver::afterLoop leaves in the Storage for particle i).
+struct Derivs {
+    double ax, ay, az, vh, du, drho, divv;
+    double dS[5];
+    double gradv[6];
+    double corr[6];
+    uint32_t ncnt;
+};
+
+/// accumulated.store + equations.finalize for one particle.
+/// S = yielded stress of i (unscaled), p = reduced pressure.
+template <bool SOLID, bool CORRECTED>
+SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const Accum& acc, double h, double rho, double p,
+    double cs, double reduce, const double S[5], Derivs& out) {
+    const double rhoInv = 1. / rho;
+    out.ncnt = acc.cnt;
+    out.ax = acc.ax;
+    out.ay = acc.ay;
+    out.az = acc.az;
+    out.divv = acc.divv * rhoInv;
+    double du = acc.du;
+    double trGradv = 0.;
+    if (SOLID) {
+        double C[6] = { 1., 1., 1., 0., 0., 0. };
+        if (CORRECTED) {
+            const double* c = acc.Cm;
+            const bool isNull = c[0] == 0. && c[1] == 0. && c[2] == 0. && c[3] == 0. && c[4] == 0. && c[5] == 0.;
+            if (!isNull) {
+                const double det = c[0] * c[1] * c[2] + 2. * c[3] * c[4] * c[5] -
+                                   (c[3] * c[3] * c[2] + c[4] * c[4] * c[1] + c[5] * c[5] * c[0]);
+                if (det > 0.01) {
+                    C[0] = (c[1] * c[2] - c[5] * c[5]) / det;
+                    C[1] = (c[2] * c[0] - c[4] * c[4]) / det;
+                    C[2] = (c[0] * c[1] - c[3] * c[3]) / det;
+                    C[3] = (c[4] * c[5] - c[2] * c[3]) / det;
+                    C[4] = (c[5] * c[3] - c[1] * c[4]) / det;
+                    C[5] = (c[3] * c[4] - c[0] * c[5]) / det;
+                }
+            }
+        }
+        for (int k = 0; k < 6; ++k) {
+            out.corr[k] = C[k];
+        }
+        // gradv = sym(T * C) / rho ; C symmetric: rows {C0,C3,C4},{C3,C1,C5},{C4,C5,C2}
+        const double* T = acc.T;
+        double M[9];
+        for (int a = 0; a < 3; ++a) {
+            M[3 * a + 0] = T[3 * a] * C[0] + T[3 * a + 1] * C[3] + T[3 * a + 2] * C[4];
+            M[3 * a + 1] = T[3 * a] * C[3] + T[3 * a + 1] * C[1] + T[3 * a + 2] * C[5];
+            M[3 * a + 2] = T[3 * a] * C[4] + T[3 * a + 1] * C[5] + T[3 * a + 2] * C[2];
+        }
+        out.gradv[0] = M[0] * rhoInv;
+        out.gradv[1] = M[4] * rhoInv;
+        out.gradv[2] = M[8] * rhoInv;
+        out.gradv[3] = 0.5 * (M[1] + M[3]) * rhoInv;
+        out.gradv[4] = 0.5 * (M[2] + M[6]) * rhoInv;
+        out.gradv[5] = 0.5 * (M[5] + M[7]) * rhoInv;
+        trGradv = out.gradv[0] + out.gradv[1] + out.gradv[2];
+    }
+    // smoothing length (AdaptiveSmoothingLength::finalize / ConstSmoothingLength::finalize)
+    double vh = 0.;
+    if (prm.flags & SPHGPU_FLAG_ADAPTIVE_H) {
+        if (h > 2. * prm.h_min) {
+            vh = h / 3. * out.divv;
+        }
+        if ((prm.flags & SPHGPU_FLAG_SOUND_SPEED_ENFORCING) && !(prm.neigh_enforcing <= -1.e2)) {
+            const double dn1 = (double)acc.cnt - prm.neigh_upper;
+            if (dn1 > 0.) {
+                vh -= exp(prm.neigh_enforcing * dn1) * cs;
+            } else {
+                const double dn2 = prm.neigh_lower - (double)acc.cnt;
+                if (dn2 > 0.) {
+                    vh += exp(prm.neigh_enforcing * dn2) * cs;
+                }
+            }
+        }
+    }
+    out.vh = vh;
+    // continuity equation
+    if (SOLID && prm.continuity_mode == SPHGPU_CONTINUITY_SUM_ONLY_UNDAMAGED && reduce > 0.) {
+        out.drho = -rho * trGradv;
+    } else {
+        out.drho = -rho * out.divv;
+    }
+    // solid stress: du += S:gradv / rho ; dS = 2 mu (gradv - tr/3 I)
+    for (int k = 0; k < 5; ++k) {
+        out.dS[k] = 0.;
+    }
+    if (SOLID && mat.yielding != SPHGPU_YIELD_NONE && mat.yielding != SPHGPU_YIELD_DUST) {
+        const double* gv = out.gradv;
+        const double ddot = (S[0] * gv[0] + S[1] * gv[1] + (-S[0] - S[1]) * gv[2]) + 2. * (S[2] * gv[3] + S[3] * gv[4] + S[4] * gv[5]);
+        du += rhoInv * ddot;
+        const double tr3 = trGradv / 3.;
+        const double mu2 = 2. * mat.shear_modulus;
+        out.dS[0] = mu2 * (gv[0] - tr3);
+        out.dS[1] = mu2 * (gv[1] - tr3);
+        out.dS[2] = mu2 * gv[3];
+        out.dS[3] = mu2 * gv[4];
+        out.dS[4] = mu2 * gv[5];
+    }
+    if (prm.forces & SPHGPU_FORCE_PRESSURE) {
+        du -= p * rhoInv * out.divv;
+    }
+    out.du = du;
+}
+
+// ---- time stepping ----------------------------------------------------------------------------------------
+
+SPH_HD bool rangeBounded(double lo, double hi) {
+    return !(lo <= -INFTY_REF && hi >= INFTY_REF);
+}
+
+/// clampWithDerivative<Float>, core/objects/wrappers/Interval.h:159-162
+SPH_HD void clampWithDerivative(double& v, double& dv, double lo, double hi) {
+    const bool zeroDeriv = (v >= hi && dv > 0.) || (v <= lo && dv < 0.);
+    v = fmax(lo, fmin(v, hi));
+    if (zeroDeriv) {
+        dv = 0.;
+    }
+}
+
+/// One component of DerivativeCriterion::computeImpl, core/timestepping/TimeStepCriterion.cpp:150-176
+SPH_HD double derivativeStep(double absv, double absdv, double minValue, double factor) {
+    if (absv < 2. * minValue) {
+        return INFTY_REF;
+    }
+    return factor * (absv + minValue) / (absdv + EPS_REF);
+}
+
+} // namespace sph

@@ -1,0 +1,136 @@
+// Internal declarations of libsphgpu: device-resident SoA state, grid, and kernel launchers.
+#pragma once
+#include "../../include/sphgpu.h"
+#include "sph_math.cuh"
+#include <cuda_runtime.h>
+#include <string>
+
+namespace sph {
+
+// ---- device-resident particle state (structure of arrays, FP64) ------------------------------------------
+// One plane of `capacity` doubles per field. Particles keep the caller's ("slot") order; the per-step cell sort
+// only produces an index permutation plus compact, sorted neighbour-input planes (see Sorted below).
+enum Field : int {
+    F_X, F_Y, F_Z, F_H,           // POSITION value {x,y,z,h}
+    F_VX, F_VY, F_VZ, F_VH,       // POSITION dt {v, dh/dt}
+    F_AX, F_AY, F_AZ,             // POSITION d2t (h lane is identically 0)
+    F_M,
+    F_RHO, F_DRHO,
+    F_U, F_DU,
+    F_P, F_CS,
+    F_S0, F_S1, F_S2, F_S3, F_S4,       // DEVIATORIC_STRESS {xx,yy,xy,xz,yz}
+    F_DS0, F_DS1, F_DS2, F_DS3, F_DS4,
+    F_REDUCE,
+    F_D, F_DD,
+    F_EPSMIN, F_MZERO, F_GROWTH,
+    F_DIVV,
+    F_GV0, F_GV1, F_GV2, F_GV3, F_GV4, F_GV5, // VELOCITY_GRADIENT {xx,yy,zz,xy,xz,yz}
+    F_C0, F_C1, F_C2, F_C3, F_C4, F_C5,       // STRAIN_RATE_CORRECTION_TENSOR
+    // PredictorCorrector "predictions": copies of the highest derivatives (TimeStepping.cpp:272-282)
+    F_AXP, F_AYP, F_AZP, F_DRHOP, F_DUP, F_DSP0, F_DSP1, F_DSP2, F_DSP3, F_DSP4, F_DDP,
+    F_COUNT
+};
+
+enum UField : int { U_NFLAWS, U_FLAG, U_MATID, U_NCNT, U_COUNT };
+
+// Sorted neighbour-input planes, rebuilt every integrate() in cell order.
+enum SField : int {
+    S_X, S_Y, S_Z, S_H, S_VX, S_VY, S_VZ, S_M, S_RHO, S_P, S_CS, S_VOL, S_S0, S_S1, S_S2, S_S3, S_S4, S_COUNT
+};
+
+struct GridDev {
+    double lo[3];
+    double cell, cellInv;
+    int dim[3];
+    uint32_t ncells;
+    double hmax;
+};
+
+struct StatsDev {
+    unsigned int neighMin, neighMax;
+    unsigned long long pairCount;
+};
+
+struct TimestepDev {
+    unsigned long long minBits[4]; // Courant, Derivative, Acceleration, Divergence (bit patterns of positive doubles)
+};
+
+struct DevicePointers {
+    double* f[F_COUNT];
+    uint32_t* u[U_COUNT];
+    double* s[S_COUNT];
+    int* sGrp;          // sorted: body flag, or -1 when reduce == 0
+    uint32_t* sCell;    // sorted: linear cell index
+    uint32_t* order;    // sorted position -> slot
+    uint32_t* cellOf;   // slot -> cell
+    uint32_t* rank;     // slot -> rank inside its cell
+    uint32_t* cellStart; // [maxCells + 1] exclusive prefix of counts
+    uint32_t* cellCount; // [maxCells + 1]
+    uint32_t* scanBlock; // block sums of the scan
+    double* boundsPartial; // [BOUNDS_BLOCKS * 8]
+    const double* lut;
+    GridDev* grid;
+    StatsDev* stats;
+    TimestepDev* tsd;
+    const MaterialDev* mats;
+};
+
+constexpr int BOUNDS_BLOCKS = 592;   // 148 SMs x 4
+constexpr int SCAN_ITEMS = 4096;     // items per scan block
+
+} // namespace sph
+
+struct sphgpu_ctx {
+    int device = 0;
+    uint32_t n = 0, capacity = 0, nActive = 0, maxCells = 0, scanBlocks = 0;
+    sph::ParamsDev prm{};
+    sph::MaterialDev matsHost[sph::MAX_MATERIALS];
+    sphgpu_material matsApi[sph::MAX_MATERIALS];
+    uint32_t nMaterials = 0;
+    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false;
+    sph::DevicePointers d{};
+    void* staging = nullptr;   // device staging for AoS <-> SoA repack (capacity * 64 B)
+    cudaStream_t stream = nullptr;        // stream all work is queued on (private or caller-provided)
+    cudaStream_t privateStream = nullptr;
+    double maxChange = 1.e308;            // TIMESTEPPING_MAX_INCREASE
+    cudaEvent_t ev[6] = {};
+    double lastMs[4] = { 0, 0, 0, 0 };
+    double lastDt = 0.;        // MultiCriterion::lastStep
+    bool lastDtInit = false;
+    int variant = 0;
+    uint32_t launches = 0;
+    bool stateUploaded = false;
+};
+
+namespace sph {
+
+void setError(const std::string& msg);
+
+#define SPH_CUDA_CHECK(expr)                                                                                          \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess) {                                                                                      \
+            sph::setError(std::string(#expr) + ": " + cudaGetErrorString(_e));                                       \
+            return _e == cudaErrorMemoryAllocation ? SPHGPU_E_OOM : SPHGPU_E_CUDA;                                    \
+        }                                                                                                             \
+    } while (0)
+
+// grid.cu
+int launchGridBuild(sphgpu_ctx* ctx);
+// pair.cu
+int launchProloguePack(sphgpu_ctx* ctx);
+int launchProloguePackPositionsOnly(sphgpu_ctx* ctx);
+int launchPair(sphgpu_ctx* ctx);
+int launchNeighbourCount(sphgpu_ctx* ctx, uint32_t* countsDev);
+int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, uint32_t* idxDev);
+// stepping.cu
+int launchPredict(sphgpu_ctx* ctx, double dt);
+int launchCorrect(sphgpu_ctx* ctx, double dt);
+int launchEuler(sphgpu_ctx* ctx, double dt);
+int launchCriteria(sphgpu_ctx* ctx);
+// transfer.cu
+int launchUnpack(sphgpu_ctx* ctx, int q, int order, int layout, const void* stagingDev, uint32_t first, uint32_t count);
+int launchPack(sphgpu_ctx* ctx, int q, int order, int layout, void* stagingDev, uint32_t first, uint32_t count);
+size_t elementBytes(int q, int layout);
+
+} // namespace sph

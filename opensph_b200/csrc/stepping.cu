@@ -1,0 +1,304 @@
+// Device-resident time integration: elementwise kernels over the SoA state, no PCIe traffic.
+// Replaces PredictorCorrector::makePredictions / makeCorrections and EulerExplicit::stepParticles
+// (core/timestepping/TimeStepping.cpp:234-346, stepFirstOrder/stepSecondOrder + clampWithDerivative :81-228) and the
+// four criteria of MultiCriterion (core/timestepping/TimeStepCriterion.cpp:117-419).
+#include "sphgpu_internal.h"
+
+namespace sph {
+
+__device__ __forceinline__ void clampFirstOrder(const MaterialDev& m, bool hasDamage, double& rho, double& drho, double& u,
+    double& du, double& D, double& dD) {
+    if (rangeBounded(m.rho_min, m.rho_max)) {
+        clampWithDerivative(rho, drho, m.rho_min, m.rho_max);
+    }
+    if (rangeBounded(m.u_min, m.u_max)) {
+        clampWithDerivative(u, du, m.u_min, m.u_max);
+    }
+    if (hasDamage && rangeBounded(m.d_min, m.d_max)) {
+        clampWithDerivative(D, dD, m.d_min, m.d_max);
+    }
+}
+
+// makePredictions (TimeStepping.cpp:286-300) + storage->swap(predictions) + zeroHighestDerivatives (:331-334).
+// The derivative planes are not zeroed: integrate() overwrites every one of them.
+template <bool SOLID>
+__global__ void __launch_bounds__(256) k_predict(DevicePointers d, uint32_t n, double dt, bool hasDamage) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const MaterialDev& m = c_mats[d.u[U_MATID][i]];
+    const double dt2 = 0.5 * dt * dt;
+    const double ax = d.f[F_AX][i], ay = d.f[F_AY][i], az = d.f[F_AZ][i];
+    const double vx = d.f[F_VX][i], vy = d.f[F_VY][i], vz = d.f[F_VZ][i], vh = d.f[F_VH][i];
+    d.f[F_X][i] += vx * dt + ax * dt2;
+    d.f[F_Y][i] += vy * dt + ay * dt2;
+    d.f[F_Z][i] += vz * dt + az * dt2;
+    d.f[F_H][i] += vh * dt + 0. * dt2;
+    d.f[F_VX][i] = vx + ax * dt;
+    d.f[F_VY][i] = vy + ay * dt;
+    d.f[F_VZ][i] = vz + az * dt;
+    d.f[F_AXP][i] = ax;
+    d.f[F_AYP][i] = ay;
+    d.f[F_AZP][i] = az;
+    const bool dmg = hasDamage && m.fracture != SPHGPU_FRACTURE_NONE;
+    double rho = d.f[F_RHO][i], drho = d.f[F_DRHO][i], u = d.f[F_U][i], du = d.f[F_DU][i];
+    double D = dmg ? d.f[F_D][i] : 0., dD = dmg ? d.f[F_DD][i] : 0.;
+    rho += drho * dt;
+    u += du * dt;
+    D += dD * dt;
+    clampFirstOrder(m, dmg, rho, drho, u, du, D, dD);
+    d.f[F_RHO][i] = rho;
+    d.f[F_U][i] = u;
+    d.f[F_DRHOP][i] = drho;
+    d.f[F_DUP][i] = du;
+    if (dmg) {
+        d.f[F_D][i] = D;
+        d.f[F_DDP][i] = dD;
+    }
+    if (SOLID) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double ds = d.f[F_DS0 + k][i];
+            d.f[F_S0 + k][i] += ds * dt;
+            d.f[F_DSP0 + k][i] = ds;
+        }
+    }
+}
+
+// makeCorrections (TimeStepping.cpp:302-322): storage1 = *storage (p*), storage2 = predictions (c*).
+template <bool SOLID>
+__global__ void __launch_bounds__(256) k_correct(DevicePointers d, uint32_t n, double dt, bool hasDamage) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const MaterialDev& m = c_mats[d.u[U_MATID][i]];
+    const double dt2 = 0.5 * dt * dt;
+    const double a = 1. / 3., b = 0.5;
+    const double ex = d.f[F_AXP][i] - d.f[F_AX][i], ey = d.f[F_AYP][i] - d.f[F_AY][i], ez = d.f[F_AZP][i] - d.f[F_AZ][i];
+    d.f[F_X][i] -= a * ex * dt2;
+    d.f[F_Y][i] -= a * ey * dt2;
+    d.f[F_Z][i] -= a * ez * dt2;
+    d.f[F_VX][i] -= b * ex * dt;
+    d.f[F_VY][i] -= b * ey * dt;
+    d.f[F_VZ][i] -= b * ez * dt;
+    const bool dmg = hasDamage && m.fracture != SPHGPU_FRACTURE_NONE;
+    double rho = d.f[F_RHO][i], drho = d.f[F_DRHO][i], u = d.f[F_U][i], du = d.f[F_DU][i];
+    double D = dmg ? d.f[F_D][i] : 0., dD = dmg ? d.f[F_DD][i] : 0.;
+    rho -= 0.5 * (d.f[F_DRHOP][i] - drho) * dt;
+    u -= 0.5 * (d.f[F_DUP][i] - du) * dt;
+    if (dmg) {
+        D -= 0.5 * (d.f[F_DDP][i] - dD) * dt;
+    }
+    const double drho0 = drho, du0 = du, dD0 = dD;
+    clampFirstOrder(m, dmg, rho, drho, u, du, D, dD);
+    d.f[F_RHO][i] = rho;
+    d.f[F_U][i] = u;
+    if (drho != drho0) {
+        d.f[F_DRHO][i] = drho;
+    }
+    if (du != du0) {
+        d.f[F_DU][i] = du;
+    }
+    if (dmg) {
+        d.f[F_D][i] = D;
+        if (dD != dD0) {
+            d.f[F_DD][i] = dD;
+        }
+    }
+    if (SOLID) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            d.f[F_S0 + k][i] -= 0.5 * (d.f[F_DSP0 + k][i] - d.f[F_DS0 + k][i]) * dt;
+        }
+    }
+}
+
+// EulerExplicit::stepParticles after solver.integrate (TimeStepping.cpp:243-264).
+template <bool SOLID>
+__global__ void __launch_bounds__(256) k_euler(DevicePointers d, uint32_t n, double dt, bool hasDamage) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const MaterialDev& m = c_mats[d.u[U_MATID][i]];
+    const double vx = d.f[F_VX][i] + d.f[F_AX][i] * dt;
+    const double vy = d.f[F_VY][i] + d.f[F_AY][i] * dt;
+    const double vz = d.f[F_VZ][i] + d.f[F_AZ][i] * dt;
+    d.f[F_VX][i] = vx;
+    d.f[F_VY][i] = vy;
+    d.f[F_VZ][i] = vz;
+    d.f[F_X][i] += vx * dt;
+    d.f[F_Y][i] += vy * dt;
+    d.f[F_Z][i] += vz * dt;
+    d.f[F_H][i] += d.f[F_VH][i] * dt;
+    const bool dmg = hasDamage && m.fracture != SPHGPU_FRACTURE_NONE;
+    double rho = d.f[F_RHO][i], drho = d.f[F_DRHO][i], u = d.f[F_U][i], du = d.f[F_DU][i];
+    double D = dmg ? d.f[F_D][i] : 0., dD = dmg ? d.f[F_DD][i] : 0.;
+    rho += drho * dt;
+    u += du * dt;
+    D += dD * dt;
+    const double drho0 = drho, du0 = du, dD0 = dD;
+    clampFirstOrder(m, dmg, rho, drho, u, du, D, dD);
+    d.f[F_RHO][i] = rho;
+    d.f[F_U][i] = u;
+    if (drho != drho0) {
+        d.f[F_DRHO][i] = drho;
+    }
+    if (du != du0) {
+        d.f[F_DU][i] = du;
+    }
+    if (dmg) {
+        d.f[F_D][i] = D;
+        if (dD != dD0) {
+            d.f[F_DD][i] = dD;
+        }
+    }
+    if (SOLID) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            d.f[F_S0 + k][i] += d.f[F_DS0 + k][i] * dt;
+        }
+    }
+}
+
+__device__ __forceinline__ double warpMinD(double v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+
+// Courant / Derivative / Acceleration / Divergence criteria in one pass; per-criterion minima are combined with
+// atomicMin on the bit pattern (all candidates are positive doubles, whose bit patterns order like the values).
+template <bool SOLID>
+__global__ void __launch_bounds__(256) k_criteria(DevicePointers d, uint32_t n, bool hasDamage) {
+    double mins[4] = { INFTY_REF, INFTY_REF, INFTY_REF, INFTY_REF };
+    const uint32_t crit = c_prm.criteria;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const MaterialDev& m = c_mats[d.u[U_MATID][i]];
+        const double h = d.f[F_H][i];
+        if (crit & SPHGPU_CRIT_COURANT) {
+            const double cs = d.f[F_CS][i];
+            if (cs > 0.) {
+                mins[0] = fmin(mins[0], c_prm.courant * h / cs);
+            }
+        }
+        if (crit & SPHGPU_CRIT_DERIVATIVES) {
+            const double f = c_prm.derivative_factor;
+            double s = derivativeStep(fabs(d.f[F_RHO][i]), fabs(d.f[F_DRHO][i]), m.rho_small, f);
+            s = fmin(s, derivativeStep(fabs(d.f[F_U][i]), fabs(d.f[F_DU][i]), m.u_small, f));
+            if (hasDamage && m.fracture != SPHGPU_FRACTURE_NONE) {
+                s = fmin(s, derivativeStep(fabs(d.f[F_D][i]), fabs(d.f[F_DD][i]), m.d_small, f));
+            }
+            if (SOLID) {
+                double S[5], dS[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    S[k] = d.f[F_S0 + k][i];
+                    dS[k] = d.f[F_DS0 + k][i];
+                    s = fmin(s, derivativeStep(fabs(S[k]), fabs(dS[k]), m.s_small, f));
+                }
+                s = fmin(s, derivativeStep(fabs(-S[0] - S[1]), fabs(-dS[0] - dS[1]), m.s_small, f));
+            }
+            mins[1] = fmin(mins[1], s);
+        }
+        if (crit & SPHGPU_CRIT_ACCELERATION) {
+            const double ax = d.f[F_AX][i], ay = d.f[F_AY][i], az = d.f[F_AZ][i];
+            const double dvNorm = ax * ax + ay * ay + az * az;
+            if (dvNorm > EPS_REF) {
+                mins[2] = fmin(mins[2], c_prm.derivative_factor * sqrt(sqrt(h * h / dvNorm)));
+            }
+        }
+        if (crit & SPHGPU_CRIT_DIVERGENCE) {
+            const double dv = fabs(d.f[F_DIVV][i]);
+            if (dv > EPS_REF) {
+                mins[3] = fmin(mins[3], c_prm.divergence_factor / dv);
+            }
+        }
+    }
+    __shared__ double sm[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 4; ++k) {
+        mins[k] = warpMinD(mins[k]);
+    }
+    if (lane == 0) {
+        for (int k = 0; k < 4; ++k) {
+            sm[warp][k] = mins[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double r = sm[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) {
+            r = fmin(r, sm[w][threadIdx.x]);
+        }
+        if (r < 0.) {
+            r = 0.;
+        }
+        atomicMin(&d.tsd->minBits[threadIdx.x], (unsigned long long)__double_as_longlong(r));
+    }
+}
+
+#define SPH_DISPATCH_SOLID(KERNEL, ...)                                                                               \
+    do {                                                                                                              \
+        if (ctx->solid) {                                                                                             \
+            KERNEL<true><<<blocks, 256, 0, ctx->stream>>>(__VA_ARGS__);                                               \
+        } else {                                                                                                      \
+            KERNEL<false><<<blocks, 256, 0, ctx->stream>>>(__VA_ARGS__);                                              \
+        }                                                                                                             \
+        ctx->launches += 1;                                                                                           \
+    } while (0)
+
+int launchPredict(sphgpu_ctx* ctx, double dt) {
+    const uint32_t n = ctx->n;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = (n + 255) / 256;
+    SPH_DISPATCH_SOLID(k_predict, ctx->d, n, dt, ctx->hasDamage);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchCorrect(sphgpu_ctx* ctx, double dt) {
+    const uint32_t n = ctx->n;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = (n + 255) / 256;
+    SPH_DISPATCH_SOLID(k_correct, ctx->d, n, dt, ctx->hasDamage);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchEuler(sphgpu_ctx* ctx, double dt) {
+    const uint32_t n = ctx->n;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = (n + 255) / 256;
+    SPH_DISPATCH_SOLID(k_euler, ctx->d, n, dt, ctx->hasDamage);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchCriteria(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->n;
+    TimestepDev init;
+    const double inf = INFTY_REF;
+    for (int k = 0; k < 4; ++k) {
+        memcpy(&init.minBits[k], &inf, 8);
+    }
+    SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->d.tsd, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = min((n + 255) / 256, (uint32_t)BOUNDS_BLOCKS * 2);
+    SPH_DISPATCH_SOLID(k_criteria, ctx->d, n, ctx->hasDamage);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+} // namespace sph

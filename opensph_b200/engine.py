@@ -1,0 +1,181 @@
+"""Python binding of the C ABI (include/sphgpu.h) -- thin ctypes layer used by the tests, bench.py and the multi-GPU
+driver. It adds no compute of its own and has no fallback: if libsphgpu.so is missing or no CUDA device is usable
+it raises.
+
+The call sequence mirrors the reference's (core/run/IRun.cpp:304-329, core/timestepping/TimeStepping.cpp:324-346):
+create (AsymmetricSolver ctor) -> upload (Storage) -> integrate / step_pc (ISolver::integrate, ITimeStepping::step)
+-> download.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Optional, Tuple
+
+import numpy as np
+
+from . import abi
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsphgpu.so")
+_lib: Optional[C.CDLL] = None
+
+
+class SphGpuError(RuntimeError):
+    """Non-zero status from libsphgpu (the C++ wrapper maps the same codes to InvalidSetup / Exception)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsphgpu error {code}: {msg}")
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise FileNotFoundError(
+                f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(_LIB_PATH)
+        lib.sphgpu_last_error.restype = C.c_char_p
+        lib.sphgpu_abi_version.restype = C.c_uint32
+        if lib.sphgpu_abi_version() != abi.ABI_VERSION:
+            raise RuntimeError("libsphgpu ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SphGpuError(rc, load_library().sphgpu_last_error().decode(errors="replace"))
+
+
+class Engine:
+    """One device context (`sphgpu_ctx`): device-resident particle state + the hot-path kernels."""
+
+    def __init__(self, setup: abi.RunSetup, n_particles: int, capacity: Optional[int] = None, device: int = 0):
+        self.lib = load_library()
+        self.setup = setup
+        self.n = int(n_particles)
+        self.capacity = int(capacity if capacity is not None else n_particles)
+        self.device = device
+        self._ctx = C.c_void_p()
+        _check(self.lib.sphgpu_create(C.byref(setup.cfg), setup.materials, C.c_uint32(setup.n_materials),
+                                      C.c_uint32(self.n), C.c_uint32(self.capacity), C.c_int(device), C.byref(self._ctx)))
+
+    # -- lifetime ----------------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if self._ctx:
+            self.lib.sphgpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- state transfer ----------------------------------------------------------------------------------------
+    def upload(self, quantity: str, order: int, array: np.ndarray, first: int = 0) -> None:
+        qid, ncomp, dtype = abi.QUANTITIES[quantity]
+        a = np.ascontiguousarray(array, dtype=dtype)
+        count = a.shape[0]
+        assert a.size == count * ncomp, f"{quantity}: expected {ncomp} components"
+        _check(self.lib.sphgpu_upload(self._ctx, C.c_int(qid), C.c_int(order), C.c_int(abi.LAYOUT_PACKED),
+                                      a.ctypes.data_as(C.c_void_p), C.c_uint32(first), C.c_uint32(count)))
+
+    def download(self, quantity: str, order: int = 0, first: int = 0, count: Optional[int] = None,
+                 out: Optional[np.ndarray] = None) -> np.ndarray:
+        qid, ncomp, dtype = abi.QUANTITIES[quantity]
+        count = self.n - first if count is None else count
+        if out is None:
+            out = np.empty((count, ncomp) if ncomp > 1 else (count,), dtype=dtype)
+        _check(self.lib.sphgpu_download(self._ctx, C.c_int(qid), C.c_int(order), C.c_int(abi.LAYOUT_PACKED),
+                                        out.ctypes.data_as(C.c_void_p), C.c_uint32(first), C.c_uint32(count)))
+        return out
+
+    def upload_device(self, quantity: str, order: int, dev_ptr: int, first: int, count: int) -> None:
+        qid, _, _ = abi.QUANTITIES[quantity]
+        _check(self.lib.sphgpu_upload_device(self._ctx, C.c_int(qid), C.c_int(order), C.c_void_p(dev_ptr),
+                                             C.c_uint32(first), C.c_uint32(count)))
+
+    def download_device(self, quantity: str, order: int, dev_ptr: int, first: int, count: int) -> None:
+        qid, _, _ = abi.QUANTITIES[quantity]
+        _check(self.lib.sphgpu_download_device(self._ctx, C.c_int(qid), C.c_int(order), C.c_void_p(dev_ptr),
+                                               C.c_uint32(first), C.c_uint32(count)))
+
+    def upload_state(self, arrays: Dict[str, np.ndarray], names: Optional[Iterable[str]] = None, first: int = 0) -> int:
+        """Uploads every snapshot-named array present (pos, vel, rho, ...). Returns the bytes copied."""
+        total = 0
+        for name in (names if names is not None else abi.SNAPSHOT_FIELDS.keys()):
+            if name in arrays and name in abi.SNAPSHOT_FIELDS:
+                q, order = abi.SNAPSHOT_FIELDS[name]
+                self.upload(q, order, arrays[name], first)
+                total += arrays[name].nbytes
+        return total
+
+    def download_state(self, names: Iterable[str]) -> Dict[str, np.ndarray]:
+        out = {}
+        for name in names:
+            q, order = abi.SNAPSHOT_FIELDS[name]
+            out[name] = self.download(q, order)
+        return out
+
+    def set_active(self, n_active: int) -> None:
+        _check(self.lib.sphgpu_set_active(self._ctx, C.c_uint32(n_active)))
+
+    # -- hot path ----------------------------------------------------------------------------------------------
+    def integrate(self, t: float = 0.0) -> abi.Stats:
+        st = abi.Stats()
+        _check(self.lib.sphgpu_integrate(self._ctx, C.c_double(t), C.byref(st)))
+        return st
+
+    def predict(self, dt: float) -> None:
+        _check(self.lib.sphgpu_step_predict(self._ctx, C.c_double(dt)))
+
+    def correct(self, dt: float) -> None:
+        _check(self.lib.sphgpu_step_correct(self._ctx, C.c_double(dt)))
+
+    def euler(self, dt: float) -> None:
+        _check(self.lib.sphgpu_step_euler(self._ctx, C.c_double(dt)))
+
+    def compute_timestep(self, max_dt: float) -> Tuple[float, int]:
+        ts = abi.TimeStep()
+        _check(self.lib.sphgpu_compute_timestep(self._ctx, C.c_double(max_dt), C.byref(ts)))
+        return float(ts.dt), int(ts.criterion)
+
+    def set_last_timestep(self, dt: float) -> None:
+        _check(self.lib.sphgpu_set_last_timestep(self._ctx, C.c_double(dt)))
+
+    def step_pc(self, dt: float, max_dt: float, t: float = 0.0) -> Tuple[float, int, abi.Stats]:
+        st, ts = abi.Stats(), abi.TimeStep()
+        _check(self.lib.sphgpu_step_pc(self._ctx, C.c_double(t), C.c_double(dt), C.c_double(max_dt), C.byref(st), C.byref(ts)))
+        return float(ts.dt), int(ts.criterion), st
+
+    # -- inspection --------------------------------------------------------------------------------------------
+    def neighbours(self) -> Tuple[np.ndarray, np.ndarray]:
+        off = np.zeros(self.n + 1, np.uint64)
+        _check(self.lib.sphgpu_neighbour_dump(self._ctx, off.ctypes.data_as(C.POINTER(C.c_uint64)), None, C.c_uint64(0)))
+        idx = np.zeros(int(off[-1]), np.uint32)
+        _check(self.lib.sphgpu_neighbour_dump(self._ctx, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(idx))))
+        return off, idx
+
+    def last_timings(self) -> np.ndarray:
+        ms = np.zeros(4)
+        _check(self.lib.sphgpu_last_timings(self._ctx, ms.ctypes.data_as(C.POINTER(C.c_double))))
+        return ms
+
+    def set_variant(self, variant: int) -> None:
+        _check(self.lib.sphgpu_set_variant(self._ctx, C.c_int(variant)))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _check(self.lib.sphgpu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def synchronize(self) -> None:
+        _check(self.lib.sphgpu_synchronize(self._ctx))

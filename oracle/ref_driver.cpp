@@ -10,7 +10,8 @@
 //
 // Commands
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
-//                    [--neighbours] [--steps K] [--integrator pc|euler] --in IN.snap --out OUT.snap
+//                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
+//                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
 //   sph_ref bench    --config C --n N --steps K --warmup W [--threads T] [--finder kd|grid] [--integrate-only]
@@ -284,7 +285,9 @@ void jitter(Storage& storage, const unsigned seed) {
     }
 }
 
-void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& w) {
+void dumpLut(const RunSettings& settings, SnapWriter& w);
+
+void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& w, const bool withLut = true) {
     ArrayView<const Vector> r, v, dv;
     tie(r, v, dv) = storage.getAll<Vector>(QuantityId::POSITION);
     w.addF64("pos", vec4(r), 4);
@@ -392,7 +395,14 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
     };
     w.addF64("run_params", run, 1);
 
+    if (withLut) {
+        dumpLut(settings, w);
+    }
+}
+
+void dumpLut(const RunSettings& settings, SnapWriter& w) {
     // the LUT exactly as the reference builds it (core/sph/kernel/Kernel.h:85-101)
+    LutKernel<3> kernel = Factory::getKernel<3>(settings);
     const Size entries = 40000;
     const Float qSqrToIdx = Float(entries) / sqr(kernel.radius());
     std::vector<double> lutGrad(entries + 1), lutVal(entries + 1);
@@ -492,9 +502,15 @@ int main(int argc, char** argv) {
         const Size N = storage->getParticleCnt();
 
         if (cmd == "snapshot") {
+            const bool withLut = !args.has("no-lut");
+            if (args.has("lut")) {
+                SnapWriter w;
+                dumpLut(settings, w);
+                w.write(args.str("lut"));
+            }
             if (args.has("in")) {
                 SnapWriter w;
-                dumpState(*storage, settings, w);
+                dumpState(*storage, settings, w, withLut);
                 w.write(args.str("in"));
             }
             Statistics stats;
@@ -513,7 +529,7 @@ int main(int argc, char** argv) {
                 dts.push_back(stepping->getTimeStep());
             }
             SnapWriter w;
-            dumpState(*storage, settings, w);
+            dumpState(*storage, settings, w, withLut);
             if (!dts.empty()) {
                 w.addF64("dt_history", dts, 1);
             }

@@ -1,0 +1,112 @@
+// Test-only harness: runs the product's per-particle / per-pair arithmetic (opensph_b200/csrc/sph_math.cuh, the very
+// functions the CUDA kernels call) on the CPU over neighbour lists supplied by the caller, so the formulas can be
+// checked against the oracle without a GPU. Not part of the product; built by tests/test_host_math.py.
+#include "../../opensph_b200/csrc/sph_math.cuh"
+#include "../../oracle/sph_oracle.h"
+#include <vector>
+
+using namespace sph;
+
+template <bool SOLID, bool CORRECTED, bool FILTER>
+static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDev>& mats, const std::vector<uint32_t>& matid,
+    const double* lut, const uint64_t* off, const uint32_t* idx, bool hasReduce, bool hasDamage) {
+    const uint32_t n = s->n;
+    std::vector<Particle> P(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const MaterialDev& mat = mats[matid[i]];
+        double p = s->p[i], cs = s->cs[i];
+        evalEos(mat, s->rho[i], s->u[i], p, cs);
+        double S[5] = { 0, 0, 0, 0, 0 };
+        double reduce = hasReduce ? s->reduce[i] : 1.;
+        if (SOLID) {
+            for (int k = 0; k < 5; ++k) S[k] = s->S[5 * (size_t)i + k];
+        }
+        if (mat.yielding == SPHGPU_YIELD_VON_MISES) {
+            const bool dmg = hasDamage && mat.fracture != SPHGPU_FRACTURE_NONE;
+            const double D = dmg ? s->damage[i] : 0.;
+            reduce = vonMises(mat, s->u[i], D, dmg, p, S);
+            s->reduce[i] = reduce;
+            if (SOLID) {
+                for (int k = 0; k < 5; ++k) s->S[5 * (size_t)i + k] = S[k];
+            }
+            if (dmg) {
+                s->ddamage[i] = damageRate(mat, p, S, D, s->eps_min[i], s->m_zero[i], s->growth[i], s->n_flaws[i]);
+            }
+        }
+        s->p[i] = p;
+        s->cs[i] = cs;
+        if (prm.flags & SPHGPU_FLAG_ADAPTIVE_H) {
+            s->pos[4 * (size_t)i + 3] = fmax(prm.h_min, fmin(s->pos[4 * (size_t)i + 3], prm.h_max));
+        }
+        Particle& q = P[i];
+        q.x = s->pos[4 * (size_t)i]; q.y = s->pos[4 * (size_t)i + 1]; q.z = s->pos[4 * (size_t)i + 2]; q.h = s->pos[4 * (size_t)i + 3];
+        q.vx = s->vel[4 * (size_t)i]; q.vy = s->vel[4 * (size_t)i + 1]; q.vz = s->vel[4 * (size_t)i + 2];
+        q.m = s->mass[i]; q.rho = s->rho[i]; q.cs = cs;
+        const double r2 = 1. / (q.rho * q.rho);
+        q.P = p * r2; q.vol = q.m / q.rho;
+        for (int k = 0; k < 5; ++k) q.Sr[k] = S[k] * r2;
+        q.grp = (hasReduce && reduce == 0.) ? -1 : (int)s->flag[i];
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        Accum acc;
+        accumZero(acc);
+        for (uint64_t k = off[i]; k < off[i + 1]; ++k) {
+            const Particle& pj = P[idx[k]];
+            const double dx = P[i].x - pj.x, dy = P[i].y - pj.y, dz = P[i].z - pj.z;
+            double d2, hbar;
+            if (!isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar)) continue;
+            pairAccumulate<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, acc);
+        }
+        double S[5] = { 0, 0, 0, 0, 0 };
+        if (SOLID) {
+            for (int k = 0; k < 5; ++k) S[k] = s->S[5 * (size_t)i + k];
+        }
+        Derivs o;
+        finalizeParticle<SOLID, CORRECTED>(prm, mats[matid[i]], acc, P[i].h, P[i].rho, s->p[i], P[i].cs, hasReduce ? s->reduce[i] : 1., S, o);
+        s->acc[4 * (size_t)i] = o.ax; s->acc[4 * (size_t)i + 1] = o.ay; s->acc[4 * (size_t)i + 2] = o.az; s->acc[4 * (size_t)i + 3] = 0.;
+        s->vel[4 * (size_t)i + 3] = o.vh;
+        s->du[i] = o.du; s->drho[i] = o.drho; s->divv[i] = o.divv; s->ncnt[i] = o.ncnt;
+        if (SOLID) {
+            for (int k = 0; k < 5; ++k) s->dS[5 * (size_t)i + k] = o.dS[k];
+            for (int k = 0; k < 6; ++k) s->gradv[6 * (size_t)i + k] = o.gradv[k];
+            if (CORRECTED) {
+                for (int k = 0; k < 6; ++k) s->corr[6 * (size_t)i + k] = o.corr[k];
+            }
+        }
+    }
+}
+
+extern "C" int hostcheck_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material* mats, uint32_t nmat,
+    const uint64_t* off, const uint32_t* idx) {
+    ParamsDev prm{};
+    prm.forces = cfg->forces; prm.flags = cfg->flags; prm.continuity_mode = cfg->continuity_mode; prm.lut_entries = cfg->lut_entries;
+    prm.kernel_radius = cfg->kernel_radius; prm.radius_sqr = cfg->kernel_radius * cfg->kernel_radius;
+    prm.q_sqr_to_idx = (double)cfg->lut_entries * (1. / (cfg->kernel_radius * cfg->kernel_radius));
+    prm.av_alpha = cfg->av_alpha; prm.av_beta = cfg->av_beta; prm.h_min = cfg->h_min; prm.h_max = cfg->h_max;
+    prm.neigh_enforcing = cfg->neigh_enforcing; prm.neigh_lower = cfg->neigh_lower; prm.neigh_upper = cfg->neigh_upper;
+    std::vector<MaterialDev> md(nmat);
+    std::vector<uint32_t> matid(s->n, 0);
+    bool hasReduce = false, hasDamage = false;
+    for (uint32_t m = 0; m < nmat; ++m) {
+        const sphgpu_material& a = mats[m];
+        MaterialDev& b = md[m];
+        b.eos = a.eos; b.yielding = a.yielding;
+        b.fracture = a.yielding == SPHGPU_YIELD_VON_MISES ? a.fracture : (uint32_t)SPHGPU_FRACTURE_NONE;
+        b.til_u0 = a.til_u0; b.til_uiv = a.til_uiv; b.til_ucv = a.til_ucv; b.til_a = a.til_a; b.til_b = a.til_b;
+        b.rho0 = a.rho0; b.til_A = a.til_A; b.til_B = a.til_B; b.til_alpha = a.til_alpha; b.til_beta = a.til_beta; b.gamma = a.gamma;
+        b.shear_modulus = a.shear_modulus; b.elasticity_limit = a.elasticity_limit; b.melt_energy = a.melt_energy;
+        b.young_modulus = a.young_modulus; b.d_min = a.d_min; b.d_max = a.d_max;
+        hasReduce |= (a.yielding == SPHGPU_YIELD_VON_MISES || a.yielding == SPHGPU_YIELD_ELASTIC);
+        hasDamage |= b.fracture != SPHGPU_FRACTURE_NONE;
+        for (uint32_t i = a.begin; i < a.end; ++i) matid[i] = m;
+    }
+    const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
+    const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
+    const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;
+    if (!solid) run<false, false, false>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else if (corrected && filter) run<true, true, true>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else if (corrected) run<true, true, false>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else if (filter) run<true, false, true>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else run<true, false, false>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    return 0;
+}

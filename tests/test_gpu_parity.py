@@ -1,0 +1,183 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path through the C ABI against (a) the committed
+golden vectors of the unmodified reference, (b) the plain-C oracle on seeded inputs, (c) the compiled reference itself
+(oracle/_ref, travels with the snapshot) at larger sizes.
+
+Bar (BASELINE.json north_star): neighbour lists bit-exact as sets; dv, drho, du, dS (and divv, gradv, C, dh/dt) within
+1e-10 relative, normalised per quantity with a floor of 1e-4 * max|q| (lattice sums cancel; see tests/test_oracle.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden, have_ref, run_ref
+from compare import assert_close
+from opensph_b200 import abi
+from opensph_b200.engine import Engine
+from oracle_port import OraclePort
+
+pytestmark = pytest.mark.gpu
+
+TOL, FLOOR = 1e-10, 1e-4
+DERIVS = ("acc", "du", "drho", "dS", "ddamage", "divv", "gradv", "corr", "vel")
+EXACT = ("p", "cs", "reduce", "S", "pos")
+STATE_IN = ("pos", "vel", "mass", "rho", "u", "p", "cs", "S", "damage", "reduce", "eps_min", "m_zero", "growth", "n_flaws", "flag")
+
+
+def gpu_integrate(snap, setup, variant=0):
+    n = len(snap["mass"])
+    eng = Engine(setup, n)
+    eng.set_variant(variant)
+    eng.upload_state(snap, STATE_IN)
+    stats = eng.integrate()
+    return eng, stats
+
+
+def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=TOL):
+    got = eng.download_state([k for k in names_exact + names_derivs + ("ncnt",) if k in ref])
+    assert np.array_equal(got["ncnt"], ref["ncnt"]), "NEIGHBOR_CNT differs"
+    assert stats.neigh_min == ref["ncnt"].min() and stats.neigh_max == ref["ncnt"].max()
+    assert stats.pair_count == int(ref["ncnt"].astype(np.int64).sum())
+    for k in names_exact:
+        if k in ref:
+            assert_close(k, got[k], ref[k], 1e-13, FLOOR)
+    for k in names_derivs:
+        if k in ref:
+            if k == "acc":
+                assert np.all(got[k][:, 3] == 0.0)
+            assert_close(k, got[k], ref[k], tol, FLOOR)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+def test_integrate_matches_golden(name, variant, lut):
+    i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
+    eng, stats = gpu_integrate(i, abi.setup_from_snapshot(i, lut), variant)
+    check_against(eng, stats, o)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+def test_neighbour_lists_bit_exact(name, lut):
+    i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
+    eng, _ = gpu_integrate(i, abi.setup_from_snapshot(i, lut))
+    off, idx = eng.neighbours()
+    assert np.array_equal(off, o["nbr_offsets"])
+    assert np.array_equal(idx, o["nbr_idx"])
+    eng.close()
+
+
+@pytest.mark.parametrize("name,integrator", [("collision_pc3", "pc"), ("hello_pc3", "pc"), ("fluid_euler3", "euler")])
+def test_time_steps_match_golden(name, integrator, lut):
+    base = name.split("_")[0]
+    i, o = golden(f"{base}_in.snap"), golden(f"{name}.snap")
+    setup = abi.setup_from_snapshot(i, lut)
+    consts = abi.run_constants(i)
+    eng = Engine(setup, len(i["mass"]))
+    eng.upload_state(i, STATE_IN + ("acc", "drho", "du", "dS", "ddamage"))
+    eng.set_last_timestep(consts["initial_dt"])
+    dts = o["dt_history"]
+    for s in range(len(dts) - 1):
+        if integrator == "pc":
+            dt, _, _ = eng.step_pc(float(dts[s]), consts["max_dt"])
+        else:
+            eng.integrate()
+            eng.euler(float(dts[s]))
+            dt, _ = eng.compute_timestep(consts["max_dt"])
+        assert abs(dt - dts[s + 1]) <= 1e-9 * dts[s + 1], (s, dt, dts[s + 1])
+    got = eng.download_state([k for k in ("pos", "vel", "rho", "u", "S", "damage", "acc", "du", "drho", "dS") if k in o])
+    for k, v in got.items():
+        assert_close(k, v, o[k], 1e-9, FLOOR)
+    eng.close()
+
+
+def test_ghost_particles_are_neighbours_only(lut):
+    """Owned particles + appended ghosts (halo) reproduce the single-domain derivatives of the owned ones."""
+    i, o = golden("hello_in.snap"), golden("hello_out.snap")
+    n = len(i["mass"])
+    owned = np.where(i["pos"][:, 0] < 0)[0]
+    ghost = np.where(i["pos"][:, 0] >= 0)[0]
+    perm = np.concatenate([owned, ghost])
+    part = {k: (v[perm] if (hasattr(v, "shape") and v.shape[:1] == (n,)) else v) for k, v in i.items()}
+    setup = abi.setup_from_snapshot(i, lut)
+    setup.materials[0].begin, setup.materials[0].end = 0, len(owned)
+    eng = Engine(setup, len(owned), capacity=n)
+    own = {k: v[: len(owned)] for k, v in part.items() if k in STATE_IN}
+    gh = {k: v[len(owned):] for k, v in part.items() if k in STATE_IN}
+    eng.upload_state(own, STATE_IN)
+    eng.upload_state(gh, STATE_IN, first=len(owned))
+    eng.upload("MATERIAL_ID", 0, np.zeros(len(ghost), np.uint32), first=len(owned))
+    eng.set_active(n)
+    eng.integrate()
+    got = eng.download_state(["acc", "du", "drho", "dS", "divv", "ncnt"])
+    assert np.array_equal(got["ncnt"], o["ncnt"][owned])
+    for k in ("acc", "du", "drho", "dS", "divv"):
+        assert_close(k, got[k], o[k][owned], TOL, FLOOR)
+    eng.close()
+
+
+def test_variants_agree_on_seeded_random_input(lut):
+    """Direct and tiled kernels on a seeded random cloud (ragged cells, strongly varying h) against the oracle."""
+    rng = np.random.default_rng(1234)
+    i = golden("collision_in.snap")
+    n = len(i["mass"])
+    snap = dict(i)
+    snap["pos"] = i["pos"].copy()
+    snap["pos"][:, :3] += rng.normal(0, 0.4, (n, 3)) * i["pos"][:, 3:4]
+    snap["pos"][:, 3] *= rng.uniform(0.6, 1.8, n)
+    setup = abi.setup_from_snapshot(i, lut)
+    orc = OraclePort(snap, setup)
+    orc.integrate()
+    for variant in (0, 1):
+        eng, stats = gpu_integrate(snap, setup, variant)
+        check_against(eng, stats, orc.a)
+        eng.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args", [
+    ["--config", "hello", "--n", 10000, "--solver", "asym"],                       # BASELINE configs[0]
+    ["--config", "collision_preset", "--n", 100000, "--jitter", 21],               # configs[1] scale, jittered
+    ["--config", "collision", "--n", 100000, "--solver", "asym"],                  # configs[1], examples/04 settings
+    ["--config", "preset", "--n", 200000],                                         # configs[2] family
+    ["--config", "preset_const_h", "--n", 30000, "--jitter", 5],
+    ["--config", "fluid", "--n", 100000, "--jitter", 22],                          # configs[4] family
+])
+def test_against_live_reference(args, tmp_path):
+    i, o = run_ref(str(tmp_path), args + ["--neighbours"])
+    eng, stats = gpu_integrate(i, abi.setup_from_snapshot(i))
+    check_against(eng, stats, o)
+    off, idx = eng.neighbours()
+    assert np.array_equal(off, o["nbr_offsets"]) and np.array_equal(idx, o["nbr_idx"])
+    eng.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_predictor_corrector_against_live_reference(tmp_path):
+    args = ["--config", "collision_preset", "--n", 20000, "--steps", 5]
+    i, o = run_ref(str(tmp_path), args)
+    setup = abi.setup_from_snapshot(i)
+    consts = abi.run_constants(i)
+    eng = Engine(setup, len(i["mass"]))
+    eng.upload_state(i, STATE_IN + ("acc", "drho", "du", "dS", "ddamage"))
+    eng.set_last_timestep(consts["initial_dt"])
+    dts = o["dt_history"]
+    for s in range(len(dts) - 1):
+        dt, _, _ = eng.step_pc(float(dts[s]), consts["max_dt"])
+        assert abs(dt - dts[s + 1]) <= 1e-9 * dts[s + 1]
+    got = eng.download_state(["pos", "vel", "rho", "u", "S", "damage"])
+    for k, v in got.items():
+        assert_close(k, v, o[k], 1e-9, FLOOR)
+    eng.close()
+
+
+def test_empty_and_tiny_inputs(lut):
+    """Edge cases the reference's finder tests cover (finders/test/Finders.cpp:23-54): empty storage, single particle."""
+    i = golden("fluid_in.snap")
+    for n in (0, 1, 2):
+        setup = abi.setup_from_snapshot(i, lut)
+        setup.materials[0].begin, setup.materials[0].end = 0, n
+        eng = Engine(setup, n)
+        eng.upload_state({k: v[:n] for k, v in i.items() if k in STATE_IN}, STATE_IN)
+        if n == 0:
+            eng.upload("MASS", 0, np.zeros(0))
+        st = eng.integrate()
+        assert st.pair_count == 0 or n == 2
+        eng.close()
