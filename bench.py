@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- SPH particle-updates/s of the collision-preset step (find + derivatives + integrate + dt criteria).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (through the C ABI)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref/sph_ref)
+
+One step = one PredictorCorrector step of BASELINE.json's collision preset (AsymmetricSolver terms: pressure + solid
+stress + standard AV + continuity + adaptive h + correction tensor; Tillotson/von Mises/Grady-Kipp basalt) on a
+synthetic hexagonal-lattice basalt sphere. `value` keeps the state resident in HBM; `e2e` moves the state host ->
+device and back every step through the same C-ABI calls. With N > 1 ranks the sphere is cut into N slabs of equal
+particle count (strong scaling), ghost layers are exchanged over NCCL every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SPH particle-updates/s (find+derivs+integrate, collision preset)"
+UNIT = "particle-updates/s"
+# Algorithmic HBM bytes per particle-update, SURVEY.md section 8(d), solid + correction tensor:
+BYTES_FULL_STEP = 1412.0      # full PredictorCorrector step
+BYTES_INTEGRATE = 628.0       # find + derivatives (integrate() only)
+BYTES_PAIR_KERNEL = 440.0     # dominant kernel, itemised in DESIGN.md (sorted record in, derivatives out)
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = float(s[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+
+
+def run_reference(args, n_sample: int):
+    """Times the unmodified reference (AsymmetricSolver + KdTree + PredictorCorrector on all host threads) on a bounded
+    sample of the same configuration. Returns the JSON fields of the reference's run."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "sph_ref")
+    if not os.path.exists(exe):
+        return None
+    cmd = [exe, "bench", "--config", "preset", "--n", str(n_sample), "--steps", str(args.steps), "--warmup",
+           str(max(args.warmup, 1)), "--threads", "0"]
+    out = subprocess.check_output(cmd, text=True)
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = min(args.n, 1_000_000)
+    t0 = time.time()
+    r = run_reference(args, n_sample)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/sph_ref was not built (needs /root/reference)"}))
+        return
+    value = r["particle_updates_per_s"]
+    sample = (f"collision preset, {r['particles']} particles (hex lattice, eta 1.3, {r['neigh_mean']:.1f} mean neighbours), "
+              f"{args.steps} PredictorCorrector steps, AsymmetricSolver + KdTree, {r['threads']} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"collision_preset_{args.n}", "sample_particles": r["particles"], "finder": "kd_tree",
+                   "threads": r["threads"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }))
+
+
+STATE_NAMES = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "damage", "ddamage", "reduce",
+               "eps_min", "m_zero", "growth", "n_flaws", "flag")
+STEP_INPUTS = ("pos", "vel", "rho", "u", "S", "damage")     # what a host-resident Storage hands over every step
+STEP_OUTPUTS = ("pos", "vel", "rho", "u", "S", "damage")    # the advanced state read back
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000, help="target particle count of the lattice (configs[3])")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fluid", action="store_true", help="fluid-only terms (BASELINE configs[4])")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    from opensph_b200 import workloads
+    from opensph_b200.engine import Engine
+    from opensph_b200 import decomp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    solid = not args.fluid
+    dt = 1.0e-6  # tiny fixed step: the lattice stays intact, every step does the same work (same as sph_ref bench)
+
+    # ---- workload -------------------------------------------------------------------------------------------
+    dom = decomp.SlabDomain(args.n, world, rank, solid=solid)
+    state = dom.generate_owned()
+    n_owned = len(state["mass"])
+    setup = workloads.make_setup(n_owned, solid=solid)
+    eng = Engine(setup, n_owned, capacity=dom.capacity(n_owned), device=local)
+    eng.set_variant(args.variant)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.upload_state(state, STATE_NAMES)
+    halo = decomp.HaloExchange(dom, eng, state) if world > 1 else None
+    n_total = dom.total_particles(n_owned)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def one_step():
+        if halo is None:
+            return eng.step_pc(dt, dt)
+        # multi-GPU: ghosts must carry the PREDICTED state, so the step is issued in its parts
+        eng.predict(dt)
+        halo.exchange()
+        st = eng.integrate()
+        eng.correct(dt)
+        new_dt, crit = eng.compute_timestep(dt)
+        t = torch.tensor([new_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # global time step = min over ranks
+        return float(t.item()), crit, st
+
+    for _ in range(args.warmup):
+        one_step()
+
+    # ---- timed region: state resident in HBM -------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pair_ms, launches, timings = 0.0, 0, np.zeros(4)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        _, _, st = one_step()
+        tm = eng.last_timings()
+        timings += tm
+        pair_ms += tm[2]
+        launches += st.kernel_launches
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    neigh_mean = st.neigh_mean
+
+    tsec = torch.tensor([max(wall, dev_s)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+    step_s = float(tsec.item()) / args.steps
+    value = n_total / step_s
+
+    # ---- e2e: host-resident state, H2D + step + D2H every step ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pinned_in = {k: torch.from_numpy(np.ascontiguousarray(state[k])).pin_memory() for k in STEP_INPUTS if k in state}
+        pinned_out = {k: torch.empty_like(v).pin_memory() for k, v in pinned_in.items()}
+        h2d = sum(v.numel() * v.element_size() for v in pinned_in.values())
+        d2h = sum(v.numel() * v.element_size() for v in pinned_out.values())
+
+        def e2e_step():
+            eng.upload_state({k: v.numpy() for k, v in pinned_in.items()}, STEP_INPUTS)
+            one_step()
+            for k, v in pinned_out.items():
+                q, order = __import__("opensph_b200").abi.SNAPSHOT_FIELDS[k]
+                eng.download(q, order, out=v.numpy())
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(3, min(args.steps, 5))
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total / (float(te.item()) / k_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": k_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = read_peaks()
+    pair_s = pair_ms * 1e-3 / args.steps
+    bytes_pair = (BYTES_PAIR_KERNEL if solid else 230.0) * n_owned
+    achieved = bytes_pair / pair_s / 1e9 if pair_s > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": ("fluid_" if args.fluid else "collision_preset_") + str(args.n), "particles": int(n_total),
+                   "particles_per_gpu": int(n_owned), "mean_neighbours": round(float(neigh_mean), 2), "integrator": "predictor_corrector",
+                   "dt": dt, "l2": "inputs larger than L2 (state %.1f GB per GPU)" % (n_owned * 464 / 1e9),
+                   "decomposition": "x-slabs of equal particle count + NCCL halo exchange" if world > 1 else "single domain",
+                   "pair_variant": args.variant},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "k_pair (fused neighbour search + pair sums + finalizers)",
+                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " HBM copy GB/s", "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "kernel_ms": pair_s * 1e3, "kernel_share_of_step": pair_s / step_s,
+                     "step_hbm_frac": BYTES_FULL_STEP * (n_owned / step_s) / 1e9 / peak,
+                     "note": "pair kernel is FP64-pipe bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},
+        "phase_ms": {"grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
+                     "pair_kernel": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference(argparse.Namespace(steps=2, warmup=1, n=args.n), min(args.n, 1_000_000))
+            if r is not None:
+                out["cpu_baseline"] = {
+                    "value": r["particle_updates_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                    "sample": f"collision preset, {r['particles']} particles, 2 PredictorCorrector steps after 1 warm-up, "
+                              f"AsymmetricSolver + KdTree on {r['threads']} host threads (oracle/_ref/sph_ref)"}
+        except Exception as e:  # the baseline is reported, never required
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -199,10 +199,10 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     for (int u = 0; u < U_COUNT; ++u) {
         SPH_TRY(devAlloc(&ctx->d.u[u], cap));
     }
-    for (int s = 0; s < S_COUNT; ++s) {
-        SPH_TRY(devAlloc(&ctx->d.s[s], cap));
-    }
-    SPH_TRY(devAlloc(&ctx->d.sGrp, cap));
+    SPH_TRY(devAlloc(&ctx->d.rec, cap * (size_t)(ctx->solid ? REC_SOLID : REC_FLUID)));
+    ctx->maxSegs = capacity / 128 + ctx->maxCells + 2;
+    SPH_TRY(devAlloc(&ctx->d.segStart, (size_t)ctx->maxCells + 2));
+    SPH_TRY(devAlloc(&ctx->d.segRow, (size_t)ctx->maxSegs));
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
     SPH_TRY(devAlloc(&ctx->d.order, cap));
     SPH_TRY(devAlloc(&ctx->d.cellOf, cap));
@@ -247,8 +247,8 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
-    for (int s = 0; s < S_COUNT; ++s) cudaFree(ctx->d.s[s]);
-    cudaFree(ctx->d.sGrp); cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
+    cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.segRow);
+    cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree(ctx->staging);
     for (int k = 0; k < 6; ++k) {

@@ -60,64 +60,56 @@ __global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_
 
     const double rhoInv2 = 1. / (rho * rho);
     const double m = d.f[F_M][i];
-    d.s[S_X][t] = d.f[F_X][i];
-    d.s[S_Y][t] = d.f[F_Y][i];
-    d.s[S_Z][t] = d.f[F_Z][i];
-    d.s[S_H][t] = d.f[F_H][i];
-    d.s[S_VX][t] = d.f[F_VX][i];
-    d.s[S_VY][t] = d.f[F_VY][i];
-    d.s[S_VZ][t] = d.f[F_VZ][i];
-    d.s[S_M][t] = m;
-    d.s[S_RHO][t] = rho;
-    d.s[S_P][t] = p * rhoInv2;
-    d.s[S_CS][t] = cs;
+    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
+    double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * RD);
+    rec[0] = make_double2(d.f[F_X][i], d.f[F_Y][i]);
+    rec[1] = make_double2(d.f[F_Z][i], d.f[F_H][i]);
+    rec[2] = make_double2(d.f[F_VX][i], d.f[F_VY][i]);
+    rec[3] = make_double2(d.f[F_VZ][i], m);
+    rec[4] = make_double2(rho, p * rhoInv2);
+    rec[5] = make_double2(cs, m / rho);
     if (SOLID) {
-        d.s[S_VOL][t] = m / rho;
-        for (int k = 0; k < 5; ++k) {
-            d.s[S_S0 + k][t] = S[k] * rhoInv2;
-        }
-        d.sGrp[t] = (hasReduce && reduce == 0.) ? -1 : (int)d.u[U_FLAG][i];
+        rec[6] = make_double2(S[0] * rhoInv2, S[1] * rhoInv2);
+        rec[7] = make_double2(S[2] * rhoInv2, S[3] * rhoInv2);
+        const int grp = (hasReduce && reduce == 0.) ? -1 : (int)d.u[U_FLAG][i];
+        rec[8] = make_double2(S[4] * rhoInv2, __hiloint2double(0, grp));
     }
     d.sCell[t] = d.cellOf[i];
 }
 
 // Sorted positions only (neighbour-list inspection; does not touch the particle state).
-__global__ void __launch_bounds__(256) k_pack_positions(DevicePointers d, uint32_t nActive) {
+__global__ void __launch_bounds__(256) k_pack_positions(DevicePointers d, uint32_t nActive, int recDoubles) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nActive) {
         return;
     }
     const uint32_t i = d.order[t];
-    d.s[S_X][t] = d.f[F_X][i];
-    d.s[S_Y][t] = d.f[F_Y][i];
-    d.s[S_Z][t] = d.f[F_Z][i];
-    d.s[S_H][t] = d.f[F_H][i];
+    double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * recDoubles);
+    rec[0] = make_double2(d.f[F_X][i], d.f[F_Y][i]);
+    rec[1] = make_double2(d.f[F_Z][i], d.f[F_H][i]);
     d.sCell[t] = d.cellOf[i];
+}
+
+/// Unpacks one neighbour-input record (global or shared memory, 16-byte aligned).
+template <bool SOLID>
+__device__ __forceinline__ void loadRecord(const double* __restrict__ recPtr, Particle& p) {
+    const double2* r = reinterpret_cast<const double2*>(recPtr);
+    const double2 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
+    p.x = a.x; p.y = a.y; p.z = b.x; p.h = b.y;
+    p.vx = c.x; p.vy = c.y; p.vz = e.x; p.m = e.y;
+    p.rho = f.x; p.P = f.y; p.cs = g.x; p.vol = g.y;
+    if (SOLID) {
+        const double2 s0 = r[6], s1 = r[7], s2 = r[8];
+        p.Sr[0] = s0.x; p.Sr[1] = s0.y; p.Sr[2] = s1.x; p.Sr[3] = s1.y; p.Sr[4] = s2.x;
+        p.grp = __double2loint(s2.y);
+    } else {
+        p.grp = 0;
+    }
 }
 
 template <bool SOLID>
 __device__ __forceinline__ void loadSorted(const DevicePointers& d, uint32_t t, Particle& p) {
-    p.x = d.s[S_X][t];
-    p.y = d.s[S_Y][t];
-    p.z = d.s[S_Z][t];
-    p.h = d.s[S_H][t];
-    p.vx = d.s[S_VX][t];
-    p.vy = d.s[S_VY][t];
-    p.vz = d.s[S_VZ][t];
-    p.m = d.s[S_M][t];
-    p.rho = d.s[S_RHO][t];
-    p.P = d.s[S_P][t];
-    p.cs = d.s[S_CS][t];
-    if (SOLID) {
-        p.vol = d.s[S_VOL][t];
-        for (int k = 0; k < 5; ++k) {
-            p.Sr[k] = d.s[S_S0 + k][t];
-        }
-        p.grp = d.sGrp[t];
-    } else {
-        p.vol = 0.;
-        p.grp = 0;
-    }
+    loadRecord<SOLID>(d.rec + (size_t)t * (SOLID ? REC_SOLID : REC_FLUID), p);
 }
 
 template <bool SOLID, bool CORRECTED>
@@ -186,9 +178,11 @@ __global__ void __launch_bounds__(128) k_pair_direct(DevicePointers d, uint32_t 
                     if (k == t) {
                         continue;
                     }
-                    const double dx = pi.x - d.s[S_X][k], dy = pi.y - d.s[S_Y][k], dz = pi.z - d.s[S_Z][k];
+                    const double2* rk = reinterpret_cast<const double2*>(d.rec + (size_t)k * (SOLID ? REC_SOLID : REC_FLUID));
+                    const double2 pxy = rk[0], pzh = rk[1];
+                    const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
                     double d2, hbar;
-                    if (!isNeighbour(dx, dy, dz, pi.h, d.s[S_H][k], c_prm.kernel_radius, d2, hbar)) {
+                    if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
                         continue;
                     }
                     Particle pj;
@@ -214,7 +208,7 @@ __global__ void __launch_bounds__(128) k_pair_direct(DevicePointers d, uint32_t 
 // ---- neighbour lists for the tests ---------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint32_t nActive, uint32_t nOwned, uint32_t* counts,
-    const unsigned long long* offsets, uint32_t* idx) {
+    const unsigned long long* offsets, uint32_t* idx, int recDoubles) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nActive) {
         return;
@@ -224,7 +218,8 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint3
         return;
     }
     const GridDev g = *d.grid;
-    const double xi = d.s[S_X][t], yi = d.s[S_Y][t], zi = d.s[S_Z][t], hi = d.s[S_H][t];
+    const double2* ri = reinterpret_cast<const double2*>(d.rec + (size_t)t * recDoubles);
+    const double xi = ri[0].x, yi = ri[0].y, zi = ri[1].x, hi = ri[1].y;
     const uint32_t c = d.sCell[t];
     const int cx = (int)(c % (uint32_t)g.dim[0]);
     const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
@@ -240,8 +235,10 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint3
                 if (k == t) {
                     continue;
                 }
+                const double2* rk = reinterpret_cast<const double2*>(d.rec + (size_t)k * recDoubles);
+                const double2 pxy = rk[0], pzh = rk[1];
                 double d2, hbar;
-                if (!isNeighbour(xi - d.s[S_X][k], yi - d.s[S_Y][k], zi - d.s[S_Z][k], hi, d.s[S_H][k], c_prm.kernel_radius, d2, hbar)) {
+                if (!isNeighbour(xi - pxy.x, yi - pxy.y, zi - pzh.x, hi, pzh.y, c_prm.kernel_radius, d2, hbar)) {
                     continue;
                 }
                 if (FILL) {
@@ -277,7 +274,7 @@ int launchProloguePackPositionsOnly(sphgpu_ctx* ctx) {
     if (n == 0) {
         return SPHGPU_OK;
     }
-    k_pack_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n);
+    k_pack_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n, ctx->solid ? REC_SOLID : REC_FLUID);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
@@ -321,7 +318,7 @@ int launchNeighbourCount(sphgpu_ctx* ctx, uint32_t* countsDev) {
     if (n == 0) {
         return SPHGPU_OK;
     }
-    k_neighbour_lists<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, countsDev, nullptr, nullptr);
+    k_neighbour_lists<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, countsDev, nullptr, nullptr, ctx->solid ? REC_SOLID : REC_FLUID);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
@@ -331,7 +328,7 @@ int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, u
     if (n == 0) {
         return SPHGPU_OK;
     }
-    k_neighbour_lists<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, nullptr, offsetsDev, idxDev);
+    k_neighbour_lists<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, nullptr, offsetsDev, idxDev, ctx->solid ? REC_SOLID : REC_FLUID);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }

@@ -33,10 +33,15 @@ enum Field : int {
 
 enum UField : int { U_NFLAWS, U_FLAG, U_MATID, U_NCNT, U_COUNT };
 
-// Sorted neighbour-input planes, rebuilt every integrate() in cell order.
-enum SField : int {
-    S_X, S_Y, S_Z, S_H, S_VX, S_VY, S_VZ, S_M, S_RHO, S_P, S_CS, S_VOL, S_S0, S_S1, S_S2, S_S3, S_S4, S_COUNT
+// Sorted neighbour-input records (array of structures, rebuilt every integrate() in cell order). One record is what a
+// particle contributes as a neighbour: {x,y | z,h | vx,vy | vz,m | rho,P | cs,vol | Sr0,Sr1 | Sr2,Sr3 | Sr4,grp} with
+// P = p/rho^2, Sr = S/rho^2, vol = m/rho, grp = body flag or -1 (fully damaged) stored in the low word of the last
+// double. Fluid runs use the first 12 doubles only. 16-byte aligned so a record moves as double2 (LDG.128 / LDS.128).
+enum RecField : int {
+    R_X, R_Y, R_Z, R_H, R_VX, R_VY, R_VZ, R_M, R_RHO, R_P, R_CS, R_VOL, R_S0, R_S1, R_S2, R_S3, R_S4, R_GRP, R_SOLID_COUNT
 };
+constexpr int REC_SOLID = 18; // doubles per record, solid
+constexpr int REC_FLUID = 12; // doubles per record, fluid (x..vol)
 
 struct GridDev {
     double lo[3];
@@ -58,8 +63,7 @@ struct TimestepDev {
 struct DevicePointers {
     double* f[F_COUNT];
     uint32_t* u[U_COUNT];
-    double* s[S_COUNT];
-    int* sGrp;          // sorted: body flag, or -1 when reduce == 0
+    double* rec;        // sorted neighbour-input records, REC_SOLID or REC_FLUID doubles each
     uint32_t* sCell;    // sorted: linear cell index
     uint32_t* order;    // sorted position -> slot
     uint32_t* cellOf;   // slot -> cell
@@ -67,6 +71,8 @@ struct DevicePointers {
     uint32_t* cellStart; // [maxCells + 1] exclusive prefix of counts
     uint32_t* cellCount; // [maxCells + 1]
     uint32_t* scanBlock; // block sums of the scan
+    uint32_t* segStart;  // [maxCells + 1] exclusive prefix of the number of 128-target segments per cell row
+    uint32_t* segRow;    // [maxSegs] row of every segment (work list of the tiled pair kernel)
     double* boundsPartial; // [BOUNDS_BLOCKS * 8]
     const double* lut;
     GridDev* grid;
@@ -82,7 +88,7 @@ constexpr int SCAN_ITEMS = 4096;     // items per scan block
 
 struct sphgpu_ctx {
     int device = 0;
-    uint32_t n = 0, capacity = 0, nActive = 0, maxCells = 0, scanBlocks = 0;
+    uint32_t n = 0, capacity = 0, nActive = 0, maxCells = 0, scanBlocks = 0, maxSegs = 0;
     sph::ParamsDev prm{};
     sph::MaterialDev matsHost[sph::MAX_MATERIALS];
     sphgpu_material matsApi[sph::MAX_MATERIALS];
@@ -117,6 +123,7 @@ void setError(const std::string& msg);
 
 // grid.cu
 int launchGridBuild(sphgpu_ctx* ctx);
+int launchSegments(sphgpu_ctx* ctx);
 // pair.cu
 int launchProloguePack(sphgpu_ctx* ctx);
 int launchProloguePackPositionsOnly(sphgpu_ctx* ctx);

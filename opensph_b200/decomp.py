@@ -1,0 +1,215 @@
+"""Multi-GPU domain decomposition for the asymmetric SPH evaluation: one process per GPU, particles sharded by
+position, ghost (halo) particles exchanged once per derivative evaluation.
+
+The reference has no distributed path (shared-memory parallelFor only). The asymmetric formulation writes
+only to particle i and reads neighbour inputs, so one exchange of the neighbour inputs per integrate() suffices
+(SURVEY 8e); ghosts are appended after the owned particles -- the analogue of GhostParticles on the CPU
+(core/sph/boundary/Boundary.h:73-) -- and are never targets.
+
+Round-1 decomposition: slabs along x with equal particle counts (a 1-D space-filling curve). Each rank keeps its
+slots ordered [left band | interior | right band], so the particles a neighbour needs are two contiguous slot ranges
+and packing is a plain range copy (sphgpu_download_device). The dynamic neighbour inputs (r,h | v | rho | u | S | D) are
+exchanged with NCCL point-to-point every step; static ones (m, flag, material) once.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi, workloads
+
+# (snapshot name, components) of the neighbour inputs
+DYNAMIC_FIELDS: Tuple[Tuple[str, int], ...] = (("pos", 4), ("vel", 4), ("rho", 1), ("u", 1), ("S", 5), ("damage", 1))
+STATIC_FIELDS: Tuple[Tuple[str, int], ...] = (("mass", 1),)
+STATIC_U32: Tuple[str, ...] = ("flag",)
+
+
+def sphere_cut_planes(radius: float, parts: int) -> np.ndarray:
+    """x positions cutting a sphere into `parts` slabs of equal volume (parts+1 values, -R .. R)."""
+    def frac(x):  # volume fraction of the cap [-R, x]
+        return (3.0 * radius * radius * (x + radius) - (x ** 3 + radius ** 3)) / (4.0 * radius ** 3)
+    cuts = [-radius]
+    for k in range(1, parts):
+        lo, hi = -radius, radius
+        for _ in range(200):
+            mid = 0.5 * (lo + hi)
+            if frac(mid) < k / parts:
+                lo = mid
+            else:
+                hi = mid
+        cuts.append(0.5 * (lo + hi))
+    cuts.append(radius)
+    return np.array(cuts)
+
+
+def band_partition(x: np.ndarray, lo_plane: Optional[float], hi_plane: Optional[float], width: float):
+    """Stable permutation ordering particles [left band | interior | right band] and the two band sizes.
+
+    Left band = particles within `width` of the lower cut plane (needed by the left neighbour), right band likewise.
+    A missing neighbour (plane None) gives an empty band."""
+    left = (x < lo_plane + width) if lo_plane is not None else np.zeros(len(x), bool)
+    right = (x >= hi_plane - width) if hi_plane is not None else np.zeros(len(x), bool)
+    if np.any(left & right):
+        raise ValueError("slab thinner than the halo width: use fewer ranks or more particles")
+    group = np.where(left, 0, np.where(right, 2, 1))
+    perm = np.argsort(group, kind="stable")
+    return perm, int(left.sum()), int(right.sum())
+
+
+class SlabDomain:
+    """Geometry of the basalt-sphere workload cut into x-slabs; every rank generates only its own lattice points."""
+
+    def __init__(self, n_target: int, world: int, rank: int, radius: float = 5.0e4, solid: bool = True):
+        self.n_target, self.world, self.rank, self.radius, self.solid = n_target, world, rank, radius, solid
+        self.cuts = sphere_cut_planes(radius, world)
+        volume = 4.0 / 3.0 * math.pi * radius ** 3
+        self.h = (volume / n_target) ** (1.0 / 3.0) * workloads.BASALT["eta"]
+        self.halo_width = 2.0 * self.h * 1.05  # kernel radius * h_max with head-room for adaptive h
+        self.lo_plane = float(self.cuts[rank]) if rank > 0 else None
+        self.hi_plane = float(self.cuts[rank + 1]) if rank < world - 1 else None
+        self.n_left = self.n_right = 0
+        self._n_total: Optional[int] = None
+
+    def generate_owned(self) -> Dict[str, np.ndarray]:
+        lo = self.lo_plane if self.lo_plane is not None else -2.0 * self.radius
+        hi = self.hi_plane if self.hi_plane is not None else 2.0 * self.radius
+        x_range = None if self.world == 1 else (lo, hi)
+        pos, _ = workloads.hexagonal_sphere(self.n_target, self.radius, x_range=x_range)
+        n_total = self.total_particles(len(pos))
+        state = workloads.basalt_sphere_state(self.n_target, self.radius, self.solid, x_range=x_range, total_hint=n_total)
+        if self.world > 1:
+            perm, self.n_left, self.n_right = band_partition(state["pos"][:, 0], self.lo_plane, self.hi_plane, self.halo_width)
+            state = {k: (v[perm] if isinstance(v, np.ndarray) and v.shape[:1] == (len(perm),) else v) for k, v in state.items()}
+        return state
+
+    def total_particles(self, n_owned: int) -> int:
+        if self._n_total is None:
+            if self.world == 1:
+                self._n_total = n_owned
+            else:
+                import torch
+                import torch.distributed as dist
+                t = torch.tensor([n_owned], dtype=torch.int64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+                dist.all_reduce(t)
+                self._n_total = int(t.item())
+        return self._n_total
+
+    def capacity(self, n_owned: int) -> int:
+        if self.world == 1:
+            return n_owned
+        density = self.n_target * 1.07 / (4.0 / 3.0 * math.pi * self.radius ** 3)
+        per_face = math.pi * self.radius ** 2 * self.halo_width * density
+        return n_owned + int(2.2 * per_face) + 1024
+
+
+class EngineAdapter:
+    """Packs / unpacks slot ranges of a device engine into flat float64 torch tensors on the GPU."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def new_buffer(self, doubles: int):
+        import torch
+        return torch.empty(max(doubles, 1), dtype=torch.float64, device="cuda")
+
+    def pack(self, fields: Sequence[Tuple[str, int]], first: int, count: int, buf) -> None:
+        off = 0
+        for name, ncomp in fields:
+            q, order = abi.SNAPSHOT_FIELDS[name]
+            self.eng.download_device(q, order, buf.data_ptr() + 8 * off, first, count)
+            off += ncomp * count
+
+    def unpack(self, fields: Sequence[Tuple[str, int]], first: int, count: int, buf) -> None:
+        off = 0
+        for name, ncomp in fields:
+            q, order = abi.SNAPSHOT_FIELDS[name]
+            self.eng.upload_device(q, order, buf.data_ptr() + 8 * off, first, count)
+            off += ncomp * count
+
+
+class HaloExchange:
+    """Ghost-layer exchange between slab neighbours (rank-1, rank+1) with torch.distributed point-to-point."""
+
+    def __init__(self, dom: SlabDomain, eng, state: Dict[str, np.ndarray], adapter=None, fields=DYNAMIC_FIELDS):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.torch = dist, torch
+        self.dom, self.eng = dom, eng
+        self.adapter = adapter or EngineAdapter(eng)
+        self.n = len(state["mass"])
+        self.fields = tuple((k, c) for k, c in fields if k in state)
+        self.width = sum(c for _, c in self.fields)
+        self.left, self.right = (dom.rank - 1 if dom.rank > 0 else None), (dom.rank + 1 if dom.rank < dom.world - 1 else None)
+        # how many ghosts arrive from each side: the neighbour's band facing us
+        counts = self._exchange_counts(dom.n_left, dom.n_right)
+        self.g_left, self.g_right = counts
+        self.ghost_left_first = self.n
+        self.ghost_right_first = self.n + self.g_left
+        self.n_active = self.n + self.g_left + self.g_right
+        if self.n_active > eng.capacity:
+            raise ValueError(f"ghost capacity too small: need {self.n_active}, have {eng.capacity}")
+        self.send_l = self.adapter.new_buffer(self.width * dom.n_left)
+        self.send_r = self.adapter.new_buffer(self.width * dom.n_right)
+        self.recv_l = self.adapter.new_buffer(self.width * self.g_left)
+        self.recv_r = self.adapter.new_buffer(self.width * self.g_right)
+        self.bytes_per_exchange = 8 * self.width * (dom.n_left + dom.n_right)
+        self._static(state)
+        eng.set_active(self.n_active)
+
+    def _exchange_counts(self, n_left: int, n_right: int) -> Tuple[int, int]:
+        torch, dist = self.torch, self.dist
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor([n_left, n_right], dtype=torch.int64, device=dev)
+        allc = [torch.zeros_like(mine) for _ in range(self.dom.world)]
+        dist.all_gather(allc, mine)
+        g_left = int(allc[self.left][1].item()) if self.left is not None else 0
+        g_right = int(allc[self.right][0].item()) if self.right is not None else 0
+        return g_left, g_right
+
+    def _p2p(self, send_l, send_r, recv_l, recv_r) -> None:
+        dist = self.dist
+        ops = []
+        if self.left is not None:
+            if send_l.numel() and self.dom.n_left:
+                ops.append(dist.P2POp(dist.isend, send_l, self.left))
+            if self.g_left:
+                ops.append(dist.P2POp(dist.irecv, recv_l, self.left))
+        if self.right is not None:
+            if send_r.numel() and self.dom.n_right:
+                ops.append(dist.P2POp(dist.isend, send_r, self.right))
+            if self.g_right:
+                ops.append(dist.P2POp(dist.irecv, recv_r, self.right))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _run(self, fields) -> None:
+        width = sum(c for _, c in fields)
+        nl, nr = self.dom.n_left, self.dom.n_right
+        sl, sr = self.send_l[: width * nl], self.send_r[: width * nr]
+        rl, rr = self.recv_l[: width * self.g_left], self.recv_r[: width * self.g_right]
+        if nl:
+            self.adapter.pack(fields, 0, nl, sl)
+        if nr:
+            self.adapter.pack(fields, self.n - nr, nr, sr)
+        self._p2p(sl, sr, rl, rr)
+        if self.g_left:
+            self.adapter.unpack(fields, self.ghost_left_first, self.g_left, rl)
+        if self.g_right:
+            self.adapter.unpack(fields, self.ghost_right_first, self.g_right, rr)
+
+    def _static(self, state) -> None:
+        fields = tuple((k, c) for k, c in STATIC_FIELDS if k in state)
+        if fields:
+            self._run(fields)
+        # flag / material id of the ghosts: single body, single material in the slab workloads
+        n_g = self.g_left + self.g_right
+        if n_g and hasattr(self.eng, "upload"):
+            self.eng.upload("FLAG", 0, np.zeros(n_g, np.uint32), first=self.n)
+            self.eng.upload("MATERIAL_ID", 0, np.zeros(n_g, np.uint32), first=self.n)
+
+    def exchange(self) -> None:
+        """Refreshes the dynamic neighbour inputs of all ghosts; call after predict and before integrate."""
+        self._run(self.fields)

@@ -37,7 +37,7 @@ def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=T
     assert stats.pair_count == int(ref["ncnt"].astype(np.int64).sum())
     for k in names_exact:
         if k in ref:
-            assert_close(k, got[k], ref[k], 1e-13, FLOOR)
+            assert_close(k, got[k], ref[k], 1e-12, FLOOR)  # (1 - D^3) cancels for D -> 1: a few hundred ulp
     for k in names_derivs:
         if k in ref:
             if k == "acc":
