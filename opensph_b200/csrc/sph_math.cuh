@@ -57,6 +57,23 @@ SPH_HD double sqr(double x) {
     return x * x;
 }
 
+/// Reciprocal of a positive normal double: hardware seed (MUFU.RCP64H, >= 20 bits) + two Newton steps. Within 1-2 ulp,
+/// and -- unlike the compiler's IEEE division -- free of the denormal/overflow fix-up branches, which would keep the
+/// scheduler from overlapping two pair bodies. On the host (formula tests) it is a plain division.
+SPH_HD double fastRcp(double a) {
+#ifdef __CUDA_ARCH__
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.);
+    x = fma(x, e, x);
+    return x;
+#else
+    return 1. / a;
+#endif
+}
+
 // ---- equation of state ---------------------------------------------------------------------------------
 
 SPH_HD void eosTillotson(const MaterialDev& m, double rho, double u, double& pOut, double& csOut) {
@@ -319,6 +336,84 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
                 acc.Cm[4] += vdx * dz;
                 acc.Cm[5] += vdy * dz;
             }
+        }
+    }
+}
+
+/// Branch-free variant of pairAccumulate used by the tiled kernel: `valid` (the exact neighbour predicate) scales the
+/// neighbour's mass / volume to zero instead of branching, and the AV condition is a select, so that two pairs can be
+/// interleaved by the scheduler (the per-pair chain 1/hbar -> q^2 -> LUT gather -> gradient is long).
+template <bool SOLID, bool CORRECTED, bool FILTER>
+SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict__ lut, const Particle& pi, const Particle& pj,
+    double dx, double dy, double dz, double d2, double hbar, bool valid, Accum& acc) {
+    acc.cnt += valid ? 1u : 0u;
+    const double mj = valid ? pj.m : 0.;
+    // one reciprocal serves 1/hbar (kernel) and 1/(D rhobar) (viscosity): inv = 1 / (hbar * D * rhobar)
+    const double rhobar = 0.5 * (pi.rho + pj.rho);
+    const double D = fma(1.e-2 * hbar, hbar, d2);
+    const double A = D * rhobar;
+    const double inv = fastRcp(hbar * A);
+    const double hInv = A * inv;
+    const double invA = hbar * inv;
+    const double hInv2 = hInv * hInv;
+    const double qSqr = d2 * hInv2;
+    const double fidx = prm.q_sqr_to_idx * qSqr;
+    uint32_t k = (uint32_t)fidx;
+    k = k < prm.lut_entries ? k : prm.lut_entries - 1;
+    const double ratio = fidx - (double)k;
+#ifdef __CUDA_ARCH__
+    const double g0 = __ldg(lut + k), g1 = __ldg(lut + k + 1);
+#else
+    const double g0 = lut[k], g1 = lut[k + 1];
+#endif
+    const double G = (qSqr < prm.radius_sqr) ? (g0 * (1. - ratio) + g1 * ratio) : 0.;
+    const double s = hInv2 * hInv2 * hInv * G;
+    const double gx = dx * s, gy = dy * s, gz = dz * s;
+    const double dvx = pj.vx - pi.vx, dvy = pj.vy - pi.vy, dvz = pj.vz - pi.vz;
+    const double dvg = dvx * gx + dvy * gy + dvz * gz;
+    const double mgx = mj * gx, mgy = mj * gy, mgz = mj * gz;
+    acc.divv += mj * dvg;
+    // StandardAV: mu = hbar w / D, Pi = (-alpha csbar mu + beta mu^2) / rhobar, only for approaching pairs (w < 0)
+    const double w = -(dvx * dx + dvy * dy + dvz * dz);
+    const double csbar = 0.5 * (pi.cs + pj.cs);
+    const double mu = hbar * w * rhobar * invA;
+    const double PiAv = (w < 0.) ? mu * fma(prm.av_beta, mu, -prm.av_alpha * csbar) * (D * invA) : 0.;
+    acc.du += 0.5 * PiAv * (-mj * dvg);
+    const double c = pi.P + pj.P + PiAv;
+    acc.ax -= c * mgx;
+    acc.ay -= c * mgy;
+    acc.az -= c * mgz;
+    if (SOLID) {
+        bool ok = true;
+        if (FILTER) {
+            ok = (pi.grp == pj.grp) && (pi.grp >= 0);
+        }
+        const double f = ok ? 1. : 0.;
+        const double fx = f * mgx, fy = f * mgy, fz = f * mgz;
+        const double sxx = pi.Sr[0] + pj.Sr[0], syy = pi.Sr[1] + pj.Sr[1], sxy = pi.Sr[2] + pj.Sr[2],
+                     sxz = pi.Sr[3] + pj.Sr[3], syz = pi.Sr[4] + pj.Sr[4];
+        const double szz = -sxx - syy;
+        acc.ax += sxx * fx + sxy * fy + sxz * fz;
+        acc.ay += sxy * fx + syy * fy + syz * fz;
+        acc.az += sxz * fx + syz * fy + szz * fz;
+        acc.T[0] += dvx * fx;
+        acc.T[1] += dvx * fy;
+        acc.T[2] += dvx * fz;
+        acc.T[3] += dvy * fx;
+        acc.T[4] += dvy * fy;
+        acc.T[5] += dvy * fz;
+        acc.T[6] += dvz * fx;
+        acc.T[7] += dvz * fy;
+        acc.T[8] += dvz * fz;
+        if (CORRECTED) {
+            const double vs = -(valid && ok ? pj.vol : 0.) * s;
+            const double vdx = vs * dx, vdy = vs * dy, vdz = vs * dz;
+            acc.Cm[0] += vdx * dx;
+            acc.Cm[1] += vdy * dy;
+            acc.Cm[2] += vdz * dz;
+            acc.Cm[3] += vdx * dy;
+            acc.Cm[4] += vdx * dz;
+            acc.Cm[5] += vdy * dz;
         }
     }
 }

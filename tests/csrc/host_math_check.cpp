@@ -7,7 +7,7 @@
 
 using namespace sph;
 
-template <bool SOLID, bool CORRECTED, bool FILTER>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool MASKED>
 static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDev>& mats, const std::vector<uint32_t>& matid,
     const double* lut, const uint64_t* off, const uint32_t* idx, bool hasReduce, bool hasDamage) {
     const uint32_t n = s->n;
@@ -54,8 +54,20 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
             const Particle& pj = P[idx[k]];
             const double dx = P[i].x - pj.x, dy = P[i].y - pj.y, dz = P[i].z - pj.z;
             double d2, hbar;
-            if (!isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar)) continue;
-            pairAccumulate<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, acc);
+            const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar);
+            if (MASKED) {
+                // the tiled kernel's branch-free body; also fed one non-neighbour per target to exercise the masking
+                pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, valid, acc);
+            } else if (valid) {
+                pairAccumulate<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, acc);
+            }
+        }
+        if (MASKED) {
+            const Particle& pj = P[(i + n / 2) % n]; // an arbitrary (almost surely non-neighbour) candidate, masked out
+            const double dx = P[i].x - pj.x, dy = P[i].y - pj.y, dz = P[i].z - pj.z;
+            double d2, hbar;
+            const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar);
+            if (!valid) pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, false, acc);
         }
         double S[5] = { 0, 0, 0, 0, 0 };
         if (SOLID) {
@@ -76,7 +88,8 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
     }
 }
 
-extern "C" int hostcheck_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material* mats, uint32_t nmat,
+template <bool MASKED>
+static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_material* mats, uint32_t nmat,
     const uint64_t* off, const uint32_t* idx) {
     ParamsDev prm{};
     prm.forces = cfg->forces; prm.flags = cfg->flags; prm.continuity_mode = cfg->continuity_mode; prm.lut_entries = cfg->lut_entries;
@@ -103,10 +116,15 @@ extern "C" int hostcheck_integrate(orc_state* s, const sphgpu_config* cfg, const
     const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
     const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;
-    if (!solid) run<false, false, false>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else if (corrected && filter) run<true, true, true>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else if (corrected) run<true, true, false>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else if (filter) run<true, false, true>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else run<true, false, false>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    else run<true, false, false, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
     return 0;
+}
+
+extern "C" int hostcheck_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material* mats, uint32_t nmat,
+    const uint64_t* off, const uint32_t* idx, int masked) {
+    return masked ? dispatch<true>(s, cfg, mats, nmat, off, idx) : dispatch<false>(s, cfg, mats, nmat, off, idx);
 }

@@ -25,15 +25,16 @@ def hostcheck():
     return C.CDLL(LIB)
 
 
+@pytest.mark.parametrize("masked", [0, 1])
 @pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
-def test_product_math_matches_golden(name, hostcheck, lut):
+def test_product_math_matches_golden(name, masked, hostcheck, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
     st = OraclePort(i, abi.setup_from_snapshot(i, lut))
     off = o["nbr_offsets"].astype(np.uint64)
     idx = o["nbr_idx"].astype(np.uint32)
     hostcheck.hostcheck_integrate(C.byref(st.state), C.byref(st.setup.cfg), st.setup.materials,
                                   C.c_uint32(st.setup.n_materials), off.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                  idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+                                  idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_int(masked))
     assert np.array_equal(st.a["ncnt"], o["ncnt"])
     for k in ("p", "cs", "reduce", "S"):
         if k in o and k in st.a:
