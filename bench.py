@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000, help="target particle count of the lattice (configs[3])")
+    ap.add_argument("--particles", dest="n", type=int, default=10_000_000, help="target particle count of the lattice (configs[3])")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

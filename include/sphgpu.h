@@ -228,9 +228,12 @@ SPHGPU_API int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_
 SPHGPU_API int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4);
 /* Selects the pair-kernel variant (0 = default tiled kernel, 1 = direct per-thread kernel). For A/B checks only. */
 SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
-/* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*), so that
- * the caller can bracket calls with its own events (e.g. torch.cuda.Event). NULL restores the private stream. */
+/* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
+ * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the
+ * caller's own work -- NCCL halo exchange, torch.cuda.Event timing -- is ordered with the engine's kernels.
+ * sphgpu_use_private_stream() returns to the context's own non-blocking stream (the initial state). */
 SPHGPU_API int sphgpu_set_stream(sphgpu_ctx* ctx, void* cuda_stream);
+SPHGPU_API int sphgpu_use_private_stream(sphgpu_ctx* ctx);
 /* Blocks until all work queued on the context's stream has finished. */
 SPHGPU_API int sphgpu_synchronize(sphgpu_ctx* ctx);
 

@@ -336,7 +336,15 @@ int sphgpu_set_stream(sphgpu_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
     SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->privateStream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return SPHGPU_OK;
+}
+
+int sphgpu_use_private_stream(sphgpu_ctx* ctx) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->privateStream;
     return SPHGPU_OK;
 }
 

@@ -177,5 +177,8 @@ class Engine:
     def set_stream(self, cuda_stream: int) -> None:
         _check(self.lib.sphgpu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
+    def use_private_stream(self) -> None:
+        _check(self.lib.sphgpu_use_private_stream(self._ctx))
+
     def synchronize(self) -> None:
         _check(self.lib.sphgpu_synchronize(self._ctx))

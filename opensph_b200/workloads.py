@@ -75,6 +75,20 @@ def hexagonal_sphere(n_target: int, radius: float, centre=(0.0, 0.0, 0.0), x_ran
     return pos, h
 
 
+def _hash01(pos3: np.ndarray, scale: float, seed: int, stream: int) -> np.ndarray:
+    """Uniform(0,1) numbers keyed by the (quantised) particle position, so that every rank of a decomposed run draws
+    the same per-particle constants as a single-domain run (splitmix64 of the lattice coordinates)."""
+    q = np.round(pos3 / scale).astype(np.int64).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x = (q[:, 0] * np.uint64(0x9E3779B97F4A7C15)) ^ (q[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F)) ^ (
+            q[:, 2] * np.uint64(0x165667B19E3779F9)) ^ np.uint64((seed * 0x632BE59BD9B4E019 + stream * 0x9E3779B97F4A7C15) % 2 ** 64)
+        for _ in range(2):
+            x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            x = x ^ (x >> np.uint64(31))
+    return ((x >> np.uint64(11)).astype(np.float64) + 0.5) / float(1 << 53)
+
+
 def basalt_material(begin: int, end: int, solid: bool = True) -> abi.Material:
     b = BASALT
     m = abi.Material()
@@ -153,21 +167,22 @@ def basalt_sphere_state(n_target: int, radius: float = 5.0e4, solid: bool = True
         S[:, 4] = 0.5e7 * np.sin(3.0 * x - 2.0 * z)
         st["S"], st["dS"] = S, np.zeros((n, 5))
         st["damage"], st["ddamage"], st["reduce"] = np.zeros(n), np.zeros(n), np.ones(n)
-        # Weibull flaws, sampled variant (Damage.cpp:71-95); numpy RNG instead of the reference's UniformRng
-        rng = np.random.default_rng(seed + (0 if x_range is None else int(abs(x_range[0])) % 9973))
+        # Weibull flaws, sampled variant (Damage.cpp:71-95); position-keyed hash instead of the reference's UniformRng
         A, mu = b["til_A"], b["shear_modulus"]
         cg = b["rayleigh"] * math.sqrt((A + 4.0 / 3.0 * mu) / b["rho0"])
         st["growth"] = cg / (2.0 * pos[:, 3])
         mw, kw = b["weibull_m"], b["weibull_k"]
         denom = 1.0 / (kw ** (1.0 / mw) * volume ** (1.0 / mw))
         size = float(max(n_total, 2))
-        xr = rng.random(n)
+        xr = _hash01(pos3, 0.05 * h_lat, seed, 1)
         p1 = -size * np.log1p(-xr)
         mult = math.exp(math.log(size)) - 1.0
         p2 = size * np.log1p(xr * mult)
         eps_min = denom * p1 ** (1.0 / mw)
         eps_max = denom * np.maximum(p1, p2) ** (1.0 / mw)
-        n_flaws = np.maximum(1, rng.poisson(math.log(size), n)).astype(np.uint32)
+        from scipy.special import ndtri
+        lam = math.log(size)  # Poisson(log N) flaws per particle, normal approximation keyed by position
+        n_flaws = np.maximum(1, np.floor(lam + math.sqrt(lam) * ndtri(_hash01(pos3, 0.05 * h_lat, seed, 2)) + 0.5)).astype(np.uint32)
         eps_max = np.minimum(eps_max, n_flaws * eps_min)
         with np.errstate(divide="ignore", invalid="ignore"):
             m_zero = np.where(n_flaws == 1, 1.0, np.log(n_flaws) / np.log(np.maximum(eps_max / eps_min, 1.0 + 1e-12)))
