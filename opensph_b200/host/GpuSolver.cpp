@@ -1,0 +1,350 @@
+#include "GpuSolver.h"
+#include "../../include/sphgpu.h"
+#include "objects/Exceptions.h"
+#include "quantities/IMaterial.h"
+#include "quantities/Storage.h"
+#include "sph/equations/av/Standard.h"
+#include "system/Factory.h"
+#include "system/Statistics.h"
+#include "thread/Scheduler.h"
+#include <string>
+#include <vector>
+
+NAMESPACE_SPH_BEGIN
+
+namespace {
+
+/// Non-zero C-ABI status -> the exception the reference would have thrown (InvalidSetup from constructors / create /
+/// sanityCheck, Exception otherwise; core/objects/Exceptions.h).
+void check(const int rc) {
+    if (rc == SPHGPU_OK) {
+        return;
+    }
+    const String msg = String::fromAscii(sphgpu_last_error());
+    if (rc == SPHGPU_E_INVALID || rc == SPHGPU_E_NO_DEVICE) {
+        throw InvalidSetup("GpuSolver: " + msg);
+    }
+    throw Exception("GpuSolver: " + msg);
+}
+
+struct QuantityBinding {
+    QuantityId id;
+    int q;
+};
+
+// first-order scalar quantities with their derivative
+const QuantityBinding SCALARS_FIRST[] = { { QuantityId::DENSITY, SPHGPU_Q_DENSITY }, { QuantityId::ENERGY, SPHGPU_Q_ENERGY },
+    { QuantityId::DAMAGE, SPHGPU_Q_DAMAGE } };
+// zero-order scalar inputs
+const QuantityBinding SCALARS_ZERO[] = { { QuantityId::MASS, SPHGPU_Q_MASS }, { QuantityId::PRESSURE, SPHGPU_Q_PRESSURE },
+    { QuantityId::SOUND_SPEED, SPHGPU_Q_SOUND_SPEED }, { QuantityId::STRESS_REDUCING, SPHGPU_Q_STRESS_REDUCING },
+    { QuantityId::EPS_MIN, SPHGPU_Q_EPS_MIN }, { QuantityId::M_ZERO, SPHGPU_Q_M_ZERO },
+    { QuantityId::EXPLICIT_GROWTH, SPHGPU_Q_EXPLICIT_GROWTH } };
+const QuantityBinding INDICES[] = { { QuantityId::FLAG, SPHGPU_Q_FLAG }, { QuantityId::N_FLAWS, SPHGPU_Q_N_FLAWS } };
+
+} // namespace
+
+GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, const int device)
+    : scheduler(scheduler)
+    , settings(settings)
+    , device(device) {
+    kernel = Factory::getKernel<DIMENSIONS>(settings);
+    equations += eqs;
+
+    // Terms with a device implementation; anything else cannot be evaluated (no CPU fallback by design).
+    Size known = 0;
+    known += equations.contains<PressureForce>() ? 1 : 0;
+    known += equations.contains<SolidStressForce>() ? 1 : 0;
+    known += equations.contains<ContinuityEquation>() ? 1 : 0;
+    known += equations.contains<StandardAV>() ? 1 : 0;
+    known += equations.contains<AdaptiveSmoothingLength>() ? 1 : 0;
+    known += equations.contains<ConstSmoothingLength>() ? 1 : 0;
+    if (known != equations.getTermCnt()) {
+        throw InvalidSetup("GpuSolver: the equation set contains a term without a GPU implementation");
+    }
+    if (!equations.contains<PressureForce>() || !equations.contains<ContinuityEquation>() || !equations.contains<StandardAV>()) {
+        throw InvalidSetup("GpuSolver needs PressureForce, ContinuityEquation and StandardAV (the collision preset)");
+    }
+    // same check as AsymmetricSolver::sanityCheck (AsymmetricSolver.cpp:228-234)
+    if (!equations.contains<AdaptiveSmoothingLength>() && !equations.contains<ConstSmoothingLength>()) {
+        throw InvalidSetup("No solver of smoothing length specified; add either ConstSmootingLength or "
+                           "AdaptiveSmootingLength into the list of equations");
+    }
+}
+
+GpuSolver::~GpuSolver() {
+    sphgpu_destroy(ctx);
+}
+
+void GpuSolver::create(Storage& storage, IMaterial& material) const {
+    storage.insert<Size>(QuantityId::NEIGHBOR_CNT, OrderEnum::ZERO, 0);
+    equations.create(storage, material);
+}
+
+sphgpu_ctx* GpuSolver::context(const Storage& storage) {
+    const Size n = storage.getParticleCnt();
+    if (ctx && ctxParticleCnt == n) {
+        return ctx;
+    }
+    sphgpu_destroy(ctx);
+    ctx = nullptr;
+
+    sphgpu_config cfg{};
+    cfg.abi_version = SPHGPU_ABI_VERSION;
+    cfg.forces = SPHGPU_FORCE_PRESSURE | (equations.contains<SolidStressForce>() ? SPHGPU_FORCE_SOLID_STRESS : 0);
+    const Flags<SmoothingLengthEnum> hflags =
+        settings.getFlags<SmoothingLengthEnum>(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH);
+    cfg.flags = 0;
+    if (equations.contains<SolidStressForce>() && settings.get<bool>(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR)) {
+        cfg.flags |= SPHGPU_FLAG_CORRECTION_TENSOR;
+    }
+    if (settings.get<bool>(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED)) {
+        cfg.flags |= SPHGPU_FLAG_SUM_ONLY_UNDAMAGED;
+    }
+    if (equations.contains<AdaptiveSmoothingLength>()) {
+        cfg.flags |= SPHGPU_FLAG_ADAPTIVE_H;
+        if (hflags.has(SmoothingLengthEnum::SOUND_SPEED_ENFORCING)) {
+            cfg.flags |= SPHGPU_FLAG_SOUND_SPEED_ENFORCING;
+        }
+    }
+    cfg.discretization = uint32_t(settings.get<DiscretizationEnum>(RunSettingsId::SPH_DISCRETIZATION));
+    cfg.continuity_mode = uint32_t(settings.get<ContinuityEnum>(RunSettingsId::SPH_CONTINUITY_MODE));
+
+    // kernel LUT exactly as the reference tabulates it (LutKernel, core/sph/kernel/Kernel.h:85-101)
+    const Size entries = 40000;
+    const Float qSqrToIdx = Float(entries) / sqr(kernel.radius());
+    std::vector<double> lutGrad(entries + 1, 0.), lutValue(entries + 1, 0.);
+    for (Size i = 0; i < entries; ++i) {
+        lutGrad[i] = kernel.gradImpl(Float(i) / qSqrToIdx);
+        lutValue[i] = kernel.valueImpl(Float(i) / qSqrToIdx);
+    }
+    cfg.lut_entries = entries;
+    cfg.lut_grad = lutGrad.data();
+    cfg.lut_value = lutValue.data();
+    cfg.kernel_radius = kernel.radius();
+    cfg.av_alpha = settings.get<Float>(RunSettingsId::SPH_AV_ALPHA);
+    cfg.av_beta = settings.get<Float>(RunSettingsId::SPH_AV_BETA);
+    const Interval hRange = settings.get<Interval>(RunSettingsId::SPH_SMOOTHING_LENGTH_RANGE);
+    cfg.h_min = hRange.lower();
+    cfg.h_max = hRange.upper();
+    cfg.neigh_enforcing = settings.get<Float>(RunSettingsId::SPH_NEIGHBOR_ENFORCING);
+    const Interval nRange = settings.get<Interval>(RunSettingsId::SPH_NEIGHBOR_RANGE);
+    cfg.neigh_lower = nRange.lower();
+    cfg.neigh_upper = nRange.upper();
+    cfg.criteria = uint32_t(settings.getFlags<TimeStepCriterionEnum>(RunSettingsId::TIMESTEPPING_CRITERION).value());
+    cfg.courant = settings.get<Float>(RunSettingsId::TIMESTEPPING_COURANT_NUMBER);
+    cfg.derivative_factor = settings.get<Float>(RunSettingsId::TIMESTEPPING_DERIVATIVE_FACTOR);
+    cfg.divergence_factor = settings.get<Float>(RunSettingsId::TIMESTEPPING_DIVERGENCE_FACTOR);
+    cfg.max_change = settings.get<Float>(RunSettingsId::TIMESTEPPING_MAX_INCREASE);
+
+    std::vector<sphgpu_material> mats(storage.getMaterialCnt());
+    for (Size i = 0; i < storage.getMaterialCnt(); ++i) {
+        MaterialView mat = storage.getMaterial(i);
+        const BodySettings& b = mat->getParams();
+        sphgpu_material& m = mats[i];
+        m = sphgpu_material{};
+        m.begin = *mat.sequence().begin();
+        m.end = *mat.sequence().end();
+        m.eos = uint32_t(b.get<EosEnum>(BodySettingsId::EOS));
+        m.yielding = uint32_t(b.get<YieldingEnum>(BodySettingsId::RHEOLOGY_YIELDING));
+        m.fracture = (m.yielding == SPHGPU_YIELD_NONE) ? uint32_t(SPHGPU_FRACTURE_NONE)
+                                                       : uint32_t(b.get<FractureEnum>(BodySettingsId::RHEOLOGY_DAMAGE));
+        m.til_u0 = b.get<Float>(BodySettingsId::TILLOTSON_SUBLIMATION);
+        m.til_uiv = b.get<Float>(BodySettingsId::TILLOTSON_ENERGY_IV);
+        m.til_ucv = b.get<Float>(BodySettingsId::TILLOTSON_ENERGY_CV);
+        m.til_a = b.get<Float>(BodySettingsId::TILLOTSON_SMALL_A);
+        m.til_b = b.get<Float>(BodySettingsId::TILLOTSON_SMALL_B);
+        m.rho0 = b.get<Float>(BodySettingsId::DENSITY);
+        m.til_A = b.get<Float>(BodySettingsId::BULK_MODULUS);
+        m.til_B = b.get<Float>(BodySettingsId::TILLOTSON_NONLINEAR_B);
+        m.til_alpha = b.get<Float>(BodySettingsId::TILLOTSON_ALPHA);
+        m.til_beta = b.get<Float>(BodySettingsId::TILLOTSON_BETA);
+        m.gamma = b.get<Float>(BodySettingsId::ADIABATIC_INDEX);
+        m.shear_modulus = b.get<Float>(BodySettingsId::SHEAR_MODULUS);
+        m.elasticity_limit = b.get<Float>(BodySettingsId::ELASTICITY_LIMIT);
+        m.melt_energy = b.get<Float>(BodySettingsId::MELT_ENERGY);
+        m.young_modulus = b.get<Float>(BodySettingsId::YOUNG_MODULUS);
+        const Interval rhoRange = mat->range(QuantityId::DENSITY), uRange = mat->range(QuantityId::ENERGY),
+                       dRange = mat->range(QuantityId::DAMAGE);
+        m.rho_min = rhoRange.lower();
+        m.rho_max = rhoRange.upper();
+        m.u_min = uRange.lower();
+        m.u_max = uRange.upper();
+        m.d_min = dRange.lower();
+        m.d_max = dRange.upper();
+        m.rho_small = mat->minimal(QuantityId::DENSITY);
+        m.u_small = mat->minimal(QuantityId::ENERGY);
+        m.d_small = mat->minimal(QuantityId::DAMAGE);
+        m.s_small = mat->minimal(QuantityId::DEVIATORIC_STRESS);
+    }
+    check(sphgpu_create(&cfg, mats.data(), uint32_t(mats.size()), n, n, device, &ctx));
+    ctxParticleCnt = n;
+    return ctx;
+}
+
+void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives) {
+    sphgpu_ctx* c = this->context(storage);
+    const Size n = storage.getParticleCnt();
+    const int L = SPHGPU_LAYOUT_OPENSPH;
+    check(sphgpu_upload(c, SPHGPU_Q_POSITION, 0, L, &storage.getValue<Vector>(QuantityId::POSITION)[0], 0, n));
+    check(sphgpu_upload(c, SPHGPU_Q_POSITION, 1, L, &storage.getDt<Vector>(QuantityId::POSITION)[0], 0, n));
+    if (derivatives) {
+        check(sphgpu_upload(c, SPHGPU_Q_POSITION, 2, L, &storage.getD2t<Vector>(QuantityId::POSITION)[0], 0, n));
+    }
+    for (const QuantityBinding& b : SCALARS_ZERO) {
+        if (storage.has(b.id)) {
+            check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Float>(b.id)[0], 0, n));
+        }
+    }
+    for (const QuantityBinding& b : SCALARS_FIRST) {
+        if (storage.has(b.id)) {
+            check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Float>(b.id)[0], 0, n));
+            if (derivatives) {
+                check(sphgpu_upload(c, b.q, 1, L, &storage.getDt<Float>(b.id)[0], 0, n));
+            }
+        }
+    }
+    for (const QuantityBinding& b : INDICES) {
+        if (storage.has(b.id)) {
+            check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Size>(b.id)[0], 0, n));
+        }
+    }
+    if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
+        check(sphgpu_upload(c, SPHGPU_Q_DEVIATORIC_STRESS, 0, L, &storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+        if (derivatives) {
+            check(sphgpu_upload(c, SPHGPU_Q_DEVIATORIC_STRESS, 1, L, &storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+        }
+    }
+}
+
+void GpuSolver::downloadQuantities(Storage& storage, const bool stateToo) {
+    sphgpu_ctx* c = this->context(storage);
+    const Size n = storage.getParticleCnt();
+    const int L = SPHGPU_LAYOUT_OPENSPH;
+    ArrayView<Vector> r, v, dv;
+    tie(r, v, dv) = storage.getAll<Vector>(QuantityId::POSITION);
+    // h may have been clamped (AdaptiveSmoothingLength::initialize) and dh/dt is a result of the evaluation
+    check(sphgpu_download(c, SPHGPU_Q_POSITION, 0, L, &r[0], 0, n));
+    check(sphgpu_download(c, SPHGPU_Q_POSITION, 1, L, &v[0], 0, n));
+    check(sphgpu_download(c, SPHGPU_Q_POSITION, 2, L, &dv[0], 0, n));
+    // p, cs, reduce and S are (re)computed by material->initialize
+    for (const QuantityBinding& b : { QuantityBinding{ QuantityId::PRESSURE, SPHGPU_Q_PRESSURE },
+             QuantityBinding{ QuantityId::SOUND_SPEED, SPHGPU_Q_SOUND_SPEED },
+             QuantityBinding{ QuantityId::STRESS_REDUCING, SPHGPU_Q_STRESS_REDUCING },
+             QuantityBinding{ QuantityId::VELOCITY_DIVERGENCE, SPHGPU_Q_VELOCITY_DIVERGENCE } }) {
+        if (storage.has(b.id)) {
+            check(sphgpu_download(c, b.q, 0, L, &storage.getValue<Float>(b.id)[0], 0, n));
+        }
+    }
+    for (const QuantityBinding& b : SCALARS_FIRST) {
+        if (storage.has(b.id)) {
+            if (stateToo) {
+                check(sphgpu_download(c, b.q, 0, L, &storage.getValue<Float>(b.id)[0], 0, n));
+            }
+            check(sphgpu_download(c, b.q, 1, L, &storage.getDt<Float>(b.id)[0], 0, n));
+        }
+    }
+    if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
+        check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 0, L, &storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+        check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 1, L, &storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+    }
+    if (storage.has(QuantityId::VELOCITY_GRADIENT)) {
+        check(sphgpu_download(c, SPHGPU_Q_VELOCITY_GRADIENT, 0, L, &storage.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT)[0], 0, n));
+    }
+    if (storage.has(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)) {
+        check(sphgpu_download(c, SPHGPU_Q_CORRECTION_TENSOR, 0, L,
+            &storage.getValue<SymmetricTensor>(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)[0], 0, n));
+    }
+    check(sphgpu_download(c, SPHGPU_Q_NEIGHBOR_CNT, 0, L, &storage.getValue<Size>(QuantityId::NEIGHBOR_CNT)[0], 0, n));
+}
+
+void GpuSolver::upload(const Storage& storage) {
+    this->uploadQuantities(storage, true);
+    hostStale = false;
+}
+
+void GpuSolver::download(Storage& storage) {
+    this->downloadQuantities(storage, true);
+    hostStale = false;
+}
+
+void GpuSolver::integrate(Storage& storage, Statistics& stats) {
+    // ISolver contract: highest derivatives are zero on entry (ISolver.h:33-34); the device overwrites them, which is
+    // what the reference's accumulate-into-zero amounts to.
+    this->uploadQuantities(storage, false);
+    sphgpu_stats st{};
+    const Float t = stats.getOr<Float>(StatisticsId::RUN_TIME, 0._f);
+    check(sphgpu_integrate(ctx, t, &st));
+    this->downloadQuantities(storage, false);
+
+    // neighbour statistics as AsymmetricSolver::afterLoop stores them (AsymmetricSolver.cpp:218-225)
+    ArrayView<const Size> neighs = storage.getValue<Size>(QuantityId::NEIGHBOR_CNT);
+    MinMaxMean neighsStats;
+    for (Size i = 0; i < neighs.size(); ++i) {
+        neighsStats.accumulate(neighs[i]);
+    }
+    stats.set(StatisticsId::NEIGHBOR_COUNT, neighsStats);
+}
+
+//-----------------------------------------------------------------------------------------------------------
+// GpuPredictorCorrector
+//-----------------------------------------------------------------------------------------------------------
+
+/// Hands the time step computed on the device to ITimeStepping::step (TimeStepping.cpp:55-62).
+class GpuPredictorCorrector::DeviceCriterion : public ITimeStepCriterion {
+private:
+    const TimeStep& step;
+
+public:
+    explicit DeviceCriterion(const TimeStep& step)
+        : step(step) {}
+
+    virtual TimeStep compute(IScheduler& UNUSED(scheduler),
+        Storage& UNUSED(storage),
+        Float UNUSED(maxStep),
+        Statistics& UNUSED(stats),
+        ArrayView<TimeStep> UNUSED(dts)) override {
+        return step;
+    }
+};
+
+GpuPredictorCorrector::GpuPredictorCorrector(const SharedPtr<Storage>& storage, const RunSettings& settings, GpuSolver& solver)
+    : ITimeStepping(storage, settings, makeAuto<DeviceCriterion>(lastStep))
+    , gpu(solver) {
+    lastStep.value = settings.get<Float>(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP);
+    lastStep.id = CriterionId::INITIAL_VALUE;
+    // PredictorCorrector's constructor clears the derivatives before the first step (TimeStepping.cpp:280-281)
+    storage->zeroHighestDerivatives(SEQUENTIAL);
+}
+
+void GpuPredictorCorrector::syncToHost() {
+    if (gpu.isHostStale()) {
+        gpu.download(*storage);
+    }
+}
+
+void GpuPredictorCorrector::stepParticles(IScheduler& UNUSED(scheduler), ISolver& solver, Statistics& stats) {
+    if (&solver != &gpu) {
+        throw InvalidSetup("GpuPredictorCorrector must be used with the GpuSolver it was constructed with");
+    }
+    sphgpu_ctx* c = gpu.context(*storage);
+    if (!uploaded) {
+        gpu.upload(*storage);
+        check(sphgpu_set_last_timestep(c, timeStep));
+        uploaded = true;
+    }
+    sphgpu_stats st{};
+    sphgpu_timestep ts{};
+    const Float t = stats.getOr<Float>(StatisticsId::RUN_TIME, 0._f);
+    check(sphgpu_step_pc(c, t, timeStep, maxTimeStep, &st, &ts));
+    gpu.setHostStale(true);
+    lastStep.value = ts.dt;
+    lastStep.id = CriterionId(ts.criterion);
+
+    MinMaxMean neighsStats; // min / max / mean only: the per-particle counts stay on the device
+    neighsStats.accumulate(Float(st.neigh_min));
+    neighsStats.accumulate(Float(st.neigh_max));
+    stats.set(StatisticsId::NEIGHBOR_COUNT, neighsStats);
+}
+
+NAMESPACE_SPH_END

@@ -1,0 +1,103 @@
+#pragma once
+
+/// \file GpuSolver.h
+/// \brief Drop-in replacements for OpenSPH's AsymmetricSolver (ISolver) and PredictorCorrector (ITimeStepping)
+///        that run the per-step SPH evaluation on a B200 through the C ABI of libsphgpu (include/sphgpu.h).
+///
+/// This is the reference-side binding: it is compiled AGAINST the reference's headers and linked with the
+/// reference's core library plus libsphgpu.so. It owns no physics; it moves Storage arrays (the reference's own
+/// AoS memory layout is understood by sphgpu_upload/download) and forwards to the C ABI.
+///
+///   reference class replaced                     file:line in the reference
+///   AsymmetricSolver (ISolver)                   core/sph/solvers/AsymmetricSolver.h:124-129, .cpp:58-238
+///   PredictorCorrector (ITimeStepping)           core/timestepping/TimeStepping.cpp:272-346
+///   MultiCriterion (ITimeStepCriterion)          core/timestepping/TimeStepCriterion.cpp:389-419
+///
+/// Usage inside IRun::setUp (cf. examples/04_simple_collision/SimpleCollision.cpp and
+/// core/run/jobs/SimulationJobs.cpp:173-180, where the protected members `solver` / `timeStepping` are assigned):
+///
+///     solver = makeAuto<GpuSolver>(*scheduler, settings, getStandardEquations(settings));
+///     // optional: keep the whole step on the device
+///     timeStepping = makeAuto<GpuPredictorCorrector>(storage, settings, static_cast<GpuSolver&>(*solver));
+
+#include "sph/equations/EquationTerm.h"
+#include "system/Settings.h"
+#include "sph/kernel/Kernel.h"
+#include "timestepping/ISolver.h"
+#include "timestepping/TimeStepCriterion.h"
+#include "timestepping/TimeStepping.h"
+
+struct sphgpu_ctx;
+
+NAMESPACE_SPH_BEGIN
+
+class GpuSolver : public ISolver {
+private:
+    IScheduler& scheduler;
+    RunSettings settings;
+    EquationHolder equations;
+    LutKernel<DIMENSIONS> kernel;
+
+    sphgpu_ctx* ctx = nullptr;
+    Size ctxParticleCnt = 0;
+    int device;
+
+    /// True while the device holds a newer state than the Storage (after GpuPredictorCorrector steps).
+    bool hostStale = false;
+
+public:
+    /// \throw InvalidSetup if the equation set contains a term without a GPU implementation (there is no CPU
+    ///        fallback), mirroring AsymmetricSolver::sanityCheck (AsymmetricSolver.cpp:228-238).
+    GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, const int device = 0);
+
+    ~GpuSolver() override;
+
+    /// ISolver::integrate: uploads the state, runs sphgpu_integrate, stores derivatives back into the Storage.
+    virtual void integrate(Storage& storage, Statistics& stats) override;
+
+    /// Same quantities as IAsymmetricSolver::create (AsymmetricSolver.cpp:98-102).
+    virtual void create(Storage& storage, IMaterial& material) const override;
+
+    /// Copies the whole time-dependent state host -> device / device -> host.
+    void upload(const Storage& storage);
+    void download(Storage& storage);
+
+    /// Device context (created lazily for the storage's particle count and materials).
+    sphgpu_ctx* context(const Storage& storage);
+
+    bool isHostStale() const {
+        return hostStale;
+    }
+    void setHostStale(const bool stale) {
+        hostStale = stale;
+    }
+
+private:
+    void uploadQuantities(const Storage& storage, const bool derivatives);
+    void downloadQuantities(Storage& storage, const bool stateToo);
+};
+
+/// \brief PredictorCorrector whose whole step (predict, derivatives, correct, time-step criteria) runs on the device.
+///
+/// The Storage on the host is refreshed only when syncToHost() is called (before output->dump, log writers or
+/// callbacks that read particle data); between calls no particle data crosses PCIe.
+class GpuPredictorCorrector : public ITimeStepping {
+private:
+    GpuSolver& gpu;
+    bool uploaded = false;
+    Float runTime = 0._f;
+
+    class DeviceCriterion;
+    TimeStep lastStep;
+
+public:
+    GpuPredictorCorrector(const SharedPtr<Storage>& storage, const RunSettings& settings, GpuSolver& solver);
+
+    /// Brings the host Storage up to date with the device state.
+    void syncToHost();
+
+protected:
+    virtual void stepParticles(IScheduler& scheduler, ISolver& solver, Statistics& stats) override;
+};
+
+NAMESPACE_SPH_END

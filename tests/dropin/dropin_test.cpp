@@ -1,0 +1,244 @@
+// Drop-in test (run on the GPU box): the reference's own AsymmetricSolver / PredictorCorrector next to GpuSolver /
+// GpuPredictorCorrector on identical Storages, all through the reference's ISolver / ITimeStepping interfaces.
+// Modelled on the reference's solver cross-check (core/sph/solvers/test/Solvers.cpp:178-216: two solvers, same
+// storage, compare every quantity) and its Impact smoke test (core/sph/solvers/test/Impact.cpp:41-85).
+//
+// Built by opensph_b200/host/Makefile against /root/reference (headers + oracle/_ref/libopensph_core_strict.a) and
+// libsphgpu.so; the binary goes to oracle/_ref/dropin_test because it embeds reference code.
+#include "../../opensph_b200/host/GpuSolver.h"
+#include "Sph.h"
+#include <cstdio>
+#include <random>
+
+using namespace Sph;
+
+namespace {
+
+int failures = 0;
+
+void expect(const bool cond, const char* what) {
+    printf("%s  %s\n", cond ? "ok  " : "FAIL", what);
+    if (!cond) {
+        failures++;
+    }
+}
+
+template <typename T, typename TGet>
+double relErr(ArrayView<const T> a, ArrayView<const T> b, const int comps, const TGet& get) {
+    double scale = 0.;
+    for (Size i = 0; i < a.size(); ++i) {
+        for (int k = 0; k < comps; ++k) {
+            scale = std::max(scale, std::max(std::abs(get(a[i], k)), std::abs(get(b[i], k))));
+        }
+    }
+    const double floorV = 1.e-4 * std::max(scale, 1.e-300);
+    double err = 0.;
+    for (Size i = 0; i < a.size(); ++i) {
+        for (int k = 0; k < comps; ++k) {
+            const double x = get(a[i], k), y = get(b[i], k);
+            err = std::max(err, std::abs(x - y) / std::max(std::max(std::abs(x), std::abs(y)), floorV));
+        }
+    }
+    return err;
+}
+
+double cmpVector(ArrayView<const Vector> a, ArrayView<const Vector> b, const int comps = 4) {
+    return relErr<Vector>(a, b, comps, [](const Vector& v, int k) { return double(v[k]); });
+}
+double cmpFloat(ArrayView<const Float> a, ArrayView<const Float> b) {
+    return relErr<Float>(a, b, 1, [](const Float& v, int) { return double(v); });
+}
+double cmpTraceless(ArrayView<const TracelessTensor> a, ArrayView<const TracelessTensor> b) {
+    static const int I[5] = { 0, 1, 0, 0, 1 }, J[5] = { 0, 1, 1, 2, 2 };
+    return relErr<TracelessTensor>(a, b, 5, [](const TracelessTensor& t, int k) { return double(t(I[k], J[k])); });
+}
+double cmpSymmetric(ArrayView<const SymmetricTensor> a, ArrayView<const SymmetricTensor> b) {
+    static const int I[6] = { 0, 1, 2, 0, 0, 1 }, J[6] = { 0, 1, 2, 1, 2, 2 };
+    return relErr<SymmetricTensor>(a, b, 6, [](const SymmetricTensor& t, int k) { return double(t(I[k], J[k])); });
+}
+
+/// Compares every quantity the solvers write; returns the largest relative error.
+double compareStorages(const Storage& a, const Storage& b, const bool derivatives, const char* label) {
+    double worst = 0.;
+    auto note = [&](const char* name, const double e) {
+        printf("    %-28s %.3e\n", name, e);
+        worst = std::max(worst, e);
+    };
+    printf("  [%s]\n", label);
+    note("POSITION", cmpVector(a.getValue<Vector>(QuantityId::POSITION), b.getValue<Vector>(QuantityId::POSITION)));
+    note("POSITION dt", cmpVector(a.getDt<Vector>(QuantityId::POSITION), b.getDt<Vector>(QuantityId::POSITION)));
+    if (derivatives) {
+        note("POSITION d2t", cmpVector(a.getD2t<Vector>(QuantityId::POSITION), b.getD2t<Vector>(QuantityId::POSITION)));
+    }
+    for (QuantityId id : { QuantityId::DENSITY, QuantityId::ENERGY, QuantityId::DAMAGE }) {
+        if (a.has(id)) {
+            note(getMetadata(id).quantityName.toAscii(), cmpFloat(a.getValue<Float>(id), b.getValue<Float>(id)));
+            if (derivatives) {
+                note((getMetadata(id).quantityName + " dt").toAscii(), cmpFloat(a.getDt<Float>(id), b.getDt<Float>(id)));
+            }
+        }
+    }
+    for (QuantityId id : { QuantityId::PRESSURE, QuantityId::SOUND_SPEED, QuantityId::STRESS_REDUCING, QuantityId::VELOCITY_DIVERGENCE }) {
+        if (a.has(id) && derivatives) {
+            note(getMetadata(id).quantityName.toAscii(), cmpFloat(a.getValue<Float>(id), b.getValue<Float>(id)));
+        }
+    }
+    if (a.has(QuantityId::DEVIATORIC_STRESS)) {
+        note("DEVIATORIC_STRESS", cmpTraceless(a.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS), b.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)));
+        if (derivatives) {
+            note("DEVIATORIC_STRESS dt", cmpTraceless(a.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS), b.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)));
+        }
+    }
+    if (derivatives && a.has(QuantityId::VELOCITY_GRADIENT)) {
+        note("VELOCITY_GRADIENT", cmpSymmetric(a.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT), b.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT)));
+    }
+    if (derivatives && a.has(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)) {
+        note("CORRECTION_TENSOR", cmpSymmetric(a.getValue<SymmetricTensor>(QuantityId::STRAIN_RATE_CORRECTION_TENSOR), b.getValue<SymmetricTensor>(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)));
+    }
+    return worst;
+}
+
+bool sameNeighbourCounts(const Storage& a, const Storage& b) {
+    ArrayView<const Size> x = a.getValue<Size>(QuantityId::NEIGHBOR_CNT), y = b.getValue<Size>(QuantityId::NEIGHBOR_CNT);
+    for (Size i = 0; i < x.size(); ++i) {
+        if (x[i] != y[i]) {
+            return false;
+        }
+    }
+    return true;
+}
+
+RunSettings presetSettings() {
+    RunSettings settings;
+    settings.set(RunSettingsId::TIMESTEPPING_INTEGRATOR, TimesteppingEnum::PREDICTOR_CORRECTOR)
+        .set(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP, 0.01_f)
+        .set(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP, 10._f)
+        .set(RunSettingsId::SPH_SOLVER_TYPE, SolverEnum::ASYMMETRIC_SOLVER)
+        .set(RunSettingsId::SPH_SOLVER_FORCES, ForceEnum::PRESSURE | ForceEnum::SOLID_STRESS)
+        .set(RunSettingsId::SPH_FINDER, FinderEnum::KD_TREE)
+        .set(RunSettingsId::FINDER_LEAF_SIZE, 20)
+        .set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH, SmoothingLengthEnum::CONTINUITY_EQUATION)
+        .set(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR, true)
+        .set(RunSettingsId::TIMESTEPPING_CRITERION, TimeStepCriterionEnum::COURANT | TimeStepCriterionEnum::DIVERGENCE)
+        .set(RunSettingsId::RUN_THREAD_CNT, 0);
+    return settings;
+}
+
+/// Target + impactor (examples/04_simple_collision) with jittered state so that every branch is exercised.
+SharedPtr<Storage> makeStorage(const RunSettings& settings, ISolver& creator, const Size n) {
+    SharedPtr<Storage> storage = makeShared<Storage>();
+    InitialConditions ic(settings);
+    BodySettings body;
+    body.set(BodySettingsId::PARTICLE_COUNT, int(n));
+    ic.addMonolithicBody(*storage, SphericalDomain(Vector(0._f), 1.e5_f), body);
+    body.set(BodySettingsId::PARTICLE_COUNT, int(std::max<Size>(n / 100, 10)));
+    BodyView impactor = ic.addMonolithicBody(*storage, SphericalDomain(Vector(1.4e5_f, 0._f, 0._f), 2.e4_f), body);
+    impactor.addVelocity(Vector(-5.e3_f, 0._f, 0._f));
+    for (Size i = 0; i < storage->getMaterialCnt(); ++i) {
+        creator.create(*storage, storage->getMaterial(i));
+    }
+    std::mt19937_64 gen(4321);
+    std::uniform_real_distribution<double> uni(0., 1.);
+    ArrayView<Vector> r, v, dv;
+    tie(r, v, dv) = storage->getAll<Vector>(QuantityId::POSITION);
+    ArrayView<Float> rho = storage->getValue<Float>(QuantityId::DENSITY), u = storage->getValue<Float>(QuantityId::ENERGY),
+                     D = storage->getValue<Float>(QuantityId::DAMAGE);
+    ArrayView<TracelessTensor> s = storage->getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS);
+    for (Size i = 0; i < r.size(); ++i) {
+        const Float h = r[i][H];
+        r[i] += Vector(0.2_f * h * (2 * uni(gen) - 1), 0.2_f * h * (2 * uni(gen) - 1), 0.2_f * h * (2 * uni(gen) - 1));
+        r[i][H] = h * (0.9_f + 0.2_f * uni(gen));
+        v[i] += Vector(30._f * (2 * uni(gen) - 1), 30._f * (2 * uni(gen) - 1), 30._f * (2 * uni(gen) - 1));
+        v[i][H] = 0._f;
+        rho[i] *= 0.95_f + 0.1_f * uni(gen);
+        u[i] = uni(gen) < 0.7 ? 1.e5_f * uni(gen) : 8.e6_f * uni(gen);
+        const Float a = 5.e8_f;
+        s[i] = TracelessTensor(a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1), a * (2 * uni(gen) - 1));
+        const Float c = uni(gen);
+        D[i] = c < 0.5 ? 0._f : (c < 0.55 ? 1._f : uni(gen));
+    }
+    return storage;
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    const Size n = argc > 1 ? Size(atoi(argv[1])) : 20000;
+    const int steps = argc > 2 ? atoi(argv[2]) : 3;
+    try {
+        RunSettings settings = presetSettings();
+        SharedPtr<IScheduler> scheduler = Factory::getScheduler(settings);
+        const EquationHolder eqs = getStandardEquations(settings);
+
+        AsymmetricSolver refSolver(*scheduler, settings, eqs);
+        GpuSolver gpuSolver(*scheduler, settings, eqs);
+
+        // ---- 1. one integrate() through ISolver ----
+        SharedPtr<Storage> base = makeStorage(settings, refSolver, n);
+        printf("particles: %u, materials: %u\n", unsigned(base->getParticleCnt()), unsigned(base->getMaterialCnt()));
+        Storage a = base->clone(VisitorEnum::ALL_BUFFERS), b = base->clone(VisitorEnum::ALL_BUFFERS);
+        Statistics statsA, statsB;
+        statsA.set(StatisticsId::RUN_TIME, 0._f);
+        statsB.set(StatisticsId::RUN_TIME, 0._f);
+        a.zeroHighestDerivatives(*scheduler);
+        b.zeroHighestDerivatives(*scheduler);
+        refSolver.integrate(a, statsA);
+        gpuSolver.integrate(b, statsB);
+        expect(sameNeighbourCounts(a, b), "NEIGHBOR_CNT identical (AsymmetricSolver vs GpuSolver)");
+        const MinMaxMean na = statsA.get<MinMaxMean>(StatisticsId::NEIGHBOR_COUNT), nb = statsB.get<MinMaxMean>(StatisticsId::NEIGHBOR_COUNT);
+        expect(na.min() == nb.min() && na.max() == nb.max() && std::abs(na.mean() - nb.mean()) < 1.e-9, "StatisticsId::NEIGHBOR_COUNT identical");
+        expect(compareStorages(a, b, true, "integrate()") <= 1.e-10, "all quantities within 1e-10 after ISolver::integrate");
+
+        // ---- 2. reference PredictorCorrector driving GpuSolver (host integrator, device derivatives) ----
+        SharedPtr<Storage> sa = makeShared<Storage>(base->clone(VisitorEnum::ALL_BUFFERS));
+        SharedPtr<Storage> sb = makeShared<Storage>(base->clone(VisitorEnum::ALL_BUFFERS));
+        SharedPtr<Storage> sc = makeShared<Storage>(base->clone(VisitorEnum::ALL_BUFFERS));
+        AutoPtr<ITimeStepping> ta = Factory::getTimeStepping(settings, sa);
+        AutoPtr<ITimeStepping> tb = Factory::getTimeStepping(settings, sb);
+        GpuSolver gpuSolver2(*scheduler, settings, eqs);
+        GpuPredictorCorrector tc(sc, settings, gpuSolver2);
+        bool dtOk = true;
+        for (int s = 0; s < steps; ++s) {
+            ta->step(*scheduler, refSolver, statsA);
+            tb->step(*scheduler, gpuSolver, statsB);
+            Statistics statsC;
+            statsC.set(StatisticsId::RUN_TIME, 0._f);
+            tc.step(*scheduler, gpuSolver2, statsC);
+            dtOk &= std::abs(ta->getTimeStep() - tb->getTimeStep()) <= 1.e-9 * ta->getTimeStep();
+            dtOk &= std::abs(ta->getTimeStep() - tc.getTimeStep()) <= 1.e-9 * ta->getTimeStep();
+            printf("  step %d: dt ref %.12e  host-PC+GpuSolver %.12e  GpuPredictorCorrector %.12e\n", s, double(ta->getTimeStep()),
+                double(tb->getTimeStep()), double(tc.getTimeStep()));
+        }
+        expect(dtOk, "time steps agree to 1e-9");
+        expect(compareStorages(*sa, *sb, false, "PredictorCorrector + GpuSolver") <= 1.e-9, "state after PC steps (host integrator + GpuSolver) within 1e-9");
+        tc.syncToHost();
+        expect(compareStorages(*sa, *sc, false, "GpuPredictorCorrector") <= 1.e-9, "state after device-resident PC steps within 1e-9");
+
+        // ---- 3. unsupported setups throw InvalidSetup instead of silently running elsewhere ----
+        bool thrown = false;
+        try {
+            RunSettings s2 = settings;
+            s2.set(RunSettingsId::SPH_USE_XSPH, true);
+            GpuSolver bad(*scheduler, s2, getStandardEquations(s2));
+        } catch (const InvalidSetup&) {
+            thrown = true;
+        }
+        expect(thrown, "equation set with XSph is rejected with InvalidSetup");
+        thrown = false;
+        try {
+            RunSettings s3 = settings;
+            s3.set(RunSettingsId::SPH_DISCRETIZATION, DiscretizationEnum::BENZ_ASPHAUG);
+            GpuSolver bad(*scheduler, s3, getStandardEquations(s3));
+            Storage c = base->clone(VisitorEnum::ALL_BUFFERS);
+            bad.integrate(c, statsA);
+        } catch (const InvalidSetup&) {
+            thrown = true;
+        }
+        expect(thrown, "BENZ_ASPHAUG discretisation is rejected with InvalidSetup");
+    } catch (const std::exception& e) {
+        printf("FAIL  exception: %s\n", e.what());
+        failures++;
+    }
+    printf(failures == 0 ? "DROPIN PASS\n" : "DROPIN FAILED (%d)\n", failures);
+    return failures == 0 ? 0 : 1;
+}

@@ -181,3 +181,17 @@ def test_empty_and_tiny_inputs(lut):
         st = eng.integrate()
         assert st.pair_count == 0 or n == 2
         eng.close()
+
+
+def test_cpp_dropin_through_isolver():
+    """The C++ drop-in (opensph_b200/host/GpuSolver.cpp, built against the reference headers) next to the reference's
+    own AsymmetricSolver / PredictorCorrector on identical Storages; see tests/dropin/dropin_test.cpp."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_test not built (needs /root/reference at build time)")
+    out = subprocess.run([exe, "20000", "3"], capture_output=True, text=True, timeout=600)
+    print(out.stdout[-3000:])
+    assert out.returncode == 0 and "DROPIN PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-500:]
