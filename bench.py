@@ -28,7 +28,7 @@ UNIT = "particle-updates/s"
 # Algorithmic HBM bytes per particle-update, SURVEY.md section 8(d), solid + correction tensor:
 BYTES_FULL_STEP = 1412.0      # full PredictorCorrector step
 BYTES_INTEGRATE = 628.0       # find + derivatives (integrate() only)
-BYTES_PAIR_KERNEL = 440.0     # dominant kernel, itemised in DESIGN.md (sorted record in, derivatives out)
+BYTES_PAIR_KERNEL = 408.0     # dominant kernel, itemised in DESIGN.md section 3 (sorted record + epilogue inputs in, derivatives out)
 
 
 def read_peaks():
