@@ -9,6 +9,8 @@
 // Phase 2    : every thread walks its list; the exact FP64 predicate (bit-identical neighbour sets) and the FP64 pair
 //              arithmetic run with (nearly) full lanes -- no divergence on the expensive path.
 // Per-target sums stay in registers; nothing is accumulated with atomics (asymmetric formulation).
+// Staging uses the TMA bulk-copy engine: one thread issues cp.async.bulk (global -> shared, completion on an mbarrier)
+// for each contiguous candidate row, the rest of the CTA only waits on the barrier's phase.
 //
 // Replaces the reference hot loop AsymmetricSolver.cpp:174-201 (finder.findAll + filter + kernel.grad +
 // derivatives.eval) -- see pair.cu for the epilogue it shares with the direct variant.
@@ -20,12 +22,43 @@ constexpr int TILE_T = 128;   // targets (threads) per work unit
 constexpr int TILE_C = 576;   // staged candidates per chunk
 constexpr int LIST_CAP = 64;  // private list entries per round
 
+constexpr int TILE_X = 20;    // cell-range entries cached in shared memory per candidate row
+
 template <bool SOLID>
 struct TileLayout {
-    static constexpr int G = SOLID ? REC_SOLID : REC_FLUID; // global record stride (doubles)
-    static constexpr int S = SOLID ? 18 : 14;                // shared record stride: 9 or 7 (odd) x 16 B
+    static constexpr int G = SOLID ? REC_SOLID : REC_FLUID; // record stride (doubles), same in global and shared memory:
+    static constexpr int S = G;                              // 9 or 7 (odd) x 16 B => conflict-free consecutive records
     static constexpr size_t bytes = (size_t)TILE_C * S * 8 + (size_t)TILE_C * 16 + (size_t)LIST_CAP * TILE_T * 2;
 };
+
+// ---- TMA bulk copy + mbarrier (raw PTX; sm_90+ / sm_100a) -----------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCopyG2S(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smemAddr(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void fenceProxyAsync() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 // ---- work list: segments of <= 128 targets per cell row ------------------------------------------------------
 __global__ void __launch_bounds__(256) k_row_segments(DevicePointers d, uint32_t maxCells) {
@@ -58,6 +91,7 @@ struct ChunkState {
     uint32_t beg[3], end[3], base[3]; // per dy row: global sorted range staged in this chunk and its smem offset
     uint32_t used;
     int z;                            // slab (absolute cell z) of this chunk
+    uint32_t cells[3][TILE_X + 2];    // cellStart[row base + x0 ...] of the three candidate rows (x0 .. x1+1)
 };
 
 struct ChunkCursor { // iteration state of the chunk builder (thread 0 only)
@@ -124,6 +158,18 @@ __device__ __forceinline__ void nextChunk(const DevicePointers& d, ChunkCursor& 
     }
     cs.used = used;
     cs.z = z;
+    if (used > 0 && x1 - x0 + 2 <= TILE_X + 2) {
+        for (int r = 0; r < 3; ++r) {
+            const int y = cy + r - 1;
+            if (y < 0 || y >= dimy) {
+                continue;
+            }
+            const uint32_t rb = (uint32_t)((z * dimy + y) * dimx);
+            for (int c = x0; c <= x1 + 1; ++c) {
+                cs.cells[r][c - x0] = d.cellStart[rb + c];
+            }
+        }
+    }
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
@@ -136,6 +182,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     __shared__ ChunkState csBuf[2];
     __shared__ float sKey[TILE_T];
     __shared__ uint16_t sPerm[TILE_T];
+    __shared__ __align__(8) uint64_t stageBar;
 
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
@@ -143,6 +190,11 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     const int tid = threadIdx.x;
     const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
     ChunkCursor cur;
+    uint32_t stagePhase = 0;
+    if (tid == 0) {
+        mbarInit(&stageBar, 1);
+    }
+    __syncthreads();
 
     for (uint32_t unit = blockIdx.x; unit < totalSegs; unit += gridDim.x) {
         const uint32_t row = d.segRow[unit];
@@ -214,25 +266,25 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             if (cs.used == 0) {
                 break;
             }
-            // ---- stage the chunk: FP64 records + FP32 relative positions ----
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const uint32_t b = cs.beg[r], n = cs.end[r] - b, base = cs.base[r];
-                for (uint32_t c = tid; c < n; c += TILE_T) {
-                    const double2* src = reinterpret_cast<const double2*>(d.rec + (size_t)(b + c) * L::G);
-                    double2* dst = reinterpret_cast<double2*>(recS + (size_t)(base + c) * L::S);
-                    const double2 a0 = src[0], a1 = src[1];
-                    dst[0] = a0;
-                    dst[1] = a1;
-#pragma unroll
-                    for (int w = 2; w < L::G / 2; ++w) {
-                        dst[w] = src[w];
-                    }
-                    f4[base + c] = make_float4((float)(a0.x - oxy.x), (float)(a0.y - oxy.y), (float)(a1.x - oz), (float)a1.y);
-                }
-            }
+            // ---- stage the chunk: TMA bulk copies of the FP64 records (one per candidate row), then the FP32 copies ----
             if (tid == 0) {
-                nextChunk(d, cur, csBuf[buf ^ 1], cy, cz, x0, x1, dimx, dimy, dimz); // overlaps with the others' staging
+                fenceProxyAsync(); // the buffer was last read through the generic proxy
+                mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8));
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const uint32_t n = cs.end[r] - cs.beg[r];
+                    if (n > 0) {
+                        bulkCopyG2S(recS + (size_t)cs.base[r] * L::S, d.rec + (size_t)cs.beg[r] * L::G, n * (uint32_t)(L::G * 8), &stageBar);
+                    }
+                }
+                nextChunk(d, cur, csBuf[buf ^ 1], cy, cz, x0, x1, dimx, dimy, dimz); // overlaps with the copies
+            }
+            mbarWait(&stageBar, stagePhase);
+            stagePhase ^= 1;
+            for (uint32_t c = tid; c < cs.used; c += TILE_T) {
+                const double2* src = reinterpret_cast<const double2*>(recS + (size_t)c * L::S);
+                const double2 a0 = src[0], a1 = src[1];
+                f4[c] = make_float4((float)(a0.x - oxy.x), (float)(a0.y - oxy.y), (float)(a1.x - oz), (float)a1.y);
             }
             __syncthreads();
             buf ^= 1;
@@ -262,9 +314,14 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                                 c0 = max(max(c0, cx - 1), 0);
                                 c1 = min(min(c1, cx + 1), dimx - 1);
                                 if (c0 <= c1) {
-                                    const uint32_t rb = (uint32_t)((z * dimy + cy + r - 1) * dimx);
-                                    gpos = max(d.cellStart[rb + c0], b);
-                                    ghi = min(d.cellStart[rb + c1 + 1], e);
+                                    if (x1 - x0 + 2 <= TILE_X + 2) {
+                                        gpos = max(cs.cells[r][c0 - x0], b);
+                                        ghi = min(cs.cells[r][c1 + 1 - x0], e);
+                                    } else {
+                                        const uint32_t rb = (uint32_t)((z * dimy + cy + r - 1) * dimx);
+                                        gpos = max(d.cellStart[rb + c0], b);
+                                        ghi = min(d.cellStart[rb + c1 + 1], e);
+                                    }
                                     gbase = cs.base[r] - b; // smem index = gbase + global index (mod 2^32)
                                 }
                             }

@@ -41,7 +41,7 @@ enum RecField : int {
     R_X, R_Y, R_Z, R_H, R_VX, R_VY, R_VZ, R_M, R_RHO, R_P, R_CS, R_VOL, R_S0, R_S1, R_S2, R_S3, R_S4, R_GRP, R_SOLID_COUNT
 };
 constexpr int REC_SOLID = 18; // doubles per record, solid
-constexpr int REC_FLUID = 12; // doubles per record, fluid (x..vol)
+constexpr int REC_FLUID = 14; // doubles per record, fluid (x..vol + 16 B pad: 7 x 16 B, odd, same stride in shared memory)
 
 struct GridDev {
     double lo[3];
