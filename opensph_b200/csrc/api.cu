@@ -171,7 +171,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     }
 
     const size_t cap = capacity;
-    ctx->maxCells = std::max<uint32_t>(capacity, 4096u);
+    ctx->maxCells = std::max<uint32_t>(capacity / 4, 4096u);
     ctx->scanBlocks = (ctx->maxCells + 1 + SCAN_ITEMS - 1) / SCAN_ITEMS;
 #define SPH_TRY(expr)                                                                                                 \
     do {                                                                                                              \
@@ -200,9 +200,9 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         SPH_TRY(devAlloc(&ctx->d.u[u], cap));
     }
     SPH_TRY(devAlloc(&ctx->d.rec, cap * (size_t)(ctx->solid ? REC_SOLID : REC_FLUID)));
-    ctx->maxSegs = capacity / 128 + ctx->maxCells + 2;
+    ctx->maxSegs = capacity / 64 + ctx->maxCells + 2; // next-fit packing: units <= 2 N / 128 + double rows
     SPH_TRY(devAlloc(&ctx->d.segStart, (size_t)ctx->maxCells + 2));
-    SPH_TRY(devAlloc(&ctx->d.segRow, (size_t)ctx->maxSegs));
+    SPH_TRY(devAlloc(&ctx->d.unitDesc, (size_t)ctx->maxSegs));
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
     SPH_TRY(devAlloc(&ctx->d.order, cap));
     SPH_TRY(devAlloc(&ctx->d.cellOf, cap));
@@ -247,7 +247,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
-    cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.segRow);
+    cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree(ctx->staging);

@@ -4,9 +4,10 @@
 // core/objects/finders/KdTree.inl.h:10-41; LookupMap::update, core/objects/containers/LookupMap.h:31-45) and
 // IAsymmetricSolver::getMaxSearchRadius (core/sph/solvers/AsymmetricSolver.cpp:104-111).
 //
-// The cell edge is R * h_max (x 1+1e-6), so every neighbour j of i (|r_i - r_j| < R (h_i + h_j)/2 <= R h_max)
-// lies in the 3x3x3 block of cells around i. If that would need more than maxCells cells the edge is enlarged,
-// like the reference's UniformGridFinder caps its grid at (cbrt(N)+1)^3 cells (UniformGrid.cpp:16).
+// The cell edge is a = R * h_max (x 1+1e-6) in x and y and a/2 in z, so every neighbour j of i
+// (|r_i - r_j| < R (h_i + h_j)/2 <= R h_max) lies within +-1 cell in x,y and +-2 cells in z. The half-height cells let
+// the tiled pair kernel pair the z-layers (-2,+3), (-1,+2), (0,+1) of a double row so that its warps stay balanced.
+// If that would need more than maxCells cells the edge is enlarged, like the reference's UniformGridFinder caps its grid at (cbrt(N)+1)^3 cells (UniformGrid.cpp:16).
 #include "sphgpu_internal.h"
 
 namespace sph {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPart
         for (int iter = 0; iter < 64; ++iter) {
             double total = 1.;
             for (int k = 0; k < 3; ++k) {
-                total *= floor(ext[k] / cell) + 1.;
+                total *= floor(ext[k] / (k == 2 ? 0.5 * cell : cell)) + 1.;
             }
             if (total <= (double)maxCells) {
                 break;
@@ -114,9 +115,11 @@ __global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPart
         }
         g.cell = cell;
         g.cellInv = 1. / cell;
+        g.cellZ = 0.5 * cell;
+        g.cellZInv = 1. / g.cellZ;
         uint32_t n = 1;
         for (int k = 0; k < 3; ++k) {
-            g.dim[k] = (int)floor(ext[k] / cell) + 1;
+            g.dim[k] = (int)floor(ext[k] / (k == 2 ? g.cellZ : cell)) + 1;
             n *= (uint32_t)g.dim[k];
         }
         g.ncells = n;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPart
 __device__ __forceinline__ uint32_t cellIndex(const GridDev& g, double x, double y, double z) {
     int cx = (int)floor((x - g.lo[0]) * g.cellInv);
     int cy = (int)floor((y - g.lo[1]) * g.cellInv);
-    int cz = (int)floor((z - g.lo[2]) * g.cellInv);
+    int cz = (int)floor((z - g.lo[2]) * g.cellZInv);
     cx = min(max(cx, 0), g.dim[0] - 1);
     cy = min(max(cy, 0), g.dim[1] - 1);
     cz = min(max(cz, 0), g.dim[2] - 1);

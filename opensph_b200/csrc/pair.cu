@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) k_pair_direct(DevicePointers d, uint32_t 
         const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
         const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+        for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
             for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
                 const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
                 const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint3
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
     uint32_t cnt = 0;
     const unsigned long long base = FILL ? offsets[i] : 0ull;
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+    for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
         for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
             const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
             const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];

@@ -1,16 +1,22 @@
 // Tiled pair kernel: the production variant of the fused neighbour search + pair sums.
 //
-// Work unit  = up to 128 consecutive sorted targets of ONE cell row (same cy, cz), one target per thread.
-// Candidates = the three cell rows of a z-slab (dy = -1,0,1) restricted to the x-range the unit's targets can reach,
-//              staged in shared memory as 144-byte FP64 records (double2 moves, odd 16-byte stride => consecutive
-//              records fall into different bank groups) plus an FP32 {x,y,z,h} copy relative to a unit-local origin.
-// Phase 1    : every thread scans the candidates of ITS OWN 3 cells per row with a conservative FP32 distance test
-//              (cheap, runs on the FP32/ALU pipes) and appends the survivors to a private list in shared memory.
-// Phase 2    : every thread walks its list; the exact FP64 predicate (bit-identical neighbour sets) and the FP64 pair
-//              arithmetic run with (nearly) full lanes -- no divergence on the expensive path.
-// Per-target sums stay in registers; nothing is accumulated with atomics (asymmetric formulation).
-// Staging uses the TMA bulk-copy engine: one thread issues cp.async.bulk (global -> shared, completion on an mbarrier)
-// for each contiguous candidate row, the rest of the CTA only waits on the barrier's phase.
+// Grid       : cells are a x a x a/2 (a = R h_max); a "double row" is the two half-height cell rows (cy, 2k), (cy, 2k+1).
+// Work unit  = up to 128 targets of ONE double row restricted to a cell range [cA, cB] in x, one target per thread,
+//              per-target sums in registers, no atomics (asymmetric formulation).
+// Candidates = the six z-layers 2k-2 .. 2k+3 (three cell rows dy = -1,0,1 each) restricted to cells [cA-1, cB+1]. They
+//              are processed as three CHUNKS that pair layers symmetrically: far (2k-2, 2k+3), near (2k-1, 2k+2),
+//              centre (2k, 2k+1). With the lanes ordered by z, every warp then sees about the same number of
+//              neighbours in every chunk (measured on the hex lattice: 5/19/45 per chunk for all four z-bands, versus
+//              25/43/0 ... 0/43/25 when whole layers are processed one after the other), so the CTA-wide barrier at the
+//              chunk boundaries costs little.
+// Staging    : one thread issues TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier), one per
+//              contiguous candidate row; records are 144-byte FP64 structures (odd 16-byte stride => consecutive
+//              records fall into different bank groups); an FP32 {x,y,z,h} copy relative to a unit-local origin is
+//              derived from them.
+// Phase 1    : every thread scans the candidates of the cells IT can reach (row-wise interval culling in y, z and x)
+//              with a conservative FP32 distance test (FP32/ALU pipes) and appends survivors to a private u16 list.
+// Phase 2    : every thread walks its list two entries at a time; the exact FP64 predicate (bit-identical neighbour
+//              sets) enters the branch-free FP64 pair body as a mask -- full lanes, no divergence on the expensive path.
 //
 // Replaces the reference hot loop AsymmetricSolver.cpp:174-201 (finder.findAll + filter + kernel.grad +
 // derivatives.eval) -- see pair.cu for the epilogue it shares with the direct variant.
@@ -21,8 +27,8 @@ namespace sph {
 constexpr int TILE_T = 128;   // targets (threads) per work unit
 constexpr int TILE_C = 576;   // staged candidates per chunk
 constexpr int LIST_CAP = 64;  // private list entries per round
-
 constexpr int TILE_X = 20;    // cell-range entries cached in shared memory per candidate row
+constexpr int CHUNK_ROWS = 6; // candidate rows per chunk: 2 z-layers x 3 y-rows
 
 template <bool SOLID>
 struct TileLayout {
@@ -60,86 +66,120 @@ __device__ __forceinline__ void fenceProxyAsync() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ---- work list: segments of <= 128 targets per cell row ------------------------------------------------------
-__global__ void __launch_bounds__(256) k_row_segments(DevicePointers d, uint32_t maxCells) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > maxCells) {
+// ---- work list: units of <= 128 targets per double row (next-fit packing of cell columns) ----------------------
+// One thread per double row walks its cells in x; FILL = false counts the units, FILL = true writes the descriptors
+// {double row, cA | cB << 16, skip, total}: the unit takes targets [skip, skip + 128) of the concatenation
+// (lower row cells cA..cB) ++ (upper row cells cA..cB).
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCells) {
+    const uint32_t dr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dr > maxCells || (FILL && dr >= maxCells)) {
         return;
     }
     const GridDev g = *d.grid;
-    const uint32_t rows = (uint32_t)(g.dim[1] * g.dim[2]);
-    uint32_t nseg = 0;
-    if (r < rows) {
-        const uint32_t cnt = d.cellStart[(r + 1) * (uint32_t)g.dim[0]] - d.cellStart[r * (uint32_t)g.dim[0]];
-        nseg = (cnt + TILE_T - 1) / TILE_T;
-    }
-    d.cellCount[r] = nseg; // cellCount is free once cellStart has been built
-}
-
-__global__ void __launch_bounds__(256) k_fill_segments(DevicePointers d, uint32_t maxCells) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= maxCells) {
+    const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
+    const uint32_t doubleRows = (uint32_t)dimy * (uint32_t)((dimz + 1) / 2);
+    if (dr >= doubleRows) {
+        if (!FILL) {
+            d.cellCount[dr] = 0; // cellCount is free once cellStart has been built
+        }
         return;
     }
-    const uint32_t s = d.segStart[r], e = d.segStart[r + 1];
-    for (uint32_t k = s; k < e; ++k) {
-        d.segRow[k] = r;
+    const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
+    const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
+    const bool hasU = 2 * k + 1 < dimz;
+    const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
+    uint32_t units = 0;
+    const uint32_t out = FILL ? d.segStart[dr] : 0u;
+    int cA = 0, cLast = 0;
+    uint32_t acc = 0;
+    auto emit = [&](int a, int b, uint32_t total) {
+        const uint32_t parts = (total + TILE_T - 1) / TILE_T;
+        if (FILL) {
+            for (uint32_t p = 0; p < parts; ++p) {
+                d.unitDesc[out + units + p] = make_uint4(dr, (uint32_t)a | ((uint32_t)b << 16), p * TILE_T, total);
+            }
+        }
+        units += parts;
+    };
+    for (int c = 0; c < dimx; ++c) {
+        uint32_t cnt = d.cellStart[rbL + c + 1] - d.cellStart[rbL + c];
+        if (hasU) {
+            cnt += d.cellStart[rbU + c + 1] - d.cellStart[rbU + c];
+        }
+        if (cnt == 0) {
+            continue;
+        }
+        // close the open unit when the column does not fit or the x-range would outgrow the cached cell table
+        if (acc > 0 && (acc + cnt > (uint32_t)TILE_T || c - cA + 3 > TILE_X)) {
+            emit(cA, cLast, acc);
+            acc = 0;
+        }
+        if (acc == 0) {
+            cA = c;
+        }
+        acc += cnt;
+        cLast = c;
+        if (acc >= (uint32_t)TILE_T) { // a single column with more than 128 targets is split by `skip`
+            emit(cA, cLast, acc);
+            acc = 0;
+        }
+    }
+    if (acc > 0) {
+        emit(cA, cLast, acc);
+    }
+    if (!FILL) {
+        d.cellCount[dr] = units;
     }
 }
 
 struct ChunkState {
-    uint32_t beg[3], end[3], base[3]; // per dy row: global sorted range staged in this chunk and its smem offset
+    uint32_t beg[CHUNK_ROWS], end[CHUNK_ROWS], base[CHUNK_ROWS]; // staged global range per candidate row + smem offset
     uint32_t used;
-    int z;                            // slab (absolute cell z) of this chunk
-    uint32_t cells[3][TILE_X + 2];    // cellStart[row base + x0 ...] of the three candidate rows (x0 .. x1+1)
+    int chunk;                                  // 0 far, 1 near, 2 centre
+    uint32_t cells[CHUNK_ROWS][TILE_X + 2];     // cellStart[row base + x0 ...] of the candidate rows (x0 .. x1+1)
 };
 
 struct ChunkCursor { // iteration state of the chunk builder (thread 0 only)
-    int dz, dy;
+    int chunk, row;
     uint32_t pos;
     int posValid;
 };
 
-/// Next chunk of the unit: as many whole / partial candidate rows of the current z-slab as fit into TILE_C records.
-__device__ __forceinline__ void nextChunk(const DevicePointers& d, ChunkCursor& cur, ChunkState& cs, int cy, int cz, int x0, int x1,
-    int dimx, int dimy, int dimz) {
+/// z-layer (absolute half-height cell index) of candidate row `r` (0..5) of chunk `c` for the double row k.
+__device__ __forceinline__ int chunkLayer(int c, int r, int k) {
+    const int lo = (c == 0) ? 2 * k - 2 : (c == 1 ? 2 * k - 1 : 2 * k);
+    const int hi = (c == 0) ? 2 * k + 3 : (c == 1 ? 2 * k + 2 : 2 * k + 1);
+    return r < 3 ? lo : hi;
+}
+
+/// Next chunk of the unit: as many whole / partial candidate rows of the current layer pair as fit into TILE_C records.
+/// rowBeg/rowEnd hold the global sorted ranges of the unit's 18 candidate rows (3 chunks x 6 rows; empty if outside).
+__device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t* rowEnd, ChunkCursor& cur, ChunkState& cs) {
     uint32_t used = 0;
-    for (int r = 0; r < 3; ++r) {
+    for (int r = 0; r < CHUNK_ROWS; ++r) {
         cs.beg[r] = cs.end[r] = cs.base[r] = 0;
     }
-    int z = 0;
-    while (cur.dz <= 1) {
-        z = cz + cur.dz;
-        if (z < 0 || z >= dimz) {
-            cur.dz++;
-            cur.dy = 0;
-            cur.posValid = 0;
-            continue;
-        }
+    int chunk = 0;
+    while (cur.chunk < 3) {
+        chunk = cur.chunk;
         bool full = false;
-        while (cur.dy < 3) {
-            const int y = cy + cur.dy - 1;
-            if (y < 0 || y >= dimy) {
-                cur.dy++;
-                cur.posValid = 0;
-                continue;
-            }
-            const uint32_t rb = (uint32_t)((z * dimy + y) * dimx);
-            const uint32_t rowEnd = d.cellStart[rb + x1 + 1];
+        while (cur.row < CHUNK_ROWS) {
+            const uint32_t rb = rowBeg[chunk * CHUNK_ROWS + cur.row], re = rowEnd[chunk * CHUNK_ROWS + cur.row];
             if (!cur.posValid) {
-                cur.pos = d.cellStart[rb + x0];
+                cur.pos = rb;
                 cur.posValid = 1;
             }
-            const uint32_t take = min(rowEnd - cur.pos, (uint32_t)TILE_C - used);
+            const uint32_t take = re > cur.pos ? min(re - cur.pos, (uint32_t)TILE_C - used) : 0u;
             if (take > 0) {
-                cs.beg[cur.dy] = cur.pos;
-                cs.end[cur.dy] = cur.pos + take;
-                cs.base[cur.dy] = used;
+                cs.beg[cur.row] = cur.pos;
+                cs.end[cur.row] = cur.pos + take;
+                cs.base[cur.row] = used;
                 used += take;
                 cur.pos += take;
             }
-            if (cur.pos >= rowEnd) {
-                cur.dy++;
+            if (cur.pos >= re) {
+                cur.row++;
                 cur.posValid = 0;
             } else {
                 full = true;
@@ -149,27 +189,15 @@ __device__ __forceinline__ void nextChunk(const DevicePointers& d, ChunkCursor& 
         if (full) {
             break;
         }
-        cur.dz++; // slab finished; a chunk never mixes slabs
-        cur.dy = 0;
+        cur.chunk++; // layer pair finished; a chunk never mixes layer pairs
+        cur.row = 0;
         cur.posValid = 0;
         if (used > 0) {
             break;
         }
     }
     cs.used = used;
-    cs.z = z;
-    if (used > 0 && x1 - x0 + 2 <= TILE_X + 2) {
-        for (int r = 0; r < 3; ++r) {
-            const int y = cy + r - 1;
-            if (y < 0 || y >= dimy) {
-                continue;
-            }
-            const uint32_t rb = (uint32_t)((z * dimy + y) * dimx);
-            for (int c = x0; c <= x1 + 1; ++c) {
-                cs.cells[r][c - x0] = d.cellStart[rb + c];
-            }
-        }
-    }
+    cs.chunk = chunk;
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
@@ -183,10 +211,11 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     __shared__ float sKey[TILE_T];
     __shared__ uint16_t sPerm[TILE_T];
     __shared__ __align__(8) uint64_t stageBar;
+    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
 
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
-    const uint32_t totalSegs = d.segStart[maxCells];
+    const uint32_t totalUnits = d.segStart[maxCells];
     const int tid = threadIdx.x;
     const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
     ChunkCursor cur;
@@ -196,26 +225,38 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     }
     __syncthreads();
 
-    for (uint32_t unit = blockIdx.x; unit < totalSegs; unit += gridDim.x) {
-        const uint32_t row = d.segRow[unit];
-        const uint32_t seg = unit - d.segStart[row];
-        const int cy = (int)(row % (uint32_t)dimy), cz = (int)(row / (uint32_t)dimy);
-        const uint32_t rowBase = row * (uint32_t)dimx;
-        const uint32_t tBeg = d.cellStart[rowBase] + seg * TILE_T;
-        const uint32_t tEnd = min(tBeg + (uint32_t)TILE_T, d.cellStart[rowBase + dimx]);
-        // x-range of cells the unit's targets occupy, and the unit-local origin of the FP32 copies
-        const int cxA = (int)(d.sCell[tBeg] - rowBase), cxB = (int)(d.sCell[tEnd - 1] - rowBase);
-        const int x0 = max(cxA - 1, 0), x1 = min(cxB + 1, dimx - 1);
-        const double2 oxy = reinterpret_cast<const double2*>(d.rec + (size_t)tBeg * L::G)[0];
-        const double oz = d.rec[(size_t)tBeg * L::G + R_Z];
+    for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
+        const uint4 desc = d.unitDesc[unit];
+        const uint32_t dr = desc.x;
+        const int cA = (int)(desc.y & 0xffffu), cB = (int)(desc.y >> 16);
+        const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
+        const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
+        const bool hasU = 2 * k + 1 < dimz;
+        const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
+        const uint32_t lBeg = d.cellStart[rbL + cA], lCnt = d.cellStart[rbL + cB + 1] - lBeg;
+        const uint32_t uBeg = hasU ? d.cellStart[rbU + cA] : 0u, uCnt = hasU ? d.cellStart[rbU + cB + 1] - uBeg : 0u;
+        const uint32_t total = lCnt + uCnt, skip = desc.z;
+        const uint32_t nLive = min((uint32_t)TILE_T, total - skip);
+        const int x0 = max(cA - 1, 0), x1 = min(cB + 1, dimx - 1);
+        // unit-local origin of the FP32 copies: corner of the unit's first cell
+        const double ox = g.lo[0] + cA * g.cell, oy = g.lo[1] + cy * g.cell, oz = g.lo[2] + (2 * k) * g.cellZ;
         // absolute error bound of the FP32 relative coordinates (2^-24 * extent per coordinate) with a wide safety factor
-        const float slack = (float)((double)(x1 - x0 + 2) * g.cell * 1.e-6);
+        const float slack = (float)((double)(x1 - x0 + 3) * g.cell * 1.e-6);
 
         // ---- lane assignment: order the unit's targets by z so that the lanes of a warp see similar numbers of
-        // neighbours in every z-slab (balanced private lists => full lanes in phase 2)
-        {
-            const uint32_t t0 = tBeg + tid;
-            sKey[tid] = (t0 < tEnd) ? (float)(d.rec[(size_t)t0 * L::G + R_Z] - oz) : 3.0e38f;
+        // neighbours in every chunk (balanced private lists => full lanes in phase 2)
+        auto targetIndex = [&](uint32_t j) { return j < lCnt ? lBeg + j : uBeg + (j - lCnt); };
+        sKey[tid] = ((uint32_t)tid < nLive) ? (float)(d.rec[(size_t)targetIndex(skip + tid) * L::G + R_Z] - oz) : 3.0e38f;
+        if (tid < 3 * CHUNK_ROWS) { // global ranges of the unit's 18 candidate rows
+            const int z = chunkLayer(tid / CHUNK_ROWS, tid % CHUNK_ROWS, k), y = cy + (tid % 3) - 1;
+            uint32_t rb = 0, re = 0;
+            if (z >= 0 && z < dimz && y >= 0 && y < dimy) {
+                const uint32_t base = (uint32_t)((z * dimy + y) * dimx);
+                rb = d.cellStart[base + x0];
+                re = d.cellStart[base + x1 + 1];
+            }
+            sRowBeg[tid] = rb;
+            sRowEnd[tid] = re;
         }
         __syncthreads();
         {
@@ -228,8 +269,10 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             sPerm[rank] = (uint16_t)tid;
         }
         __syncthreads();
-        const uint32_t t = tBeg + sPerm[tid];
-        const bool live = t < tEnd;
+        const bool live = (uint32_t)tid < nLive;
+        const uint32_t jOwn = skip + sPerm[tid];
+        const uint32_t t = live ? targetIndex(jOwn) : 0u;
+        const bool upper = live && jOwn >= lCnt;
         const uint32_t slot = live ? d.order[t] : 0xffffffffu;
         const bool target = live && slot < nOwned; // ghosts are neighbours only
 
@@ -239,25 +282,25 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
         double reach = 0.;
         if (live) {
             loadRecord<SOLID>(d.rec + (size_t)t * L::G, pi);
-            cx = (int)(d.sCell[t] - rowBase);
-            fxi = (float)(pi.x - oxy.x);
-            fyi = (float)(pi.y - oxy.y);
+            cx = (int)(d.sCell[t] - (upper ? rbU : rbL));
+            fxi = (float)(pi.x - ox);
+            fyi = (float)(pi.y - oy);
             fzi = (float)(pi.z - oz);
             fhi = (float)pi.h;
             reach = 0.5 * c_prm.kernel_radius * (pi.h + g.hmax) * (1. + 1.e-9); // >= R * hbar for every neighbour
+        } else {
+            pi.x = pi.y = pi.z = 0.;
+            pi.h = 1.;
         }
-        // distance of the target to the faces of its own cell in y and z (lower bounds, shrunk for rounding safety)
         const double tol = 1.e-9 * g.cell;
-        const double yLo = fmax(pi.y - (g.lo[1] + cy * g.cell) - tol, 0.), yHi = fmax((g.lo[1] + (cy + 1) * g.cell) - pi.y - tol, 0.);
-        const double zLo = fmax(pi.z - (g.lo[2] + cz * g.cell) - tol, 0.), zHi = fmax((g.lo[2] + (cz + 1) * g.cell) - pi.z - tol, 0.);
         Accum acc;
         accumZero(acc);
 
         if (tid == 0) {
-            cur.dz = -1;
-            cur.dy = 0;
+            cur.chunk = 0;
+            cur.row = 0;
             cur.posValid = 0;
-            nextChunk(d, cur, csBuf[0], cy, cz, x0, x1, dimx, dimy, dimz);
+            nextChunk(sRowBeg, sRowEnd, cur, csBuf[0]);
         }
         int buf = 0;
         while (true) {
@@ -271,20 +314,29 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                 fenceProxyAsync(); // the buffer was last read through the generic proxy
                 mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8));
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
+                for (int r = 0; r < CHUNK_ROWS; ++r) {
                     const uint32_t n = cs.end[r] - cs.beg[r];
                     if (n > 0) {
                         bulkCopyG2S(recS + (size_t)cs.base[r] * L::S, d.rec + (size_t)cs.beg[r] * L::G, n * (uint32_t)(L::G * 8), &stageBar);
                     }
                 }
-                nextChunk(d, cur, csBuf[buf ^ 1], cy, cz, x0, x1, dimx, dimy, dimz); // overlaps with the copies
+                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
+            }
+            // cell ranges of the candidate rows, one entry per thread (issued before waiting for the copies)
+            ChunkState& csw = csBuf[buf];
+            for (int e = tid; e < CHUNK_ROWS * (TILE_X + 2); e += TILE_T) {
+                const int r = e / (TILE_X + 2), c = x0 + e % (TILE_X + 2);
+                const int z = chunkLayer(cs.chunk, r, k), y = cy + (r % 3) - 1;
+                if (c <= x1 + 1 && z >= 0 && z < dimz && y >= 0 && y < dimy) {
+                    csw.cells[r][c - x0] = d.cellStart[(uint32_t)((z * dimy + y) * dimx) + c];
+                }
             }
             mbarWait(&stageBar, stagePhase);
             stagePhase ^= 1;
             for (uint32_t c = tid; c < cs.used; c += TILE_T) {
                 const double2* src = reinterpret_cast<const double2*>(recS + (size_t)c * L::S);
                 const double2 a0 = src[0], a1 = src[1];
-                f4[c] = make_float4((float)(a0.x - oxy.x), (float)(a0.y - oxy.y), (float)(a1.x - oz), (float)a1.y);
+                f4[c] = make_float4((float)(a0.x - ox), (float)(a0.y - oy), (float)(a1.x - oz), (float)a1.y);
             }
             __syncthreads();
             buf ^= 1;
@@ -292,44 +344,48 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                 continue;
             }
             // ---- private rounds: phase 1 (FP32 filter -> list), phase 2 (FP64 pairs) ----
-            const int z = cs.z;
-            const double dzMin = (z == cz) ? 0. : (z < cz ? zLo : zHi);
+            const int chunk = cs.chunk;
+            // the target's own record, if it is staged in this chunk (centre chunk, own layer, dy = 0)
+            const int selfRow = upper ? 4 : 1;
+            const double* self = recS + ((chunk == 2 && t >= cs.beg[selfRow] && t < cs.end[selfRow])
+                                                ? (size_t)(cs.base[selfRow] + (t - cs.beg[selfRow])) * L::S
+                                                : (size_t)TILE_C * L::S);
             int r = 0;
-            uint32_t gpos = 0, ghi = 0, gbase = 0;
+            uint32_t kpos = 0, khi = 0;
             bool open = false;
-            while (r < 3) {
+            while (r < CHUNK_ROWS) {
                 int cnt = 0;
-                while (r < 3) {
+                while (r < CHUNK_ROWS) {
                     if (!open) {
                         const uint32_t b = cs.beg[r], e = cs.end[r];
-                        gpos = ghi = 0;
+                        kpos = khi = 0;
                         if (e > b) {
-                            // x-interval of this candidate row the target can reach => cell sub-range [c0, c1]
-                            const double dyMin = (r == 1) ? 0. : (r == 0 ? yLo : yHi);
+                            // intervals of this candidate row in y and z, and the x-interval the target can reach in it
+                            const int z = chunkLayer(chunk, r, k), y = cy + (r % 3) - 1;
+                            const double yl = g.lo[1] + y * g.cell, zl = g.lo[2] + z * g.cellZ;
+                            const double dyMin = fmax(fmax(yl - pi.y, pi.y - (yl + g.cell)) - tol, 0.);
+                            const double dzMin = fmax(fmax(zl - pi.z, pi.z - (zl + g.cellZ)) - tol, 0.);
                             const double rem = reach * reach - dyMin * dyMin - dzMin * dzMin;
                             if (rem > 0.) {
                                 const double ext = sqrt(rem) * (1. + 1.e-9);
                                 int c0 = (int)floor((pi.x - ext - g.lo[0]) * g.cellInv);
                                 int c1 = (int)floor((pi.x + ext - g.lo[0]) * g.cellInv);
-                                c0 = max(max(c0, cx - 1), 0);
-                                c1 = min(min(c1, cx + 1), dimx - 1);
+                                c0 = max(max(c0, cx - 1), x0);
+                                c1 = min(min(c1, cx + 1), x1);
                                 if (c0 <= c1) {
-                                    if (x1 - x0 + 2 <= TILE_X + 2) {
-                                        gpos = max(cs.cells[r][c0 - x0], b);
-                                        ghi = min(cs.cells[r][c1 + 1 - x0], e);
-                                    } else {
-                                        const uint32_t rb = (uint32_t)((z * dimy + cy + r - 1) * dimx);
-                                        gpos = max(d.cellStart[rb + c0], b);
-                                        ghi = min(d.cellStart[rb + c1 + 1], e);
+                                    // smem index = base + (global index - beg); the staged piece may be a part of the row
+                                    const uint32_t glo = max(cs.cells[r][c0 - x0], b), ghi = min(cs.cells[r][c1 + 1 - x0], e);
+                                    if (ghi > glo) {
+                                        kpos = cs.base[r] + (glo - b);
+                                        khi = cs.base[r] + (ghi - b);
                                     }
-                                    gbase = cs.base[r] - b; // smem index = gbase + global index (mod 2^32)
                                 }
                             }
                         }
                         open = true;
                     }
                     // four candidates per trip: the loads are independent, only the list append is serial. The target
-                    // itself is not excluded here (672 compares) but masked in phase 2 (68 compares).
+                    // itself is not excluded here (~600 compares) but masked in phase 2 (~70 compares).
                     {
                         uint16_t* lp = list + cnt * TILE_T + tid;
 #define SPH_F32_TEST(C, K)                                                                                            \
@@ -343,24 +399,22 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             cnt++;                                                                                                    \
         }                                                                                                             \
     }
-                        while (gpos + 4 <= ghi && cnt + 4 <= LIST_CAP) {
-                            const uint32_t k0 = gbase + gpos;
-                            const float4 ca = f4[k0], cb = f4[k0 + 1], cc = f4[k0 + 2], cd = f4[k0 + 3];
-                            SPH_F32_TEST(ca, k0)
-                            SPH_F32_TEST(cb, k0 + 1)
-                            SPH_F32_TEST(cc, k0 + 2)
-                            SPH_F32_TEST(cd, k0 + 3)
-                            gpos += 4;
+                        while (kpos + 4 <= khi && cnt + 4 <= LIST_CAP) {
+                            const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
+                            SPH_F32_TEST(ca, kpos)
+                            SPH_F32_TEST(cb, kpos + 1)
+                            SPH_F32_TEST(cc, kpos + 2)
+                            SPH_F32_TEST(cd, kpos + 3)
+                            kpos += 4;
                         }
-                        while (gpos < ghi && ghi - gpos < 4 && cnt < LIST_CAP) {
-                            const uint32_t k0 = gbase + gpos;
-                            const float4 ca = f4[k0];
-                            SPH_F32_TEST(ca, k0)
-                            gpos++;
+                        while (kpos < khi && khi - kpos < 4 && cnt < LIST_CAP) {
+                            const float4 ca = f4[kpos];
+                            SPH_F32_TEST(ca, kpos)
+                            kpos++;
                         }
 #undef SPH_F32_TEST
                     }
-                    if (gpos >= ghi) {
+                    if (kpos >= khi) {
                         r++;
                         open = false;
                     } else {
@@ -368,7 +422,6 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                     }
                 }
                 // phase 2: two list entries per trip so the long per-pair chains overlap
-                const double* self = recS + ((t >= cs.beg[1] && t < cs.end[1]) ? (size_t)(cs.base[1] + (t - cs.beg[1])) * L::S : (size_t)TILE_C * L::S);
                 int q = 0;
                 for (; q + 1 < cnt; q += 2) {
                     const double* rp0 = recS + (size_t)list[q * TILE_T + tid] * L::S;
@@ -400,8 +453,8 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             const MaterialDev& mat = c_mats[d.u[U_MATID][slot]];
             double S[5] = { 0., 0., 0., 0., 0. };
             if (SOLID) {
-                for (int k = 0; k < 5; ++k) {
-                    S[k] = d.f[F_S0 + k][slot];
+                for (int q = 0; q < 5; ++q) {
+                    S[q] = d.f[F_S0 + q][slot];
                 }
             }
             Derivs out;
@@ -415,11 +468,11 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
 int launchSegments(sphgpu_ctx* ctx) {
     cudaStream_t st = ctx->stream;
     const uint32_t total = ctx->maxCells + 1;
-    k_row_segments<<<(total + 255) / 256, 256, 0, st>>>(ctx->d, ctx->maxCells);
+    k_units<false><<<(total + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
     k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.segStart, ctx->d.scanBlock, total);
     k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks);
     k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.segStart, ctx->d.scanBlock, total);
-    k_fill_segments<<<(ctx->maxCells + 255) / 256, 256, 0, st>>>(ctx->d, ctx->maxCells);
+    k_units<true><<<(ctx->maxCells + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
     ctx->launches += 5;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
@@ -436,7 +489,7 @@ static int launchTiledVariant(sphgpu_ctx* ctx) {
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const uint32_t upper = ctx->nActive / TILE_T + ctx->maxCells + 1; // >= number of segments
+    const uint32_t upper = ctx->nActive / (TILE_T / 2) + ctx->maxCells + 1; // >= number of units
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 2 * 8, std::max<uint32_t>(upper, 1u));
     kernel<<<grid, TILE_T, smem, ctx->stream>>>(ctx->d, ctx->n, ctx->maxCells);
     ctx->launches += 1;

@@ -45,7 +45,8 @@ constexpr int REC_FLUID = 14; // doubles per record, fluid (x..vol + 16 B pad: 7
 
 struct GridDev {
     double lo[3];
-    double cell, cellInv;
+    double cell, cellInv;   // cell edge in x and y: R * h_max (x 1+1e-6), possibly enlarged to cap the cell count
+    double cellZ, cellZInv; // cells are HALF as high in z (cell / 2): neighbours span +-1 cell in x,y and +-2 in z
     int dim[3];
     uint32_t ncells;
     double hmax;
@@ -71,8 +72,8 @@ struct DevicePointers {
     uint32_t* cellStart; // [maxCells + 1] exclusive prefix of counts
     uint32_t* cellCount; // [maxCells + 1]
     uint32_t* scanBlock; // block sums of the scan
-    uint32_t* segStart;  // [maxCells + 1] exclusive prefix of the number of 128-target segments per cell row
-    uint32_t* segRow;    // [maxSegs] row of every segment (work list of the tiled pair kernel)
+    uint32_t* segStart;  // [maxCells + 1] exclusive prefix of the number of work units per double row
+    uint4* unitDesc;     // [maxSegs] work units of the tiled pair kernel: {double row, cA | cB << 16, skip, total}
     double* boundsPartial; // [BOUNDS_BLOCKS * 8]
     const double* lut;
     GridDev* grid;
