@@ -242,6 +242,8 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
         const double ox = g.lo[0] + cA * g.cell, oy = g.lo[1] + cy * g.cell, oz = g.lo[2] + (2 * k) * g.cellZ;
         // absolute error bound of the FP32 relative coordinates (2^-24 * extent per coordinate) with a wide safety factor
         const float slack = (float)((double)(x1 - x0 + 3) * g.cell * 1.e-6);
+        const float cellF = (float)g.cell, cellZF = (float)g.cellZ, cellInvF = (float)g.cellInv;
+        const float guard = (float)((double)(x1 - x0 + 3) * g.cell * 1.e-5);
 
         // ---- lane assignment: order the unit's targets by z so that the lanes of a warp see similar numbers of
         // neighbours in every chunk (balanced private lists => full lanes in phase 2)
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
         Particle pi;
         int cx = 0;
         float fxi = 0.f, fyi = 0.f, fzi = 0.f, fhi = 0.f;
-        double reach = 0.;
+        float reachF = 0.f;
         if (live) {
             loadRecord<SOLID>(d.rec + (size_t)t * L::G, pi);
             cx = (int)(d.sCell[t] - (upper ? rbU : rbL));
@@ -287,12 +289,11 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             fyi = (float)(pi.y - oy);
             fzi = (float)(pi.z - oz);
             fhi = (float)pi.h;
-            reach = 0.5 * c_prm.kernel_radius * (pi.h + g.hmax) * (1. + 1.e-9); // >= R * hbar for every neighbour
+            reachF = (float)(0.5 * c_prm.kernel_radius * (pi.h + g.hmax) * (1. + 1.e-5)); // >= R * hbar for every neighbour
         } else {
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
         }
-        const double tol = 1.e-9 * g.cell;
         Accum acc;
         accumZero(acc);
 
@@ -360,16 +361,17 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                         const uint32_t b = cs.beg[r], e = cs.end[r];
                         kpos = khi = 0;
                         if (e > b) {
-                            // intervals of this candidate row in y and z, and the x-interval the target can reach in it
-                            const int z = chunkLayer(chunk, r, k), y = cy + (r % 3) - 1;
-                            const double yl = g.lo[1] + y * g.cell, zl = g.lo[2] + z * g.cellZ;
-                            const double dyMin = fmax(fmax(yl - pi.y, pi.y - (yl + g.cell)) - tol, 0.);
-                            const double dzMin = fmax(fmax(zl - pi.z, pi.z - (zl + g.cellZ)) - tol, 0.);
-                            const double rem = reach * reach - dyMin * dyMin - dzMin * dzMin;
-                            if (rem > 0.) {
-                                const double ext = sqrt(rem) * (1. + 1.e-9);
-                                int c0 = (int)floor((pi.x - ext - g.lo[0]) * g.cellInv);
-                                int c1 = (int)floor((pi.x + ext - g.lo[0]) * g.cellInv);
+                            // intervals of this candidate row in y and z, and the x-interval the target can reach in it:
+                            // FP32 relative to the unit origin with a guard band (cells were assigned in FP64)
+                            const int zrel = chunkLayer(chunk, r, 0), yrel = (r % 3) - 1; // relative to (2k, cy)
+                            const float yl = (float)yrel * cellF, zl = (float)zrel * cellZF;
+                            const float dyMin = fmaxf(fmaxf(yl - fyi, fyi - (yl + cellF)) - guard, 0.f);
+                            const float dzMin = fmaxf(fmaxf(zl - fzi, fzi - (zl + cellZF)) - guard, 0.f);
+                            const float rem = reachF * reachF - dyMin * dyMin - dzMin * dzMin;
+                            if (rem > 0.f) {
+                                const float ext = sqrtf(rem) * (1.f + 1.e-5f) + guard;
+                                int c0 = cA + (int)floorf((fxi - ext) * cellInvF);
+                                int c1 = cA + (int)floorf((fxi + ext) * cellInvF);
                                 c0 = max(max(c0, cx - 1), x0);
                                 c1 = min(min(c1, cx + 1), x1);
                                 if (c0 <= c1) {
