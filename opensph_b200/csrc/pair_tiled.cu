@@ -401,6 +401,19 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             cnt++;                                                                                                    \
         }                                                                                                             \
     }
+                        while (kpos + 8 <= khi && cnt + 8 <= LIST_CAP) {
+                            const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
+                            const float4 ce = f4[kpos + 4], cf = f4[kpos + 5], cg = f4[kpos + 6], ch = f4[kpos + 7];
+                            SPH_F32_TEST(ca, kpos)
+                            SPH_F32_TEST(cb, kpos + 1)
+                            SPH_F32_TEST(cc, kpos + 2)
+                            SPH_F32_TEST(cd, kpos + 3)
+                            SPH_F32_TEST(ce, kpos + 4)
+                            SPH_F32_TEST(cf, kpos + 5)
+                            SPH_F32_TEST(cg, kpos + 6)
+                            SPH_F32_TEST(ch, kpos + 7)
+                            kpos += 8;
+                        }
                         while (kpos + 4 <= khi && cnt + 4 <= LIST_CAP) {
                             const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
                             SPH_F32_TEST(ca, kpos)

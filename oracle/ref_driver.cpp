@@ -11,6 +11,7 @@
 // Commands
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
 //                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
+//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--criteria MASK]
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
@@ -182,6 +183,16 @@ RunSettings makeSettings(const std::string& config, const Args& args) {
     }
     if (args.has("const-h")) {
         settings.set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH, EMPTY_FLAGS);
+    }
+    if (args.has("enforcing")) { // AdaptiveSmoothingLength::enforce (EquationTerm.cpp:396-418)
+        settings.set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH,
+            SmoothingLengthEnum::CONTINUITY_EQUATION | SmoothingLengthEnum::SOUND_SPEED_ENFORCING);
+    }
+    if (args.has("continuity-undamaged")) { // ContinuityEnum::SUM_ONLY_UNDAMAGED (EquationTerm.cpp:302-313)
+        settings.set(RunSettingsId::SPH_CONTINUITY_MODE, ContinuityEnum::SUM_ONLY_UNDAMAGED);
+    }
+    if (args.has("sum-all")) { // SPH_SUM_ONLY_UNDAMAGED = false: no undamaged filter
+        settings.set(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED, false);
     }
     if (args.str("integrator") == "euler") {
         settings.set(RunSettingsId::TIMESTEPPING_INTEGRATOR, TimesteppingEnum::EULER_EXPLICIT);

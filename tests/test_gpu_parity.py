@@ -139,6 +139,10 @@ def test_variants_agree_on_seeded_random_input(lut):
     ["--config", "preset", "--n", 200000],                                         # configs[2] family
     ["--config", "preset_const_h", "--n", 30000, "--jitter", 5],
     ["--config", "fluid", "--n", 100000, "--jitter", 22],                          # configs[4] family
+    ["--config", "collision_preset", "--n", 20000, "--jitter", 14, "--enforcing"],            # SOUND_SPEED_ENFORCING
+    ["--config", "collision_preset", "--n", 20000, "--jitter", 15, "--continuity-undamaged"], # ContinuityEnum mode
+    ["--config", "collision_preset", "--n", 20000, "--jitter", 16, "--sum-all", "--corrected", 0],
+    ["--config", "hello", "--n", 20000, "--solver", "asym", "--jitter", 17, "--const-h", "--corrected", 1],
 ])
 def test_against_live_reference(args, tmp_path):
     i, o = run_ref(str(tmp_path), args + ["--neighbours"])

@@ -84,6 +84,10 @@ def test_time_steps_match_golden(name, integrator, lut):
     ["--config", "preset", "--n", 4000],
     ["--config", "preset_const_h", "--n", 3000, "--jitter", 2],
     ["--config", "fluid", "--n", 4000, "--jitter", 13],
+    ["--config", "collision_preset", "--n", 3000, "--jitter", 14, "--enforcing"],
+    ["--config", "collision_preset", "--n", 3000, "--jitter", 15, "--continuity-undamaged"],
+    ["--config", "collision_preset", "--n", 3000, "--jitter", 16, "--sum-all", "--corrected", 0],
+    ["--config", "hello", "--n", 3000, "--solver", "asym", "--jitter", 17, "--const-h", "--corrected", 1],
 ])
 def test_port_against_live_reference(args, tmp_path):
     i, o = run_ref(str(tmp_path), args)
