@@ -57,6 +57,18 @@ SPH_HD double sqr(double x) {
     return x * x;
 }
 
+/// c ? a : b as a single predicated move. Written in PTX so that the compiler cannot turn the select (and the
+/// arithmetic feeding it) into a divergent branch; keeps the pair body straight-line code.
+SPH_HD double selectD(bool c, double a, double b) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((unsigned)c));
+    return r;
+#else
+    return c ? a : b;
+#endif
+}
+
 /// Reciprocal of a positive normal double: hardware seed (MUFU.RCP64H, >= 20 bits) + two Newton steps. Within 1-2 ulp,
 /// and -- unlike the compiler's IEEE division -- free of the denormal/overflow fix-up branches, which would keep the
 /// scheduler from overlapping two pair bodies. On the host (formula tests) it is a plain division.
@@ -347,7 +359,7 @@ template <bool SOLID, bool CORRECTED, bool FILTER>
 SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict__ lut, const Particle& pi, const Particle& pj,
     double dx, double dy, double dz, double d2, double hbar, bool valid, Accum& acc) {
     acc.cnt += valid ? 1u : 0u;
-    const double mj = valid ? pj.m : 0.;
+    const double mj = selectD(valid, pj.m, 0.);
     // one reciprocal serves 1/hbar (kernel) and 1/(D rhobar) (viscosity): inv = 1 / (hbar * D * rhobar)
     const double rhobar = 0.5 * (pi.rho + pj.rho);
     const double D = fma(1.e-2 * hbar, hbar, d2);
@@ -357,39 +369,42 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
     const double invA = hbar * inv;
     const double hInv2 = hInv * hInv;
     const double qSqr = d2 * hInv2;
-    const double fidx = prm.q_sqr_to_idx * qSqr;
-    uint32_t k = (uint32_t)fidx;
-    k = k < prm.lut_entries ? k : prm.lut_entries - 1;
+    // branch-free table lookup: q^2 is clamped to R^2 (the table has a zero guard entry behind index `entries`),
+    // rejected candidates only ever read the clamped slot and are masked by mj = 0
+    const double fidx = prm.q_sqr_to_idx * fmin(qSqr, prm.radius_sqr);
+    const uint32_t k = (uint32_t)fidx;
     const double ratio = fidx - (double)k;
 #ifdef __CUDA_ARCH__
     const double g0 = __ldg(lut + k), g1 = __ldg(lut + k + 1);
 #else
     const double g0 = lut[k], g1 = lut[k + 1];
 #endif
-    const double G = (qSqr < prm.radius_sqr) ? (g0 * (1. - ratio) + g1 * ratio) : 0.;
+    const double G = selectD(qSqr < prm.radius_sqr, g0 * (1. - ratio) + g1 * ratio, 0.);
     const double s = hInv2 * hInv2 * hInv * G;
     const double gx = dx * s, gy = dy * s, gz = dz * s;
     const double dvx = pj.vx - pi.vx, dvy = pj.vy - pi.vy, dvz = pj.vz - pi.vz;
     const double dvg = dvx * gx + dvy * gy + dvz * gz;
     const double mgx = mj * gx, mgy = mj * gy, mgz = mj * gz;
     acc.divv += mj * dvg;
-    // StandardAV: mu = hbar w / D, Pi = (-alpha csbar mu + beta mu^2) / rhobar, only for approaching pairs (w < 0)
-    const double w = -(dvx * dx + dvy * dy + dvz * dz);
+    // StandardAV: mu = hbar w / D, Pi = (-alpha csbar mu + beta mu^2) / rhobar for approaching pairs (w < 0); with
+    // w clamped to min(w, 0) the receding pairs give mu = 0 and Pi = 0 exactly, without a branch
+    const double w = fmin(-(dvx * dx + dvy * dy + dvz * dz), 0.);
     const double csbar = 0.5 * (pi.cs + pj.cs);
     const double mu = hbar * w * rhobar * invA;
-    const double PiAv = (w < 0.) ? mu * fma(prm.av_beta, mu, -prm.av_alpha * csbar) * (D * invA) : 0.;
+    const double PiAv = mu * fma(prm.av_beta, mu, -prm.av_alpha * csbar) * (D * invA);
     acc.du += 0.5 * PiAv * (-mj * dvg);
     const double c = pi.P + pj.P + PiAv;
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
     if (SOLID) {
-        bool ok = true;
+        bool ok = valid;
         if (FILTER) {
-            ok = (pi.grp == pj.grp) && (pi.grp >= 0);
+            ok = valid && (pi.grp == pj.grp) && (pi.grp >= 0);
         }
-        const double f = ok ? 1. : 0.;
-        const double fx = f * mgx, fy = f * mgy, fz = f * mgz;
+        // masked mass / volume instead of a branch around the tensor sums
+        const double fm = selectD(ok, pj.m, 0.);
+        const double fx = fm * gx, fy = fm * gy, fz = fm * gz;
         const double sxx = pi.Sr[0] + pj.Sr[0], syy = pi.Sr[1] + pj.Sr[1], sxy = pi.Sr[2] + pj.Sr[2],
                      sxz = pi.Sr[3] + pj.Sr[3], syz = pi.Sr[4] + pj.Sr[4];
         const double szz = -sxx - syy;
@@ -406,7 +421,7 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
         acc.T[7] += dvz * fy;
         acc.T[8] += dvz * fz;
         if (CORRECTED) {
-            const double vs = -(valid && ok ? pj.vol : 0.) * s;
+            const double vs = -selectD(ok, pj.vol, 0.) * s;
             const double vdx = vs * dx, vdy = vs * dy, vdz = vs * dz;
             acc.Cm[0] += vdx * dx;
             acc.Cm[1] += vdy * dy;

@@ -113,14 +113,18 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
         hasDamage |= b.fracture != SPHGPU_FRACTURE_NONE;
         for (uint32_t i = a.begin; i < a.end; ++i) matid[i] = m;
     }
+    // same guard entry behind the table as the device copy (api.cu allocates lut_entries + 2 zero-initialised doubles)
+    std::vector<double> lutGuard(cfg->lut_grad, cfg->lut_grad + cfg->lut_entries + 1);
+    lutGuard.push_back(0.);
+    const double* lutPtr = lutGuard.data();
     const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
     const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;
-    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
-    else run<true, false, false, MASKED>(s, prm, md, matid, cfg->lut_grad, off, idx, hasReduce, hasDamage);
+    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
+    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
+    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
+    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
+    else run<true, false, false, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
     return 0;
 }
 
