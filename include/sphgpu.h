@@ -193,6 +193,13 @@ SPHGPU_API int sphgpu_download(sphgpu_ctx* ctx, int q, int order, int layout, vo
 /* Same, PACKED layout only, with a DEVICE pointer on the context's device (used by the multi-GPU halo plumbing). */
 SPHGPU_API int sphgpu_upload_device(sphgpu_ctx* ctx, int q, int order, const void* dev, uint32_t first, uint32_t count);
 SPHGPU_API int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_t first, uint32_t count);
+/* Halo exchange helpers (multi-GPU): pack / unpack the dynamic neighbour inputs {r,h | v,dh/dt | rho | u | S[5] | D}
+ * of `count` particles starting at slot `first` as records of SPHGPU_HALO_DOUBLES doubles into / from a DEVICE buffer
+ * in one kernel each. The reference has no counterpart (single address space); ghosts play the role of
+ * GhostParticles (core/sph/boundary/Boundary.h:73-). */
+#define SPHGPU_HALO_DOUBLES 16
+SPHGPU_API int sphgpu_halo_pack(sphgpu_ctx* ctx, uint32_t first, uint32_t count, void* dev_buffer);
+SPHGPU_API int sphgpu_halo_unpack(sphgpu_ctx* ctx, uint32_t first, uint32_t count, const void* dev_buffer);
 /* Number of particles that take part as neighbours: owned + ghosts (ghosts occupy [n_particles, n_active)). */
 SPHGPU_API int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
 

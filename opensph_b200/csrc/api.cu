@@ -317,6 +317,22 @@ int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_
     return launchPack(ctx, q, order, SPHGPU_LAYOUT_PACKED, dev, first, count);
 }
 
+int sphgpu_halo_pack(sphgpu_ctx* ctx, uint32_t first, uint32_t count, void* dev_buffer) {
+    int rc = checkRange(ctx, first, count, dev_buffer);
+    if (rc != SPHGPU_OK) return rc;
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return launchHalo(ctx, true, first, count, dev_buffer);
+}
+
+int sphgpu_halo_unpack(sphgpu_ctx* ctx, uint32_t first, uint32_t count, const void* dev_buffer) {
+    int rc = checkRange(ctx, first, count, dev_buffer);
+    if (rc != SPHGPU_OK) return rc;
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    rc = launchHalo(ctx, false, first, count, const_cast<void*>(dev_buffer));
+    if (rc == SPHGPU_OK) ctx->stateUploaded = true;
+    return rc;
+}
+
 int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
     if (n_active < ctx->n || n_active > ctx->capacity) {

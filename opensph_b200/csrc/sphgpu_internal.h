@@ -140,5 +140,6 @@ int launchCriteria(sphgpu_ctx* ctx);
 int launchUnpack(sphgpu_ctx* ctx, int q, int order, int layout, const void* stagingDev, uint32_t first, uint32_t count);
 int launchPack(sphgpu_ctx* ctx, int q, int order, int layout, void* stagingDev, uint32_t first, uint32_t count);
 size_t elementBytes(int q, int layout);
+int launchHalo(sphgpu_ctx* ctx, bool pack, uint32_t first, uint32_t count, void* buf);
 
 } // namespace sph

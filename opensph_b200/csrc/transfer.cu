@@ -145,6 +145,49 @@ static int makePlaneSet(sphgpu_ctx* ctx, int q, int order, int layout, PlaneSet&
     return SPHGPU_OK;
 }
 
+// ---- halo records: {x,y,z,h, vx,vy,vz,vh, rho, u, S0..S4, D} ----------------------------------------------------
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_halo(DevicePointers d, uint32_t first, uint32_t count, double* __restrict__ buf, bool solid,
+    bool damage) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) {
+        return;
+    }
+    const uint32_t i = first + k;
+    const int planes[16] = { F_X, F_Y, F_Z, F_H, F_VX, F_VY, F_VZ, F_VH, F_RHO, F_U, F_S0, F_S1, F_S2, F_S3, F_S4, F_D };
+    double2* rec = reinterpret_cast<double2*>(buf + (size_t)k * SPHGPU_HALO_DOUBLES);
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+        const bool use0 = (c < 10) || (c < 15 && solid) || (c == 15 && damage);
+        const bool use1 = (c + 1 < 10) || (c + 1 < 15 && solid) || (c + 1 == 15 && damage);
+        if (PACK) {
+            rec[c / 2] = make_double2(use0 ? d.f[planes[c]][i] : 0., use1 ? d.f[planes[c + 1]][i] : 0.);
+        } else {
+            const double2 v = rec[c / 2];
+            if (use0) {
+                d.f[planes[c]][i] = v.x;
+            }
+            if (use1) {
+                d.f[planes[c + 1]][i] = v.y;
+            }
+        }
+    }
+}
+
+int launchHalo(sphgpu_ctx* ctx, bool pack, uint32_t first, uint32_t count, void* buf) {
+    if (count == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = (count + 255) / 256;
+    if (pack) {
+        k_halo<true><<<blocks, 256, 0, ctx->stream>>>(ctx->d, first, count, (double*)buf, ctx->solid, ctx->hasDamage);
+    } else {
+        k_halo<false><<<blocks, 256, 0, ctx->stream>>>(ctx->d, first, count, (double*)buf, ctx->solid, ctx->hasDamage);
+    }
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
 int launchUnpack(sphgpu_ctx* ctx, int q, int order, int layout, const void* stagingDev, uint32_t first, uint32_t count) {
     PlaneSet ps;
     bool isU32;

@@ -115,6 +115,9 @@ class EngineAdapter:
         return torch.empty(max(doubles, 1), dtype=torch.float64, device="cuda")
 
     def pack(self, fields: Sequence[Tuple[str, int]], first: int, count: int, buf) -> None:
+        if tuple(fields) == DYNAMIC_FIELDS:  # one fused kernel for the per-step exchange
+            self.eng.halo_pack(first, count, buf.data_ptr())
+            return
         off = 0
         for name, ncomp in fields:
             q, order = abi.SNAPSHOT_FIELDS[name]
@@ -122,6 +125,9 @@ class EngineAdapter:
             off += ncomp * count
 
     def unpack(self, fields: Sequence[Tuple[str, int]], first: int, count: int, buf) -> None:
+        if tuple(fields) == DYNAMIC_FIELDS:
+            self.eng.halo_unpack(first, count, buf.data_ptr())
+            return
         off = 0
         for name, ncomp in fields:
             q, order = abi.SNAPSHOT_FIELDS[name]

@@ -109,6 +109,12 @@ class Engine:
         _check(self.lib.sphgpu_download_device(self._ctx, C.c_int(qid), C.c_int(order), C.c_void_p(dev_ptr),
                                                C.c_uint32(first), C.c_uint32(count)))
 
+    def halo_pack(self, first: int, count: int, dev_ptr: int) -> None:
+        _check(self.lib.sphgpu_halo_pack(self._ctx, C.c_uint32(first), C.c_uint32(count), C.c_void_p(dev_ptr)))
+
+    def halo_unpack(self, first: int, count: int, dev_ptr: int) -> None:
+        _check(self.lib.sphgpu_halo_unpack(self._ctx, C.c_uint32(first), C.c_uint32(count), C.c_void_p(dev_ptr)))
+
     def upload_state(self, arrays: Dict[str, np.ndarray], names: Optional[Iterable[str]] = None, first: int = 0) -> int:
         """Uploads every snapshot-named array present (pos, vel, rho, ...). Returns the bytes copied."""
         total = 0
