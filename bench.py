@@ -179,7 +179,10 @@ def main():
     def one_step():
         if halo is None:
             return eng.step_pc(dt, dt)
-        # multi-GPU: ghosts must carry the PREDICTED state, so the step is issued in its parts
+        if halo.native:
+            # predict -> NCCL halo exchange -> integrate -> correct -> criteria -> allreduce(min dt), one host sync
+            return eng.step_pc_mgpu(dt, dt)
+        # multi-GPU without the native path: ghosts must carry the PREDICTED state, so the step is issued in its parts
         eng.predict(dt)
         halo.exchange()
         st = eng.integrate()

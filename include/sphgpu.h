@@ -200,6 +200,20 @@ SPHGPU_API int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* d
 #define SPHGPU_HALO_DOUBLES 16
 SPHGPU_API int sphgpu_halo_pack(sphgpu_ctx* ctx, uint32_t first, uint32_t count, void* dev_buffer);
 SPHGPU_API int sphgpu_halo_unpack(sphgpu_ctx* ctx, uint32_t first, uint32_t count, const void* dev_buffer);
+/* Multi-GPU step inside the library (one process per GPU, slab neighbours left/right; NCCL is resolved at run time).
+ *  - sphgpu_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller distributes it (e.g. torch.distributed);
+ *  - sphgpu_comm_init: every rank joins the communicator (collective);
+ *  - sphgpu_halo_configure: neighbour ranks (-1 = none) and the sizes of the slot bands [0, send_left) and
+ *    [n - send_right, n) that are sent, and of the ghost ranges [n, n + recv_left), [.., + recv_right) that are filled;
+ *  - sphgpu_halo_exchange: pack -> grouped ncclSend/ncclRecv -> unpack, queued on the context's stream;
+ *  - sphgpu_step_pc_mgpu: predict -> halo exchange -> integrate -> correct -> criteria -> ncclAllReduce(min) of the time
+ *    step, one host synchronisation per step. */
+SPHGPU_API int sphgpu_comm_unique_id(void* out128);
+SPHGPU_API int sphgpu_comm_init(sphgpu_ctx* ctx, const void* id128, int rank, int world);
+SPHGPU_API int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32_t send_left, uint32_t send_right,
+    uint32_t recv_left, uint32_t recv_right);
+SPHGPU_API int sphgpu_halo_exchange(sphgpu_ctx* ctx);
+SPHGPU_API int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
 /* Number of particles that take part as neighbours: owned + ghosts (ghosts occupy [n_particles, n_active)). */
 SPHGPU_API int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
 

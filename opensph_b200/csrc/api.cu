@@ -245,6 +245,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    destroyHalo(ctx);
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc);
@@ -371,8 +372,12 @@ int sphgpu_synchronize(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
+} // extern "C"
+
+namespace sph {
+
 // Queues one integrate() on the stream; events 0..3 bracket grid build / prologue / pair kernel.
-static int enqueueIntegrate(sphgpu_ctx* ctx) {
+int enqueueIntegrate(sphgpu_ctx* ctx) {
     int rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((rc = launchGridBuild(ctx)) != SPHGPU_OK) return rc;
@@ -384,7 +389,7 @@ static int enqueueIntegrate(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
-static int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEvent_t end) {
+int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEvent_t end) {
     StatsDev sd;
     SPH_CUDA_CHECK(cudaMemcpyAsync(&sd, ctx->d.stats, sizeof(sd), cudaMemcpyDeviceToHost, ctx->stream));
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -406,6 +411,10 @@ static int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin,
     }
     return SPHGPU_OK;
 }
+
+} // namespace sph
+
+extern "C" {
 
 int sphgpu_integrate(sphgpu_ctx* ctx, double t, sphgpu_stats* stats) {
     (void)t;
@@ -436,8 +445,12 @@ int sphgpu_step_euler(sphgpu_ctx* ctx, double dt) {
     return launchEuler(ctx, dt);
 }
 
+} // extern "C"
+
+namespace sph {
+
 // MultiCriterion::compute (TimeStepCriterion.cpp:389-419) from the four per-criterion minima.
-static int finishTimestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out) {
+int finishTimestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out) {
     TimestepDev td;
     SPH_CUDA_CHECK(cudaMemcpyAsync(&td, ctx->d.tsd, sizeof(td), cudaMemcpyDeviceToHost, ctx->stream));
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -479,6 +492,10 @@ static int finishTimestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out) 
     }
     return SPHGPU_OK;
 }
+
+} // namespace sph
+
+extern "C" {
 
 int sphgpu_compute_timestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");

@@ -1,0 +1,207 @@
+// Multi-GPU step inside the library: ghost (halo) exchange and the global time-step reduction with NCCL, queued on the
+// context's stream between the kernels of one PredictorCorrector step, so a step costs ONE host synchronisation.
+//
+// The reference has no distributed path (core/thread/Scheduler.h:27 rules out MPI); this is the B200-native plumbing
+// of SURVEY 8(e): slab neighbours exchange the dynamic neighbour inputs of their boundary bands with grouped
+// ncclSend/ncclRecv over NVLink after the prediction and before the derivative evaluation; ncclAllReduce(min) combines
+// the per-criterion time-step minima. NCCL is resolved at run time (dlopen of libnccl.so.2 -- inside a PyTorch process
+// that is PyTorch's own copy), so libsphgpu has no link-time dependency on it.
+#include "sphgpu_internal.h"
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace sph {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* ncclApi() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) {
+#define SPH_NCCL_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name))
+            SPH_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+            SPH_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+            SPH_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+            SPH_NCCL_SYM(Send, "ncclSend");
+            SPH_NCCL_SYM(Recv, "ncclRecv");
+            SPH_NCCL_SYM(AllReduce, "ncclAllReduce");
+            SPH_NCCL_SYM(GroupStart, "ncclGroupStart");
+            SPH_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+            SPH_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef SPH_NCCL_SYM
+        }
+    }
+    const bool ok = api.handle && api.GetUniqueId && api.CommInitRank && api.Send && api.Recv && api.AllReduce && api.GroupStart &&
+                    api.GroupEnd;
+    return ok ? &api : nullptr;
+}
+
+#define SPH_NCCL_CHECK(expr)                                                                                          \
+    do {                                                                                                              \
+        ncclResult_t _r = (expr);                                                                                     \
+        if (_r != ncclSuccess) {                                                                                      \
+            sph::setError(std::string(#expr) + ": " + (api->GetErrorString ? api->GetErrorString(_r) : "NCCL error")); \
+            return SPHGPU_E_CUDA;                                                                                     \
+        }                                                                                                             \
+    } while (0)
+
+struct HaloState {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    int left = -1, right = -1;
+    uint32_t sendLeft = 0, sendRight = 0, recvLeft = 0, recvRight = 0;
+    double *bufSendL = nullptr, *bufSendR = nullptr, *bufRecvL = nullptr, *bufRecvR = nullptr;
+};
+
+static int exchange(sphgpu_ctx* ctx) {
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    NcclApi* api = ncclApi();
+    const uint32_t n = ctx->n;
+    int rc;
+    if ((rc = launchHalo(ctx, true, 0, h->sendLeft, h->bufSendL)) != SPHGPU_OK) return rc;
+    if ((rc = launchHalo(ctx, true, n - h->sendRight, h->sendRight, h->bufSendR)) != SPHGPU_OK) return rc;
+    const size_t w = SPHGPU_HALO_DOUBLES;
+    SPH_NCCL_CHECK(api->GroupStart());
+    if (h->left >= 0) {
+        if (h->sendLeft) SPH_NCCL_CHECK(api->Send(h->bufSendL, w * h->sendLeft, ncclFloat64, h->left, h->comm, ctx->stream));
+        if (h->recvLeft) SPH_NCCL_CHECK(api->Recv(h->bufRecvL, w * h->recvLeft, ncclFloat64, h->left, h->comm, ctx->stream));
+    }
+    if (h->right >= 0) {
+        if (h->sendRight) SPH_NCCL_CHECK(api->Send(h->bufSendR, w * h->sendRight, ncclFloat64, h->right, h->comm, ctx->stream));
+        if (h->recvRight) SPH_NCCL_CHECK(api->Recv(h->bufRecvR, w * h->recvRight, ncclFloat64, h->right, h->comm, ctx->stream));
+    }
+    SPH_NCCL_CHECK(api->GroupEnd());
+    if ((rc = launchHalo(ctx, false, n, h->recvLeft, h->bufRecvL)) != SPHGPU_OK) return rc;
+    if ((rc = launchHalo(ctx, false, n + h->recvLeft, h->recvRight, h->bufRecvR)) != SPHGPU_OK) return rc;
+    ctx->launches += 4;
+    return SPHGPU_OK;
+}
+
+void destroyHalo(sphgpu_ctx* ctx) {
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    if (!h) {
+        return;
+    }
+    cudaFree(h->bufSendL);
+    cudaFree(h->bufSendR);
+    cudaFree(h->bufRecvL);
+    cudaFree(h->bufRecvR);
+    NcclApi* api = ncclApi();
+    if (api && h->comm && api->CommDestroy) {
+        api->CommDestroy(h->comm);
+    }
+    delete h;
+    ctx->halo = nullptr;
+}
+
+} // namespace sph
+
+using namespace sph;
+
+extern "C" {
+
+int sphgpu_comm_unique_id(void* out128) {
+    NcclApi* api = ncclApi();
+    if (!api || !out128) {
+        setError("NCCL (libnccl.so.2) is not available");
+        return SPHGPU_E_INVALID;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    SPH_NCCL_CHECK(api->GetUniqueId(static_cast<ncclUniqueId*>(out128)));
+    return SPHGPU_OK;
+}
+
+int sphgpu_comm_init(sphgpu_ctx* ctx, const void* id128, int rank, int world) {
+    NcclApi* api = ncclApi();
+    if (!ctx || !id128 || !api) {
+        setError("NCCL (libnccl.so.2) is not available or null argument");
+        return SPHGPU_E_INVALID;
+    }
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    destroyHalo(ctx);
+    HaloState* h = new HaloState();
+    h->rank = rank;
+    h->world = world;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    SPH_NCCL_CHECK(api->CommInitRank(&h->comm, world, id, rank));
+    ctx->halo = h;
+    return SPHGPU_OK;
+}
+
+int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32_t send_left, uint32_t send_right, uint32_t recv_left,
+    uint32_t recv_right) {
+    if (!ctx || !ctx->halo) {
+        setError("sphgpu_comm_init must be called first");
+        return SPHGPU_E_STATE;
+    }
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    if ((uint64_t)ctx->n + recv_left + recv_right > ctx->capacity || send_left + send_right > ctx->n) {
+        setError("halo sizes exceed the context capacity");
+        return SPHGPU_E_INVALID;
+    }
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    h->left = left_rank;
+    h->right = right_rank;
+    h->sendLeft = left_rank >= 0 ? send_left : 0;
+    h->sendRight = right_rank >= 0 ? send_right : 0;
+    h->recvLeft = left_rank >= 0 ? recv_left : 0;
+    h->recvRight = right_rank >= 0 ? recv_right : 0;
+    const size_t w = SPHGPU_HALO_DOUBLES * sizeof(double);
+    cudaFree(h->bufSendL); cudaFree(h->bufSendR); cudaFree(h->bufRecvL); cudaFree(h->bufRecvR);
+    SPH_CUDA_CHECK(cudaMalloc(&h->bufSendL, std::max<size_t>(w * h->sendLeft, 16)));
+    SPH_CUDA_CHECK(cudaMalloc(&h->bufSendR, std::max<size_t>(w * h->sendRight, 16)));
+    SPH_CUDA_CHECK(cudaMalloc(&h->bufRecvL, std::max<size_t>(w * h->recvLeft, 16)));
+    SPH_CUDA_CHECK(cudaMalloc(&h->bufRecvR, std::max<size_t>(w * h->recvRight, 16)));
+    ctx->nActive = ctx->n + h->recvLeft + h->recvRight;
+    return SPHGPU_OK;
+}
+
+int sphgpu_halo_exchange(sphgpu_ctx* ctx) {
+    if (!ctx || !ctx->halo) {
+        setError("halo exchange is not configured");
+        return SPHGPU_E_STATE;
+    }
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return exchange(ctx);
+}
+
+int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out) {
+    (void)t;
+    if (!ctx || !ctx->halo) {
+        setError("sphgpu_comm_init / sphgpu_halo_configure must be called first");
+        return SPHGPU_E_STATE;
+    }
+    NcclApi* api = ncclApi();
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    int rc;
+    if ((rc = launchPredict(ctx, dt)) != SPHGPU_OK) return rc;
+    if ((rc = exchange(ctx)) != SPHGPU_OK) return rc; // ghosts carry the PREDICTED state
+    if ((rc = enqueueIntegrate(ctx)) != SPHGPU_OK) return rc;
+    if ((rc = launchCorrect(ctx, dt)) != SPHGPU_OK) return rc;
+    if ((rc = launchCriteria(ctx)) != SPHGPU_OK) return rc;
+    // global time step: the bit patterns of positive doubles order like the values, so min over ranks is a u64 min
+    SPH_NCCL_CHECK(api->AllReduce(ctx->d.tsd, ctx->d.tsd, 4, ncclUint64, ncclMin, h->comm, ctx->stream));
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    if ((rc = collectStats(ctx, stats, ctx->ev[4], ctx->ev[5])) != SPHGPU_OK) return rc;
+    return finishTimestep(ctx, max_dt, out);
+}
+
+} // extern "C"

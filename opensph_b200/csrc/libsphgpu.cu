@@ -6,3 +6,4 @@
 #include "pair_tiled.cu"
 #include "stepping.cu"
 #include "transfer.cu"
+#include "halo.cu"

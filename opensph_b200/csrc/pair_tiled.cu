@@ -277,6 +277,9 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
         const bool upper = live && jOwn >= lCnt;
         const uint32_t slot = live ? d.order[t] : 0xffffffffu;
         const bool target = live && slot < nOwned; // ghosts are neighbours only
+        if (!__syncthreads_or(target ? 1 : 0)) {
+            continue; // a unit made of ghost particles only (halo band of a decomposed run)
+        }
 
         Particle pi;
         int cx = 0;

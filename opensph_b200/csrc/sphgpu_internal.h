@@ -107,6 +107,7 @@ struct sphgpu_ctx {
     int variant = 0;
     uint32_t launches = 0;
     bool stateUploaded = false;
+    void* halo = nullptr;      // sph::HaloState (halo.cu): NCCL communicator + exchange buffers
 };
 
 namespace sph {
@@ -141,5 +142,10 @@ int launchUnpack(sphgpu_ctx* ctx, int q, int order, int layout, const void* stag
 int launchPack(sphgpu_ctx* ctx, int q, int order, int layout, void* stagingDev, uint32_t first, uint32_t count);
 size_t elementBytes(int q, int layout);
 int launchHalo(sphgpu_ctx* ctx, bool pack, uint32_t first, uint32_t count, void* buf);
+// api.cu / halo.cu
+int enqueueIntegrate(sphgpu_ctx* ctx);
+int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEvent_t end);
+int finishTimestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out);
+void destroyHalo(sphgpu_ctx* ctx);
 
 } // namespace sph

@@ -163,6 +163,12 @@ class HaloExchange:
         self.bytes_per_exchange = 8 * self.width * (dom.n_left + dom.n_right)
         self._static(state)
         eng.set_active(self.n_active)
+        # the per-step exchange runs inside the library (NCCL on the engine's stream) when the engine supports it
+        self.native = hasattr(eng, "comm_init") and dist.get_backend() == "nccl" and self.fields == DYNAMIC_FIELDS
+        if self.native:
+            eng.comm_init(dom.rank, dom.world)
+            eng.halo_configure(-1 if self.left is None else self.left, -1 if self.right is None else self.right,
+                               dom.n_left, dom.n_right, self.g_left, self.g_right)
 
     def _exchange_counts(self, n_left: int, n_right: int) -> Tuple[int, int]:
         torch, dist = self.torch, self.dist
@@ -218,4 +224,7 @@ class HaloExchange:
 
     def exchange(self) -> None:
         """Refreshes the dynamic neighbour inputs of all ghosts; call after predict and before integrate."""
-        self._run(self.fields)
+        if self.native:
+            self.eng.halo_exchange()
+        else:
+            self._run(self.fields)

@@ -115,6 +115,32 @@ class Engine:
     def halo_unpack(self, first: int, count: int, dev_ptr: int) -> None:
         _check(self.lib.sphgpu_halo_unpack(self._ctx, C.c_uint32(first), C.c_uint32(count), C.c_void_p(dev_ptr)))
 
+    # -- multi-GPU step inside the library (NCCL) ------------------------------------------------------------------
+    def comm_init(self, rank: int, world: int) -> None:
+        """Joins the library's own NCCL communicator; the 128-byte id is distributed with torch.distributed."""
+        import torch
+        import torch.distributed as dist
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            _check(self.lib.sphgpu_comm_unique_id(ident))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        _check(self.lib.sphgpu_comm_init(self._ctx, ident, C.c_int(rank), C.c_int(world)))
+
+    def halo_configure(self, left: int, right: int, send_left: int, send_right: int, recv_left: int, recv_right: int) -> None:
+        _check(self.lib.sphgpu_halo_configure(self._ctx, C.c_int(left), C.c_int(right), C.c_uint32(send_left),
+                                              C.c_uint32(send_right), C.c_uint32(recv_left), C.c_uint32(recv_right)))
+
+    def halo_exchange(self) -> None:
+        _check(self.lib.sphgpu_halo_exchange(self._ctx))
+
+    def step_pc_mgpu(self, dt: float, max_dt: float, t: float = 0.0) -> Tuple[float, int, abi.Stats]:
+        st, ts = abi.Stats(), abi.TimeStep()
+        _check(self.lib.sphgpu_step_pc_mgpu(self._ctx, C.c_double(t), C.c_double(dt), C.c_double(max_dt), C.byref(st), C.byref(ts)))
+        return float(ts.dt), int(ts.criterion), st
+
     def upload_state(self, arrays: Dict[str, np.ndarray], names: Optional[Iterable[str]] = None, first: int = 0) -> int:
         """Uploads every snapshot-named array present (pos, vel, rho, ...). Returns the bytes copied."""
         total = 0
