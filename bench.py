@@ -267,7 +267,7 @@ def main():
         "config": {"workload": ("fluid_" if args.fluid else "collision_preset_") + str(args.n), "particles": int(n_total),
                    "particles_per_gpu": int(n_owned), "mean_neighbours": round(float(neigh_mean), 2), "integrator": "predictor_corrector",
                    "dt": dt, "l2": "inputs larger than L2 (state %.1f GB per GPU)" % (n_owned * 464 / 1e9),
-                   "decomposition": "x-slabs of equal particle count + NCCL halo exchange" if world > 1 else "single domain",
+                   "decomposition": "z-slabs of equal particle count + NCCL halo exchange inside the step" if world > 1 else "single domain",
                    "pair_variant": args.variant},
         "clocks": clocks,
         "gpu_launches": int(launches),

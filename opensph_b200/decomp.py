@@ -6,7 +6,8 @@ only to particle i and reads neighbour inputs, so one exchange of the neighbour 
 (SURVEY 8e); ghosts are appended after the owned particles -- the analogue of GhostParticles on the CPU
 (core/sph/boundary/Boundary.h:73-) -- and are never targets.
 
-Round-1 decomposition: slabs along x with equal particle counts (a 1-D space-filling curve). Each rank keeps its
+Round-1 decomposition: slabs of equal particle counts along z (a 1-D space-filling curve; z because the cell rows of
+the pair kernel run along x and must stay long). Each rank keeps its
 slots ordered [left band | interior | right band], so the particles a neighbour needs are two contiguous slot ranges
 and packing is a plain range copy (sphgpu_download_device). The dynamic neighbour inputs (r,h | v | rho | u | S | D) are
 exchanged with NCCL point-to-point every step; static ones (m, flag, material) once.
@@ -61,8 +62,9 @@ def band_partition(x: np.ndarray, lo_plane: Optional[float], hi_plane: Optional[
 class SlabDomain:
     """Geometry of the basalt-sphere workload cut into x-slabs; every rank generates only its own lattice points."""
 
-    def __init__(self, n_target: int, world: int, rank: int, radius: float = 5.0e4, solid: bool = True):
+    def __init__(self, n_target: int, world: int, rank: int, radius: float = 5.0e4, solid: bool = True, axis: int = 2):
         self.n_target, self.world, self.rank, self.radius, self.solid = n_target, world, rank, radius, solid
+        self.axis = axis  # slabs are cut perpendicular to this axis
         self.cuts = sphere_cut_planes(radius, world)
         volume = 4.0 / 3.0 * math.pi * radius ** 3
         self.h = (volume / n_target) ** (1.0 / 3.0) * workloads.BASALT["eta"]
@@ -76,11 +78,13 @@ class SlabDomain:
         lo = self.lo_plane if self.lo_plane is not None else -2.0 * self.radius
         hi = self.hi_plane if self.hi_plane is not None else 2.0 * self.radius
         x_range = None if self.world == 1 else (lo, hi)
-        pos, _ = workloads.hexagonal_sphere(self.n_target, self.radius, x_range=x_range)
+        pos, _ = workloads.hexagonal_sphere(self.n_target, self.radius, x_range=x_range, axis=self.axis)
         n_total = self.total_particles(len(pos))
-        state = workloads.basalt_sphere_state(self.n_target, self.radius, self.solid, x_range=x_range, total_hint=n_total)
+        state = workloads.basalt_sphere_state(self.n_target, self.radius, self.solid, x_range=x_range, total_hint=n_total,
+                                              axis=self.axis)
         if self.world > 1:
-            perm, self.n_left, self.n_right = band_partition(state["pos"][:, 0], self.lo_plane, self.hi_plane, self.halo_width)
+            perm, self.n_left, self.n_right = band_partition(state["pos"][:, self.axis], self.lo_plane, self.hi_plane,
+                                                             self.halo_width)
             state = {k: (v[perm] if isinstance(v, np.ndarray) and v.shape[:1] == (len(perm),) else v) for k, v in state.items()}
         return state
 

@@ -42,10 +42,10 @@ def cubic_spline_lut(entries: int = 40000, radius: float = 2.0) -> Tuple[np.ndar
     return grad, val
 
 
-def hexagonal_sphere(n_target: int, radius: float, centre=(0.0, 0.0, 0.0), x_range=None) -> Tuple[np.ndarray, float]:
+def hexagonal_sphere(n_target: int, radius: float, centre=(0.0, 0.0, 0.0), x_range=None, axis: int = 0) -> Tuple[np.ndarray, float]:
     """Positions of the hexagonal lattice filling a sphere (about 1.06 n_target particles) and the lattice h.
 
-    `x_range` = (lo, hi) keeps only lattice points with lo <= x < hi (used by ranks to generate just their slab)."""
+    `x_range` = (lo, hi) keeps only lattice points with lo <= r[axis] < hi (used by ranks to generate just their slab)."""
     volume = 4.0 / 3.0 * math.pi * radius ** 3
     h = 1.0 / (n_target / volume) ** (1.0 / 3.0)
     dx = 1.1 * h
@@ -67,7 +67,12 @@ def hexagonal_sphere(n_target: int, radius: float, centre=(0.0, 0.0, 0.0), x_ran
         Y = np.broadcast_to(y[:, None], X.shape)
         mask = X * X + Y * Y + z * z <= r2
         if x_range is not None:
-            mask &= (X >= x_range[0]) & (X < x_range[1])
+            if axis == 2:
+                if not (x_range[0] <= z < x_range[1]):
+                    continue
+            else:
+                coord = X if axis == 0 else Y
+                mask &= (coord >= x_range[0]) & (coord < x_range[1])
         if mask.any():
             out.append(np.stack([X[mask], Y[mask], np.full(int(mask.sum()), z)], axis=1))
     pos = np.concatenate(out, axis=0) if out else np.zeros((0, 3))
@@ -131,13 +136,13 @@ def make_setup(n_particles: int, solid: bool = True, adaptive_h: bool = True, co
 
 
 def basalt_sphere_state(n_target: int, radius: float = 5.0e4, solid: bool = True, seed: int = 1234, x_range=None,
-                        total_hint: int = None) -> Dict[str, np.ndarray]:
+                        total_hint: int = None, axis: int = 0) -> Dict[str, np.ndarray]:
     """Particle state of one basalt sphere on the hexagonal lattice (BASELINE configs[2..4]).
 
     Fields are seeded with smooth analytic functions of position (velocity ~ 50 m/s with compression and shear, 1 %
     density contrast, u ~ 1e4 J/kg, S ~ 1e7 Pa, damage 0) so AV, stress, EoS and damage terms all do real work.
     """
-    pos3, h_lat = hexagonal_sphere(n_target, radius, x_range=x_range)
+    pos3, h_lat = hexagonal_sphere(n_target, radius, x_range=x_range, axis=axis)
     n = len(pos3)
     b = BASALT
     x, y, z = (pos3[:, k] / radius for k in range(3))
