@@ -31,6 +31,15 @@ BYTES_INTEGRATE = 628.0       # find + derivatives (integrate() only)
 BYTES_PAIR_KERNEL = 408.0     # dominant kernel, itemised in DESIGN.md section 3 (sorted record + epilogue inputs in, derivatives out)
 
 
+def read_traffic():
+    """DRAM bytes per particle of the pair kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -257,6 +266,7 @@ def main():
         return
 
     peak, peak_kind = read_peaks()
+    prof = read_traffic() if solid else None
     pair_s = pair_ms * 1e-3 / args.steps
     bytes_pair = (BYTES_PAIR_KERNEL if solid else 230.0) * n_owned
     achieved = bytes_pair / pair_s / 1e9 if pair_s > 0 else 0.0
@@ -274,7 +284,10 @@ def main():
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": "k_pair (fused neighbour search + pair sums + finalizers)",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " HBM copy GB/s", "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak,
+                     "traffic": (prof["bytes_per_particle"] * n_owned if prof else None),
+                     "traffic_source": (prof["source"] if prof else None),
+                     "fp64_pipe_active_pct_ncu": (prof["fp64_pipe_active_pct"] if prof else None),
                      "kernel_ms": pair_s * 1e3, "kernel_share_of_step": pair_s / step_s,
                      "step_hbm_frac": BYTES_FULL_STEP * (n_owned / step_s) / 1e9 / peak,
                      "note": "pair kernel is FP64-pipe bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},

@@ -1,9 +1,9 @@
 #!/bin/sh
 # Run under gpurun (one GPU). Produces the launch list and one full capture of the pair kernel for bench.py's workload.
-#   sh profiles/run_ncu.sh <tag> [extra bench args]
-TAG=${1:-r01}; shift
+#   sh profiles/run_ncu.sh <tag> [particles] [extra bench args]
+TAG=${1:-r01}; N=${2:-1000000}; shift; shift
 mkdir -p gpurun_out
-BENCH="python bench.py --particles 1000000 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline $*"
+BENCH="python bench.py --particles $N --steps 2 --warmup 3 --no-e2e --no-cpu-baseline $*"
 # every launch of two timed steps with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches.log 2>&1
 # the dominant kernel, full set, source-level
