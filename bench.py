@@ -208,7 +208,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    pair_ms, launches, timings = 0.0, 0, np.zeros(4)
+    pair_ms, launches, timings, halo_ms = 0.0, 0, np.zeros(4), 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
@@ -219,6 +219,8 @@ def main():
         timings += tm
         pair_ms += tm[2]
         launches += st.kernel_launches
+        if halo is not None and halo.native:
+            halo_ms += eng.last_halo_ms()
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -260,6 +262,12 @@ def main():
         e2e = {"value": n_total / (float(te.item()) / k_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": k_e2e}
 
+    per_rank = None
+    if world > 1:  # per-rank device-time breakdown (ms per step): grid, prologue, pair kernel, rest, of which halo exchange
+        mine = torch.tensor(list(timings / args.steps) + [halo_ms / args.steps, float(n_owned)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x), 4) for x in r.tolist()] for r in allr]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -294,6 +302,9 @@ def main():
         "phase_ms": {"grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
                      "pair_kernel": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps},
     }
+    if per_rank is not None:
+        out["per_rank_ms"] = {"columns": ["grid_build", "prologue_pack", "pair_kernel", "rest", "halo_exchange_in_rest", "owned_particles"],
+                              "rows": per_rank}
     if world == 1 and not args.no_cpu_baseline:
         try:
             r = run_reference(argparse.Namespace(steps=2, warmup=1, n=args.n), min(args.n, 1_000_000))

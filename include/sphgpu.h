@@ -247,6 +247,9 @@ SPHGPU_API int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_
 /* Device-time breakdown of the last integrate call in milliseconds: [0] grid build + sort, [1] prologue + pack,
  * [2] pair kernel, [3] rest. */
 SPHGPU_API int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4);
+/* Device time of the halo exchange of the last sphgpu_step_pc_mgpu call (pack + NCCL send/recv + unpack, including the
+ * time spent waiting for the neighbour ranks), milliseconds. */
+SPHGPU_API int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms);
 /* Selects the pair-kernel variant (0 = default tiled kernel, 1 = direct per-thread kernel). For A/B checks only. */
 SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the

@@ -190,7 +190,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     };
     SPH_TRY(wrap(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
     ctx->privateStream = ctx->stream;
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 8; ++k) {
         SPH_TRY(wrap(cudaEventCreate(&ctx->ev[k]), "cudaEventCreate"));
     }
     for (int f = 0; f < F_COUNT; ++f) {
@@ -252,7 +252,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree(ctx->staging);
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 8; ++k) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     }
     if (ctx->privateStream) cudaStreamDestroy(ctx->privateStream);
@@ -532,6 +532,12 @@ int sphgpu_set_last_timestep(sphgpu_ctx* ctx, double dt) {
 int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4) {
     if (!ctx || !ms4) return fail(SPHGPU_E_INVALID, "null argument");
     for (int k = 0; k < 4; ++k) ms4[k] = ctx->lastMs[k];
+    return SPHGPU_OK;
+}
+
+int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return fail(SPHGPU_E_INVALID, "null argument");
+    *ms = ctx->lastHaloMs;
     return SPHGPU_OK;
 }
 

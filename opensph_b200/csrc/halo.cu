@@ -193,7 +193,9 @@ int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sph
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[4], ctx->stream));
     int rc;
     if ((rc = launchPredict(ctx, dt)) != SPHGPU_OK) return rc;
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[6], ctx->stream));
     if ((rc = exchange(ctx)) != SPHGPU_OK) return rc; // ghosts carry the PREDICTED state
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[7], ctx->stream));
     if ((rc = enqueueIntegrate(ctx)) != SPHGPU_OK) return rc;
     if ((rc = launchCorrect(ctx, dt)) != SPHGPU_OK) return rc;
     if ((rc = launchCriteria(ctx)) != SPHGPU_OK) return rc;
@@ -201,6 +203,9 @@ int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sph
     SPH_NCCL_CHECK(api->AllReduce(ctx->d.tsd, ctx->d.tsd, 4, ncclUint64, ncclMin, h->comm, ctx->stream));
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
     if ((rc = collectStats(ctx, stats, ctx->ev[4], ctx->ev[5])) != SPHGPU_OK) return rc;
+    float ms = 0.f;
+    SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+    ctx->lastHaloMs = ms;
     return finishTimestep(ctx, max_dt, out);
 }
 

@@ -100,8 +100,9 @@ struct sphgpu_ctx {
     cudaStream_t stream = nullptr;        // stream all work is queued on (private or caller-provided)
     cudaStream_t privateStream = nullptr;
     double maxChange = 1.e308;            // TIMESTEPPING_MAX_INCREASE
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[8] = {};
     double lastMs[4] = { 0, 0, 0, 0 };
+    double lastHaloMs = 0.;    // device time of the last halo exchange (pack + NCCL + unpack, includes waiting for peers)
     double lastDt = 0.;        // MultiCriterion::lastStep
     bool lastDtInit = false;
     int variant = 0;

@@ -203,6 +203,11 @@ class Engine:
         _check(self.lib.sphgpu_last_timings(self._ctx, ms.ctypes.data_as(C.POINTER(C.c_double))))
         return ms
 
+    def last_halo_ms(self) -> float:
+        ms = C.c_double(0.0)
+        _check(self.lib.sphgpu_last_halo_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
+
     def set_variant(self, variant: int) -> None:
         _check(self.lib.sphgpu_set_variant(self._ctx, C.c_int(variant)))
 
