@@ -68,7 +68,7 @@ __device__ __forceinline__ void fenceProxyAsync() {
 
 // ---- work list: units of <= 128 targets per double row (next-fit packing of cell columns) ----------------------
 // One thread per double row walks its cells in x; FILL = false counts the units, FILL = true writes the descriptors
-// {double row, cA | cB << 16, skip, total}: the unit takes targets [skip, skip + 128) of the concatenation
+// {double row, cA, skip, cB}: the unit takes targets [skip, skip + 128) of the concatenation
 // (lower row cells cA..cB) ++ (upper row cells cA..cB).
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCells) {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCel
         const uint32_t parts = (total + TILE_T - 1) / TILE_T;
         if (FILL) {
             for (uint32_t p = 0; p < parts; ++p) {
-                d.unitDesc[out + units + p] = make_uint4(dr, (uint32_t)a | ((uint32_t)b << 16), p * TILE_T, total);
+                d.unitDesc[out + units + p] = make_uint4(dr, (uint32_t)a, p * TILE_T, (uint32_t)b);
             }
         }
         units += parts;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
         const uint4 desc = d.unitDesc[unit];
         const uint32_t dr = desc.x;
-        const int cA = (int)(desc.y & 0xffffu), cB = (int)(desc.y >> 16);
+        const int cA = (int)desc.y, cB = (int)desc.w;
         const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
         const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
         const bool hasU = 2 * k + 1 < dimz;

@@ -73,13 +73,12 @@ struct DevicePointers {
     uint32_t* cellCount; // [maxCells + 1]
     uint32_t* scanBlock; // block sums of the scan
     uint32_t* segStart;  // [maxCells + 1] exclusive prefix of the number of work units per double row
-    uint4* unitDesc;     // [maxSegs] work units of the tiled pair kernel: {double row, cA | cB << 16, skip, total}
+    uint4* unitDesc;     // [maxSegs] work units of the tiled pair kernel: {double row, cA, skip, cB}
     double* boundsPartial; // [BOUNDS_BLOCKS * 8]
     const double* lut;
     GridDev* grid;
     StatsDev* stats;
     TimestepDev* tsd;
-    const MaterialDev* mats;
 };
 
 constexpr int BOUNDS_BLOCKS = 592;   // 148 SMs x 4

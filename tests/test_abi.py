@@ -67,3 +67,21 @@ def test_invalid_setups_are_rejected(lut):
     with pytest.raises(engine.SphGpuError) as e:
         engine.Engine(setup, n)
     assert e.value.code == abi.E_INVALID
+
+
+def test_quantity_ids_match_header():
+    text = open(HEADER).read()
+    ids = {m.group(1): int(m.group(2)) for m in re.finditer(r"SPHGPU_Q_(\w+)\s*=\s*(\d+)", text)}
+    for name, (qid, _, _) in abi.QUANTITIES.items():
+        assert ids[name] == qid, name
+    assert ids["COUNT"] == len(abi.QUANTITIES)
+
+
+def test_workload_constants_are_decomposition_independent():
+    """Per-particle flaw constants are keyed by position, so a rank generating only its slab draws the same values."""
+    from opensph_b200 import workloads
+    a = workloads.basalt_sphere_state(4000)
+    b = workloads.basalt_sphere_state(4000, x_range=(-1e9, 0.0), total_hint=len(a["mass"]), axis=2)
+    m = a["pos"][:, 2] < 0
+    assert m.sum() == len(b["mass"])
+    assert np.array_equal(a["eps_min"][m], b["eps_min"]) and np.array_equal(a["n_flaws"][m], b["n_flaws"])
