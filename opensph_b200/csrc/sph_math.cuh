@@ -360,19 +360,21 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
     double dx, double dy, double dz, double d2, double hbar, bool valid, Accum& acc) {
     acc.cnt += valid ? 1u : 0u;
     const double mj = selectD(valid, pj.m, 0.);
-    // one reciprocal serves 1/hbar (kernel) and 1/(D rhobar) (viscosity): inv = 1 / (hbar * D * rhobar)
-    const double rhobar = 0.5 * (pi.rho + pj.rho);
+    // one reciprocal serves 1/hbar (kernel) and 1/(D rhobar) (viscosity); the factors 1/2 of rhobar and csbar are folded:
+    // rs = 2 rhobar, inv = 1 / (hbar D rs)  =>  1/hbar = D rs inv,  1/(D rhobar) = 2 hbar inv
+    const double rs = pi.rho + pj.rho;
     const double D = fma(1.e-2 * hbar, hbar, d2);
-    const double A = D * rhobar;
+    const double A = D * rs;
     const double inv = fastRcp(hbar * A);
     const double hInv = A * inv;
-    const double invA = hbar * inv;
+    const double invA = hbar * inv; // = 1 / (2 D rhobar)
     const double hInv2 = hInv * hInv;
     const double qSqr = d2 * hInv2;
-    // branch-free table lookup: q^2 is clamped to R^2 (the table has a zero guard entry behind index `entries`),
-    // rejected candidates only ever read the clamped slot and are masked by mj = 0
-    const double fidx = prm.q_sqr_to_idx * fmin(qSqr, prm.radius_sqr);
-    const uint32_t k = (uint32_t)fidx;
+    // branch-free table lookup: the index is clamped to the zero guard entry behind the table; rejected candidates only
+    // ever read the clamped slot and are masked by mj = 0
+    const double fidx = prm.q_sqr_to_idx * qSqr;
+    uint32_t k = (uint32_t)fidx;
+    k = k < prm.lut_entries ? k : prm.lut_entries;
     const double ratio = fidx - (double)k;
 #ifdef __CUDA_ARCH__
     const double g0 = __ldg(lut + k), g1 = __ldg(lut + k + 1);
@@ -380,20 +382,20 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
     const double g0 = lut[k], g1 = lut[k + 1];
 #endif
     const double G = selectD(qSqr < prm.radius_sqr, g0 * (1. - ratio) + g1 * ratio, 0.);
-    const double s = hInv2 * hInv2 * hInv * G;
-    const double gx = dx * s, gy = dy * s, gz = dz * s;
+    const double s = hInv2 * hInv2 * hInv * G; // gradW = s d
     const double dvx = pj.vx - pi.vx, dvy = pj.vy - pi.vy, dvz = pj.vz - pi.vz;
-    const double dvg = dvx * gx + dvy * gy + dvz * gz;
-    const double mgx = mj * gx, mgy = mj * gy, mgz = mj * gz;
+    const double t = dvx * dx + dvy * dy + dvz * dz; // (v_j - v_i).(r_i - r_j)
+    const double dvg = t * s;                        // (v_j - v_i).gradW
+    const double ms = mj * s;
+    const double mgx = dx * ms, mgy = dy * ms, mgz = dz * ms;
     acc.divv += mj * dvg;
     // StandardAV: mu = hbar w / D, Pi = (-alpha csbar mu + beta mu^2) / rhobar for approaching pairs (w < 0); with
-    // w clamped to min(w, 0) the receding pairs give mu = 0 and Pi = 0 exactly, without a branch
-    const double w = fmin(-(dvx * dx + dvy * dy + dvz * dz), 0.);
-    const double csbar = 0.5 * (pi.cs + pj.cs);
-    const double mu = hbar * w * rhobar * invA;
-    const double PiAv = mu * fma(prm.av_beta, mu, -prm.av_alpha * csbar) * (D * invA);
-    acc.du += 0.5 * PiAv * (-mj * dvg);
-    const double c = pi.P + pj.P + PiAv;
+    // w clamped to min(w, 0) the receding pairs give mu = 0 and Pi = 0 exactly, without a branch. Q = Pi / 2.
+    const double w = fmin(-t, 0.);
+    const double mu = hbar * w * rs * invA;
+    const double Q = mu * fma(prm.av_beta, mu, (-0.5 * prm.av_alpha) * (pi.cs + pj.cs)) * (D * invA);
+    acc.du -= Q * (mj * dvg);
+    const double c = fma(2., Q, pi.P + pj.P);
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
@@ -403,8 +405,8 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
             ok = valid && (pi.grp == pj.grp) && (pi.grp >= 0);
         }
         // masked mass / volume instead of a branch around the tensor sums
-        const double fm = selectD(ok, pj.m, 0.);
-        const double fx = fm * gx, fy = fm * gy, fz = fm * gz;
+        const double fs = selectD(ok, pj.m, 0.) * s;
+        const double fx = dx * fs, fy = dy * fs, fz = dz * fs;
         const double sxx = pi.Sr[0] + pj.Sr[0], syy = pi.Sr[1] + pj.Sr[1], sxy = pi.Sr[2] + pj.Sr[2],
                      sxz = pi.Sr[3] + pj.Sr[3], syz = pi.Sr[4] + pj.Sr[4];
         const double szz = -sxx - syy;
