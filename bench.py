@@ -28,6 +28,7 @@ UNIT = "particle-updates/s"
 # Algorithmic HBM bytes per particle-update, SURVEY.md section 8(d), solid + correction tensor:
 BYTES_FULL_STEP = 1412.0      # full PredictorCorrector step
 BYTES_INTEGRATE = 628.0       # find + derivatives (integrate() only)
+FP64_INSTR_PER_PAIR = 105.0    # FP64 instructions of the pair body per neighbour pair (SASS count)
 BYTES_PAIR_KERNEL = 408.0     # dominant kernel, itemised in DESIGN.md section 3 (sorted record + epilogue inputs in, derivatives out)
 
 
@@ -227,6 +228,8 @@ def main():
     dev_s = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
     neigh_mean = st.neigh_mean
+    pairs_per_step = float(st.pair_count)
+    fp64_peak = eng.measure_fp64_peak() if rank == 0 else 0.0
 
     tsec = torch.tensor([max(wall, dev_s)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -298,7 +301,10 @@ def main():
                      "fp64_pipe_active_pct_ncu": (prof["fp64_pipe_active_pct"] if prof else None),
                      "kernel_ms": pair_s * 1e3, "kernel_share_of_step": pair_s / step_s,
                      "step_hbm_frac": BYTES_FULL_STEP * (n_owned / step_s) / 1e9 / peak,
-                     "note": "pair kernel is FP64-pipe bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},
+                     "fp64": {"peak_fma_per_s": fp64_peak, "peak_tflops": 2e-12 * fp64_peak, "kind": "measured live (DFMA loop, all SMs)",
+                              "achieved_fp64_instr_per_s": (FP64_INSTR_PER_PAIR * pairs_per_step / pair_s if (solid and pair_s > 0) else None),
+                              "frac": (FP64_INSTR_PER_PAIR * pairs_per_step / pair_s / fp64_peak if (solid and pair_s > 0 and fp64_peak > 0) else None)},
+                     "note": "pair kernel is FP64-pipe / latency bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},
         "phase_ms": {"grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
                      "pair_kernel": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps},
     }

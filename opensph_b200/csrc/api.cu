@@ -535,6 +535,12 @@ int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4) {
     return SPHGPU_OK;
 }
 
+int sphgpu_measure_fp64_peak(sphgpu_ctx* ctx, double* fma_per_second) {
+    if (!ctx || !fma_per_second) return fail(SPHGPU_E_INVALID, "null argument");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return measureFp64Peak(ctx, fma_per_second);
+}
+
 int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms) {
     if (!ctx || !ms) return fail(SPHGPU_E_INVALID, "null argument");
     *ms = ctx->lastHaloMs;

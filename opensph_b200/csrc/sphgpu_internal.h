@@ -137,6 +137,7 @@ int launchPredict(sphgpu_ctx* ctx, double dt);
 int launchCorrect(sphgpu_ctx* ctx, double dt);
 int launchEuler(sphgpu_ctx* ctx, double dt);
 int launchCriteria(sphgpu_ctx* ctx);
+int measureFp64Peak(sphgpu_ctx* ctx, double* fmaPerSecond);
 // transfer.cu
 int launchUnpack(sphgpu_ctx* ctx, int q, int order, int layout, const void* stagingDev, uint32_t first, uint32_t count);
 int launchPack(sphgpu_ctx* ctx, int q, int order, int layout, void* stagingDev, uint32_t first, uint32_t count);

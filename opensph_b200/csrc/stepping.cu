@@ -241,6 +241,20 @@ __global__ void __launch_bounds__(256) k_criteria(DevicePointers d, uint32_t n, 
     }
 }
 
+// FP64 FMA throughput probe (the secondary roofline of the pair kernel; SURVEY 8d asks for a measured DFMA peak).
+__global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double b = 1.0000001, c = 1.e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) {
+        out[0] = r; // never true; keeps the loop alive
+    }
+}
+
 #define SPH_DISPATCH_SOLID(KERNEL, ...)                                                                               \
     do {                                                                                                              \
         if (ctx->solid) {                                                                                             \
@@ -250,6 +264,22 @@ __global__ void __launch_bounds__(256) k_criteria(DevicePointers d, uint32_t n, 
         }                                                                                                             \
         ctx->launches += 1;                                                                                           \
     } while (0)
+
+int measureFp64Peak(sphgpu_ctx* ctx, double* fmaPerSecond) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    cudaStream_t st = ctx->stream;
+    k_dfma_probe<<<blocks, threads, 0, st>>>(ctx->d.boundsPartial, 1024, 0.5); // warm-up
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[6], st));
+    k_dfma_probe<<<blocks, threads, 0, st>>>(ctx->d.boundsPartial, iters, 0.5);
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[7], st));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+    *fmaPerSecond = (double)blocks * threads * 8. * iters / (ms * 1.e-3);
+    return SPHGPU_OK;
+}
 
 int launchPredict(sphgpu_ctx* ctx, double dt) {
     const uint32_t n = ctx->n;

@@ -203,6 +203,12 @@ class Engine:
         _check(self.lib.sphgpu_last_timings(self._ctx, ms.ctypes.data_as(C.POINTER(C.c_double))))
         return ms
 
+    def measure_fp64_peak(self) -> float:
+        """FP64 fused multiply-adds per second of this device (DFMA microbenchmark inside the library)."""
+        v = C.c_double(0.0)
+        _check(self.lib.sphgpu_measure_fp64_peak(self._ctx, C.byref(v)))
+        return float(v.value)
+
     def last_halo_ms(self) -> float:
         ms = C.c_double(0.0)
         _check(self.lib.sphgpu_last_halo_ms(self._ctx, C.byref(ms)))
