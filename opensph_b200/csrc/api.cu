@@ -204,6 +204,8 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     SPH_TRY(devAlloc(&ctx->d.segStart, (size_t)ctx->maxCells + 2));
     SPH_TRY(devAlloc(&ctx->d.unitDesc, (size_t)ctx->maxSegs));
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
+    SPH_TRY(devAlloc(&ctx->d.posF, cap));
+    SPH_TRY(devAlloc(&ctx->d.cellHmax, (size_t)ctx->maxCells + 1));
     SPH_TRY(devAlloc(&ctx->d.order, cap));
     SPH_TRY(devAlloc(&ctx->d.cellOf, cap));
     SPH_TRY(devAlloc(&ctx->d.rank, cap));
@@ -249,6 +251,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc);
+    cudaFree(ctx->d.posF); cudaFree(ctx->d.cellHmax);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree(ctx->staging);

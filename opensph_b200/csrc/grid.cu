@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPart
             n *= (uint32_t)g.dim[k];
         }
         g.ncells = n;
+        g.extent = fmax(fmax(ext[0], ext[1]), ext[2]) + cell;
+        g.unsorted = 0u;
         *d.grid = g;
     }
 }
@@ -264,25 +266,68 @@ __global__ void __launch_bounds__(256) k_scatter(DevicePointers d, uint32_t nAct
     d.order[d.cellStart[d.cellOf[i]] + d.rank[i]] = i;
 }
 
-// The histogram ranks come from atomics and are not reproducible; order every cell by slot index so that the
-// summation order (and therefore every bit of the result) is the same from run to run.
+// The histogram ranks come from atomics and are not reproducible; order every cell by (x, slot index) so that the
+// summation order (and therefore every bit of the result) is the same from run to run. Cells of one row are ordered
+// in x already, so every cell ROW ends up sorted by x: the pair kernel finds the x-window a target can reach in a
+// candidate row by bisection. Also records the largest h of every cell (bound of the conservative FP32 pre-filter).
+constexpr int SORT_LOCAL = 48;
 __global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t maxCells) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= maxCells || c >= d.grid->ncells) {
+    if (c >= maxCells) {
+        return;
+    }
+    if (c >= d.grid->ncells) {
+        d.cellHmax[c] = 0u;
         return;
     }
     const uint32_t s = d.cellStart[c], e = d.cellStart[c + 1];
-    if (e - s < 2 || e - s > 4096) {
+    const uint32_t n = e - s;
+    float hm = 0.f;
+    for (uint32_t a = s; a < e; ++a) {
+        hm = fmaxf(hm, __double2float_ru(d.f[F_H][d.order[a]]));
+    }
+    d.cellHmax[c] = __float_as_uint(hm);
+    if (n < 2) {
+        return;
+    }
+    if (n <= (uint32_t)SORT_LOCAL) { // the usual case: insertion sort on a private copy of the keys
+        double kx[SORT_LOCAL];
+        uint32_t ks[SORT_LOCAL];
+        for (uint32_t a = 0; a < n; ++a) {
+            const uint32_t slot = d.order[s + a];
+            const double x = d.f[F_X][slot];
+            uint32_t b = a;
+            while (b > 0 && (kx[b - 1] > x || (kx[b - 1] == x && ks[b - 1] > slot))) {
+                kx[b] = kx[b - 1];
+                ks[b] = ks[b - 1];
+                --b;
+            }
+            kx[b] = x;
+            ks[b] = slot;
+        }
+        for (uint32_t a = 0; a < n; ++a) {
+            d.order[s + a] = ks[a];
+        }
+        return;
+    }
+    if (n > 4096) { // degenerate grid (one huge h): give up the order, the pair kernel then scans whole rows
+        d.grid->unsorted = 1u;
         return;
     }
     for (uint32_t a = s + 1; a < e; ++a) {
-        const uint32_t key = d.order[a];
+        const uint32_t slot = d.order[a];
+        const double x = d.f[F_X][slot];
         uint32_t b = a;
-        while (b > s && d.order[b - 1] > key) {
-            d.order[b] = d.order[b - 1];
+        while (b > s) {
+            const uint32_t prev = d.order[b - 1];
+            const double xp = d.f[F_X][prev];
+            if (!(xp > x || (xp == x && prev > slot))) {
+                break;
+            }
+            d.order[b] = prev;
             --b;
         }
-        d.order[b] = key;
+        d.order[b] = slot;
     }
 }
 

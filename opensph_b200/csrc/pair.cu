@@ -15,6 +15,12 @@ int uploadConstants(const sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
+/// FP32 copy of a position relative to the grid origin (the pre-filter of the tiled pair kernel compares these; targets
+/// and candidates must be converted by this very expression so that equal positions stay equal).
+__device__ __forceinline__ float4 gridRelative(const GridDev& g, double x, double y, double z, double h) {
+    return make_float4((float)(x - g.lo[0]), (float)(y - g.lo[1]), (float)(z - g.lo[2]), (float)h);
+}
+
 // ---- prologue: EoS + rheology + damage growth, and packing of the sorted neighbour-input planes -----------
 // One thread per SORTED position t; slot i = order[t]. Reads the slot state once, writes p, cs, reduce, yielded S
 // and dD/dt back to the slot planes and the neighbour inputs (with p/rho^2, S/rho^2, m/rho precomputed) to the
@@ -62,8 +68,10 @@ __global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_
     const double m = d.f[F_M][i];
     constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
     double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * RD);
-    rec[0] = make_double2(d.f[F_X][i], d.f[F_Y][i]);
-    rec[1] = make_double2(d.f[F_Z][i], d.f[F_H][i]);
+    const double x = d.f[F_X][i], y = d.f[F_Y][i], z = d.f[F_Z][i], h = d.f[F_H][i];
+    rec[0] = make_double2(x, y);
+    rec[1] = make_double2(z, h);
+    d.posF[t] = gridRelative(*d.grid, x, y, z, h);
     rec[2] = make_double2(d.f[F_VX][i], d.f[F_VY][i]);
     rec[3] = make_double2(d.f[F_VZ][i], m);
     rec[4] = make_double2(rho, p * rhoInv2);

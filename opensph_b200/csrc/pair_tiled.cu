@@ -11,10 +11,11 @@
 //              chunk boundaries costs little.
 // Staging    : one thread issues TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier), one per
 //              contiguous candidate row; records are 144-byte FP64 structures (odd 16-byte stride => consecutive
-//              records fall into different bank groups); an FP32 {x,y,z,h} copy relative to a unit-local origin is
-//              derived from them.
-// Phase 1    : every thread scans the candidates of the cells IT can reach (row-wise interval culling in y, z and x)
-//              with a conservative FP32 distance test (FP32/ALU pipes) and appends survivors to a private u16 list.
+//              records fall into different bank groups); the FP32 {x,y,z,h} copies relative to the grid origin
+//              (written by the prologue) are staged the same way.
+// Phase 1    : every thread scans, per candidate row, the x-window IT can reach (interval culling in y and z, then
+//              bisection on x: cell rows are sorted by x, see k_sort_cells) with a conservative FP32 distance test
+//              (FP32/ALU pipes) and appends survivors to a private u16 list.
 // Phase 2    : every thread walks its list two entries at a time; the exact FP64 predicate (bit-identical neighbour
 //              sets) enters the branch-free FP64 pair body as a mask -- full lanes, no divergence on the expensive path.
 //
@@ -27,7 +28,7 @@ namespace sph {
 constexpr int TILE_T = 128;   // targets (threads) per work unit
 constexpr int TILE_C = 576;   // staged candidates per chunk
 constexpr int LIST_CAP = 64;  // private list entries per round
-constexpr int TILE_X = 20;    // cell-range entries cached in shared memory per candidate row
+constexpr int TILE_X = 20;    // widest unit in cells (bounds the per-unit loops over candidate cells)
 constexpr int CHUNK_ROWS = 6; // candidate rows per chunk: 2 z-layers x 3 y-rows
 
 template <bool SOLID>
@@ -62,14 +63,20 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
                      : "memory");
     }
 }
+/// 16-bit store to shared memory through a 32-bit shared-window address (keeps the list cursor a single register).
+__device__ __forceinline__ void storeSharedU16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
 __device__ __forceinline__ void fenceProxyAsync() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ---- work list: units of <= 128 targets per double row (next-fit packing of cell columns) ----------------------
-// One thread per double row walks its cells in x; FILL = false counts the units, FILL = true writes the descriptors
-// {double row, cA, skip, cB}: the unit takes targets [skip, skip + 128) of the concatenation
-// (lower row cells cA..cB) ++ (upper row cells cA..cB).
+// ---- work list: units of <= 128 targets per double row ---------------------------------------------------------
+// The targets of a double row are taken in COLUMN order: for every cell column c the lower cell's particles, then the
+// upper cell's. One thread per double row cuts this sequence into pieces of 128 (a column may be split between two
+// units, so units are full except at the end of a row or where the x-range would outgrow TILE_X). FILL = false counts
+// the units, FILL = true writes the descriptors {double row, cA, skip, (cB - cA) | targets << 8}: the unit takes
+// `targets` entries of the sequence of columns cA.., starting `skip` entries into column cA.
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCells) {
     const uint32_t dr = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,42 +98,47 @@ __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCel
     const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
     uint32_t units = 0;
     const uint32_t out = FILL ? d.segStart[dr] : 0u;
-    int cA = 0, cLast = 0;
-    uint32_t acc = 0;
-    auto emit = [&](int a, int b, uint32_t total) {
-        const uint32_t parts = (total + TILE_T - 1) / TILE_T;
-        if (FILL) {
-            for (uint32_t p = 0; p < parts; ++p) {
-                d.unitDesc[out + units + p] = make_uint4(dr, (uint32_t)a, p * TILE_T, (uint32_t)b);
-            }
-        }
-        units += parts;
-    };
-    for (int c = 0; c < dimx; ++c) {
+    auto columnCount = [&](int c) {
         uint32_t cnt = d.cellStart[rbL + c + 1] - d.cellStart[rbL + c];
         if (hasU) {
             cnt += d.cellStart[rbU + c + 1] - d.cellStart[rbU + c];
         }
-        if (cnt == 0) {
+        return cnt;
+    };
+    int c = 0;
+    uint32_t skip = 0; // entries of column c already handed out
+    while (c < dimx) {
+        if (columnCount(c) - skip == 0) {
+            c++;
+            skip = 0;
             continue;
         }
-        // close the open unit when the column does not fit or the x-range would outgrow the cached cell table
-        if (acc > 0 && (acc + cnt > (uint32_t)TILE_T || c - cA + 3 > TILE_X)) {
-            emit(cA, cLast, acc);
-            acc = 0;
+        const int cA = c;
+        const uint32_t skipA = skip;
+        uint32_t taken = 0;
+        int cLast = c;
+        while (c < dimx && taken < (uint32_t)TILE_T && c - cA + 3 <= TILE_X) {
+            const uint32_t avail = columnCount(c) - skip;
+            if (avail == 0) {
+                c++;
+                skip = 0;
+                continue;
+            }
+            const uint32_t take = min(avail, (uint32_t)TILE_T - taken);
+            taken += take;
+            cLast = c;
+            if (take == avail) {
+                c++;
+                skip = 0;
+            } else {
+                skip += take;
+                break;
+            }
         }
-        if (acc == 0) {
-            cA = c;
+        if (FILL) {
+            d.unitDesc[out + units] = make_uint4(dr, (uint32_t)cA, skipA, (uint32_t)(cLast - cA) | (taken << 8));
         }
-        acc += cnt;
-        cLast = c;
-        if (acc >= (uint32_t)TILE_T) { // a single column with more than 128 targets is split by `skip`
-            emit(cA, cLast, acc);
-            acc = 0;
-        }
-    }
-    if (acc > 0) {
-        emit(cA, cLast, acc);
+        units++;
     }
     if (!FILL) {
         d.cellCount[dr] = units;
@@ -137,7 +149,6 @@ struct ChunkState {
     uint32_t beg[CHUNK_ROWS], end[CHUNK_ROWS], base[CHUNK_ROWS]; // staged global range per candidate row + smem offset
     uint32_t used;
     int chunk;                                  // 0 far, 1 near, 2 centre
-    uint32_t cells[CHUNK_ROWS][TILE_X + 2];     // cellStart[row base + x0 ...] of the candidate rows (x0 .. x1+1)
 };
 
 struct ChunkCursor { // iteration state of the chunk builder (thread 0 only)
@@ -212,12 +223,18 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     __shared__ uint16_t sPerm[TILE_T];
     __shared__ __align__(8) uint64_t stageBar;
     __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
+    __shared__ uint32_t sHmax;
+    __shared__ uint32_t sColL[TILE_X + 2], sColU[TILE_X + 2], sTarget[TILE_T];
 
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
     const uint32_t totalUnits = d.segStart[maxCells];
     const int tid = threadIdx.x;
     const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
+    // the FP32 coordinates are relative to the grid origin: absolute rounding error <= 2^-24 * extent per coordinate
+    const float slack = (float)(g.extent * 1.e-6), guard = (float)(g.extent * 1.e-5);
+    const float cellF = (float)g.cell, cellZF = (float)g.cellZ;
+    const bool rowsSorted = g.unsorted == 0u;
     ChunkCursor cur;
     uint32_t stagePhase = 0;
     if (tid == 0) {
@@ -227,38 +244,58 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
 
     for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
         const uint4 desc = d.unitDesc[unit];
-        const uint32_t dr = desc.x;
-        const int cA = (int)desc.y, cB = (int)desc.w;
+        const uint32_t dr = desc.x, skip = desc.z, nLive = desc.w >> 8;
+        const int cA = (int)desc.y, span = (int)(desc.w & 0xffu), cB = cA + span;
         const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
         const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
         const bool hasU = 2 * k + 1 < dimz;
         const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
-        const uint32_t lBeg = d.cellStart[rbL + cA], lCnt = d.cellStart[rbL + cB + 1] - lBeg;
-        const uint32_t uBeg = hasU ? d.cellStart[rbU + cA] : 0u, uCnt = hasU ? d.cellStart[rbU + cB + 1] - uBeg : 0u;
-        const uint32_t total = lCnt + uCnt, skip = desc.z;
-        const uint32_t nLive = min((uint32_t)TILE_T, total - skip);
         const int x0 = max(cA - 1, 0), x1 = min(cB + 1, dimx - 1);
-        // unit-local origin of the FP32 copies: corner of the unit's first cell
-        const double ox = g.lo[0] + cA * g.cell, oy = g.lo[1] + cy * g.cell, oz = g.lo[2] + (2 * k) * g.cellZ;
-        // absolute error bound of the FP32 relative coordinates (2^-24 * extent per coordinate) with a wide safety factor
-        const float slack = (float)((double)(x1 - x0 + 3) * g.cell * 1.e-6);
-        const float cellF = (float)g.cell, cellZF = (float)g.cellZ, cellInvF = (float)g.cellInv;
-        const float guard = (float)((double)(x1 - x0 + 3) * g.cell * 1.e-5);
 
-        // ---- lane assignment: order the unit's targets by z so that the lanes of a warp see similar numbers of
-        // neighbours in every chunk (balanced private lists => full lanes in phase 2)
-        auto targetIndex = [&](uint32_t j) { return j < lCnt ? lBeg + j : uBeg + (j - lCnt); };
-        sKey[tid] = ((uint32_t)tid < nLive) ? (float)(d.rec[(size_t)targetIndex(skip + tid) * L::G + R_Z] - oz) : 3.0e38f;
-        if (tid < 3 * CHUNK_ROWS) { // global ranges of the unit's 18 candidate rows
-            const int z = chunkLayer(tid / CHUNK_ROWS, tid % CHUNK_ROWS, k), y = cy + (tid % 3) - 1;
+        // ---- sorted ranges of the unit's cell columns (targets) and of its 18 candidate rows ----
+        if (tid <= span + 1) {
+            sColL[tid] = d.cellStart[rbL + cA + tid];
+            sColU[tid] = hasU ? d.cellStart[rbU + cA + tid] : 0u;
+        }
+        if (tid == 0) {
+            sHmax = 0u;
+        }
+        if (tid >= 32 && tid < 32 + 3 * CHUNK_ROWS) {
+            const int row = tid - 32;
+            const int z = chunkLayer(row / CHUNK_ROWS, row % CHUNK_ROWS, k), y = cy + (row % 3) - 1;
             uint32_t rb = 0, re = 0;
             if (z >= 0 && z < dimz && y >= 0 && y < dimy) {
                 const uint32_t base = (uint32_t)((z * dimy + y) * dimx);
                 rb = d.cellStart[base + x0];
                 re = d.cellStart[base + x1 + 1];
             }
-            sRowBeg[tid] = rb;
-            sRowEnd[tid] = re;
+            sRowBeg[row] = rb;
+            sRowEnd[row] = re;
+        }
+        __syncthreads();
+        // ---- lane assignment: the unit's targets in column order (lower cell, then upper cell of every column), then
+        // ordered by z so that the lanes of a warp see similar numbers of neighbours in every chunk (balanced private
+        // lists => full lanes in phase 2)
+        {
+            uint32_t tIdx = 0u; // sorted index of target `tid` of the unit, bit 31 = upper row
+            if ((uint32_t)tid < nLive) {
+                uint32_t pos = skip + (uint32_t)tid;
+                for (int c = 0; c <= span; ++c) {
+                    const uint32_t nl = sColL[c + 1] - sColL[c], nu = sColU[c + 1] - sColU[c];
+                    if (pos < nl) {
+                        tIdx = sColL[c] + pos;
+                        break;
+                    }
+                    pos -= nl;
+                    if (pos < nu) {
+                        tIdx = (sColU[c] + pos) | 0x80000000u;
+                        break;
+                    }
+                    pos -= nu;
+                }
+            }
+            sTarget[tid] = tIdx;
+            sKey[tid] = ((uint32_t)tid < nLive) ? d.posF[tIdx & 0x7fffffffu].z : 3.0e38f;
         }
         __syncthreads();
         {
@@ -269,12 +306,25 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                 rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
             }
             sPerm[rank] = (uint16_t)tid;
+            // largest h among the unit's candidates (cells x0..x1 of the 18 rows): bound of the FP32 filter radius
+            uint32_t hm = 0u;
+            for (int e = tid; e < 3 * CHUNK_ROWS * (TILE_X + 2); e += TILE_T) {
+                const int row = e / (TILE_X + 2), c = x0 + e % (TILE_X + 2);
+                const int z = chunkLayer(row / CHUNK_ROWS, row % CHUNK_ROWS, k), y = cy + (row % 3) - 1;
+                if (c <= x1 && z >= 0 && z < dimz && y >= 0 && y < dimy) {
+                    hm = max(hm, d.cellHmax[(uint32_t)((z * dimy + y) * dimx) + c]); // bit patterns of floats >= 0 order like the values
+                }
+            }
+            hm = __reduce_max_sync(0xffffffffu, hm);
+            if ((tid & 31) == 0) {
+                atomicMax(&sHmax, hm);
+            }
         }
         __syncthreads();
-        const bool live = (uint32_t)tid < nLive;
-        const uint32_t jOwn = skip + sPerm[tid];
-        const uint32_t t = live ? targetIndex(jOwn) : 0u;
-        const bool upper = live && jOwn >= lCnt;
+        const bool live = (uint32_t)tid < nLive; // the idle lanes sort last (key 3e38)
+        const uint32_t tOwn = sTarget[sPerm[tid]];
+        const uint32_t t = live ? (tOwn & 0x7fffffffu) : 0u;
+        const bool upper = live && (tOwn >> 31) != 0u;
         const uint32_t slot = live ? d.order[t] : 0xffffffffu;
         const bool target = live && slot < nOwned; // ghosts are neighbours only
         if (!__syncthreads_or(target ? 1 : 0)) {
@@ -282,21 +332,21 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
         }
 
         Particle pi;
-        int cx = 0;
-        float fxi = 0.f, fyi = 0.f, fzi = 0.f, fhi = 0.f;
-        float reachF = 0.f;
+        float fxi = 0.f, fyi = 0.f, fzi = 0.f;
+        float lim = 0.f;
         if (live) {
             loadRecord<SOLID>(d.rec + (size_t)t * L::G, pi);
-            cx = (int)(d.sCell[t] - (upper ? rbU : rbL));
-            fxi = (float)(pi.x - ox);
-            fyi = (float)(pi.y - oy);
-            fzi = (float)(pi.z - oz);
-            fhi = (float)pi.h;
-            reachF = (float)(0.5 * c_prm.kernel_radius * (pi.h + g.hmax) * (1. + 1.e-5)); // >= R * hbar for every neighbour
+            const float4 pf = d.posF[t];
+            fxi = pf.x;
+            fyi = pf.y;
+            fzi = pf.z;
+            // >= R * hbar + the rounding of the FP32 coordinates, for every candidate of the unit
+            lim = fmaf(Rhalf, pf.w * (1.f + 1.e-6f) + __uint_as_float(sHmax), slack);
         } else {
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
         }
+        const float lim2 = lim * lim;
         Accum acc;
         accumZero(acc);
 
@@ -313,36 +363,22 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             if (cs.used == 0) {
                 break;
             }
-            // ---- stage the chunk: TMA bulk copies of the FP64 records (one per candidate row), then the FP32 copies ----
+            // ---- stage the chunk: TMA bulk copies of the FP64 records and of the FP32 positions, one pair per row ----
             if (tid == 0) {
-                fenceProxyAsync(); // the buffer was last read through the generic proxy
-                mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8));
+                fenceProxyAsync(); // the buffers were last read through the generic proxy
+                mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8 + 16));
 #pragma unroll
                 for (int r = 0; r < CHUNK_ROWS; ++r) {
                     const uint32_t n = cs.end[r] - cs.beg[r];
                     if (n > 0) {
                         bulkCopyG2S(recS + (size_t)cs.base[r] * L::S, d.rec + (size_t)cs.beg[r] * L::G, n * (uint32_t)(L::G * 8), &stageBar);
+                        bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
                     }
                 }
                 nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
             }
-            // cell ranges of the candidate rows, one entry per thread (issued before waiting for the copies)
-            ChunkState& csw = csBuf[buf];
-            for (int e = tid; e < CHUNK_ROWS * (TILE_X + 2); e += TILE_T) {
-                const int r = e / (TILE_X + 2), c = x0 + e % (TILE_X + 2);
-                const int z = chunkLayer(cs.chunk, r, k), y = cy + (r % 3) - 1;
-                if (c <= x1 + 1 && z >= 0 && z < dimz && y >= 0 && y < dimy) {
-                    csw.cells[r][c - x0] = d.cellStart[(uint32_t)((z * dimy + y) * dimx) + c];
-                }
-            }
             mbarWait(&stageBar, stagePhase);
             stagePhase ^= 1;
-            for (uint32_t c = tid; c < cs.used; c += TILE_T) {
-                const double2* src = reinterpret_cast<const double2*>(recS + (size_t)c * L::S);
-                const double2 a0 = src[0], a1 = src[1];
-                f4[c] = make_float4((float)(a0.x - ox), (float)(a0.y - oy), (float)(a1.x - oz), (float)a1.y);
-            }
-            __syncthreads();
             buf ^= 1;
             if (!target) {
                 continue;
@@ -354,57 +390,65 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             const double* self = recS + ((chunk == 2 && t >= cs.beg[selfRow] && t < cs.end[selfRow])
                                                 ? (size_t)(cs.base[selfRow] + (t - cs.beg[selfRow])) * L::S
                                                 : (size_t)TILE_C * L::S);
+            const uint32_t listOwn = smemAddr(list + tid); // byte address of this lane's first list slot
+            constexpr uint32_t LIST_STRIDE = TILE_T * 2u;
             int r = 0;
             uint32_t kpos = 0, khi = 0;
             bool open = false;
             while (r < CHUNK_ROWS) {
-                int cnt = 0;
+                uint32_t lp = listOwn;
                 while (r < CHUNK_ROWS) {
                     if (!open) {
-                        const uint32_t b = cs.beg[r], e = cs.end[r];
+                        const uint32_t b = cs.beg[r], len = cs.end[r] - b;
                         kpos = khi = 0;
-                        if (e > b) {
-                            // intervals of this candidate row in y and z, and the x-interval the target can reach in it:
-                            // FP32 relative to the unit origin with a guard band (cells were assigned in FP64)
-                            const int zrel = chunkLayer(chunk, r, 0), yrel = (r % 3) - 1; // relative to (2k, cy)
-                            const float yl = (float)yrel * cellF, zl = (float)zrel * cellZF;
+                        if (len > 0) {
+                            // y- and z-intervals of this candidate row (FP32 relative to the grid origin, with a guard band:
+                            // cells were assigned in FP64) and the x-window [xlo, xhi] the target can reach in it
+                            const int zabs = chunkLayer(chunk, r, k), yabs = cy + (r % 3) - 1;
+                            const float yl = (float)yabs * cellF, zl = (float)zabs * cellZF;
                             const float dyMin = fmaxf(fmaxf(yl - fyi, fyi - (yl + cellF)) - guard, 0.f);
                             const float dzMin = fmaxf(fmaxf(zl - fzi, fzi - (zl + cellZF)) - guard, 0.f);
-                            const float rem = reachF * reachF - dyMin * dyMin - dzMin * dzMin;
-                            if (rem > 0.f) {
-                                const float ext = sqrtf(rem) * (1.f + 1.e-5f) + guard;
-                                int c0 = cA + (int)floorf((fxi - ext) * cellInvF);
-                                int c1 = cA + (int)floorf((fxi + ext) * cellInvF);
-                                c0 = max(max(c0, cx - 1), x0);
-                                c1 = min(min(c1, cx + 1), x1);
-                                if (c0 <= c1) {
-                                    // smem index = base + (global index - beg); the staged piece may be a part of the row
-                                    const uint32_t glo = max(cs.cells[r][c0 - x0], b), ghi = min(cs.cells[r][c1 + 1 - x0], e);
-                                    if (ghi > glo) {
-                                        kpos = cs.base[r] + (glo - b);
-                                        khi = cs.base[r] + (ghi - b);
-                                    }
+                            const float rem = lim2 - dyMin * dyMin - dzMin * dzMin;
+                            const float ext = sqrtf(fmaxf(rem, 0.f)) * (1.f + 1.e-5f) + guard;
+                            const float xlo = rem > 0.f ? fxi - ext : 3.0e38f, xhi = rem > 0.f ? fxi + ext : -3.0e38f;
+                            const uint32_t pieceBase = cs.base[r];
+                            uint32_t pl = 0, ph = len;
+                            if (rowsSorted) {
+                                // bisection for both ends at once: pl = #{x < xlo}, ph = #{x <= xhi}; the trip count depends on
+                                // the row only, so the warp stays converged
+                                const float* fx = reinterpret_cast<const float*>(f4 + pieceBase);
+                                ph = 0;
+                                for (uint32_t step = 1u << (31 - __clz(len)); step > 0; step >>= 1) {
+                                    const uint32_t tl = pl + step, th = ph + step;
+                                    const float vl = fx[4 * (min(tl, len) - 1)], vh = fx[4 * (min(th, len) - 1)];
+                                    pl = (tl <= len && vl < xlo) ? tl : pl;
+                                    ph = (th <= len && vh <= xhi) ? th : ph;
                                 }
+                            } else if (!(rem > 0.f)) {
+                                ph = 0;
+                            }
+                            if (ph > pl) {
+                                kpos = pieceBase + pl;
+                                khi = pieceBase + ph;
                             }
                         }
                         open = true;
                     }
-                    // four candidates per trip: the loads are independent, only the list append is serial. The target
-                    // itself is not excluded here (~600 compares) but masked in phase 2 (~70 compares).
+                    // eight candidates per trip: the loads are independent, only the list append is serial. The target
+                    // itself is not excluded here (~300 compares) but masked in phase 2 (~70 compares).
                     {
-                        uint16_t* lp = list + cnt * TILE_T + tid;
 #define SPH_F32_TEST(C, K)                                                                                            \
     {                                                                                                                 \
         const float ddx = fxi - C.x, ddy = fyi - C.y, ddz = fzi - C.z;                                                \
         const float dd2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));                                                  \
-        const float lim = fmaf(Rhalf, fhi + C.w, slack);                                                              \
-        if (dd2 <= lim * lim) {                                                                                       \
-            *lp = (uint16_t)(K);                                                                                      \
-            lp += TILE_T;                                                                                             \
-            cnt++;                                                                                                    \
+        if (dd2 <= lim2) {                                                                                            \
+            storeSharedU16(lp, K);                                                                                    \
+            lp += LIST_STRIDE;                                                                                        \
         }                                                                                                             \
     }
-                        while (kpos + 8 <= khi && cnt + 8 <= LIST_CAP) {
+                        const uint32_t lpMax8 = listOwn + (LIST_CAP - 8) * LIST_STRIDE;
+                        const uint32_t lpMax4 = listOwn + (LIST_CAP - 4) * LIST_STRIDE;
+                        while (kpos + 8 <= khi && lp <= lpMax8) {
                             const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
                             const float4 ce = f4[kpos + 4], cf = f4[kpos + 5], cg = f4[kpos + 6], ch = f4[kpos + 7];
                             SPH_F32_TEST(ca, kpos)
@@ -417,7 +461,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                             SPH_F32_TEST(ch, kpos + 7)
                             kpos += 8;
                         }
-                        while (kpos + 4 <= khi && cnt + 4 <= LIST_CAP) {
+                        while (kpos + 4 <= khi && lp <= lpMax4) {
                             const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
                             SPH_F32_TEST(ca, kpos)
                             SPH_F32_TEST(cb, kpos + 1)
@@ -425,7 +469,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                             SPH_F32_TEST(cd, kpos + 3)
                             kpos += 4;
                         }
-                        while (kpos < khi && khi - kpos < 4 && cnt < LIST_CAP) {
+                        while (kpos < khi && khi - kpos < 4 && lp < listOwn + LIST_CAP * LIST_STRIDE) {
                             const float4 ca = f4[kpos];
                             SPH_F32_TEST(ca, kpos)
                             kpos++;
@@ -439,6 +483,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                         break; // list (nearly) full: drain it, then resume the scan
                     }
                 }
+                const int cnt = (int)((lp - listOwn) / LIST_STRIDE);
                 // phase 2: two list entries per trip so the long per-pair chains overlap
                 int q = 0;
                 for (; q + 1 < cnt; q += 2) {

@@ -50,6 +50,8 @@ struct GridDev {
     int dim[3];
     uint32_t ncells;
     double hmax;
+    double extent;     // largest edge of the grid box: scale of the FP32 rounding of the grid-relative coordinates
+    uint32_t unsorted; // set by k_sort_cells when a cell was too large to be ordered by x (windows then span whole rows)
 };
 
 struct StatsDev {
@@ -66,6 +68,8 @@ struct DevicePointers {
     uint32_t* u[U_COUNT];
     double* rec;        // sorted neighbour-input records, REC_SOLID or REC_FLUID doubles each
     uint32_t* sCell;    // sorted: linear cell index
+    float4* posF;       // sorted: FP32 {x, y, z} relative to the grid origin and h (conservative pre-filter of the pair kernel)
+    uint32_t* cellHmax; // [maxCells] bit pattern of the largest (float) h inside each cell
     uint32_t* order;    // sorted position -> slot
     uint32_t* cellOf;   // slot -> cell
     uint32_t* rank;     // slot -> rank inside its cell
