@@ -163,7 +163,7 @@ typedef struct sphgpu_stats {
     uint64_t pair_count;           /* sum of NEIGHBOR_CNT                                                    */
     double gpu_ms;                 /* device time of the call, CUDA events                                   */
     uint32_t kernel_launches;      /* kernels launched by this call                                          */
-    uint32_t reserved0;
+    uint32_t reserved0;            /* work units whose candidate lists overflowed the list pool (slow path)  */
 } sphgpu_stats;
 
 typedef struct sphgpu_timestep {
@@ -253,7 +253,8 @@ SPHGPU_API int sphgpu_measure_fp64_peak(sphgpu_ctx* ctx, double* fma_per_second)
 /* Device time of the halo exchange of the last sphgpu_step_pc_mgpu call (pack + NCCL send/recv + unpack, including the
  * time spent waiting for the neighbour ranks), milliseconds. */
 SPHGPU_API int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms);
-/* Selects the pair-kernel variant (0 = default tiled kernel, 1 = direct per-thread kernel). For A/B checks only. */
+/* Selects the pair-kernel variant: 0 = default (candidate lists in their own kernel + tiled pair sums), 1 = direct
+ * per-thread kernel, 2 = tiled kernel with both phases fused. For A/B checks only. */
 SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
  * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the

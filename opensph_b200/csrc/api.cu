@@ -170,6 +170,9 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         return fail(SPHGPU_E_INVALID, "ContinuityEnum::SUM_ONLY_UNDAMAGED needs STRESS_REDUCING (a rheology)");
     }
 
+    if (capacity >= (1u << 30)) {
+        return fail(SPHGPU_E_INVALID, "capacity must be below 2^30 particles per device");
+    }
     const size_t cap = capacity;
     ctx->maxCells = std::max<uint32_t>(capacity / 4, 4096u);
     ctx->scanBlocks = (ctx->maxCells + 1 + SCAN_ITEMS - 1) / SCAN_ITEMS;
@@ -200,9 +203,17 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         SPH_TRY(devAlloc(&ctx->d.u[u], cap));
     }
     SPH_TRY(devAlloc(&ctx->d.rec, cap * (size_t)(ctx->solid ? REC_SOLID : REC_FLUID)));
-    ctx->maxSegs = capacity / 64 + ctx->maxCells + 2; // next-fit packing: units <= 2 N / 128 + double rows
+    ctx->maxSegs = capacity / 64 + ctx->maxCells + ctx->maxCells / 16 + 2; // units <= N / 128 + double rows + x-range cuts
     SPH_TRY(devAlloc(&ctx->d.segStart, (size_t)ctx->maxCells + 2));
     SPH_TRY(devAlloc(&ctx->d.unitDesc, (size_t)ctx->maxSegs));
+    SPH_TRY(devAlloc(&ctx->d.unitAux, (size_t)ctx->maxSegs));
+    SPH_TRY(devAlloc(&ctx->d.unitLane, cap));
+    SPH_TRY(devAlloc(&ctx->d.unitList, (size_t)ctx->maxSegs));
+    // list pool: ~0.8 rows of 256 B per particle on the eta = 1.3 lattice (68 neighbours); units that do not fit fall
+    // back to building their lists inside the pair kernel
+    ctx->poolRows = (uint32_t)std::min<size_t>(cap + cap / 2 + 8192, 0xfffffff0u);
+    SPH_TRY(devAlloc(&ctx->d.listPool, (size_t)ctx->poolRows * 256));
+    SPH_TRY(devAlloc(&ctx->d.listCursor, 1));
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
     SPH_TRY(devAlloc(&ctx->d.posF, cap));
     SPH_TRY(devAlloc(&ctx->d.cellHmax, (size_t)ctx->maxCells + 1));
@@ -250,7 +261,8 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     destroyHalo(ctx);
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
-    cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc);
+    cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc); cudaFree(ctx->d.unitAux); cudaFree(ctx->d.unitLane); cudaFree(ctx->d.unitList);
+    cudaFree(ctx->d.listPool); cudaFree(ctx->d.listCursor);
     cudaFree(ctx->d.posF); cudaFree(ctx->d.cellHmax);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
@@ -410,7 +422,7 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
         stats->neigh_mean = ctx->n ? (double)sd.pairCount / (double)ctx->n : 0.;
         stats->gpu_ms = ms;
         stats->kernel_launches = ctx->launches;
-        stats->reserved0 = 0;
+        stats->reserved0 = sd.fallbackUnits; // units whose candidate lists did not fit the list pool
     }
     return SPHGPU_OK;
 }

@@ -291,7 +291,7 @@ int launchPairTiled(sphgpu_ctx* ctx); // pair_tiled.cu
 
 int launchPair(sphgpu_ctx* ctx) {
     const uint32_t n = ctx->nActive;
-    const StatsDev init = { 0xffffffffu, 0u, 0ull };
+    const StatsDev init = { 0xffffffffu, 0u, 0ull, 0u, 0u };
     SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->d.stats, &init, sizeof(StatsDev), cudaMemcpyHostToDevice, ctx->stream));
     if (n == 0) {
         return SPHGPU_OK;

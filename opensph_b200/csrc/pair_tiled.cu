@@ -35,7 +35,7 @@ template <bool SOLID>
 struct TileLayout {
     static constexpr int G = SOLID ? REC_SOLID : REC_FLUID; // record stride (doubles), same in global and shared memory:
     static constexpr int S = G;                              // 9 or 7 (odd) x 16 B => conflict-free consecutive records
-    static constexpr size_t bytes = (size_t)TILE_C * S * 8 + (size_t)TILE_C * 16 + (size_t)LIST_CAP * TILE_T * 2;
+    static constexpr size_t bytes = (size_t)TILE_C * S * 8 + (size_t)TILE_C * 16 + (size_t)(LIST_CAP + 1) * TILE_T * 2;
 };
 
 // ---- TMA bulk copy + mbarrier (raw PTX; sm_90+ / sm_100a) -----------------------------------------------------
@@ -145,6 +145,101 @@ __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCel
     }
 }
 
+/// Where the lane words of a unit start in unitLane: units partition the particles, so the number of targets of all
+/// earlier units (earlier double rows, then earlier columns of this one) is a sum of cellStart differences.
+__device__ __forceinline__ uint32_t unitLaneBase(const DevicePointers& d, int dimx, int dimy, int dimz, int k, int cy, int cA, uint32_t skip) {
+    const uint32_t layerL = (uint32_t)((2 * k) * dimy * dimx), rowL = layerL + (uint32_t)(cy * dimx);
+    uint32_t base = d.cellStart[rowL + cA]; // all layers below 2k + earlier rows of layer 2k + earlier columns of its row cy
+    if (2 * k + 1 < dimz) {
+        const uint32_t layerU = (uint32_t)((2 * k + 1) * dimy * dimx), rowU = layerU + (uint32_t)(cy * dimx);
+        base += d.cellStart[rowU + cA] - d.cellStart[layerU]; // earlier rows of layer 2k+1 + earlier columns of its row cy
+    }
+    return base + skip;
+}
+
+// ---- unit preparation: lane order, filter radius bound, ghost-only flag -----------------------------------------
+// One CTA per unit (grid-stride). Orders the unit's targets by z (the lanes of a warp then see similar numbers of
+// neighbours in every chunk => full lanes in phase 2 of the pair kernel) and stores the order once, so that the
+// register- and shared-memory-heavy pair kernel starts every unit with a single coalesced load.
+__global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t nOwned, uint32_t maxCells) {
+    __shared__ uint32_t sColL[TILE_X + 2], sColU[TILE_X + 2], sHmax;
+    __shared__ float sKey[TILE_T];
+    const GridDev g = *d.grid;
+    const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
+    const uint32_t totalUnits = d.segStart[maxCells];
+    const int tid = threadIdx.x;
+    for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
+        const uint4 desc = d.unitDesc[unit];
+        const uint32_t dr = desc.x, skip = desc.z, nLive = desc.w >> 8;
+        const int cA = (int)desc.y, span = (int)(desc.w & 0xffu), cB = cA + span;
+        const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
+        const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
+        const bool hasU = 2 * k + 1 < dimz;
+        const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
+        const int x0 = max(cA - 1, 0), x1 = min(cB + 1, dimx - 1);
+        __syncthreads(); // the previous unit is done with the shared tables
+        if (tid <= span + 1) {
+            sColL[tid] = d.cellStart[rbL + cA + tid];
+            sColU[tid] = hasU ? d.cellStart[rbU + cA + tid] : 0u;
+        }
+        if (tid == 0) {
+            sHmax = 0u;
+        }
+        __syncthreads();
+        // the unit's targets in column order: lower cell, then upper cell of every column
+        uint32_t word = 0xffffffffu; // idle lane
+        bool owned = false;
+        float key = 3.0e38f;
+        if ((uint32_t)tid < nLive) {
+            uint32_t pos = skip + (uint32_t)tid, tIdx = 0u;
+            for (int c = 0; c <= span; ++c) {
+                const uint32_t nl = sColL[c + 1] - sColL[c], nu = sColU[c + 1] - sColU[c];
+                if (pos < nl) {
+                    tIdx = sColL[c] + pos;
+                    break;
+                }
+                pos -= nl;
+                if (pos < nu) {
+                    tIdx = (sColU[c] + pos) | 0x80000000u;
+                    break;
+                }
+                pos -= nu;
+            }
+            const uint32_t t = tIdx & 0x3fffffffu;
+            owned = d.order[t] < nOwned; // ghosts are neighbours only
+            word = tIdx | (owned ? 0u : 0x40000000u);
+            key = d.posF[t].z;
+        }
+        sKey[tid] = key;
+        // largest h among the unit's candidates (cells x0..x1 of the 18 rows): bound of the FP32 filter radius
+        uint32_t hm = 0u;
+        for (int e = tid; e < 18 * (TILE_X + 2); e += TILE_T) {
+            const int row = e / (TILE_X + 2), c = x0 + e % (TILE_X + 2);
+            const int z = 2 * k - 2 + row / 3, y = cy + (row % 3) - 1;
+            if (c <= x1 && z >= 0 && z < dimz && y >= 0 && y < dimy) {
+                hm = max(hm, d.cellHmax[(uint32_t)((z * dimy + y) * dimx) + c]); // bit patterns of floats >= 0 order like the values
+            }
+        }
+        hm = __reduce_max_sync(0xffffffffu, hm);
+        if ((tid & 31) == 0) {
+            atomicMax(&sHmax, hm);
+        }
+        const int anyOwned = __syncthreads_or(owned ? 1 : 0);
+        int rank = 0;
+        for (int j = 0; j < TILE_T; ++j) {
+            const float kj = sKey[j];
+            rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
+        }
+        const uint32_t base = unitLaneBase(d, dimx, dimy, dimz, k, cy, cA, skip);
+        if ((uint32_t)tid < nLive) {
+            d.unitLane[base + rank] = word; // live lanes sort before the idle ones: rank < nLive
+        }
+        if (tid == 0) {
+            d.unitAux[unit] = make_uint4(base, sHmax, (uint32_t)anyOwned, 0u);
+        }
+    }
+}
+
 struct ChunkState {
     uint32_t beg[CHUNK_ROWS], end[CHUNK_ROWS], base[CHUNK_ROWS]; // staged global range per candidate row + smem offset
     uint32_t used;
@@ -211,232 +306,141 @@ __device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t
     cs.chunk = chunk;
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER>
-__global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint32_t nOwned, uint32_t maxCells) {
-    using L = TileLayout<SOLID>;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    double* recS = reinterpret_cast<double*>(smemRaw);
-    float4* f4 = reinterpret_cast<float4*>(recS + (size_t)TILE_C * L::S);
-    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C);
-    __shared__ ChunkState csBuf[2];
-    __shared__ float sKey[TILE_T];
-    __shared__ uint16_t sPerm[TILE_T];
-    __shared__ __align__(8) uint64_t stageBar;
-    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
-    __shared__ uint32_t sHmax;
-    __shared__ uint32_t sColL[TILE_X + 2], sColU[TILE_X + 2], sTarget[TILE_T];
+// ---- pieces shared by the list kernel and the pair-sum kernel ---------------------------------------------------
+constexpr uint32_t LIST_STRIDE = TILE_T * 2u;        // bytes between consecutive entries of one lane's list
+constexpr uint32_t LIST_END = 0xffffffffu;           // unitList / block header: no (further) block
+constexpr uint32_t LIST_FALLBACK = 0xfffffffeu;      // unitList: the pool was exhausted, build the lists in the pair kernel
+constexpr uint32_t LIST_ROW_BYTES = TILE_T * 2u;     // one row of a list block: one u16 per lane
+// A list block is (1 + rows) rows of 256 B. Row 0: bytes 0..127 = per-lane entry counts (u8), bytes 128..139 = header
+// {row offset, rows, chunk ordinal} of the NEXT block of the unit (LIST_END terminates). Rows 1.. = entries, [entry][lane],
+// each entry the shared-memory index of a staged candidate of the chunk.
 
-    const GridDev g = *d.grid;
-    const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
-    const uint32_t totalUnits = d.segStart[maxCells];
-    const int tid = threadIdx.x;
-    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
-    // the FP32 coordinates are relative to the grid origin: absolute rounding error <= 2^-24 * extent per coordinate
-    const float slack = (float)(g.extent * 1.e-6), guard = (float)(g.extent * 1.e-5);
-    const float cellF = (float)g.cell, cellZF = (float)g.cellZ;
-    const bool rowsSorted = g.unsorted == 0u;
-    ChunkCursor cur;
-    uint32_t stagePhase = 0;
-    if (tid == 0) {
-        mbarInit(&stageBar, 1);
+/// What a thread knows about its target and its unit.
+struct UnitLane {
+    int k, cy;          // double row
+    uint32_t t;         // sorted index of the target
+    uint32_t slot;      // particle slot of the target (0xffffffff for ghosts / idle lanes)
+    bool live, upper, target;
+    float fx, fy, fz;   // grid-relative FP32 position
+    float lim2;         // squared FP32 filter radius
+};
+
+/// Decodes unit `unit` for thread `tid`, publishes the unit's 18 candidate row ranges and the first chunk (thread 0).
+/// Returns false (for the whole CTA) if the unit has no owned target. Contains one CTA-wide barrier.
+__device__ __forceinline__ bool beginUnit(const DevicePointers& d, const GridDev& g, uint32_t unit, int tid, float Rhalf, float slack,
+    uint32_t* sRowBeg, uint32_t* sRowEnd, ChunkCursor& cur, ChunkState& cs0, UnitLane& u) {
+    const uint4 desc = d.unitDesc[unit];
+    const uint4 aux = d.unitAux[unit];
+    if (aux.z == 0u) {
+        return false; // a unit made of ghost particles only (halo band of a decomposed run)
     }
-    __syncthreads();
-
-    for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
-        const uint4 desc = d.unitDesc[unit];
-        const uint32_t dr = desc.x, skip = desc.z, nLive = desc.w >> 8;
-        const int cA = (int)desc.y, span = (int)(desc.w & 0xffu), cB = cA + span;
-        const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
-        const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
-        const bool hasU = 2 * k + 1 < dimz;
-        const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
-        const int x0 = max(cA - 1, 0), x1 = min(cB + 1, dimx - 1);
-
-        // ---- sorted ranges of the unit's cell columns (targets) and of its 18 candidate rows ----
-        if (tid <= span + 1) {
-            sColL[tid] = d.cellStart[rbL + cA + tid];
-            sColU[tid] = hasU ? d.cellStart[rbU + cA + tid] : 0u;
+    const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
+    const uint32_t dr = desc.x, nLive = desc.w >> 8;
+    const int cA = (int)desc.y, cB = cA + (int)(desc.w & 0xffu);
+    u.cy = (int)(dr % (uint32_t)dimy);
+    u.k = (int)(dr / (uint32_t)dimy);
+    const int x0 = max(cA - 1, 0), x1 = min(cB + 1, dimx - 1);
+    // lane order prepared by k_unit_prep: sorted index | upper row << 31 | ghost << 30
+    u.live = (uint32_t)tid < nLive;
+    const uint32_t word = u.live ? d.unitLane[aux.x + tid] : 0xffffffffu;
+    u.t = u.live ? (word & 0x3fffffffu) : 0u;
+    u.upper = u.live && (word >> 31) != 0u;
+    u.target = u.live && (word & 0x40000000u) == 0u; // ghosts are neighbours only
+    u.slot = u.target ? d.order[u.t] : 0xffffffffu;
+    u.fx = u.fy = u.fz = 0.f;
+    u.lim2 = 0.f;
+    if (u.live) {
+        const float4 pf = d.posF[u.t];
+        u.fx = pf.x;
+        u.fy = pf.y;
+        u.fz = pf.z;
+        // >= R * hbar + the rounding of the FP32 coordinates, for every candidate of the unit
+        const float lim = fmaf(Rhalf, pf.w * (1.f + 1.e-6f) + __uint_as_float(aux.y), slack);
+        u.lim2 = lim * lim;
+    }
+    __syncthreads(); // everyone has left the previous unit's loop
+    if (tid < 3 * CHUNK_ROWS) { // global sorted ranges of the unit's 18 candidate rows
+        const int z = chunkLayer(tid / CHUNK_ROWS, tid % CHUNK_ROWS, u.k), y = u.cy + (tid % 3) - 1;
+        uint32_t rb = 0, re = 0;
+        if (z >= 0 && z < dimz && y >= 0 && y < dimy) {
+            const uint32_t base = (uint32_t)((z * dimy + y) * dimx);
+            rb = d.cellStart[base + x0];
+            re = d.cellStart[base + x1 + 1];
         }
-        if (tid == 0) {
-            sHmax = 0u;
-        }
-        if (tid >= 32 && tid < 32 + 3 * CHUNK_ROWS) {
-            const int row = tid - 32;
-            const int z = chunkLayer(row / CHUNK_ROWS, row % CHUNK_ROWS, k), y = cy + (row % 3) - 1;
-            uint32_t rb = 0, re = 0;
-            if (z >= 0 && z < dimz && y >= 0 && y < dimy) {
-                const uint32_t base = (uint32_t)((z * dimy + y) * dimx);
-                rb = d.cellStart[base + x0];
-                re = d.cellStart[base + x1 + 1];
-            }
-            sRowBeg[row] = rb;
-            sRowEnd[row] = re;
-        }
-        __syncthreads();
-        // ---- lane assignment: the unit's targets in column order (lower cell, then upper cell of every column), then
-        // ordered by z so that the lanes of a warp see similar numbers of neighbours in every chunk (balanced private
-        // lists => full lanes in phase 2)
-        {
-            uint32_t tIdx = 0u; // sorted index of target `tid` of the unit, bit 31 = upper row
-            if ((uint32_t)tid < nLive) {
-                uint32_t pos = skip + (uint32_t)tid;
-                for (int c = 0; c <= span; ++c) {
-                    const uint32_t nl = sColL[c + 1] - sColL[c], nu = sColU[c + 1] - sColU[c];
-                    if (pos < nl) {
-                        tIdx = sColL[c] + pos;
-                        break;
-                    }
-                    pos -= nl;
-                    if (pos < nu) {
-                        tIdx = (sColU[c] + pos) | 0x80000000u;
-                        break;
-                    }
-                    pos -= nu;
-                }
-            }
-            sTarget[tid] = tIdx;
-            sKey[tid] = ((uint32_t)tid < nLive) ? d.posF[tIdx & 0x7fffffffu].z : 3.0e38f;
-        }
-        __syncthreads();
-        {
-            const float key = sKey[tid];
-            int rank = 0;
-            for (int j = 0; j < TILE_T; ++j) {
-                const float kj = sKey[j];
-                rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
-            }
-            sPerm[rank] = (uint16_t)tid;
-            // largest h among the unit's candidates (cells x0..x1 of the 18 rows): bound of the FP32 filter radius
-            uint32_t hm = 0u;
-            for (int e = tid; e < 3 * CHUNK_ROWS * (TILE_X + 2); e += TILE_T) {
-                const int row = e / (TILE_X + 2), c = x0 + e % (TILE_X + 2);
-                const int z = chunkLayer(row / CHUNK_ROWS, row % CHUNK_ROWS, k), y = cy + (row % 3) - 1;
-                if (c <= x1 && z >= 0 && z < dimz && y >= 0 && y < dimy) {
-                    hm = max(hm, d.cellHmax[(uint32_t)((z * dimy + y) * dimx) + c]); // bit patterns of floats >= 0 order like the values
-                }
-            }
-            hm = __reduce_max_sync(0xffffffffu, hm);
-            if ((tid & 31) == 0) {
-                atomicMax(&sHmax, hm);
-            }
-        }
-        __syncthreads();
-        const bool live = (uint32_t)tid < nLive; // the idle lanes sort last (key 3e38)
-        const uint32_t tOwn = sTarget[sPerm[tid]];
-        const uint32_t t = live ? (tOwn & 0x7fffffffu) : 0u;
-        const bool upper = live && (tOwn >> 31) != 0u;
-        const uint32_t slot = live ? d.order[t] : 0xffffffffu;
-        const bool target = live && slot < nOwned; // ghosts are neighbours only
-        if (!__syncthreads_or(target ? 1 : 0)) {
-            continue; // a unit made of ghost particles only (halo band of a decomposed run)
-        }
-
-        Particle pi;
-        float fxi = 0.f, fyi = 0.f, fzi = 0.f;
-        float lim = 0.f;
-        if (live) {
-            loadRecord<SOLID>(d.rec + (size_t)t * L::G, pi);
-            const float4 pf = d.posF[t];
-            fxi = pf.x;
-            fyi = pf.y;
-            fzi = pf.z;
-            // >= R * hbar + the rounding of the FP32 coordinates, for every candidate of the unit
-            lim = fmaf(Rhalf, pf.w * (1.f + 1.e-6f) + __uint_as_float(sHmax), slack);
-        } else {
-            pi.x = pi.y = pi.z = 0.;
-            pi.h = 1.;
-        }
-        const float lim2 = lim * lim;
-        Accum acc;
-        accumZero(acc);
-
+        sRowBeg[tid] = rb;
+        sRowEnd[tid] = re;
+    }
+    if (tid < 32) {
+        __syncwarp();
         if (tid == 0) {
             cur.chunk = 0;
             cur.row = 0;
             cur.posValid = 0;
-            nextChunk(sRowBeg, sRowEnd, cur, csBuf[0]);
+            nextChunk(sRowBeg, sRowEnd, cur, cs0);
         }
-        int buf = 0;
-        while (true) {
-            __syncthreads(); // chunk descriptor published; everyone is done with the previous chunk's shared memory
-            const ChunkState& cs = csBuf[buf];
-            if (cs.used == 0) {
-                break;
-            }
-            // ---- stage the chunk: TMA bulk copies of the FP64 records and of the FP32 positions, one pair per row ----
-            if (tid == 0) {
-                fenceProxyAsync(); // the buffers were last read through the generic proxy
-                mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8 + 16));
-#pragma unroll
-                for (int r = 0; r < CHUNK_ROWS; ++r) {
-                    const uint32_t n = cs.end[r] - cs.beg[r];
-                    if (n > 0) {
-                        bulkCopyG2S(recS + (size_t)cs.base[r] * L::S, d.rec + (size_t)cs.beg[r] * L::G, n * (uint32_t)(L::G * 8), &stageBar);
-                        bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
+    }
+    return true;
+}
+
+struct ScanGeometry {
+    float cellF, cellZF, guard;
+    bool rowsSorted;
+};
+
+struct ScanState { // where a lane stands in the candidate rows of the staged chunk
+    int r;
+    uint32_t kpos, khi;
+    bool open;
+};
+
+/// Phase 1: scans the candidate rows of the staged chunk from `st` on, appending the shared-memory index of every
+/// candidate within the FP32 filter radius to the lane's list (u16 at listOwn + n * LIST_STRIDE), until the chunk is
+/// exhausted (st.r == CHUNK_ROWS) or the list is (nearly) full. Returns the list cursor.
+__device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLane& u, const ScanGeometry& sg, const float4* f4,
+    uint32_t listOwn, ScanState& st) {
+    uint32_t lp = listOwn;
+    const float fxi = u.fx, fyi = u.fy, fzi = u.fz, lim2 = u.lim2;
+    while (st.r < CHUNK_ROWS) {
+        if (!st.open) {
+            const int r = st.r;
+            const uint32_t len = cs.end[r] - cs.beg[r];
+            st.kpos = st.khi = 0;
+            if (len > 0) {
+                // y- and z-intervals of this candidate row (FP32 relative to the grid origin, with a guard band: cells
+                // were assigned in FP64) and the x-window [xlo, xhi] the target can reach in it
+                const int zabs = chunkLayer(cs.chunk, r, u.k), yabs = u.cy + (r % 3) - 1;
+                const float yl = (float)yabs * sg.cellF, zl = (float)zabs * sg.cellZF;
+                const float dyMin = fmaxf(fmaxf(yl - fyi, fyi - (yl + sg.cellF)) - sg.guard, 0.f);
+                const float dzMin = fmaxf(fmaxf(zl - fzi, fzi - (zl + sg.cellZF)) - sg.guard, 0.f);
+                const float rem = lim2 - dyMin * dyMin - dzMin * dzMin;
+                if (rem > 0.f) {
+                    const float ext = sqrtf(rem) * (1.f + 1.e-5f) + sg.guard;
+                    const float xlo = fxi - ext, xhi = fxi + ext;
+                    const uint32_t pieceBase = cs.base[r];
+                    uint32_t pl = 0, ph = len;
+                    if (sg.rowsSorted) {
+                        // bisection for both ends at once (cell rows are sorted by x): pl = #{x < xlo}, ph = #{x <= xhi}
+                        const float* fx = reinterpret_cast<const float*>(f4 + pieceBase);
+                        ph = 0;
+                        for (uint32_t step = 1u << (31 - __clz(len)); step > 0; step >>= 1) {
+                            const uint32_t tl = pl + step, th = ph + step;
+                            const float vl = fx[4 * (min(tl, len) - 1)], vh = fx[4 * (min(th, len) - 1)];
+                            pl = (tl <= len && vl < xlo) ? tl : pl;
+                            ph = (th <= len && vh <= xhi) ? th : ph;
+                        }
+                    }
+                    if (ph > pl) {
+                        st.kpos = pieceBase + pl;
+                        st.khi = pieceBase + ph;
                     }
                 }
-                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
             }
-            mbarWait(&stageBar, stagePhase);
-            stagePhase ^= 1;
-            buf ^= 1;
-            if (!target) {
-                continue;
-            }
-            // ---- private rounds: phase 1 (FP32 filter -> list), phase 2 (FP64 pairs) ----
-            const int chunk = cs.chunk;
-            // the target's own record, if it is staged in this chunk (centre chunk, own layer, dy = 0)
-            const int selfRow = upper ? 4 : 1;
-            const double* self = recS + ((chunk == 2 && t >= cs.beg[selfRow] && t < cs.end[selfRow])
-                                                ? (size_t)(cs.base[selfRow] + (t - cs.beg[selfRow])) * L::S
-                                                : (size_t)TILE_C * L::S);
-            const uint32_t listOwn = smemAddr(list + tid); // byte address of this lane's first list slot
-            constexpr uint32_t LIST_STRIDE = TILE_T * 2u;
-            int r = 0;
-            uint32_t kpos = 0, khi = 0;
-            bool open = false;
-            while (r < CHUNK_ROWS) {
-                uint32_t lp = listOwn;
-                while (r < CHUNK_ROWS) {
-                    if (!open) {
-                        const uint32_t b = cs.beg[r], len = cs.end[r] - b;
-                        kpos = khi = 0;
-                        if (len > 0) {
-                            // y- and z-intervals of this candidate row (FP32 relative to the grid origin, with a guard band:
-                            // cells were assigned in FP64) and the x-window [xlo, xhi] the target can reach in it
-                            const int zabs = chunkLayer(chunk, r, k), yabs = cy + (r % 3) - 1;
-                            const float yl = (float)yabs * cellF, zl = (float)zabs * cellZF;
-                            const float dyMin = fmaxf(fmaxf(yl - fyi, fyi - (yl + cellF)) - guard, 0.f);
-                            const float dzMin = fmaxf(fmaxf(zl - fzi, fzi - (zl + cellZF)) - guard, 0.f);
-                            const float rem = lim2 - dyMin * dyMin - dzMin * dzMin;
-                            const float ext = sqrtf(fmaxf(rem, 0.f)) * (1.f + 1.e-5f) + guard;
-                            const float xlo = rem > 0.f ? fxi - ext : 3.0e38f, xhi = rem > 0.f ? fxi + ext : -3.0e38f;
-                            const uint32_t pieceBase = cs.base[r];
-                            uint32_t pl = 0, ph = len;
-                            if (rowsSorted) {
-                                // bisection for both ends at once: pl = #{x < xlo}, ph = #{x <= xhi}; the trip count depends on
-                                // the row only, so the warp stays converged
-                                const float* fx = reinterpret_cast<const float*>(f4 + pieceBase);
-                                ph = 0;
-                                for (uint32_t step = 1u << (31 - __clz(len)); step > 0; step >>= 1) {
-                                    const uint32_t tl = pl + step, th = ph + step;
-                                    const float vl = fx[4 * (min(tl, len) - 1)], vh = fx[4 * (min(th, len) - 1)];
-                                    pl = (tl <= len && vl < xlo) ? tl : pl;
-                                    ph = (th <= len && vh <= xhi) ? th : ph;
-                                }
-                            } else if (!(rem > 0.f)) {
-                                ph = 0;
-                            }
-                            if (ph > pl) {
-                                kpos = pieceBase + pl;
-                                khi = pieceBase + ph;
-                            }
-                        }
-                        open = true;
-                    }
-                    // eight candidates per trip: the loads are independent, only the list append is serial. The target
-                    // itself is not excluded here (~300 compares) but masked in phase 2 (~70 compares).
-                    {
+            st.open = true;
+        }
+        // eight candidates per trip: the loads are independent, only the list append is serial. The target itself is
+        // not excluded here (~300 compares) but masked in phase 2 (~70 compares).
+        uint32_t kpos = st.kpos;
+        const uint32_t khi = st.khi;
 #define SPH_F32_TEST(C, K)                                                                                            \
     {                                                                                                                 \
         const float ddx = fxi - C.x, ddy = fyi - C.y, ddz = fzi - C.z;                                                \
@@ -446,73 +450,355 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             lp += LIST_STRIDE;                                                                                        \
         }                                                                                                             \
     }
-                        const uint32_t lpMax8 = listOwn + (LIST_CAP - 8) * LIST_STRIDE;
-                        const uint32_t lpMax4 = listOwn + (LIST_CAP - 4) * LIST_STRIDE;
-                        while (kpos + 8 <= khi && lp <= lpMax8) {
-                            const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
-                            const float4 ce = f4[kpos + 4], cf = f4[kpos + 5], cg = f4[kpos + 6], ch = f4[kpos + 7];
-                            SPH_F32_TEST(ca, kpos)
-                            SPH_F32_TEST(cb, kpos + 1)
-                            SPH_F32_TEST(cc, kpos + 2)
-                            SPH_F32_TEST(cd, kpos + 3)
-                            SPH_F32_TEST(ce, kpos + 4)
-                            SPH_F32_TEST(cf, kpos + 5)
-                            SPH_F32_TEST(cg, kpos + 6)
-                            SPH_F32_TEST(ch, kpos + 7)
-                            kpos += 8;
-                        }
-                        while (kpos + 4 <= khi && lp <= lpMax4) {
-                            const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
-                            SPH_F32_TEST(ca, kpos)
-                            SPH_F32_TEST(cb, kpos + 1)
-                            SPH_F32_TEST(cc, kpos + 2)
-                            SPH_F32_TEST(cd, kpos + 3)
-                            kpos += 4;
-                        }
-                        while (kpos < khi && khi - kpos < 4 && lp < listOwn + LIST_CAP * LIST_STRIDE) {
-                            const float4 ca = f4[kpos];
-                            SPH_F32_TEST(ca, kpos)
-                            kpos++;
-                        }
+        const uint32_t lpMax8 = listOwn + (LIST_CAP - 8) * LIST_STRIDE;
+        const uint32_t lpMax4 = listOwn + (LIST_CAP - 4) * LIST_STRIDE;
+        while (kpos + 8 <= khi && lp <= lpMax8) {
+            const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
+            const float4 ce = f4[kpos + 4], cf = f4[kpos + 5], cg = f4[kpos + 6], ch = f4[kpos + 7];
+            SPH_F32_TEST(ca, kpos)
+            SPH_F32_TEST(cb, kpos + 1)
+            SPH_F32_TEST(cc, kpos + 2)
+            SPH_F32_TEST(cd, kpos + 3)
+            SPH_F32_TEST(ce, kpos + 4)
+            SPH_F32_TEST(cf, kpos + 5)
+            SPH_F32_TEST(cg, kpos + 6)
+            SPH_F32_TEST(ch, kpos + 7)
+            kpos += 8;
+        }
+        while (kpos + 4 <= khi && lp <= lpMax4) {
+            const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
+            SPH_F32_TEST(ca, kpos)
+            SPH_F32_TEST(cb, kpos + 1)
+            SPH_F32_TEST(cc, kpos + 2)
+            SPH_F32_TEST(cd, kpos + 3)
+            kpos += 4;
+        }
+        while (kpos < khi && khi - kpos < 4 && lp < listOwn + LIST_CAP * LIST_STRIDE) {
+            const float4 ca = f4[kpos];
+            SPH_F32_TEST(ca, kpos)
+            kpos++;
+        }
 #undef SPH_F32_TEST
-                    }
-                    if (kpos >= khi) {
-                        r++;
-                        open = false;
-                    } else {
-                        break; // list (nearly) full: drain it, then resume the scan
+        st.kpos = kpos;
+        if (kpos >= khi) {
+            st.r++;
+            st.open = false;
+        } else {
+            break; // list (nearly) full: drain it, then resume the scan
+        }
+    }
+    return lp;
+}
+
+/// Phase 2: walks the lane's list two entries at a time (so that the long per-pair chains overlap); the exact FP64
+/// predicate enters the branch-free pair body as a mask.
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__device__ __forceinline__ void sumListedPairs(const double* recS, const uint16_t* lst, int cnt, const double* self, const Particle& pi,
+    const double* lut, Accum& acc) {
+    constexpr int S = TileLayout<SOLID>::S;
+    int q = 0;
+    for (; q + 1 < cnt; q += 2) {
+        const double* rp0 = recS + (size_t)lst[q * TILE_T] * S;
+        const double* rp1 = recS + (size_t)lst[(q + 1) * TILE_T] * S;
+        Particle pj0, pj1;
+        loadRecord<SOLID>(rp0, pj0);
+        loadRecord<SOLID>(rp1, pj1);
+        const double dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
+        const double dx1 = pi.x - pj1.x, dy1 = pi.y - pj1.y, dz1 = pi.z - pj1.z;
+        double d20, hb0, d21, hb1;
+        const bool v0 = isNeighbour(dx0, dy0, dz0, pi.h, pj0.h, c_prm.kernel_radius, d20, hb0) && rp0 != self;
+        const bool v1 = isNeighbour(dx1, dy1, dz1, pi.h, pj1.h, c_prm.kernel_radius, d21, hb1) && rp1 != self;
+        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj0, dx0, dy0, dz0, d20, hb0, v0, acc);
+        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj1, dx1, dy1, dz1, d21, hb1, v1, acc);
+    }
+    if (q < cnt) {
+        const double* rp0 = recS + (size_t)lst[q * TILE_T] * S;
+        Particle pj0;
+        loadRecord<SOLID>(rp0, pj0);
+        const double dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
+        double d20, hb0;
+        const bool v0 = isNeighbour(dx0, dy0, dz0, pi.h, pj0.h, c_prm.kernel_radius, d20, hb0) && rp0 != self;
+        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj0, dx0, dy0, dz0, d20, hb0, v0, acc);
+    }
+}
+
+// ---- kernel A: candidate lists ------------------------------------------------------------------------------------
+// Phase 1 of every unit at high occupancy (26 KB of shared memory, few registers: 8 CTAs per SM): stages the FP32
+// positions of each chunk, runs the conservative filter and writes the per-lane lists of the chunk as one contiguous
+// block of the list pool, chained per unit. The pair-sum kernel then only stages records + list blocks and spends its
+// 8 warps per SM on FP64 work.
+constexpr size_t LISTS_SMEM = (size_t)TILE_C * 16 + (size_t)(LIST_CAP + 1) * LIST_ROW_BYTES;
+
+__global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint32_t maxCells, uint32_t poolRows) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float4* f4 = reinterpret_cast<float4*>(smemRaw);
+    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C); // one block: row 0 = counts + header, rows 1.. = entries
+    __shared__ ChunkState csBuf[2];
+    __shared__ __align__(8) uint64_t stageBar;
+    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
+    __shared__ uint32_t sWarp[TILE_T / 32], sOff;
+
+    const GridDev g = *d.grid;
+    const uint32_t totalUnits = d.segStart[maxCells];
+    const int tid = threadIdx.x;
+    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
+    // the FP32 coordinates are relative to the grid origin: absolute rounding error <= 2^-24 * extent per coordinate
+    const float slack = (float)(g.extent * 1.e-6);
+    const ScanGeometry sg = { (float)g.cell, (float)g.cellZ, (float)(g.extent * 1.e-5), g.unsorted == 0u };
+    ChunkCursor cur;
+    uint32_t stagePhase = 0;
+    if (tid == 0) {
+        mbarInit(&stageBar, 1);
+    }
+    __syncthreads();
+    const uint32_t listOwn = smemAddr(list + TILE_T + tid); // this lane's first entry (row 1)
+    uint4* pool = reinterpret_cast<uint4*>(d.listPool);
+
+    for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
+        UnitLane u;
+        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], u)) {
+            if (tid == 0) {
+                d.unitList[unit] = make_uint4(LIST_END, 0u, 0u, 0u);
+            }
+            continue;
+        }
+        // thread 0 chains the blocks of the unit
+        uint32_t prevOff = LIST_END, firstOff = LIST_END, firstRows = 0, firstOrd = 0;
+        bool failed = false;
+        uint32_t ordinal = 0;
+        int buf = 0;
+        while (true) {
+            __syncthreads(); // chunk descriptor published; everyone is done with the previous chunk's shared memory
+            const ChunkState& cs = csBuf[buf];
+            if (cs.used == 0) {
+                break;
+            }
+            if (tid == 0) {
+                fenceProxyAsync(); // the buffer was last read through the generic proxy
+                mbarExpectTx(&stageBar, cs.used * 16u);
+#pragma unroll
+                for (int r = 0; r < CHUNK_ROWS; ++r) {
+                    const uint32_t n = cs.end[r] - cs.beg[r];
+                    if (n > 0) {
+                        bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
                     }
                 }
-                const int cnt = (int)((lp - listOwn) / LIST_STRIDE);
-                // phase 2: two list entries per trip so the long per-pair chains overlap
-                int q = 0;
-                for (; q + 1 < cnt; q += 2) {
-                    const double* rp0 = recS + (size_t)list[q * TILE_T + tid] * L::S;
-                    const double* rp1 = recS + (size_t)list[(q + 1) * TILE_T + tid] * L::S;
-                    Particle pj0, pj1;
-                    loadRecord<SOLID>(rp0, pj0);
-                    loadRecord<SOLID>(rp1, pj1);
-                    const double dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
-                    const double dx1 = pi.x - pj1.x, dy1 = pi.y - pj1.y, dz1 = pi.z - pj1.z;
-                    double d20, hb0, d21, hb1;
-                    const bool v0 = isNeighbour(dx0, dy0, dz0, pi.h, pj0.h, c_prm.kernel_radius, d20, hb0) && rp0 != self;
-                    const bool v1 = isNeighbour(dx1, dy1, dz1, pi.h, pj1.h, c_prm.kernel_radius, d21, hb1) && rp1 != self;
-                    pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj0, dx0, dy0, dz0, d20, hb0, v0, acc);
-                    pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj1, dx1, dy1, dz1, d21, hb1, v1, acc);
+                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
+            }
+            mbarWait(&stageBar, stagePhase);
+            stagePhase ^= 1;
+            buf ^= 1;
+            ScanState st = { u.target ? 0 : CHUNK_ROWS, 0u, 0u, false };
+            while (true) { // rounds: one block per round (a second round only if some lane's list overflowed)
+                const uint32_t lp = scanRows(cs, u, sg, f4, listOwn, st);
+                const uint32_t cnt = (lp - listOwn) / LIST_STRIDE;
+                reinterpret_cast<unsigned char*>(list)[tid] = (unsigned char)cnt;
+                const uint32_t wmax = __reduce_max_sync(0xffffffffu, cnt);
+                const bool wmore = __any_sync(0xffffffffu, st.r < CHUNK_ROWS);
+                if ((tid & 31) == 0) {
+                    sWarp[tid >> 5] = wmax | (wmore ? 0x100u : 0u);
                 }
-                if (q < cnt) {
-                    const double* rp0 = recS + (size_t)list[q * TILE_T + tid] * L::S;
-                    Particle pj0;
-                    loadRecord<SOLID>(rp0, pj0);
-                    const double dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
-                    double d20, hb0;
-                    const bool v0 = isNeighbour(dx0, dy0, dz0, pi.h, pj0.h, c_prm.kernel_radius, d20, hb0) && rp0 != self;
-                    pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj0, dx0, dy0, dz0, d20, hb0, v0, acc);
+                __syncthreads(); // lists, counts and the warp summaries are complete
+                uint32_t rows = 0;
+                bool anyMore = false;
+#pragma unroll
+                for (int w = 0; w < TILE_T / 32; ++w) {
+                    rows = max(rows, sWarp[w] & 0xffu);
+                    anyMore = anyMore || (sWarp[w] & 0x100u) != 0u;
+                }
+                if (rows > 0) {
+                    if (tid == 0) {
+                        uint32_t off = LIST_FALLBACK;
+                        if (!failed) {
+                            off = atomicAdd(d.listCursor, rows + 1u);
+                            if (off > poolRows || rows + 1u > poolRows - off) {
+                                failed = true;
+                                off = LIST_FALLBACK;
+                            }
+                        }
+                        uint32_t* hdr = reinterpret_cast<uint32_t*>(list) + TILE_T / 4; // byte 128 of row 0
+                        hdr[0] = LIST_END;
+                        hdr[1] = 0u;
+                        hdr[2] = 0u;
+                        hdr[3] = 0u;
+                        sOff = off;
+                    }
+                    __syncthreads();
+                    const uint32_t off = sOff;
+                    if (off != LIST_FALLBACK) {
+                        const uint4* src = reinterpret_cast<const uint4*>(list);
+                        uint4* dst = pool + (size_t)off * (LIST_ROW_BYTES / 16);
+                        for (uint32_t w = tid; w < (rows + 1u) * (LIST_ROW_BYTES / 16); w += TILE_T) {
+                            dst[w] = src[w];
+                        }
+                        if (tid == 0) {
+                            if (prevOff == LIST_END) {
+                                firstOff = off;
+                                firstRows = rows;
+                                firstOrd = ordinal;
+                            } else { // patch the header of the previous block (its copy finished before the last barrier)
+                                uint32_t* ph = reinterpret_cast<uint32_t*>(pool + (size_t)prevOff * (LIST_ROW_BYTES / 16)) + TILE_T / 4;
+                                ph[0] = off;
+                                ph[1] = rows;
+                                ph[2] = ordinal;
+                            }
+                            prevOff = off;
+                        }
+                    }
+                }
+                if (!anyMore) {
+                    break;
+                }
+                __syncthreads(); // the block has been copied out: the lanes may overwrite the list
+            }
+            ordinal++;
+        }
+        if (tid == 0) {
+            if (failed) {
+                atomicAdd(&d.stats->fallbackUnits, 1u);
+                d.unitList[unit] = make_uint4(LIST_FALLBACK, 0u, 0u, 0u);
+            } else {
+                d.unitList[unit] = make_uint4(firstOff, firstRows, firstOrd, 0u);
+            }
+        }
+    }
+}
+
+// ---- kernel B: pair sums ---------------------------------------------------------------------------------------------
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint32_t nOwned, uint32_t maxCells, bool useLists) {
+    using L = TileLayout<SOLID>;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    double* recS = reinterpret_cast<double*>(smemRaw);
+    float4* f4 = reinterpret_cast<float4*>(recS + (size_t)TILE_C * L::S);
+    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C); // row 0 = counts + header (list mode), rows 1.. = entries
+    __shared__ ChunkState csBuf[2];
+    __shared__ __align__(8) uint64_t stageBar;
+    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
+
+    const GridDev g = *d.grid;
+    const uint32_t totalUnits = d.segStart[maxCells];
+    const int tid = threadIdx.x;
+    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
+    const float slack = (float)(g.extent * 1.e-6);
+    const ScanGeometry sg = { (float)g.cell, (float)g.cellZ, (float)(g.extent * 1.e-5), g.unsorted == 0u };
+    ChunkCursor cur;
+    uint32_t stagePhase = 0;
+    if (tid == 0) {
+        mbarInit(&stageBar, 1);
+    }
+    __syncthreads();
+    const uint16_t* const lst = list + TILE_T + tid; // this lane's first entry
+    const unsigned char* pool = reinterpret_cast<const unsigned char*>(d.listPool);
+    (void)nOwned;
+
+    for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
+        UnitLane u;
+        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], u)) {
+            continue;
+        }
+        Particle pi;
+        if (u.live) {
+            loadRecord<SOLID>(d.rec + (size_t)u.t * L::G, pi);
+        } else {
+            pi.x = pi.y = pi.z = 0.;
+            pi.h = 1.;
+        }
+        Accum acc;
+        accumZero(acc);
+        const int selfRow = u.upper ? 4 : 1; // the target's own record sits in the centre chunk, own layer, dy = 0
+        auto selfPointer = [&](const ChunkState& cs) {
+            return recS + ((cs.chunk == 2 && u.t >= cs.beg[selfRow] && u.t < cs.end[selfRow])
+                                  ? (size_t)(cs.base[selfRow] + (u.t - cs.beg[selfRow])) * L::S
+                                  : (size_t)TILE_C * L::S);
+        };
+        const uint4 ul = useLists ? d.unitList[unit] : make_uint4(LIST_FALLBACK, 0u, 0u, 0u);
+
+        if (ul.x != LIST_FALLBACK) {
+            // ---- list mode: the blocks written by k_pair_lists drive the loop ----
+            uint32_t off = ul.x, rows = ul.y, ord = ul.z;
+            uint32_t staged = 0xffffffffu; // ordinal of the chunk whose records are in shared memory
+            uint32_t have = 0;             // ordinal of the chunk described by csBuf[0] (thread 0 advances it)
+            while (off != LIST_END) {
+                __syncthreads(); // everyone is done with the previous block (list and records)
+                const bool newChunk = ord != staged;
+                if (tid == 0) {
+                    fenceProxyAsync(); // the buffers were last read through the generic proxy
+                    uint32_t bytes = (rows + 1u) * LIST_ROW_BYTES;
+                    if (newChunk) {
+                        while (have < ord) {
+                            nextChunk(sRowBeg, sRowEnd, cur, csBuf[0]);
+                            have++;
+                        }
+                        bytes += csBuf[0].used * (uint32_t)(L::G * 8);
+                    }
+                    mbarExpectTx(&stageBar, bytes);
+                    if (newChunk) {
+#pragma unroll
+                        for (int r = 0; r < CHUNK_ROWS; ++r) {
+                            const uint32_t n = csBuf[0].end[r] - csBuf[0].beg[r];
+                            if (n > 0) {
+                                bulkCopyG2S(recS + (size_t)csBuf[0].base[r] * L::S, d.rec + (size_t)csBuf[0].beg[r] * L::G,
+                                    n * (uint32_t)(L::G * 8), &stageBar);
+                            }
+                        }
+                    }
+                    bulkCopyG2S(list, pool + (size_t)off * LIST_ROW_BYTES, (rows + 1u) * LIST_ROW_BYTES, &stageBar);
+                }
+                staged = ord;
+                mbarWait(&stageBar, stagePhase);
+                stagePhase ^= 1;
+                const uint32_t* hdr = reinterpret_cast<const uint32_t*>(list) + TILE_T / 4;
+                off = hdr[0];
+                rows = hdr[1];
+                ord = hdr[2];
+                if (u.target) {
+                    const int cnt = reinterpret_cast<const unsigned char*>(list)[tid];
+                    sumListedPairs<SOLID, CORRECTED, FILTER>(recS, lst, cnt, selfPointer(csBuf[0]), pi, d.lut, acc);
+                }
+            }
+        } else {
+            // ---- fused mode: phase 1 in this kernel (list pool exhausted, or lists switched off) ----
+            const uint32_t listOwn = smemAddr(lst);
+            int buf = 0;
+            while (true) {
+                __syncthreads(); // chunk descriptor published; everyone is done with the previous chunk's shared memory
+                const ChunkState& cs = csBuf[buf];
+                if (cs.used == 0) {
+                    break;
+                }
+                // stage the chunk: TMA bulk copies of the FP64 records and of the FP32 positions, one pair per row
+                if (tid == 0) {
+                    fenceProxyAsync(); // the buffers were last read through the generic proxy
+                    mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8 + 16));
+#pragma unroll
+                    for (int r = 0; r < CHUNK_ROWS; ++r) {
+                        const uint32_t n = cs.end[r] - cs.beg[r];
+                        if (n > 0) {
+                            bulkCopyG2S(recS + (size_t)cs.base[r] * L::S, d.rec + (size_t)cs.beg[r] * L::G, n * (uint32_t)(L::G * 8), &stageBar);
+                            bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
+                        }
+                    }
+                    nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
+                }
+                mbarWait(&stageBar, stagePhase);
+                stagePhase ^= 1;
+                buf ^= 1;
+                if (!u.target) {
+                    continue;
+                }
+                const double* self = selfPointer(cs);
+                ScanState st = { 0, 0u, 0u, false };
+                while (st.r < CHUNK_ROWS) { // private rounds: phase 1 (FP32 filter -> list), phase 2 (FP64 pairs)
+                    const uint32_t lp = scanRows(cs, u, sg, f4, listOwn, st);
+                    const int cnt = (int)((lp - listOwn) / LIST_STRIDE);
+                    sumListedPairs<SOLID, CORRECTED, FILTER>(recS, lst, cnt, self, pi, d.lut, acc);
                 }
             }
         }
         // ---- epilogue: finalizers + stores (shared with the direct variant) ----
-        if (target) {
+        if (u.target) {
+            const uint32_t slot = u.slot;
             const MaterialDev& mat = c_mats[d.u[U_MATID][slot]];
             double S[5] = { 0., 0., 0., 0., 0. };
             if (SOLID) {
@@ -524,7 +810,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][slot], pi.cs, SOLID ? d.f[F_REDUCE][slot] : 1., S, out);
             storeDerivs<SOLID, CORRECTED>(d, slot, out);
         }
-        neighbourStats(d, acc.cnt, target);
+        neighbourStats(d, acc.cnt, u.target);
     }
 }
 
@@ -536,13 +822,34 @@ int launchSegments(sphgpu_ctx* ctx) {
     k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks);
     k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.segStart, ctx->d.scanBlock, total);
     k_units<true><<<(ctx->maxCells + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
-    ctx->launches += 5;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const uint32_t upper = ctx->nActive / (TILE_T / 2) + ctx->maxCells + 1; // >= number of units
+    k_unit_prep<<<(uint32_t)std::min<uint64_t>((uint64_t)sms * 16, upper), TILE_T, 0, st>>>(ctx->d, ctx->n, ctx->maxCells);
+    ctx->launches += 6;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+static int launchLists(sphgpu_ctx* ctx) {
+    static bool configured = false;
+    if (!configured) {
+        SPH_CUDA_CHECK(cudaFuncSetAttribute(k_pair_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LISTS_SMEM));
+        configured = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const uint32_t upper = ctx->nActive / (TILE_T / 2) + ctx->maxCells + 1; // >= number of units
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8 * 4, std::max<uint32_t>(upper, 1u));
+    SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.listCursor, 0, sizeof(uint32_t), ctx->stream));
+    k_pair_lists<<<grid, TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, ctx->poolRows);
+    ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
-static int launchTiledVariant(sphgpu_ctx* ctx) {
+static int launchTiledVariant(sphgpu_ctx* ctx, bool useLists) {
     auto kernel = k_pair_tiled<SOLID, CORRECTED, FILTER>;
     static bool configured = false; // per instantiation; the attribute is per device function
     const size_t smem = TileLayout<SOLID>::bytes;
@@ -554,24 +861,29 @@ static int launchTiledVariant(sphgpu_ctx* ctx) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const uint32_t upper = ctx->nActive / (TILE_T / 2) + ctx->maxCells + 1; // >= number of units
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sms * 2 * 8, std::max<uint32_t>(upper, 1u));
-    kernel<<<grid, TILE_T, smem, ctx->stream>>>(ctx->d, ctx->n, ctx->maxCells);
+    kernel<<<grid, TILE_T, smem, ctx->stream>>>(ctx->d, ctx->n, ctx->maxCells, useLists);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
 
+/// variant 0: candidate lists in their own kernel (k_pair_lists) + pair sums; variant 2: both phases fused in the pair kernel.
 int launchPairTiled(sphgpu_ctx* ctx) {
     int rc = launchSegments(ctx);
     if (rc != SPHGPU_OK) {
         return rc;
     }
+    const bool useLists = ctx->variant != 2;
+    if (useLists && (rc = launchLists(ctx)) != SPHGPU_OK) {
+        return rc;
+    }
     if (!ctx->solid) {
-        return launchTiledVariant<false, false, false>(ctx);
+        return launchTiledVariant<false, false, false>(ctx, useLists);
     }
     if (ctx->corrected) {
-        return ctx->filter ? launchTiledVariant<true, true, true>(ctx) : launchTiledVariant<true, true, false>(ctx);
+        return ctx->filter ? launchTiledVariant<true, true, true>(ctx, useLists) : launchTiledVariant<true, true, false>(ctx, useLists);
     }
-    return ctx->filter ? launchTiledVariant<true, false, true>(ctx) : launchTiledVariant<true, false, false>(ctx);
+    return ctx->filter ? launchTiledVariant<true, false, true>(ctx, useLists) : launchTiledVariant<true, false, false>(ctx, useLists);
 }
 
 } // namespace sph

@@ -57,6 +57,7 @@ struct GridDev {
 struct StatsDev {
     unsigned int neighMin, neighMax;
     unsigned long long pairCount;
+    unsigned int fallbackUnits, pad; // units whose candidate lists did not fit the list pool (handled by the fused path)
 };
 
 struct TimestepDev {
@@ -77,7 +78,12 @@ struct DevicePointers {
     uint32_t* cellCount; // [maxCells + 1]
     uint32_t* scanBlock; // block sums of the scan
     uint32_t* segStart;  // [maxCells + 1] exclusive prefix of the number of work units per double row
-    uint4* unitDesc;     // [maxSegs] work units of the tiled pair kernel: {double row, cA, skip, cB}
+    uint4* unitDesc;     // [maxSegs] work units of the tiled pair kernel: {double row, cA, skip, (cB - cA) | targets << 8}
+    uint4* unitAux;      // [maxSegs] {first entry in unitLane, bits of the largest candidate h, any owned target, -}
+    uint4* unitList;     // [maxSegs] {row offset of the unit's first list block, its rows, its chunk ordinal, -}
+    unsigned char* listPool; // candidate lists written by k_pair_lists, blocks of 256-byte rows
+    uint32_t* listCursor;    // bump allocator of the pool (rows)
+    uint32_t* unitLane;  // [capacity] lane order of every unit: sorted index | upper row << 31 | ghost << 30
     double* boundsPartial; // [BOUNDS_BLOCKS * 8]
     const double* lut;
     GridDev* grid;
@@ -92,7 +98,7 @@ constexpr int SCAN_ITEMS = 4096;     // items per scan block
 
 struct sphgpu_ctx {
     int device = 0;
-    uint32_t n = 0, capacity = 0, nActive = 0, maxCells = 0, scanBlocks = 0, maxSegs = 0;
+    uint32_t n = 0, capacity = 0, nActive = 0, maxCells = 0, scanBlocks = 0, maxSegs = 0, poolRows = 0;
     sph::ParamsDev prm{};
     sph::MaterialDev matsHost[sph::MAX_MATERIALS];
     sphgpu_material matsApi[sph::MAX_MATERIALS];

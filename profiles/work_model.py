@@ -157,6 +157,13 @@ def model(n_target, lane_mode="z4", p1_mode="cells", pack="nextfit", tile_c=576)
                                 ln = np.where((rem > 0) & (c0 <= c1), start[base + np.clip(c1, 0, dim[0] - 1) + 1] - start[base + np.clip(c0, 0, dim[0] - 1)], 0)
                                 ln = np.maximum(ln, 0)
                                 ctest, crow = C_TEST_OLD, C_ROW
+                            elif p1_mode.startswith("fine"):  # x-windows at the granularity of cells a / XSUB wide
+                                xs = a / int(p1_mode[4:])
+                                f0 = np.floor((P[:, 0] - ext - lo[0]) / xs)
+                                f1 = np.floor((P[:, 0] + ext - lo[0]) / xs)
+                                cf = np.floor((C[:, 0] - lo[0]) / xs)
+                                ln = np.where(rem > 0, ((cf[None, :] >= f0[:, None]) & (cf[None, :] <= f1[:, None])).sum(1), 0)
+                                ctest, crow = C_TEST_NEW, C_ROW
                             elif p1_mode == "exact":
                                 ln = np.where(rem > 0, (np.abs(P[:, None, 0] - C[None, :, 0]) <= ext[:, None]).sum(1), 0)
                                 ctest, crow = C_TEST_NEW, C_ROW + C_SEARCH

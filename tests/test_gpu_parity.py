@@ -45,7 +45,7 @@ def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=T
             assert_close(k, got[k], ref[k], tol, FLOOR)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
 def test_integrate_matches_golden(name, variant, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
@@ -125,7 +125,7 @@ def test_variants_agree_on_seeded_random_input(lut):
     setup = abi.setup_from_snapshot(i, lut)
     orc = OraclePort(snap, setup)
     orc.integrate()
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         eng, stats = gpu_integrate(snap, setup, variant)
         check_against(eng, stats, orc.a)
         eng.close()
