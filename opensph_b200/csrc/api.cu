@@ -208,7 +208,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     SPH_TRY(devAlloc(&ctx->d.unitDesc, (size_t)ctx->maxSegs));
     SPH_TRY(devAlloc(&ctx->d.unitAux, (size_t)ctx->maxSegs));
     SPH_TRY(devAlloc(&ctx->d.unitLane, cap));
-    SPH_TRY(devAlloc(&ctx->d.unitList, (size_t)ctx->maxSegs));
+    SPH_TRY(devAlloc(&ctx->d.unitList, (size_t)ctx->maxSegs * 4));
     // list pool: ~0.8 rows of 256 B per particle on the eta = 1.3 lattice (68 neighbours); units that do not fit fall
     // back to building their lists inside the pair kernel
     ctx->poolRows = (uint32_t)std::min<size_t>(cap + cap / 2 + 8192, 0xfffffff0u);

@@ -80,7 +80,7 @@ struct DevicePointers {
     uint32_t* segStart;  // [maxCells + 1] exclusive prefix of the number of work units per double row
     uint4* unitDesc;     // [maxSegs] work units of the tiled pair kernel: {double row, cA, skip, (cB - cA) | targets << 8}
     uint4* unitAux;      // [maxSegs] {first entry in unitLane, bits of the largest candidate h, any owned target, -}
-    uint4* unitList;     // [maxSegs] {row offset of the unit's first list block, its rows, its chunk ordinal, -}
+    uint4* unitList;     // [4 * maxSegs] descriptor of every unit's first list block (pair_tiled.cu)
     unsigned char* listPool; // candidate lists written by k_pair_lists, blocks of 256-byte rows
     uint32_t* listCursor;    // bump allocator of the pool (rows)
     uint32_t* unitLane;  // [capacity] lane order of every unit: sorted index | upper row << 31 | ghost << 30
