@@ -26,13 +26,10 @@
 namespace sph {
 
 constexpr int TILE_T = 128;   // targets (threads) per work unit
-constexpr int TILE_C = 576;   // staged candidates per chunk of the fused kernel
+constexpr int TILE_C = 576;   // staged candidates per chunk
 constexpr int LIST_CAP = 64;  // private list entries per round
 constexpr int TILE_X = 20;    // widest unit in cells (bounds the per-unit loops over candidate cells)
-constexpr int CHUNK_ROWS = 3; // candidate rows per chunk: the three y-rows (dy = -1, 0, 1) of one z-layer
-constexpr int CHUNK_SLOTS = 6; // z-layers of a unit's neighbourhood, processed in the order of chunkLayer()
-constexpr int PIPE_C = 288;   // records per pipeline stage of the pair-sum kernel (one z-layer of a typical unit)
-constexpr int PIPE_LIST = 40; // list entries per lane and block in the list pool
+constexpr int CHUNK_ROWS = 6; // candidate rows per chunk: 2 z-layers x 3 y-rows
 
 template <bool SOLID>
 struct TileLayout {
@@ -246,30 +243,31 @@ __global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t
 struct ChunkState {
     uint32_t beg[CHUNK_ROWS], end[CHUNK_ROWS], base[CHUNK_ROWS]; // staged global range per candidate row + smem offset
     uint32_t used;
-    int chunk;                                  // layer slot 0..5, see chunkLayer()
+    int chunk;                                  // 0 far, 1 near, 2 centre
 };
 
-struct ChunkCursor { // iteration state of the chunk builder (one thread)
+struct ChunkCursor { // iteration state of the chunk builder (thread 0 only)
     int chunk, row;
     uint32_t pos;
     int posValid;
 };
 
-/// z-layer (absolute half-height cell index) of layer slot `c` for the double row k. The two outermost layers come
-/// first, the target's own layers (slots 4 and 5) last.
-__device__ __forceinline__ int chunkLayer(int c, int k) {
-    return c == 0 ? 2 * k - 2 : (c == 1 ? 2 * k + 3 : (c == 2 ? 2 * k - 1 : (c == 3 ? 2 * k + 2 : (c == 4 ? 2 * k : 2 * k + 1))));
+/// z-layer (absolute half-height cell index) of candidate row `r` (0..5) of chunk `c` for the double row k.
+__device__ __forceinline__ int chunkLayer(int c, int r, int k) {
+    const int lo = (c == 0) ? 2 * k - 2 : (c == 1 ? 2 * k - 1 : 2 * k);
+    const int hi = (c == 0) ? 2 * k + 3 : (c == 1 ? 2 * k + 2 : 2 * k + 1);
+    return r < 3 ? lo : hi;
 }
 
-/// Next chunk of the unit: as many whole / partial candidate rows of the current z-layer as fit into `capacity` records.
-/// rowBeg/rowEnd hold the global sorted ranges of the unit's 18 candidate rows (6 layers x 3 rows; empty if outside).
-__device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t* rowEnd, ChunkCursor& cur, ChunkState& cs, uint32_t capacity) {
+/// Next chunk of the unit: as many whole / partial candidate rows of the current layer pair as fit into TILE_C records.
+/// rowBeg/rowEnd hold the global sorted ranges of the unit's 18 candidate rows (3 chunks x 6 rows; empty if outside).
+__device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t* rowEnd, ChunkCursor& cur, ChunkState& cs) {
     uint32_t used = 0;
     for (int r = 0; r < CHUNK_ROWS; ++r) {
         cs.beg[r] = cs.end[r] = cs.base[r] = 0;
     }
     int chunk = 0;
-    while (cur.chunk < CHUNK_SLOTS) {
+    while (cur.chunk < 3) {
         chunk = cur.chunk;
         bool full = false;
         while (cur.row < CHUNK_ROWS) {
@@ -278,7 +276,7 @@ __device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t
                 cur.pos = rb;
                 cur.posValid = 1;
             }
-            const uint32_t take = re > cur.pos ? min(re - cur.pos, capacity - used) : 0u;
+            const uint32_t take = re > cur.pos ? min(re - cur.pos, (uint32_t)TILE_C - used) : 0u;
             if (take > 0) {
                 cs.beg[cur.row] = cur.pos;
                 cs.end[cur.row] = cur.pos + take;
@@ -297,7 +295,7 @@ __device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t
         if (full) {
             break;
         }
-        cur.chunk++; // layer finished; a chunk never mixes layers
+        cur.chunk++; // layer pair finished; a chunk never mixes layer pairs
         cur.row = 0;
         cur.posValid = 0;
         if (used > 0) {
@@ -308,16 +306,14 @@ __device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t
     cs.chunk = chunk;
 }
 
-// ---- pieces shared by the list kernel, the pair-sum kernel and the fused kernel --------------------------------------
+// ---- pieces shared by the list kernel and the pair-sum kernel ---------------------------------------------------
 constexpr uint32_t LIST_STRIDE = TILE_T * 2u;        // bytes between consecutive entries of one lane's list
-constexpr uint32_t LIST_END = 0xffffffffu;           // block descriptor: no (further) block
-constexpr uint32_t LIST_FALLBACK = 0xfffffffeu;      // unitList: the pool was exhausted, the fused kernel handles the unit
+constexpr uint32_t LIST_END = 0xffffffffu;           // unitList / block header: no (further) block
+constexpr uint32_t LIST_FALLBACK = 0xfffffffeu;      // unitList: the pool was exhausted, build the lists in the pair kernel
 constexpr uint32_t LIST_ROW_BYTES = TILE_T * 2u;     // one row of a list block: one u16 per lane
-constexpr int DESC_WORDS = 10;
-// A list block is (1 + rows) rows of 256 B. Row 0: bytes 0..127 = per-lane entry counts (u8), bytes 128..167 = the
-// DESCRIPTOR of the unit's next block (word 0 = LIST_END terminates the chain). Rows 1.. = entries, [entry][lane], each
-// the stage index of a candidate record. Descriptor words: {row offset in the pool, rows, layer slot, 0, then per
-// candidate row r = 0..2: first sorted index, count | stage offset << 16}. unitList[4 * unit ..] holds the descriptor of
+// A list block is (1 + rows) rows of 256 B. Row 0: bytes 0..127 = per-lane entry counts (u8), bytes 128..187 = the
+// descriptor of the NEXT block of the unit (word 0 = LIST_END terminates the chain). Rows 1.. = entries, [entry][lane],
+// each entry the shared-memory index of a staged candidate of the chunk. unitList[4 * unit ..] holds the descriptor of
 // the unit's first block.
 
 /// What a thread knows about its target and its unit.
@@ -330,7 +326,7 @@ struct UnitLane {
     float lim2;         // squared FP32 filter radius
 };
 
-/// Decodes the lane of thread `tid` in unit `unit` (no synchronisation).
+/// Decodes the lane of thread `tid` in a unit (no synchronisation).
 __device__ __forceinline__ void loadLane(const DevicePointers& d, const GridDev& g, const uint4& desc, const uint4& aux, int tid, float Rhalf,
     float slack, UnitLane& u) {
     const uint32_t dr = desc.x, nLive = desc.w >> 8;
@@ -359,7 +355,7 @@ __device__ __forceinline__ void loadLane(const DevicePointers& d, const GridDev&
 /// Decodes unit `unit` for thread `tid`, publishes the unit's 18 candidate row ranges and the first chunk (thread 0).
 /// Returns false (for the whole CTA) if the unit has no owned target. Contains one CTA-wide barrier.
 __device__ __forceinline__ bool beginUnit(const DevicePointers& d, const GridDev& g, uint32_t unit, int tid, float Rhalf, float slack,
-    uint32_t* sRowBeg, uint32_t* sRowEnd, ChunkCursor& cur, ChunkState& cs0, uint32_t capacity, UnitLane& u) {
+    uint32_t* sRowBeg, uint32_t* sRowEnd, ChunkCursor& cur, ChunkState& cs0, UnitLane& u) {
     const uint4 desc = d.unitDesc[unit];
     const uint4 aux = d.unitAux[unit];
     if (aux.z == 0u) {
@@ -370,8 +366,8 @@ __device__ __forceinline__ bool beginUnit(const DevicePointers& d, const GridDev
     const int x0 = max(cA - 1, 0), x1 = min(cB + 1, dimx - 1);
     loadLane(d, g, desc, aux, tid, Rhalf, slack, u);
     __syncthreads(); // everyone has left the previous unit's loop
-    if (tid < CHUNK_SLOTS * CHUNK_ROWS) { // global sorted ranges of the unit's 18 candidate rows
-        const int z = chunkLayer(tid / CHUNK_ROWS, u.k), y = u.cy + (tid % CHUNK_ROWS) - 1;
+    if (tid < 3 * CHUNK_ROWS) { // global sorted ranges of the unit's 18 candidate rows
+        const int z = chunkLayer(tid / CHUNK_ROWS, tid % CHUNK_ROWS, u.k), y = u.cy + (tid % 3) - 1;
         uint32_t rb = 0, re = 0;
         if (z >= 0 && z < dimz && y >= 0 && y < dimy) {
             const uint32_t base = (uint32_t)((z * dimy + y) * dimx);
@@ -387,7 +383,7 @@ __device__ __forceinline__ bool beginUnit(const DevicePointers& d, const GridDev
             cur.chunk = 0;
             cur.row = 0;
             cur.posValid = 0;
-            nextChunk(sRowBeg, sRowEnd, cur, cs0, capacity);
+            nextChunk(sRowBeg, sRowEnd, cur, cs0);
         }
     }
     return true;
@@ -404,10 +400,9 @@ struct ScanState { // where a lane stands in the candidate rows of the staged ch
     bool open;
 };
 
-/// Phase 1: scans the candidate rows of the staged chunk from `st` on, appending the stage index of every candidate
-/// within the FP32 filter radius to the lane's list (u16 at listOwn + n * LIST_STRIDE, at most CAP entries), until the
-/// chunk is exhausted (st.r == CHUNK_ROWS) or the list is (nearly) full. Returns the list cursor.
-template <int CAP>
+/// Phase 1: scans the candidate rows of the staged chunk from `st` on, appending the shared-memory index of every
+/// candidate within the FP32 filter radius to the lane's list (u16 at listOwn + n * LIST_STRIDE), until the chunk is
+/// exhausted (st.r == CHUNK_ROWS) or the list is (nearly) full. Returns the list cursor.
 __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLane& u, const ScanGeometry& sg, const float4* f4,
     uint32_t listOwn, ScanState& st) {
     uint32_t lp = listOwn;
@@ -420,7 +415,7 @@ __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLan
             if (len > 0) {
                 // y- and z-intervals of this candidate row (FP32 relative to the grid origin, with a guard band: cells
                 // were assigned in FP64) and the x-window [xlo, xhi] the target can reach in it
-                const int zabs = chunkLayer(cs.chunk, u.k), yabs = u.cy + r - 1;
+                const int zabs = chunkLayer(cs.chunk, r, u.k), yabs = u.cy + (r % 3) - 1;
                 const float yl = (float)yabs * sg.cellF, zl = (float)zabs * sg.cellZF;
                 const float dyMin = fmaxf(fmaxf(yl - fyi, fyi - (yl + sg.cellF)) - sg.guard, 0.f);
                 const float dzMin = fmaxf(fmaxf(zl - fzi, fzi - (zl + sg.cellZF)) - sg.guard, 0.f);
@@ -450,7 +445,7 @@ __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLan
             st.open = true;
         }
         // eight candidates per trip: the loads are independent, only the list append is serial. The target itself is
-        // not excluded here (~200 compares) but masked in phase 2 (~70 compares).
+        // not excluded here (~300 compares) but masked in phase 2 (~70 compares).
         uint32_t kpos = st.kpos;
         const uint32_t khi = st.khi;
 #define SPH_F32_TEST(C, K)                                                                                            \
@@ -462,8 +457,8 @@ __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLan
             lp += LIST_STRIDE;                                                                                        \
         }                                                                                                             \
     }
-        const uint32_t lpMax8 = listOwn + (CAP - 8) * LIST_STRIDE;
-        const uint32_t lpMax4 = listOwn + (CAP - 4) * LIST_STRIDE;
+        const uint32_t lpMax8 = listOwn + (LIST_CAP - 8) * LIST_STRIDE;
+        const uint32_t lpMax4 = listOwn + (LIST_CAP - 4) * LIST_STRIDE;
         while (kpos + 8 <= khi && lp <= lpMax8) {
             const float4 ca = f4[kpos], cb = f4[kpos + 1], cc = f4[kpos + 2], cd = f4[kpos + 3];
             const float4 ce = f4[kpos + 4], cf = f4[kpos + 5], cg = f4[kpos + 6], ch = f4[kpos + 7];
@@ -485,7 +480,7 @@ __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLan
             SPH_F32_TEST(cd, kpos + 3)
             kpos += 4;
         }
-        while (kpos < khi && khi - kpos < 4 && lp < listOwn + CAP * LIST_STRIDE) {
+        while (kpos < khi && khi - kpos < 4 && lp < listOwn + LIST_CAP * LIST_STRIDE) {
             const float4 ca = f4[kpos];
             SPH_F32_TEST(ca, kpos)
             kpos++;
@@ -554,19 +549,21 @@ __device__ __forceinline__ void finishTarget(const DevicePointers& d, const Unit
 }
 
 // ---- kernel A: candidate lists ------------------------------------------------------------------------------------
-// Phase 1 of every unit at high occupancy (15 KB of shared memory, 64 registers: 8 CTAs per SM): stages the FP32
-// positions of each chunk (one z-layer, <= PIPE_C candidates), runs the conservative filter and writes the per-lane
-// lists of the chunk as one contiguous block of the list pool, chained per unit through block descriptors. The
-// pair-sum kernel then only stages records + list blocks and spends its 8 warps per SM on FP64 work.
-constexpr size_t LISTS_SMEM = (size_t)PIPE_C * 16 + (size_t)(PIPE_LIST + 1) * LIST_ROW_BYTES;
+// Phase 1 of every unit at high occupancy (26 KB of shared memory, 64 registers: 8 CTAs per SM): stages the FP32
+// positions of each chunk, runs the conservative filter and writes the per-lane lists of the chunk as one contiguous
+// block of the list pool. Every block carries the DESCRIPTOR of the unit's next block (pool offset, rows, chunk and the
+// six staged record ranges), so the pair-sum kernel only follows the chain: it stages records + list blocks and spends
+// its 8 warps per SM on FP64 work.
+constexpr size_t LISTS_SMEM = (size_t)TILE_C * 16 + (size_t)(LIST_CAP + 1) * LIST_ROW_BYTES;
+constexpr int DESC_WORDS = 3 + 2 * CHUNK_ROWS; // {pool row offset, rows, chunk, 6 x {first sorted index, count | stage offset << 16}}
 
 __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint32_t maxCells, uint32_t poolRows) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float4* f4 = reinterpret_cast<float4*>(smemRaw);
-    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + PIPE_C); // one block: row 0 = counts + descriptor, rows 1.. = entries
+    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C); // one block: row 0 = counts + descriptor, rows 1.. = entries
     __shared__ ChunkState csBuf[2];
     __shared__ __align__(8) uint64_t stageBar;
-    __shared__ uint32_t sRowBeg[CHUNK_SLOTS * CHUNK_ROWS], sRowEnd[CHUNK_SLOTS * CHUNK_ROWS];
+    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
     __shared__ uint32_t sWarp[TILE_T / 32], sOff;
 
     const GridDev g = *d.grid;
@@ -589,7 +586,7 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
     for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
         UnitLane u;
         uint32_t* const first = reinterpret_cast<uint32_t*>(d.unitList + (size_t)unit * 4);
-        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], PIPE_C, u)) {
+        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], u)) {
             if (tid == 0) {
                 first[0] = LIST_END;
             }
@@ -615,14 +612,14 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
                         bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
                     }
                 }
-                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1], PIPE_C); // overlaps with the copies
+                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
             }
             mbarWait(&stageBar, stagePhase);
             stagePhase ^= 1;
             buf ^= 1;
             ScanState st = { u.target ? 0 : CHUNK_ROWS, 0u, 0u, false };
             while (true) { // rounds: one block per round (a second round only if some lane's list overflowed)
-                const uint32_t lp = scanRows<PIPE_LIST>(cs, u, sg, f4, listOwn, st);
+                const uint32_t lp = scanRows(cs, u, sg, f4, listOwn, st);
                 const uint32_t cnt = (lp - listOwn) / LIST_STRIDE;
                 reinterpret_cast<unsigned char*>(list)[tid] = (unsigned char)cnt;
                 const uint32_t wmax = __reduce_max_sync(0xffffffffu, cnt);
@@ -659,15 +656,14 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
                         for (uint32_t w = tid; w < (rows + 1u) * ROW_Q; w += TILE_T) {
                             dst[w] = src[w];
                         }
-                        if (tid == 0) { // descriptor of this block -> unitList (first block) or the previous block's header,
-                                        // whose copy finished before the last barrier
+                        if (tid == 0) { // descriptor of this block -> unitList (first block) or the header of the previous
+                                        // block, whose copy finished before the last barrier
                             link[1] = rows;
                             link[2] = (uint32_t)cs.chunk;
-                            link[3] = 0u;
 #pragma unroll
                             for (int r = 0; r < CHUNK_ROWS; ++r) {
-                                link[4 + 2 * r] = cs.beg[r];
-                                link[5 + 2 * r] = (cs.end[r] - cs.beg[r]) | (cs.base[r] << 16);
+                                link[3 + 2 * r] = cs.beg[r];
+                                link[4 + 2 * r] = (cs.end[r] - cs.beg[r]) | (cs.base[r] << 16);
                             }
                             link[0] = off;
                             link = reinterpret_cast<uint32_t*>(pool + (size_t)off * ROW_Q) + TILE_T / 4;
@@ -692,27 +688,25 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
 }
 
 // ---- kernel B: pair sums, list-driven --------------------------------------------------------------------------------
-// Two-stage TMA pipeline without CTA-wide barriers: block n of the CTA's block sequence (the chained blocks of its units)
-// lives in stage n % 2 = {<= PIPE_C FP64 records, list block}. Every warp walks the sequence on its own; the last
-// warp to finish block n (shared-memory counter) issues the copies of block n + 2 into the freed stage, so the loads of
-// the next block always overlap the FP64 work on the current one.
+// Follows the block chains written by k_pair_lists. Per block: one CTA barrier (the stage is free), thread 0 issues the
+// TMA copies of the block's record rows and of its list block, everyone waits on the mbarrier and runs phase 2. At the
+// end of a chain the first block of the CTA's next unit is issued BEFORE the finalizers / stores of the finished unit and
+// the loads of the next unit's targets, so those overlap with the copies.
 template <bool SOLID>
-struct PipeLayout {
+struct SumLayout {
     static constexpr int S = SOLID ? REC_SOLID : REC_FLUID;
-    static constexpr size_t recBytes = (size_t)PIPE_C * S * 8;
-    static constexpr size_t listBytes = (size_t)(PIPE_LIST + 1) * LIST_ROW_BYTES;
-    static constexpr size_t stageBytes = recBytes + listBytes;
-    static constexpr size_t bytes = 2 * stageBytes;
+    static constexpr size_t recBytes = (size_t)TILE_C * S * 8;
+    static constexpr size_t bytes = recBytes + (size_t)(LIST_CAP + 1) * LIST_ROW_BYTES;
 };
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
 __global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32_t maxCells) {
-    using P = PipeLayout<SOLID>;
+    using P = SumLayout<SOLID>;
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    __shared__ __align__(8) uint64_t fullBar[2];
-    __shared__ uint32_t sDone[2];
-    __shared__ uint32_t sIssueUnit; // unit of the most recently issued block
-    __shared__ uint32_t sExhausted; // the CTA's block sequence has been issued completely
+    double* recS = reinterpret_cast<double*>(smemRaw);
+    uint16_t* list = reinterpret_cast<uint16_t*>(smemRaw + P::recBytes); // row 0 = counts + next descriptor, rows 1.. = entries
+    __shared__ __align__(8) uint64_t stageBar;
+    __shared__ uint32_t sFirst[2][16]; // first-block descriptors of the CTA's current and next unit
 
     const GridDev g = *d.grid;
     const uint32_t totalUnits = d.segStart[maxCells];
@@ -721,135 +715,119 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32
     const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
     const float slack = (float)(g.extent * 1.e-6);
     const unsigned char* pool = reinterpret_cast<const unsigned char*>(d.listPool);
-    auto recStage = [&](uint32_t s) { return reinterpret_cast<double*>(smemRaw + s * P::stageBytes); };
-    auto listStage = [&](uint32_t s) { return reinterpret_cast<uint16_t*>(smemRaw + s * P::stageBytes + P::recBytes); };
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(list) + TILE_T / 4; // descriptor of the chain's next block
+    const uint16_t* const lst = list + TILE_T + tid;                           // this lane's first entry
 
-    // Issues block m of the CTA's sequence (one thread). Its descriptor is the header of block m - 1 or, when that was the
-    // last block of its unit (or m == 0), the first descriptor of the next unit that has blocks.
-    auto issueBlock = [&](uint32_t m) {
-        if (sExhausted != 0u) {
-            return; // block m - 1 does not exist either
+    uint32_t unit = blockIdx.x;
+    if (unit >= totalUnits) {
+        return;
+    }
+    auto loadFirst = [&](uint32_t v, int ring) { // threads 0..15: descriptor of unit v's first block -> sFirst[ring]
+        if (tid < 16) {
+            sFirst[ring][tid] = v < totalUnits ? reinterpret_cast<const uint32_t*>(d.unitList + (size_t)v * 4)[tid] : LIST_END;
         }
-        uint32_t desc[DESC_WORDS];
-        desc[0] = LIST_END;
-        if (m > 0) {
-            const uint32_t ps = (m - 1) & 1u;
-            mbarWait(&fullBar[ps], ((m - 1) >> 1) & 1u);
-            const uint32_t* h = reinterpret_cast<const uint32_t*>(listStage(ps)) + TILE_T / 4;
-#pragma unroll
-            for (int w = 0; w < DESC_WORDS; ++w) {
-                desc[w] = h[w];
-            }
-        }
-        uint32_t unit = sIssueUnit;
-        while (desc[0] == LIST_END) {
-            unit += stride;
-            if (unit >= totalUnits) {
-                sExhausted = 1u;
-                return;
-            }
-            const uint4* src = d.unitList + (size_t)unit * 4;
-            const uint4 a = src[0];
-            if (a.x >= LIST_FALLBACK) {
-                continue; // no blocks (LIST_END) or left to the fused kernel (LIST_FALLBACK)
-            }
-            const uint4 b = src[1], c = src[2];
-            desc[0] = a.x; desc[1] = a.y; desc[2] = a.z; desc[3] = a.w;
-            desc[4] = b.x; desc[5] = b.y; desc[6] = b.z; desc[7] = b.w;
-            desc[8] = c.x; desc[9] = c.y;
-        }
-        sIssueUnit = unit;
-        const uint32_t s = m & 1u;
-        fenceProxyAsync(); // the stage was last read through the generic proxy
-        uint32_t bytes = (desc[1] + 1u) * LIST_ROW_BYTES;
-#pragma unroll
-        for (int r = 0; r < CHUNK_ROWS; ++r) {
-            bytes += (desc[5 + 2 * r] & 0xffffu) * (uint32_t)(P::S * 8);
-        }
-        mbarExpectTx(&fullBar[s], bytes);
-#pragma unroll
-        for (int r = 0; r < CHUNK_ROWS; ++r) {
-            const uint32_t n = desc[5 + 2 * r] & 0xffffu, base = desc[5 + 2 * r] >> 16;
-            if (n > 0) {
-                bulkCopyG2S(recStage(s) + (size_t)base * P::S, d.rec + (size_t)desc[4 + 2 * r] * P::S, n * (uint32_t)(P::S * 8), &fullBar[s]);
-            }
-        }
-        bulkCopyG2S(listStage(s), pool + (size_t)desc[0] * LIST_ROW_BYTES, (desc[1] + 1u) * LIST_ROW_BYTES, &fullBar[s]);
     };
-
-    if (tid == 0) {
-        mbarInit(&fullBar[0], 1);
-        mbarInit(&fullBar[1], 1);
-        sDone[0] = sDone[1] = 0u;
-        sIssueUnit = blockIdx.x - stride; // wraps; the first advance lands on blockIdx.x
-        sExhausted = 0u;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        issueBlock(0);
-        issueBlock(1);
-    }
-    __syncthreads();
-
-    uint32_t n = 0; // index of the next block in the CTA's sequence (every warp counts on its own)
-    for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += stride) {
-        const uint4 aux = d.unitAux[unit];
-        if (aux.z == 0u) {
-            continue; // ghost particles only: no targets, no blocks
+    auto issue = [&](const uint32_t* dsc) { // thread 0: TMA copies of the block described by dsc
+        fenceProxyAsync(); // the stage was last read through the generic proxy
+        const uint32_t listBytes = (dsc[1] + 1u) * LIST_ROW_BYTES;
+        uint32_t bytes = listBytes;
+#pragma unroll
+        for (int r = 0; r < CHUNK_ROWS; ++r) {
+            bytes += (dsc[4 + 2 * r] & 0xffffu) * (uint32_t)(P::S * 8);
         }
-        const uint4* firstDesc = d.unitList + (size_t)unit * 4;
-        const uint4 fa = firstDesc[0];
-        if (fa.x == LIST_FALLBACK) {
-            continue; // the fused kernel handles this unit
+        const uint32_t off = dsc[0];
+        uint32_t beg[CHUNK_ROWS], nb[CHUNK_ROWS];
+#pragma unroll
+        for (int r = 0; r < CHUNK_ROWS; ++r) { // read the descriptor before the list copy may overwrite it
+            beg[r] = dsc[3 + 2 * r];
+            nb[r] = dsc[4 + 2 * r];
         }
-        const uint4 fb = firstDesc[1];
-        UnitLane u;
-        loadLane(d, g, d.unitDesc[unit], aux, tid, Rhalf, slack, u);
-        Particle pi;
+        mbarExpectTx(&stageBar, bytes);
+#pragma unroll
+        for (int r = 0; r < CHUNK_ROWS; ++r) {
+            const uint32_t n = nb[r] & 0xffffu;
+            if (n > 0) {
+                bulkCopyG2S(recS + (size_t)(nb[r] >> 16) * P::S, d.rec + (size_t)beg[r] * P::S, n * (uint32_t)(P::S * 8), &stageBar);
+            }
+        }
+        bulkCopyG2S(list, pool + (size_t)off * LIST_ROW_BYTES, listBytes, &stageBar);
+    };
+    auto setupUnit = [&](uint32_t v, UnitLane& u, Particle& pi, Accum& acc) {
+        loadLane(d, g, d.unitDesc[v], d.unitAux[v], tid, Rhalf, slack, u);
         if (u.live) {
             loadRecord<SOLID>(d.rec + (size_t)u.t * P::S, pi);
         } else {
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
         }
-        Accum acc;
         accumZero(acc);
-        const uint32_t ownSlot = u.upper ? 5u : 4u; // the target's own record: own layer, row dy = 0
-        bool more = fa.x != LIST_END;
-        uint32_t curSlot = fa.z, curBeg1 = fb.z, curNB1 = fb.w; // of the block about to be processed
-        while (more) {
-            const uint32_t s = n & 1u;
-            mbarWait(&fullBar[s], (n >> 1) & 1u);
-            const double* rs = recStage(s);
-            const uint16_t* ls = listStage(s);
-            const uint32_t* h = reinterpret_cast<const uint32_t*>(ls) + TILE_T / 4; // descriptor of the unit's next block
-            const uint32_t nextOff = h[0], nextSlot = h[2], nextBeg1 = h[6], nextNB1 = h[7];
-            if (u.target) {
-                const bool selfHere = curSlot == ownSlot && u.t >= curBeg1 && u.t < curBeg1 + (curNB1 & 0xffffu);
-                const double* self = rs + (selfHere ? (size_t)((curNB1 >> 16) + (u.t - curBeg1)) * P::S : (size_t)PIPE_C * P::S);
-                const int cnt = reinterpret_cast<const unsigned char*>(ls)[tid];
-                sumListedPairs<SOLID, CORRECTED, FILTER>(rs, ls + TILE_T + tid, cnt, self, pi, d.lut, acc);
+    };
+
+    if (tid == 0) {
+        mbarInit(&stageBar, 1);
+    }
+    int ring = 0;
+    loadFirst(unit, 0);
+    loadFirst(unit + stride, 1);
+    UnitLane u;
+    Particle pi;
+    Accum acc;
+    setupUnit(unit, u, pi, acc);
+    __syncthreads();
+    uint32_t stagePhase = 0;
+    bool firstOfUnit = true; // the next block is the first one of `unit` (its descriptor is sFirst[ring])
+    bool issued = false;     // ... and its copies are already in flight
+    while (true) {
+        const uint32_t* dsc = firstOfUnit ? sFirst[ring] : hdr;
+        const uint32_t off = dsc[0];
+        if (off >= LIST_FALLBACK) { // the chain of `unit` has ended (or the unit has no chain)
+            const bool fallback = firstOfUnit && off == LIST_FALLBACK; // left to the fused kernel
+            const uint32_t nextUnit = unit + stride;
+            const int nextRing = ring ^ 1;
+            // everyone is done with the stage and has read sFirst[ring]: issue the next unit's first block right away
+            __syncthreads();
+            issued = nextUnit < totalUnits && sFirst[nextRing][0] < LIST_FALLBACK;
+            if (issued && tid == 0) {
+                issue(sFirst[nextRing]);
             }
-            more = nextOff != LIST_END;
-            curSlot = nextSlot;
-            curBeg1 = nextBeg1;
-            curNB1 = nextNB1;
-            __syncwarp();
-            if ((tid & 31) == 0) { // release the stage; the last of the four warps refills it
-                __threadfence_block();
-                if (atomicAdd(&sDone[s], 1u) == TILE_T / 32 - 1) {
-                    sDone[s] = 0u;
-                    issueBlock(n + 2);
-                }
+            if (!fallback) {
+                finishTarget<SOLID, CORRECTED>(d, u, pi, acc); // overlaps with the copies
             }
-            n++;
+            if (nextUnit >= totalUnits) {
+                break;
+            }
+            loadFirst(nextUnit + stride, ring); // ring slot of the finished unit; visible after the next barrier
+            unit = nextUnit;
+            ring = nextRing;
+            setupUnit(unit, u, pi, acc);
+            firstOfUnit = true;
+            continue;
         }
-        finishTarget<SOLID, CORRECTED>(d, u, pi, acc);
+        // descriptor words every thread needs: chunk and the staged row that may hold the target's own record
+        const int selfRow = u.upper ? 4 : 1;
+        const uint32_t chunk = dsc[2], selfBeg = dsc[3 + 2 * selfRow], selfNB = dsc[4 + 2 * selfRow];
+        if (!issued) {
+            __syncthreads(); // everyone is done with the previous block (records, list, its header)
+            if (tid == 0) {
+                issue(dsc);
+            }
+        }
+        issued = false;
+        firstOfUnit = false;
+        mbarWait(&stageBar, stagePhase);
+        stagePhase ^= 1;
+        if (u.target) {
+            const bool selfHere = chunk == 2u && u.t >= selfBeg && u.t < selfBeg + (selfNB & 0xffffu);
+            const double* self = recS + (selfHere ? (size_t)((selfNB >> 16) + (u.t - selfBeg)) * P::S : (size_t)TILE_C * P::S);
+            const int cnt = reinterpret_cast<const unsigned char*>(list)[tid];
+            sumListedPairs<SOLID, CORRECTED, FILTER>(recS, lst, cnt, self, pi, d.lut, acc);
+        }
     }
 }
 
 // ---- fused kernel: both phases in one kernel ---------------------------------------------------------------------------
-// The round-1 design, kept for the units whose lists did not fit the pool (onlyFallback) and as variant 2 for A/B checks.
+// The first design of the tiled kernel, kept for the units whose lists did not fit the pool (onlyFallback) and as
+// variant 2 for A/B checks.
 template <bool SOLID, bool CORRECTED, bool FILTER>
 __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint32_t maxCells, bool onlyFallback) {
     using L = TileLayout<SOLID>;
@@ -859,7 +837,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
     uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C);
     __shared__ ChunkState csBuf[2];
     __shared__ __align__(8) uint64_t stageBar;
-    __shared__ uint32_t sRowBeg[CHUNK_SLOTS * CHUNK_ROWS], sRowEnd[CHUNK_SLOTS * CHUNK_ROWS];
+    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
 
     if (onlyFallback && d.stats->fallbackUnits == 0u) {
         return;
@@ -884,7 +862,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             continue;
         }
         UnitLane u;
-        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], TILE_C, u)) {
+        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], u)) {
             continue;
         }
         Particle pi;
@@ -896,7 +874,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
         }
         Accum acc;
         accumZero(acc);
-        const int ownSlot = u.upper ? 5 : 4; // the target's own record: own layer, row dy = 0
+        const int selfRow = u.upper ? 4 : 1; // the target's own record sits in the centre chunk, own layer, dy = 0
         int buf = 0;
         while (true) {
             __syncthreads(); // chunk descriptor published; everyone is done with the previous chunk's shared memory
@@ -916,7 +894,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
                         bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
                     }
                 }
-                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1], TILE_C); // overlaps with the copies
+                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
             }
             mbarWait(&stageBar, stagePhase);
             stagePhase ^= 1;
@@ -924,12 +902,12 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             if (!u.target) {
                 continue;
             }
-            const double* self = recS + ((cs.chunk == ownSlot && u.t >= cs.beg[1] && u.t < cs.end[1])
-                                                ? (size_t)(cs.base[1] + (u.t - cs.beg[1])) * L::S
+            const double* self = recS + ((cs.chunk == 2 && u.t >= cs.beg[selfRow] && u.t < cs.end[selfRow])
+                                                ? (size_t)(cs.base[selfRow] + (u.t - cs.beg[selfRow])) * L::S
                                                 : (size_t)TILE_C * L::S);
             ScanState st = { 0, 0u, 0u, false };
             while (st.r < CHUNK_ROWS) { // private rounds: phase 1 (FP32 filter -> list), phase 2 (FP64 pairs)
-                const uint32_t lp = scanRows<LIST_CAP>(cs, u, sg, f4, listOwn, st);
+                const uint32_t lp = scanRows(cs, u, sg, f4, listOwn, st);
                 const int cnt = (int)((lp - listOwn) / LIST_STRIDE);
                 sumListedPairs<SOLID, CORRECTED, FILTER>(recS, lst, cnt, self, pi, d.lut, acc);
             }
@@ -974,7 +952,7 @@ template <bool SOLID, bool CORRECTED, bool FILTER>
 static int launchSumVariant(sphgpu_ctx* ctx) {
     auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER>;
     static bool configured = false; // per instantiation; the attribute is per device function
-    const size_t smem = PipeLayout<SOLID>::bytes;
+    const size_t smem = SumLayout<SOLID>::bytes;
     if (!configured) {
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -1015,7 +993,7 @@ static int launchPairKernels(sphgpu_ctx* ctx) {
     return rc;
 }
 
-/// variant 0: candidate lists (k_pair_lists) + pipelined pair sums (k_pair_sum); variant 2: the fused kernel only.
+/// variant 0: candidate lists (k_pair_lists) + list-driven pair sums (k_pair_sum); variant 2: the fused kernel only.
 int launchPairTiled(sphgpu_ctx* ctx) {
     int rc = launchSegments(ctx);
     if (rc != SPHGPU_OK) {
