@@ -28,7 +28,7 @@ UNIT = "particle-updates/s"
 # Algorithmic HBM bytes per particle-update, SURVEY.md section 8(d), solid + correction tensor:
 BYTES_FULL_STEP = 1412.0      # full PredictorCorrector step
 BYTES_INTEGRATE = 628.0       # find + derivatives (integrate() only)
-FP64_INSTR_PER_PAIR = 105.0    # FP64 instructions of the pair body per neighbour pair (SASS count)
+FP64_INSTR_PER_PAIR = 102.0    # FP64 instructions of the pair body per neighbour pair (SASS count)
 BYTES_PAIR_KERNEL = 408.0     # dominant kernel, itemised in DESIGN.md section 3 (sorted record + epilogue inputs in, derivatives out)
 
 
@@ -209,7 +209,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    pair_ms, launches, timings, halo_ms = 0.0, 0, np.zeros(4), 0.0
+    pair_ms, launches, timings, halo_ms, pair_parts = 0.0, 0, np.zeros(4), 0.0, np.zeros(3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
@@ -219,6 +219,7 @@ def main():
         tm = eng.last_timings()
         timings += tm
         pair_ms += tm[2]
+        pair_parts += eng.last_pair_timings()
         launches += st.kernel_launches
         if halo is not None and halo.native:
             halo_ms += eng.last_halo_ms()
@@ -278,7 +279,9 @@ def main():
 
     peak, peak_kind = read_peaks()
     prof = read_traffic() if solid else None
-    pair_s = pair_ms * 1e-3 / args.steps
+    # the dominant kernel is k_pair_sum (FP64 pair sums); the other variants run everything in one kernel
+    sum_ms = pair_parts[2] if pair_parts[2] > 0 else pair_ms
+    pair_s = sum_ms * 1e-3 / args.steps
     bytes_pair = (BYTES_PAIR_KERNEL if solid else 230.0) * n_owned
     achieved = bytes_pair / pair_s / 1e9 if pair_s > 0 else 0.0
     out = {
@@ -293,7 +296,8 @@ def main():
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": e2e,
-        "roofline": {"bound": "hbm", "kernel": "k_pair (fused neighbour search + pair sums + finalizers)",
+        "roofline": {"bound": "hbm", "kernel": "k_pair_sum (list-driven FP64 pair sums + finalizers)" if pair_parts[2] > 0 else
+                     "k_pair (fused neighbour search + pair sums + finalizers)",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " HBM copy GB/s", "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (prof["bytes_per_particle"] * n_owned if prof else None),
@@ -306,7 +310,9 @@ def main():
                               "frac": (FP64_INSTR_PER_PAIR * pairs_per_step / pair_s / fp64_peak if (solid and pair_s > 0 and fp64_peak > 0) else None)},
                      "note": "pair kernel is FP64-pipe / latency bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},
         "phase_ms": {"grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
-                     "pair_kernel": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps},
+                     "pair_stage": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps,
+                     "pair_stage_parts": {"units_and_lane_order": pair_parts[0] / args.steps, "k_pair_lists": pair_parts[1] / args.steps,
+                                          "k_pair_sum": pair_parts[2] / args.steps}},
     }
     if per_rank is not None:
         out["per_rank_ms"] = {"columns": ["grid_build", "prologue_pack", "pair_kernel", "rest", "halo_exchange_in_rest", "owned_particles"],

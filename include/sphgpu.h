@@ -247,6 +247,9 @@ SPHGPU_API int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_
 /* Device-time breakdown of the last integrate call in milliseconds: [0] grid build + sort, [1] prologue + pack,
  * [2] pair kernel, [3] rest. */
 SPHGPU_API int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4);
+/* Device times (ms) of the parts of the last pair stage: {work units + lane order, candidate lists (k_pair_lists),
+ * pair sums (k_pair_sum)}; zeros for the other variants. */
+SPHGPU_API int sphgpu_last_pair_timings(sphgpu_ctx* ctx, double* ms3);
 /* Measures the device's FP64 FMA throughput (fused multiply-adds per second, all SMs) with a register-resident DFMA
  * loop; the pair kernel is bound by this pipe, not by HBM. */
 SPHGPU_API int sphgpu_measure_fp64_peak(sphgpu_ctx* ctx, double* fma_per_second);

@@ -196,6 +196,9 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     for (int k = 0; k < 8; ++k) {
         SPH_TRY(wrap(cudaEventCreate(&ctx->ev[k]), "cudaEventCreate"));
     }
+    for (int k = 0; k < 4; ++k) {
+        SPH_TRY(wrap(cudaEventCreate(&ctx->evPair[k]), "cudaEventCreate"));
+    }
     for (int f = 0; f < F_COUNT; ++f) {
         SPH_TRY(devAlloc(&ctx->d.f[f], cap));
     }
@@ -269,6 +272,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree(ctx->staging);
     for (int k = 0; k < 8; ++k) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+        if (k < 4 && ctx->evPair[k]) cudaEventDestroy(ctx->evPair[k]);
     }
     if (ctx->privateStream) cudaStreamDestroy(ctx->privateStream);
     cudaGetLastError();
@@ -413,6 +417,13 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
         SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]));
         ctx->lastMs[k] = ms;
     }
+    for (int k = 0; k < 3; ++k) {
+        ctx->lastPairMs[k] = 0.;
+        if (ctx->pairTimed) {
+            SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->evPair[k], ctx->evPair[k + 1]));
+            ctx->lastPairMs[k] = ms;
+        }
+    }
     SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, begin, end));
     ctx->lastMs[3] = ms - (ctx->lastMs[0] + ctx->lastMs[1] + ctx->lastMs[2]);
     if (stats) {
@@ -547,6 +558,12 @@ int sphgpu_set_last_timestep(sphgpu_ctx* ctx, double dt) {
 int sphgpu_last_timings(sphgpu_ctx* ctx, double* ms4) {
     if (!ctx || !ms4) return fail(SPHGPU_E_INVALID, "null argument");
     for (int k = 0; k < 4; ++k) ms4[k] = ctx->lastMs[k];
+    return SPHGPU_OK;
+}
+
+int sphgpu_last_pair_timings(sphgpu_ctx* ctx, double* ms3) {
+    if (!ctx || !ms3) return fail(SPHGPU_E_INVALID, "null argument");
+    for (int k = 0; k < 3; ++k) ms3[k] = ctx->lastPairMs[k];
     return SPHGPU_OK;
 }
 

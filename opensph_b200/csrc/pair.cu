@@ -296,6 +296,7 @@ int launchPair(sphgpu_ctx* ctx) {
     if (n == 0) {
         return SPHGPU_OK;
     }
+    ctx->pairTimed = false;
     if (ctx->variant != 1) {
         return launchPairTiled(ctx);
     }

@@ -28,6 +28,7 @@ namespace sph {
 constexpr int TILE_T = 128;   // targets (threads) per work unit
 constexpr int TILE_C = 576;   // staged candidates per chunk
 constexpr int LIST_CAP = 64;  // private list entries per round
+constexpr int PAIRS_PER_TRIP = 3; // list entries the pair-sum kernel processes together
 constexpr int TILE_X = 20;    // widest unit in cells (bounds the per-unit loops over candidate cells)
 constexpr int CHUNK_ROWS = 6; // candidate rows per chunk: 2 z-layers x 3 y-rows
 
@@ -79,69 +80,77 @@ __device__ __forceinline__ void fenceProxyAsync() {
 // `targets` entries of the sequence of columns cA.., starting `skip` entries into column cA.
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCells) {
-    const uint32_t dr = blockIdx.x * blockDim.x + threadIdx.x;
-    if (dr > maxCells || (FILL && dr >= maxCells)) {
-        return;
-    }
+    // one WARP per double row: the lanes fetch the column counts of 256 columns at a time into shared memory (the loads
+    // overlap), lane 0 then walks them; a thread-per-row walk would pay one L2 round trip per column
+    constexpr int CHUNK = 256;
+    __shared__ uint32_t sCnt[4][CHUNK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
-    const uint32_t doubleRows = (uint32_t)dimy * (uint32_t)((dimz + 1) / 2);
-    if (dr >= doubleRows) {
-        if (!FILL) {
-            d.cellCount[dr] = 0; // cellCount is free once cellStart has been built
-        }
-        return;
-    }
-    const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
-    const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
-    const bool hasU = 2 * k + 1 < dimz;
-    const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
-    uint32_t units = 0;
-    const uint32_t out = FILL ? d.segStart[dr] : 0u;
-    auto columnCount = [&](int c) {
-        uint32_t cnt = d.cellStart[rbL + c + 1] - d.cellStart[rbL + c];
-        if (hasU) {
-            cnt += d.cellStart[rbU + c + 1] - d.cellStart[rbU + c];
-        }
-        return cnt;
-    };
-    int c = 0;
-    uint32_t skip = 0; // entries of column c already handed out
-    while (c < dimx) {
-        if (columnCount(c) - skip == 0) {
-            c++;
-            skip = 0;
-            continue;
-        }
-        const int cA = c;
-        const uint32_t skipA = skip;
-        uint32_t taken = 0;
-        int cLast = c;
-        while (c < dimx && taken < (uint32_t)TILE_T && c - cA + 3 <= TILE_X) {
-            const uint32_t avail = columnCount(c) - skip;
-            if (avail == 0) {
-                c++;
-                skip = 0;
-                continue;
+    const uint32_t doubleRows = min((uint32_t)dimy * (uint32_t)((dimz + 1) / 2), maxCells);
+    // (cellCount, free once cellStart has been built, receives the unit counts; the host zeroed it beyond the double rows)
+    for (uint32_t dr = blockIdx.x * 4 + warp; dr < doubleRows; dr += gridDim.x * 4) {
+        const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
+        const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
+        const bool hasU = 2 * k + 1 < dimz;
+        const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
+        uint32_t units = 0;
+        const uint32_t out = FILL ? d.segStart[dr] : 0u;
+        // walk state (lane 0): the open unit [cA, cLast] with `taken` targets, `skipA` entries into column cA
+        int cA = 0, cLast = 0;
+        uint32_t skipA = 0, taken = 0;
+        auto emit = [&]() {
+            if (FILL) {
+                d.unitDesc[out + units] = make_uint4(dr, (uint32_t)cA, skipA, (uint32_t)(cLast - cA) | (taken << 8));
             }
-            const uint32_t take = min(avail, (uint32_t)TILE_T - taken);
-            taken += take;
-            cLast = c;
-            if (take == avail) {
-                c++;
-                skip = 0;
-            } else {
-                skip += take;
-                break;
+            units++;
+            taken = 0;
+        };
+        for (int c0 = 0; c0 < dimx; c0 += CHUNK) {
+            const int n = min(CHUNK, dimx - c0);
+            for (int i = lane; i < n; i += 32) {
+                uint32_t cnt = d.cellStart[rbL + c0 + i + 1] - d.cellStart[rbL + c0 + i];
+                if (hasU) {
+                    cnt += d.cellStart[rbU + c0 + i + 1] - d.cellStart[rbU + c0 + i];
+                }
+                sCnt[warp][i] = cnt;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < n; ++i) {
+                    const int c = c0 + i;
+                    uint32_t avail = sCnt[warp][i];
+                    uint32_t skip = 0; // entries of column c already handed out
+                    while (avail > 0) {
+                        if (taken > 0 && c - cA + 3 > TILE_X) {
+                            emit(); // the x-range would outgrow the tables of the unit preparation
+                        }
+                        if (taken == 0) {
+                            cA = c;
+                            skipA = skip;
+                        }
+                        const uint32_t take = min(avail, (uint32_t)TILE_T - taken);
+                        taken += take;
+                        skip += take;
+                        avail -= take;
+                        cLast = c;
+                        if (taken == (uint32_t)TILE_T) {
+                            emit();
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (taken > 0) {
+                emit();
+            }
+            if (!FILL) {
+                d.cellCount[dr] = units;
             }
         }
-        if (FILL) {
-            d.unitDesc[out + units] = make_uint4(dr, (uint32_t)cA, skipA, (uint32_t)(cLast - cA) | (taken << 8));
-        }
-        units++;
-    }
-    if (!FILL) {
-        d.cellCount[dr] = units;
+        __syncwarp();
     }
 }
 
@@ -497,35 +506,48 @@ __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLan
     return lp;
 }
 
-/// Phase 2: walks the lane's list two entries at a time (so that the long per-pair chains overlap); the exact FP64
-/// predicate enters the branch-free pair body as a mask.
-template <bool SOLID, bool CORRECTED, bool FILTER>
-__device__ __forceinline__ void sumListedPairs(const double* recS, const uint16_t* lst, int cnt, const double* self, const Particle& pi,
+/// W list entries together: the exact FP64 predicate enters the branch-free pair body as a mask; the W long per-pair
+/// dependency chains overlap.
+template <bool SOLID, bool CORRECTED, bool FILTER, int W>
+__device__ __forceinline__ void pairTrip(const double* recS, const uint16_t* lst, int q, const double* self, const Particle& pi,
     const double* lut, Accum& acc) {
     constexpr int S = TileLayout<SOLID>::S;
+    const double* rp[W];
+    Particle pj[W];
+    double dx[W], dy[W], dz[W], d2[W], hb[W];
+    bool v[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        rp[w] = recS + (size_t)lst[(q + w) * TILE_T] * S;
+        loadRecord<SOLID>(rp[w], pj[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        dx[w] = pi.x - pj[w].x;
+        dy[w] = pi.y - pj[w].y;
+        dz[w] = pi.z - pj[w].z;
+        v[w] = isNeighbour(dx[w], dy[w], dz[w], pi.h, pj[w].h, c_prm.kernel_radius, d2[w], hb[w]) && rp[w] != self;
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj[w], dx[w], dy[w], dz[w], d2[w], hb[w], v[w], acc);
+    }
+}
+
+/// Phase 2: walks the lane's list W entries at a time.
+template <bool SOLID, bool CORRECTED, bool FILTER, int W>
+__device__ __forceinline__ void sumListedPairs(const double* recS, const uint16_t* lst, int cnt, const double* self, const Particle& pi,
+    const double* lut, Accum& acc) {
     int q = 0;
-    for (; q + 1 < cnt; q += 2) {
-        const double* rp0 = recS + (size_t)lst[q * TILE_T] * S;
-        const double* rp1 = recS + (size_t)lst[(q + 1) * TILE_T] * S;
-        Particle pj0, pj1;
-        loadRecord<SOLID>(rp0, pj0);
-        loadRecord<SOLID>(rp1, pj1);
-        const double dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
-        const double dx1 = pi.x - pj1.x, dy1 = pi.y - pj1.y, dz1 = pi.z - pj1.z;
-        double d20, hb0, d21, hb1;
-        const bool v0 = isNeighbour(dx0, dy0, dz0, pi.h, pj0.h, c_prm.kernel_radius, d20, hb0) && rp0 != self;
-        const bool v1 = isNeighbour(dx1, dy1, dz1, pi.h, pj1.h, c_prm.kernel_radius, d21, hb1) && rp1 != self;
-        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj0, dx0, dy0, dz0, d20, hb0, v0, acc);
-        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj1, dx1, dy1, dz1, d21, hb1, v1, acc);
+    for (; q + W <= cnt; q += W) {
+        pairTrip<SOLID, CORRECTED, FILTER, W>(recS, lst, q, self, pi, lut, acc);
+    }
+    if (W > 2 && q + 2 <= cnt) {
+        pairTrip<SOLID, CORRECTED, FILTER, 2>(recS, lst, q, self, pi, lut, acc);
+        q += 2;
     }
     if (q < cnt) {
-        const double* rp0 = recS + (size_t)lst[q * TILE_T] * S;
-        Particle pj0;
-        loadRecord<SOLID>(rp0, pj0);
-        const double dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
-        double d20, hb0;
-        const bool v0 = isNeighbour(dx0, dy0, dz0, pi.h, pj0.h, c_prm.kernel_radius, d20, hb0) && rp0 != self;
-        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj0, dx0, dy0, dz0, d20, hb0, v0, acc);
+        pairTrip<SOLID, CORRECTED, FILTER, 1>(recS, lst, q, self, pi, lut, acc);
     }
 }
 
@@ -820,7 +842,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32
             const bool selfHere = chunk == 2u && u.t >= selfBeg && u.t < selfBeg + (selfNB & 0xffffu);
             const double* self = recS + (selfHere ? (size_t)((selfNB >> 16) + (u.t - selfBeg)) * P::S : (size_t)TILE_C * P::S);
             const int cnt = reinterpret_cast<const unsigned char*>(list)[tid];
-            sumListedPairs<SOLID, CORRECTED, FILTER>(recS, lst, cnt, self, pi, d.lut, acc);
+            sumListedPairs<SOLID, CORRECTED, FILTER, PAIRS_PER_TRIP>(recS, lst, cnt, self, pi, d.lut, acc);
         }
     }
 }
@@ -909,7 +931,7 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
             while (st.r < CHUNK_ROWS) { // private rounds: phase 1 (FP32 filter -> list), phase 2 (FP64 pairs)
                 const uint32_t lp = scanRows(cs, u, sg, f4, listOwn, st);
                 const int cnt = (int)((lp - listOwn) / LIST_STRIDE);
-                sumListedPairs<SOLID, CORRECTED, FILTER>(recS, lst, cnt, self, pi, d.lut, acc);
+                sumListedPairs<SOLID, CORRECTED, FILTER, 2>(recS, lst, cnt, self, pi, d.lut, acc);
             }
         }
         finishTarget<SOLID, CORRECTED>(d, u, pi, acc);
@@ -919,11 +941,14 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint
 int launchSegments(sphgpu_ctx* ctx) {
     cudaStream_t st = ctx->stream;
     const uint32_t total = ctx->maxCells + 1;
-    k_units<false><<<(total + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
+    int smsU = 148;
+    cudaDeviceGetAttribute(&smsU, cudaDevAttrMultiProcessorCount, ctx->device);
+    SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.cellCount, 0, sizeof(uint32_t) * total, st));
+    k_units<false><<<smsU * 16, 128, 0, st>>>(ctx->d, ctx->maxCells);
     k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.segStart, ctx->d.scanBlock, total);
     k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks);
     k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.segStart, ctx->d.scanBlock, total);
-    k_units<true><<<(ctx->maxCells + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
+    k_units<true><<<smsU * 16, 128, 0, st>>>(ctx->d, ctx->maxCells);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const uint32_t upper = ctx->nActive / (TILE_T / 2) + ctx->maxCells + 1; // >= number of units
@@ -983,18 +1008,24 @@ static int launchPairKernels(sphgpu_ctx* ctx) {
     if (ctx->variant == 2) { // both phases fused in one kernel
         return launchTiledVariant<SOLID, CORRECTED, FILTER>(ctx, false);
     }
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[1], ctx->stream));
     int rc = launchLists(ctx);
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[2], ctx->stream));
     if (rc == SPHGPU_OK) {
         rc = launchSumVariant<SOLID, CORRECTED, FILTER>(ctx);
     }
     if (rc == SPHGPU_OK) { // returns at once unless the list pool overflowed
         rc = launchTiledVariant<SOLID, CORRECTED, FILTER>(ctx, true);
     }
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[3], ctx->stream));
+    ctx->pairTimed = true;
     return rc;
 }
 
 /// variant 0: candidate lists (k_pair_lists) + list-driven pair sums (k_pair_sum); variant 2: the fused kernel only.
 int launchPairTiled(sphgpu_ctx* ctx) {
+    ctx->pairTimed = false;
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[0], ctx->stream));
     int rc = launchSegments(ctx);
     if (rc != SPHGPU_OK) {
         return rc;

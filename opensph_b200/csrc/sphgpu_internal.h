@@ -110,6 +110,9 @@ struct sphgpu_ctx {
     cudaStream_t privateStream = nullptr;
     double maxChange = 1.e308;            // TIMESTEPPING_MAX_INCREASE
     cudaEvent_t ev[8] = {};
+    cudaEvent_t evPair[4] = {}; // unit preparation | k_pair_lists | k_pair_sum (+ fallback) boundaries
+    double lastPairMs[3] = { 0, 0, 0 };
+    bool pairTimed = false;     // the last pair stage recorded evPair (variant 0)
     double lastMs[4] = { 0, 0, 0, 0 };
     double lastHaloMs = 0.;    // device time of the last halo exchange (pack + NCCL + unpack, includes waiting for peers)
     double lastDt = 0.;        // MultiCriterion::lastStep

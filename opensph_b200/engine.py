@@ -203,6 +203,12 @@ class Engine:
         _check(self.lib.sphgpu_last_timings(self._ctx, ms.ctypes.data_as(C.POINTER(C.c_double))))
         return ms
 
+    def last_pair_timings(self) -> np.ndarray:
+        """Device ms of {unit preparation, candidate lists, pair sums} of the last pair stage."""
+        out = (C.c_double * 3)()
+        _check(self.lib.sphgpu_last_pair_timings(self._ctx, out))
+        return np.array(list(out))
+
     def measure_fp64_peak(self) -> float:
         """FP64 fused multiply-adds per second of this device (DFMA microbenchmark inside the library)."""
         v = C.c_double(0.0)

@@ -7,5 +7,5 @@ BENCH="python bench.py --particles $N --steps 2 --warmup 3 --no-e2e --no-cpu-bas
 # every launch of two timed steps with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches.log 2>&1
 # the dominant kernel, full set, source-level
-ncu --set full --clock-control none --import-source on -k regex:k_pair -s 3 -c 1 -f -o gpurun_out/${TAG}_pair $BENCH > gpurun_out/${TAG}_pair.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pair_sum -s 1 -c 1 -f -o gpurun_out/${TAG}_pair $BENCH > gpurun_out/${TAG}_pair.log 2>&1
 ls -la gpurun_out/${TAG}_*

@@ -116,6 +116,15 @@ def model(n_target, lane_mode="z4", p1_mode="cells", pack="nextfit", tile_c=576)
                 elif lane_mode == "z2x2":  # two z-bands (halves in z), each split in two x-halves
                     pz = np.argsort(P[:, 2], kind="stable")
                     perm = np.concatenate([h2[np.argsort(P[h2, 0], kind="stable")] for h2 in (pz[:64], pz[64:])])
+                elif lane_mode == "zrr":  # z-ranks dealt round-robin to the four warps
+                    pz = np.argsort(P[:, 2], kind="stable")
+                    perm = np.concatenate([pz[w::4] for w in range(4)])
+                elif lane_mode == "z2rr":  # two z-bands, each dealt round-robin to two warps
+                    pz = np.argsort(P[:, 2], kind="stable")
+                    perm = np.concatenate([pz[:64][0::2], pz[:64][1::2], pz[64:][0::2], pz[64:][1::2]])
+                elif lane_mode == "z8":  # eight z-bands; warp w takes bands w and 7 - w (mirror images)
+                    pz = np.argsort(P[:, 2], kind="stable").reshape(8, 16)
+                    perm = np.concatenate([np.concatenate([pz[w], pz[7 - w]]) for w in range(4)])
                 elif lane_mode == "x4":
                     perm = np.argsort(P[:, 0], kind="stable")
                 elif lane_mode == "z4x":  # z-bands, lanes inside a warp ordered by x (same warps as z4)
