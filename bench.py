@@ -309,6 +309,8 @@ def main():
                               "achieved_fp64_instr_per_s": (FP64_INSTR_PER_PAIR * pairs_per_step / pair_s if (solid and pair_s > 0) else None),
                               "frac": (FP64_INSTR_PER_PAIR * pairs_per_step / pair_s / fp64_peak if (solid and pair_s > 0 and fp64_peak > 0) else None)},
                      "note": "pair kernel is FP64-pipe / latency bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},
+        "integrate_only": {"value": n_owned / (max(timings[0] + timings[1] + timings[2], 1e-9) * 1e-3 / args.steps), "unit": UNIT,
+                           "note": "find + derivatives + finalize of this rank (ISolver::integrate alone), device time"},
         "phase_ms": {"grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
                      "pair_stage": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps,
                      "pair_stage_parts": {"units_and_lane_order": pair_parts[0] / args.steps, "k_pair_lists": pair_parts[1] / args.steps,

@@ -257,7 +257,8 @@ SPHGPU_API int sphgpu_measure_fp64_peak(sphgpu_ctx* ctx, double* fma_per_second)
  * time spent waiting for the neighbour ranks), milliseconds. */
 SPHGPU_API int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms);
 /* Selects the pair-kernel variant: 0 = default (candidate lists in their own kernel + tiled pair sums), 1 = direct
- * per-thread kernel, 2 = tiled kernel with both phases fused. For A/B checks only. */
+ * per-thread kernel, 2 = tiled kernel with both phases fused, 3 = as 0 with a tiny list pool (exercises the overflow
+ * path). For A/B checks only. */
 SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
  * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the

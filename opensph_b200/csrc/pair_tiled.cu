@@ -967,7 +967,9 @@ static uint32_t unitGrid(sphgpu_ctx* ctx, int ctasPerSm, int waves) {
 
 static int launchLists(sphgpu_ctx* ctx) {
     SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.listCursor, 0, sizeof(uint32_t), ctx->stream));
-    k_pair_lists<<<unitGrid(ctx, 8, 4), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, ctx->poolRows);
+    // variant 3 (tests): a pool of a few blocks only, so that most units take the fallback path
+    const uint32_t poolRows = ctx->variant == 3 ? std::min<uint32_t>(ctx->poolRows, 4096u) : ctx->poolRows;
+    k_pair_lists<<<unitGrid(ctx, 8, 4), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;

@@ -45,7 +45,7 @@ def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=T
             assert_close(k, got[k], ref[k], tol, FLOOR)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
 def test_integrate_matches_golden(name, variant, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
@@ -125,7 +125,7 @@ def test_variants_agree_on_seeded_random_input(lut):
     setup = abi.setup_from_snapshot(i, lut)
     orc = OraclePort(snap, setup)
     orc.integrate()
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         eng, stats = gpu_integrate(snap, setup, variant)
         check_against(eng, stats, orc.a)
         eng.close()
@@ -243,6 +243,36 @@ def test_line_of_particles_with_increasing_h(lut):
     snap["pos"][:, 3] = np.linspace(1.5, 9.0, n)
     snap["vel"][:, :3] = np.stack([np.sin(x / 50.0), np.zeros(n), np.zeros(n)], axis=1) * 10.0
     _oracle_vs_gpu(snap, setup, names=("acc", "du", "drho", "divv"))
+
+
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_one_giant_smoothing_length(variant, lut):
+    """One particle whose h covers the whole cloud: the grid degenerates to a few cells with thousands of particles each
+    (cell rows are then no longer ordered by x and are scanned whole, chunks are split into pieces), and that particle
+    has every other one as a neighbour (its candidate list overflows many times: several list blocks per chunk)."""
+    i = golden("fluid_in.snap")
+    n0, reps = len(i["mass"]), 12
+    n = n0 * reps
+    rng = np.random.default_rng(77)
+    setup = abi.setup_from_snapshot(i, lut)
+    setup.materials[0].begin, setup.materials[0].end = 0, n
+    snap = {k: np.concatenate([v] * reps) for k, v in i.items() if hasattr(v, "shape") and v.shape[:1] == (n0,)}
+    ext = np.ptp(i["pos"][:, :3], axis=0).max()
+    shift = rng.uniform(0, 2.0 * ext, (reps, 3))
+    snap["pos"] = snap["pos"].copy()
+    snap["pos"][:, :3] += np.repeat(shift, n0, axis=0) + rng.normal(0, 0.05, (n, 3)) * snap["pos"][:, 3:4]
+    snap["pos"][n // 2, 3] = 4.0 * ext
+    snap["vel"] = snap["vel"].copy()
+    snap["vel"][:, :3] = np.sin(snap["pos"][:, :3] / ext * 3.0) * 5.0
+    orc = OraclePort(snap, setup)
+    orc.integrate()
+    assert orc.a["ncnt"].max() == n - 1
+    eng, stats = gpu_integrate(snap, setup, variant)
+    got = eng.download_state(["acc", "du", "drho", "divv", "ncnt"])
+    eng.close()
+    assert np.array_equal(got["ncnt"], orc.a["ncnt"])
+    for k in ("acc", "du", "drho", "divv"):
+        assert_close(k, got[k], orc.a[k], TOL, FLOOR)
 
 
 def test_constant_velocity_gives_exactly_zero_gradient(lut):
