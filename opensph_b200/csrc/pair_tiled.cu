@@ -28,6 +28,7 @@ namespace sph {
 constexpr int TILE_T = 128;   // targets (threads) per work unit
 constexpr int TILE_C = 576;   // staged candidates per chunk
 constexpr int LIST_CAP = 64;  // private list entries per round
+constexpr int UNIT_KBLOCK = 4;    // double rows (in z) interleaved in the unit order, see k_units
 constexpr int PAIRS_PER_TRIP = 3; // list entries the pair-sum kernel processes together
 constexpr int TILE_X = 20;    // widest unit in cells (bounds the per-unit loops over candidate cells)
 constexpr int CHUNK_ROWS = 6; // candidate rows per chunk: 2 z-layers x 3 y-rows
@@ -89,13 +90,21 @@ __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCel
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
     const uint32_t doubleRows = min((uint32_t)dimy * (uint32_t)((dimz + 1) / 2), maxCells);
     // (cellCount, free once cellStart has been built, receives the unit counts; the host zeroed it beyond the double rows)
-    for (uint32_t dr = blockIdx.x * 4 + warp; dr < doubleRows; dr += gridDim.x * 4) {
-        const int cy = (int)(dr % (uint32_t)dimy), k = (int)(dr / (uint32_t)dimy);
+    // Units are numbered in the order the kernels process them. Double rows are taken in blocks of UNIT_KBLOCK
+    // consecutive k (z) per cy, so that the CTAs running at the same time work on z-neighbours as well as y-neighbours
+    // and find each other's candidate rows in L2 (plain k-major order re-reads every record from DRAM for k - 1, k, k + 1).
+    const int nk = (dimz + 1) / 2;
+    for (uint32_t p = blockIdx.x * 4 + warp; p < doubleRows; p += gridDim.x * 4) {
+        const int kb = min((int)(p / (uint32_t)(UNIT_KBLOCK * dimy)), (nk - 1) / UNIT_KBLOCK);
+        const int hB = min(UNIT_KBLOCK, nk - kb * UNIT_KBLOCK);
+        const uint32_t rem = p - (uint32_t)(kb * UNIT_KBLOCK * dimy);
+        const int cy = (int)(rem / (uint32_t)hB), k = kb * UNIT_KBLOCK + (int)(rem % (uint32_t)hB);
+        const uint32_t dr = (uint32_t)(k * dimy + cy);
         const uint32_t rbL = (uint32_t)(((2 * k) * dimy + cy) * dimx);
         const bool hasU = 2 * k + 1 < dimz;
         const uint32_t rbU = hasU ? (uint32_t)(((2 * k + 1) * dimy + cy) * dimx) : 0u;
         uint32_t units = 0;
-        const uint32_t out = FILL ? d.segStart[dr] : 0u;
+        const uint32_t out = FILL ? d.segStart[p] : 0u;
         // walk state (lane 0): the open unit [cA, cLast] with `taken` targets, `skipA` entries into column cA
         int cA = 0, cLast = 0;
         uint32_t skipA = 0, taken = 0;
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCel
                 emit();
             }
             if (!FILL) {
-                d.cellCount[dr] = units;
+                d.cellCount[p] = units;
             }
         }
         __syncwarp();
@@ -969,7 +978,7 @@ static int launchLists(sphgpu_ctx* ctx) {
     SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.listCursor, 0, sizeof(uint32_t), ctx->stream));
     // variant 3 (tests): a pool of a few blocks only, so that most units take the fallback path
     const uint32_t poolRows = ctx->variant == 3 ? std::min<uint32_t>(ctx->poolRows, 4096u) : ctx->poolRows;
-    k_pair_lists<<<unitGrid(ctx, 8, 4), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows);
+    k_pair_lists<<<unitGrid(ctx, 8, 8), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
@@ -984,7 +993,8 @@ static int launchSumVariant(sphgpu_ctx* ctx) {
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kernel<<<unitGrid(ctx, 2, 8), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
+    // many more CTAs than fit at once: the block scheduler balances the load (measured: 32 waves beat 8 by 1 %, 1 by 4 %)
+    kernel<<<unitGrid(ctx, 2, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
