@@ -256,6 +256,10 @@ SPHGPU_API int sphgpu_measure_fp64_peak(sphgpu_ctx* ctx, double* fma_per_second)
 /* Device time of the halo exchange of the last sphgpu_step_pc_mgpu call (pack + NCCL send/recv + unpack, including the
  * time spent waiting for the neighbour ranks), milliseconds. */
 SPHGPU_API int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms);
+/* Changes the number of owned particles (<= capacity) after particles were added, removed or migrated between the
+ * ranks of a decomposed run (the analogue of Storage::remove / merge, core/quantities/Storage.h:560-). Slots [0, n) must
+ * be uploaded again, including MATERIAL_ID for more than one material; ghosts are dropped (n_active = n). */
+SPHGPU_API int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles);
 /* Selects the pair-kernel variant: 0 = default (candidate lists in their own kernel + tiled pair sums), 1 = direct
  * per-thread kernel, 2 = tiled kernel with both phases fused, 3 = as 0 with a tiny list pool (exercises the overflow
  * path). For A/B checks only. */

@@ -362,6 +362,18 @@ int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active) {
     return SPHGPU_OK;
 }
 
+int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (n_particles > ctx->capacity) {
+        return fail(SPHGPU_E_INVALID, "particle count exceeds the capacity of the context");
+    }
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->n = n_particles;
+    ctx->nActive = n_particles; // ghosts are dropped; the caller appends them again (sphgpu_set_active)
+    return SPHGPU_OK;
+}
+
 int sphgpu_set_variant(sphgpu_ctx* ctx, int variant) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
     ctx->variant = variant;

@@ -6,7 +6,7 @@ only to particle i and reads neighbour inputs, so one exchange of the neighbour 
 (SURVEY 8e); ghosts are appended after the owned particles -- the analogue of GhostParticles on the CPU
 (core/sph/boundary/Boundary.h:73-) -- and are never targets.
 
-Round-1 decomposition: slabs of equal particle counts along z (a 1-D space-filling curve; z because the cell rows of
+Round-1 decomposition: slabs of equal particle counts along z, re-cut and migrated on demand (`repartition`) (a 1-D space-filling curve; z because the cell rows of
 the pair kernel run along x and must stay long). Each rank keeps its
 slots ordered [left band | interior | right band], so the particles a neighbour needs are two contiguous slot ranges
 and packing is a plain range copy (sphgpu_download_device). The dynamic neighbour inputs (r,h | v | rho | u | S | D) are
@@ -88,6 +88,14 @@ class SlabDomain:
             state = {k: (v[perm] if isinstance(v, np.ndarray) and v.shape[:1] == (len(perm),) else v) for k, v in state.items()}
         return state
 
+    def adopt_cuts(self, cuts: np.ndarray, halo_width: float) -> None:
+        """New cut planes (from balanced_cut_planes) and halo width after a repartition."""
+        self.cuts = np.asarray(cuts, dtype=np.float64)
+        self.lo_plane = float(self.cuts[self.rank]) if self.rank > 0 else None
+        self.hi_plane = float(self.cuts[self.rank + 1]) if self.rank < self.world - 1 else None
+        self.halo_width = float(halo_width)
+        self._n_total = None
+
     def total_particles(self, n_owned: int) -> int:
         if self._n_total is None:
             if self.world == 1:
@@ -106,6 +114,120 @@ class SlabDomain:
         density = self.n_target * 1.07 / (4.0 / 3.0 * math.pi * self.radius ** 3)
         per_face = math.pi * self.radius ** 2 * self.halo_width * density
         return n_owned + int(2.2 * per_face) + 1024
+
+
+# everything a particle carries when it changes rank: state, the derivatives the next predictor step extrapolates with,
+# and the per-particle material constants
+MIGRATE_FIELDS: Tuple[str, ...] = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "S", "dS", "damage", "ddamage", "reduce",
+                                   "eps_min", "m_zero", "growth", "n_flaws", "flag")
+
+
+def _dist_device(dist) -> str:
+    return "cuda" if dist.get_backend() == "nccl" else "cpu"
+
+
+def balanced_cut_planes(coord: np.ndarray, world: int, dist=None, bins: int = 4096) -> np.ndarray:
+    """Cut planes (world + 1 ascending values) splitting the particles of ALL ranks into `world` slabs of (nearly) equal
+    count along one coordinate: global histogram (all_reduce), cuts at the count quantiles, linear inside a bin.
+    The analogue of re-cutting a space-filling curve into equal pieces; works for any particle distribution."""
+    import torch
+    lo = float(coord.min()) if len(coord) else np.inf
+    hi = float(coord.max()) if len(coord) else -np.inf
+    if dist is not None and world > 1:
+        t = torch.tensor([lo, -hi], dtype=torch.float64, device=_dist_device(dist))
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        lo, hi = float(t[0].item()), -float(t[1].item())
+    span = max(hi - lo, 1e-300)
+    edges = lo + span * np.arange(bins + 1) / bins
+    edges[-1] = hi + 1e-9 * span
+    hist = np.histogram(coord, edges)[0].astype(np.float64)
+    if dist is not None and world > 1:
+        t = torch.from_numpy(hist).to(_dist_device(dist))
+        dist.all_reduce(t)
+        hist = t.cpu().numpy()
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    total = cum[-1]
+    cuts = [lo - 1e-6 * span]
+    for k in range(1, world):
+        target = total * k / world
+        b = int(np.searchsorted(cum, target, side="right")) - 1
+        b = min(max(b, 0), bins - 1)
+        frac = (target - cum[b]) / hist[b] if hist[b] > 0 else 0.0
+        cuts.append(float(edges[b] + frac * (edges[b + 1] - edges[b])))
+    cuts.append(hi + 1e-6 * span)
+    return np.array(cuts)
+
+
+def migrate(state: Dict[str, np.ndarray], dest: np.ndarray, world: int, rank: int, dist) -> Dict[str, np.ndarray]:
+    """Moves every particle to rank dest[i]: one message per pair of ranks (all per-particle arrays of `state` packed as
+    rows of doubles; u32 fields are exact in a double). Returns the new owned state: kept particles first (original
+    order), then the received ones by source rank."""
+    import torch
+    n = len(dest)
+    names = [k for k, v in state.items() if isinstance(v, np.ndarray) and v.shape[:1] == (n,)]
+    widths = [int(np.prod(state[k].shape[1:], dtype=np.int64)) for k in names]
+    width = sum(widths)
+    rows = np.empty((n, width), np.float64)
+    off = 0
+    for k, w in zip(names, widths):
+        rows[:, off:off + w] = state[k].reshape(n, w)
+        off += w
+    dev = _dist_device(dist)
+    mine = torch.tensor([int((dest == r).sum()) for r in range(world)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(counts, mine)
+    counts = torch.stack(counts).cpu().numpy()  # counts[src, dst]
+    ops, recv = [], {}
+    send_bufs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if counts[rank, peer] > 0:
+            buf = torch.from_numpy(np.ascontiguousarray(rows[dest == peer])).to(dev)
+            send_bufs.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, peer))
+        if counts[peer, rank] > 0:
+            recv[peer] = torch.empty((int(counts[peer, rank]), width), dtype=torch.float64, device=dev)
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    parts = [rows[dest == rank]] + [recv[p].cpu().numpy() for p in sorted(recv)]
+    rows = np.concatenate(parts, axis=0) if parts else rows[:0]
+    out = {k: v for k, v in state.items() if k not in names}
+    off = 0
+    for k, w in zip(names, widths):
+        block = rows[:, off:off + w]
+        out[k] = np.ascontiguousarray(block.reshape((len(rows),) + state[k].shape[1:]).astype(state[k].dtype))
+        off += w
+    return out
+
+
+def repartition(dom: "SlabDomain", eng, names: Sequence[str] = MIGRATE_FIELDS, adapter=None, kernel_radius: float = 2.0):
+    """Re-cuts the slabs to equal particle counts and migrates the particles that changed slab ('re-cut every
+    m steps and migrate particles'). Host-orchestrated and rare: downloads the owned state, exchanges rows point-to-point,
+    restores the [lower band | interior | upper band] slot order, uploads, and rebuilds the halo exchange.
+    Returns (new owned state on the host, new HaloExchange)."""
+    import torch
+    import torch.distributed as dist
+    state = eng.download_state([k for k in names])
+    axis = dom.axis
+    cuts = balanced_cut_planes(state["pos"][:, axis], dom.world, dist)
+    dest = np.clip(np.searchsorted(cuts[1:-1], state["pos"][:, axis], side="right"), 0, dom.world - 1)
+    state = migrate(state, dest, dom.world, dom.rank, dist)
+    # halo width from the CURRENT largest smoothing length of the whole run
+    hmax = torch.tensor([float(state["pos"][:, 3].max()) if len(state["pos"]) else 0.0], dtype=torch.float64, device=_dist_device(dist))
+    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    dom.adopt_cuts(cuts, kernel_radius * float(hmax.item()) * 1.05)
+    perm, dom.n_left, dom.n_right = band_partition(state["pos"][:, axis], dom.lo_plane, dom.hi_plane, dom.halo_width)
+    state = {k: (v[perm] if isinstance(v, np.ndarray) and v.shape[:1] == (len(perm),) else v) for k, v in state.items()}
+    n_new = len(perm)
+    if n_new > eng.capacity:
+        raise ValueError(f"rank {dom.rank}: {n_new} particles after migration exceed the engine capacity {eng.capacity}")
+    eng.set_particle_count(n_new)
+    eng.upload_state(state, names)
+    halo = HaloExchange(dom, eng, state, adapter=adapter)
+    return state, halo
 
 
 class EngineAdapter:
@@ -170,7 +292,9 @@ class HaloExchange:
         # the per-step exchange runs inside the library (NCCL on the engine's stream) when the engine supports it
         self.native = hasattr(eng, "comm_init") and dist.get_backend() == "nccl" and self.fields == DYNAMIC_FIELDS
         if self.native:
-            eng.comm_init(dom.rank, dom.world)
+            if not getattr(eng, "_comm_ready", False):  # the communicator survives a repartition
+                eng.comm_init(dom.rank, dom.world)
+                eng._comm_ready = True
             eng.halo_configure(-1 if self.left is None else self.left, -1 if self.right is None else self.right,
                                dom.n_left, dom.n_right, self.g_left, self.g_right)
 

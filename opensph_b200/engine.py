@@ -158,6 +158,11 @@ class Engine:
             out[name] = self.download(q, order)
         return out
 
+    def set_particle_count(self, n: int) -> None:
+        """Changes the number of owned particles (after migration between ranks); the state must be uploaded again."""
+        _check(self.lib.sphgpu_set_particle_count(self._ctx, C.c_uint32(n)))
+        self.n = n
+
     def set_active(self, n_active: int) -> None:
         _check(self.lib.sphgpu_set_active(self._ctx, C.c_uint32(n_active)))
 

@@ -80,6 +80,36 @@ def main():
             print(f"{k:6s} rel err {e:.3e}")
             ok &= e <= 1e-9
         print("MGPU PARITY", "OK" if ok else "FAILED", f"world={world} particles={nf} ghosts={halo.g_left + halo.g_right}")
+    # ---- re-cut + migration: displace the particles across the cut planes, repartition, compare again ----
+    def warp(pos0):
+        out = pos0.copy()
+        out[:, 2] += 0.2 * 5.0e4 * np.sin(2.0 * np.pi * pos0[:, 0] / 5.0e4)
+        return out
+
+    n_before = eng.n
+    eng.upload("POSITION", 0, warp(eng.download_state(["pos"])["pos"]))
+    _, halo2 = decomp.repartition(dom, eng)
+    halo2.exchange()
+    eng.integrate()
+    got2 = eng.download_state(("pos", "acc", "du", "drho", "dS", "divv", "ncnt"))
+    gathered2 = [None] * world
+    dist.gather_object(got2, gathered2 if rank == 0 else None, dst=0)
+    if rank == 0:
+        moved = warp(single.download_state(["pos"])["pos"])
+        single.upload("POSITION", 0, moved)
+        single.integrate()
+        ref2 = single.download_state(("pos", "acc", "du", "drho", "dS", "divv", "ncnt"))
+        all2 = {k: np.concatenate([g[k] for g in gathered2]) for k in ref2}
+        ok2 = len(all2["ncnt"]) == nf
+        if ok2:
+            a, b = key(all2["pos"]), key(ref2["pos"])
+            ok2 = np.array_equal(all2["ncnt"][a], ref2["ncnt"][b])
+            for k in ("acc", "du", "drho", "dS", "divv"):
+                e = rel_err(all2[k][a], ref2[k][b], 1e-4)
+                print(f"{k:6s} rel err after repartition {e:.3e}")
+                ok2 &= e <= 1e-9
+        print("MGPU REPARTITION", "OK" if ok2 else "FAILED", f"owned before={n_before} (rank 0) after={[len(g['ncnt']) for g in gathered2]}")
+        ok &= bool(ok2)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
