@@ -176,16 +176,18 @@ __device__ __forceinline__ uint32_t unitLaneBase(const DevicePointers& d, int di
 }
 
 // ---- unit preparation: lane order, filter radius bound, ghost-only flag -----------------------------------------
-// One CTA per unit (grid-stride). Orders the unit's targets by z (the lanes of a warp then see similar numbers of
-// neighbours in every chunk => full lanes in phase 2 of the pair kernel) and stores the order once, so that the
-// register- and shared-memory-heavy pair kernel starts every unit with a single coalesced load.
+// One CTA per unit (grid-stride). Orders the unit's targets by z (stable counting sort on 32 height bins): the lanes of
+// a warp then see similar numbers of neighbours in every chunk => full lanes in phase 2. The order is stored once, so
+// that the register- and shared-memory-heavy pair kernels start every unit with a single coalesced load.
 __global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t nOwned, uint32_t maxCells) {
+    constexpr int ZBINS = 32; // z resolution of the lane order: 1/32 of the double row's height
     __shared__ uint32_t sColL[TILE_X + 2], sColU[TILE_X + 2], sHmax;
-    __shared__ float sKey[TILE_T];
+    __shared__ uint32_t sBinW[TILE_T / 32][ZBINS], sBase[ZBINS];
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
     const uint32_t totalUnits = d.segStart[maxCells];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float binScale = (float)(ZBINS / (2. * g.cellZ));
     for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
         const uint4 desc = d.unitDesc[unit];
         const uint32_t dr = desc.x, skip = desc.z, nLive = desc.w >> 8;
@@ -203,11 +205,12 @@ __global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t
         if (tid == 0) {
             sHmax = 0u;
         }
+        sBinW[warp][lane] = 0u;
         __syncthreads();
         // the unit's targets in column order: lower cell, then upper cell of every column
         uint32_t word = 0xffffffffu; // idle lane
         bool owned = false;
-        float key = 3.0e38f;
+        uint32_t bin = ZBINS + (uint32_t)lane; // idle lanes: a key of their own
         if ((uint32_t)tid < nLive) {
             uint32_t pos = skip + (uint32_t)tid, tIdx = 0u;
             for (int c = 0; c <= span; ++c) {
@@ -226,9 +229,15 @@ __global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t
             const uint32_t t = tIdx & 0x3fffffffu;
             owned = d.order[t] < nOwned; // ghosts are neighbours only
             word = tIdx | (owned ? 0u : 0x40000000u);
-            key = d.posF[t].z;
+            const float zrel = d.posF[t].z - (float)(2 * k) * (float)g.cellZ; // height above the bottom of the double row
+            bin = (uint32_t)min(max((int)(zrel * binScale), 0), ZBINS - 1);
         }
-        sKey[tid] = key;
+        // stable counting sort by z bin: lanes of equal bin keep the column (x) order
+        const uint32_t same = __match_any_sync(0xffffffffu, bin);
+        const uint32_t lower = __popc(same & ((1u << lane) - 1u));
+        if (bin < (uint32_t)ZBINS && lower == 0u) {
+            sBinW[warp][bin] = __popc(same);
+        }
         // largest h among the unit's candidates (cells x0..x1 of the 18 rows): bound of the FP32 filter radius
         uint32_t hm = 0u;
         for (int e = tid; e < 18 * (TILE_X + 2); e += TILE_T) {
@@ -243,14 +252,28 @@ __global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t
             atomicMax(&sHmax, hm);
         }
         const int anyOwned = __syncthreads_or(owned ? 1 : 0);
-        int rank = 0;
-        for (int j = 0; j < TILE_T; ++j) {
-            const float kj = sKey[j];
-            rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
+        if (warp == 0) { // exclusive prefix of the bin totals
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < TILE_T / 32; ++w) {
+                tot += sBinW[w][lane];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += lane >= o ? v : 0u;
+            }
+            sBase[lane] = incl - tot;
         }
+        __syncthreads();
         const uint32_t base = unitLaneBase(d, dimx, dimy, dimz, k, cy, cA, skip);
         if ((uint32_t)tid < nLive) {
-            d.unitLane[base + rank] = word; // live lanes sort before the idle ones: rank < nLive
+            uint32_t rank = sBase[bin] + lower;
+            for (int w = 0; w < warp; ++w) {
+                rank += sBinW[w][bin];
+            }
+            d.unitLane[base + rank] = word;
         }
         if (tid == 0) {
             d.unitAux[unit] = make_uint4(base, sHmax, (uint32_t)anyOwned, 0u);
