@@ -51,15 +51,55 @@ def read_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+    """Samples SM clocks / throttle reasons while the timed region runs (B200_PROFILING.md): NVML from a thread every
+    20 ms (the timed region of the default run is a fraction of a second), nvidia-smi as the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
         self.index, self.samples, self.proc = index, [], None
+        self.nvml, self.handle, self.running, self.thread, self.max_mhz = None, None, False, None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, handle
+
+    def _sample_nvml(self):
+        p, h = self.nvml, self.handle
+        mhz = float(p.nvmlDeviceGetClockInfo(h, p.NVML_CLOCK_SM))
+        try:
+            bits = int(p.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            bits = int(p.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.samples.append((mhz, bits))
+
+    def _loop(self):
+        while self.running:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -72,6 +112,18 @@ class ClockSampler:
             self.samples.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            try:
+                self._sample_nvml()  # the GPU is still busy / boosted when the timed region has just ended
+            except Exception:
+                pass
+            self.running = False
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            sm = sorted(m for m, _ in self.samples)
+            reasons = sorted({name for _, bits in self.samples for mask, name in self.REASON_BITS if bits & mask})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +139,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def run_reference(args, n_sample: int):
