@@ -438,6 +438,19 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
     }
     SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, begin, end));
     ctx->lastMs[3] = ms - (ctx->lastMs[0] + ctx->lastMs[1] + ctx->lastMs[2]);
+    // Units whose candidate lists did not fit the list pool were handled by the (slower) fused kernel; give the next
+    // steps a larger pool (the stream is idle here). Variant 3 keeps its deliberately tiny pool.
+    if (sd.fallbackUnits > 0 && ctx->variant != 3 && ctx->poolRows < 0x7ffffff0u) {
+        const uint32_t grown = (uint32_t)std::min<uint64_t>((uint64_t)ctx->poolRows * 2, 0xfffffff0ull);
+        unsigned char* bigger = nullptr;
+        if (cudaMalloc(&bigger, (size_t)grown * 256) == cudaSuccess) {
+            cudaFree(ctx->d.listPool);
+            ctx->d.listPool = bigger;
+            ctx->poolRows = grown;
+        } else {
+            cudaGetLastError(); // out of memory: keep the pool, the fused path stays correct
+        }
+    }
     if (stats) {
         stats->neigh_min = ctx->n ? sd.neighMin : 0;
         stats->neigh_max = sd.neighMax;

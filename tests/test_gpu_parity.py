@@ -275,6 +275,39 @@ def test_one_giant_smoothing_length(variant, lut):
         assert_close(k, got[k], orc.a[k], TOL, FLOOR)
 
 
+def test_list_pool_overflow_falls_back_and_grows(lut):
+    """Thousands of neighbours per particle (h three times the spacing-consistent value): the candidate lists need far
+    more rows than the pool reserves, so the first evaluation takes the fused path for the overflowing units
+    (stats.reserved0 > 0) and enlarges the pool; results must be right both times."""
+    i = golden("fluid_in.snap")
+    n0, reps = len(i["mass"]), 6
+    n = n0 * reps
+    rng = np.random.default_rng(5)
+    setup = abi.setup_from_snapshot(i, lut)
+    setup.materials[0].begin, setup.materials[0].end = 0, n
+    snap = {k: np.concatenate([v] * reps) for k, v in i.items() if hasattr(v, "shape") and v.shape[:1] == (n0,)}
+    snap["pos"] = snap["pos"].copy()
+    snap["pos"][:, :3] += rng.normal(0, 0.3, (n, 3)) * snap["pos"][:, 3:4]  # the copies overlap: six times the density
+    snap["pos"][:, 3] *= 3.0
+    orc = OraclePort(snap, setup)
+    orc.integrate()
+    assert orc.a["ncnt"].mean() > 1000
+    eng = Engine(setup, n)
+    eng.upload_state(snap, STATE_IN)
+    first = eng.integrate()
+    assert first.reserved0 > 0, "the pool was expected to overflow"
+    for attempt in range(4):
+        got = eng.download_state(["acc", "du", "drho", "divv", "ncnt"])
+        assert np.array_equal(got["ncnt"], orc.a["ncnt"])
+        for k in ("acc", "du", "drho", "divv"):
+            assert_close(k, got[k], orc.a[k], TOL, FLOOR)
+        again = eng.integrate()
+        if again.reserved0 == 0:
+            break
+    assert again.reserved0 < first.reserved0, "the pool did not grow"
+    eng.close()
+
+
 def test_constant_velocity_gives_exactly_zero_gradient(lut):
     """equations/test/EquationTerm.cpp:177-375: the gradient of a constant velocity field is EXACTLY zero."""
     i = golden("hello_in.snap")
