@@ -1,33 +1,37 @@
-// Tiled pair kernel: the production variant of the fused neighbour search + pair sums.
+// The pair stage: fused neighbour search + pair sums of the asymmetric solver, as a chain of kernels over WORK UNITS.
 //
 // Grid       : cells are a x a x a/2 (a = R h_max); a "double row" is the two half-height cell rows (cy, 2k), (cy, 2k+1).
-// Work unit  = up to 128 targets of ONE double row restricted to a cell range [cA, cB] in x, one target per thread,
-//              per-target sums in registers, no atomics (asymmetric formulation).
+// Work unit  = up to 128 targets of ONE double row (column order, a cell column may be split between units), one
+//              target per thread, per-target sums in registers, no atomics (asymmetric formulation). k_units builds the
+//              units, k_unit_prep orders the targets of a unit by z and stores the lane assignment.
 // Candidates = the six z-layers 2k-2 .. 2k+3 (three cell rows dy = -1,0,1 each) restricted to cells [cA-1, cB+1]. They
 //              are processed as three CHUNKS that pair layers symmetrically: far (2k-2, 2k+3), near (2k-1, 2k+2),
 //              centre (2k, 2k+1). With the lanes ordered by z, every warp then sees about the same number of
 //              neighbours in every chunk (measured on the hex lattice: 5/19/45 per chunk for all four z-bands, versus
 //              25/43/0 ... 0/43/25 when whole layers are processed one after the other), so the CTA-wide barrier at the
 //              chunk boundaries costs little.
-// Staging    : one thread issues TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier), one per
-//              contiguous candidate row; records are 144-byte FP64 structures (odd 16-byte stride => consecutive
-//              records fall into different bank groups); the FP32 {x,y,z,h} copies relative to the grid origin
-//              (written by the prologue) are staged the same way.
-// Phase 1    : every thread scans, per candidate row, the x-window IT can reach (interval culling in y and z, then
-//              bisection on x: cell rows are sorted by x, see k_sort_cells) with a conservative FP32 distance test
-//              (FP32/ALU pipes) and appends survivors to a private u16 list.
-// Phase 2    : every thread walks its list two entries at a time; the exact FP64 predicate (bit-identical neighbour
-//              sets) enters the branch-free FP64 pair body as a mask -- full lanes, no divergence on the expensive path.
+// Phase 1    = k_pair_lists (FP32/ALU pipes, 32 warps per SM): TMA bulk copies (cp.async.bulk global -> shared,
+//              completion on an mbarrier) stage the FP32 {x,y,z,h} copies of a chunk (relative to the grid origin, written
+//              by the prologue); every thread scans, per candidate row, the x-window IT can reach (interval culling in y
+//              and z, then bisection on x: cell rows are sorted by x, see k_sort_cells) with a conservative FP32 distance
+//              test and appends survivors to its u16 list; the lists of a chunk leave as one block of the list pool,
+//              blocks are chained per unit through descriptors.
+// Phase 2    = k_pair_sum (FP64 pipe, 8 warps per SM): follows the chains; per block TMA copies of the chunk's records
+//              (144-byte FP64 structures; odd 16-byte stride => consecutive records fall into different bank groups) and of
+//              the list block; every thread walks its list three entries at a time; the exact FP64 predicate
+//              (bit-identical neighbour sets) enters the branch-free FP64 pair body as a mask.
+// k_pair_tiled runs both phases in one kernel (the first design): used for units whose lists overflow the pool and as a
+// cross-check (variant 2).
 //
 // Replaces the reference hot loop AsymmetricSolver.cpp:174-201 (finder.findAll + filter + kernel.grad +
-// derivatives.eval) -- see pair.cu for the epilogue it shares with the direct variant.
+// derivatives.eval) -- see pair.cu for the prologue, the epilogue helpers and the direct variant.
 #include "sphgpu_internal.h"
 
 namespace sph {
 
 constexpr int TILE_T = 128;   // targets (threads) per work unit
 constexpr int TILE_C = 576;   // staged candidates per chunk
-constexpr int LIST_CAP = 64;  // private list entries per round
+constexpr int LIST_CAP = 64;  // list entries per lane and block
 constexpr int UNIT_KBLOCK = 4;    // double rows (in z) interleaved in the unit order, see k_units
 constexpr int PAIRS_PER_TRIP = 3; // list entries the pair-sum kernel processes together
 constexpr int TILE_X = 20;    // widest unit in cells (bounds the per-unit loops over candidate cells)
