@@ -6,6 +6,7 @@
 #include "sph/equations/av/Standard.h"
 #include "system/Factory.h"
 #include "system/Statistics.h"
+#include "system/Timer.h"
 #include "thread/Scheduler.h"
 #include <string>
 #include <vector>
@@ -284,6 +285,55 @@ void GpuSolver::integrate(Storage& storage, Statistics& stats) {
         neighsStats.accumulate(neighs[i]);
     }
     stats.set(StatisticsId::NEIGHBOR_COUNT, neighsStats);
+}
+
+//-----------------------------------------------------------------------------------------------------------
+// GpuGravitySolver
+//-----------------------------------------------------------------------------------------------------------
+
+GpuGravitySolver::GpuGravitySolver(IScheduler& scheduler,
+    const RunSettings& settings,
+    const EquationHolder& eqs,
+    AutoPtr<IGravity>&& gravityImpl,
+    const int device)
+    : scheduler(scheduler)
+    , sph(scheduler, settings, eqs, device)
+    , gravity(std::move(gravityImpl)) {
+    if (!gravity) {
+        gravity = Factory::getGravity(settings);
+    }
+}
+
+GpuGravitySolver::~GpuGravitySolver() = default;
+
+void GpuGravitySolver::create(Storage& storage, IMaterial& material) const {
+    sph.create(storage, material);
+}
+
+void GpuGravitySolver::integrate(Storage& storage, Statistics& stats) {
+    // SPH part on the device; it overwrites the (zeroed) highest derivatives of the Storage
+    Timer timer;
+    sph.integrate(storage, stats);
+    stats.set(StatisticsId::SPH_EVAL_TIME, int(timer.elapsed(TimerUnit::MILLISECOND)));
+
+    // gravity as GravitySolver::loop does it (GravitySolver.cpp:68-88): build the tree, add the accelerations of the
+    // particles and of the attractors to the acceleration buffer. The reference adds gravity first and the SPH terms
+    // afterwards; the sum differs by rounding only.
+    timer.restart();
+    gravity->build(scheduler, storage);
+    stats.set(StatisticsId::GRAVITY_BUILD_TIME, int(timer.elapsed(TimerUnit::MILLISECOND)));
+    ArrayView<Vector> dv = storage.getD2t<Vector>(QuantityId::POSITION);
+    timer.restart();
+    gravity->evalSelfGravity(scheduler, dv, stats);
+    stats.set(StatisticsId::GRAVITY_EVAL_TIME, int(timer.elapsed(TimerUnit::MILLISECOND)));
+    ArrayView<Attractor> attractors = storage.getAttractors();
+    gravity->evalAttractors(scheduler, attractors, dv);
+    // the gravity kernels work on whole Vectors and leave a value in the H lane; the smoothing length is a first-order
+    // quantity (AdaptiveSmoothingLength::finalize / ConstSmoothingLength::finalize zero it AFTER gravity in the
+    // reference's order of operations, EquationTerm.cpp:381-383,427-434)
+    for (Size i = 0; i < dv.size(); ++i) {
+        dv[i][H] = 0._f;
+    }
 }
 
 //-----------------------------------------------------------------------------------------------------------

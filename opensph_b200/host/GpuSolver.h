@@ -20,6 +20,7 @@
 ///     // optional: keep the whole step on the device
 ///     timeStepping = makeAuto<GpuPredictorCorrector>(storage, settings, static_cast<GpuSolver&>(*solver));
 
+#include "gravity/IGravity.h"
 #include "sph/equations/EquationTerm.h"
 #include "system/Settings.h"
 #include "sph/kernel/Kernel.h"
@@ -75,6 +76,39 @@ public:
 private:
     void uploadQuantities(const Storage& storage, const bool derivatives);
     void downloadQuantities(Storage& storage, const bool stateToo);
+};
+
+/// \brief GpuSolver plus the reference's own self-gravity, the composition GravitySolver<TSphSolver> performs
+///        (core/sph/solvers/GravitySolver.cpp:64-99, selected by ForceEnum::SELF_GRAVITY in Factory.cpp:300-312).
+///
+/// The SPH derivatives come from the device; the gravitational accelerations are evaluated by the IGravity object of
+/// the reference (Barnes-Hut or brute force, Factory::getGravity) on the host cores and added to the acceleration
+/// buffer, so that setups with self-gravity -- the GUI collision preset, SimulationJobs.cpp:209-223 -- run with the
+/// device as their SPH part. Gravity on the device is SURVEY section 8(f) #1; until then this solver is the way to run
+/// such setups, at the cost of the host-side tree walk.
+class GpuGravitySolver : public ISolver {
+private:
+    IScheduler& scheduler;
+    GpuSolver sph;
+    AutoPtr<IGravity> gravity;
+
+public:
+    /// \param gravity Gravity implementation; nullptr selects Factory::getGravity(settings) like GravitySolver does.
+    GpuGravitySolver(IScheduler& scheduler,
+        const RunSettings& settings,
+        const EquationHolder& eqs,
+        AutoPtr<IGravity>&& gravity = nullptr,
+        const int device = 0);
+
+    ~GpuGravitySolver() override;
+
+    virtual void integrate(Storage& storage, Statistics& stats) override;
+
+    virtual void create(Storage& storage, IMaterial& material) const override;
+
+    GpuSolver& sphSolver() {
+        return sph;
+    }
 };
 
 /// \brief PredictorCorrector whose whole step (predict, derivatives, correct, time-step criteria) runs on the device.

@@ -7,6 +7,7 @@
 // libsphgpu.so; the binary goes to oracle/_ref/dropin_test because it embeds reference code.
 #include "../../opensph_b200/host/GpuSolver.h"
 #include "Sph.h"
+#include "sph/solvers/GravitySolver.h"
 #include <cstdio>
 #include <random>
 
@@ -214,7 +215,33 @@ int main(int argc, char** argv) {
         tc.syncToHost();
         expect(compareStorages(*sa, *sc, false, "GpuPredictorCorrector") <= 1.e-9, "state after device-resident PC steps within 1e-9");
 
-        // ---- 3. unsupported setups throw InvalidSetup instead of silently running elsewhere ----
+        // ---- 3. self-gravity: GravitySolver<AsymmetricSolver> (Factory.cpp:300-312) next to GpuGravitySolver ----
+        {
+            RunSettings gs = settings;
+            gs.set(RunSettingsId::SPH_SOLVER_FORCES, ForceEnum::PRESSURE | ForceEnum::SOLID_STRESS | ForceEnum::SELF_GRAVITY)
+                .set(RunSettingsId::GRAVITY_SOLVER, GravityEnum::BARNES_HUT)
+                .set(RunSettingsId::GRAVITY_OPENING_ANGLE, 0.8_f)
+                .set(RunSettingsId::GRAVITY_MULTIPOLE_ORDER, 3);
+            const EquationHolder geqs = getStandardEquations(gs);
+            GravitySolver<AsymmetricSolver> refGravity(*scheduler, gs, geqs);
+            GpuGravitySolver gpuGravity(*scheduler, gs, geqs);
+            Storage ga = base->clone(VisitorEnum::ALL_BUFFERS), gb = base->clone(VisitorEnum::ALL_BUFFERS);
+            ga.zeroHighestDerivatives(*scheduler);
+            gb.zeroHighestDerivatives(*scheduler);
+            Statistics sa2, sb2;
+            sa2.set(StatisticsId::RUN_TIME, 0._f);
+            sb2.set(StatisticsId::RUN_TIME, 0._f);
+            refGravity.integrate(ga, sa2);
+            gpuGravity.integrate(gb, sb2);
+            expect(sameNeighbourCounts(ga, gb), "NEIGHBOR_CNT identical with self-gravity");
+            expect(compareStorages(ga, gb, true, "integrate() with Barnes-Hut self-gravity") <= 1.e-10,
+                "all quantities within 1e-10 (GravitySolver<AsymmetricSolver> vs GpuGravitySolver)");
+            // the gravity part is not negligible in this comparison: accelerations must differ from the SPH-only ones
+            const double diff = cmpVector(gb.getD2t<Vector>(QuantityId::POSITION), b.getD2t<Vector>(QuantityId::POSITION), 3);
+            expect(diff > 1.e-6, "gravity contributes to the accelerations");
+        }
+
+        // ---- 4. unsupported setups throw InvalidSetup instead of silently running elsewhere ----
         bool thrown = false;
         try {
             RunSettings s2 = settings;
