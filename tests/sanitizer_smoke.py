@@ -1,0 +1,57 @@
+"""compute-sanitizer driver (run on the GPU box):
+
+    compute-sanitizer --tool memcheck  python tests/sanitizer_smoke.py
+    compute-sanitizer --tool racecheck python tests/sanitizer_smoke.py
+
+Runs every tiled pair-kernel variant on the golden inputs (one work unit each), then a 20 k-particle lattice with
+ghost-free multi-unit chains, and a cloud with one giant smoothing length (split chunks, multi-block lists)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import golden  # noqa: E402
+from opensph_b200 import abi, workloads  # noqa: E402
+from opensph_b200.engine import Engine  # noqa: E402
+
+STATE_IN = ("pos", "vel", "mass", "rho", "u", "p", "cs", "S", "damage", "reduce", "eps_min", "m_zero", "growth", "n_flaws", "flag")
+lut = golden("lut.snap")
+
+
+def run(snap, setup, variant, label):
+    eng = Engine(setup, len(snap["mass"]))
+    eng.set_variant(variant)
+    eng.upload_state(snap, STATE_IN)
+    st = eng.integrate()
+    got = eng.download_state(["ncnt"])
+    assert st.pair_count == int(got["ncnt"].astype(np.int64).sum())
+    print(label, "variant", variant, "pairs", st.pair_count, "fallback units", st.reserved0)
+    eng.close()
+
+
+for name in ("collision", "fluid"):
+    i = golden(f"{name}_in.snap")
+    for variant in (0, 2, 3):
+        run(i, abi.setup_from_snapshot(i, lut), variant, name)
+
+state = workloads.basalt_sphere_state(20000, 5.0e4, solid=True)
+for variant in (0, 3):
+    run(state, workloads.make_setup(len(state["mass"]), solid=True), variant, "lattice 20k")
+
+i = golden("fluid_in.snap")
+n0, reps = len(i["mass"]), 4
+n = n0 * reps
+rng = np.random.default_rng(77)
+setup = abi.setup_from_snapshot(i, lut)
+setup.materials[0].begin, setup.materials[0].end = 0, n
+snap = {k: np.concatenate([v] * reps) for k, v in i.items() if hasattr(v, "shape") and v.shape[:1] == (n0,)}
+ext = np.ptp(i["pos"][:, :3], axis=0).max()
+snap["pos"] = snap["pos"].copy()
+snap["pos"][:, :3] += np.repeat(rng.uniform(0, 2.0 * ext, (reps, 3)), n0, axis=0)
+snap["pos"][n // 2, 3] = 4.0 * ext
+run(snap, setup, 0, "giant h")
+print("SANITIZER SMOKE DONE")
