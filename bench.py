@@ -264,18 +264,27 @@ def main():
         sampler.start()
     pair_ms, launches, timings, halo_ms, pair_parts = 0.0, 0, np.zeros(4), 0.0, np.zeros(3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    batched = halo is None or halo.native  # the K steps are queued back to back, dt stays on the device (sphgpu_run_pc)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
-        _, _, st = one_step()
-        tm = eng.last_timings()
-        timings += tm
-        pair_ms += tm[2]
-        pair_parts += eng.last_pair_timings()
-        launches += st.kernel_launches
-        if halo is not None and halo.native:
-            halo_ms += eng.last_halo_ms()
+    if batched:
+        _, _, st = eng.run_pc(args.steps, dt, dt)
+        tm = eng.last_timings()  # CUDA-event times of the last step of the batch
+        timings += tm * args.steps
+        pair_ms += tm[2] * args.steps
+        pair_parts += eng.last_pair_timings() * args.steps
+        launches += st.kernel_launches * args.steps
+        if halo is not None:
+            halo_ms += eng.last_halo_ms() * args.steps
+    else:
+        for _ in range(args.steps):
+            _, _, st = one_step()
+            tm = eng.last_timings()
+            timings += tm
+            pair_ms += tm[2]
+            pair_parts += eng.last_pair_timings()
+            launches += st.kernel_launches
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -345,6 +354,8 @@ def main():
                    "particles_per_gpu": int(n_owned), "mean_neighbours": round(float(neigh_mean), 2), "integrator": "predictor_corrector",
                    "dt": dt, "l2": "inputs larger than L2 (state %.1f GB per GPU)" % (n_owned * 464 / 1e9),
                    "decomposition": "z-slabs of equal particle count + NCCL halo exchange inside the step" if world > 1 else "single domain",
+                   "stepping": "sphgpu_run_pc: K steps queued back to back, time step fed back on the device, one host sync" if batched
+                   else "one call and one host sync per step",
                    "pair_variant": args.variant},
         "clocks": clocks,
         "gpu_launches": int(launches),

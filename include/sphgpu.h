@@ -214,6 +214,13 @@ SPHGPU_API int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_r
     uint32_t recv_left, uint32_t recv_right);
 SPHGPU_API int sphgpu_halo_exchange(sphgpu_ctx* ctx);
 SPHGPU_API int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
+/* `steps` PredictorCorrector steps queued back to back: the time step chosen by the criteria (MultiCriterion::compute,
+ * TimeStepCriterion.cpp:389-419, evaluated by a device kernel) stays on the device and feeds the next step, so the host
+ * synchronises once for the whole batch instead of once per step (what IRun::run's loop does between output times,
+ * core/run/IRun.cpp:232-250). Uses the halo exchange + ncclAllReduce of the time step when a communicator is configured.
+ * `dt` is the first step, history[s] the step chosen AFTER step s (history[steps-1].dt is the next dt); stats and the
+ * timings refer to the last step. Identical results to `steps` calls of sphgpu_step_pc / sphgpu_step_pc_mgpu. */
+SPHGPU_API int sphgpu_run_pc(sphgpu_ctx* ctx, uint32_t steps, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* history);
 /* Number of particles that take part as neighbours: owned + ghosts (ghosts occupy [n_particles, n_active)). */
 SPHGPU_API int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active);
 

@@ -217,6 +217,8 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     ctx->poolRows = (uint32_t)std::min<size_t>(cap + cap / 2 + 8192, 0xfffffff0u);
     SPH_TRY(devAlloc(&ctx->d.listPool, (size_t)ctx->poolRows * 256));
     SPH_TRY(devAlloc(&ctx->d.listCursor, 1));
+    SPH_TRY(devAlloc(&ctx->d.stepState, 1));
+    ctx->d.dtDev = nullptr;
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
     SPH_TRY(devAlloc(&ctx->d.posF, cap));
     SPH_TRY(devAlloc(&ctx->d.cellHmax, (size_t)ctx->maxCells + 1));
@@ -265,7 +267,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc); cudaFree(ctx->d.unitAux); cudaFree(ctx->d.unitLane); cudaFree(ctx->d.unitList);
-    cudaFree(ctx->d.listPool); cudaFree(ctx->d.listCursor);
+    cudaFree(ctx->d.listPool); cudaFree(ctx->d.listCursor); cudaFree(ctx->d.stepState);
     cudaFree(ctx->d.posF); cudaFree(ctx->d.cellHmax);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);

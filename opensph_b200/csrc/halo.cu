@@ -180,6 +180,88 @@ int sphgpu_halo_exchange(sphgpu_ctx* ctx) {
     return exchange(ctx);
 }
 
+int sphgpu_run_pc(sphgpu_ctx* ctx, uint32_t steps, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* history) {
+    if (!ctx || (steps > 0 && !history)) {
+        setError("null argument");
+        return SPHGPU_E_INVALID;
+    }
+    if (!ctx->stateUploaded && ctx->n > 0) {
+        setError("run called before any state was uploaded");
+        return SPHGPU_E_STATE;
+    }
+    if (steps == 0) {
+        return SPHGPU_OK;
+    }
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    NcclApi* api = h ? ncclApi() : nullptr;
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    StepRecordDev* histDev = nullptr;
+    SPH_CUDA_CHECK(cudaMalloc(&histDev, sizeof(StepRecordDev) * steps));
+    const StepStateDev init = { dt, ctx->lastDt, ctx->lastDtInit ? 1u : 0u, 0u };
+    int rc = SPHGPU_OK;
+    cudaError_t ce = cudaMemcpyAsync(ctx->d.stepState, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
+    ctx->d.dtDev = &ctx->d.stepState->dt;
+    ctx->launches = 0;
+    for (uint32_t s = 0; s < steps && rc == SPHGPU_OK && ce == cudaSuccess; ++s) {
+        if (s + 1 == steps) { // the events time the last step
+            ce = cudaEventRecord(ctx->ev[4], ctx->stream);
+            ctx->launches = 0;
+        }
+        rc = launchPredict(ctx, 0.);
+        if (rc == SPHGPU_OK && h) {
+            cudaEventRecord(ctx->ev[6], ctx->stream);
+            rc = exchange(ctx); // ghosts carry the PREDICTED state
+            cudaEventRecord(ctx->ev[7], ctx->stream);
+        }
+        if (rc == SPHGPU_OK) rc = enqueueIntegrate(ctx);
+        if (rc == SPHGPU_OK) rc = launchCorrect(ctx, 0.);
+        if (rc == SPHGPU_OK) rc = launchCriteria(ctx);
+        if (rc == SPHGPU_OK && h) {
+            if (api->AllReduce(ctx->d.tsd, ctx->d.tsd, 4, ncclUint64, ncclMin, h->comm, ctx->stream) != ncclSuccess) {
+                setError("ncclAllReduce failed");
+                rc = SPHGPU_E_CUDA;
+            }
+        }
+        if (rc == SPHGPU_OK) rc = launchFinishTimestep(ctx, max_dt, histDev, s);
+    }
+    ctx->d.dtDev = nullptr;
+    if (ce != cudaSuccess) {
+        setError(std::string("CUDA: ") + cudaGetErrorString(ce));
+        rc = SPHGPU_E_CUDA;
+    }
+    if (rc == SPHGPU_OK) {
+        ce = cudaEventRecord(ctx->ev[5], ctx->stream);
+        rc = collectStats(ctx, stats, ctx->ev[4], ctx->ev[5]); // the one host synchronisation
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (rc == SPHGPU_OK) {
+        std::vector<StepRecordDev> hist(steps);
+        StepStateDev fin;
+        ce = cudaMemcpy(hist.data(), histDev, sizeof(StepRecordDev) * steps, cudaMemcpyDeviceToHost);
+        if (ce == cudaSuccess) ce = cudaMemcpy(&fin, ctx->d.stepState, sizeof(fin), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) {
+            setError(std::string("CUDA: ") + cudaGetErrorString(ce));
+            rc = SPHGPU_E_CUDA;
+        } else {
+            for (uint32_t s = 0; s < steps; ++s) {
+                history[s].dt = hist[s].dt;
+                history[s].criterion = hist[s].criterion;
+                history[s].reserved0 = 0;
+            }
+            ctx->lastDt = fin.lastDt;
+            ctx->lastDtInit = fin.lastDtInit != 0u;
+            if (h) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+                ctx->lastHaloMs = ms;
+            }
+        }
+    }
+    cudaFree(histDev);
+    return rc;
+}
+
 int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out) {
     (void)t;
     if (!ctx || !ctx->halo) {

@@ -64,6 +64,17 @@ struct TimestepDev {
     unsigned long long minBits[4]; // Courant, Derivative, Acceleration, Divergence (bit patterns of positive doubles)
 };
 
+struct StepStateDev { // time-step bookkeeping of sphgpu_run_pc (MultiCriterion::compute on the device)
+    double dt;          // step the next predict / correct will use
+    double lastDt;      // MultiCriterion::lastStep
+    uint32_t lastDtInit, pad;
+};
+
+struct StepRecordDev {
+    double dt;          // step chosen after this PredictorCorrector step
+    uint32_t criterion, pad;
+};
+
 struct DevicePointers {
     double* f[F_COUNT];
     uint32_t* u[U_COUNT];
@@ -89,6 +100,8 @@ struct DevicePointers {
     GridDev* grid;
     StatsDev* stats;
     TimestepDev* tsd;
+    StepStateDev* stepState;   // allocated once
+    const double* dtDev;       // != null: k_predict / k_correct take dt from here (sphgpu_run_pc), not from their argument
 };
 
 constexpr int BOUNDS_BLOCKS = 592;   // 148 SMs x 4
@@ -151,6 +164,7 @@ int launchCorrect(sphgpu_ctx* ctx, double dt);
 int launchEuler(sphgpu_ctx* ctx, double dt);
 int launchCriteria(sphgpu_ctx* ctx);
 int measureFp64Peak(sphgpu_ctx* ctx, double* fmaPerSecond);
+int launchFinishTimestep(sphgpu_ctx* ctx, double maxDt, StepRecordDev* history, uint32_t index);
 // transfer.cu
 int launchUnpack(sphgpu_ctx* ctx, int q, int order, int layout, const void* stagingDev, uint32_t first, uint32_t count);
 int launchPack(sphgpu_ctx* ctx, int q, int order, int layout, void* stagingDev, uint32_t first, uint32_t count);

@@ -22,11 +22,12 @@ __device__ __forceinline__ void clampFirstOrder(const MaterialDev& m, bool hasDa
 // makePredictions (TimeStepping.cpp:286-300) + storage->swap(predictions) + zeroHighestDerivatives (:331-334).
 // The derivative planes are not zeroed: integrate() overwrites every one of them.
 template <bool SOLID>
-__global__ void __launch_bounds__(256) k_predict(DevicePointers d, uint32_t n, double dt, bool hasDamage) {
+__global__ void __launch_bounds__(256) k_predict(DevicePointers d, uint32_t n, double dtArg, bool hasDamage) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) {
         return;
     }
+    const double dt = d.dtDev ? *d.dtDev : dtArg;
     const MaterialDev& m = c_mats[d.u[U_MATID][i]];
     const double dt2 = 0.5 * dt * dt;
     const double ax = d.f[F_AX][i], ay = d.f[F_AY][i], az = d.f[F_AZ][i];
@@ -68,11 +69,12 @@ __global__ void __launch_bounds__(256) k_predict(DevicePointers d, uint32_t n, d
 
 // makeCorrections (TimeStepping.cpp:302-322): storage1 = *storage (p*), storage2 = predictions (c*).
 template <bool SOLID>
-__global__ void __launch_bounds__(256) k_correct(DevicePointers d, uint32_t n, double dt, bool hasDamage) {
+__global__ void __launch_bounds__(256) k_correct(DevicePointers d, uint32_t n, double dtArg, bool hasDamage) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) {
         return;
     }
+    const double dt = d.dtDev ? *d.dtDev : dtArg;
     const MaterialDev& m = c_mats[d.u[U_MATID][i]];
     const double dt2 = 0.5 * dt * dt;
     const double a = 1. / 3., b = 0.5;
@@ -278,6 +280,58 @@ int measureFp64Peak(sphgpu_ctx* ctx, double* fmaPerSecond) {
     float ms = 0.f;
     SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
     *fmaPerSecond = (double)blocks * threads * 8. * iters / (ms * 1.e-3);
+    return SPHGPU_OK;
+}
+
+// MultiCriterion::compute (TimeStepCriterion.cpp:389-419) on the device, the same operations as finishTimestep() in
+// api.cu: lets sphgpu_run_pc queue several steps without a host round trip for the time step.
+__global__ void k_finish_timestep(DevicePointers d, double maxDt, double maxChange, uint32_t criteria, StepRecordDev* history,
+    uint32_t index) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) {
+        return;
+    }
+    const uint32_t bits[4] = { SPHGPU_CRIT_COURANT, SPHGPU_CRIT_DERIVATIVES, SPHGPU_CRIT_ACCELERATION, SPHGPU_CRIT_DIVERGENCE };
+    const uint32_t ids[4] = { SPHGPU_CRITID_CFL_CONDITION, SPHGPU_CRITID_DERIVATIVE, SPHGPU_CRITID_ACCELERATION,
+        SPHGPU_CRITID_DIVERGENCE };
+    double minStep = INFTY_REF;
+    uint32_t minId = SPHGPU_CRITID_INITIAL_VALUE;
+    for (int k = 0; k < 4; ++k) {
+        if (!(criteria & bits[k])) {
+            continue;
+        }
+        double step = __longlong_as_double((long long)d.tsd->minBits[k]);
+        uint32_t id = ids[k];
+        if (step > maxDt) {
+            step = maxDt;
+            id = SPHGPU_CRITID_MAXIMAL_VALUE;
+        }
+        if (step < minStep) {
+            minStep = step;
+            minId = id;
+        }
+    }
+    StepStateDev& st = *d.stepState;
+    if (maxChange < 1.e300) {
+        if (!st.lastDtInit) {
+            st.lastDt = minStep;
+            st.lastDtInit = 1u;
+        }
+        const double maxStep = __dmul_rn(st.lastDt, 1. + maxChange);
+        if (minStep > maxStep) {
+            minStep = maxStep;
+            minId = SPHGPU_CRITID_MAX_CHANGE;
+        }
+        st.lastDt = minStep;
+    }
+    st.dt = minStep;
+    history[index].dt = minStep;
+    history[index].criterion = minId;
+    history[index].pad = 0u;
+}
+
+int launchFinishTimestep(sphgpu_ctx* ctx, double maxDt, StepRecordDev* history, uint32_t index) {
+    k_finish_timestep<<<1, 32, 0, ctx->stream>>>(ctx->d, maxDt, ctx->maxChange, ctx->prm.criteria, history, index);
+    SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
 

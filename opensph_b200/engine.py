@@ -208,6 +208,14 @@ class Engine:
         _check(self.lib.sphgpu_last_timings(self._ctx, ms.ctypes.data_as(C.POINTER(C.c_double))))
         return ms
 
+    def run_pc(self, steps: int, dt: float, max_dt: float):
+        """`steps` PredictorCorrector steps with one host synchronisation; returns (dt chosen after every step, criterion ids,
+        stats of the last step)."""
+        st = abi.Stats()
+        hist = (abi.TimeStep * max(steps, 1))()
+        _check(self.lib.sphgpu_run_pc(self._ctx, C.c_uint32(steps), C.c_double(dt), C.c_double(max_dt), C.byref(st), hist))
+        return (np.array([hist[s].dt for s in range(steps)]), np.array([hist[s].criterion for s in range(steps)], np.uint32), st)
+
     def last_pair_timings(self) -> np.ndarray:
         """Device ms of {unit preparation, candidate lists, pair sums} of the last pair stage."""
         out = (C.c_double * 3)()

@@ -26,6 +26,10 @@ CHECK = ("pos", "vel", "rho", "u", "S", "acc", "du", "drho", "dS", "divv")
 
 
 def steps(eng, halo, n_steps, dt):
+    if os.environ.get("MGPU_BATCHED", "1") == "1" and (halo is None or halo.native):
+        # all steps queued back to back, the (global) time step fed back on the device: sphgpu_run_pc on both sides
+        eng.run_pc(n_steps, dt, dt)
+        return
     for _ in range(n_steps):
         if halo is not None and halo.native and os.environ.get("MGPU_NATIVE", "1") == "1":
             eng.step_pc_mgpu(dt, 1.0e30)  # the whole step inside the library, NCCL on the engine's stream

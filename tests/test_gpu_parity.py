@@ -275,6 +275,34 @@ def test_one_giant_smoothing_length(variant, lut):
         assert_close(k, got[k], orc.a[k], TOL, FLOOR)
 
 
+def test_batched_steps_equal_single_steps(lut):
+    """sphgpu_run_pc (time step chosen on the device, one host synchronisation for the batch) against the same number
+    of sphgpu_step_pc calls with the host feeding the time step back: identical dt sequence and state."""
+    i = golden("collision_in.snap")
+    setup = abi.setup_from_snapshot(i, lut)
+    consts = abi.run_constants(i)
+    n, steps = len(i["mass"]), 6
+    a, b = Engine(setup, n), Engine(setup, n)
+    for eng in (a, b):
+        eng.upload_state(i, STATE_IN)
+        eng.set_last_timestep(consts["initial_dt"])
+    dts, dt = [], consts["initial_dt"]
+    for _ in range(steps):
+        dt, crit, _ = a.step_pc(dt, consts["max_dt"])
+        dts.append(dt)
+    hist, crits, st = b.run_pc(steps, consts["initial_dt"], consts["max_dt"])
+    assert np.array_equal(hist, np.array(dts)), (hist, dts)
+    ga, gb = (e.download_state(["pos", "vel", "rho", "u", "S", "damage", "acc", "du", "drho", "dS"]) for e in (a, b))
+    for k in ga:
+        assert np.array_equal(ga[k], gb[k]), k
+    # and the batch can be continued by single steps
+    dt_a, _, _ = a.step_pc(dts[-1], consts["max_dt"])
+    dt_b, _, _ = b.step_pc(float(hist[-1]), consts["max_dt"])
+    assert dt_a == dt_b
+    a.close()
+    b.close()
+
+
 def test_list_pool_overflow_falls_back_and_grows(lut):
     """Thousands of neighbours per particle (h three times the spacing-consistent value): the candidate lists need far
     more rows than the pool reserves, so the first evaluation takes the fused path for the overflowing units
