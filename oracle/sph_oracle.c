@@ -409,15 +409,6 @@ static void materials_finalize(orc_state* s, const sphgpu_material* mats, uint32
 
 /* ---- derivatives ------------------------------------------------------------------------------------------ */
 
-static const sphgpu_material* material_of(const sphgpu_material* mats, uint32_t nmat, uint32_t i) {
-    for (uint32_t m = 0; m < nmat; ++m) {
-        if (i >= mats[m].begin && i < mats[m].end) {
-            return &mats[m];
-        }
-    }
-    return &mats[0];
-}
-
 /* DerivativeTemplate::sum / AccelerationTemplate::sum filter, core/sph/equations/DerivativeHelpers.h:132-139 */
 static int undamaged_skip(const orc_state* s, uint32_t i, uint32_t j) {
     return s->flag[i] != s->flag[j] || s->reduce[i] == 0. || s->reduce[j] == 0.;
@@ -699,7 +690,6 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
         }
     }
     materials_finalize(s, mats, nmat);
-    (void)material_of;
 }
 
 /* ---- time stepping ---------------------------------------------------------------------------------------- */
