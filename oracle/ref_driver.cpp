@@ -132,7 +132,7 @@ struct Args {
 /// Run settings of the named config.
 RunSettings makeSettings(const std::string& config, const Args& args) {
     RunSettings settings; // library defaults (core/system/Settings.cpp:486-715)
-    if (config == "preset" || config == "preset_const_h" || config == "fluid" || config == "collision_preset") {
+    if (config == "preset" || config == "preset_const_h" || config == "fluid" || config == "gas" || config == "collision_preset") {
         // GUI "collision" preset, SphJob::getDefaultSettings (core/run/jobs/SimulationJobs.cpp:195-232),
         // SELF_GRAVITY removed (out of scope), adaptive h per BASELINE.json configs 3-4.
         settings.set(RunSettingsId::TIMESTEPPING_INTEGRATOR, TimesteppingEnum::PREDICTOR_CORRECTOR)
@@ -158,7 +158,7 @@ RunSettings makeSettings(const std::string& config, const Args& args) {
         if (config == "preset_const_h") {
             settings.set(RunSettingsId::SPH_ADAPTIVE_SMOOTHING_LENGTH, EMPTY_FLAGS);
         }
-        if (config == "fluid") {
+        if (config == "fluid" || config == "gas") {
             settings.set(RunSettingsId::SPH_SOLVER_FORCES, ForceEnum::PRESSURE)
                 .set(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR, false);
         }
@@ -236,6 +236,19 @@ void makeStorage(const std::string& config, const Size n, const RunSettings& set
             .set(BodySettingsId::RHEOLOGY_YIELDING, YieldingEnum::NONE)
             .set(BodySettingsId::RHEOLOGY_DAMAGE, FractureEnum::NONE);
         ic.addMonolithicBody(storage, SphericalDomain(Vector(0._f), 5.e4_f), body);
+    } else if (config == "gas") {
+        // ideal gas ball (IdealGasEos::evaluate, core/physics/Eos.cpp:42-45), cf. the reference's gas-ball solver tests
+        // (core/sph/solvers/test/Solvers.cpp:41-76: Tests::getGassStorage)
+        body.set(BodySettingsId::PARTICLE_COUNT, int(n))
+            .set(BodySettingsId::EOS, EosEnum::IDEAL_GAS)
+            .set(BodySettingsId::ADIABATIC_INDEX, 1.4_f)
+            .set(BodySettingsId::DENSITY, 1._f)
+            .set(BodySettingsId::DENSITY_RANGE, Interval(1.e-3_f, INFTY))
+            .set(BodySettingsId::ENERGY, 1._f)
+            .set(BodySettingsId::ENERGY_RANGE, Interval(1.e-3_f, INFTY))
+            .set(BodySettingsId::RHEOLOGY_YIELDING, YieldingEnum::NONE)
+            .set(BodySettingsId::RHEOLOGY_DAMAGE, FractureEnum::NONE);
+        ic.addMonolithicBody(storage, SphericalDomain(Vector(0._f), 1._f), body);
     } else {
         throw std::runtime_error("unknown config " + config);
     }

@@ -10,10 +10,13 @@ $R snapshot --config hello            --n 500 --solver asym --jitter 7 --neighbo
 $R snapshot --config collision_preset --n 500 --jitter 3 --neighbours           --in collision_in.snap --out collision_out.snap --no-lut
 $R snapshot --config preset           --n 500 --neighbours                      --in preset_in.snap    --out preset_out.snap --no-lut
 $R snapshot --config fluid            --n 500 --jitter 5 --neighbours           --in fluid_in.snap     --out fluid_out.snap --no-lut
+# ideal gas ball (IdealGasEos, Eos.cpp:42-45)
+$R snapshot --config gas              --n 500 --jitter 9 --neighbours           --in gas_in.snap       --out gas_out.snap --no-lut
 # three full time steps (PredictorCorrector / EulerExplicit + MultiCriterion)
 $R snapshot --config collision_preset --n 500 --jitter 3 --steps 3 --out collision_pc3.snap --no-lut
 $R snapshot --config hello --n 500 --solver asym --jitter 7 --steps 3 --out hello_pc3.snap --no-lut
 $R snapshot --config fluid --n 500 --jitter 5 --steps 3 --integrator euler --out fluid_euler3.snap --no-lut
+$R snapshot --config gas --n 500 --jitter 9 --steps 3 --out gas_pc3.snap --no-lut
 # the library-default SymmetricSolver on the same input must agree with the asymmetric path (Solvers.cpp:178-216)
 $R snapshot --config hello --n 500 --solver sym --jitter 7 --out hello_sym_out.snap --no-lut
 ls -la *.snap

@@ -46,7 +46,7 @@ def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=T
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
-@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid", "gas"])
 def test_integrate_matches_golden(name, variant, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
     eng, stats = gpu_integrate(i, abi.setup_from_snapshot(i, lut), variant)
@@ -54,7 +54,7 @@ def test_integrate_matches_golden(name, variant, lut):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid", "gas"])
 def test_neighbour_lists_bit_exact(name, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
     eng, _ = gpu_integrate(i, abi.setup_from_snapshot(i, lut))
@@ -64,7 +64,7 @@ def test_neighbour_lists_bit_exact(name, lut):
     eng.close()
 
 
-@pytest.mark.parametrize("name,integrator", [("collision_pc3", "pc"), ("hello_pc3", "pc"), ("fluid_euler3", "euler")])
+@pytest.mark.parametrize("name,integrator", [("collision_pc3", "pc"), ("hello_pc3", "pc"), ("fluid_euler3", "euler"), ("gas_pc3", "pc")])
 def test_time_steps_match_golden(name, integrator, lut):
     base = name.split("_")[0]
     i, o = golden(f"{base}_in.snap"), golden(f"{name}.snap")

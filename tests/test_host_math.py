@@ -26,7 +26,7 @@ def hostcheck():
 
 
 @pytest.mark.parametrize("masked", [0, 1])
-@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid", "gas"])
 def test_product_math_matches_golden(name, masked, hostcheck, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
     st = OraclePort(i, abi.setup_from_snapshot(i, lut))

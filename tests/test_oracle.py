@@ -32,7 +32,7 @@ def test_lut_matches_reference(lut):
     assert np.abs(val - lut["lut_val"]).max() <= 4e-16
 
 
-@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid", "gas"])
 def test_integrate_matches_golden(name, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
     orc = OraclePort(i, abi.setup_from_snapshot(i, lut))
@@ -40,7 +40,7 @@ def test_integrate_matches_golden(name, lut):
     check_integrate(i, o, orc)
 
 
-@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid"])
+@pytest.mark.parametrize("name", ["hello", "collision", "preset", "fluid", "gas"])
 def test_neighbour_sets_bit_exact(name, lut):
     i, o = golden(f"{name}_in.snap"), golden(f"{name}_out.snap")
     orc = OraclePort(i, abi.setup_from_snapshot(i, lut))
@@ -59,7 +59,7 @@ def test_symmetric_solver_agrees(lut):
         assert_close(k, orc.a[k], o[k], TOL, FLOOR)
 
 
-@pytest.mark.parametrize("name,integrator", [("collision_pc3", "pc"), ("hello_pc3", "pc"), ("fluid_euler3", "euler")])
+@pytest.mark.parametrize("name,integrator", [("collision_pc3", "pc"), ("hello_pc3", "pc"), ("fluid_euler3", "euler"), ("gas_pc3", "pc")])
 def test_time_steps_match_golden(name, integrator, lut):
     base = name.split("_")[0]
     i, o = golden(f"{base}_in.snap"), golden(f"{name}.snap")
