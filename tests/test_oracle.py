@@ -88,6 +88,8 @@ def test_time_steps_match_golden(name, integrator, lut):
     ["--config", "collision_preset", "--n", 3000, "--jitter", 15, "--continuity-undamaged"],
     ["--config", "collision_preset", "--n", 3000, "--jitter", 16, "--sum-all", "--corrected", 0],
     ["--config", "hello", "--n", 3000, "--solver", "asym", "--jitter", 17, "--const-h", "--corrected", 1],
+    ["--config", "collision_preset", "--n", 3000, "--jitter", 18, "--finder", "grid"],  # UniformGridFinder instead of KdTree
+    ["--config", "gas", "--n", 3000, "--jitter", 19],                                     # IdealGasEos
 ])
 def test_port_against_live_reference(args, tmp_path):
     i, o = run_ref(str(tmp_path), args)
