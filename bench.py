@@ -28,8 +28,9 @@ UNIT = "particle-updates/s"
 # Algorithmic HBM bytes per particle-update, SURVEY.md section 8(d), solid + correction tensor:
 BYTES_FULL_STEP = 1412.0      # full PredictorCorrector step
 BYTES_INTEGRATE = 628.0       # find + derivatives (integrate() only)
-FP64_INSTR_PER_PAIR = 102.0    # FP64 instructions of the pair body per neighbour pair (SASS count)
-BYTES_PAIR_KERNEL = 408.0     # dominant kernel, itemised in DESIGN.md section 3 (sorted record + epilogue inputs in, derivatives out)
+FP64_INSTR_PER_PAIR = 97.0     # FP64 instructions of the pair body per neighbour pair (SASS count)
+BYTES_PAIR_KERNEL = 392.0     # dominant kernel, itemised in DESIGN.md section 3 (sorted record + epilogue inputs in, derivatives out)
+DT_INITIAL, DT_MAX = 0.01, 10.0  # TIMESTEPPING_INITIAL_TIMESTEP / MAX_TIMESTEP of the collision preset (oracle/ref_driver.cpp)
 
 
 def read_traffic():
@@ -151,6 +152,8 @@ def run_reference(args, n_sample: int):
         return None
     cmd = [exe, "bench", "--config", "preset", "--n", str(n_sample), "--steps", str(args.steps), "--warmup",
            str(max(args.warmup, 1)), "--threads", "0"]
+    if getattr(args, "dt_mode", "criteria") == "fixed":
+        cmd += ["--fixed-dt", "1e-6"]
     out = subprocess.check_output(cmd, text=True)
     return json.loads(out.strip().splitlines()[-1])
 
@@ -159,7 +162,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = min(args.n, 1_000_000)
+    n_sample = args.n if args.full_reference else min(args.n, 1_000_000)
     t0 = time.time()
     r = run_reference(args, n_sample)
     if r is None:
@@ -173,7 +176,8 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"collision_preset_{args.n}", "sample_particles": r["particles"], "finder": "kd_tree",
-                   "threads": r["threads"]},
+                   "threads": r["threads"], "same_config": bool(n_sample == args.n),
+                   "dt": "chosen by the preset's criteria (Courant + divergence)" if args.dt_mode == "criteria" else 1e-6},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
@@ -197,6 +201,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fluid", action="store_true", help="fluid-only terms (BASELINE configs[4])")
+    ap.add_argument("--dt-mode", choices=["criteria", "fixed"], default="criteria",
+                    help="criteria: the step the preset's criteria choose (particles move); fixed: dt = 1e-6 (static lattice)")
+    ap.add_argument("--list-skin", type=float, default=None, help="skin of the candidate-list reuse (0: rebuild every step)")
+    ap.add_argument("--full-reference", action="store_true", help="--impl reference at the full particle count (minutes)")
+    ap.add_argument("--weak", action="store_true", help="--particles is the count PER GPU (weak scaling, BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -220,15 +229,21 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     solid = not args.fluid
-    dt = 1.0e-6  # tiny fixed step: the lattice stays intact, every step does the same work (same as sph_ref bench)
+    if args.dt_mode == "fixed":
+        dt0 = dt_max = 1.0e-6  # tiny fixed step: the lattice stays intact, every step does the same work
+    else:
+        dt0, dt_max = DT_INITIAL, DT_MAX  # first step, then whatever the preset's criteria choose (same as sph_ref bench)
+    n_lattice = args.n * world if args.weak else args.n
 
     # ---- workload -------------------------------------------------------------------------------------------
-    dom = decomp.SlabDomain(args.n, world, rank, solid=solid)
+    dom = decomp.SlabDomain(n_lattice, world, rank, solid=solid)
     state = dom.generate_owned()
     n_owned = len(state["mass"])
     setup = workloads.make_setup(n_owned, solid=solid)
     eng = Engine(setup, n_owned, capacity=dom.capacity(n_owned), device=local)
     eng.set_variant(args.variant)
+    if args.list_skin is not None:
+        eng.set_list_skin(args.list_skin)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     eng.upload_state(state, STATE_NAMES)
     halo = decomp.HaloExchange(dom, eng, state) if world > 1 else None
@@ -239,21 +254,27 @@ def main():
         if world > 1:
             dist.barrier()
 
+    cur = {"dt": dt0}  # the step the next call uses: fed back from the criteria
+
     def one_step():
+        dt = cur["dt"]
         if halo is None:
-            return eng.step_pc(dt, dt)
-        if halo.native:
+            r = eng.step_pc(dt, dt_max)
+        elif halo.native:
             # predict -> NCCL halo exchange -> integrate -> correct -> criteria -> allreduce(min dt), one host sync
-            return eng.step_pc_mgpu(dt, dt)
-        # multi-GPU without the native path: ghosts must carry the PREDICTED state, so the step is issued in its parts
-        eng.predict(dt)
-        halo.exchange()
-        st = eng.integrate()
-        eng.correct(dt)
-        new_dt, crit = eng.compute_timestep(dt)
-        t = torch.tensor([new_dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # global time step = min over ranks
-        return float(t.item()), crit, st
+            r = eng.step_pc_mgpu(dt, dt_max)
+        else:
+            # multi-GPU without the native path: ghosts must carry the PREDICTED state, so the step is issued in its parts
+            eng.predict(dt)
+            halo.exchange()
+            st = eng.integrate()
+            eng.correct(dt)
+            new_dt, crit = eng.compute_timestep(dt_max)
+            t = torch.tensor([new_dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # global time step = min over ranks
+            r = (float(t.item()), crit, st)
+        cur["dt"] = r[0]
+        return r
 
     for _ in range(args.warmup):
         one_step()
@@ -265,34 +286,53 @@ def main():
     pair_ms, launches, timings, halo_ms, pair_parts = 0.0, 0, np.zeros(4), 0.0, np.zeros(3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     batched = halo is None or halo.native  # the K steps are queued back to back, dt stays on the device (sphgpu_run_pc)
+    builds0 = eng.list_stats()[0]
     barrier()
     t0 = time.perf_counter()
     ev0.record()
     if batched:
-        _, _, st = eng.run_pc(args.steps, dt, dt)
-        tm = eng.last_timings()  # CUDA-event times of the last step of the batch
-        timings += tm * args.steps
-        pair_ms += tm[2] * args.steps
-        pair_parts += eng.last_pair_timings() * args.steps
+        dts, _, st = eng.run_pc(args.steps, cur["dt"], dt_max)
+        cur["dt"] = float(dts[-1])
         launches += st.kernel_launches * args.steps
-        if halo is not None:
-            halo_ms += eng.last_halo_ms() * args.steps
     else:
         for _ in range(args.steps):
             _, _, st = one_step()
-            tm = eng.last_timings()
-            timings += tm
-            pair_ms += tm[2]
-            pair_parts += eng.last_pair_timings()
             launches += st.kernel_launches
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
     dev_s = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
+    list_builds = eng.list_stats()[0] - builds0  # steps of the timed region that rebuilt cell list + candidate lists
     neigh_mean = st.neigh_mean
     pairs_per_step = float(st.pair_count)
+    dt_last = cur["dt"]
+
+    # ---- phase breakdown (not timed above): the same K steps again, one call each, CUDA events of every step -------
+    # (with list reuse the steps differ: most skip the cell-list / unit / candidate-list build)
+    phase_builds0 = eng.list_stats()[0]
+    for _ in range(args.steps):
+        one_step()
+        tm = eng.last_timings()
+        timings += tm
+        pair_ms += tm[2]
+        pair_parts += eng.last_pair_timings()
+        if halo is not None:
+            halo_ms += eng.last_halo_ms()
+    phase_builds = eng.list_stats()[0] - phase_builds0
     fp64_peak = eng.measure_fp64_peak() if rank == 0 else 0.0
+
+    # ---- parity fields: invariants that must not depend on the number of ranks -----------------------------------
+    # global pair count of the last step and a checksum of the accelerations: sum_i w_i a_i over all owned particles, with
+    # weights in [0.5, 1.5) keyed by the particle's INITIAL lattice position (the same on every decomposition)
+    acc = eng.download_state(["acc"])["acc"][:n_owned, :3]
+    h_lat = dom.h / workloads.BASALT["eta"]
+    wgt = 0.5 + workloads._hash01(state["pos"][:n_owned, :3], 0.05 * h_lat, 77, 3)
+    par = torch.tensor([float(st.pair_count)] + [float(np.sum(wgt * acc[:, k])) for k in range(3)] +
+                       [float(np.sum(np.abs(acc[:, k]))) for k in range(3)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(par, op=dist.ReduceOp.SUM)
+    par = par.tolist()
 
     tsec = torch.tensor([max(wall, dev_s)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -344,21 +384,30 @@ def main():
     # the dominant kernel is k_pair_sum (FP64 pair sums); the other variants run everything in one kernel
     sum_ms = pair_parts[2] if pair_parts[2] > 0 else pair_ms
     pair_s = sum_ms * 1e-3 / args.steps
-    bytes_pair = (BYTES_PAIR_KERNEL if solid else 230.0) * n_owned
+    bytes_pair = (BYTES_PAIR_KERNEL if solid else 222.0) * n_owned
     achieved = bytes_pair / pair_s / 1e9 if pair_s > 0 else 0.0
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": ("fluid_" if args.fluid else "collision_preset_") + str(args.n), "particles": int(n_total),
+        "config": {"workload": ("fluid_" if args.fluid else "collision_preset_") + str(n_lattice), "particles": int(n_total),
                    "particles_per_gpu": int(n_owned), "mean_neighbours": round(float(neigh_mean), 2), "integrator": "predictor_corrector",
-                   "dt": dt, "l2": "inputs larger than L2 (state %.1f GB per GPU)" % (n_owned * 464 / 1e9),
+                   "dt": ("chosen by the preset's criteria (Courant + divergence), initial %g, max %g; last step %.4g s" % (dt0, dt_max, dt_last))
+                   if args.dt_mode == "criteria" else dt0,
+                   "list_reuse": {"skin": args.list_skin if args.list_skin is not None else 0.03, "builds_in_timed_steps": int(list_builds),
+                                  "note": "cell list / work units / candidate lists are rebuilt when the device-side displacement "
+                                          "check says so; every step applies the exact neighbour predicate"},
+                   "l2": "inputs larger than L2 (state %.1f GB per GPU)" % (n_owned * 480 / 1e9),
                    "decomposition": "z-slabs of equal particle count + NCCL halo exchange inside the step" if world > 1 else "single domain",
                    "stepping": "sphgpu_run_pc: K steps queued back to back, time step fed back on the device, one host sync" if batched
                    else "one call and one host sync per step",
                    "pair_variant": args.variant},
         "clocks": clocks,
         "gpu_launches": int(launches),
+        "parity": {"pair_count_global": int(round(par[0])), "acc_checksum": [par[1], par[2], par[3]],
+                   "acc_abs_sum": [par[4], par[5], par[6]],
+                   "note": "after warm-up + 2 x steps PredictorCorrector steps; must agree across --gpus N (pair count exactly, checksum to "
+                           "1e-10 of acc_abs_sum)"},
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": "k_pair_sum (list-driven FP64 pair sums + finalizers)" if pair_parts[2] > 0 else
                      "k_pair (fused neighbour search + pair sums + finalizers)",
@@ -375,7 +424,8 @@ def main():
                      "note": "pair kernel is FP64-pipe / latency bound, see DESIGN.md; step_hbm_frac uses SURVEY 8(d)'s 1412 B/particle"},
         "integrate_only": {"value": n_owned / (max(timings[0] + timings[1] + timings[2], 1e-9) * 1e-3 / args.steps), "unit": UNIT,
                            "note": "find + derivatives + finalize of this rank (ISolver::integrate alone), device time"},
-        "phase_ms": {"grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
+        "phase_ms": {"note": "mean over %d steps run one call at a time after the timed region; %d of them rebuilt the lists" % (args.steps, phase_builds),
+                     "grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
                      "pair_stage": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps,
                      "pair_stage_parts": {"units_and_lane_order": pair_parts[0] / args.steps, "k_pair_lists": pair_parts[1] / args.steps,
                                           "k_pair_sum": pair_parts[2] / args.steps}},
@@ -385,7 +435,7 @@ def main():
                               "rows": per_rank}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference(argparse.Namespace(steps=2, warmup=1, n=args.n), min(args.n, 1_000_000))
+            r = run_reference(argparse.Namespace(steps=2, warmup=1, n=args.n, dt_mode=args.dt_mode), min(args.n, 1_000_000))
             if r is not None:
                 out["cpu_baseline"] = {
                     "value": r["particle_updates_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",

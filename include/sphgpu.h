@@ -271,6 +271,15 @@ SPHGPU_API int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles);
  * per-thread kernel, 2 = tiled kernel with both phases fused, 3 = as 0 with a tiny list pool (exercises the overflow
  * path). For A/B checks only. */
 SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
+/* Reuse of the cell list / work units / candidate lists over several steps (the reference rebuilds its finder in every
+ * ISolver::integrate, AsymmetricSolver.cpp:81-84; results do not depend on this setting beyond summation order, because
+ * the exact neighbour predicate of AsymmetricSolver.cpp:186-191 is evaluated for every listed candidate in every step).
+ * The lists are built with the search radius enlarged by (1 + skin) and rebuilt -- decided on the device, no host round
+ * trip -- once 2 max|r - r_build| / (R h_build) + max(h / h_build - 1) reaches 0.9 skin. skin = 0 rebuilds every call.
+ * Default 0.03. sphgpu_list_stats: builds so far, calls served by the current lists, the metric seen by the last call
+ * (values as of the last call that synchronised with the device). */
+SPHGPU_API int sphgpu_set_list_skin(sphgpu_ctx* ctx, double skin);
+SPHGPU_API int sphgpu_list_stats(sphgpu_ctx* ctx, uint32_t* rebuilds, uint32_t* age, double* metric);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
  * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the
  * caller's own work -- NCCL halo exchange, torch.cuda.Event timing -- is ordered with the engine's kernels.

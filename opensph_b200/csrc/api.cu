@@ -100,6 +100,9 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     if (rc != SPHGPU_OK) {
         return rc;
     }
+    if (capacity >= (1u << 30)) {
+        return fail(SPHGPU_E_INVALID, "capacity must be below 2^30 particles per device");
+    }
     int devCount = 0;
     if (cudaGetDeviceCount(&devCount) != cudaSuccess || devCount == 0) {
         cudaGetLastError();
@@ -129,6 +132,8 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     p.q_sqr_to_idx = (double)cfg->lut_entries * (1. / (cfg->kernel_radius * cfg->kernel_radius)); // Kernel.h:88-90
     p.av_alpha = cfg->av_alpha;
     p.av_beta = cfg->av_beta;
+    p.av_minus_half_alpha = -0.5 * cfg->av_alpha;
+    p.av_eps_over_radius_sqr = 1.e-2 / (cfg->kernel_radius * cfg->kernel_radius);
     p.h_min = cfg->h_min;
     p.h_max = cfg->h_max;
     p.neigh_enforcing = cfg->neigh_enforcing;
@@ -170,9 +175,6 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         return fail(SPHGPU_E_INVALID, "ContinuityEnum::SUM_ONLY_UNDAMAGED needs STRESS_REDUCING (a rheology)");
     }
 
-    if (capacity >= (1u << 30)) {
-        return fail(SPHGPU_E_INVALID, "capacity must be below 2^30 particles per device");
-    }
     const size_t cap = capacity;
     ctx->maxCells = std::max<uint32_t>(capacity / 4, 4096u);
     ctx->scanBlocks = (ctx->maxCells + 1 + SCAN_ITEMS - 1) / SCAN_ITEMS;
@@ -221,6 +223,8 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     ctx->d.dtDev = nullptr;
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
     SPH_TRY(devAlloc(&ctx->d.posF, cap));
+    SPH_TRY(devAlloc(&ctx->d.pos0, cap));
+    SPH_TRY(devAlloc(&ctx->d.listCtl, 1));
     SPH_TRY(devAlloc(&ctx->d.cellHmax, (size_t)ctx->maxCells + 1));
     SPH_TRY(devAlloc(&ctx->d.order, cap));
     SPH_TRY(devAlloc(&ctx->d.cellOf, cap));
@@ -228,14 +232,27 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     SPH_TRY(devAlloc(&ctx->d.cellStart, (size_t)ctx->maxCells + 2));
     SPH_TRY(devAlloc(&ctx->d.cellCount, (size_t)ctx->maxCells + 2));
     SPH_TRY(devAlloc(&ctx->d.scanBlock, (size_t)ctx->scanBlocks + 1));
-    SPH_TRY(devAlloc(&ctx->d.boundsPartial, (size_t)BOUNDS_BLOCKS * 8));
+    SPH_TRY(devAlloc(&ctx->d.boundsPartial, (size_t)BOUNDS_BLOCKS * BOUNDS_STRIDE));
     SPH_TRY(devAlloc(&ctx->d.grid, 1));
     SPH_TRY(devAlloc(&ctx->d.stats, 1));
+    SPH_TRY(devAlloc(&ctx->d.statsInit, 1));
+    {
+        const StatsDev init = { 0xffffffffu, 0u, 0ull, 0u, 0u };
+        SPH_TRY(wrap(cudaMemcpy(ctx->d.statsInit, &init, sizeof(init), cudaMemcpyHostToDevice), "init"));
+    }
     SPH_TRY(devAlloc(&ctx->d.tsd, 1));
     double* lut = nullptr;
     SPH_TRY(devAlloc(&lut, (size_t)cfg->lut_entries + 2));
     ctx->d.lut = lut;
     SPH_TRY(wrap(cudaMemcpy(lut, cfg->lut_grad, sizeof(double) * ((size_t)cfg->lut_entries + 1), cudaMemcpyHostToDevice), "LUT upload"));
+    {
+        std::vector<LutPair> pairs((size_t)cfg->lut_entries + 1);
+        buildLutPairs(cfg->lut_grad, cfg->lut_entries, pairs.data());
+        LutPair* lut2 = nullptr;
+        SPH_TRY(devAlloc(&lut2, pairs.size()));
+        ctx->d.lut2 = lut2;
+        SPH_TRY(wrap(cudaMemcpy(lut2, pairs.data(), sizeof(LutPair) * pairs.size(), cudaMemcpyHostToDevice), "LUT upload"));
+    }
     SPH_TRY(wrap(cudaMalloc(&ctx->staging, std::max<size_t>(cap, 1) * 64), "staging"));
     // identity correction tensor and reduce = 1 by default (SolidStressForce::create, EquationTerm.cpp:215-218)
     {
@@ -268,10 +285,10 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc); cudaFree(ctx->d.unitAux); cudaFree(ctx->d.unitLane); cudaFree(ctx->d.unitList);
     cudaFree(ctx->d.listPool); cudaFree(ctx->d.listCursor); cudaFree(ctx->d.stepState);
-    cudaFree(ctx->d.posF); cudaFree(ctx->d.cellHmax);
+    cudaFree(ctx->d.posF); cudaFree(ctx->d.pos0); cudaFree(ctx->d.listCtl); cudaFree(ctx->d.cellHmax);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
-    cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree(ctx->staging);
+    cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.statsInit); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree((void*)ctx->d.lut2); cudaFree(ctx->staging);
     for (int k = 0; k < 8; ++k) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
         if (k < 4 && ctx->evPair[k]) cudaEventDestroy(ctx->evPair[k]);
@@ -360,6 +377,9 @@ int sphgpu_set_active(sphgpu_ctx* ctx, uint32_t n_active) {
     if (n_active < ctx->n || n_active > ctx->capacity) {
         return fail(SPHGPU_E_INVALID, "active count must be in [n_particles, capacity]");
     }
+    if (ctx->nActive != n_active) {
+        ctx->listsDirty = true; // the candidate lists were built for another set of particles
+    }
     ctx->nActive = n_active;
     return SPHGPU_OK;
 }
@@ -373,12 +393,32 @@ int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles) {
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->n = n_particles;
     ctx->nActive = n_particles; // ghosts are dropped; the caller appends them again (sphgpu_set_active)
+    ctx->listsDirty = true;
     return SPHGPU_OK;
 }
 
 int sphgpu_set_variant(sphgpu_ctx* ctx, int variant) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (ctx->variant != variant) {
+        ctx->listsDirty = true; // variant 3 builds its lists against a different pool size
+    }
     ctx->variant = variant;
+    return SPHGPU_OK;
+}
+
+int sphgpu_set_list_skin(sphgpu_ctx* ctx, double skin) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (!(skin >= 0.) || skin > 0.5) return fail(SPHGPU_E_INVALID, "list skin must be in [0, 0.5]");
+    ctx->listSkin = skin;
+    ctx->listsDirty = true;
+    return SPHGPU_OK;
+}
+
+int sphgpu_list_stats(sphgpu_ctx* ctx, uint32_t* rebuilds, uint32_t* age, double* metric) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (rebuilds) *rebuilds = ctx->listRebuilds;
+    if (age) *age = ctx->listAge;
+    if (metric) *metric = ctx->listMetric;
     return SPHGPU_OK;
 }
 
@@ -413,6 +453,7 @@ namespace sph {
 int enqueueIntegrate(sphgpu_ctx* ctx) {
     int rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->d.stats, ctx->d.statsInit, sizeof(StatsDev), cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = launchGridBuild(ctx)) != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((rc = launchProloguePack(ctx)) != SPHGPU_OK) return rc;
@@ -424,8 +465,14 @@ int enqueueIntegrate(sphgpu_ctx* ctx) {
 
 int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEvent_t end) {
     StatsDev sd;
+    ListCtlDev lc;
     SPH_CUDA_CHECK(cudaMemcpyAsync(&sd, ctx->d.stats, sizeof(sd), cudaMemcpyDeviceToHost, ctx->stream));
+    SPH_CUDA_CHECK(cudaMemcpyAsync(&lc, ctx->d.listCtl, sizeof(lc), cudaMemcpyDeviceToHost, ctx->stream));
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    sd.fallbackUnits = lc.fallbackUnits;
+    ctx->listRebuilds = lc.rebuilds;
+    ctx->listAge = lc.age;
+    ctx->listMetric = lc.lastMetric;
     float ms = 0.f;
     for (int k = 0; k < 3; ++k) {
         SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]));
@@ -449,9 +496,13 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
             cudaFree(ctx->d.listPool);
             ctx->d.listPool = bigger;
             ctx->poolRows = grown;
+            ctx->listsDirty = true; // the lists lived in the old pool
         } else {
             cudaGetLastError(); // out of memory: keep the pool, the fused path stays correct
         }
+    }
+    if (sd.badFlags > 0) {
+        return fail(SPHGPU_E_INVALID, "body flags must be below 254 on the solid GPU path (group field of the neighbour record)");
     }
     if (stats) {
         stats->neigh_min = ctx->n ? sd.neighMin : 0;
@@ -611,8 +662,10 @@ int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_t* idx, uin
     SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
     int rc;
     // uses the cell list and sorted planes of the current positions
+    ctx->listsDirty = true;
     if ((rc = launchGridBuild(ctx)) != SPHGPU_OK) return rc;
     if ((rc = launchProloguePackPositionsOnly(ctx)) != SPHGPU_OK) return rc;
+    ctx->listsDirty = true; // the work units and candidate lists no longer match the rebuilt cell list
     const uint32_t n = ctx->n;
     uint32_t* countsDev = nullptr;
     SPH_CUDA_CHECK(cudaMalloc(&countsDev, sizeof(uint32_t) * std::max<uint32_t>(n, 1)));

@@ -25,9 +25,13 @@ __device__ __forceinline__ double warpMax(double v) {
     return v;
 }
 
-// AdaptiveSmoothingLength::initialize (h clamp, EquationTerm.cpp:356-364) fused with the bounding-box / h_max pass.
-__global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax) {
+// AdaptiveSmoothingLength::initialize (h clamp, EquationTerm.cpp:356-364) fused with the bounding-box / h_max pass and
+// with the displacement check of the list reuse (ListCtlDev): how far every particle has moved, relative to R h, and how
+// much its h has grown since the lists were built.
+__global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax, double kernelRadius) {
     double lo[3] = { INFTY_REF, INFTY_REF, INFTY_REF }, hi[3] = { -INFTY_REF, -INFTY_REF, -INFTY_REF }, hm = 0.;
+    double ratio2 = 0., grow = 0.;
+    const double gx = d.grid->lo[0], gy = d.grid->lo[1], gz = d.grid->lo[2]; // origin of the grid the lists were built on
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nActive; i += gridDim.x * blockDim.x) {
         double h = d.f[F_H][i];
         if (clampH) {
@@ -45,56 +49,80 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
         hi[1] = fmax(hi[1], y);
         hi[2] = fmax(hi[2], z);
         hm = fmax(hm, h);
+        const float4 p0 = d.pos0[i];
+        const double ex = (x - gx) - (double)p0.x, ey = (y - gy) - (double)p0.y, ez = (z - gz) - (double)p0.z;
+        const double rh0 = kernelRadius * (double)p0.w;
+        ratio2 = fmax(ratio2, (ex * ex + ey * ey + ez * ez) / (rh0 * rh0));
+        grow = fmax(grow, h / (double)p0.w - 1.);
     }
-    __shared__ double sm[8][7];
+    __shared__ double sm[8][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double v[7] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm) };
+    double v[9] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm),
+        warpMax(ratio2), warpMax(grow) };
     if (lane == 0) {
-        for (int k = 0; k < 7; ++k) {
+        for (int k = 0; k < 9; ++k) {
             sm[warp][k] = v[k];
         }
     }
     __syncthreads();
-    if (threadIdx.x < 7) {
+    if (threadIdx.x < 9) {
         const int k = threadIdx.x;
         double r = sm[0][k];
         for (int w = 1; w < 8; ++w) {
             r = (k < 3) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
         }
-        d.boundsPartial[blockIdx.x * 8 + k] = r;
+        d.boundsPartial[blockIdx.x * BOUNDS_STRIDE + k] = r;
     }
 }
 
-__global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPartials, double kernelRadius, uint32_t maxCells) {
-    __shared__ double sm[8][7];
-    double v[7] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0. };
+/// Reduces the partial bounds, decides whether this integrate() rebuilds the cell list / units / candidate lists (force,
+/// or the displacement metric has used up the skin; the margin covers the FP32 rounding of pos0) and, if so, sets up the
+/// new grid. Every later build kernel reads ListCtlDev::rebuild and returns at once when it is 0.
+__global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPartials, double kernelRadius, uint32_t maxCells, bool force,
+    double skin) {
+    __shared__ double sm[8][9];
+    double v[9] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0., 0., 0. };
     for (int b = threadIdx.x; b < nPartials; b += blockDim.x) {
-        for (int k = 0; k < 7; ++k) {
-            const double p = d.boundsPartial[b * 8 + k];
+        for (int k = 0; k < 9; ++k) {
+            const double p = d.boundsPartial[b * BOUNDS_STRIDE + k];
             v[k] = (k < 3) ? fmin(v[k], p) : fmax(v[k], p);
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = 0; k < 7; ++k) {
+    for (int k = 0; k < 9; ++k) {
         v[k] = (k < 3) ? warpMin(v[k]) : warpMax(v[k]);
     }
     if (lane == 0) {
-        for (int k = 0; k < 7; ++k) {
+        for (int k = 0; k < 9; ++k) {
             sm[warp][k] = v[k];
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 7; ++k) {
+        for (int k = 0; k < 9; ++k) {
             double r = sm[0][k];
             for (int w = 1; w < 8; ++w) {
                 r = (k < 3) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
             }
             v[k] = r;
         }
+        ListCtlDev ctl = *d.listCtl;
+        const double metric = 2. * sqrt(v[7]) + fmax(v[8], 0.);
+        ctl.lastMetric = metric;
+        const bool rebuild = force || !(metric < 0.9 * skin);
+        ctl.rebuild = rebuild ? 1u : 0u;
+        if (!rebuild) {
+            ctl.age++;
+            *d.listCtl = ctl;
+            return;
+        }
+        ctl.age = 0u;
+        ctl.rebuilds++;
+        ctl.fallbackUnits = 0u;
+        *d.listCtl = ctl;
         GridDev g;
         g.hmax = v[6];
-        double cell = kernelRadius * v[6] * (1. + 1.e-6);
+        double cell = kernelRadius * v[6] * (1. + 1.e-6) * (1. + skin);
         if (!(cell > 0.)) {
             cell = 1.;
         }
@@ -141,7 +169,7 @@ __device__ __forceinline__ uint32_t cellIndex(const GridDev& g, double x, double
 
 __global__ void __launch_bounds__(256) k_cell_count(DevicePointers d, uint32_t nActive) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nActive) {
+    if (i >= nActive || d.listCtl->rebuild == 0u) {
         return;
     }
     const GridDev g = *d.grid;
@@ -152,9 +180,12 @@ __global__ void __launch_bounds__(256) k_cell_count(DevicePointers d, uint32_t n
 
 // ---- exclusive scan of cellCount[0..total) into cellStart, three passes -----------------------------------
 __global__ void __launch_bounds__(512) k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-    uint32_t* __restrict__ blockSums, uint32_t total) {
+    uint32_t* __restrict__ blockSums, uint32_t total, const ListCtlDev* ctl) {
     // each thread owns 8 consecutive items
     __shared__ uint32_t warpSums[16];
+    if (ctl->rebuild == 0u) {
+        return;
+    }
     const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
     uint32_t v[8];
     uint32_t sum = 0;
@@ -201,10 +232,13 @@ __global__ void __launch_bounds__(512) k_scan_block(const uint32_t* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* blockSums, uint32_t nBlocks) {
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* blockSums, uint32_t nBlocks, const ListCtlDev* ctl) {
     // single block, sequential over chunks of 1024
     __shared__ uint32_t warpSums[32];
     __shared__ uint32_t carry;
+    if (ctl->rebuild == 0u) {
+        return;
+    }
     if (threadIdx.x == 0) {
         carry = 0;
     }
@@ -247,7 +281,11 @@ __global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* blockSums, uint32_
     }
 }
 
-__global__ void __launch_bounds__(512) k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ blockSums, uint32_t total) {
+__global__ void __launch_bounds__(512) k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ blockSums, uint32_t total,
+    const ListCtlDev* ctl) {
+    if (ctl->rebuild == 0u) {
+        return;
+    }
     const uint32_t base = blockIdx.x * SCAN_ITEMS + threadIdx.x * 8;
     const uint32_t add = blockSums[blockIdx.x];
 #pragma unroll
@@ -260,7 +298,7 @@ __global__ void __launch_bounds__(512) k_scan_add(uint32_t* __restrict__ out, co
 
 __global__ void __launch_bounds__(256) k_scatter(DevicePointers d, uint32_t nActive) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nActive) {
+    if (i >= nActive || d.listCtl->rebuild == 0u) {
         return;
     }
     d.order[d.cellStart[d.cellOf[i]] + d.rank[i]] = i;
@@ -273,7 +311,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevicePointers d, uint32_t nAct
 constexpr int SORT_LOCAL = 48;
 __global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t maxCells) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= maxCells) {
+    if (c >= maxCells || d.listCtl->rebuild == 0u) {
         return;
     }
     if (c >= d.grid->ncells) {
@@ -335,17 +373,19 @@ int launchGridBuild(sphgpu_ctx* ctx) {
     const uint32_t n = ctx->nActive;
     cudaStream_t st = ctx->stream;
     const bool clampH = (ctx->prm.flags & SPHGPU_FLAG_ADAPTIVE_H) != 0;
-    k_bounds<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n, clampH, ctx->prm.h_min, ctx->prm.h_max);
-    k_grid_params<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, ctx->prm.kernel_radius, ctx->maxCells);
+    k_bounds<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n, clampH, ctx->prm.h_min, ctx->prm.h_max, ctx->prm.kernel_radius);
+    const bool force = ctx->listsDirty || !(ctx->listSkin > 0.);
+    k_grid_params<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, ctx->prm.kernel_radius, ctx->maxCells, force, ctx->listSkin);
+    ctx->listsDirty = false;
     SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.cellCount, 0, sizeof(uint32_t) * (ctx->maxCells + 1), st));
     const uint32_t blocks = (n + 255) / 256;
     if (blocks > 0) {
         k_cell_count<<<blocks, 256, 0, st>>>(ctx->d, n);
     }
     const uint32_t total = ctx->maxCells + 1;
-    k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.cellStart, ctx->d.scanBlock, total);
-    k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks);
-    k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellStart, ctx->d.scanBlock, total);
+    k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.cellStart, ctx->d.scanBlock, total, ctx->d.listCtl);
+    k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks, ctx->d.listCtl);
+    k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellStart, ctx->d.scanBlock, total, ctx->d.listCtl);
     if (blocks > 0) {
         k_scatter<<<blocks, 256, 0, st>>>(ctx->d, n);
     }

@@ -68,21 +68,35 @@ __global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_
     const double m = d.f[F_M][i];
     constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
     double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * RD);
+    const uint32_t sw = SOLID ? (t & 7u) : 0u; // XOR swizzle of the solid record's pieces (sphgpu_internal.h)
     const double x = d.f[F_X][i], y = d.f[F_Y][i], z = d.f[F_Z][i], h = d.f[F_H][i];
-    rec[0] = make_double2(x, y);
-    rec[1] = make_double2(z, h);
-    d.posF[t] = gridRelative(*d.grid, x, y, z, h);
-    rec[2] = make_double2(d.f[F_VX][i], d.f[F_VY][i]);
-    rec[3] = make_double2(d.f[F_VZ][i], m);
-    rec[4] = make_double2(rho, p * rhoInv2);
-    rec[5] = make_double2(cs, m / rho);
-    if (SOLID) {
-        rec[6] = make_double2(S[0] * rhoInv2, S[1] * rhoInv2);
-        rec[7] = make_double2(S[2] * rhoInv2, S[3] * rhoInv2);
-        const int grp = (hasReduce && reduce == 0.) ? -1 : (int)d.u[U_FLAG][i];
-        rec[8] = make_double2(S[4] * rhoInv2, __hiloint2double(0, grp));
+    rec[0 ^ sw] = make_double2(x, y);
+    rec[1 ^ sw] = make_double2(z, h);
+    const bool rebuild = d.listCtl->rebuild != 0u; // the lists are being rebuilt: new FP32 copies for the search ...
+    if (rebuild) {
+        const float4 pf = gridRelative(*d.grid, x, y, z, h);
+        d.posF[t] = pf;
+        d.pos0[i] = pf; // ... and the reference point of the displacement check (k_bounds)
     }
-    d.sCell[t] = d.cellOf[i];
+    rec[2 ^ sw] = make_double2(d.f[F_VX][i], d.f[F_VY][i]);
+    rec[3 ^ sw] = make_double2(d.f[F_VZ][i], rho);
+    if (SOLID) {
+        const uint32_t flag = d.u[U_FLAG][i];
+        if (flag >= GROUP_FLAG_LIMIT) {
+            atomicAdd(&d.stats->badFlags, 1u);
+        }
+        const int grp = (hasReduce && reduce == 0.) ? -1 : (int)flag;
+        rec[4 ^ sw] = make_double2(p * rhoInv2, packCsGroup(cs, grp));
+        rec[5 ^ sw] = make_double2(m / rho, S[0] * rhoInv2);
+        rec[6 ^ sw] = make_double2(S[1] * rhoInv2, S[2] * rhoInv2);
+        rec[7 ^ sw] = make_double2(S[3] * rhoInv2, S[4] * rhoInv2);
+    } else {
+        rec[4] = make_double2(p * rhoInv2, cs);
+        rec[5] = make_double2(m / rho, 0.);
+    }
+    if (rebuild) {
+        d.sCell[t] = d.cellOf[i];
+    }
 }
 
 // Sorted positions only (neighbour-list inspection; does not touch the particle state).
@@ -93,31 +107,47 @@ __global__ void __launch_bounds__(256) k_pack_positions(DevicePointers d, uint32
     }
     const uint32_t i = d.order[t];
     double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * recDoubles);
-    rec[0] = make_double2(d.f[F_X][i], d.f[F_Y][i]);
-    rec[1] = make_double2(d.f[F_Z][i], d.f[F_H][i]);
+    const uint32_t sw = recDoubles == REC_SOLID ? (t & 7u) : 0u;
+    rec[0 ^ sw] = make_double2(d.f[F_X][i], d.f[F_Y][i]);
+    rec[1 ^ sw] = make_double2(d.f[F_Z][i], d.f[F_H][i]);
     d.sCell[t] = d.cellOf[i];
 }
 
-/// Unpacks one neighbour-input record (global or shared memory, 16-byte aligned).
+/// Unpacks one neighbour-input record (global or shared memory); `sw` = sorted (or staged) index & 7, the XOR swizzle of
+/// the solid record's pieces (ignored for fluid records).
 template <bool SOLID>
-__device__ __forceinline__ void loadRecord(const double* __restrict__ recPtr, Particle& p) {
+__device__ __forceinline__ void loadRecord(const double* __restrict__ recPtr, uint32_t sw, Particle& p) {
     const double2* r = reinterpret_cast<const double2*>(recPtr);
-    const double2 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
-    p.x = a.x; p.y = a.y; p.z = b.x; p.h = b.y;
-    p.vx = c.x; p.vy = c.y; p.vz = e.x; p.m = e.y;
-    p.rho = f.x; p.P = f.y; p.cs = g.x; p.vol = g.y;
     if (SOLID) {
-        const double2 s0 = r[6], s1 = r[7], s2 = r[8];
-        p.Sr[0] = s0.x; p.Sr[1] = s0.y; p.Sr[2] = s1.x; p.Sr[3] = s1.y; p.Sr[4] = s2.x;
-        p.grp = __double2loint(s2.y);
+        const double2 a = r[0 ^ sw], b = r[1 ^ sw], c = r[2 ^ sw], e = r[3 ^ sw], f = r[4 ^ sw], g = r[5 ^ sw], s1 = r[6 ^ sw],
+                      s2 = r[7 ^ sw];
+        p.x = a.x; p.y = a.y; p.z = b.x; p.h = b.y;
+        p.vx = c.x; p.vy = c.y; p.vz = e.x; p.rho = e.y;
+        p.P = f.x;
+        unpackCsGroup(f.y, p.cs, p.grp);
+        p.vol = g.x;
+        p.Sr[0] = g.y; p.Sr[1] = s1.x; p.Sr[2] = s1.y; p.Sr[3] = s2.x; p.Sr[4] = s2.y;
     } else {
+        const double2 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
+        p.x = a.x; p.y = a.y; p.z = b.x; p.h = b.y;
+        p.vx = c.x; p.vy = c.y; p.vz = e.x; p.rho = e.y;
+        p.P = f.x; p.cs = f.y; p.vol = g.x;
         p.grp = 0;
     }
+    p.m = p.vol * p.rho;
 }
 
 template <bool SOLID>
 __device__ __forceinline__ void loadSorted(const DevicePointers& d, uint32_t t, Particle& p) {
-    loadRecord<SOLID>(d.rec + (size_t)t * (SOLID ? REC_SOLID : REC_FLUID), p);
+    loadRecord<SOLID>(d.rec + (size_t)t * (SOLID ? REC_SOLID : REC_FLUID), t & 7u, p);
+}
+
+/// Position pieces {x, y}, {z, h} of the sorted record t.
+__device__ __forceinline__ void loadSortedPosition(const double* __restrict__ rec, uint32_t t, int recDoubles, double2& pxy, double2& pzh) {
+    const double2* r = reinterpret_cast<const double2*>(rec + (size_t)t * recDoubles);
+    const uint32_t sw = recDoubles == REC_SOLID ? (t & 7u) : 0u;
+    pxy = r[0 ^ sw];
+    pzh = r[1 ^ sw];
 }
 
 template <bool SOLID, bool CORRECTED>
@@ -159,58 +189,69 @@ __device__ __forceinline__ void neighbourStats(const DevicePointers& d, uint32_t
     }
 }
 
-// ---- variant 1: one thread per target, candidates streamed from the sorted planes through L1 -----------------
-// Simple and obviously correct; kept as the cross-check for the tiled variants.
+// ---- direct evaluation of one target: candidates streamed from the sorted records through L1 / L2 -------------------
+// Simple and obviously correct: the cross-check for the tiled kernels (variant 1) and the path of the work units whose
+// candidate lists did not fit the list pool (k_pair_fallback, pair_tiled.cu).
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t, uint32_t i) {
+    Accum acc;
+    accumZero(acc);
+    const GridDev g = *d.grid;
+    Particle pi;
+    loadSorted<SOLID>(d, t, pi);
+    const uint32_t c = d.sCell[t];
+    const int cx = (int)(c % (uint32_t)g.dim[0]);
+    const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+    const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
+    for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+            const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+            const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
+            for (uint32_t k = s; k < e; ++k) {
+                if (k == t) {
+                    continue;
+                }
+                double2 pxy, pzh;
+                loadSortedPosition(d.rec, k, RD, pxy, pzh);
+                const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
+                double d2, hbar;
+                if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
+                    continue;
+                }
+                Particle pj;
+                loadSorted<SOLID>(d, k, pj);
+                pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+            }
+        }
+    }
+    const MaterialDev& mat = c_mats[d.u[U_MATID][i]];
+    double S[5] = { 0., 0., 0., 0., 0. };
+    if (SOLID) {
+        for (int k = 0; k < 5; ++k) {
+            S[k] = d.f[F_S0 + k][i];
+        }
+    }
+    Derivs out;
+    finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][i], d.f[F_CS][i], SOLID ? d.f[F_REDUCE][i] : 1., S, out);
+    storeDerivs<SOLID, CORRECTED>(d, i, out);
+    // neighbour statistics (AsymmetricSolver.cpp:218-225); the callers' warps are divergent here, so plain atomics
+    atomicMin(&d.stats->neighMin, acc.cnt);
+    atomicMax(&d.stats->neighMax, acc.cnt);
+    atomicAdd(&d.stats->pairCount, (unsigned long long)acc.cnt);
+}
+
 template <bool SOLID, bool CORRECTED, bool FILTER>
 __global__ void __launch_bounds__(128) k_pair_direct(DevicePointers d, uint32_t nActive, uint32_t nOwned) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t < nActive;
-    const uint32_t i = live ? d.order[t] : 0xffffffffu;
-    const bool target = live && i < nOwned; // ghosts are neighbours only
-    Accum acc;
-    accumZero(acc);
-    if (target) {
-        const GridDev g = *d.grid;
-        Particle pi;
-        loadSorted<SOLID>(d, t, pi);
-        const uint32_t c = d.sCell[t];
-        const int cx = (int)(c % (uint32_t)g.dim[0]);
-        const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
-        const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-        for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
-                const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
-                for (uint32_t k = s; k < e; ++k) {
-                    if (k == t) {
-                        continue;
-                    }
-                    const double2* rk = reinterpret_cast<const double2*>(d.rec + (size_t)k * (SOLID ? REC_SOLID : REC_FLUID));
-                    const double2 pxy = rk[0], pzh = rk[1];
-                    const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
-                    double d2, hbar;
-                    if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
-                        continue;
-                    }
-                    Particle pj;
-                    loadSorted<SOLID>(d, k, pj);
-                    pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
-                }
-            }
-        }
-        const MaterialDev& mat = c_mats[d.u[U_MATID][i]];
-        double S[5] = { 0., 0., 0., 0., 0. };
-        if (SOLID) {
-            for (int k = 0; k < 5; ++k) {
-                S[k] = d.f[F_S0 + k][i];
-            }
-        }
-        Derivs out;
-        finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][i], pi.cs, SOLID ? d.f[F_REDUCE][i] : 1., S, out);
-        storeDerivs<SOLID, CORRECTED>(d, i, out);
+    if (t >= nActive) {
+        return;
     }
-    neighbourStats(d, acc.cnt, target);
+    const uint32_t i = d.order[t];
+    if (i < nOwned) { // ghosts are neighbours only
+        directTarget<SOLID, CORRECTED, FILTER>(d, t, i);
+    }
 }
 
 // ---- neighbour lists for the tests ---------------------------------------------------------------------------
@@ -226,8 +267,9 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint3
         return;
     }
     const GridDev g = *d.grid;
-    const double2* ri = reinterpret_cast<const double2*>(d.rec + (size_t)t * recDoubles);
-    const double xi = ri[0].x, yi = ri[0].y, zi = ri[1].x, hi = ri[1].y;
+    double2 ixy, izh;
+    loadSortedPosition(d.rec, t, recDoubles, ixy, izh);
+    const double xi = ixy.x, yi = ixy.y, zi = izh.x, hi = izh.y;
     const uint32_t c = d.sCell[t];
     const int cx = (int)(c % (uint32_t)g.dim[0]);
     const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
@@ -243,8 +285,8 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint3
                 if (k == t) {
                     continue;
                 }
-                const double2* rk = reinterpret_cast<const double2*>(d.rec + (size_t)k * recDoubles);
-                const double2 pxy = rk[0], pzh = rk[1];
+                double2 pxy, pzh;
+                loadSortedPosition(d.rec, k, recDoubles, pxy, pzh);
                 double d2, hbar;
                 if (!isNeighbour(xi - pxy.x, yi - pxy.y, zi - pzh.x, hi, pzh.y, c_prm.kernel_radius, d2, hbar)) {
                     continue;
@@ -290,9 +332,7 @@ int launchProloguePackPositionsOnly(sphgpu_ctx* ctx) {
 int launchPairTiled(sphgpu_ctx* ctx); // pair_tiled.cu
 
 int launchPair(sphgpu_ctx* ctx) {
-    const uint32_t n = ctx->nActive;
-    const StatsDev init = { 0xffffffffu, 0u, 0ull, 0u, 0u };
-    SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->d.stats, &init, sizeof(StatsDev), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t n = ctx->nActive; // (the statistics were reset at the start of enqueueIntegrate)
     if (n == 0) {
         return SPHGPU_OK;
     }

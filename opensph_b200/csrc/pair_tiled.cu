@@ -14,14 +14,16 @@
 //              completion on an mbarrier) stage the FP32 {x,y,z,h} copies of a chunk (relative to the grid origin, written
 //              by the prologue); every thread scans, per candidate row, the x-window IT can reach (interval culling in y
 //              and z, then bisection on x: cell rows are sorted by x, see k_sort_cells) with a conservative FP32 distance
-//              test and appends survivors to its u16 list; the lists of a chunk leave as one block of the list pool,
-//              blocks are chained per unit through descriptors.
-// Phase 2    = k_pair_sum (FP64 pipe, 8 warps per SM): follows the chains; per block TMA copies of the chunk's records
-//              (144-byte FP64 structures; odd 16-byte stride => consecutive records fall into different bank groups) and of
-//              the list block; every thread walks its list three entries at a time; the exact FP64 predicate
-//              (bit-identical neighbour sets) enters the branch-free FP64 pair body as a mask.
-// k_pair_tiled runs both phases in one kernel (the first design): used for units whose lists overflow the pool and as a
-// cross-check (variant 2).
+//              test and appends survivors to its u16 list. The list is then SCHEDULED against shared-memory bank
+//              conflicts of phase 2 (entry q of lane l prefers a candidate whose staged index is q + l mod 8, see
+//              scheduleList) and leaves as one block of the list pool; blocks are chained per unit through descriptors.
+// Phase 2    = k_pair_sum (FP64 pipe, 12 warps per SM): follows the chains; per block TMA copies of the chunk's records
+//              (128-byte FP64 structures with XOR-swizzled 16-byte pieces, sphgpu_internal.h) into the single stage;
+//              every thread walks its list (read from the pool through L2, prefetched four entries ahead) two entries
+//              at a time; the exact FP64 predicate (bit-identical neighbour sets) enters the branch-free FP64 pair body
+//              as a mask.
+// k_pair_fallback evaluates the units whose lists overflowed the pool with the direct per-target loop of pair.cu (and
+// every unit in variant 2, the cross-check of the unit bookkeeping).
 //
 // Replaces the reference hot loop AsymmetricSolver.cpp:174-201 (finder.findAll + filter + kernel.grad +
 // derivatives.eval) -- see pair.cu for the prologue, the epilogue helpers and the direct variant.
@@ -30,19 +32,12 @@
 namespace sph {
 
 constexpr int TILE_T = 128;   // targets (threads) per work unit
-constexpr int TILE_C = 576;   // staged candidates per chunk
-constexpr int LIST_CAP = 64;  // list entries per lane and block
+constexpr int TILE_C = 576;   // staged candidate slots per chunk (incl. the alignment gaps between row pieces)
+constexpr int LIST_CAP = 60;  // list entries per lane and block (15 quads; 63 is the null link of scheduleList)
 constexpr int UNIT_KBLOCK = 4;    // double rows (in z) interleaved in the unit order, see k_units
-constexpr int PAIRS_PER_TRIP = 3; // list entries the pair-sum kernel processes together
+constexpr int PAIRS_PER_TRIP = 2; // list entries the pair-sum kernel processes together
 constexpr int TILE_X = 20;    // widest unit in cells (bounds the per-unit loops over candidate cells)
 constexpr int CHUNK_ROWS = 6; // candidate rows per chunk: 2 z-layers x 3 y-rows
-
-template <bool SOLID>
-struct TileLayout {
-    static constexpr int G = SOLID ? REC_SOLID : REC_FLUID; // record stride (doubles), same in global and shared memory:
-    static constexpr int S = G;                              // 9 or 7 (odd) x 16 B => conflict-free consecutive records
-    static constexpr size_t bytes = (size_t)TILE_C * S * 8 + (size_t)TILE_C * 16 + (size_t)LIST_CAP * TILE_T * 2;
-};
 
 // ---- TMA bulk copy + mbarrier (raw PTX; sm_90+ / sm_100a) -----------------------------------------------------
 __device__ __forceinline__ uint32_t smemAddr(const void* p) {
@@ -76,6 +71,41 @@ __device__ __forceinline__ void storeSharedU16(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void fenceProxyAsync() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+/// Asynchronous copies global -> shared (LDGSTS): the data never occupies a register while it is in flight.
+__device__ __forceinline__ void copyAsync4(void* dstSmem, const void* srcGlobal) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
+}
+__device__ __forceinline__ void copyAsync8(void* dstSmem, const void* srcGlobal) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal) : "memory");
+}
+__device__ __forceinline__ void copyAsyncWaitAll() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+/// Predicated 8-byte read-only global load (keeps the caller's code free of branches).
+__device__ __forceinline__ void loadGlobalU2If(bool p, const uint2* ptr, uint2& v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+                 : "+r"(v.x), "+r"(v.y)
+                 : "l"(ptr), "r"((uint32_t)p));
+}
+/// 16-byte load from shared memory through a 32-bit shared-window address (LDS.128).
+__device__ __forceinline__ double2 loadSharedD2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t loadSharedU16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t loadSharedU8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void storeSharedU8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 // ---- work list: units of <= 128 targets per double row ---------------------------------------------------------
 // The targets of a double row are taken in COLUMN order: for every cell column c the lower cell's particles, then the
@@ -89,6 +119,9 @@ __global__ void __launch_bounds__(128) k_units(DevicePointers d, uint32_t maxCel
     // overlap), lane 0 then walks them; a thread-per-row walk would pay one L2 round trip per column
     constexpr int CHUNK = 256;
     __shared__ uint32_t sCnt[4][CHUNK];
+    if (d.listCtl->rebuild == 0u) {
+        return; // the units of the last build are reused
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
@@ -187,6 +220,9 @@ __global__ void __launch_bounds__(TILE_T) k_unit_prep(DevicePointers d, uint32_t
     constexpr int ZBINS = 32; // z resolution of the lane order: 1/32 of the double row's height
     __shared__ uint32_t sColL[TILE_X + 2], sColU[TILE_X + 2], sHmax;
     __shared__ uint32_t sBinW[TILE_T / 32][ZBINS], sBase[ZBINS];
+    if (d.listCtl->rebuild == 0u) {
+        return;
+    }
     const GridDev g = *d.grid;
     const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
     const uint32_t totalUnits = d.segStart[maxCells];
@@ -321,12 +357,15 @@ __device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t
                 cur.pos = rb;
                 cur.posValid = 1;
             }
-            const uint32_t take = re > cur.pos ? min(re - cur.pos, (uint32_t)TILE_C - used) : 0u;
+            // the staged index of a record is congruent to its sorted index mod 8 (swizzle of the solid records, bank
+            // schedule of the lists): up to 7 slots are skipped in front of a row piece
+            const uint32_t base = used + ((cur.pos - used) & 7u);
+            const uint32_t take = (re > cur.pos && base < (uint32_t)TILE_C) ? min(re - cur.pos, (uint32_t)TILE_C - base) : 0u;
             if (take > 0) {
                 cs.beg[cur.row] = cur.pos;
                 cs.end[cur.row] = cur.pos + take;
-                cs.base[cur.row] = used;
-                used += take;
+                cs.base[cur.row] = base;
+                used = base + take;
                 cur.pos += take;
             }
             if (cur.pos >= re) {
@@ -354,12 +393,14 @@ __device__ __forceinline__ void nextChunk(const uint32_t* rowBeg, const uint32_t
 // ---- pieces shared by the list kernel and the pair-sum kernel ---------------------------------------------------
 constexpr uint32_t LIST_STRIDE = TILE_T * 2u;        // bytes between consecutive entries of one lane's list
 constexpr uint32_t LIST_END = 0xffffffffu;           // unitList / block header: no (further) block
-constexpr uint32_t LIST_FALLBACK = 0xfffffffeu;      // unitList: the pool was exhausted, build the lists in the pair kernel
-constexpr uint32_t LIST_ROW_BYTES = TILE_T * 2u;     // one row of a list block: one u16 per lane
-// A list block is (1 + rows) rows of 256 B. Row 0: bytes 0..127 = per-lane entry counts (u8), bytes 128..187 = the
-// descriptor of the NEXT block of the unit (word 0 = LIST_END terminates the chain). Rows 1.. = entries, [entry][lane],
-// each entry the shared-memory index of a staged candidate of the chunk. unitList[4 * unit ..] holds the descriptor of
-// the unit's first block.
+constexpr uint32_t LIST_FALLBACK = 0xfffffffeu;      // unitList: the pool was exhausted, the unit goes to k_pair_fallback
+constexpr uint32_t LIST_ROW_BYTES = TILE_T * 2u;     // one row of the list pool (and of the list in shared memory): 256 B
+constexpr uint32_t LIST_QUAD_BYTES = TILE_T * 8u;    // one quad row of a block: four u16 entries per lane
+constexpr uint32_t LIST_NULL = 63u;                  // scheduleList: end of a residue chain
+// A list block in the pool is 1 + 4 Q rows of 256 B. Row 0: bytes 0..127 = per-lane entry counts (u8), bytes 128..187 =
+// the descriptor of the NEXT block of the unit (word 0 = LIST_END terminates the chain). Then Q quad rows of 1 KB:
+// [quad][lane][4] u16, entry q of a lane in quad q / 4, each entry the staged (shared-memory) index of a candidate of the
+// chunk. unitList[4 * unit ..] holds the descriptor of the unit's first block.
 
 /// What a thread knows about its target and its unit.
 struct UnitLane {
@@ -542,48 +583,76 @@ __device__ __forceinline__ uint32_t scanRows(const ChunkState& cs, const UnitLan
     return lp;
 }
 
-/// W list entries together: the exact FP64 predicate enters the branch-free pair body as a mask; the W long per-pair
-/// dependency chains overlap.
-template <bool SOLID, bool CORRECTED, bool FILTER, int W>
-__device__ __forceinline__ void pairTrip(const double* recS, const uint16_t* lst, int q, const double* self, const Particle& pi,
-    const double* lut, Accum& acc) {
-    constexpr int S = TileLayout<SOLID>::S;
-    const double* rp[W];
-    Particle pj[W];
-    double dx[W], dy[W], dz[W], d2[W], hb[W];
-    bool v[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        rp[w] = recS + (size_t)lst[(q + w) * TILE_T] * S;
-        loadRecord<SOLID>(rp[w], pj[w]);
-    }
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        dx[w] = pi.x - pj[w].x;
-        dy[w] = pi.y - pj[w].y;
-        dz[w] = pi.z - pj[w].z;
-        v[w] = isNeighbour(dx[w], dy[w], dz[w], pi.h, pj[w].h, c_prm.kernel_radius, d2[w], hb[w]) && rp[w] != self;
-    }
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        pairAccumulateMasked<SOLID, CORRECTED, FILTER>(c_prm, lut, pi, pj[w], dx[w], dy[w], dz[w], d2[w], hb[w], v[w], acc);
+// ---- list schedule: ordering a lane's list against bank conflicts in phase 2 -------------------------------------------
+// Phase 2 gathers, per list entry, one staged record per lane with LDS.128; the 8 lanes of a quarter warp are served
+// together and collide when their records' staged indices agree mod 8 (equal indices broadcast). Entry q of lane l
+// therefore PREFERS a candidate of residue class (q + l) mod 8: as long as every lane of a quarter finds its preferred
+// class, the quarter reads 8 different bank groups. A lane whose preferred class has run out takes the next non-empty
+// one. Measured with profiles/conflict_model.py on the bench lattice: 1.92 -> 1.36 wavefronts per ideal wavefront (a
+// jittered lattice: 2.27 -> 1.41).
+//
+// chainList (backwards over the lane's list) threads the entries of every class into a chain: bits 10..15 of an entry
+// receive the list position of the next entry of its class, byte b of `heads` the first one of class b. emitList pops
+// the chains in the preferred order and writes the quads {4 x u16} straight to the block in the pool. Both loops run in
+// lockstep over the warp (every lane is at the same list row, so the u16 accesses of two lanes that share a 32-bit word
+// do not collide); the eight chain heads live in two registers.
+struct ChainHeads {
+    uint32_t lo, hi; // byte b: list position of the first entry of class b (LIST_NULL: none)
+};
+
+__device__ __forceinline__ uint32_t headGet(const ChainHeads& h, uint32_t b) {
+    return __byte_perm(h.lo, h.hi, b) & 0xffu;
+}
+__device__ __forceinline__ void headSet(ChainHeads& h, uint32_t b, uint32_t v) {
+    // byte (b & 3) of the selected word <- v: PRMT selector 0x3210 with nibble (b & 3) replaced by 4 (= byte 0 of v)
+    const uint32_t n = b & 3u;
+    const uint32_t sel = 0x3210u + ((4u - n) << (4u * n));
+    const uint32_t lo = __byte_perm(h.lo, v, sel), hi = __byte_perm(h.hi, v, sel);
+    h.lo = b < 4u ? lo : h.lo;
+    h.hi = b < 4u ? h.hi : hi;
+}
+
+__device__ __forceinline__ void chainList(uint32_t listOwn, uint32_t cnt, uint32_t warpMax, ChainHeads& heads) {
+    heads.lo = heads.hi = LIST_NULL * 0x01010101u;
+    for (uint32_t e = warpMax; e-- > 0;) {
+        if (e < cnt) {
+            const uint32_t addr = listOwn + e * LIST_STRIDE;
+            const uint32_t v = loadSharedU16(addr);
+            const uint32_t b = v & 7u;
+            storeSharedU16(addr, v | (headGet(heads, b) << 10));
+            headSet(heads, b, e);
+        }
     }
 }
 
-/// Phase 2: walks the lane's list W entries at a time.
-template <bool SOLID, bool CORRECTED, bool FILTER, int W>
-__device__ __forceinline__ void sumListedPairs(const double* recS, const uint16_t* lst, int cnt, const double* self, const Particle& pi,
-    const double* lut, Accum& acc) {
-    int q = 0;
-    for (; q + W <= cnt; q += W) {
-        pairTrip<SOLID, CORRECTED, FILTER, W>(recS, lst, q, self, pi, lut, acc);
+__device__ __forceinline__ void emitList(uint32_t listOwn, uint32_t cnt, uint32_t warpMax, uint32_t lane, ChainHeads heads, uint2* quadOut) {
+    uint32_t lo = 0u, hi = 0u;
+    uint32_t live = 0u; // bit b: class b still has entries
+#pragma unroll
+    for (uint32_t b = 0; b < 8; ++b) {
+        live |= headGet(heads, b) != LIST_NULL ? 1u << b : 0u;
     }
-    if (W > 2 && q + 2 <= cnt) {
-        pairTrip<SOLID, CORRECTED, FILTER, 2>(recS, lst, q, self, pi, lut, acc);
-        q += 2;
-    }
-    if (q < cnt) {
-        pairTrip<SOLID, CORRECTED, FILTER, 1>(recS, lst, q, self, pi, lut, acc);
+    for (uint32_t q = 0; q < warpMax; ++q) {
+        if (q < cnt) {
+            // the preferred class (q + lane) mod 8 or, if it has run out, the next live one (entries remain: q < cnt)
+            const uint32_t want = (q + lane) & 7u;
+            const uint32_t rot = ((live | (live << 8)) >> want) & 0xffu;
+            const uint32_t b = (want + (uint32_t)__ffs((int)rot) - 1u) & 7u;
+            const uint32_t v = loadSharedU16(listOwn + headGet(heads, b) * LIST_STRIDE);
+            const uint32_t next = v >> 10;
+            headSet(heads, b, next);
+            live = next == LIST_NULL ? live & ~(1u << b) : live;
+            const uint32_t idx = (v & 0x3ffu) << ((q & 1u) * 16u);
+            if (q & 2u) {
+                hi |= idx;
+            } else {
+                lo |= idx;
+            }
+            if ((q & 3u) == 3u || q + 1u == cnt) {
+                quadOut[(size_t)(q >> 2) * TILE_T] = make_uint2(lo, hi);
+                lo = hi = 0u;
+            }
+        }
     }
 }
 
@@ -600,7 +669,8 @@ __device__ __forceinline__ void finishTarget(const DevicePointers& d, const Unit
             }
         }
         Derivs out;
-        finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][slot], pi.cs, SOLID ? d.f[F_REDUCE][slot] : 1., S, out);
+        finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][slot], d.f[F_CS][slot], SOLID ? d.f[F_REDUCE][slot] : 1., S,
+            out);
         storeDerivs<SOLID, CORRECTED>(d, slot, out);
     }
     neighbourStats(d, acc.cnt, u.target);
@@ -608,26 +678,32 @@ __device__ __forceinline__ void finishTarget(const DevicePointers& d, const Unit
 
 // ---- kernel A: candidate lists ------------------------------------------------------------------------------------
 // Phase 1 of every unit at high occupancy (26 KB of shared memory, 64 registers: 8 CTAs per SM): stages the FP32
-// positions of each chunk, runs the conservative filter and writes the per-lane lists of the chunk as one contiguous
-// block of the list pool. Every block carries the DESCRIPTOR of the unit's next block (pool offset, rows, chunk and the
-// six staged record ranges), so the pair-sum kernel only follows the chain: it stages records + list blocks and spends
-// its 8 warps per SM on FP64 work.
+// positions of each chunk, runs the conservative filter, schedules the per-lane lists (above) and writes them as one
+// contiguous block of the list pool. Every block carries the DESCRIPTOR of the unit's next block (pool offset, quad rows,
+// chunk and the six staged record ranges), so the pair-sum kernel only follows the chain: it stages records and spends
+// its warps on FP64 work.
 constexpr size_t LISTS_SMEM = (size_t)TILE_C * 16 + (size_t)(LIST_CAP + 1) * LIST_ROW_BYTES;
-constexpr int DESC_WORDS = 3 + 2 * CHUNK_ROWS; // {pool row offset, rows, chunk, 6 x {first sorted index, count | stage offset << 16}}
+// descriptor of a block: {pool row offset, quad rows, chunk, 6 x {first sorted index, count | stage offset << 16}}, word 15 =
+// the pool row offset of the block AFTER it in the chain (or LIST_END): the pair-sum kernel prefetches one block ahead
+constexpr int DESC_WORDS = 16;
 
-__global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint32_t maxCells, uint32_t poolRows) {
+__global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint32_t maxCells, uint32_t poolRows, double skin) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float4* f4 = reinterpret_cast<float4*>(smemRaw);
-    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C); // one block: row 0 = counts + descriptor, rows 1.. = entries
+    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C); // row 0 = counts + "no next block", rows 1.. = entries [entry][lane]
     __shared__ ChunkState csBuf[2];
     __shared__ __align__(8) uint64_t stageBar;
     __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
     __shared__ uint32_t sWarp[TILE_T / 32], sOff;
 
+    if (d.listCtl->rebuild == 0u) {
+        return; // the lists of the last build are reused
+    }
     const GridDev g = *d.grid;
     const uint32_t totalUnits = d.segStart[maxCells];
     const int tid = threadIdx.x;
-    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
+    // search radius enlarged by the skin of the list reuse (ListCtlDev)
+    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5) * (1. + skin));
     // the FP32 coordinates are relative to the grid origin: absolute rounding error <= 2^-24 * extent per coordinate
     const float slack = (float)(g.extent * 1.e-6);
     const ScanGeometry sg = { (float)g.cell, (float)g.cellZ, (float)(g.extent * 1.e-5), g.unsorted == 0u };
@@ -652,6 +728,7 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
         }
         // thread 0 chains the blocks of the unit: the descriptor of a block goes into the header of its predecessor
         uint32_t* link = first;
+        uint32_t* prev = nullptr; // descriptor of the chain's current last block (its word 15 names the block after it)
         bool failed = false;
         int buf = 0;
         while (true) {
@@ -662,7 +739,12 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
             }
             if (tid == 0) {
                 fenceProxyAsync(); // the buffer was last read through the generic proxy
-                mbarExpectTx(&stageBar, cs.used * 16u);
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int r = 0; r < CHUNK_ROWS; ++r) {
+                    bytes += (cs.end[r] - cs.beg[r]) * 16u;
+                }
+                mbarExpectTx(&stageBar, bytes);
 #pragma unroll
                 for (int r = 0; r < CHUNK_ROWS; ++r) {
                     const uint32_t n = cs.end[r] - cs.beg[r];
@@ -681,11 +763,13 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
                 const uint32_t cnt = (lp - listOwn) / LIST_STRIDE;
                 reinterpret_cast<unsigned char*>(list)[tid] = (unsigned char)cnt;
                 const uint32_t wmax = __reduce_max_sync(0xffffffffu, cnt);
+                ChainHeads heads;
+                chainList(listOwn, cnt, wmax, heads);
                 const bool wmore = __any_sync(0xffffffffu, st.r < CHUNK_ROWS);
                 if ((tid & 31) == 0) {
                     sWarp[tid >> 5] = wmax | (wmore ? 0x100u : 0u);
                 }
-                __syncthreads(); // lists, counts and the warp summaries are complete
+                __syncthreads(); // counts and the warp summaries are complete
                 uint32_t rows = 0;
                 bool anyMore = false;
 #pragma unroll
@@ -694,11 +778,13 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
                     anyMore = anyMore || (sWarp[w] & 0x100u) != 0u;
                 }
                 if (rows > 0) {
+                    const uint32_t quads = (rows + 3u) / 4u;
+                    const uint32_t need = 1u + 4u * quads; // pool rows of the block
                     if (tid == 0) {
                         uint32_t off = LIST_FALLBACK;
                         if (!failed) {
-                            off = atomicAdd(d.listCursor, rows + 1u);
-                            if (off > poolRows || rows + 1u > poolRows - off) {
+                            off = atomicAdd(d.listCursor, need);
+                            if (off > poolRows || need > poolRows - off) {
                                 failed = true;
                                 off = LIST_FALLBACK;
                             }
@@ -709,21 +795,25 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
                     __syncthreads();
                     const uint32_t off = sOff;
                     if (off != LIST_FALLBACK) {
-                        const uint4* src = reinterpret_cast<const uint4*>(list);
-                        uint4* dst = pool + (size_t)off * ROW_Q;
-                        for (uint32_t w = tid; w < (rows + 1u) * ROW_Q; w += TILE_T) {
-                            dst[w] = src[w];
+                        emitList(listOwn, cnt, wmax, (uint32_t)tid, heads, reinterpret_cast<uint2*>(pool + (size_t)(off + 1u) * ROW_Q) + tid);
+                        if (tid < (int)ROW_Q) { // row 0: the counts and the end-of-chain mark
+                            pool[(size_t)off * ROW_Q + tid] = reinterpret_cast<const uint4*>(list)[tid];
                         }
                         if (tid == 0) { // descriptor of this block -> unitList (first block) or the header of the previous
-                                        // block, whose copy finished before the last barrier
-                            link[1] = rows;
+                                        // block, which was written in an earlier round
+                            link[1] = quads;
                             link[2] = (uint32_t)cs.chunk;
 #pragma unroll
                             for (int r = 0; r < CHUNK_ROWS; ++r) {
                                 link[3 + 2 * r] = cs.beg[r];
                                 link[4 + 2 * r] = (cs.end[r] - cs.beg[r]) | (cs.base[r] << 16);
                             }
+                            link[15] = LIST_END; // no block after this one (yet)
                             link[0] = off;
+                            if (prev != nullptr) {
+                                prev[15] = off;
+                            }
+                            prev = link;
                             link = reinterpret_cast<uint32_t*>(pool + (size_t)off * ROW_Q) + TILE_T / 4;
                         }
                     }
@@ -731,12 +821,12 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
                 if (!anyMore) {
                     break;
                 }
-                __syncthreads(); // the block has been copied out: the lanes may overwrite the list
+                __syncthreads(); // row 0 has been copied out: the lanes may overwrite the counts
             }
         }
         if (tid == 0) {
             if (failed) {
-                atomicAdd(&d.stats->fallbackUnits, 1u);
+                atomicAdd(&d.listCtl->fallbackUnits, 1u);
                 first[0] = LIST_FALLBACK;
             } else if (link == first) {
                 first[0] = LIST_END; // no candidate at all
@@ -746,35 +836,92 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
 }
 
 // ---- kernel B: pair sums, list-driven --------------------------------------------------------------------------------
-// Follows the block chains written by k_pair_lists. Per block: one CTA barrier (the stage is free), thread 0 issues the
-// TMA copies of the block's record rows and of its list block, everyone waits on the mbarrier and runs phase 2. At the
-// end of a chain the first block of the CTA's next unit is issued BEFORE the finalizers / stores of the finished unit and
-// the loads of the next unit's targets, so those overlap with the copies.
+// Follows the block chains written by k_pair_lists. The only shared memory is the record stage (72 KB solid: three CTAs
+// per SM); the lists stay in the pool and every lane reads its own quads through L2, one quad (four entries) ahead.
+// Per block: thread 0 issues the TMA copies of the block's record rows, everyone fetches its entry count and first quads
+// (threads 0..15 also the descriptor of the next block), waits on the mbarrier and walks its list; one CTA barrier frees
+// the stage. At the end of a chain the first block of the CTA's next unit is issued BEFORE the finalizers / stores of the
+// finished unit and the loads of the next unit's targets, so those overlap with the copies.
 template <bool SOLID>
 struct SumLayout {
-    static constexpr int S = SOLID ? REC_SOLID : REC_FLUID;
-    static constexpr size_t recBytes = (size_t)TILE_C * S * 8;
-    static constexpr size_t bytes = recBytes + (size_t)(LIST_CAP + 1) * LIST_ROW_BYTES;
+    static constexpr int S = SOLID ? REC_SOLID : REC_FLUID;     // doubles per staged record
+    static constexpr uint32_t REC_BYTES = (uint32_t)S * 8u;
+    static constexpr size_t bytes = (size_t)TILE_C * REC_BYTES; // 73 728 B solid, 64 512 B fluid
 };
 
+/// One list entry between the two stages of the pair body (sph_math.cuh).
+struct PairSlot {
+    PairGeom g;
+    double vz, rho;  // second half of the {vz, rho} piece stage A loads for the density
+    double2 lut;     // table entry {G[k], G[k+1] - G[k]}, in flight between the stages
+    uint32_t rec;    // shared address of the staged record (solid: swizzle applied)
+};
+
+/// Stage A of staged record k: the position pieces and {vz, rho} (LDS.128 through 32-bit shared addresses), geometry,
+/// and the table load. `stage` is 128-byte aligned, so piece c of a solid record sits at (record start + swizzle) ^ (c << 4).
+template <bool SOLID>
+__device__ __forceinline__ void stageA(uint32_t stage, uint32_t k, uint32_t selfIdx, const Particle& pi, const LutPair* lut2, PairSlot& s) {
+    double2 a, b, e;
+    if (SOLID) {
+        s.rec = stage + k * 128u + ((k & 7u) << 4);
+        a = loadSharedD2(s.rec);
+        b = loadSharedD2(s.rec ^ 16u);
+        e = loadSharedD2(s.rec ^ 48u);
+    } else {
+        s.rec = stage + k * (uint32_t)(REC_FLUID * 8);
+        a = loadSharedD2(s.rec);
+        b = loadSharedD2(s.rec + 16u);
+        e = loadSharedD2(s.rec + 48u);
+    }
+    s.vz = e.x;
+    s.rho = e.y;
+    pairGeometry(c_prm, pi.x, pi.y, pi.z, pi.h, pi.rho, a.x, a.y, b.x, b.y, e.y, s.g);
+    s.g.valid = s.g.valid && k != selfIdx;
+    s.lut = __ldg(reinterpret_cast<const double2*>(lut2) + s.g.k);
+}
+
+/// Stage B: the rest of the record and the sums.
 template <bool SOLID, bool CORRECTED, bool FILTER>
-__global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32_t maxCells) {
+__device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Accum& acc) {
+    Particle pj;
+    pj.vz = s.vz;
+    pj.rho = s.rho;
+    if (SOLID) {
+        const double2 c = loadSharedD2(s.rec ^ 32u), f = loadSharedD2(s.rec ^ 64u), g = loadSharedD2(s.rec ^ 80u);
+        const double2 s1 = loadSharedD2(s.rec ^ 96u), s2 = loadSharedD2(s.rec ^ 112u);
+        pj.vx = c.x; pj.vy = c.y;
+        pj.P = f.x;
+        unpackCsGroup(f.y, pj.cs, pj.grp);
+        pj.vol = g.x;
+        pj.Sr[0] = g.y; pj.Sr[1] = s1.x; pj.Sr[2] = s1.y; pj.Sr[3] = s2.x; pj.Sr[4] = s2.y;
+    } else {
+        const double2 c = loadSharedD2(s.rec + 32u), f = loadSharedD2(s.rec + 64u), g = loadSharedD2(s.rec + 80u);
+        pj.vx = c.x; pj.vy = c.y;
+        pj.P = f.x; pj.cs = f.y; pj.vol = g.x;
+        pj.grp = 0;
+    }
+    pj.m = pj.vol * pj.rho;
+    pairSums<SOLID, CORRECTED, FILTER>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc);
+}
+
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__global__ void __launch_bounds__(TILE_T, 3) k_pair_sum(DevicePointers d, uint32_t maxCells) {
     using P = SumLayout<SOLID>;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    double* recS = reinterpret_cast<double*>(smemRaw);
-    uint16_t* list = reinterpret_cast<uint16_t*>(smemRaw + P::recBytes); // row 0 = counts + next descriptor, rows 1.. = entries
+    extern __shared__ __align__(128) unsigned char smemStage[];
     __shared__ __align__(8) uint64_t stageBar;
     __shared__ uint32_t sFirst[2][16]; // first-block descriptors of the CTA's current and next unit
+    __shared__ uint32_t sDesc[2][16];  // descriptor of the chain's next block, double-buffered over the blocks
+    // per-thread landing slots of the asynchronous prefetches (no registers are held while the loads are in flight):
+    __shared__ uint2 sPfQuad[TILE_T];     // first quad of the block this thread processes next
+    __shared__ uint32_t sPfCnt[TILE_T];   // the word of that block's count row that holds this thread's entry count
+    __shared__ uint32_t sPfWord[TILE_T];  // this thread's lane word in the CTA's next unit
 
     const GridDev g = *d.grid;
     const uint32_t totalUnits = d.segStart[maxCells];
     const uint32_t stride = gridDim.x;
     const int tid = threadIdx.x;
-    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
-    const float slack = (float)(g.extent * 1.e-6);
     const unsigned char* pool = reinterpret_cast<const unsigned char*>(d.listPool);
-    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(list) + TILE_T / 4; // descriptor of the chain's next block
-    const uint16_t* const lst = list + TILE_T + tid;                           // this lane's first entry
+    const uint32_t stage = smemAddr(smemStage);
 
     uint32_t unit = blockIdx.x;
     if (unit >= totalUnits) {
@@ -785,35 +932,46 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32
             sFirst[ring][tid] = v < totalUnits ? reinterpret_cast<const uint32_t*>(d.unitList + (size_t)v * 4)[tid] : LIST_END;
         }
     };
-    auto issue = [&](const uint32_t* dsc) { // thread 0: TMA copies of the block described by dsc
+    auto issue = [&](const uint32_t* dsc) { // thread 0: TMA copies of the record rows of the block described by dsc
         fenceProxyAsync(); // the stage was last read through the generic proxy
-        const uint32_t listBytes = (dsc[1] + 1u) * LIST_ROW_BYTES;
-        uint32_t bytes = listBytes;
+        uint32_t bytes = 0;
 #pragma unroll
         for (int r = 0; r < CHUNK_ROWS; ++r) {
-            bytes += (dsc[4 + 2 * r] & 0xffffu) * (uint32_t)(P::S * 8);
-        }
-        const uint32_t off = dsc[0];
-        uint32_t beg[CHUNK_ROWS], nb[CHUNK_ROWS];
-#pragma unroll
-        for (int r = 0; r < CHUNK_ROWS; ++r) { // read the descriptor before the list copy may overwrite it
-            beg[r] = dsc[3 + 2 * r];
-            nb[r] = dsc[4 + 2 * r];
+            bytes += (dsc[4 + 2 * r] & 0xffffu) * P::REC_BYTES;
         }
         mbarExpectTx(&stageBar, bytes);
 #pragma unroll
         for (int r = 0; r < CHUNK_ROWS; ++r) {
-            const uint32_t n = nb[r] & 0xffffu;
+            const uint32_t nb = dsc[4 + 2 * r], n = nb & 0xffffu;
             if (n > 0) {
-                bulkCopyG2S(recS + (size_t)(nb[r] >> 16) * P::S, d.rec + (size_t)beg[r] * P::S, n * (uint32_t)(P::S * 8), &stageBar);
+                bulkCopyG2S(smemStage + (size_t)(nb >> 16) * P::REC_BYTES, d.rec + (size_t)dsc[3 + 2 * r] * P::S, n * P::REC_BYTES, &stageBar);
             }
         }
-        bulkCopyG2S(list, pool + (size_t)off * LIST_ROW_BYTES, listBytes, &stageBar);
     };
-    auto setupUnit = [&](uint32_t v, UnitLane& u, Particle& pi, Accum& acc) {
-        loadLane(d, g, d.unitDesc[v], d.unitAux[v], tid, Rhalf, slack, u);
+    auto laneWord = [&](uint32_t v) -> uint32_t { // lane order word of thread tid in unit v (k_unit_prep), idle: ~0
+        const uint4 desc = d.unitDesc[v];
+        return (uint32_t)tid < (desc.w >> 8) ? d.unitLane[d.unitAux[v].x + tid] : 0xffffffffu;
+    };
+    auto prefetchLaneWord = [&](uint32_t v) { // the same word for the CTA's NEXT unit, into sPfWord[tid]
+        sPfWord[tid] = 0xffffffffu;
+        if (v < totalUnits) {
+            const uint4 desc = d.unitDesc[v];
+            if ((uint32_t)tid < (desc.w >> 8)) {
+                copyAsync4(&sPfWord[tid], d.unitLane + d.unitAux[v].x + tid);
+            }
+        }
+    };
+    auto setupUnit = [&](uint32_t v, uint32_t word, UnitLane& u, Particle& pi, Accum& acc) {
+        const uint32_t dr = d.unitDesc[v].x;
+        u.cy = (int)(dr % (uint32_t)g.dim[1]);
+        u.k = (int)(dr / (uint32_t)g.dim[1]);
+        u.live = word != 0xffffffffu;
+        u.t = u.live ? (word & 0x3fffffffu) : 0u;
+        u.upper = u.live && (word >> 31) != 0u;
+        u.target = u.live && (word & 0x40000000u) == 0u; // ghosts are neighbours only
+        u.slot = u.target ? d.order[u.t] : 0xffffffffu;
         if (u.live) {
-            loadRecord<SOLID>(d.rec + (size_t)u.t * P::S, pi);
+            loadRecord<SOLID>(d.rec + (size_t)u.t * P::S, u.t & 7u, pi);
         } else {
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
@@ -824,29 +982,45 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32
     if (tid == 0) {
         mbarInit(&stageBar, 1);
     }
-    int ring = 0;
+    int ring = 0, par = 0;
     loadFirst(unit, 0);
     loadFirst(unit + stride, 1);
     UnitLane u;
     Particle pi;
     Accum acc;
-    setupUnit(unit, u, pi, acc);
+    setupUnit(unit, laneWord(unit), u, pi, acc);
+    prefetchLaneWord(unit + stride); // one unit ahead
     __syncthreads();
+    // This lane's share of the block it processes NEXT is fetched from the pool (through L2) as soon as that block's
+    // offset is known -- one block ahead: entry count and first quad.
+    auto prefetchBlock = [&](uint32_t off) {
+        const unsigned char* blk = pool + (size_t)off * LIST_ROW_BYTES;
+        copyAsync4(&sPfCnt[tid], blk + (tid & ~3));
+        copyAsync8(&sPfQuad[tid], reinterpret_cast<const uint2*>(blk + LIST_ROW_BYTES) + tid);
+    };
+    if (sFirst[0][0] < LIST_FALLBACK) {
+        prefetchBlock(sFirst[0][0]);
+    }
     uint32_t stagePhase = 0;
     bool firstOfUnit = true; // the next block is the first one of `unit` (its descriptor is sFirst[ring])
     bool issued = false;     // ... and its copies are already in flight
+    // Invariant at the top of the loop: a CTA barrier has passed since the descriptor read here was written and since
+    // every thread finished with the stage; pfCnt / pfQuad belong to the block that descriptor names.
     while (true) {
-        const uint32_t* dsc = firstOfUnit ? sFirst[ring] : hdr;
+        const uint32_t* dsc = firstOfUnit ? sFirst[ring] : sDesc[par];
         const uint32_t off = dsc[0];
         if (off >= LIST_FALLBACK) { // the chain of `unit` has ended (or the unit has no chain)
-            const bool fallback = firstOfUnit && off == LIST_FALLBACK; // left to the fused kernel
+            const bool fallback = firstOfUnit && off == LIST_FALLBACK; // left to k_pair_fallback
             const uint32_t nextUnit = unit + stride;
             const int nextRing = ring ^ 1;
-            // everyone is done with the stage and has read sFirst[ring]: issue the next unit's first block right away
-            __syncthreads();
-            issued = nextUnit < totalUnits && sFirst[nextRing][0] < LIST_FALLBACK;
-            if (issued && tid == 0) {
-                issue(sFirst[nextRing]);
+            __syncthreads(); // everyone has read sFirst[ring]: its slot may be refilled below
+            const uint32_t nextOff = nextUnit < totalUnits ? sFirst[nextRing][0] : LIST_END;
+            issued = nextOff < LIST_FALLBACK;
+            if (issued) {
+                if (tid == 0) {
+                    issue(sFirst[nextRing]); // the next unit's first block, right away
+                }
+                prefetchBlock(nextOff);
             }
             if (!fallback) {
                 finishTarget<SOLID, CORRECTED>(d, u, pi, acc); // overlaps with the copies
@@ -857,120 +1031,100 @@ __global__ void __launch_bounds__(TILE_T, 2) k_pair_sum(DevicePointers d, uint32
             loadFirst(nextUnit + stride, ring); // ring slot of the finished unit; visible after the next barrier
             unit = nextUnit;
             ring = nextRing;
-            setupUnit(unit, u, pi, acc);
+            copyAsyncWaitAll(); // (also completes the block prefetch issued above; it has had the finalizers' time)
+            setupUnit(unit, sPfWord[tid], u, pi, acc);
+            prefetchLaneWord(unit + stride);
             firstOfUnit = true;
             continue;
         }
         // descriptor words every thread needs: chunk and the staged row that may hold the target's own record
         const int selfRow = u.upper ? 4 : 1;
         const uint32_t chunk = dsc[2], selfBeg = dsc[3 + 2 * selfRow], selfNB = dsc[4 + 2 * selfRow];
-        if (!issued) {
-            __syncthreads(); // everyone is done with the previous block (records, list, its header)
-            if (tid == 0) {
-                issue(dsc);
-            }
+        if (!issued && tid == 0) {
+            issue(dsc);
         }
         issued = false;
         firstOfUnit = false;
+        copyAsyncWaitAll();
+        const uint32_t cnt = (sPfCnt[tid] >> (8 * (tid & 3))) & 0xffu;
+        uint2 cur = sPfQuad[tid];
+        if (dsc[15] < LIST_FALLBACK) {
+            prefetchBlock(dsc[15]); // the chain's next block: in flight during the copies and the walk
+        }
+        if (tid < 16) { // the descriptor of that block, from the header of this one
+            copyAsync4(&sDesc[par ^ 1][tid], reinterpret_cast<const uint32_t*>(pool + (size_t)off * LIST_ROW_BYTES) + TILE_T / 4 + tid);
+        }
+        const uint2* quads = reinterpret_cast<const uint2*>(pool + (size_t)(off + 1u) * LIST_ROW_BYTES) + tid;
         mbarWait(&stageBar, stagePhase);
         stagePhase ^= 1;
-        if (u.target) {
+        if (cnt > 0u) {
             const bool selfHere = chunk == 2u && u.t >= selfBeg && u.t < selfBeg + (selfNB & 0xffffu);
-            const double* self = recS + (selfHere ? (size_t)((selfNB >> 16) + (u.t - selfBeg)) * P::S : (size_t)TILE_C * P::S);
-            const int cnt = reinterpret_cast<const unsigned char*>(list)[tid];
-            sumListedPairs<SOLID, CORRECTED, FILTER, PAIRS_PER_TRIP>(recS, lst, cnt, self, pi, d.lut, acc);
+            const uint32_t selfIdx = selfHere ? (selfNB >> 16) + (u.t - selfBeg) : 0xffffffffu;
+            // One quad (four entries) per trip of the loop, the next quad fetched at its top and first used by the last
+            // stage A of the trip. Stage A runs one entry ahead of stage B and is unconditional (past the end of the list
+            // it runs on whatever the exhausted quads hold and its result is dropped): every [A; B] pair below is ONE
+            // basic block, so that the scheduler interleaves the two stages.
+            PairSlot s0, s1;
+            stageA<SOLID>(stage, cur.x & 0xffffu, selfIdx, pi, d.lut2, s0);
+            uint32_t q = 0;
+            while (true) {
+                quads += TILE_T;
+                uint2 nxt = make_uint2(0u, 0u);
+                loadGlobalU2If(q + 4u < cnt, quads, nxt);
+                stageA<SOLID>(stage, cur.x >> 16, selfIdx, pi, d.lut2, s1);
+                stageB<SOLID, CORRECTED, FILTER>(s0, pi, acc);
+                if (++q >= cnt) {
+                    break;
+                }
+                stageA<SOLID>(stage, cur.y & 0xffffu, selfIdx, pi, d.lut2, s0);
+                stageB<SOLID, CORRECTED, FILTER>(s1, pi, acc);
+                if (++q >= cnt) {
+                    break;
+                }
+                stageA<SOLID>(stage, cur.y >> 16, selfIdx, pi, d.lut2, s1);
+                stageB<SOLID, CORRECTED, FILTER>(s0, pi, acc);
+                if (++q >= cnt) {
+                    break;
+                }
+                stageA<SOLID>(stage, nxt.x & 0xffffu, selfIdx, pi, d.lut2, s0);
+                stageB<SOLID, CORRECTED, FILTER>(s1, pi, acc);
+                if (++q >= cnt) {
+                    break;
+                }
+                cur = nxt;
+            }
         }
+        copyAsyncWaitAll(); // the next descriptor (threads 0..15) has landed
+        par ^= 1;
+        __syncthreads(); // the stage is free and the next descriptor is visible
     }
 }
 
-// ---- fused kernel: both phases in one kernel ---------------------------------------------------------------------------
-// The first design of the tiled kernel, kept for the units whose lists did not fit the pool (onlyFallback) and as
-// variant 2 for A/B checks.
+// ---- fallback: direct evaluation of whole units ------------------------------------------------------------------------
+// Units whose candidate lists did not fit the list pool (the pool is then enlarged for the following steps, api.cu), and
+// every unit in variant 2: one thread per target of the unit, candidates streamed from the sorted records (pair.cu).
 template <bool SOLID, bool CORRECTED, bool FILTER>
-__global__ void __launch_bounds__(TILE_T, 2) k_pair_tiled(DevicePointers d, uint32_t maxCells, bool onlyFallback) {
-    using L = TileLayout<SOLID>;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    double* recS = reinterpret_cast<double*>(smemRaw);
-    float4* f4 = reinterpret_cast<float4*>(recS + (size_t)TILE_C * L::S);
-    uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C);
-    __shared__ ChunkState csBuf[2];
-    __shared__ __align__(8) uint64_t stageBar;
-    __shared__ uint32_t sRowBeg[3 * CHUNK_ROWS], sRowEnd[3 * CHUNK_ROWS];
-
-    if (onlyFallback && d.stats->fallbackUnits == 0u) {
+__global__ void __launch_bounds__(TILE_T) k_pair_fallback(DevicePointers d, uint32_t maxCells, bool allUnits) {
+    if (!allUnits && d.listCtl->fallbackUnits == 0u) {
         return;
     }
-    const GridDev g = *d.grid;
     const uint32_t totalUnits = d.segStart[maxCells];
     const int tid = threadIdx.x;
-    const float Rhalf = (float)(0.5 * c_prm.kernel_radius * (1. + 2.e-5));
-    const float slack = (float)(g.extent * 1.e-6);
-    const ScanGeometry sg = { (float)g.cell, (float)g.cellZ, (float)(g.extent * 1.e-5), g.unsorted == 0u };
-    ChunkCursor cur;
-    uint32_t stagePhase = 0;
-    if (tid == 0) {
-        mbarInit(&stageBar, 1);
-    }
-    __syncthreads();
-    const uint16_t* const lst = list + tid; // this lane's first entry
-    const uint32_t listOwn = smemAddr(lst);
-
     for (uint32_t unit = blockIdx.x; unit < totalUnits; unit += gridDim.x) {
-        if (onlyFallback && d.unitList[(size_t)unit * 4].x != LIST_FALLBACK) {
+        if (!allUnits && d.unitList[(size_t)unit * 4].x != LIST_FALLBACK) {
             continue;
         }
-        UnitLane u;
-        if (!beginUnit(d, g, unit, tid, Rhalf, slack, sRowBeg, sRowEnd, cur, csBuf[0], u)) {
-            continue;
+        const uint4 desc = d.unitDesc[unit];
+        const uint4 aux = d.unitAux[unit];
+        if (aux.z == 0u || (uint32_t)tid >= (desc.w >> 8)) {
+            continue; // ghost-only unit / idle lane
         }
-        Particle pi;
-        if (u.live) {
-            loadRecord<SOLID>(d.rec + (size_t)u.t * L::G, pi);
-        } else {
-            pi.x = pi.y = pi.z = 0.;
-            pi.h = 1.;
+        const uint32_t word = d.unitLane[aux.x + tid];
+        if (word & 0x40000000u) {
+            continue; // ghosts are neighbours only
         }
-        Accum acc;
-        accumZero(acc);
-        const int selfRow = u.upper ? 4 : 1; // the target's own record sits in the centre chunk, own layer, dy = 0
-        int buf = 0;
-        while (true) {
-            __syncthreads(); // chunk descriptor published; everyone is done with the previous chunk's shared memory
-            const ChunkState& cs = csBuf[buf];
-            if (cs.used == 0) {
-                break;
-            }
-            // stage the chunk: TMA bulk copies of the FP64 records and of the FP32 positions, one pair per row
-            if (tid == 0) {
-                fenceProxyAsync(); // the buffers were last read through the generic proxy
-                mbarExpectTx(&stageBar, cs.used * (uint32_t)(L::G * 8 + 16));
-#pragma unroll
-                for (int r = 0; r < CHUNK_ROWS; ++r) {
-                    const uint32_t n = cs.end[r] - cs.beg[r];
-                    if (n > 0) {
-                        bulkCopyG2S(recS + (size_t)cs.base[r] * L::S, d.rec + (size_t)cs.beg[r] * L::G, n * (uint32_t)(L::G * 8), &stageBar);
-                        bulkCopyG2S(f4 + cs.base[r], d.posF + cs.beg[r], n * 16u, &stageBar);
-                    }
-                }
-                nextChunk(sRowBeg, sRowEnd, cur, csBuf[buf ^ 1]); // overlaps with the copies
-            }
-            mbarWait(&stageBar, stagePhase);
-            stagePhase ^= 1;
-            buf ^= 1;
-            if (!u.target) {
-                continue;
-            }
-            const double* self = recS + ((cs.chunk == 2 && u.t >= cs.beg[selfRow] && u.t < cs.end[selfRow])
-                                                ? (size_t)(cs.base[selfRow] + (u.t - cs.beg[selfRow])) * L::S
-                                                : (size_t)TILE_C * L::S);
-            ScanState st = { 0, 0u, 0u, false };
-            while (st.r < CHUNK_ROWS) { // private rounds: phase 1 (FP32 filter -> list), phase 2 (FP64 pairs)
-                const uint32_t lp = scanRows(cs, u, sg, f4, listOwn, st);
-                const int cnt = (int)((lp - listOwn) / LIST_STRIDE);
-                sumListedPairs<SOLID, CORRECTED, FILTER, 2>(recS, lst, cnt, self, pi, d.lut, acc);
-            }
-        }
-        finishTarget<SOLID, CORRECTED>(d, u, pi, acc);
+        const uint32_t t = word & 0x3fffffffu;
+        directTarget<SOLID, CORRECTED, FILTER>(d, t, d.order[t]);
     }
 }
 
@@ -981,9 +1135,9 @@ int launchSegments(sphgpu_ctx* ctx) {
     cudaDeviceGetAttribute(&smsU, cudaDevAttrMultiProcessorCount, ctx->device);
     SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.cellCount, 0, sizeof(uint32_t) * total, st));
     k_units<false><<<smsU * 16, 128, 0, st>>>(ctx->d, ctx->maxCells);
-    k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.segStart, ctx->d.scanBlock, total);
-    k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks);
-    k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.segStart, ctx->d.scanBlock, total);
+    k_scan_block<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.cellCount, ctx->d.segStart, ctx->d.scanBlock, total, ctx->d.listCtl);
+    k_scan_sums<<<1, 1024, 0, st>>>(ctx->d.scanBlock, ctx->scanBlocks, ctx->d.listCtl);
+    k_scan_add<<<ctx->scanBlocks, 512, 0, st>>>(ctx->d.segStart, ctx->d.scanBlock, total, ctx->d.listCtl);
     k_units<true><<<smsU * 16, 128, 0, st>>>(ctx->d, ctx->maxCells);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -1005,7 +1159,12 @@ static int launchLists(sphgpu_ctx* ctx) {
     SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.listCursor, 0, sizeof(uint32_t), ctx->stream));
     // variant 3 (tests): a pool of a few blocks only, so that most units take the fallback path
     const uint32_t poolRows = ctx->variant == 3 ? std::min<uint32_t>(ctx->poolRows, 4096u) : ctx->poolRows;
-    k_pair_lists<<<unitGrid(ctx, 8, 8), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows);
+    static bool configured[64] = {}; // per device: the attribute is per device function
+    if (!configured[ctx->device & 63]) {
+        SPH_CUDA_CHECK(cudaFuncSetAttribute(k_pair_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LISTS_SMEM));
+        configured[ctx->device & 63] = true;
+    }
+    k_pair_lists<<<unitGrid(ctx, 8, 8), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows, ctx->listSkin > 0. ? ctx->listSkin : 0.);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
@@ -1014,29 +1173,23 @@ static int launchLists(sphgpu_ctx* ctx) {
 template <bool SOLID, bool CORRECTED, bool FILTER>
 static int launchSumVariant(sphgpu_ctx* ctx) {
     auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER>;
-    static bool configured = false; // per instantiation; the attribute is per device function
+    static bool configured[64] = {}; // per instantiation and device; the attribute is per device function
     const size_t smem = SumLayout<SOLID>::bytes;
-    if (!configured) {
+    if (!configured[ctx->device & 63]) {
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[ctx->device & 63] = true;
     }
     // many more CTAs than fit at once: the block scheduler balances the load (measured: 32 waves beat 8 by 1 %, 1 by 4 %)
-    kernel<<<unitGrid(ctx, 2, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
+    kernel<<<unitGrid(ctx, 3, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
-static int launchTiledVariant(sphgpu_ctx* ctx, bool onlyFallback) {
-    auto kernel = k_pair_tiled<SOLID, CORRECTED, FILTER>;
-    static bool configured = false; // per instantiation; the attribute is per device function
-    const size_t smem = TileLayout<SOLID>::bytes;
-    if (!configured) {
-        SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    kernel<<<unitGrid(ctx, 2, 8), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells, onlyFallback);
+static int launchFallback(sphgpu_ctx* ctx, bool allUnits) {
+    k_pair_fallback<SOLID, CORRECTED, FILTER><<<unitGrid(ctx, 8, 4), TILE_T, 0, ctx->stream>>>(ctx->d, ctx->maxCells, allUnits);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
@@ -1044,8 +1197,8 @@ static int launchTiledVariant(sphgpu_ctx* ctx, bool onlyFallback) {
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
 static int launchPairKernels(sphgpu_ctx* ctx) {
-    if (ctx->variant == 2) { // both phases fused in one kernel
-        return launchTiledVariant<SOLID, CORRECTED, FILTER>(ctx, false);
+    if (ctx->variant == 2) { // every unit through the direct per-target loop (cross-check of the unit bookkeeping)
+        return launchFallback<SOLID, CORRECTED, FILTER>(ctx, true);
     }
     SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[1], ctx->stream));
     int rc = launchLists(ctx);
@@ -1054,14 +1207,15 @@ static int launchPairKernels(sphgpu_ctx* ctx) {
         rc = launchSumVariant<SOLID, CORRECTED, FILTER>(ctx);
     }
     if (rc == SPHGPU_OK) { // returns at once unless the list pool overflowed
-        rc = launchTiledVariant<SOLID, CORRECTED, FILTER>(ctx, true);
+        rc = launchFallback<SOLID, CORRECTED, FILTER>(ctx, false);
     }
     SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[3], ctx->stream));
     ctx->pairTimed = true;
     return rc;
 }
 
-/// variant 0: candidate lists (k_pair_lists) + list-driven pair sums (k_pair_sum); variant 2: the fused kernel only.
+/// variant 0: candidate lists (k_pair_lists) + list-driven pair sums (k_pair_sum); variant 2: k_pair_fallback only;
+/// variant 3: as 0 with a deliberately tiny list pool (most units overflow).
 int launchPairTiled(sphgpu_ctx* ctx) {
     ctx->pairTimed = false;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->evPair[0], ctx->stream));

@@ -48,6 +48,7 @@ struct ParamsDev {
     uint32_t forces, flags, continuity_mode, lut_entries;
     double kernel_radius, radius_sqr, q_sqr_to_idx;
     double av_alpha, av_beta;
+    double av_minus_half_alpha, av_eps_over_radius_sqr; // -alpha / 2 and 0.01 / R^2 (masked pair body)
     double h_min, h_max, neigh_enforcing, neigh_lower, neigh_upper;
     uint32_t criteria, n_materials;
     double courant, derivative_factor, divergence_factor;
@@ -69,18 +70,17 @@ SPH_HD double selectD(bool c, double a, double b) {
 #endif
 }
 
-/// Reciprocal of a positive normal double: hardware seed (MUFU.RCP64H, >= 20 bits) + two Newton steps. Within 1-2 ulp,
-/// and -- unlike the compiler's IEEE division -- free of the denormal/overflow fix-up branches, which would keep the
-/// scheduler from overlapping two pair bodies. On the host (formula tests) it is a plain division.
+/// Reciprocal of a positive normal double: hardware seed (MUFU.RCP64H, >= 20 bits) + one cubically convergent step
+/// x (1 + e + e^2), e = 1 - a x (3 FMA; error e^3 <= 2^-60 plus rounding). Within 1-2 ulp, and -- unlike the compiler's
+/// IEEE division -- free of the denormal/overflow fix-up branches, which would keep the scheduler from overlapping two
+/// pair bodies. On the host (formula tests) it is a plain division.
 SPH_HD double fastRcp(double a) {
 #ifdef __CUDA_ARCH__
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-    double e = fma(-a, x, 1.);
-    x = fma(x, e, x);
-    e = fma(-a, x, 1.);
-    x = fma(x, e, x);
-    return x;
+    const double e = fma(-a, x, 1.);
+    const double t = fma(e, e, e);
+    return fma(x, t, x);
 #else
     return 1. / a;
 #endif
@@ -226,7 +226,8 @@ SPH_HD double damageRate(const MaterialDev& m, double p, const double S[5], doub
 // ---- pair interaction ------------------------------------------------------------------------------------
 
 /// What one particle contributes as a neighbour. P = p/rho^2, Sr = S/rho^2, vol = m/rho, grp = body flag or -1 if the
-/// particle is fully damaged (reduce == 0), i.e. excluded by the SUM_ONLY_UNDAMAGED filter.
+/// particle is fully damaged (reduce == 0), i.e. excluded by the SUM_ONLY_UNDAMAGED filter. The sorted records do not
+/// carry m: the loaders set m = vol * rho (one rounding, 1e-16 relative).
 struct Particle {
     double x, y, z, h;
     double vx, vy, vz;
@@ -240,6 +241,7 @@ struct Accum {
     double ax, ay, az, du, divv;
     double T[9];
     double Cm[6];
+    double F[3]; // sum of the stress-weighted kernel gradients m_j gradW (pairSums): the target's own Sr is applied once
     uint32_t cnt;
 };
 
@@ -251,22 +253,88 @@ SPH_HD void accumZero(Accum& a) {
     for (int k = 0; k < 6; ++k) {
         a.Cm[k] = 0.;
     }
+    a.F[0] = a.F[1] = a.F[2] = 0.;
     a.cnt = 0;
 }
 
 /// Exact neighbour predicate of AsymmetricSolver::loop (AsymmetricSolver.cpp:186-191): d^2 < (R * hbar)^2, evaluated
 /// without FMA contraction and in the reference's operation order so that the neighbour SETS are bit-identical.
-SPH_HD bool isNeighbour(double dx, double dy, double dz, double hi, double hj, double R, double& d2, double& hbar) {
+/// sq receives {dx^2, dy^2, dz^2, (R hbar)^2}, by-products the masked pair body reuses.
+SPH_HD bool isNeighbour(double dx, double dy, double dz, double hi, double hj, double R, double& d2, double& hbar, double sq[4]) {
 #ifdef __CUDA_ARCH__
-    d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    sq[0] = __dmul_rn(dx, dx);
+    sq[1] = __dmul_rn(dy, dy);
+    sq[2] = __dmul_rn(dz, dz);
+    d2 = __dadd_rn(__dadd_rn(sq[0], sq[1]), sq[2]);
     hbar = __dmul_rn(0.5, __dadd_rn(hi, hj));
     const double rh = __dmul_rn(R, hbar);
-    return d2 < __dmul_rn(rh, rh);
+    sq[3] = __dmul_rn(rh, rh);
+    return d2 < sq[3];
 #else
-    d2 = dx * dx + dy * dy + dz * dz;
+    sq[0] = dx * dx;
+    sq[1] = dy * dy;
+    sq[2] = dz * dz;
+    d2 = sq[0] + sq[1] + sq[2];
     hbar = 0.5 * (hi + hj);
     const double rh = R * hbar;
-    return d2 < rh * rh;
+    sq[3] = rh * rh;
+    return d2 < sq[3];
+#endif
+}
+
+SPH_HD bool isNeighbour(double dx, double dy, double dz, double hi, double hj, double R, double& d2, double& hbar) {
+    double sq[4];
+    return isNeighbour(dx, dy, dz, hi, hj, R, d2, hbar, sq);
+}
+
+/// One entry of the interleaved gradient table: {G[k], G[k + 1] - G[k]}, so that the interpolation is one 16-byte load
+/// and one FMA. Entry lut_entries is the zero guard {0, 0}.
+struct LutPair {
+    double g, dg;
+};
+
+/// Fills out[0 .. entries] from the reference table lutGrad[0 .. entries] (Kernel.h:85-101); G[entries + 1] = 0.
+inline void buildLutPairs(const double* lutGrad, uint32_t entries, LutPair* out) {
+    for (uint32_t k = 0; k <= entries; ++k) {
+        const double next = k < entries ? lutGrad[k + 1] : 0.;
+        out[k].g = lutGrad[k];
+        out[k].dg = next - lutGrad[k];
+    }
+}
+
+/// The solid record keeps the group id (body flag + 1, 0 = fully damaged, see Particle::grp) in the 8 low mantissa bits
+/// of the sound speed: cs only enters the artificial viscosity through csbar, a relative change of 2^-44 is far below
+/// the 1e-10 tolerance, and the record shrinks to 16 doubles = 128 bytes. Body flags must be below GROUP_FLAG_LIMIT.
+constexpr uint32_t GROUP_FLAG_LIMIT = 254;
+
+SPH_HD double packCsGroup(double cs, int grp) {
+    uint64_t bits;
+#ifdef __CUDA_ARCH__
+    bits = (uint64_t)__double_as_longlong(cs);
+#else
+    memcpy(&bits, &cs, 8);
+#endif
+    bits = (bits & ~0xffull) | (uint64_t)((uint32_t)(grp + 1) & 0xffu);
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)bits);
+#else
+    double r;
+    memcpy(&r, &bits, 8);
+    return r;
+#endif
+}
+
+SPH_HD void unpackCsGroup(double packed, double& cs, int& grp) {
+#ifdef __CUDA_ARCH__
+    const int lo = __double2loint(packed), hi = __double2hiint(packed);
+    grp = (lo & 0xff) - 1;
+    cs = __hiloint2double(hi, lo & ~0xff);
+#else
+    uint64_t bits;
+    memcpy(&bits, &packed, 8);
+    grp = (int)(bits & 0xffu) - 1;
+    bits &= ~0xffull;
+    memcpy(&cs, &bits, 8);
 #endif
 }
 
@@ -352,67 +420,114 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
     }
 }
 
-/// Branch-free variant of pairAccumulate used by the tiled kernel: `valid` (the exact neighbour predicate) scales the
-/// neighbour's mass / volume to zero instead of branching, and the AV condition is a select, so that two pairs can be
-/// interleaved by the scheduler (the per-pair chain 1/hbar -> q^2 -> LUT gather -> gradient is long).
-template <bool SOLID, bool CORRECTED, bool FILTER>
-SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict__ lut, const Particle& pi, const Particle& pj,
-    double dx, double dy, double dz, double d2, double hbar, bool valid, Accum& acc) {
-    acc.cnt += valid ? 1u : 0u;
-    const double mj = selectD(valid, pj.m, 0.);
+/// floor(x) and x - floor(x) of 0 <= x < 2^32 without the (quarter-rate) F2I / I2F conversions: adding 2^52 - 1/2 rounds
+/// x - 1/2 to the nearest integer, which then sits in the low mantissa bits. At an exact integer x the tie may go down
+/// (k = x - 1, frac = 1) instead of (k = x, frac = 0): the interpolated value is the same table entry either way.
+SPH_HD void floorFrac(double x, uint32_t& k, double& frac) {
+    const double MAGIC = 4503599627370496. - 0.5; // 2^52 - 1/2 (exact)
+#ifdef __CUDA_ARCH__
+    const double t = __dadd_rn(x, MAGIC);
+    k = (uint32_t)__double2loint(t);
+    frac = x - __dadd_rn(t, -4503599627370496.);
+#else
+    volatile double t = x + MAGIC;
+    uint64_t bits;
+    double tt = t;
+    memcpy(&bits, &tt, 8);
+    k = (uint32_t)bits;
+    frac = x - (tt - 4503599627370496.);
+#endif
+}
+
+// ---- the branch-free pair body of the tiled kernels, in two stages -----------------------------------------------------
+// Stage A (pairGeometry) needs only the positions, h and the densities of the pair: exact predicate, the merged
+// reciprocal, the kernel argument and the table index. Stage B (pairSums) needs the rest of the neighbour's record and
+// the table entry. k_pair_sum runs stage A of entry q + 1 before stage B of entry q, so that the table load (L2 latency)
+// and the remaining record loads of a pair are in flight while the previous pair is summed.
+// `valid` (the exact neighbour predicate) scales the neighbour's mass / volume to zero instead of branching, and the AV
+// condition is a min: straight-line code. About 95 FP64 instructions per pair (solid, corrected), no conversions.
+
+/// What stage A hands to stage B.
+struct PairGeom {
+    double dx, dy, dz; // r_i - r_j
+    double hbar;
+    double hInv5;      // hbar^-5: gradW = hInv5 G(q^2) (r_i - r_j)
+    double ratio;      // interpolation weight inside table entry k
+    double iD, irs;    // 1 / (d^2 + 0.01 hbar^2) and 1 / (rho_i + rho_j)
+    uint32_t k;
+    bool valid;
+};
+
+SPH_HD void pairGeometry(const ParamsDev& prm, double xi, double yi, double zi, double hi, double rhoi, double xj, double yj, double zj,
+    double hj, double rhoj, PairGeom& g) {
+    g.dx = xi - xj;
+    g.dy = yi - yj;
+    g.dz = zi - zj;
+    double d2, sq[4];
+    g.valid = isNeighbour(g.dx, g.dy, g.dz, hi, hj, prm.kernel_radius, d2, g.hbar, sq);
     // one reciprocal serves 1/hbar (kernel) and 1/(D rhobar) (viscosity); the factors 1/2 of rhobar and csbar are folded:
-    // rs = 2 rhobar, inv = 1 / (hbar D rs)  =>  1/hbar = D rs inv,  1/(D rhobar) = 2 hbar inv
-    const double rs = pi.rho + pj.rho;
-    const double D = fma(1.e-2 * hbar, hbar, d2);
+    // rs = 2 rhobar, inv = 1 / (hbar D rs)  =>  1/hbar = D rs inv,  1/(D rs) = hbar inv
+    const double rs = rhoi + rhoj;
+    const double D = fma(prm.av_eps_over_radius_sqr, sq[3], d2); // d^2 + 0.01 hbar^2, from (R hbar)^2
     const double A = D * rs;
-    const double inv = fastRcp(hbar * A);
+    const double inv = fastRcp(g.hbar * A);
     const double hInv = A * inv;
-    const double invA = hbar * inv; // = 1 / (2 D rhobar)
+    const double invA = g.hbar * inv;
     const double hInv2 = hInv * hInv;
     const double qSqr = d2 * hInv2;
     // branch-free table lookup: the index is clamped to the zero guard entry behind the table; rejected candidates only
-    // ever read the clamped slot and are masked by mj = 0
-    const double fidx = prm.q_sqr_to_idx * qSqr;
-    uint32_t k = (uint32_t)fidx;
-    k = k < prm.lut_entries ? k : prm.lut_entries;
-    const double ratio = fidx - (double)k;
-#ifdef __CUDA_ARCH__
-    const double g0 = __ldg(lut + k), g1 = __ldg(lut + k + 1);
-#else
-    const double g0 = lut[k], g1 = lut[k + 1];
-#endif
-    const double G = selectD(qSqr < prm.radius_sqr, g0 * (1. - ratio) + g1 * ratio, 0.);
-    const double s = hInv2 * hInv2 * hInv * G; // gradW = s d
+    // ever read a clamped (finite) slot and are masked in stage B. A valid pair has qSqr < R^2 up to rounding, where the
+    // table goes to zero quadratically, so the reference's extra `qSqr < R^2` test changes nothing above 1e-30.
+    uint32_t k;
+    floorFrac(prm.q_sqr_to_idx * qSqr, k, g.ratio);
+    g.k = k < prm.lut_entries ? k : prm.lut_entries;
+    g.hInv5 = hInv2 * hInv2 * hInv;
+    g.iD = rs * invA;
+    g.irs = D * invA;
+}
+
+/// Stage B. G = the interpolated table value g + ratio dg of entry g.k. Of pi only v, P, cs, grp are read; of pj v, m,
+/// P, cs, vol, Sr, grp. The stress sum is split: sum_j (Sr_i + Sr_j) f_j = Sr_i F + sum_j Sr_j f_j with F = sum_j f_j
+/// (acc.F, applied by finalizeParticle), which saves the target's Sr registers and two additions per pair.
+template <bool SOLID, bool CORRECTED, bool FILTER>
+SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& pj, const PairGeom& g, double G, Accum& acc) {
+    acc.cnt += g.valid ? 1u : 0u;
+    const double mj = selectD(g.valid, pj.m, 0.);
+    const double s = g.hInv5 * G; // gradW = s d
+    const double dx = g.dx, dy = g.dy, dz = g.dz;
     const double dvx = pj.vx - pi.vx, dvy = pj.vy - pi.vy, dvz = pj.vz - pi.vz;
     const double t = dvx * dx + dvy * dy + dvz * dz; // (v_j - v_i).(r_i - r_j)
     const double dvg = t * s;                        // (v_j - v_i).gradW
     const double ms = mj * s;
     const double mgx = dx * ms, mgy = dy * ms, mgz = dz * ms;
-    acc.divv += mj * dvg;
+    const double mdvg = mj * dvg;
+    acc.divv += mdvg;
     // StandardAV: mu = hbar w / D, Pi = (-alpha csbar mu + beta mu^2) / rhobar for approaching pairs (w < 0); with
     // w clamped to min(w, 0) the receding pairs give mu = 0 and Pi = 0 exactly, without a branch. Q = Pi / 2.
     const double w = fmin(-t, 0.);
-    const double mu = hbar * w * rs * invA;
-    const double Q = mu * fma(prm.av_beta, mu, (-0.5 * prm.av_alpha) * (pi.cs + pj.cs)) * (D * invA);
-    acc.du -= Q * (mj * dvg);
+    const double mu = (g.hbar * w) * g.iD;
+    const double Q = mu * fma(prm.av_beta, mu, prm.av_minus_half_alpha * (pi.cs + pj.cs)) * g.irs;
+    acc.du -= Q * mdvg;
     const double c = fma(2., Q, pi.P + pj.P);
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
     if (SOLID) {
-        bool ok = valid;
+        bool ok = g.valid;
         if (FILTER) {
-            ok = valid && (pi.grp == pj.grp) && (pi.grp >= 0);
+            ok = g.valid && (pi.grp == pj.grp) && (pi.grp >= 0);
         }
         // masked mass / volume instead of a branch around the tensor sums
         const double fs = selectD(ok, pj.m, 0.) * s;
         const double fx = dx * fs, fy = dy * fs, fz = dz * fs;
-        const double sxx = pi.Sr[0] + pj.Sr[0], syy = pi.Sr[1] + pj.Sr[1], sxy = pi.Sr[2] + pj.Sr[2],
-                     sxz = pi.Sr[3] + pj.Sr[3], syz = pi.Sr[4] + pj.Sr[4];
+        acc.F[0] += fx;
+        acc.F[1] += fy;
+        acc.F[2] += fz;
+        const double sxx = pj.Sr[0], syy = pj.Sr[1], sxy = pj.Sr[2], sxz = pj.Sr[3], syz = pj.Sr[4];
         const double szz = -sxx - syy;
-        acc.ax += sxx * fx + sxy * fy + sxz * fz;
-        acc.ay += sxy * fx + syy * fy + syz * fz;
-        acc.az += sxz * fx + syz * fy + szz * fz;
+        acc.ax = fma(sxz, fz, fma(sxy, fy, fma(sxx, fx, acc.ax)));
+        acc.ay = fma(syz, fz, fma(syy, fy, fma(sxy, fx, acc.ay)));
+        acc.az = fma(szz, fz, fma(syz, fy, fma(sxz, fx, acc.az)));
         acc.T[0] += dvx * fx;
         acc.T[1] += dvx * fy;
         acc.T[2] += dvx * fz;
@@ -423,6 +538,7 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
         acc.T[7] += dvz * fy;
         acc.T[8] += dvz * fz;
         if (CORRECTED) {
+            // (r_j - r_i) (x) gradW = -s d (x) d  (symmetric)
             const double vs = -selectD(ok, pj.vol, 0.) * s;
             const double vdx = vs * dx, vdy = vs * dy, vdz = vs * dz;
             acc.Cm[0] += vdx * dx;
@@ -433,6 +549,15 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const double* __restrict_
             acc.Cm[5] += vdy * dz;
         }
     }
+}
+
+/// Both stages for one pair (host formula tests).
+template <bool SOLID, bool CORRECTED, bool FILTER>
+SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const LutPair* __restrict__ lut2, const Particle& pi, const Particle& pj,
+    Accum& acc) {
+    PairGeom g;
+    pairGeometry(prm, pi.x, pi.y, pi.z, pi.h, pi.rho, pj.x, pj.y, pj.z, pj.h, pj.rho, g);
+    pairSums<SOLID, CORRECTED, FILTER>(prm, pi, pj, g, fma(g.ratio, lut2[g.k].dg, lut2[g.k].g), acc);
 }
 
 /// Derivatives of one particle (everything IAsymmetricSolver::afterLoop leaves in the Storage for particle i).
@@ -454,6 +579,13 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
     out.ax = acc.ax;
     out.ay = acc.ay;
     out.az = acc.az;
+    if (SOLID) { // the target's half of the stress divergence, (S_i / rho_i^2) . F  (zero F for the unsplit variants)
+        const double r2 = rhoInv * rhoInv;
+        const double sxx = S[0] * r2, syy = S[1] * r2, sxy = S[2] * r2, sxz = S[3] * r2, syz = S[4] * r2;
+        out.ax += sxx * acc.F[0] + sxy * acc.F[1] + sxz * acc.F[2];
+        out.ay += sxy * acc.F[0] + syy * acc.F[1] + syz * acc.F[2];
+        out.az += sxz * acc.F[0] + syz * acc.F[1] + (-sxx - syy) * acc.F[2];
+    }
     out.divv = acc.divv * rhoInv;
     double du = acc.du;
     double trGradv = 0.;

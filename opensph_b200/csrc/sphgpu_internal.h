@@ -34,14 +34,16 @@ enum Field : int {
 enum UField : int { U_NFLAWS, U_FLAG, U_MATID, U_NCNT, U_COUNT };
 
 // Sorted neighbour-input records (array of structures, rebuilt every integrate() in cell order). One record is what a
-// particle contributes as a neighbour: {x,y | z,h | vx,vy | vz,m | rho,P | cs,vol | Sr0,Sr1 | Sr2,Sr3 | Sr4,grp} with
-// P = p/rho^2, Sr = S/rho^2, vol = m/rho, grp = body flag or -1 (fully damaged) stored in the low word of the last
-// double. Fluid runs use the first 12 doubles only. 16-byte aligned so a record moves as double2 (LDG.128 / LDS.128).
-enum RecField : int {
-    R_X, R_Y, R_Z, R_H, R_VX, R_VY, R_VZ, R_M, R_RHO, R_P, R_CS, R_VOL, R_S0, R_S1, R_S2, R_S3, R_S4, R_GRP, R_SOLID_COUNT
-};
-constexpr int REC_SOLID = 18; // doubles per record, solid
-constexpr int REC_FLUID = 14; // doubles per record, fluid (x..vol + 16 B pad: 7 x 16 B, odd, same stride in shared memory)
+// particle contributes as a neighbour, as 16-byte PIECES {x,y | z,h | vx,vy | vz,rho | P,cs* | vol,Sr0 | Sr1,Sr2 |
+// Sr3,Sr4} with P = p/rho^2, Sr = S/rho^2, vol = m/rho (m = vol * rho is rebuilt by the loaders) and cs* = the sound
+// speed with the group id (body flag + 1, 0 = fully damaged) in its 8 low mantissa bits (sph_math.cuh: packCsGroup).
+// Solid: 8 pieces = 128 bytes; piece c of the record with sorted index t sits at position c ^ (t & 7) inside the record
+// (XOR swizzle), so that the lanes of a quarter warp that gather records with different t mod 8 hit different bank
+// groups of shared memory although the stride is a multiple of 128 bytes. Staged copies keep t mod 8 (the chunk
+// builder aligns every staged row piece accordingly), so the same loader serves global and shared memory.
+// Fluid: the first 6 pieces + 16 bytes of padding = 7 pieces (odd stride, no swizzle needed).
+constexpr int REC_SOLID = 16; // doubles per record, solid
+constexpr int REC_FLUID = 14; // doubles per record, fluid
 
 struct GridDev {
     double lo[3];
@@ -57,7 +59,20 @@ struct GridDev {
 struct StatsDev {
     unsigned int neighMin, neighMax;
     unsigned long long pairCount;
-    unsigned int fallbackUnits, pad; // units whose candidate lists did not fit the list pool (handled by the fused path)
+    unsigned int fallbackUnits; // units whose candidate lists did not fit the list pool (handled by k_pair_fallback)
+    unsigned int badFlags;      // particles whose body flag does not fit the record's group field
+};
+
+// Reuse of the cell list, the work units and the candidate lists over several steps (Verlet lists). The lists are built
+// with the search radius enlarged by (1 + skin); they stay valid (conservative supersets; the exact predicate is applied
+// by the pair-sum kernel every step) as long as  2 max_i |r_i - r_i0| / (R h_i0)  +  max_i (h_i / h_i0 - 1)  <  skin,
+// where r_i0, h_i0 are the values at build time (pos0). k_bounds measures both maxima every step, k_grid_params decides.
+struct ListCtlDev {
+    uint32_t rebuild;       // decision of the current integrate(): the build kernels run (1) or return at once (0)
+    uint32_t age;           // integrate() calls served by the current lists after the one that built them
+    uint32_t rebuilds;      // builds so far
+    uint32_t fallbackUnits; // units whose candidate lists did not fit the list pool at the last build
+    double lastMetric;      // 2 max ratio + max growth seen by the last call
 };
 
 struct TimestepDev {
@@ -81,6 +96,8 @@ struct DevicePointers {
     double* rec;        // sorted neighbour-input records, REC_SOLID or REC_FLUID doubles each
     uint32_t* sCell;    // sorted: linear cell index
     float4* posF;       // sorted: FP32 {x, y, z} relative to the grid origin and h (conservative pre-filter of the pair kernel)
+    float4* pos0;       // by slot: the same at the time the lists were built (displacement check of the list reuse)
+    ListCtlDev* listCtl;
     uint32_t* cellHmax; // [maxCells] bit pattern of the largest (float) h inside each cell
     uint32_t* order;    // sorted position -> slot
     uint32_t* cellOf;   // slot -> cell
@@ -96,15 +113,18 @@ struct DevicePointers {
     uint32_t* listCursor;    // bump allocator of the pool (rows)
     uint32_t* unitLane;  // [capacity] lane order of every unit: sorted index | upper row << 31 | ghost << 30
     double* boundsPartial; // [BOUNDS_BLOCKS * 8]
-    const double* lut;
+    const double* lut;          // (dW/dq)/q table of the reference, lut_entries + 2 doubles (direct variant)
+    const LutPair* lut2;        // the same table as {G[k], G[k+1] - G[k]} pairs, lut_entries + 1 entries (tiled kernels)
     GridDev* grid;
     StatsDev* stats;
+    StatsDev* statsInit;       // constant {min = ~0, 0, ...}: copied over stats at the start of every integrate()
     TimestepDev* tsd;
     StepStateDev* stepState;   // allocated once
     const double* dtDev;       // != null: k_predict / k_correct take dt from here (sphgpu_run_pc), not from their argument
 };
 
 constexpr int BOUNDS_BLOCKS = 592;   // 148 SMs x 4
+constexpr int BOUNDS_STRIDE = 16;    // doubles per block in boundsPartial: lo[3], hi[3], hmax, max ratio, max growth
 constexpr int SCAN_ITEMS = 4096;     // items per scan block
 
 } // namespace sph
@@ -131,6 +151,10 @@ struct sphgpu_ctx {
     double lastDt = 0.;        // MultiCriterion::lastStep
     bool lastDtInit = false;
     int variant = 0;
+    double listSkin = 0.03;    // relative enlargement of the search radius of the candidate lists (0: rebuild every step)
+    bool listsDirty = true;    // the next integrate() must rebuild (first call, particle counts changed, pool resized)
+    uint32_t listRebuilds = 0, listAge = 0; // ListCtlDev as of the last call that synchronised (collectStats)
+    double listMetric = 0.;
     uint32_t launches = 0;
     bool stateUploaded = false;
     void* halo = nullptr;      // sph::HaloState (halo.cu): NCCL communicator + exchange buffers

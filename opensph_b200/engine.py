@@ -236,6 +236,16 @@ class Engine:
     def set_variant(self, variant: int) -> None:
         _check(self.lib.sphgpu_set_variant(self._ctx, C.c_int(variant)))
 
+    def set_list_skin(self, skin: float) -> None:
+        """Relative enlargement of the candidate lists' search radius (0: the lists are rebuilt in every integrate)."""
+        _check(self.lib.sphgpu_set_list_skin(self._ctx, C.c_double(skin)))
+
+    def list_stats(self):
+        """(builds so far, calls served by the current lists, displacement metric of the last call)."""
+        r, a, m = C.c_uint32(0), C.c_uint32(0), C.c_double(0.0)
+        _check(self.lib.sphgpu_list_stats(self._ctx, C.byref(r), C.byref(a), C.byref(m)))
+        return int(r.value), int(a.value), float(m.value)
+
     def set_stream(self, cuda_stream: int) -> None:
         _check(self.lib.sphgpu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 

@@ -15,7 +15,7 @@
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
-//   sph_ref bench    --config C --n N --steps K --warmup W [--threads T] [--finder kd|grid] [--integrate-only]
+//   sph_ref bench    --config C --n N --steps K --warmup W [--threads T] [--finder kd|grid] [--integrate-only] [--fixed-dt X]
 //       prints one JSON line with seconds per step of the reference CPU path.
 //
 // Snapshot format "SPHSNAP1": u32 count, then per array {char name[32]; u32 dtype(0=f64,1=u32); u32 ncomp;
@@ -578,9 +578,13 @@ int main(int argc, char** argv) {
                     }
                 }
             } else {
-                // tiny fixed dt keeps the lattice intact so every step does the same work
-                settings.set(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP, 1.e-6_f)
-                    .set(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP, 1.e-6_f);
+                // default: the time step the config's criteria choose (initial / maximal step of the config), so the
+                // particles move; --fixed-dt X pins the step (X = 1e-6 keeps the lattice intact: identical work per step)
+                if (args.has("fixed-dt")) {
+                    const Float fixedDt = Float(atof(args.str("fixed-dt", "1e-6").c_str()));
+                    settings.set(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP, fixedDt)
+                        .set(RunSettingsId::TIMESTEPPING_MAX_TIMESTEP, fixedDt);
+                }
                 AutoPtr<ITimeStepping> stepping = Factory::getTimeStepping(settings, storage);
                 for (long s = 0; s < warmup + steps; ++s) {
                     const double t0 = now();

@@ -9,7 +9,7 @@ using namespace sph;
 
 template <bool SOLID, bool CORRECTED, bool FILTER, bool MASKED>
 static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDev>& mats, const std::vector<uint32_t>& matid,
-    const double* lut, const uint64_t* off, const uint32_t* idx, bool hasReduce, bool hasDamage) {
+    const double* lut, const LutPair* lut2, const uint64_t* off, const uint32_t* idx, bool hasReduce, bool hasDamage) {
     const uint32_t n = s->n;
     std::vector<Particle> P(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -46,6 +46,10 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         q.P = p * r2; q.vol = q.m / q.rho;
         for (int k = 0; k < 5; ++k) q.Sr[k] = S[k] * r2;
         q.grp = (hasReduce && reduce == 0.) ? -1 : (int)s->flag[i];
+        if (MASKED) { // what the device loaders see: cs carries the group id, m is rebuilt from vol * rho
+            unpackCsGroup(packCsGroup(q.cs, q.grp), q.cs, q.grp);
+            q.m = q.vol * q.rho;
+        }
     }
     for (uint32_t i = 0; i < n; ++i) {
         Accum acc;
@@ -53,11 +57,11 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         for (uint64_t k = off[i]; k < off[i + 1]; ++k) {
             const Particle& pj = P[idx[k]];
             const double dx = P[i].x - pj.x, dy = P[i].y - pj.y, dz = P[i].z - pj.z;
-            double d2, hbar;
-            const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar);
+            double d2, hbar, sq[4];
+            const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar, sq);
             if (MASKED) {
                 // the tiled kernel's branch-free body; also fed one non-neighbour per target to exercise the masking
-                pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, valid, acc);
+                pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut2, P[i], pj, acc);
             } else if (valid) {
                 pairAccumulate<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, acc);
             }
@@ -65,9 +69,9 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         if (MASKED) {
             const Particle& pj = P[(i + n / 2) % n]; // an arbitrary (almost surely non-neighbour) candidate, masked out
             const double dx = P[i].x - pj.x, dy = P[i].y - pj.y, dz = P[i].z - pj.z;
-            double d2, hbar;
-            const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar);
-            if (!valid) pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, false, acc);
+            double d2, hbar, sq[4];
+            const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar, sq);
+            if (!valid) pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut2, P[i], pj, acc);
         }
         double S[5] = { 0, 0, 0, 0, 0 };
         if (SOLID) {
@@ -95,7 +99,8 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
     prm.forces = cfg->forces; prm.flags = cfg->flags; prm.continuity_mode = cfg->continuity_mode; prm.lut_entries = cfg->lut_entries;
     prm.kernel_radius = cfg->kernel_radius; prm.radius_sqr = cfg->kernel_radius * cfg->kernel_radius;
     prm.q_sqr_to_idx = (double)cfg->lut_entries * (1. / (cfg->kernel_radius * cfg->kernel_radius));
-    prm.av_alpha = cfg->av_alpha; prm.av_beta = cfg->av_beta; prm.h_min = cfg->h_min; prm.h_max = cfg->h_max;
+    prm.av_alpha = cfg->av_alpha; prm.av_beta = cfg->av_beta;
+    prm.av_minus_half_alpha = -0.5 * cfg->av_alpha; prm.av_eps_over_radius_sqr = 1.e-2 / (cfg->kernel_radius * cfg->kernel_radius); prm.h_min = cfg->h_min; prm.h_max = cfg->h_max;
     prm.neigh_enforcing = cfg->neigh_enforcing; prm.neigh_lower = cfg->neigh_lower; prm.neigh_upper = cfg->neigh_upper;
     std::vector<MaterialDev> md(nmat);
     std::vector<uint32_t> matid(s->n, 0);
@@ -117,14 +122,17 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
     std::vector<double> lutGuard(cfg->lut_grad, cfg->lut_grad + cfg->lut_entries + 1);
     lutGuard.push_back(0.);
     const double* lutPtr = lutGuard.data();
+    std::vector<LutPair> lutPairs(cfg->lut_entries + 1);
+    buildLutPairs(cfg->lut_grad, cfg->lut_entries, lutPairs.data());
+    const LutPair* lut2 = lutPairs.data();
     const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
     const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;
-    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
-    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
-    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
-    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
-    else run<true, false, false, MASKED>(s, prm, md, matid, lutPtr, off, idx, hasReduce, hasDamage);
+    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
+    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
+    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
+    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
+    else run<true, false, false, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
     return 0;
 }
 

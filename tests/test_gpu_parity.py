@@ -30,14 +30,14 @@ def gpu_integrate(snap, setup, variant=0):
     return eng, stats
 
 
-def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=TOL):
+def check_against(eng, stats, ref, names_exact=EXACT, names_derivs=DERIVS, tol=TOL, tol_exact=1e-12):
     got = eng.download_state([k for k in names_exact + names_derivs + ("ncnt",) if k in ref])
     assert np.array_equal(got["ncnt"], ref["ncnt"]), "NEIGHBOR_CNT differs"
     assert stats.neigh_min == ref["ncnt"].min() and stats.neigh_max == ref["ncnt"].max()
     assert stats.pair_count == int(ref["ncnt"].astype(np.int64).sum())
     for k in names_exact:
         if k in ref:
-            assert_close(k, got[k], ref[k], 1e-12, FLOOR)  # (1 - D^3) cancels for D -> 1: a few hundred ulp
+            assert_close(k, got[k], ref[k], tol_exact, FLOOR)  # (1 - D^3) cancels for D -> 1: a few hundred ulp
     for k in names_derivs:
         if k in ref:
             if k == "acc":
@@ -347,3 +347,87 @@ def test_constant_velocity_gives_exactly_zero_gradient(lut):
     got = eng.download_state(["divv", "gradv"])
     eng.close()
     assert np.all(got["divv"] == 0.0) and np.all(got["gradv"] == 0.0)
+
+
+def test_symmetric_solver_golden_on_gpu(lut):
+    """the reference's SymmetricSolver output (golden hello_sym_out.snap, made with --solver sym) equals the
+    asymmetric evaluation (the reference's own cross-check, solvers/test/Solvers.cpp:178-216); the GPU path must reproduce
+    it within the parity tolerance as well."""
+    i, o = golden("hello_in.snap"), golden("hello_sym_out.snap")
+    eng, stats = gpu_integrate(i, abi.setup_from_snapshot(i, lut))
+    got = eng.download_state(["acc", "du", "drho", "dS", "divv", "ncnt"])
+    if "ncnt" in o:
+        assert np.array_equal(got["ncnt"], o["ncnt"])
+    for k in ("acc", "du", "drho", "dS", "divv"):
+        assert_close(k, got[k], o[k], TOL, FLOOR)
+    eng.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_bench_scale_preset_against_live_reference(tmp_path):
+    """BASELINE configs[2] at its full size: the 1 M-particle collision-preset lattice (jittered so that lattice sums do
+    not cancel to zero), one integrate() of the unmodified reference against the GPU path: NEIGHBOR_CNT exactly, the
+    derivatives within tolerance. Exercises the code paths small inputs never reach (thousands of work units, list pool
+    near its design load, 32-bit cell ranges)."""
+    i, o = run_ref(str(tmp_path), ["--config", "preset", "--n", 1000000, "--jitter", 31])
+    assert len(i["mass"]) > 1_000_000
+    eng, stats = gpu_integrate(i, abi.setup_from_snapshot(i))
+    # a million particles sample the cancellation of (1 - D^3) in VonMisesRheology::initialize ten times closer to D = 1
+    # than the 100 k cases do: the stress-reducing factor agrees to 2e-12 instead of 1e-12
+    check_against(eng, stats, o, tol_exact=1e-11)
+    eng.close()
+
+
+def test_list_reuse_matches_rebuild_every_step(lut):
+    """The candidate lists are conservative supersets built with a skin; the exact predicate runs every step. A run that
+    reuses them (device-side displacement check decides when to rebuild) must give the same neighbour counts and, up to
+    summation order, the same state as a run that rebuilds in every step -- while the particles really move."""
+    from opensph_b200 import workloads
+    state = workloads.basalt_sphere_state(20000)
+    state["vel"] = state["vel"] * 60.0  # ~3 km/s: a step moves particles by a few percent of h
+    n = len(state["mass"])
+    setup = workloads.make_setup(n)
+    names = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "damage", "ddamage", "reduce",
+             "eps_min", "m_zero", "growth", "n_flaws", "flag")
+    out = {}
+    for skin in (0.0, 0.04):
+        eng = Engine(setup, n)
+        eng.set_list_skin(skin)
+        eng.upload_state(state, names)
+        steps = 40
+        ncnts = []
+        dts, _, _ = eng.run_pc(steps // 2, 0.01, 10.0)
+        ncnts.append(eng.download_state(["ncnt"])["ncnt"])
+        dts2, _, _ = eng.run_pc(steps // 2, float(dts[-1]), 10.0)
+        ncnts.append(eng.download_state(["ncnt"])["ncnt"])
+        out[skin] = (eng.download_state(["pos", "vel", "rho", "u", "S", "damage", "acc", "du", "drho", "dS"]), np.concatenate([dts, dts2]),
+                     eng.list_stats(), ncnts)
+        eng.close()
+    (a, dta, sa, na), (b, dtb, sb, nb) = out[0.0], out[0.04]
+    moved = np.abs(a["pos"][:, :3] - state["pos"][:, :3]).max() / state["pos"][0, 3]
+    assert moved > 0.1, f"the test must move the particles (max displacement {moved:.3f} h)"
+    assert sa[0] == 40, sa
+    assert 2 <= sb[0] < 30, f"expected a few rebuilds with the skin, got {sb}"
+    for x, y in zip(na, nb):
+        assert np.array_equal(x, y), "NEIGHBOR_CNT differs between reused and rebuilt lists"
+    assert np.allclose(dta, dtb, rtol=1e-11, atol=0)
+    for k in a:
+        assert_close(k, b[k], a[k], 1e-9, FLOOR)
+
+
+def test_multi_gpu_parity_script():
+    """tests/run_mgpu_parity.py (two ranks: NCCL halo exchange, batched stepping, repartition) against a single-domain run;
+    needs two GPUs on the box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from conftest import ROOT
+    env = dict(os.environ, MGPU_PARTICLES="120000")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(ROOT, "tests", "run_mgpu_parity.py")], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MGPU PARITY OK" in r.stdout, r.stdout[-3000:]
