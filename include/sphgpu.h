@@ -213,6 +213,15 @@ SPHGPU_API int sphgpu_comm_init(sphgpu_ctx* ctx, const void* id128, int rank, in
 SPHGPU_API int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32_t send_left, uint32_t send_right,
     uint32_t recv_left, uint32_t recv_right);
 SPHGPU_API int sphgpu_halo_exchange(sphgpu_ctx* ctx);
+/* Guard of the fixed send bands: the cut planes of this rank's domain perpendicular to `axis` (has_lo / has_hi: there is
+ * a neighbour behind that plane). Every exchange then measures the smallest head-room of an interior particle (one that
+ * is in neither band) towards a plane, (distance / (R (h_i + h_max) / 2)) - 1. Once it would be negative the next
+ * synchronising call fails with SPHGPU_E_STATE instead of silently missing cross-rank neighbours (the caller repartitions
+ * and calls sphgpu_halo_configure again). sphgpu_halo_margin returns the head-room seen at the last synchronisation, so a
+ * driver can repartition before that happens. The reference's analogue of stale ghosts is GhostParticles being
+ * regenerated in every IBoundaryCondition::initialize (core/sph/boundary/Boundary.cpp). */
+SPHGPU_API int sphgpu_halo_set_guard(sphgpu_ctx* ctx, int axis, double lo_plane, double hi_plane, int has_lo, int has_hi);
+SPHGPU_API int sphgpu_halo_margin(sphgpu_ctx* ctx, double* margin);
 SPHGPU_API int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
 /* `steps` PredictorCorrector steps queued back to back: the time step chosen by the criteria (MultiCriterion::compute,
  * TimeStepCriterion.cpp:389-419, evaluated by a device kernel) stays on the device and feeds the next step, so the host

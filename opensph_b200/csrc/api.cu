@@ -13,7 +13,6 @@ void setError(const std::string& msg) {
     g_lastError = msg;
 }
 
-int uploadConstants(const sphgpu_ctx* ctx); // pair.cu
 
 static int fail(int code, const std::string& msg) {
     setError(msg);
@@ -268,7 +267,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         }
         SPH_TRY(wrap(cudaMemcpy(ctx->d.u[U_MATID], matid.data(), sizeof(uint32_t) * cap, cudaMemcpyHostToDevice), "init"));
     }
-    SPH_TRY(uploadConstants(ctx));
+    SPH_TRY(ensureConstants(ctx));
 #undef SPH_TRY
     *out = ctx;
     return SPHGPU_OK;
@@ -280,6 +279,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    forgetConstants(ctx);
     destroyHalo(ctx);
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
@@ -394,6 +394,7 @@ int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles) {
     ctx->n = n_particles;
     ctx->nActive = n_particles; // ghosts are dropped; the caller appends them again (sphgpu_set_active)
     ctx->listsDirty = true;
+    invalidateHalo(ctx); // the band slot ranges referred to the old particle set
     return SPHGPU_OK;
 }
 
@@ -452,6 +453,7 @@ namespace sph {
 // Queues one integrate() on the stream; events 0..3 bracket grid build / prologue / pair kernel.
 int enqueueIntegrate(sphgpu_ctx* ctx) {
     int rc;
+    if ((rc = ensureConstants(ctx)) != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
     SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->d.stats, ctx->d.statsInit, sizeof(StatsDev), cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = launchGridBuild(ctx)) != SPHGPU_OK) return rc;
@@ -473,6 +475,15 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
     ctx->listRebuilds = lc.rebuilds;
     ctx->listAge = lc.age;
     ctx->listMetric = lc.lastMetric;
+    {
+        float m;
+        std::memcpy(&m, &lc.haloMarginBits, sizeof(m));
+        ctx->haloMargin = m;
+    }
+    if (lc.haloViolation != 0u) {
+        return fail(SPHGPU_E_STATE, "halo band outgrown: an interior particle has come within the kernel reach of a cut plane "
+                                    "(neighbours on the other rank would be missed); repartition and configure the halo again");
+    }
     float ms = 0.f;
     for (int k = 0; k < 3; ++k) {
         SPH_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[k], ctx->ev[k + 1]));

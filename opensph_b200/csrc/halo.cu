@@ -60,6 +60,9 @@ static NcclApi* ncclApi() {
     } while (0)
 
 struct HaloState {
+    int guardAxis = -1;            // cut planes perpendicular to this axis (sphgpu_halo_set_guard); -1: no guard
+    double guardLo = 0., guardHi = 0.;
+    bool guardHasLo = false, guardHasHi = false;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     int left = -1, right = -1;
@@ -67,28 +70,90 @@ struct HaloState {
     double *bufSendL = nullptr, *bufSendR = nullptr, *bufRecvL = nullptr, *bufRecvR = nullptr;
 };
 
+// The bands a rank sends are fixed slot ranges chosen at decomposition time. An INTERIOR particle (neither band) that
+// comes within reach R (h_i + h_max) / 2 of a cut plane would need neighbours the other rank never sends -- and would be
+// needed by them. The guard measures the smallest head-room every exchange; a negative one raises a sticky flag that
+// turns the next synchronising call into SPHGPU_E_STATE ("repartition"), so neighbours are never lost silently.
+// h_max bound: the grid's h_max at the last list build times (1 + skin) -- the list reuse rebuilds before h grows more.
+__global__ void __launch_bounds__(256) k_halo_guard(DevicePointers d, uint32_t first, uint32_t last, int axis, double lo, double hi, bool hasLo,
+    bool hasHi, double kernelRadius, double skin) {
+    const double hmax = d.grid->hmax * (1. + skin);
+    float margin = 3.0e38f;
+    for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < last; i += gridDim.x * blockDim.x) {
+        const double x = d.f[F_X + axis][i];
+        const double reach = 0.5 * kernelRadius * (d.f[F_H][i] + hmax);
+        if (hasLo) {
+            margin = fminf(margin, (float)((x - lo) / reach - 1.));
+        }
+        if (hasHi) {
+            margin = fminf(margin, (float)((hi - x) / reach - 1.));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        margin = fminf(margin, __shfl_xor_sync(0xffffffffu, margin, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (margin < 0.f) {
+            d.listCtl->haloViolation = 1u;
+            margin = 0.f;
+        }
+        atomicMin(&d.listCtl->haloMarginBits, __float_as_int(margin));
+    }
+}
+
 static int exchange(sphgpu_ctx* ctx) {
     HaloState* h = static_cast<HaloState*>(ctx->halo);
     NcclApi* api = ncclApi();
     const uint32_t n = ctx->n;
+    if (h->sendLeft + h->sendRight > n || (uint64_t)n + h->recvLeft + h->recvRight > ctx->capacity) {
+        setError("the halo configuration does not fit the current particle count: call sphgpu_halo_configure again");
+        return SPHGPU_E_STATE;
+    }
     int rc;
     if ((rc = launchHalo(ctx, true, 0, h->sendLeft, h->bufSendL)) != SPHGPU_OK) return rc;
     if ((rc = launchHalo(ctx, true, n - h->sendRight, h->sendRight, h->bufSendR)) != SPHGPU_OK) return rc;
+    if (h->guardAxis >= 0 && n > h->sendLeft + h->sendRight) {
+        const int inf = 0x7f7fffff; // FLT_MAX
+        SPH_CUDA_CHECK(cudaMemcpyAsync(&ctx->d.listCtl->haloMarginBits, &inf, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        k_halo_guard<<<296, 256, 0, ctx->stream>>>(ctx->d, h->sendLeft, n - h->sendRight, h->guardAxis, h->guardLo, h->guardHi, h->guardHasLo,
+            h->guardHasHi, ctx->prm.kernel_radius, ctx->listSkin > 0. ? ctx->listSkin : 0.);
+        ctx->launches += 1;
+    }
     const size_t w = SPHGPU_HALO_DOUBLES;
-    SPH_NCCL_CHECK(api->GroupStart());
-    if (h->left >= 0) {
-        if (h->sendLeft) SPH_NCCL_CHECK(api->Send(h->bufSendL, w * h->sendLeft, ncclFloat64, h->left, h->comm, ctx->stream));
-        if (h->recvLeft) SPH_NCCL_CHECK(api->Recv(h->bufRecvL, w * h->recvLeft, ncclFloat64, h->left, h->comm, ctx->stream));
+    // (every operation of the group is attempted and the group is always closed, also after an error)
+    ncclResult_t nr = api->GroupStart();
+    auto keep = [&](ncclResult_t r) {
+        if (nr == ncclSuccess) {
+            nr = r;
+        }
+    };
+    if (nr == ncclSuccess) {
+        if (h->left >= 0) {
+            if (h->sendLeft) keep(api->Send(h->bufSendL, w * h->sendLeft, ncclFloat64, h->left, h->comm, ctx->stream));
+            if (h->recvLeft) keep(api->Recv(h->bufRecvL, w * h->recvLeft, ncclFloat64, h->left, h->comm, ctx->stream));
+        }
+        if (h->right >= 0) {
+            if (h->sendRight) keep(api->Send(h->bufSendR, w * h->sendRight, ncclFloat64, h->right, h->comm, ctx->stream));
+            if (h->recvRight) keep(api->Recv(h->bufRecvR, w * h->recvRight, ncclFloat64, h->right, h->comm, ctx->stream));
+        }
+        keep(api->GroupEnd());
     }
-    if (h->right >= 0) {
-        if (h->sendRight) SPH_NCCL_CHECK(api->Send(h->bufSendR, w * h->sendRight, ncclFloat64, h->right, h->comm, ctx->stream));
-        if (h->recvRight) SPH_NCCL_CHECK(api->Recv(h->bufRecvR, w * h->recvRight, ncclFloat64, h->right, h->comm, ctx->stream));
+    if (nr != ncclSuccess) {
+        setError(std::string("NCCL halo exchange: ") + (api->GetErrorString ? api->GetErrorString(nr) : "NCCL error"));
+        return SPHGPU_E_CUDA;
     }
-    SPH_NCCL_CHECK(api->GroupEnd());
     if ((rc = launchHalo(ctx, false, n, h->recvLeft, h->bufRecvL)) != SPHGPU_OK) return rc;
     if ((rc = launchHalo(ctx, false, n + h->recvLeft, h->recvRight, h->bufRecvR)) != SPHGPU_OK) return rc;
     ctx->launches += 4;
     return SPHGPU_OK;
+}
+
+void invalidateHalo(sphgpu_ctx* ctx) {
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    if (h) {
+        h->sendLeft = h->sendRight = 0xffffffffu; // fails the range check of exchange()
+        h->recvLeft = h->recvRight = 0u;
+    }
 }
 
 void destroyHalo(sphgpu_ctx* ctx) {
@@ -138,7 +203,14 @@ int sphgpu_comm_init(sphgpu_ctx* ctx, const void* id128, int rank, int world) {
     h->world = world;
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
-    SPH_NCCL_CHECK(api->CommInitRank(&h->comm, world, id, rank));
+    {
+        const ncclResult_t r = api->CommInitRank(&h->comm, world, id, rank);
+        if (r != ncclSuccess) {
+            delete h;
+            setError(std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(r) : "NCCL error"));
+            return SPHGPU_E_CUDA;
+        }
+    }
     ctx->halo = h;
     return SPHGPU_OK;
 }
@@ -168,6 +240,35 @@ int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32
     SPH_CUDA_CHECK(cudaMalloc(&h->bufRecvL, std::max<size_t>(w * h->recvLeft, 16)));
     SPH_CUDA_CHECK(cudaMalloc(&h->bufRecvR, std::max<size_t>(w * h->recvRight, 16)));
     ctx->nActive = ctx->n + h->recvLeft + h->recvRight;
+    ctx->listsDirty = true; // another set of ghosts
+    SPH_CUDA_CHECK(cudaMemsetAsync(&ctx->d.listCtl->haloViolation, 0, sizeof(uint32_t), ctx->stream));
+    return SPHGPU_OK;
+}
+
+int sphgpu_halo_set_guard(sphgpu_ctx* ctx, int axis, double lo_plane, double hi_plane, int has_lo, int has_hi) {
+    if (!ctx || !ctx->halo) {
+        setError("sphgpu_comm_init must be called first");
+        return SPHGPU_E_STATE;
+    }
+    if (axis < -1 || axis > 2) {
+        setError("axis must be 0, 1, 2 or -1 (guard off)");
+        return SPHGPU_E_INVALID;
+    }
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    h->guardAxis = axis;
+    h->guardLo = lo_plane;
+    h->guardHi = hi_plane;
+    h->guardHasLo = has_lo != 0;
+    h->guardHasHi = has_hi != 0;
+    return SPHGPU_OK;
+}
+
+int sphgpu_halo_margin(sphgpu_ctx* ctx, double* margin) {
+    if (!ctx || !margin) {
+        setError("null argument");
+        return SPHGPU_E_INVALID;
+    }
+    *margin = ctx->haloMargin;
     return SPHGPU_OK;
 }
 

@@ -3,6 +3,7 @@
 // filter, kernel.grad, derivatives.eval) together with material->initialize (AsymmetricSolver.cpp:75-79),
 // accumulated.store + equations.finalize (:204-216) and material->finalize (:90-95).
 #include "sphgpu_internal.h"
+#include <mutex>
 
 namespace sph {
 
@@ -13,6 +14,35 @@ int uploadConstants(const sphgpu_ctx* ctx) {
     SPH_CUDA_CHECK(cudaMemcpyToSymbol(c_prm, &ctx->prm, sizeof(ParamsDev)));
     SPH_CUDA_CHECK(cudaMemcpyToSymbol(c_mats, ctx->matsHost, sizeof(MaterialDev) * MAX_MATERIALS));
     return SPHGPU_OK;
+}
+
+// The run-level constants live in __constant__ symbols, which are per device, not per context. Every entry point that
+// launches kernels calls ensureConstants first: if another context of this device launched last, the device is drained
+// (that context's kernels may still be reading the symbols) and this context's constants are uploaded. Contexts with
+// different settings can therefore coexist on one device; alternating between them costs a device synchronisation.
+static std::mutex g_constMutex;
+static const sphgpu_ctx* g_constOwner[64] = {};
+
+int ensureConstants(const sphgpu_ctx* ctx) {
+    std::lock_guard<std::mutex> lock(g_constMutex);
+    const int dev = ctx->device & 63;
+    if (g_constOwner[dev] == ctx) {
+        return SPHGPU_OK;
+    }
+    if (g_constOwner[dev] != nullptr) {
+        SPH_CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    const int rc = uploadConstants(ctx);
+    g_constOwner[dev] = rc == SPHGPU_OK ? ctx : nullptr;
+    return rc;
+}
+
+void forgetConstants(const sphgpu_ctx* ctx) {
+    std::lock_guard<std::mutex> lock(g_constMutex);
+    const int dev = ctx->device & 63;
+    if (g_constOwner[dev] == ctx) {
+        g_constOwner[dev] = nullptr;
+    }
 }
 
 /// FP32 copy of a position relative to the grid origin (the pre-filter of the tiled pair kernel compares these; targets

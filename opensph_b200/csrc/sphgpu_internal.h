@@ -73,6 +73,10 @@ struct ListCtlDev {
     uint32_t rebuilds;      // builds so far
     uint32_t fallbackUnits; // units whose candidate lists did not fit the list pool at the last build
     double lastMetric;      // 2 max ratio + max growth seen by the last call
+    // halo guard (halo.cu): smallest head-room of an interior particle towards a cut plane, in units of its reach
+    // R (h_i + h_max) / 2; negative = an interior particle has come within reach of the other rank: neighbours are missing
+    int haloMarginBits;     // bit pattern of a non-negative float (atomicMin), reset to +inf by every exchange
+    uint32_t haloViolation; // sticky until the halo is configured again
 };
 
 struct TimestepDev {
@@ -155,6 +159,7 @@ struct sphgpu_ctx {
     bool listsDirty = true;    // the next integrate() must rebuild (first call, particle counts changed, pool resized)
     uint32_t listRebuilds = 0, listAge = 0; // ListCtlDev as of the last call that synchronised (collectStats)
     double listMetric = 0.;
+    double haloMargin = 0.;    // head-room seen by the halo guard at the last exchange (collectStats)
     uint32_t launches = 0;
     bool stateUploaded = false;
     void* halo = nullptr;      // sph::HaloState (halo.cu): NCCL communicator + exchange buffers
@@ -177,6 +182,8 @@ void setError(const std::string& msg);
 int launchGridBuild(sphgpu_ctx* ctx);
 int launchSegments(sphgpu_ctx* ctx);
 // pair.cu
+int ensureConstants(const sphgpu_ctx* ctx);  // this context's ParamsDev / MaterialDev are the ones in constant memory
+void forgetConstants(const sphgpu_ctx* ctx);
 int launchProloguePack(sphgpu_ctx* ctx);
 int launchProloguePackPositionsOnly(sphgpu_ctx* ctx);
 int launchPair(sphgpu_ctx* ctx);
@@ -199,5 +206,6 @@ int enqueueIntegrate(sphgpu_ctx* ctx);
 int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEvent_t end);
 int finishTimestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out);
 void destroyHalo(sphgpu_ctx* ctx);
+void invalidateHalo(sphgpu_ctx* ctx); // the exchange refuses to run until sphgpu_halo_configure is called again
 
 } // namespace sph

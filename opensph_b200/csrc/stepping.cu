@@ -336,6 +336,12 @@ int launchFinishTimestep(sphgpu_ctx* ctx, double maxDt, StepRecordDev* history, 
 }
 
 int launchPredict(sphgpu_ctx* ctx, double dt) {
+    {
+        const int rcConst = ensureConstants(ctx);
+        if (rcConst != SPHGPU_OK) {
+            return rcConst;
+        }
+    }
     const uint32_t n = ctx->n;
     if (n == 0) {
         return SPHGPU_OK;
@@ -347,6 +353,12 @@ int launchPredict(sphgpu_ctx* ctx, double dt) {
 }
 
 int launchCorrect(sphgpu_ctx* ctx, double dt) {
+    {
+        const int rcConst = ensureConstants(ctx);
+        if (rcConst != SPHGPU_OK) {
+            return rcConst;
+        }
+    }
     const uint32_t n = ctx->n;
     if (n == 0) {
         return SPHGPU_OK;
@@ -358,6 +370,12 @@ int launchCorrect(sphgpu_ctx* ctx, double dt) {
 }
 
 int launchEuler(sphgpu_ctx* ctx, double dt) {
+    {
+        const int rcConst = ensureConstants(ctx);
+        if (rcConst != SPHGPU_OK) {
+            return rcConst;
+        }
+    }
     const uint32_t n = ctx->n;
     if (n == 0) {
         return SPHGPU_OK;
@@ -369,6 +387,12 @@ int launchEuler(sphgpu_ctx* ctx, double dt) {
 }
 
 int launchCriteria(sphgpu_ctx* ctx) {
+    {
+        const int rcConst = ensureConstants(ctx);
+        if (rcConst != SPHGPU_OK) {
+            return rcConst;
+        }
+    }
     const uint32_t n = ctx->n;
     TimestepDev init;
     const double inf = INFTY_REF;

@@ -25,6 +25,7 @@ from . import abi, workloads
 DYNAMIC_FIELDS: Tuple[Tuple[str, int], ...] = (("pos", 4), ("vel", 4), ("rho", 1), ("u", 1), ("S", 5), ("damage", 1))
 STATIC_FIELDS: Tuple[Tuple[str, int], ...] = (("mass", 1),)
 STATIC_U32: Tuple[str, ...] = ("flag",)
+HALO_MARGIN = 0.25  # relative head-room of the send bands beyond the kernel reach R h_max
 
 
 def sphere_cut_planes(radius: float, parts: int) -> np.ndarray:
@@ -68,7 +69,9 @@ class SlabDomain:
         self.cuts = sphere_cut_planes(radius, world)
         volume = 4.0 / 3.0 * math.pi * radius ** 3
         self.h = (volume / n_target) ** (1.0 / 3.0) * workloads.BASALT["eta"]
-        self.halo_width = 2.0 * self.h * 1.05  # kernel radius * h_max with head-room for adaptive h
+        # kernel radius * h_max with head-room for drifting particles and growing h: the bands are fixed slot ranges, the
+        # library's halo guard (sphgpu_halo_set_guard) reports how much of the head-room is left and fails hard at zero
+        self.halo_width = 2.0 * self.h * (1.0 + HALO_MARGIN)
         self.lo_plane = float(self.cuts[rank]) if rank > 0 else None
         self.hi_plane = float(self.cuts[rank + 1]) if rank < world - 1 else None
         self.n_left = self.n_right = 0
@@ -211,6 +214,7 @@ def repartition(dom: "SlabDomain", eng, names: Sequence[str] = MIGRATE_FIELDS, a
     import torch
     import torch.distributed as dist
     state = eng.download_state([k for k in names])
+    state["material_id"] = eng.download("MATERIAL_ID", 0, 0, eng.n) if hasattr(eng, "download") else np.zeros(len(state["pos"]), np.uint32)
     axis = dom.axis
     cuts = balanced_cut_planes(state["pos"][:, axis], dom.world, dist)
     dest = np.clip(np.searchsorted(cuts[1:-1], state["pos"][:, axis], side="right"), 0, dom.world - 1)
@@ -218,7 +222,7 @@ def repartition(dom: "SlabDomain", eng, names: Sequence[str] = MIGRATE_FIELDS, a
     # halo width from the CURRENT largest smoothing length of the whole run
     hmax = torch.tensor([float(state["pos"][:, 3].max()) if len(state["pos"]) else 0.0], dtype=torch.float64, device=_dist_device(dist))
     dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
-    dom.adopt_cuts(cuts, kernel_radius * float(hmax.item()) * 1.05)
+    dom.adopt_cuts(cuts, kernel_radius * float(hmax.item()) * (1.0 + HALO_MARGIN))
     perm, dom.n_left, dom.n_right = band_partition(state["pos"][:, axis], dom.lo_plane, dom.hi_plane, dom.halo_width)
     state = {k: (v[perm] if isinstance(v, np.ndarray) and v.shape[:1] == (len(perm),) else v) for k, v in state.items()}
     n_new = len(perm)
@@ -226,6 +230,8 @@ def repartition(dom: "SlabDomain", eng, names: Sequence[str] = MIGRATE_FIELDS, a
         raise ValueError(f"rank {dom.rank}: {n_new} particles after migration exceed the engine capacity {eng.capacity}")
     eng.set_particle_count(n_new)
     eng.upload_state(state, names)
+    if hasattr(eng, "upload") and n_new:
+        eng.upload("MATERIAL_ID", 0, state["material_id"].astype(np.uint32))
     halo = HaloExchange(dom, eng, state, adapter=adapter)
     return state, halo
 
@@ -297,6 +303,8 @@ class HaloExchange:
                 eng._comm_ready = True
             eng.halo_configure(-1 if self.left is None else self.left, -1 if self.right is None else self.right,
                                dom.n_left, dom.n_right, self.g_left, self.g_right)
+            if hasattr(eng, "halo_set_guard"):
+                eng.halo_set_guard(dom.axis, dom.lo_plane, dom.hi_plane)
 
     def _exchange_counts(self, n_left: int, n_right: int) -> Tuple[int, int]:
         torch, dist = self.torch, self.dist
@@ -344,11 +352,24 @@ class HaloExchange:
         fields = tuple((k, c) for k, c in STATIC_FIELDS if k in state)
         if fields:
             self._run(fields)
-        # flag / material id of the ghosts: single body, single material in the slab workloads
-        n_g = self.g_left + self.g_right
-        if n_g and hasattr(self.eng, "upload"):
-            self.eng.upload("FLAG", 0, np.zeros(n_g, np.uint32), first=self.n)
-            self.eng.upload("MATERIAL_ID", 0, np.zeros(n_g, np.uint32), first=self.n)
+        # Body flag and material id of the ghosts come from their owners (a ghost of another body must not pass the
+        # SUM_ONLY_UNDAMAGED group test, and its EoS / rheology constants are its material's): the band's values travel
+        # once, as doubles (u32 is exact in a double), over the same point-to-point pattern.
+        if not hasattr(self.eng, "upload"):
+            return
+        torch = self.torch
+        dev = _dist_device(self.dist)
+        nl, nr = self.dom.n_left, self.dom.n_right
+        for q in ("FLAG", "MATERIAL_ID"):
+            own = self.eng.download(q, 0, 0, self.n).astype(np.float64) if self.n else np.zeros(0)
+            sl = torch.from_numpy(np.ascontiguousarray(own[:nl])).to(dev)
+            sr = torch.from_numpy(np.ascontiguousarray(own[self.n - nr:] if nr else own[:0])).to(dev)
+            rl = torch.zeros(max(self.g_left, 1), dtype=torch.float64, device=dev)[: self.g_left]
+            rr = torch.zeros(max(self.g_right, 1), dtype=torch.float64, device=dev)[: self.g_right]
+            self._p2p(sl, sr, rl, rr)
+            ghosts = np.concatenate([rl.cpu().numpy(), rr.cpu().numpy()]).astype(np.uint32)
+            if len(ghosts):
+                self.eng.upload(q, 0, ghosts, first=self.n)
 
     def exchange(self) -> None:
         """Refreshes the dynamic neighbour inputs of all ghosts; call after predict and before integrate."""

@@ -236,6 +236,17 @@ class Engine:
     def set_variant(self, variant: int) -> None:
         _check(self.lib.sphgpu_set_variant(self._ctx, C.c_int(variant)))
 
+    def halo_set_guard(self, axis: int, lo_plane, hi_plane) -> None:
+        """Cut planes of this rank's domain (None: no neighbour on that side); see sphgpu_halo_set_guard."""
+        _check(self.lib.sphgpu_halo_set_guard(self._ctx, C.c_int(axis), C.c_double(0.0 if lo_plane is None else lo_plane),
+                                              C.c_double(0.0 if hi_plane is None else hi_plane), C.c_int(lo_plane is not None),
+                                              C.c_int(hi_plane is not None)))
+
+    def halo_margin(self) -> float:
+        m = C.c_double(0.0)
+        _check(self.lib.sphgpu_halo_margin(self._ctx, C.byref(m)))
+        return float(m.value)
+
     def set_list_skin(self, skin: float) -> None:
         """Relative enlargement of the candidate lists' search radius (0: the lists are rebuilt in every integrate)."""
         _check(self.lib.sphgpu_set_list_skin(self._ctx, C.c_double(skin)))

@@ -114,6 +114,26 @@ def main():
                 ok2 &= e <= 1e-9
         print("MGPU REPARTITION", "OK" if ok2 else "FAILED", f"owned before={n_before} (rank 0) after={[len(g['ncnt']) for g in gathered2]}")
         ok &= bool(ok2)
+    # ---- halo guard: grow every smoothing length by 30 %; the fixed send bands (head-room 25 %) are then too narrow. The
+    # first step still passes (the guard's h_max bound is the one of the last list build), the next exchange must fail
+    # hard on every rank that has a neighbour -- never silently drop cross-rank neighbours.
+    from opensph_b200.engine import SphGpuError
+    from opensph_b200 import abi
+    margin_before = eng.halo_margin()
+    pos = eng.download_state(["pos"])["pos"]
+    pos[:, 3] *= 1.3
+    eng.upload("POSITION", 0, pos)
+    raised = False
+    try:
+        for _ in range(3):
+            eng.step_pc_mgpu(1.0e-6, 1.0e-6)
+    except SphGpuError as e:
+        raised = e.code == abi.E_STATE
+    guard_ok = torch.tensor([1 if (raised and margin_before > 0.0) else 0], device="cuda")
+    dist.all_reduce(guard_ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MGPU HALO GUARD", "OK" if int(guard_ok.item()) else "FAILED", f"head-room before growing h: {margin_before:.3f}")
+        ok &= bool(int(guard_ok.item()))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -67,6 +67,11 @@ class NumpyEngine:
         if name in self.a:
             self.a[name][first:first + len(arr)] = arr
 
+    def download(self, quantity, order=0, first=0, count=None):
+        name = {"FLAG": "flag", "MATERIAL_ID": "matid"}[quantity]
+        count = self.n - first if count is None else count
+        return self.a[name][first:first + count].copy() if name in self.a else np.zeros(count, np.uint32)
+
 
 class NumpyAdapter:
     def __init__(self, eng):
@@ -101,10 +106,16 @@ def _worker(rank, world, n_target, tmpdir):
     dom = decomp.SlabDomain(n_target, world, rank, radius=1.0e3, solid=True)
     state = dom.generate_owned()
     n_owned = len(state["mass"])
+    # two "bodies" and two "materials" split by a plane that crosses every slab: ghosts must arrive with their owner's values
+    state["flag"] = (state["pos"][:, 0] > 0.0).astype(np.uint32)
+    state["matid"] = (state["pos"][:, 1] > 0.0).astype(np.uint32)
     eng = NumpyEngine(state, dom.capacity(n_owned))
     halo = decomp.HaloExchange(dom, eng, state, adapter=NumpyAdapter(eng))
     halo.exchange()
     n_act = halo.n_active
+    assert np.array_equal(eng.a["flag"][n_owned:n_act], (eng.a["pos"][n_owned:n_act, 0] > 0.0).astype(np.uint32))
+    assert np.array_equal(eng.a["matid"][n_owned:n_act], (eng.a["pos"][n_owned:n_act, 1] > 0.0).astype(np.uint32))
+    eng.a["flag"][:n_act] = 0  # (the oracle check below runs the single-body setup)
     snap = {k: v[:n_act].copy() for k, v in eng.a.items()}
     # ghosts: static per-particle constants that only matter for targets get neutral values
     for k, fill in (("reduce", 1.0), ("eps_min", 1.0), ("m_zero", 1.0), ("growth", 0.0)):
