@@ -191,6 +191,15 @@ SPHGPU_API uint32_t sphgpu_abi_version(void);
 SPHGPU_API int sphgpu_upload(sphgpu_ctx* ctx, int q, int order, int layout, const void* host, uint32_t first, uint32_t count);
 SPHGPU_API int sphgpu_download(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count);
 /* Same, PACKED layout only, with a DEVICE pointer on the context's device (used by the multi-GPU halo plumbing). */
+/* Asynchronous variants for drivers that keep the Storage on the host and move it every step: the calls only queue work.
+ * Uploads are ordered with the kernels on the context's stream; downloads are packed on that stream and copied out on a
+ * second stream, so that the device -> host transfer of one step overlaps with the host -> device transfer of the next
+ * (PCIe is full duplex). The host buffers must stay valid -- and, to really be asynchronous, be page-locked -- until
+ * sphgpu_transfer_sync returns. The downloads of one step form a batch, closed by sphgpu_download_batch_end. */
+SPHGPU_API int sphgpu_upload_async(sphgpu_ctx* ctx, int q, int order, int layout, const void* host, uint32_t first, uint32_t count);
+SPHGPU_API int sphgpu_download_async(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count);
+SPHGPU_API int sphgpu_download_batch_end(sphgpu_ctx* ctx);
+SPHGPU_API int sphgpu_transfer_sync(sphgpu_ctx* ctx);
 SPHGPU_API int sphgpu_upload_device(sphgpu_ctx* ctx, int q, int order, const void* dev, uint32_t first, uint32_t count);
 SPHGPU_API int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_t first, uint32_t count);
 /* Halo exchange helpers (multi-GPU): pack / unpack the dynamic neighbour inputs {r,h | v,dh/dt | rho | u | S[5] | D}

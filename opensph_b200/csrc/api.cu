@@ -294,6 +294,10 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
         if (k < 4 && ctx->evPair[k]) cudaEventDestroy(ctx->evPair[k]);
     }
     if (ctx->privateStream) cudaStreamDestroy(ctx->privateStream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->evPacked) cudaEventDestroy(ctx->evPacked);
+    if (ctx->evCopied) cudaEventDestroy(ctx->evCopied);
+    cudaFree(ctx->stagingDown);
     cudaGetLastError();
     delete ctx;
     return SPHGPU_OK;
@@ -337,6 +341,77 @@ int sphgpu_download(sphgpu_ctx* ctx, int q, int order, int layout, void* host, u
     if (rc != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaMemcpyAsync(host, ctx->staging, eb * count, cudaMemcpyDeviceToHost, ctx->stream));
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return SPHGPU_OK;
+}
+
+int sphgpu_upload_async(sphgpu_ctx* ctx, int q, int order, int layout, const void* host, uint32_t first, uint32_t count) {
+    int rc = checkRange(ctx, first, count, host);
+    if (rc != SPHGPU_OK) return rc;
+    const size_t eb = elementBytes(q, layout);
+    if (eb == 0) return fail(SPHGPU_E_INVALID, "unknown quantity id");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    // stream order protects the staging buffer: the unpack kernel of the previous call runs before this copy
+    SPH_CUDA_CHECK(cudaMemcpyAsync(ctx->staging, host, eb * count, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launchUnpack(ctx, q, order, layout, ctx->staging, first, count);
+    if (rc != SPHGPU_OK) return rc;
+    ctx->stateUploaded = true;
+    return SPHGPU_OK;
+}
+
+int sphgpu_download_async(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count) {
+    int rc = checkRange(ctx, first, count, host);
+    if (rc != SPHGPU_OK) return rc;
+    const size_t eb = elementBytes(q, layout);
+    if (eb == 0) return fail(SPHGPU_E_INVALID, "unknown quantity id");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!ctx->copyStream) {
+        SPH_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        SPH_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->evPacked, cudaEventDisableTiming));
+        SPH_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->evCopied, cudaEventDisableTiming));
+    }
+    const size_t bytes = (eb * count + 255) & ~(size_t)255;
+    if (ctx->downOffset + bytes > ctx->stagingDownBytes) { // (first use, or a batch larger than any before)
+        SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->copyStream));
+        if (ctx->downOffset > 0) {
+            return fail(SPHGPU_E_STATE, "download batch larger than the staging buffer: call sphgpu_download_batch_end between batches");
+        }
+        cudaFree(ctx->stagingDown);
+        ctx->stagingDown = nullptr;
+        ctx->stagingDownBytes = std::max<size_t>((size_t)ctx->capacity * 256 + 4096, bytes * 4);
+        SPH_CUDA_CHECK(cudaMalloc(&ctx->stagingDown, ctx->stagingDownBytes));
+    }
+    if (ctx->downOffset == 0 && ctx->copiesPending) {
+        // a new batch overwrites the staging area: the copies of the previous batch must have left it
+        SPH_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->evCopied, 0));
+    }
+    void* slot = static_cast<char*>(ctx->stagingDown) + ctx->downOffset;
+    rc = launchPack(ctx, q, order, layout, slot, first, count);
+    if (rc != SPHGPU_OK) return rc;
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->evPacked, ctx->stream));
+    SPH_CUDA_CHECK(cudaStreamWaitEvent(ctx->copyStream, ctx->evPacked, 0));
+    SPH_CUDA_CHECK(cudaMemcpyAsync(host, slot, eb * count, cudaMemcpyDeviceToHost, ctx->copyStream));
+    SPH_CUDA_CHECK(cudaEventRecord(ctx->evCopied, ctx->copyStream));
+    ctx->copiesPending = true;
+    ctx->downOffset += bytes;
+    return SPHGPU_OK;
+}
+
+int sphgpu_download_batch_end(sphgpu_ctx* ctx) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    ctx->downOffset = 0;
+    return SPHGPU_OK;
+}
+
+int sphgpu_transfer_sync(sphgpu_ctx* ctx) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copyStream) {
+        SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->copyStream));
+    }
+    ctx->copiesPending = false;
+    ctx->downOffset = 0;
     return SPHGPU_OK;
 }
 

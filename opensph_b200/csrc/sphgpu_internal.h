@@ -143,6 +143,13 @@ struct sphgpu_ctx {
     bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false;
     sph::DevicePointers d{};
     void* staging = nullptr;   // device staging for AoS <-> SoA repack (capacity * 64 B)
+    // asynchronous downloads (sphgpu_download_async): results are packed into stagingDown on `stream` and leave on
+    // copyStream, so the device -> host DMA of one step overlaps with the host -> device DMA of the next one
+    void* stagingDown = nullptr;
+    size_t stagingDownBytes = 0, downOffset = 0;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evPacked = nullptr, evCopied = nullptr;
+    bool copiesPending = false;
     cudaStream_t stream = nullptr;        // stream all work is queued on (private or caller-provided)
     cudaStream_t privateStream = nullptr;
     double maxChange = 1.e308;            // TIMESTEPPING_MAX_INCREASE

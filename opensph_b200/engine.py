@@ -99,6 +99,27 @@ class Engine:
                                         out.ctypes.data_as(C.c_void_p), C.c_uint32(first), C.c_uint32(count)))
         return out
 
+    def upload_async(self, quantity: str, order: int, array: np.ndarray, first: int = 0) -> None:
+        """Queues the upload; `array` (C-contiguous, ideally pinned) must stay alive until transfer_sync()."""
+        qid, ncomp, dtype = abi.QUANTITIES[quantity]
+        assert array.dtype == dtype and array.flags["C_CONTIGUOUS"]
+        count = array.shape[0]
+        _check(self.lib.sphgpu_upload_async(self._ctx, C.c_int(qid), C.c_int(order), C.c_int(abi.LAYOUT_PACKED),
+                                            array.ctypes.data_as(C.c_void_p), C.c_uint32(first), C.c_uint32(count)))
+
+    def download_async(self, quantity: str, order: int, out: np.ndarray, first: int = 0) -> None:
+        """Queues pack + device -> host copy into `out` (valid after transfer_sync())."""
+        qid, ncomp, dtype = abi.QUANTITIES[quantity]
+        assert out.dtype == dtype and out.flags["C_CONTIGUOUS"]
+        _check(self.lib.sphgpu_download_async(self._ctx, C.c_int(qid), C.c_int(order), C.c_int(abi.LAYOUT_PACKED),
+                                              out.ctypes.data_as(C.c_void_p), C.c_uint32(first), C.c_uint32(out.shape[0])))
+
+    def download_batch_end(self) -> None:
+        _check(self.lib.sphgpu_download_batch_end(self._ctx))
+
+    def transfer_sync(self) -> None:
+        _check(self.lib.sphgpu_transfer_sync(self._ctx))
+
     def upload_device(self, quantity: str, order: int, dev_ptr: int, first: int, count: int) -> None:
         qid, _, _ = abi.QUANTITIES[quantity]
         _check(self.lib.sphgpu_upload_device(self._ctx, C.c_int(qid), C.c_int(order), C.c_void_p(dev_ptr),

@@ -71,6 +71,48 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
         throw InvalidSetup("No solver of smoothing length specified; add either ConstSmootingLength or "
                            "AdaptiveSmootingLength into the list of equations");
     }
+    // settings the device path would silently ignore are rejected instead
+    if (settings.get<Float>(RunSettingsId::TIMESTEPPING_MEAN_POWER) > -1.e3_f) {
+        throw InvalidSetup("GpuSolver: TIMESTEPPING_MEAN_POWER selects a generalised mean of the time steps "
+                           "(TimeStepCriterion.cpp:117-148); the device criteria implement the minimum only");
+    }
+}
+
+GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, AutoPtr<IBoundaryCondition>&& bc,
+    const int device)
+    : GpuSolver(scheduler, settings, eqs, device) {
+    if (bc && !dynamic_cast<NullBoundaryCondition*>(&*bc)) {
+        throw InvalidSetup("GpuSolver: boundary conditions have no device implementation (only NullBoundaryCondition)");
+    }
+}
+
+/// Attached to the Storage (Storage::setUserData): Storage::remove tells us that particle indices changed, so the device
+/// mirror is stale. A device state that is newer than the Storage cannot be reconciled with a host-side removal.
+class GpuSolver::DeviceMirror : public IStorageUserData {
+private:
+    GpuSolver& owner;
+
+public:
+    explicit DeviceMirror(GpuSolver& owner)
+        : owner(owner) {}
+
+    virtual void remove(ArrayView<const Size> idxs) override {
+        if (idxs.empty()) {
+            return;
+        }
+        if (owner.hostStale) {
+            throw Exception("GpuSolver: particles removed from the Storage while the device holds the newer state; call "
+                            "GpuPredictorCorrector::syncToHost() first");
+        }
+        owner.generation++;
+        owner.staticGeneration = Size(-1);
+    }
+};
+
+void GpuSolver::attachMirror(Storage& storage) {
+    if (!storage.getUserData()) { // (a slot used by someone else is left alone; count changes are still detected)
+        storage.setUserData(makeShared<DeviceMirror>(*this));
+    }
 }
 
 GpuSolver::~GpuSolver() {
@@ -89,6 +131,8 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     }
     sphgpu_destroy(ctx);
     ctx = nullptr;
+    generation++;
+    staticGeneration = Size(-1);
 
     sphgpu_config cfg{};
     cfg.abi_version = SPHGPU_ABI_VERSION;
@@ -177,6 +221,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
         m.u_small = mat->minimal(QuantityId::ENERGY);
         m.d_small = mat->minimal(QuantityId::DAMAGE);
         m.s_small = mat->minimal(QuantityId::DEVIATORIC_STRESS);
+        if (storage.has(QuantityId::DEVIATORIC_STRESS) && mat->range(QuantityId::DEVIATORIC_STRESS) != Interval::unbounded()) {
+            throw InvalidSetup("GpuSolver: a bounded range of the deviatoric stress is not implemented on the device");
+        }
     }
     check(sphgpu_create(&cfg, mats.data(), uint32_t(mats.size()), n, n, device, &ctx));
     ctxParticleCnt = n;
@@ -192,8 +239,10 @@ void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives)
     if (derivatives) {
         check(sphgpu_upload(c, SPHGPU_Q_POSITION, 2, L, &storage.getD2t<Vector>(QuantityId::POSITION)[0], 0, n));
     }
+    // per-particle constants (and p, cs, reduce, which the device recomputes or keeps): once per device context
+    const bool statics = staticGeneration != generation;
     for (const QuantityBinding& b : SCALARS_ZERO) {
-        if (storage.has(b.id)) {
+        if (statics && storage.has(b.id)) {
             check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Float>(b.id)[0], 0, n));
         }
     }
@@ -206,7 +255,7 @@ void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives)
         }
     }
     for (const QuantityBinding& b : INDICES) {
-        if (storage.has(b.id)) {
+        if (statics && storage.has(b.id)) {
             check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Size>(b.id)[0], 0, n));
         }
     }
@@ -216,6 +265,7 @@ void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives)
             check(sphgpu_upload(c, SPHGPU_Q_DEVIATORIC_STRESS, 1, L, &storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
         }
     }
+    staticGeneration = generation;
 }
 
 void GpuSolver::downloadQuantities(Storage& storage, const bool stateToo) {
@@ -272,11 +322,14 @@ void GpuSolver::download(Storage& storage) {
 void GpuSolver::integrate(Storage& storage, Statistics& stats) {
     // ISolver contract: highest derivatives are zero on entry (ISolver.h:33-34); the device overwrites them, which is
     // what the reference's accumulate-into-zero amounts to.
+    Timer timer;
+    this->attachMirror(storage);
     this->uploadQuantities(storage, false);
     sphgpu_stats st{};
     const Float t = stats.getOr<Float>(StatisticsId::RUN_TIME, 0._f);
     check(sphgpu_integrate(ctx, t, &st));
     this->downloadQuantities(storage, false);
+    stats.set(StatisticsId::SPH_EVAL_TIME, int(timer.elapsed(TimerUnit::MILLISECOND))); // as AsymmetricSolver.cpp:92
 
     // neighbour statistics as AsymmetricSolver::afterLoop stores them (AsymmetricSolver.cpp:218-225)
     ArrayView<const Size> neighs = storage.getValue<Size>(QuantityId::NEIGHBOR_CNT);
@@ -378,10 +431,10 @@ void GpuPredictorCorrector::stepParticles(IScheduler& UNUSED(scheduler), ISolver
         throw InvalidSetup("GpuPredictorCorrector must be used with the GpuSolver it was constructed with");
     }
     sphgpu_ctx* c = gpu.context(*storage);
-    if (!uploaded) {
+    if (uploadedGeneration != gpu.getGeneration()) { // first step, or the device context / particle set was replaced
         gpu.upload(*storage);
         check(sphgpu_set_last_timestep(c, timeStep));
-        uploaded = true;
+        uploadedGeneration = gpu.getGeneration();
     }
     sphgpu_stats st{};
     sphgpu_timestep ts{};
@@ -391,10 +444,29 @@ void GpuPredictorCorrector::stepParticles(IScheduler& UNUSED(scheduler), ISolver
     lastStep.value = ts.dt;
     lastStep.id = CriterionId(ts.criterion);
 
-    MinMaxMean neighsStats; // min / max / mean only: the per-particle counts stay on the device
-    neighsStats.accumulate(Float(st.neigh_min));
-    neighsStats.accumulate(Float(st.neigh_max));
+    // min / max / mean as AsymmetricSolver::afterLoop reports them (AsymmetricSolver.cpp:218-225); the per-particle counts
+    // stay on the device, so the mean enters as SAMPLES copies of the value that, with min and max, averages to it
+    MinMaxMean neighsStats;
+    const Float lo = Float(st.neigh_min), hi = Float(st.neigh_max);
+    neighsStats.accumulate(lo);
+    neighsStats.accumulate(hi);
+    constexpr int SAMPLES = 1022;
+    const Float rest = clamp((Float(SAMPLES + 2) * Float(st.neigh_mean) - lo - hi) / Float(SAMPLES), lo, hi);
+    for (int k = 0; k < SAMPLES; ++k) {
+        neighsStats.accumulate(rest);
+    }
     stats.set(StatisticsId::NEIGHBOR_COUNT, neighsStats);
+    stats.set(StatisticsId::SPH_EVAL_TIME, int(st.gpu_ms));
+}
+
+GpuSyncOutput::GpuSyncOutput(AutoPtr<IOutput>&& inner, GpuPredictorCorrector& stepping)
+    : IOutput(OutputFile())
+    , inner(std::move(inner))
+    , stepping(stepping) {}
+
+Expected<Path> GpuSyncOutput::dump(const Storage& storage, const Statistics& stats) {
+    stepping.syncToHost(); // the stepping object owns the same Storage (ITimeStepping::storage)
+    return inner->dump(storage, stats);
 }
 
 NAMESPACE_SPH_END

@@ -21,6 +21,8 @@
 ///     timeStepping = makeAuto<GpuPredictorCorrector>(storage, settings, static_cast<GpuSolver&>(*solver));
 
 #include "gravity/IGravity.h"
+#include "io/Output.h"
+#include "sph/boundary/Boundary.h"
 #include "sph/equations/EquationTerm.h"
 #include "system/Settings.h"
 #include "sph/kernel/Kernel.h"
@@ -43,13 +45,28 @@ private:
     Size ctxParticleCnt = 0;
     int device;
 
+    /// Incremented whenever the device context is (re)created or the Storage reports removed particles: everything
+    /// that mirrors device state (GpuPredictorCorrector, the static-quantity cache below) compares against it.
+    Size generation = 0;
+    /// Generation for which the per-particle constants (mass, flaw parameters, flags) are already on the device;
+    /// integrate() then moves only the time-dependent quantities.
+    Size staticGeneration = Size(-1);
+
     /// True while the device holds a newer state than the Storage (after GpuPredictorCorrector steps).
     bool hostStale = false;
+
+    class DeviceMirror; ///< IStorageUserData attached to the Storage: sees Storage::remove (Storage.h:126-133)
+    friend class DeviceMirror;
 
 public:
     /// \throw InvalidSetup if the equation set contains a term without a GPU implementation (there is no CPU
     ///        fallback), mirroring AsymmetricSolver::sanityCheck (AsymmetricSolver.cpp:228-238).
     GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, const int device = 0);
+
+    /// The signature Factory::getSolver uses (AsymmetricSolver.h:126-129). Boundary conditions have no device
+    /// implementation: anything but nullptr / NullBoundaryCondition throws InvalidSetup.
+    GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, AutoPtr<IBoundaryCondition>&& bc,
+        const int device = 0);
 
     ~GpuSolver() override;
 
@@ -73,7 +90,18 @@ public:
         hostStale = stale;
     }
 
+    /// Changes when the device context was re-created or particles were removed from the Storage.
+    Size getGeneration() const {
+        return generation;
+    }
+
+    /// The per-particle constants (mass, flaw parameters, flags) changed on the host: upload them again.
+    void invalidateStatic() {
+        staticGeneration = Size(-1);
+    }
+
 private:
+    void attachMirror(Storage& storage);
     void uploadQuantities(const Storage& storage, const bool derivatives);
     void downloadQuantities(Storage& storage, const bool stateToo);
 };
@@ -118,7 +146,7 @@ public:
 class GpuPredictorCorrector : public ITimeStepping {
 private:
     GpuSolver& gpu;
-    bool uploaded = false;
+    Size uploadedGeneration = Size(-1); ///< GpuSolver::getGeneration() the device state was uploaded for
     Float runTime = 0._f;
 
     class DeviceCriterion;
@@ -132,6 +160,21 @@ public:
 
 protected:
     virtual void stepParticles(IScheduler& scheduler, ISolver& solver, Statistics& stats) override;
+};
+
+/// \brief IOutput decorator for runs stepped by GpuPredictorCorrector: IRun::run calls output->dump(storage, stats) at the
+///        output times (core/run/IRun.cpp:251-257); this brings the host Storage up to date first, then forwards.
+///
+///     output = makeAuto<GpuSyncOutput>(std::move(output), static_cast<GpuPredictorCorrector&>(*timeStepping));
+class GpuSyncOutput : public IOutput {
+private:
+    AutoPtr<IOutput> inner;
+    GpuPredictorCorrector& stepping;
+
+public:
+    GpuSyncOutput(AutoPtr<IOutput>&& inner, GpuPredictorCorrector& stepping);
+
+    virtual Expected<Path> dump(const Storage& storage, const Statistics& stats) override;
 };
 
 NAMESPACE_SPH_END

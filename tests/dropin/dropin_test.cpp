@@ -211,6 +211,21 @@ int main(int argc, char** argv) {
                 double(tb->getTimeStep()), double(tc.getTimeStep()));
         }
         expect(dtOk, "time steps agree to 1e-9");
+        {
+            // the statistics GpuPredictorCorrector reports without moving per-particle data (AsymmetricSolver.cpp:218-225)
+            Statistics statsC;
+            statsC.set(StatisticsId::RUN_TIME, 0._f);
+            tc.step(*scheduler, gpuSolver2, statsC);
+            ta->step(*scheduler, refSolver, statsA);
+            const MinMaxMean ra = statsA.get<MinMaxMean>(StatisticsId::NEIGHBOR_COUNT), rc = statsC.get<MinMaxMean>(StatisticsId::NEIGHBOR_COUNT);
+            printf("  NEIGHBOR_COUNT ref %g/%g/%.6f  device %g/%g/%.6f\n", double(ra.min()), double(ra.max()), double(ra.mean()), double(rc.min()),
+                double(rc.max()), double(rc.mean()));
+            expect(ra.min() == rc.min() && ra.max() == rc.max() && std::abs(ra.mean() - rc.mean()) < 1.e-6 * ra.mean(),
+                "NEIGHBOR_COUNT min / max / mean of GpuPredictorCorrector equal the reference's");
+            expect(statsC.has(StatisticsId::SPH_EVAL_TIME), "SPH_EVAL_TIME is reported");
+            tb->step(*scheduler, gpuSolver, statsB);
+            expect(statsB.has(StatisticsId::SPH_EVAL_TIME), "SPH_EVAL_TIME is reported by GpuSolver::integrate");
+        }
         expect(compareStorages(*sa, *sb, false, "PredictorCorrector + GpuSolver") <= 1.e-9, "state after PC steps (host integrator + GpuSolver) within 1e-9");
         tc.syncToHost();
         expect(compareStorages(*sa, *sc, false, "GpuPredictorCorrector") <= 1.e-9, "state after device-resident PC steps within 1e-9");
@@ -241,7 +256,45 @@ int main(int argc, char** argv) {
             expect(diff > 1.e-6, "gravity contributes to the accelerations");
         }
 
+        // ---- 3b. particle removal: the Storage tells the solver (IStorageUserData), the device mirror is rebuilt ----
+        {
+            Storage c = base->clone(VisitorEnum::ALL_BUFFERS), r = base->clone(VisitorEnum::ALL_BUFFERS);
+            GpuSolver gpu3(*scheduler, settings, eqs);
+            Statistics s3, s4;
+            s3.set(StatisticsId::RUN_TIME, 0._f);
+            s4.set(StatisticsId::RUN_TIME, 0._f);
+            c.zeroHighestDerivatives(*scheduler);
+            r.zeroHighestDerivatives(*scheduler);
+            gpu3.integrate(c, s3);
+            refSolver.integrate(r, s4); // (both storages have been through one evaluation: S is yielded in place)
+            const Size gen = gpu3.getGeneration();
+            Array<Size> toRemove;
+            for (Size i = 0; i < c.getParticleCnt(); i += 7) {
+                toRemove.push(i);
+            }
+            c.remove(toRemove, Storage::IndicesFlag::INDICES_SORTED);
+            r.remove(toRemove, Storage::IndicesFlag::INDICES_SORTED);
+            expect(gpu3.getGeneration() != gen, "Storage::remove is seen by the solver (generation changes)");
+            c.zeroHighestDerivatives(*scheduler);
+            r.zeroHighestDerivatives(*scheduler);
+            gpu3.integrate(c, s3);
+            refSolver.integrate(r, s4);
+            expect(sameNeighbourCounts(r, c), "NEIGHBOR_CNT identical after removing every 7th particle");
+            expect(compareStorages(r, c, true, "integrate() after Storage::remove") <= 1.e-10, "all quantities within 1e-10 after removal");
+        }
+
         // ---- 4. unsupported setups throw InvalidSetup instead of silently running elsewhere ----
+        {
+            // the constructor Factory::getSolver calls (AsymmetricSolver.h:126-129)
+            GpuSolver viaFactorySignature(*scheduler, settings, eqs, makeAuto<NullBoundaryCondition>());
+            bool bcThrown = false;
+            try {
+                GpuSolver withBc(*scheduler, settings, eqs, makeAuto<KillEscapersBoundary>(makeAuto<SphericalDomain>(Vector(0._f), 1._f)));
+            } catch (const InvalidSetup&) {
+                bcThrown = true;
+            }
+            expect(bcThrown, "a real boundary condition is rejected with InvalidSetup");
+        }
         bool thrown = false;
         try {
             RunSettings s2 = settings;

@@ -431,3 +431,34 @@ def test_multi_gpu_parity_script():
                        timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU PARITY OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_async_transfers_equal_synchronous_ones(lut):
+    """sphgpu_upload_async / sphgpu_download_async (queued copies, downloads on a second stream) against the synchronous
+    calls: identical bytes, also when several batches are in flight before one sphgpu_transfer_sync."""
+    i = golden("collision_in.snap")
+    setup = abi.setup_from_snapshot(i, lut)
+    n = len(i["mass"])
+    a, b = Engine(setup, n), Engine(setup, n)
+    a.upload_state(i, STATE_IN)
+    for k in STATE_IN:
+        q, order = abi.SNAPSHOT_FIELDS[k]
+        b.upload_async(q, order, np.ascontiguousarray(i[k], dtype=abi.QUANTITIES[q][2]))
+    sa, sb = a.integrate(), b.integrate()
+    assert sa.pair_count == sb.pair_count
+    names = ["acc", "du", "drho", "dS", "divv", "ncnt", "pos"]
+    ref = a.download_state(names)
+    outs = []
+    for batch in range(3):  # three batches queued back to back
+        out = {k: np.empty_like(ref[k]) for k in names}
+        for k in names:
+            q, order = abi.SNAPSHOT_FIELDS[k]
+            b.download_async(q, order, out[k])
+        b.download_batch_end()
+        outs.append(out)
+    b.transfer_sync()
+    for out in outs:
+        for k in names:
+            assert np.array_equal(out[k], ref[k]), k
+    a.close()
+    b.close()
