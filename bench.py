@@ -410,7 +410,8 @@ def main():
                                   "note": "cell list / work units / candidate lists are rebuilt when the device-side displacement "
                                           "check says so; every step applies the exact neighbour predicate"},
                    "l2": "inputs larger than L2 (state %.1f GB per GPU)" % (n_owned * 480 / 1e9),
-                   "decomposition": "z-slabs of equal particle count + NCCL halo exchange inside the step" if world > 1 else "single domain",
+                   "decomposition": ("z-slabs of equal particle count, halo exchange inside the step: " + getattr(halo, "transport", "nccl point-to-point"))
+                   if world > 1 else "single domain",
                    "stepping": "sphgpu_run_pc: K steps queued back to back, time step fed back on the device, one host sync" if batched
                    else "one call and one host sync per step",
                    "pair_variant": args.variant},

@@ -222,6 +222,15 @@ SPHGPU_API int sphgpu_comm_init(sphgpu_ctx* ctx, const void* id128, int rank, in
 SPHGPU_API int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32_t send_left, uint32_t send_right,
     uint32_t recv_left, uint32_t recv_right);
 SPHGPU_API int sphgpu_halo_exchange(sphgpu_ctx* ctx);
+/* Exchange over peer memory (NVLink) instead of NCCL point-to-point, for ranks on one node (one process per GPU):
+ * sphgpu_peer_export fills SPHGPU_PEER_BLOB_BYTES with the CUDA IPC handles of this rank's halo planes and mailbox; the
+ * caller gathers the blobs of all ranks (rank order) and passes them to sphgpu_peer_connect. From then on
+ * sphgpu_halo_exchange / sphgpu_step_pc_mgpu / sphgpu_run_pc write the send bands straight into the neighbours' ghost
+ * slots with one kernel (no staging, no unpack) and combine the time-step minima through the mailboxes. Call both again
+ * after every sphgpu_halo_configure. Without them the NCCL path is used. */
+#define SPHGPU_PEER_BLOB_BYTES 1280
+SPHGPU_API int sphgpu_peer_export(sphgpu_ctx* ctx, void* blob);
+SPHGPU_API int sphgpu_peer_connect(sphgpu_ctx* ctx, const void* blobs, int world);
 /* Guard of the fixed send bands: the cut planes of this rank's domain perpendicular to `axis` (has_lo / has_hi: there is
  * a neighbour behind that plane). Every exchange then measures the smallest head-room of an interior particle (one that
  * is in neither band) towards a plane, (distance / (R (h_i + h_max) / 2)) - 1. Once it would be negative the next

@@ -555,6 +555,9 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
         std::memcpy(&m, &lc.haloMarginBits, sizeof(m));
         ctx->haloMargin = m;
     }
+    if (lc.peerTimeout != 0u) {
+        return fail(SPHGPU_E_STATE, "a peer rank did not arrive within 20 s (peer-memory halo exchange / all-reduce): the ranks are out of step");
+    }
     if (lc.haloViolation != 0u) {
         return fail(SPHGPU_E_STATE, "halo band outgrown: an interior particle has come within the kernel reach of a cut plane "
                                     "(neighbours on the other rank would be missed); repartition and configure the halo again");

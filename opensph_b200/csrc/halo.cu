@@ -59,7 +59,45 @@ static NcclApi* ncclApi() {
         }                                                                                                             \
     } while (0)
 
+// ---- exchange over peer memory (NVLink) instead of NCCL ---------------------------------------------------------------
+// Every rank exports CUDA IPC handles of the 16 planes a halo record consists of and of a small MAILBOX; after
+// sphgpu_peer_connect a rank holds mapped pointers to the planes of its two slab neighbours and to every rank's mailbox.
+// One kernel then packs the send bands and writes them straight into the neighbours' ghost slots (no staging buffers, no
+// unpack pass, both directions at once), and the four time-step minima are combined by every rank writing its values
+// into every mailbox. Ordering is by sequence numbers with system-scope release / acquire:
+//   ack[side]   -- "I have finished reading the ghosts you sent last time" (written into the neighbour's mailbox before a
+//                  rank pushes; a rank pushes only after both neighbours' acks have arrived)
+//   halo[side]  -- "my push number seq has landed in your ghost slots"
+//   redSeq/redVal[parity][rank] -- contribution of `rank` to all-reduce number seq (double-buffered by parity: a rank can
+//                  be at most one all-reduce ahead of another, because finishing one needs everybody's contribution)
+constexpr int PEER_MAX_WORLD = 64;
+struct PeerMailbox {
+    unsigned long long ack[2];
+    unsigned long long halo[2];
+    unsigned long long redSeq[2][PEER_MAX_WORLD];
+    unsigned long long redVal[2][PEER_MAX_WORLD][4];
+};
+struct PeerBlob { // what sphgpu_peer_export hands to the other ranks
+    cudaIpcMemHandle_t planes[16];
+    cudaIpcMemHandle_t mailbox;
+    uint32_t n, recvLeft, recvRight, rank;
+};
+static_assert(sizeof(PeerBlob) <= SPHGPU_PEER_BLOB_BYTES, "SPHGPU_PEER_BLOB_BYTES too small");
+struct PeerPlanes {
+    double* f[16];
+};
+static const int HALO_PLANES[16] = { F_X, F_Y, F_Z, F_H, F_VX, F_VY, F_VZ, F_VH, F_RHO, F_U, F_S0, F_S1, F_S2, F_S3, F_S4, F_D };
+
 struct HaloState {
+    // peer-memory path (sphgpu_peer_connect); unused (nullptr) on the NCCL path
+    PeerMailbox* mailbox = nullptr;                 // mine (device memory, exported)
+    PeerMailbox* peerMailbox[PEER_MAX_WORLD] = {};  // everybody's, mapped (own entry = mailbox)
+    void* mapped[2][16] = {};                       // planes of the left / right neighbour, mapped
+    PeerPlanes peerPlanes[2] = {};
+    uint32_t peerGhostFirst[2] = { 0, 0 };          // slot in the neighbour's arrays where my band goes
+    bool peerReady = false;
+    unsigned long long haloSeq = 0, redSeqNo = 0;
+    uint32_t* pushCounter = nullptr;                // device: blocks of the push kernel that have finished
     int guardAxis = -1;            // cut planes perpendicular to this axis (sphgpu_halo_set_guard); -1: no guard
     double guardLo = 0., guardHi = 0.;
     bool guardHasLo = false, guardHasHi = false;
@@ -101,6 +139,166 @@ __global__ void __launch_bounds__(256) k_halo_guard(DevicePointers d, uint32_t f
     }
 }
 
+__device__ __forceinline__ void storeRelease(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long loadAcquire(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/// Spins until *p >= seq. A peer that never arrives (it failed, or the ranks' call sequences differ) must not hang the
+/// GPU: after 20 s the wait gives up and raises ListCtlDev::peerTimeout, which fails the next synchronising call.
+__device__ __forceinline__ void waitForSeq(const unsigned long long* p, unsigned long long seq, uint32_t* timeoutFlag) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t spins = 0;
+    while (loadAcquire(p) < seq) {
+        if ((++spins & 0x3ffu) == 0u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 20000000000ull) {
+                *timeoutFlag = 1u;
+                return;
+            }
+        }
+    }
+}
+
+/// One thread: tells both neighbours that their previous push has been consumed, then waits for their acks.
+__global__ void k_peer_ack(PeerMailbox* mine, PeerMailbox* left, PeerMailbox* right, unsigned long long seq, uint32_t* timeoutFlag) {
+    if (threadIdx.x != 0) {
+        return;
+    }
+    // my left neighbour sees me on its right side (index 1) and vice versa
+    if (left) storeRelease(&left->ack[1], seq);
+    if (right) storeRelease(&right->ack[0], seq);
+    if (left) waitForSeq(&mine->ack[0], seq, timeoutFlag);
+    if (right) waitForSeq(&mine->ack[1], seq, timeoutFlag);
+}
+
+/// Packs both send bands and writes them into the neighbours' ghost slots over NVLink; the last block to finish publishes
+/// the sequence number in both neighbours' mailboxes.
+__global__ void __launch_bounds__(256) k_halo_push(DevicePointers d, uint32_t n, uint32_t sendLeft, uint32_t sendRight, PeerPlanes toLeft,
+    PeerPlanes toRight, uint32_t firstLeft, uint32_t firstRight, bool solid, bool damage, PeerMailbox* left, PeerMailbox* right,
+    unsigned long long seq, uint32_t* counter) {
+    const uint32_t total = sendLeft + sendRight;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const bool toL = k < sendLeft;
+        const uint32_t src = toL ? k : n - sendRight + (k - sendLeft);
+        const uint32_t dst = toL ? firstLeft + k : firstRight + (k - sendLeft);
+        const PeerPlanes& out = toL ? toLeft : toRight;
+        const int planes[16] = { F_X, F_Y, F_Z, F_H, F_VX, F_VY, F_VZ, F_VH, F_RHO, F_U, F_S0, F_S1, F_S2, F_S3, F_S4, F_D };
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const bool use = (c < 10) || (c < 15 && solid) || (c == 15 && damage);
+            if (use) {
+                out.f[c][dst] = d.f[planes[c]][src];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter, 1u) == gridDim.x - 1u) {
+            *counter = 0u;
+            __threadfence_system();
+            if (left) storeRelease(&left->halo[1], seq);
+            if (right) storeRelease(&right->halo[0], seq);
+        }
+    }
+}
+
+/// One thread: waits until both neighbours' pushes number seq have landed.
+__global__ void k_halo_arrived(PeerMailbox* mine, bool hasLeft, bool hasRight, unsigned long long seq, uint32_t* timeoutFlag) {
+    if (threadIdx.x != 0) {
+        return;
+    }
+    if (hasLeft) waitForSeq(&mine->halo[0], seq, timeoutFlag);
+    if (hasRight) waitForSeq(&mine->halo[1], seq, timeoutFlag);
+}
+
+struct MailboxList {
+    PeerMailbox* p[PEER_MAX_WORLD];
+};
+
+/// All-reduce (min) of the four time-step minima: lane r writes this rank's values into rank r's mailbox, then waits for
+/// rank r's values in its own; a warp reduction combines them. One warp.
+__global__ void k_peer_allreduce_min(unsigned long long* vals, MailboxList boxes, PeerMailbox* mine, int rank, int world, unsigned long long seq,
+    uint32_t* timeoutFlag) {
+    const int r = threadIdx.x;
+    const int par = (int)(seq & 1ull);
+    unsigned long long v[4] = { ~0ull, ~0ull, ~0ull, ~0ull };
+    if (r < world) {
+        PeerMailbox* box = boxes.p[r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            box->redVal[par][rank][k] = vals[k];
+        }
+        __threadfence_system();
+        storeRelease(&box->redSeq[par][rank], seq);
+        waitForSeq(&mine->redSeq[par][r], seq, timeoutFlag);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = mine->redVal[par][r][k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[k], o);
+            v[k] = other < v[k] ? other : v[k];
+        }
+    }
+    __syncwarp();
+    if (r == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            vals[k] = v[k];
+        }
+    }
+}
+
+static int exchangePeer(sphgpu_ctx* ctx, HaloState* h) {
+    const uint32_t n = ctx->n;
+    const unsigned long long seq = ++h->haloSeq;
+    PeerMailbox* left = h->left >= 0 ? h->peerMailbox[h->left] : nullptr;
+    PeerMailbox* right = h->right >= 0 ? h->peerMailbox[h->right] : nullptr;
+    k_peer_ack<<<1, 32, 0, ctx->stream>>>(h->mailbox, left, right, seq, &ctx->d.listCtl->peerTimeout);
+    if (h->sendLeft + h->sendRight > 0) {
+        const uint32_t blocks = std::min<uint32_t>((h->sendLeft + h->sendRight + 255) / 256, 592u);
+        k_halo_push<<<blocks, 256, 0, ctx->stream>>>(ctx->d, n, h->sendLeft, h->sendRight, h->peerPlanes[0], h->peerPlanes[1],
+            h->peerGhostFirst[0], h->peerGhostFirst[1], ctx->solid, ctx->hasDamage, h->sendLeft ? left : nullptr, h->sendRight ? right : nullptr,
+            seq, h->pushCounter);
+    }
+    k_halo_arrived<<<1, 32, 0, ctx->stream>>>(h->mailbox, h->left >= 0 && h->recvLeft > 0, h->right >= 0 && h->recvRight > 0, seq,
+        &ctx->d.listCtl->peerTimeout);
+    ctx->launches += 3;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+/// Global minimum of the four per-criterion time steps in d.tsd (bit patterns of positive doubles order like the values).
+static int allReduceTimestep(sphgpu_ctx* ctx, HaloState* h, NcclApi* api) {
+    if (h->peerReady) {
+        MailboxList boxes;
+        for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+            boxes.p[r] = r < h->world ? h->peerMailbox[r] : nullptr;
+        }
+        k_peer_allreduce_min<<<1, 32, 0, ctx->stream>>>(ctx->d.tsd->minBits, boxes, h->mailbox, h->rank, h->world, ++h->redSeqNo,
+            &ctx->d.listCtl->peerTimeout);
+        ctx->launches += 1;
+        SPH_CUDA_CHECK(cudaGetLastError());
+        return SPHGPU_OK;
+    }
+    if (api->AllReduce(ctx->d.tsd, ctx->d.tsd, 4, ncclUint64, ncclMin, h->comm, ctx->stream) != ncclSuccess) {
+        setError("ncclAllReduce failed");
+        return SPHGPU_E_CUDA;
+    }
+    return SPHGPU_OK;
+}
+
 static int exchange(sphgpu_ctx* ctx) {
     HaloState* h = static_cast<HaloState*>(ctx->halo);
     NcclApi* api = ncclApi();
@@ -110,14 +308,19 @@ static int exchange(sphgpu_ctx* ctx) {
         return SPHGPU_E_STATE;
     }
     int rc;
-    if ((rc = launchHalo(ctx, true, 0, h->sendLeft, h->bufSendL)) != SPHGPU_OK) return rc;
-    if ((rc = launchHalo(ctx, true, n - h->sendRight, h->sendRight, h->bufSendR)) != SPHGPU_OK) return rc;
+    if (!h->peerReady) {
+        if ((rc = launchHalo(ctx, true, 0, h->sendLeft, h->bufSendL)) != SPHGPU_OK) return rc;
+        if ((rc = launchHalo(ctx, true, n - h->sendRight, h->sendRight, h->bufSendR)) != SPHGPU_OK) return rc;
+    }
     if (h->guardAxis >= 0 && n > h->sendLeft + h->sendRight) {
         const int inf = 0x7f7fffff; // FLT_MAX
         SPH_CUDA_CHECK(cudaMemcpyAsync(&ctx->d.listCtl->haloMarginBits, &inf, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         k_halo_guard<<<296, 256, 0, ctx->stream>>>(ctx->d, h->sendLeft, n - h->sendRight, h->guardAxis, h->guardLo, h->guardHi, h->guardHasLo,
             h->guardHasHi, ctx->prm.kernel_radius, ctx->listSkin > 0. ? ctx->listSkin : 0.);
         ctx->launches += 1;
+    }
+    if (h->peerReady) {
+        return exchangePeer(ctx, h);
     }
     const size_t w = SPHGPU_HALO_DOUBLES;
     // (every operation of the group is attempted and the group is always closed, also after an error)
@@ -148,9 +351,28 @@ static int exchange(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
+static void closePeers(HaloState* h) {
+    for (int side = 0; side < 2; ++side) {
+        for (int c = 0; c < 16; ++c) {
+            if (h->mapped[side][c]) {
+                cudaIpcCloseMemHandle(h->mapped[side][c]);
+                h->mapped[side][c] = nullptr;
+            }
+        }
+    }
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+        if (h->peerMailbox[r] && h->peerMailbox[r] != h->mailbox) {
+            cudaIpcCloseMemHandle(h->peerMailbox[r]);
+        }
+        h->peerMailbox[r] = nullptr;
+    }
+    h->peerReady = false;
+}
+
 void invalidateHalo(sphgpu_ctx* ctx) {
     HaloState* h = static_cast<HaloState*>(ctx->halo);
     if (h) {
+        h->peerReady = false;
         h->sendLeft = h->sendRight = 0xffffffffu; // fails the range check of exchange()
         h->recvLeft = h->recvRight = 0u;
     }
@@ -165,6 +387,9 @@ void destroyHalo(sphgpu_ctx* ctx) {
     cudaFree(h->bufSendR);
     cudaFree(h->bufRecvL);
     cudaFree(h->bufRecvR);
+    closePeers(h);
+    cudaFree(h->mailbox);
+    cudaFree(h->pushCounter);
     NcclApi* api = ncclApi();
     if (api && h->comm && api->CommDestroy) {
         api->CommDestroy(h->comm);
@@ -240,8 +465,90 @@ int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32
     SPH_CUDA_CHECK(cudaMalloc(&h->bufRecvL, std::max<size_t>(w * h->recvLeft, 16)));
     SPH_CUDA_CHECK(cudaMalloc(&h->bufRecvR, std::max<size_t>(w * h->recvRight, 16)));
     ctx->nActive = ctx->n + h->recvLeft + h->recvRight;
+    h->peerReady = false; // the neighbours' ghost offsets are stale: sphgpu_peer_export / sphgpu_peer_connect again
     ctx->listsDirty = true; // another set of ghosts
     SPH_CUDA_CHECK(cudaMemsetAsync(&ctx->d.listCtl->haloViolation, 0, sizeof(uint32_t), ctx->stream));
+    return SPHGPU_OK;
+}
+
+int sphgpu_peer_export(sphgpu_ctx* ctx, void* blob) {
+    if (!ctx || !ctx->halo || !blob) {
+        setError("sphgpu_comm_init / sphgpu_halo_configure must be called first");
+        return SPHGPU_E_STATE;
+    }
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!h->mailbox) {
+        SPH_CUDA_CHECK(cudaMalloc(&h->mailbox, sizeof(PeerMailbox)));
+        SPH_CUDA_CHECK(cudaMemset(h->mailbox, 0, sizeof(PeerMailbox)));
+        SPH_CUDA_CHECK(cudaMalloc(&h->pushCounter, sizeof(uint32_t)));
+        SPH_CUDA_CHECK(cudaMemset(h->pushCounter, 0, sizeof(uint32_t)));
+    }
+    PeerBlob b;
+    std::memset(&b, 0, sizeof(b));
+    for (int c = 0; c < 16; ++c) {
+        SPH_CUDA_CHECK(cudaIpcGetMemHandle(&b.planes[c], ctx->d.f[HALO_PLANES[c]]));
+    }
+    SPH_CUDA_CHECK(cudaIpcGetMemHandle(&b.mailbox, h->mailbox));
+    b.n = ctx->n;
+    b.recvLeft = h->recvLeft;
+    b.recvRight = h->recvRight;
+    b.rank = (uint32_t)h->rank;
+    std::memset(blob, 0, SPHGPU_PEER_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof(b));
+    return SPHGPU_OK;
+}
+
+int sphgpu_peer_connect(sphgpu_ctx* ctx, const void* blobs, int world) {
+    if (!ctx || !ctx->halo || !blobs) {
+        setError("sphgpu_comm_init / sphgpu_halo_configure must be called first");
+        return SPHGPU_E_STATE;
+    }
+    HaloState* h = static_cast<HaloState*>(ctx->halo);
+    if (world != h->world || world > PEER_MAX_WORLD || !h->mailbox) {
+        setError("sphgpu_peer_connect: world size mismatch, too many ranks, or sphgpu_peer_export was not called");
+        return SPHGPU_E_INVALID;
+    }
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    closePeers(h);
+    const char* base = static_cast<const char*>(blobs);
+    auto blobOf = [&](int r) {
+        PeerBlob b;
+        std::memcpy(&b, base + (size_t)r * SPHGPU_PEER_BLOB_BYTES, sizeof(b));
+        return b;
+    };
+    for (int r = 0; r < world; ++r) {
+        if (r == h->rank) {
+            h->peerMailbox[r] = h->mailbox;
+            continue;
+        }
+        const PeerBlob b = blobOf(r);
+        void* p = nullptr;
+        SPH_CUDA_CHECK(cudaIpcOpenMemHandle(&p, b.mailbox, cudaIpcMemLazyEnablePeerAccess));
+        h->peerMailbox[r] = static_cast<PeerMailbox*>(p);
+    }
+    const int nb[2] = { h->left, h->right };
+    for (int side = 0; side < 2; ++side) {
+        if (nb[side] < 0) {
+            continue;
+        }
+        const PeerBlob b = blobOf(nb[side]);
+        for (int c = 0; c < 16; ++c) {
+            SPH_CUDA_CHECK(cudaIpcOpenMemHandle(&h->mapped[side][c], b.planes[c], cudaIpcMemLazyEnablePeerAccess));
+            h->peerPlanes[side].f[c] = static_cast<double*>(h->mapped[side][c]);
+        }
+        // my band arrives behind the neighbour's own particles; the left neighbour files me as ITS right neighbour, i.e.
+        // behind the ghosts it receives from its left
+        h->peerGhostFirst[side] = side == 0 ? b.n + b.recvLeft : b.n;
+        const uint32_t expect = side == 0 ? b.recvRight : b.recvLeft;
+        const uint32_t mine = side == 0 ? h->sendLeft : h->sendRight;
+        if (expect != mine) {
+            setError("sphgpu_peer_connect: the neighbour expects a different number of ghosts than this rank sends");
+            return SPHGPU_E_INVALID;
+        }
+    }
+    h->peerReady = true;
     return SPHGPU_OK;
 }
 
@@ -318,10 +625,7 @@ int sphgpu_run_pc(sphgpu_ctx* ctx, uint32_t steps, double dt, double max_dt, sph
         if (rc == SPHGPU_OK) rc = launchCorrect(ctx, 0.);
         if (rc == SPHGPU_OK) rc = launchCriteria(ctx);
         if (rc == SPHGPU_OK && h) {
-            if (api->AllReduce(ctx->d.tsd, ctx->d.tsd, 4, ncclUint64, ncclMin, h->comm, ctx->stream) != ncclSuccess) {
-                setError("ncclAllReduce failed");
-                rc = SPHGPU_E_CUDA;
-            }
+            rc = allReduceTimestep(ctx, h, api);
         }
         if (rc == SPHGPU_OK) rc = launchFinishTimestep(ctx, max_dt, histDev, s);
     }
@@ -383,7 +687,7 @@ int sphgpu_step_pc_mgpu(sphgpu_ctx* ctx, double t, double dt, double max_dt, sph
     if ((rc = launchCorrect(ctx, dt)) != SPHGPU_OK) return rc;
     if ((rc = launchCriteria(ctx)) != SPHGPU_OK) return rc;
     // global time step: the bit patterns of positive doubles order like the values, so min over ranks is a u64 min
-    SPH_NCCL_CHECK(api->AllReduce(ctx->d.tsd, ctx->d.tsd, 4, ncclUint64, ncclMin, h->comm, ctx->stream));
+    if ((rc = allReduceTimestep(ctx, h, api)) != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[5], ctx->stream));
     if ((rc = collectStats(ctx, stats, ctx->ev[4], ctx->ev[5])) != SPHGPU_OK) return rc;
     float ms = 0.f;

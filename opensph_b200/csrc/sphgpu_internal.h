@@ -77,6 +77,8 @@ struct ListCtlDev {
     // R (h_i + h_max) / 2; negative = an interior particle has come within reach of the other rank: neighbours are missing
     int haloMarginBits;     // bit pattern of a non-negative float (atomicMin), reset to +inf by every exchange
     uint32_t haloViolation; // sticky until the halo is configured again
+    uint32_t peerTimeout;   // a wait on a peer's mailbox gave up (halo.cu: waitForSeq)
+    uint32_t pad;
 };
 
 struct TimestepDev {

@@ -305,6 +305,12 @@ class HaloExchange:
                                dom.n_left, dom.n_right, self.g_left, self.g_right)
             if hasattr(eng, "halo_set_guard"):
                 eng.halo_set_guard(dom.axis, dom.lo_plane, dom.hi_plane)
+            # ranks of one node: band particles go straight into the neighbours' ghost slots over NVLink
+            import os
+            self.transport = "nccl point-to-point"
+            if hasattr(eng, "peer_connect") and os.environ.get("SPHGPU_HALO_TRANSPORT", "peer") == "peer":
+                if eng.peer_connect(dom.rank, dom.world):
+                    self.transport = "peer-memory push kernel (CUDA IPC over NVLink)"
 
     def _exchange_counts(self, n_left: int, n_right: int) -> Tuple[int, int]:
         torch, dist = self.torch, self.dist

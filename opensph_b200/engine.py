@@ -154,6 +154,31 @@ class Engine:
         _check(self.lib.sphgpu_halo_configure(self._ctx, C.c_int(left), C.c_int(right), C.c_uint32(send_left),
                                               C.c_uint32(send_right), C.c_uint32(recv_left), C.c_uint32(recv_right)))
 
+    def peer_connect(self, rank: int, world: int) -> bool:
+        """Switches the halo exchange and the time-step reduction to peer memory (CUDA IPC over NVLink): every rank exports
+        its handles, the blobs are gathered with torch.distributed, every rank maps its neighbours. Returns False (and stays
+        on the NCCL path) if the devices cannot map each other's memory."""
+        import torch
+        import torch.distributed as dist
+        nbytes = 1280  # SPHGPU_PEER_BLOB_BYTES
+        blob = (C.c_ubyte * nbytes)()
+        ok = self.lib.sphgpu_peer_export(self._ctx, blob) == 0
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor(list(bytes(blob)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+        allb = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        allb = [t.cpu().numpy() for t in allb]
+        if not all(int(b[-1]) == 1 for b in allb):
+            return False
+        packed = b"".join(bytes(b[:-1].tobytes()) for b in allb)
+        buf = (C.c_ubyte * len(packed)).from_buffer_copy(packed)
+        ok = self.lib.sphgpu_peer_connect(self._ctx, buf, C.c_int(world)) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            raise SphGpuError(abi.E_STATE, "peer-memory connection failed on some rank: " + self.lib.sphgpu_last_error().decode())
+        return True
+
     def halo_exchange(self) -> None:
         _check(self.lib.sphgpu_halo_exchange(self._ctx))
 
