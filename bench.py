@@ -162,7 +162,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = args.n if args.full_reference else min(args.n, 1_000_000)
+    # the full configuration whenever the whole run fits in about five minutes of host time (measured: 0.82 us per
+    # particle and step on 16 threads), otherwise the largest lattice that does
+    budget_particles = int(300.0 / (0.82e-6 * max(args.steps + max(args.warmup, 1), 1)))
+    n_sample = args.n if (args.full_reference or args.n <= budget_particles) else max(budget_particles, 100_000)
     t0 = time.time()
     r = run_reference(args, n_sample)
     if r is None:

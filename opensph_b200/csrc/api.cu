@@ -223,6 +223,9 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     SPH_TRY(devAlloc(&ctx->d.sCell, cap));
     SPH_TRY(devAlloc(&ctx->d.posF, cap));
     SPH_TRY(devAlloc(&ctx->d.pos0, cap));
+    SPH_TRY(devAlloc(&ctx->d.accLarge, cap));
+    SPH_TRY(devAlloc(&ctx->d.largePartial, (size_t)LARGE_MAX));
+    SPH_TRY(devAlloc(&ctx->d.largeCounter, (size_t)LARGE_MAX));
     SPH_TRY(devAlloc(&ctx->d.listCtl, 1));
     SPH_TRY(devAlloc(&ctx->d.cellHmax, (size_t)ctx->maxCells + 1));
     SPH_TRY(devAlloc(&ctx->d.order, cap));
@@ -285,7 +288,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc); cudaFree(ctx->d.unitAux); cudaFree(ctx->d.unitLane); cudaFree(ctx->d.unitList);
     cudaFree(ctx->d.listPool); cudaFree(ctx->d.listCursor); cudaFree(ctx->d.stepState);
-    cudaFree(ctx->d.posF); cudaFree(ctx->d.pos0); cudaFree(ctx->d.listCtl); cudaFree(ctx->d.cellHmax);
+    cudaFree(ctx->d.posF); cudaFree(ctx->d.pos0); cudaFree(ctx->d.accLarge); cudaFree(ctx->d.largePartial); cudaFree(ctx->d.largeCounter); cudaFree(ctx->d.listCtl); cudaFree(ctx->d.cellHmax);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.statsInit); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree((void*)ctx->d.lut2); cudaFree(ctx->staging);

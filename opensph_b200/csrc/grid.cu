@@ -30,7 +30,7 @@ __device__ __forceinline__ double warpMax(double v) {
 // much its h has grown since the lists were built.
 __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax, double kernelRadius) {
     double lo[3] = { INFTY_REF, INFTY_REF, INFTY_REF }, hi[3] = { -INFTY_REF, -INFTY_REF, -INFTY_REF }, hm = 0.;
-    double ratio2 = 0., grow = 0.;
+    double ratio2 = 0., grow = 0., hsum = 0.;
     const double gx = d.grid->lo[0], gy = d.grid->lo[1], gz = d.grid->lo[2]; // origin of the grid the lists were built on
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nActive; i += gridDim.x * blockDim.x) {
         double h = d.f[F_H][i];
@@ -49,61 +49,109 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
         hi[1] = fmax(hi[1], y);
         hi[2] = fmax(hi[2], z);
         hm = fmax(hm, h);
+        hsum += h;
         const float4 p0 = d.pos0[i];
         const double ex = (x - gx) - (double)p0.x, ey = (y - gy) - (double)p0.y, ez = (z - gz) - (double)p0.z;
         const double rh0 = kernelRadius * (double)p0.w;
         ratio2 = fmax(ratio2, (ex * ex + ey * ey + ez * ez) / (rh0 * rh0));
         grow = fmax(grow, h / (double)p0.w - 1.);
     }
-    __shared__ double sm[8][9];
+    for (int o = 16; o > 0; o >>= 1) {
+        hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+    }
+    __shared__ double sm[8][10];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double v[9] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm),
-        warpMax(ratio2), warpMax(grow) };
+    double v[10] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm),
+        warpMax(ratio2), warpMax(grow), hsum };
     if (lane == 0) {
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < 10; ++k) {
             sm[warp][k] = v[k];
         }
     }
     __syncthreads();
-    if (threadIdx.x < 9) {
+    if (threadIdx.x < 10) {
         const int k = threadIdx.x;
         double r = sm[0][k];
         for (int w = 1; w < 8; ++w) {
-            r = (k < 3) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
+            r = (k < 3) ? fmin(r, sm[w][k]) : (k == 9 ? r + sm[w][k] : fmax(r, sm[w][k]));
         }
         d.boundsPartial[blockIdx.x * BOUNDS_STRIDE + k] = r;
     }
 }
 
-/// Reduces the partial bounds, decides whether this integrate() rebuilds the cell list / units / candidate lists (force,
-/// or the displacement metric has used up the skin; the margin covers the FP32 rounding of pos0) and, if so, sets up the
-/// new grid. Every later build kernel reads ListCtlDev::rebuild and returns at once when it is 0.
-__global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPartials, double kernelRadius, uint32_t maxCells, bool force,
-    double skin) {
-    __shared__ double sm[8][9];
-    double v[9] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0., 0., 0. };
+/// Largest h among the particles with h <= hSplit and the number of particles above it (only when the lists are being
+/// rebuilt and some particle exceeds the split).
+__global__ void __launch_bounds__(256) k_hmax_small(DevicePointers d, uint32_t nActive) {
+    const ListCtlDev ctl = *d.listCtl;
+    if (ctl.rebuild == 0u || !(ctl.hmaxAll > ctl.hSplit)) {
+        return;
+    }
+    double hm = 0., cnt = 0.;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nActive; i += gridDim.x * blockDim.x) {
+        const double h = d.f[F_H][i];
+        if (h > ctl.hSplit) {
+            cnt += 1.;
+        } else {
+            hm = fmax(hm, h);
+        }
+    }
+    hm = warpMax(hm);
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    __shared__ double sm[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sm[warp][0] = hm;
+        sm[warp][1] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            hm = fmax(hm, sm[w][0]);
+            cnt += sm[w][1];
+        }
+        d.boundsPartial[blockIdx.x * BOUNDS_STRIDE + 10] = fmax(sm[0][0], hm);
+        d.boundsPartial[blockIdx.x * BOUNDS_STRIDE + 11] = cnt;
+    }
+}
+
+/// Reduces the partial bounds and decides whether this integrate() rebuilds the cell list / units / candidate lists (force,
+/// or the displacement metric has used up the skin; the margin covers the FP32 rounding of pos0). Every later build
+/// kernel reads ListCtlDev::rebuild and returns at once when it is 0. Also fixes the split of the search radii.
+__global__ void __launch_bounds__(256) k_grid_decide(DevicePointers d, int nPartials, uint32_t nActive, bool force, double skin) {
+    __shared__ double sm[8][10];
+    double v[10] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0., 0., 0., 0. };
     for (int b = threadIdx.x; b < nPartials; b += blockDim.x) {
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < 10; ++k) {
             const double p = d.boundsPartial[b * BOUNDS_STRIDE + k];
-            v[k] = (k < 3) ? fmin(v[k], p) : fmax(v[k], p);
+            v[k] = (k < 3) ? fmin(v[k], p) : (k == 9 ? v[k] + p : fmax(v[k], p));
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = 0; k < 9; ++k) {
-        v[k] = (k < 3) ? warpMin(v[k]) : warpMax(v[k]);
+    for (int k = 0; k < 10; ++k) {
+        if (k == 9) {
+            for (int o = 16; o > 0; o >>= 1) {
+                v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            }
+        } else {
+            v[k] = (k < 3) ? warpMin(v[k]) : warpMax(v[k]);
+        }
     }
     if (lane == 0) {
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < 10; ++k) {
             sm[warp][k] = v[k];
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 9; ++k) {
+        for (int k = 0; k < 10; ++k) {
             double r = sm[0][k];
             for (int w = 1; w < 8; ++w) {
-                r = (k < 3) ? fmin(r, sm[w][k]) : fmax(r, sm[w][k]);
+                r = (k < 3) ? fmin(r, sm[w][k]) : (k == 9 ? r + sm[w][k] : fmax(r, sm[w][k]));
             }
+            // the first slots of the partial array carry the totals to k_grid_params
+            d.boundsPartial[k] = r;
             v[k] = r;
         }
         ListCtlDev ctl = *d.listCtl;
@@ -111,18 +159,49 @@ __global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPart
         ctl.lastMetric = metric;
         const bool rebuild = force || !(metric < 0.9 * skin);
         ctl.rebuild = rebuild ? 1u : 0u;
-        if (!rebuild) {
+        if (rebuild) {
+            ctl.age = 0u;
+            ctl.rebuilds++;
+            ctl.fallbackUnits = 0u;
+            ctl.hmaxAll = v[6];
+            ctl.hSplit = LARGE_FACTOR * v[9] / fmax((double)nActive, 1.);
+        } else {
             ctl.age++;
-            *d.listCtl = ctl;
-            return;
         }
-        ctl.age = 0u;
-        ctl.rebuilds++;
-        ctl.fallbackUnits = 0u;
         *d.listCtl = ctl;
-        GridDev g;
-        g.hmax = v[6];
-        double cell = kernelRadius * v[6] * (1. + 1.e-6) * (1. + skin);
+    }
+}
+
+/// Sets up the grid of a rebuild: cell edge R h_max (1 + skin) with h_max the largest SMALL h (GridDev::hSplit).
+__global__ void k_grid_params(DevicePointers d, int nPartials, double kernelRadius, uint32_t maxCells, double skin) {
+    if (threadIdx.x != 0 || d.listCtl->rebuild == 0u) {
+        return;
+    }
+    const ListCtlDev ctl = *d.listCtl;
+    double v[7];
+    for (int k = 0; k < 7; ++k) {
+        v[k] = d.boundsPartial[k];
+    }
+    GridDev g;
+    g.hmaxAll = ctl.hmaxAll;
+    g.hmax = ctl.hmaxAll;
+    g.hSplit = INFTY_REF;
+    g.nLarge = 0u;
+    g.largeBegin = 0u;
+    if (ctl.hmaxAll > ctl.hSplit) { // some particles are much larger than the mean: keep them out of the cell list
+        double hSmall = 0., nLarge = 0.;
+        for (int b = 0; b < nPartials; ++b) {
+            hSmall = fmax(hSmall, d.boundsPartial[b * BOUNDS_STRIDE + 10]);
+            nLarge += d.boundsPartial[b * BOUNDS_STRIDE + 11];
+        }
+        if (nLarge <= (double)LARGE_MAX && hSmall > 0.) {
+            g.hmax = hSmall;
+            g.hSplit = ctl.hSplit;
+            g.nLarge = (uint32_t)nLarge;
+        }
+    }
+    {
+        double cell = kernelRadius * g.hmax * (1. + 1.e-6) * (1. + skin);
         if (!(cell > 0.)) {
             cell = 1.;
         }
@@ -136,10 +215,10 @@ __global__ void __launch_bounds__(256) k_grid_params(DevicePointers d, int nPart
             for (int k = 0; k < 3; ++k) {
                 total *= floor(ext[k] / (k == 2 ? 0.5 * cell : cell)) + 1.;
             }
-            if (total <= (double)maxCells) {
+            if (total <= (double)(maxCells - 1u)) { // (one more cell, the overflow cell of the large particles, must fit)
                 break;
             }
-            cell *= fmax(cbrt(total / (double)maxCells), 1.0) * 1.02;
+            cell *= fmax(cbrt(total / (double)(maxCells - 1u)), 1.0) * 1.02;
         }
         g.cell = cell;
         g.cellInv = 1. / cell;
@@ -173,7 +252,9 @@ __global__ void __launch_bounds__(256) k_cell_count(DevicePointers d, uint32_t n
         return;
     }
     const GridDev g = *d.grid;
-    const uint32_t c = cellIndex(g, d.f[F_X][i], d.f[F_Y][i], d.f[F_Z][i]);
+    // large particles (two-level radii) sit in the overflow cell behind the last real one: never targets or candidates of
+    // the tiled kernels
+    const uint32_t c = d.f[F_H][i] > g.hSplit ? g.ncells : cellIndex(g, d.f[F_X][i], d.f[F_Y][i], d.f[F_Z][i]);
     d.cellOf[i] = c;
     d.rank[i] = atomicAdd(&d.cellCount[c], 1u);
 }
@@ -316,6 +397,9 @@ __global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t m
     }
     if (c >= d.grid->ncells) {
         d.cellHmax[c] = 0u;
+        if (c == d.grid->ncells) {
+            d.grid->largeBegin = d.cellStart[c]; // first sorted index of the large particles
+        }
         return;
     }
     const uint32_t s = d.cellStart[c], e = d.cellStart[c + 1];
@@ -375,7 +459,9 @@ int launchGridBuild(sphgpu_ctx* ctx) {
     const bool clampH = (ctx->prm.flags & SPHGPU_FLAG_ADAPTIVE_H) != 0;
     k_bounds<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n, clampH, ctx->prm.h_min, ctx->prm.h_max, ctx->prm.kernel_radius);
     const bool force = ctx->listsDirty || !(ctx->listSkin > 0.);
-    k_grid_params<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, ctx->prm.kernel_radius, ctx->maxCells, force, ctx->listSkin);
+    k_grid_decide<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, n, force, ctx->listSkin);
+    k_hmax_small<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n);
+    k_grid_params<<<1, 32, 0, st>>>(ctx->d, BOUNDS_BLOCKS, ctx->prm.kernel_radius, ctx->maxCells, ctx->listSkin > 0. ? ctx->listSkin : 0.);
     ctx->listsDirty = false;
     SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.cellCount, 0, sizeof(uint32_t) * (ctx->maxCells + 1), st));
     const uint32_t blocks = (n + 255) / 256;
@@ -390,7 +476,7 @@ int launchGridBuild(sphgpu_ctx* ctx) {
         k_scatter<<<blocks, 256, 0, st>>>(ctx->d, n);
     }
     k_sort_cells<<<(ctx->maxCells + 127) / 128, 128, 0, st>>>(ctx->d, ctx->maxCells);
-    ctx->launches += 8;
+    ctx->launches += 10;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }

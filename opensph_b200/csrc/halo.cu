@@ -115,7 +115,7 @@ struct HaloState {
 // h_max bound: the grid's h_max at the last list build times (1 + skin) -- the list reuse rebuilds before h grows more.
 __global__ void __launch_bounds__(256) k_halo_guard(DevicePointers d, uint32_t first, uint32_t last, int axis, double lo, double hi, bool hasLo,
     bool hasHi, double kernelRadius, double skin) {
-    const double hmax = d.grid->hmax * (1. + skin);
+    const double hmax = d.grid->hmaxAll * (1. + skin);
     float margin = 3.0e38f;
     for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < last; i += gridDim.x * blockDim.x) {
         const double x = d.f[F_X + axis][i];

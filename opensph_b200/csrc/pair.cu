@@ -225,8 +225,12 @@ __device__ __forceinline__ void neighbourStats(const DevicePointers& d, uint32_t
 template <bool SOLID, bool CORRECTED, bool FILTER>
 __device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t, uint32_t i) {
     Accum acc;
-    accumZero(acc);
     const GridDev g = *d.grid;
+    if (g.nLarge > 0u) {
+        acc = d.accLarge[t]; // sums over the large neighbours (two-level radii), k_large_neighbours
+    } else {
+        accumZero(acc);
+    }
     Particle pi;
     loadSorted<SOLID>(d, t, pi);
     const uint32_t c = d.sCell[t];
@@ -279,9 +283,174 @@ __global__ void __launch_bounds__(128) k_pair_direct(DevicePointers d, uint32_t 
         return;
     }
     const uint32_t i = d.order[t];
-    if (i < nOwned) { // ghosts are neighbours only
+    if (i < nOwned && !(d.grid->nLarge > 0u && t >= d.grid->largeBegin)) { // ghosts are neighbours only; large targets: k_large_targets
         directTarget<SOLID, CORRECTED, FILTER>(d, t, i);
     }
+}
+
+// ---- two-level search radii: every pair that involves a LARGE particle (GridDev::hSplit) ---------------------------------
+// k_large_neighbours: one thread per small target, loops over the (few) large particles and leaves the partial sums in
+// accLarge, from which the tiled / direct kernels start instead of from zero. k_large_targets: one CTA per large target,
+// the threads share ALL other particles, a fixed-order reduction combines the partial sums. Both apply the exact
+// predicate of AsymmetricSolver.cpp:186-191; the pair arithmetic is pairAccumulate (as in the direct variant).
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__global__ void __launch_bounds__(128) k_large_neighbours(DevicePointers d, uint32_t nActive) {
+    const GridDev g = *d.grid;
+    if (g.nLarge == 0u) {
+        return;
+    }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.largeBegin) {
+        return;
+    }
+    Accum acc;
+    accumZero(acc);
+    Particle pi;
+    loadSorted<SOLID>(d, t, pi);
+    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
+    for (uint32_t k = g.largeBegin; k < nActive; ++k) {
+        double2 pxy, pzh;
+        loadSortedPosition(d.rec, k, RD, pxy, pzh);
+        const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
+        double d2, hbar;
+        if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
+            continue;
+        }
+        Particle pj;
+        loadSorted<SOLID>(d, k, pj);
+        pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+    }
+    d.accLarge[t] = acc;
+}
+
+template <bool SOLID, bool CORRECTED, bool FILTER>
+__global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_t nActive, uint32_t nOwned) {
+    const GridDev g = *d.grid;
+    if (g.nLarge == 0u) {
+        return;
+    }
+    // The grid's CTAs are dealt to the large targets: target L gets S = gridDim / nLarge CTAs, each summing one slice of
+    // the particles; the CTA that finishes last adds the slices' partial sums in slice order (the result does not depend
+    // on which one that is) and runs the finalizers.
+    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
+    constexpr int NV = 23; // doubles of Accum in front of the counter
+    __shared__ double red[8][NV];
+    __shared__ uint32_t redCnt[8];
+    __shared__ bool isLast;
+    const uint32_t nL = g.nLarge;
+    const uint32_t S = max(gridDim.x / nL, 1u);
+    const uint32_t per = (nActive + S - 1u) / S;
+    for (uint32_t w = blockIdx.x; w < nL * S; w += gridDim.x) {
+        const uint32_t L = w % nL, slice = w / nL;
+        const uint32_t t = g.largeBegin + L;
+        const uint32_t i = d.order[t];
+        if (i >= nOwned) {
+            continue; // ghosts are neighbours only (uniform for the CTA)
+        }
+        Particle pi;
+        loadSorted<SOLID>(d, t, pi);
+        Accum acc;
+        accumZero(acc);
+        const uint32_t kEnd = min((slice + 1u) * per, nActive);
+        for (uint32_t k = slice * per + threadIdx.x; k < kEnd; k += blockDim.x) {
+            if (k == t) {
+                continue;
+            }
+            double2 pxy, pzh;
+            loadSortedPosition(d.rec, k, RD, pxy, pzh);
+            const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
+            double d2, hbar;
+            if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
+                continue;
+            }
+            Particle pj;
+            loadSorted<SOLID>(d, k, pj);
+            pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+        }
+        // fixed-order reduction inside the CTA: lanes by shuffle, warps through shared memory
+        double* a = reinterpret_cast<double*>(&acc);
+        uint32_t cnt = acc.cnt;
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                a[q] += __shfl_down_sync(0xffffffffu, a[q], o);
+            }
+            cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __syncthreads(); // (the previous reduction has been read)
+        if (lane == 0) {
+            for (int q = 0; q < NV; ++q) {
+                red[warp][q] = a[q];
+            }
+            redCnt[warp] = cnt;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int wp = 1; wp < 8; ++wp) {
+                for (int q = 0; q < NV; ++q) {
+                    a[q] += red[wp][q];
+                }
+                cnt += redCnt[wp];
+            }
+            acc.cnt = cnt;
+            d.largePartial[slice * nL + L] = acc;
+            __threadfence();
+            isLast = atomicAdd(&d.largeCounter[L], 1u) == S - 1u;
+            if (isLast) {
+                d.largeCounter[L] = 0u;
+                __threadfence();
+                Accum sum;
+                accumZero(sum);
+                double* b = reinterpret_cast<double*>(&sum);
+                for (uint32_t sl = 0; sl < S; ++sl) {
+                    const Accum part = d.largePartial[sl * nL + L];
+                    const double* p = reinterpret_cast<const double*>(&part);
+                    for (int q = 0; q < NV; ++q) {
+                        b[q] += p[q];
+                    }
+                    sum.cnt += part.cnt;
+                }
+                const MaterialDev& mat = c_mats[d.u[U_MATID][i]];
+                double Sv[5] = { 0., 0., 0., 0., 0. };
+                if (SOLID) {
+                    for (int q = 0; q < 5; ++q) {
+                        Sv[q] = d.f[F_S0 + q][i];
+                    }
+                }
+                Derivs out;
+                finalizeParticle<SOLID, CORRECTED>(c_prm, mat, sum, pi.h, pi.rho, d.f[F_P][i], d.f[F_CS][i], SOLID ? d.f[F_REDUCE][i] : 1., Sv, out);
+                storeDerivs<SOLID, CORRECTED>(d, i, out);
+                atomicMin(&d.stats->neighMin, sum.cnt);
+                atomicMax(&d.stats->neighMax, sum.cnt);
+                atomicAdd(&d.stats->pairCount, (unsigned long long)sum.cnt);
+            }
+        }
+    }
+}
+
+template <bool SOLID, bool CORRECTED, bool FILTER>
+static int launchLargeVariant(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->nActive;
+    k_large_neighbours<SOLID, CORRECTED, FILTER><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n);
+    k_large_targets<SOLID, CORRECTED, FILTER><<<(unsigned)LARGE_MAX, 256, 0, ctx->stream>>>(ctx->d, n, ctx->n);
+    ctx->launches += 2;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+/// Pairs with large particles (returns at once on the device when there are none).
+int launchLargePairs(sphgpu_ctx* ctx) {
+    if (ctx->nActive == 0) {
+        return SPHGPU_OK;
+    }
+    if (!ctx->solid) {
+        return launchLargeVariant<false, false, false>(ctx);
+    }
+    if (ctx->corrected) {
+        return ctx->filter ? launchLargeVariant<true, true, true>(ctx) : launchLargeVariant<true, true, false>(ctx);
+    }
+    return ctx->filter ? launchLargeVariant<true, false, true>(ctx) : launchLargeVariant<true, false, false>(ctx);
 }
 
 // ---- neighbour lists for the tests ---------------------------------------------------------------------------
@@ -300,31 +469,46 @@ __global__ void __launch_bounds__(128) k_neighbour_lists(DevicePointers d, uint3
     double2 ixy, izh;
     loadSortedPosition(d.rec, t, recDoubles, ixy, izh);
     const double xi = ixy.x, yi = ixy.y, zi = izh.x, hi = izh.y;
-    const uint32_t c = d.sCell[t];
-    const int cx = (int)(c % (uint32_t)g.dim[0]);
-    const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
-    const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
     uint32_t cnt = 0;
     const unsigned long long base = FILL ? offsets[i] : 0ull;
-    for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
-        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-            const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
-            const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
-            for (uint32_t k = s; k < e; ++k) {
-                if (k == t) {
-                    continue;
+    auto test = [&](uint32_t k) {
+        double2 pxy, pzh;
+        loadSortedPosition(d.rec, k, recDoubles, pxy, pzh);
+        double d2, hbar;
+        if (isNeighbour(xi - pxy.x, yi - pxy.y, zi - pzh.x, hi, pzh.y, c_prm.kernel_radius, d2, hbar)) {
+            if (FILL) {
+                idx[base + cnt] = d.order[k];
+            }
+            cnt++;
+        }
+    };
+    const bool large = g.nLarge > 0u && t >= g.largeBegin;
+    if (large) { // a large particle (two-level radii): everything can be its neighbour
+        for (uint32_t k = 0; k < nActive; ++k) {
+            if (k != t) {
+                test(k);
+            }
+        }
+    } else {
+        const uint32_t c = d.sCell[t];
+        const int cx = (int)(c % (uint32_t)g.dim[0]);
+        const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
+        const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+        for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+                const uint32_t s = d.cellStart[row + x0], e = d.cellStart[row + x1 + 1];
+                for (uint32_t k = s; k < e; ++k) {
+                    if (k != t) {
+                        test(k);
+                    }
                 }
-                double2 pxy, pzh;
-                loadSortedPosition(d.rec, k, recDoubles, pxy, pzh);
-                double d2, hbar;
-                if (!isNeighbour(xi - pxy.x, yi - pxy.y, zi - pzh.x, hi, pzh.y, c_prm.kernel_radius, d2, hbar)) {
-                    continue;
-                }
-                if (FILL) {
-                    idx[base + cnt] = d.order[k];
-                }
-                cnt++;
+            }
+        }
+        if (g.nLarge > 0u) {
+            for (uint32_t k = g.largeBegin; k < nActive; ++k) {
+                test(k);
             }
         }
     }
@@ -367,6 +551,12 @@ int launchPair(sphgpu_ctx* ctx) {
         return SPHGPU_OK;
     }
     ctx->pairTimed = false;
+    {
+        const int rcLarge = launchLargePairs(ctx);
+        if (rcLarge != SPHGPU_OK) {
+            return rcLarge;
+        }
+    }
     if (ctx->variant != 1) {
         return launchPairTiled(ctx);
     }

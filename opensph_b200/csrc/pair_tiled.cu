@@ -976,7 +976,11 @@ __global__ void __launch_bounds__(TILE_T, 3) k_pair_sum(DevicePointers d, uint32
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
         }
-        accumZero(acc);
+        if (g.nLarge > 0u && u.target) {
+            acc = d.accLarge[u.t]; // sums over the large neighbours (two-level radii, pair.cu: k_large_neighbours)
+        } else {
+            accumZero(acc);
+        }
     };
 
     if (tid == 0) {

@@ -51,7 +51,14 @@ struct GridDev {
     double cellZ, cellZInv; // cells are HALF as high in z (cell / 2): neighbours span +-1 cell in x,y and +-2 in z
     int dim[3];
     uint32_t ncells;
-    double hmax;
+    double hmax;       // largest h of the particles in the cell list (the "small" ones when the radii are split, see hSplit)
+    double hmaxAll;    // largest h of all particles
+    // Two-level search radii (the reference's answer to a few huge particles is RadiiHashMap, AsymmetricSolver.cpp:14-56):
+    // particles with h > hSplit ("large": at most LARGE_MAX of them, else +inf and everything is small) are kept out of
+    // the cell list -- they sit in one overflow cell behind the last real cell -- so the cell edge follows the largest
+    // SMALL h; every pair with a large particle is evaluated by k_large_targets / k_large_neighbours (pair.cu).
+    double hSplit;
+    uint32_t nLarge, largeBegin; // number of large particles and their first sorted index
     double extent;     // largest edge of the grid box: scale of the FP32 rounding of the grid-relative coordinates
     uint32_t unsorted; // set by k_sort_cells when a cell was too large to be ordered by x (windows then span whole rows)
 };
@@ -73,6 +80,7 @@ struct ListCtlDev {
     uint32_t rebuilds;      // builds so far
     uint32_t fallbackUnits; // units whose candidate lists did not fit the list pool at the last build
     double lastMetric;      // 2 max ratio + max growth seen by the last call
+    double hSplit, hmaxAll; // k_grid_decide -> k_hmax_small -> k_grid_params (split of the search radii, GridDev)
     // halo guard (halo.cu): smallest head-room of an interior particle towards a cut plane, in units of its reach
     // R (h_i + h_max) / 2; negative = an interior particle has come within reach of the other rank: neighbours are missing
     int haloMarginBits;     // bit pattern of a non-negative float (atomicMin), reset to +inf by every exchange
@@ -103,6 +111,9 @@ struct DevicePointers {
     uint32_t* sCell;    // sorted: linear cell index
     float4* posF;       // sorted: FP32 {x, y, z} relative to the grid origin and h (conservative pre-filter of the pair kernel)
     float4* pos0;       // by slot: the same at the time the lists were built (displacement check of the list reuse)
+    Accum* accLarge;    // sorted: partial sums of the small targets over their LARGE neighbours (two-level radii)
+    Accum* largePartial;    // [LARGE_MAX] per-slice partial sums of the large targets (k_large_targets)
+    uint32_t* largeCounter; // [LARGE_MAX] slices of a large target that have finished
     ListCtlDev* listCtl;
     uint32_t* cellHmax; // [maxCells] bit pattern of the largest (float) h inside each cell
     uint32_t* order;    // sorted position -> slot
@@ -130,7 +141,10 @@ struct DevicePointers {
 };
 
 constexpr int BOUNDS_BLOCKS = 592;   // 148 SMs x 4
-constexpr int BOUNDS_STRIDE = 16;    // doubles per block in boundsPartial: lo[3], hi[3], hmax, max ratio, max growth
+constexpr int BOUNDS_STRIDE = 16;    // doubles per block in boundsPartial: lo[3], hi[3], hmax, max ratio, max growth, sum h,
+                                     // [10] largest small h, [11] number of large particles (k_hmax_small)
+constexpr double LARGE_FACTOR = 2.;  // particles with h > LARGE_FACTOR * mean h are "large" ...
+constexpr uint32_t LARGE_MAX = 1024; // ... if there are at most this many of them
 constexpr int SCAN_ITEMS = 4096;     // items per scan block
 
 } // namespace sph

@@ -246,10 +246,14 @@ def test_line_of_particles_with_increasing_h(lut):
 
 
 @pytest.mark.parametrize("variant", [0, 2, 3])
-def test_one_giant_smoothing_length(variant, lut):
-    """One particle whose h covers the whole cloud: the grid degenerates to a few cells with thousands of particles each
-    (cell rows are then no longer ordered by x and are scanned whole, chunks are split into pieces), and that particle
-    has every other one as a neighbour (its candidate list overflows many times: several list blocks per chunk)."""
+@pytest.mark.parametrize("giants", [1, 1500])
+def test_one_giant_smoothing_length(variant, giants, lut):
+    """Particles whose h covers the whole cloud; each has every other particle as a neighbour.
+    giants = 1: the two-level search radii (the device's answer to AsymmetricSolver's RadiiHashMap,
+    AsymmetricSolver.cpp:14-56) keep it out of the cell list, the cell edge follows the ordinary particles.
+    giants = 1500 (> LARGE_MAX): no split; the grid degenerates to a few cells with thousands of particles each (cell rows
+    are then no longer ordered by x and are scanned whole, chunks are split into pieces, candidate lists overflow many
+    times: several list blocks per chunk)."""
     i = golden("fluid_in.snap")
     n0, reps = len(i["mass"]), 12
     n = n0 * reps
@@ -261,7 +265,7 @@ def test_one_giant_smoothing_length(variant, lut):
     shift = rng.uniform(0, 2.0 * ext, (reps, 3))
     snap["pos"] = snap["pos"].copy()
     snap["pos"][:, :3] += np.repeat(shift, n0, axis=0) + rng.normal(0, 0.05, (n, 3)) * snap["pos"][:, 3:4]
-    snap["pos"][n // 2, 3] = 4.0 * ext
+    snap["pos"][rng.choice(n, giants, replace=False), 3] = 4.0 * ext
     snap["vel"] = snap["vel"].copy()
     snap["vel"][:, :3] = np.sin(snap["pos"][:, :3] / ext * 3.0) * 5.0
     orc = OraclePort(snap, setup)
@@ -269,10 +273,44 @@ def test_one_giant_smoothing_length(variant, lut):
     assert orc.a["ncnt"].max() == n - 1
     eng, stats = gpu_integrate(snap, setup, variant)
     got = eng.download_state(["acc", "du", "drho", "divv", "ncnt"])
+    off, idx = eng.neighbours()
+    ooff, oidx = orc.neighbours()
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
     eng.close()
     assert np.array_equal(got["ncnt"], orc.a["ncnt"])
     for k in ("acc", "du", "drho", "divv"):
         assert_close(k, got[k], orc.a[k], TOL, FLOOR)
+
+
+def test_giant_smoothing_length_costs_little_at_bench_scale():
+    """one huge particle in the 1 M-particle lattice must not set the cell edge for everybody. The step time
+    with the giant stays within 2x of the uniform-h time (it was ~100x with a single-level grid), the neighbour count of
+    every ordinary particle rises by exactly one and the giant sees all others."""
+    from opensph_b200 import workloads
+    state = workloads.basalt_sphere_state(1_000_000)
+    n = len(state["mass"])
+    setup = workloads.make_setup(n)
+    names = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "damage", "ddamage", "reduce",
+             "eps_min", "m_zero", "growth", "n_flaws", "flag")
+    times, ncnt = {}, {}
+    for giant in (False, True):
+        st = {k: v.copy() for k, v in state.items()}
+        if giant:
+            st["pos"][n // 2, 3] = 4.0 * 5.0e4
+        eng = Engine(setup, n)
+        eng.upload_state(st, names)
+        eng.integrate()
+        best = min(eng.integrate().gpu_ms for _ in range(3))
+        times[giant] = best
+        ncnt[giant] = eng.download_state(["ncnt"])["ncnt"]
+        eng.close()
+    assert ncnt[True][n // 2] == n - 1
+    # every other particle gains the giant as a neighbour -- except those that had particle n/2 as a neighbour already
+    gain = ncnt[True].astype(np.int64) - ncnt[False].astype(np.int64)
+    gain[n // 2] = 1
+    assert set(np.unique(gain)) <= {0, 1}
+    assert int((gain == 0).sum()) == int(ncnt[False][n // 2])
+    assert times[True] <= 2.0 * times[False], times
 
 
 def test_batched_steps_equal_single_steps(lut):
