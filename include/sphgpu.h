@@ -200,6 +200,9 @@ SPHGPU_API int sphgpu_upload_async(sphgpu_ctx* ctx, int q, int order, int layout
 SPHGPU_API int sphgpu_download_async(sphgpu_ctx* ctx, int q, int order, int layout, void* host, uint32_t first, uint32_t count);
 SPHGPU_API int sphgpu_download_batch_end(sphgpu_ctx* ctx);
 SPHGPU_API int sphgpu_transfer_sync(sphgpu_ctx* ctx);
+/* Page-locked host memory for the asynchronous transfers (so that host code needs no CUDA headers). */
+SPHGPU_API int sphgpu_host_alloc(void** out, size_t bytes);
+SPHGPU_API int sphgpu_host_free(void* ptr);
 SPHGPU_API int sphgpu_upload_device(sphgpu_ctx* ctx, int q, int order, const void* dev, uint32_t first, uint32_t count);
 SPHGPU_API int sphgpu_download_device(sphgpu_ctx* ctx, int q, int order, void* dev, uint32_t first, uint32_t count);
 /* Halo exchange helpers (multi-GPU): pack / unpack the dynamic neighbour inputs {r,h | v,dh/dt | rho | u | S[5] | D}

@@ -406,6 +406,21 @@ int sphgpu_download_batch_end(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
+int sphgpu_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(SPHGPU_E_INVALID, "null argument");
+    *out = nullptr;
+    SPH_CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return SPHGPU_OK;
+}
+
+int sphgpu_host_free(void* ptr) {
+    if (ptr) {
+        cudaFreeHost(ptr);
+        cudaGetLastError();
+    }
+    return SPHGPU_OK;
+}
+
 int sphgpu_transfer_sync(sphgpu_ctx* ctx) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
     SPH_CUDA_CHECK(cudaSetDevice(ctx->device));

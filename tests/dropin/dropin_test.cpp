@@ -6,9 +6,13 @@
 // Built by opensph_b200/host/Makefile against /root/reference (headers + oracle/_ref/libopensph_core_strict.a) and
 // libsphgpu.so; the binary goes to oracle/_ref/dropin_test because it embeds reference code.
 #include "../../opensph_b200/host/GpuSolver.h"
+#include "../../opensph_b200/host/GpuOutput.h"
 #include "Sph.h"
 #include "sph/solvers/GravitySolver.h"
 #include <cstdio>
+#include <fstream>
+#include <iterator>
+#include <vector>
 #include <random>
 
 using namespace Sph;
@@ -227,7 +231,46 @@ int main(int argc, char** argv) {
             expect(statsB.has(StatisticsId::SPH_EVAL_TIME), "SPH_EVAL_TIME is reported by GpuSolver::integrate");
         }
         expect(compareStorages(*sa, *sb, false, "PredictorCorrector + GpuSolver") <= 1.e-9, "state after PC steps (host integrator + GpuSolver) within 1e-9");
-        tc.syncToHost();
+        {
+            // ---- 2b. snapshot straight from the device planes (the host Storage is stale here) against the reference's
+            // BinaryOutput of the synchronised Storage: identical files, loadable by the reference's BinaryInput ----
+            Statistics dumpStats;
+            dumpStats.set(StatisticsId::RUN_TIME, 1.5_f);
+            dumpStats.set(StatisticsId::TIMESTEP_VALUE, tc.getTimeStep());
+            const Path pathGpu("dropin_gpu_dump.ssf"), pathRef("dropin_ref_dump.ssf");
+            GpuBinaryOutput gpuOut(OutputFile(pathGpu), gpuSolver2);
+            expect(gpuSolver2.isHostStale(), "the host Storage is stale when the device snapshot is written");
+            Expected<Path> wa = gpuOut.dump(*sc, dumpStats);
+            expect(bool(wa), "GpuBinaryOutput::dump succeeds");
+            expect(gpuSolver2.isHostStale(), "GpuBinaryOutput does not synchronise the host Storage");
+            tc.syncToHost();
+            BinaryOutput refOut{ OutputFile(pathRef) };
+            Expected<Path> wb = refOut.dump(*sc, dumpStats);
+            expect(bool(wb), "BinaryOutput::dump succeeds");
+            std::ifstream fa(pathGpu.native(), std::ios::binary), fb(pathRef.native(), std::ios::binary);
+            std::vector<char> ba((std::istreambuf_iterator<char>(fa)), std::istreambuf_iterator<char>());
+            std::vector<char> bb((std::istreambuf_iterator<char>(fb)), std::istreambuf_iterator<char>());
+            bool same = ba.size() == bb.size() && !ba.empty();
+            size_t firstDiff = 0;
+            for (size_t k = 0; same && k < ba.size(); ++k) {
+                if (ba[k] != bb[k] && !(k >= 68 && k < 84)) { // (bytes 69-84: build date of the writing translation unit)
+                    same = false;
+                    firstDiff = k;
+                }
+            }
+            printf("  snapshot sizes: device %zu bytes, reference %zu bytes, first difference at %zu\n", ba.size(), bb.size(), firstDiff);
+            expect(same, "snapshot written from the device planes is byte-identical to BinaryOutput's");
+            BinaryInput input;
+            Storage loaded;
+            Statistics loadedStats;
+            Outcome res = input.load(pathGpu, loaded, loadedStats);
+            expect(bool(res), "the reference's BinaryInput loads the device snapshot");
+            if (res) {
+                expect(loaded.getParticleCnt() == sc->getParticleCnt() && loaded.getMaterialCnt() == sc->getMaterialCnt(),
+                    "loaded snapshot has the same particles and materials");
+                expect(compareStorages(loaded, *sc, true, "snapshot round trip") == 0., "loaded snapshot equals the Storage bit for bit");
+            }
+        }
         expect(compareStorages(*sa, *sc, false, "GpuPredictorCorrector") <= 1.e-9, "state after device-resident PC steps within 1e-9");
 
         // ---- 3. self-gravity: GravitySolver<AsymmetricSolver> (Factory.cpp:300-312) next to GpuGravitySolver ----
