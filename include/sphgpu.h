@@ -50,7 +50,9 @@ enum {
     SPHGPU_FLAG_CORRECTION_TENSOR = 1u << 0,    /* RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR          */
     SPHGPU_FLAG_SUM_ONLY_UNDAMAGED = 1u << 1,   /* RunSettingsId::SPH_SUM_ONLY_UNDAMAGED                     */
     SPHGPU_FLAG_ADAPTIVE_H = 1u << 2,           /* SmoothingLengthEnum::CONTINUITY_EQUATION                  */
-    SPHGPU_FLAG_SOUND_SPEED_ENFORCING = 1u << 3 /* SmoothingLengthEnum::SOUND_SPEED_ENFORCING                */
+    SPHGPU_FLAG_SOUND_SPEED_ENFORCING = 1u << 3, /* SmoothingLengthEnum::SOUND_SPEED_ENFORCING               */
+    SPHGPU_FLAG_BALSARA = 1u << 4               /* RunSettingsId::SPH_AV_USE_BALSARA: BalsaraSwitch<StandardAV>,
+                                                   core/sph/equations/av/Balsara.h:36-153                      */
 };
 enum { SPHGPU_DISCR_STANDARD = 0, SPHGPU_DISCR_BENZ_ASPHAUG = 1 };        /* DiscretizationEnum            */
 enum { SPHGPU_CONTINUITY_STANDARD = 0, SPHGPU_CONTINUITY_SUM_ONLY_UNDAMAGED = 1 }; /* ContinuityEnum       */
@@ -98,7 +100,8 @@ enum {
     SPHGPU_Q_NEIGHBOR_CNT = 17,       /* u32                                                                 */
     SPHGPU_Q_MATERIAL_ID = 18,        /* u32  index into the materials passed to sphgpu_create; initialised from
                                          their [begin,end) ranges, must be uploaded for ghost particles      */
-    SPHGPU_Q_COUNT = 19
+    SPHGPU_Q_VELOCITY_ROTATION = 19,  /* Vector {x,y,z,0}: nabla x v, input and output of the Balsara switch  */
+    SPHGPU_Q_COUNT = 20
 };
 
 /* Host memory layouts understood by upload/download. */

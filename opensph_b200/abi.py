@@ -12,7 +12,7 @@ ABI_VERSION = 1
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_OOM, E_STATE = 0, -1, -2, -3, -4, -5
 
 FORCE_PRESSURE, FORCE_SOLID_STRESS = 1, 2
-FLAG_CORRECTION_TENSOR, FLAG_SUM_ONLY_UNDAMAGED, FLAG_ADAPTIVE_H, FLAG_SOUND_SPEED_ENFORCING = 1, 2, 4, 8
+FLAG_CORRECTION_TENSOR, FLAG_SUM_ONLY_UNDAMAGED, FLAG_ADAPTIVE_H, FLAG_SOUND_SPEED_ENFORCING, FLAG_BALSARA = 1, 2, 4, 8, 16
 EOS_NONE, EOS_IDEAL_GAS, EOS_TILLOTSON = 0, 1, 4
 YIELD_NONE, YIELD_ELASTIC, YIELD_VON_MISES, YIELD_DUST = 0, 1, 2, 4
 FRACTURE_NONE, FRACTURE_SCALAR_GRADY_KIPP = 0, 1
@@ -40,6 +40,7 @@ QUANTITIES: Dict[str, Tuple[int, int, type]] = {
     "FLAG": (16, 1, np.uint32),
     "NEIGHBOR_CNT": (17, 1, np.uint32),
     "MATERIAL_ID": (18, 1, np.uint32),
+    "VELOCITY_ROTATION": (19, 4, np.float64),
 }
 
 # snapshot array name -> (quantity, order)
@@ -138,7 +139,8 @@ def setup_from_snapshot(snap: Dict[str, np.ndarray], lut: Dict[str, np.ndarray] 
     cfg.kernel_radius, cfg.av_alpha, cfg.av_beta = rp[0], rp[1], rp[2]
     cfg.forces = (FORCE_PRESSURE if rp[3] else 0) | (FORCE_SOLID_STRESS if rp[4] else 0)
     cfg.flags = ((FLAG_CORRECTION_TENSOR if (rp[5] and rp[4]) else 0) | (FLAG_SUM_ONLY_UNDAMAGED if rp[6] else 0)
-                 | (FLAG_ADAPTIVE_H if rp[7] else 0) | (FLAG_SOUND_SPEED_ENFORCING if rp[8] else 0))
+                 | (FLAG_ADAPTIVE_H if rp[7] else 0) | (FLAG_SOUND_SPEED_ENFORCING if rp[8] else 0)
+                 | (FLAG_BALSARA if (len(rp) > 25 and rp[25]) else 0))
     cfg.continuity_mode = int(rp[9])
     cfg.discretization = int(rp[10])
     cfg.h_min, cfg.h_max = rp[11], rp[12]

@@ -147,6 +147,8 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
 
     ctx->solid = (cfg->forces & SPHGPU_FORCE_SOLID_STRESS) != 0;
     ctx->corrected = ctx->solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
+    ctx->balsara = (cfg->flags & SPHGPU_FLAG_BALSARA) != 0;
+    ctx->recDoubles = recordDoubles(ctx->solid, ctx->balsara);
     ctx->hasReduce = false;
     ctx->hasDamage = false;
     std::memset(ctx->matsHost, 0, sizeof(ctx->matsHost));
@@ -206,7 +208,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     for (int u = 0; u < U_COUNT; ++u) {
         SPH_TRY(devAlloc(&ctx->d.u[u], cap));
     }
-    SPH_TRY(devAlloc(&ctx->d.rec, cap * (size_t)(ctx->solid ? REC_SOLID : REC_FLUID)));
+    SPH_TRY(devAlloc(&ctx->d.rec, cap * (size_t)ctx->recDoubles));
     ctx->maxSegs = capacity / 64 + ctx->maxCells + ctx->maxCells / 16 + 2; // units <= N / 128 + double rows + x-range cuts
     SPH_TRY(devAlloc(&ctx->d.segStart, (size_t)ctx->maxCells + 2));
     SPH_TRY(devAlloc(&ctx->d.unitDesc, (size_t)ctx->maxSegs));

@@ -3,6 +3,8 @@
 // filter, kernel.grad, derivatives.eval) together with material->initialize (AsymmetricSolver.cpp:75-79),
 // accumulated.store + equations.finalize (:204-216) and material->finalize (:90-95).
 #include "sphgpu_internal.h"
+#include <algorithm>
+#include <cstddef>
 #include <mutex>
 
 namespace sph {
@@ -96,9 +98,10 @@ __global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_
 
     const double rhoInv2 = 1. / (rho * rho);
     const double m = d.f[F_M][i];
-    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
+    const bool balsara = (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0;
+    const int RD = recordDoubles(SOLID, balsara);
     double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * RD);
-    const uint32_t sw = SOLID ? (t & 7u) : 0u; // XOR swizzle of the solid record's pieces (sphgpu_internal.h)
+    const uint32_t sw = recordSwizzle(RD, t); // XOR swizzle of the 128-byte solid record's pieces (sphgpu_internal.h)
     const double x = d.f[F_X][i], y = d.f[F_Y][i], z = d.f[F_Z][i], h = d.f[F_H][i];
     rec[0 ^ sw] = make_double2(x, y);
     rec[1 ^ sw] = make_double2(z, h);
@@ -124,6 +127,10 @@ __global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_
         rec[4] = make_double2(p * rhoInv2, cs);
         rec[5] = make_double2(m / rho, 0.);
     }
+    if (balsara) { // the factor of the PREVIOUS evaluation's div v / rot v with the current sound speed (Balsara.h:76-80)
+        const double f = balsaraFactor(d.f[F_DIVV][i], d.f[F_ROTX][i], d.f[F_ROTY][i], d.f[F_ROTZ][i], cs, h);
+        rec[SOLID ? 8 : 6] = make_double2(f, 0.);
+    }
     if (rebuild) {
         d.sCell[t] = d.cellOf[i];
     }
@@ -137,17 +144,18 @@ __global__ void __launch_bounds__(256) k_pack_positions(DevicePointers d, uint32
     }
     const uint32_t i = d.order[t];
     double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * recDoubles);
-    const uint32_t sw = recDoubles == REC_SOLID ? (t & 7u) : 0u;
+    const uint32_t sw = recordSwizzle(recDoubles, t);
     rec[0 ^ sw] = make_double2(d.f[F_X][i], d.f[F_Y][i]);
     rec[1 ^ sw] = make_double2(d.f[F_Z][i], d.f[F_H][i]);
     d.sCell[t] = d.cellOf[i];
 }
 
-/// Unpacks one neighbour-input record (global or shared memory); `sw` = sorted (or staged) index & 7, the XOR swizzle of
-/// the solid record's pieces (ignored for fluid records).
+/// Unpacks the neighbour-input record with sorted index t from global memory (layouts: sphgpu_internal.h).
 template <bool SOLID>
-__device__ __forceinline__ void loadRecord(const double* __restrict__ recPtr, uint32_t sw, Particle& p) {
-    const double2* r = reinterpret_cast<const double2*>(recPtr);
+__device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, uint32_t t, int recDoubles, Particle& p) {
+    const double2* r = reinterpret_cast<const double2*>(recBase + (size_t)t * recDoubles);
+    const uint32_t sw = recordSwizzle(recDoubles, t);
+    p.bal = 0.;
     if (SOLID) {
         const double2 a = r[0 ^ sw], b = r[1 ^ sw], c = r[2 ^ sw], e = r[3 ^ sw], f = r[4 ^ sw], g = r[5 ^ sw], s1 = r[6 ^ sw],
                       s2 = r[7 ^ sw];
@@ -157,25 +165,29 @@ __device__ __forceinline__ void loadRecord(const double* __restrict__ recPtr, ui
         unpackCsGroup(f.y, p.cs, p.grp);
         p.vol = g.x;
         p.Sr[0] = g.y; p.Sr[1] = s1.x; p.Sr[2] = s1.y; p.Sr[3] = s2.x; p.Sr[4] = s2.y;
+        if (recDoubles == REC_SOLID_BALSARA) {
+            p.bal = r[8].x;
+        }
     } else {
         const double2 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
         p.x = a.x; p.y = a.y; p.z = b.x; p.h = b.y;
         p.vx = c.x; p.vy = c.y; p.vz = e.x; p.rho = e.y;
         p.P = f.x; p.cs = f.y; p.vol = g.x;
         p.grp = 0;
+        p.bal = r[6].x; // (the padding piece: the Balsara factor when the switch is on, unused otherwise)
     }
     p.m = p.vol * p.rho;
 }
 
 template <bool SOLID>
 __device__ __forceinline__ void loadSorted(const DevicePointers& d, uint32_t t, Particle& p) {
-    loadRecord<SOLID>(d.rec + (size_t)t * (SOLID ? REC_SOLID : REC_FLUID), t & 7u, p);
+    loadRecord<SOLID>(d.rec, t, recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0), p);
 }
 
 /// Position pieces {x, y}, {z, h} of the sorted record t.
 __device__ __forceinline__ void loadSortedPosition(const double* __restrict__ rec, uint32_t t, int recDoubles, double2& pxy, double2& pzh) {
     const double2* r = reinterpret_cast<const double2*>(rec + (size_t)t * recDoubles);
-    const uint32_t sw = recDoubles == REC_SOLID ? (t & 7u) : 0u;
+    const uint32_t sw = recordSwizzle(recDoubles, t);
     pxy = r[0 ^ sw];
     pzh = r[1 ^ sw];
 }
@@ -190,6 +202,11 @@ __device__ __forceinline__ void storeDerivs(const DevicePointers& d, uint32_t i,
     d.f[F_DRHO][i] = o.drho;
     d.f[F_DIVV][i] = o.divv;
     d.u[U_NCNT][i] = o.ncnt;
+    if (c_prm.flags & SPHGPU_FLAG_BALSARA) {
+        d.f[F_ROTX][i] = o.rot[0];
+        d.f[F_ROTY][i] = o.rot[1];
+        d.f[F_ROTZ][i] = o.rot[2];
+    }
     if (SOLID) {
         for (int k = 0; k < 5; ++k) {
             d.f[F_DS0 + k][i] = o.dS[k];
@@ -238,7 +255,7 @@ __device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t
     const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
     const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
+    const int RD = recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0);
     for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
         for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
             const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
@@ -299,28 +316,27 @@ __global__ void __launch_bounds__(128) k_large_neighbours(DevicePointers d, uint
     if (g.nLarge == 0u) {
         return;
     }
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.largeBegin) {
-        return;
-    }
-    Accum acc;
-    accumZero(acc);
-    Particle pi;
-    loadSorted<SOLID>(d, t, pi);
-    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
-    for (uint32_t k = g.largeBegin; k < nActive; ++k) {
-        double2 pxy, pzh;
-        loadSortedPosition(d.rec, k, RD, pxy, pzh);
-        const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
-        double d2, hbar;
-        if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
-            continue;
+    const int RD = recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0);
+    // (a small grid with a stride loop: in the usual case -- no large particles -- the launch must cost next to nothing)
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < g.largeBegin; t += gridDim.x * blockDim.x) {
+        Accum acc;
+        accumZero(acc);
+        Particle pi;
+        loadSorted<SOLID>(d, t, pi);
+        for (uint32_t k = g.largeBegin; k < nActive; ++k) {
+            double2 pxy, pzh;
+            loadSortedPosition(d.rec, k, RD, pxy, pzh);
+            const double dx = pi.x - pxy.x, dy = pi.y - pxy.y, dz = pi.z - pzh.x;
+            double d2, hbar;
+            if (!isNeighbour(dx, dy, dz, pi.h, pzh.y, c_prm.kernel_radius, d2, hbar)) {
+                continue;
+            }
+            Particle pj;
+            loadSorted<SOLID>(d, k, pj);
+            pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
         }
-        Particle pj;
-        loadSorted<SOLID>(d, k, pj);
-        pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+        d.accLarge[t] = acc;
     }
-    d.accLarge[t] = acc;
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
@@ -332,8 +348,8 @@ __global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_
     // The grid's CTAs are dealt to the large targets: target L gets S = gridDim / nLarge CTAs, each summing one slice of
     // the particles; the CTA that finishes last adds the slices' partial sums in slice order (the result does not depend
     // on which one that is) and runs the finalizers.
-    constexpr int RD = SOLID ? REC_SOLID : REC_FLUID;
-    constexpr int NV = 23; // doubles of Accum in front of the counter
+    const int RD = recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0);
+    constexpr int NV = (int)(offsetof(Accum, cnt) / sizeof(double)); // doubles of Accum in front of the counter
     __shared__ double red[8][NV];
     __shared__ uint32_t redCnt[8];
     __shared__ bool isLast;
@@ -432,7 +448,7 @@ __global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_
 template <bool SOLID, bool CORRECTED, bool FILTER>
 static int launchLargeVariant(sphgpu_ctx* ctx) {
     const uint32_t n = ctx->nActive;
-    k_large_neighbours<SOLID, CORRECTED, FILTER><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n);
+    k_large_neighbours<SOLID, CORRECTED, FILTER><<<std::min<uint32_t>((n + 127) / 128, 148u * 8u), 128, 0, ctx->stream>>>(ctx->d, n);
     k_large_targets<SOLID, CORRECTED, FILTER><<<(unsigned)LARGE_MAX, 256, 0, ctx->stream>>>(ctx->d, n, ctx->n);
     ctx->launches += 2;
     SPH_CUDA_CHECK(cudaGetLastError());
@@ -538,7 +554,7 @@ int launchProloguePackPositionsOnly(sphgpu_ctx* ctx) {
     if (n == 0) {
         return SPHGPU_OK;
     }
-    k_pack_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n, ctx->solid ? REC_SOLID : REC_FLUID);
+    k_pack_positions<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n, ctx->recDoubles);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
@@ -587,7 +603,7 @@ int launchNeighbourCount(sphgpu_ctx* ctx, uint32_t* countsDev) {
     if (n == 0) {
         return SPHGPU_OK;
     }
-    k_neighbour_lists<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, countsDev, nullptr, nullptr, ctx->solid ? REC_SOLID : REC_FLUID);
+    k_neighbour_lists<false><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, countsDev, nullptr, nullptr, ctx->recDoubles);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
@@ -597,7 +613,7 @@ int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, u
     if (n == 0) {
         return SPHGPU_OK;
     }
-    k_neighbour_lists<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, nullptr, offsetsDev, idxDev, ctx->solid ? REC_SOLID : REC_FLUID);
+    k_neighbour_lists<true><<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, ctx->n, nullptr, offsetsDev, idxDev, ctx->recDoubles);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }

@@ -842,11 +842,14 @@ __global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint
 // (threads 0..15 also the descriptor of the next block), waits on the mbarrier and walks its list; one CTA barrier frees
 // the stage. At the end of a chain the first block of the CTA's next unit is issued BEFORE the finalizers / stores of the
 // finished unit and the loads of the next unit's targets, so those overlap with the copies.
-template <bool SOLID>
+template <bool SOLID, bool BALSARA>
 struct SumLayout {
-    static constexpr int S = SOLID ? REC_SOLID : REC_FLUID;     // doubles per staged record
+    static constexpr int S = SOLID ? (BALSARA ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID; // doubles per staged record
     static constexpr uint32_t REC_BYTES = (uint32_t)S * 8u;
-    static constexpr size_t bytes = (size_t)TILE_C * REC_BYTES; // 73 728 B solid, 64 512 B fluid
+    static constexpr bool SWIZZLED = S == REC_SOLID;
+    static constexpr size_t bytes = (size_t)TILE_C * REC_BYTES; // 73 728 B solid (three CTAs per SM), 64 512 B fluid, 82 944 B
+                                                                // solid with the Balsara factor (two CTAs per SM)
+    static constexpr int CTAS_PER_SM = bytes > 74 * 1024 ? 2 : 3;
 };
 
 /// One list entry between the two stages of the pair body (sph_math.cuh).
@@ -858,17 +861,18 @@ struct PairSlot {
 };
 
 /// Stage A of staged record k: the position pieces and {vz, rho} (LDS.128 through 32-bit shared addresses), geometry,
-/// and the table load. `stage` is 128-byte aligned, so piece c of a solid record sits at (record start + swizzle) ^ (c << 4).
-template <bool SOLID>
+/// and the table load. `stage` is 128-byte aligned, so piece c of a swizzled (128-byte) record sits at
+/// (record start + swizzle) ^ (c << 4); the other layouts have an odd stride and plain offsets.
+template <typename P>
 __device__ __forceinline__ void stageA(uint32_t stage, uint32_t k, uint32_t selfIdx, const Particle& pi, const LutPair* lut2, PairSlot& s) {
     double2 a, b, e;
-    if (SOLID) {
+    if (P::SWIZZLED) {
         s.rec = stage + k * 128u + ((k & 7u) << 4);
         a = loadSharedD2(s.rec);
         b = loadSharedD2(s.rec ^ 16u);
         e = loadSharedD2(s.rec ^ 48u);
     } else {
-        s.rec = stage + k * (uint32_t)(REC_FLUID * 8);
+        s.rec = stage + k * P::REC_BYTES;
         a = loadSharedD2(s.rec);
         b = loadSharedD2(s.rec + 16u);
         e = loadSharedD2(s.rec + 48u);
@@ -881,14 +885,31 @@ __device__ __forceinline__ void stageA(uint32_t stage, uint32_t k, uint32_t self
 }
 
 /// Stage B: the rest of the record and the sums.
-template <bool SOLID, bool CORRECTED, bool FILTER>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA>
 __device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Accum& acc) {
+    using P = SumLayout<SOLID, BALSARA>;
     Particle pj;
     pj.vz = s.vz;
     pj.rho = s.rho;
+    pj.bal = 0.;
     if (SOLID) {
-        const double2 c = loadSharedD2(s.rec ^ 32u), f = loadSharedD2(s.rec ^ 64u), g = loadSharedD2(s.rec ^ 80u);
-        const double2 s1 = loadSharedD2(s.rec ^ 96u), s2 = loadSharedD2(s.rec ^ 112u);
+        double2 c, f, g, s1, s2;
+        if (P::SWIZZLED) {
+            c = loadSharedD2(s.rec ^ 32u);
+            f = loadSharedD2(s.rec ^ 64u);
+            g = loadSharedD2(s.rec ^ 80u);
+            s1 = loadSharedD2(s.rec ^ 96u);
+            s2 = loadSharedD2(s.rec ^ 112u);
+        } else {
+            c = loadSharedD2(s.rec + 32u);
+            f = loadSharedD2(s.rec + 64u);
+            g = loadSharedD2(s.rec + 80u);
+            s1 = loadSharedD2(s.rec + 96u);
+            s2 = loadSharedD2(s.rec + 112u);
+            if (BALSARA) {
+                pj.bal = loadSharedD2(s.rec + 128u).x;
+            }
+        }
         pj.vx = c.x; pj.vy = c.y;
         pj.P = f.x;
         unpackCsGroup(f.y, pj.cs, pj.grp);
@@ -899,14 +920,17 @@ __device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Ac
         pj.vx = c.x; pj.vy = c.y;
         pj.P = f.x; pj.cs = f.y; pj.vol = g.x;
         pj.grp = 0;
+        if (BALSARA) {
+            pj.bal = loadSharedD2(s.rec + 96u).x;
+        }
     }
     pj.m = pj.vol * pj.rho;
-    pairSums<SOLID, CORRECTED, FILTER>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc);
+    pairSums<SOLID, CORRECTED, FILTER, BALSARA>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc);
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER>
-__global__ void __launch_bounds__(TILE_T, 3) k_pair_sum(DevicePointers d, uint32_t maxCells) {
-    using P = SumLayout<SOLID>;
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA>
+__global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA>::CTAS_PER_SM)) k_pair_sum(DevicePointers d, uint32_t maxCells) {
+    using P = SumLayout<SOLID, BALSARA>;
     extern __shared__ __align__(128) unsigned char smemStage[];
     __shared__ __align__(8) uint64_t stageBar;
     __shared__ uint32_t sFirst[2][16]; // first-block descriptors of the CTA's current and next unit
@@ -971,7 +995,7 @@ __global__ void __launch_bounds__(TILE_T, 3) k_pair_sum(DevicePointers d, uint32
         u.target = u.live && (word & 0x40000000u) == 0u; // ghosts are neighbours only
         u.slot = u.target ? d.order[u.t] : 0xffffffffu;
         if (u.live) {
-            loadRecord<SOLID>(d.rec + (size_t)u.t * P::S, u.t & 7u, pi);
+            loadRecord<SOLID>(d.rec, u.t, P::S, pi);
         } else {
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
@@ -1069,29 +1093,29 @@ __global__ void __launch_bounds__(TILE_T, 3) k_pair_sum(DevicePointers d, uint32
             // it runs on whatever the exhausted quads hold and its result is dropped): every [A; B] pair below is ONE
             // basic block, so that the scheduler interleaves the two stages.
             PairSlot s0, s1;
-            stageA<SOLID>(stage, cur.x & 0xffffu, selfIdx, pi, d.lut2, s0);
+            stageA<P>(stage, cur.x & 0xffffu, selfIdx, pi, d.lut2, s0);
             uint32_t q = 0;
             while (true) {
                 quads += TILE_T;
                 uint2 nxt = make_uint2(0u, 0u);
                 loadGlobalU2If(q + 4u < cnt, quads, nxt);
-                stageA<SOLID>(stage, cur.x >> 16, selfIdx, pi, d.lut2, s1);
-                stageB<SOLID, CORRECTED, FILTER>(s0, pi, acc);
+                stageA<P>(stage, cur.x >> 16, selfIdx, pi, d.lut2, s1);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s0, pi, acc);
                 if (++q >= cnt) {
                     break;
                 }
-                stageA<SOLID>(stage, cur.y & 0xffffu, selfIdx, pi, d.lut2, s0);
-                stageB<SOLID, CORRECTED, FILTER>(s1, pi, acc);
+                stageA<P>(stage, cur.y & 0xffffu, selfIdx, pi, d.lut2, s0);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s1, pi, acc);
                 if (++q >= cnt) {
                     break;
                 }
-                stageA<SOLID>(stage, cur.y >> 16, selfIdx, pi, d.lut2, s1);
-                stageB<SOLID, CORRECTED, FILTER>(s0, pi, acc);
+                stageA<P>(stage, cur.y >> 16, selfIdx, pi, d.lut2, s1);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s0, pi, acc);
                 if (++q >= cnt) {
                     break;
                 }
-                stageA<SOLID>(stage, nxt.x & 0xffffu, selfIdx, pi, d.lut2, s0);
-                stageB<SOLID, CORRECTED, FILTER>(s1, pi, acc);
+                stageA<P>(stage, nxt.x & 0xffffu, selfIdx, pi, d.lut2, s0);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s1, pi, acc);
                 if (++q >= cnt) {
                     break;
                 }
@@ -1174,26 +1198,33 @@ static int launchLists(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER>
-static int launchSumVariant(sphgpu_ctx* ctx) {
-    auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER>;
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA>
+static int launchSumVariantB(sphgpu_ctx* ctx) {
+    auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER, BALSARA>;
     static bool configured[64] = {}; // per instantiation and device; the attribute is per device function
-    const size_t smem = SumLayout<SOLID>::bytes;
+    const size_t smem = SumLayout<SOLID, BALSARA>::bytes;
     if (!configured[ctx->device & 63]) {
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[ctx->device & 63] = true;
     }
     // many more CTAs than fit at once: the block scheduler balances the load (measured: 32 waves beat 8 by 1 %, 1 by 4 %)
-    kernel<<<unitGrid(ctx, 3, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
+    kernel<<<unitGrid(ctx, SumLayout<SOLID, BALSARA>::CTAS_PER_SM, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
+static int launchSumVariant(sphgpu_ctx* ctx) {
+    return ctx->balsara ? launchSumVariantB<SOLID, CORRECTED, FILTER, true>(ctx) : launchSumVariantB<SOLID, CORRECTED, FILTER, false>(ctx);
+}
+
+template <bool SOLID, bool CORRECTED, bool FILTER>
 static int launchFallback(sphgpu_ctx* ctx, bool allUnits) {
-    k_pair_fallback<SOLID, CORRECTED, FILTER><<<unitGrid(ctx, 8, 4), TILE_T, 0, ctx->stream>>>(ctx->d, ctx->maxCells, allUnits);
+    // (all units: a full grid; otherwise a small one -- the kernel returns at once unless the list pool overflowed)
+    k_pair_fallback<SOLID, CORRECTED, FILTER><<<unitGrid(ctx, allUnits ? 8 : 2, allUnits ? 4 : 1), TILE_T, 0, ctx->stream>>>(ctx->d, ctx->maxCells,
+        allUnits);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;

@@ -223,6 +223,14 @@ SPH_HD double damageRate(const MaterialDev& m, double p, const double S[5], doub
     return growth * cbrt(fmin(pow(ratio, mZero), (double)nFlaws));
 }
 
+/// BalsaraSwitch::Derivative::factor (core/sph/equations/av/Balsara.h:76-80), from the divergence and rotation of the
+/// PREVIOUS evaluation (the Storage values at the time of the call) and the current sound speed.
+SPH_HD double balsaraFactor(double divv, double rx, double ry, double rz, double cs, double h) {
+    const double dv = fabs(divv);
+    const double rv = sqrt(rx * rx + ry * ry + rz * rz);
+    return dv / (dv + rv + 1.e-4 * cs / h);
+}
+
 // ---- pair interaction ------------------------------------------------------------------------------------
 
 /// What one particle contributes as a neighbour. P = p/rho^2, Sr = S/rho^2, vol = m/rho, grp = body flag or -1 if the
@@ -233,6 +241,7 @@ struct Particle {
     double vx, vy, vz;
     double m, rho, P, cs, vol;
     double Sr[5];
+    double bal; // Balsara factor |div v| / (|div v| + |rot v| + 1e-4 cs / h) (Balsara.h:76-80); unused without the switch
     int grp;
 };
 
@@ -242,6 +251,7 @@ struct Accum {
     double T[9];
     double Cm[6];
     double F[3]; // sum of the stress-weighted kernel gradients m_j gradW (pairSums): the target's own Sr is applied once
+    double rot[3]; // sum m_j gradW x (v_j - v_i)  (VelocityRotation, DerivativeHelpers.h:374-395; Balsara switch only)
     uint32_t cnt;
 };
 
@@ -254,6 +264,7 @@ SPH_HD void accumZero(Accum& a) {
         a.Cm[k] = 0.;
     }
     a.F[0] = a.F[1] = a.F[2] = 0.;
+    a.rot[0] = a.rot[1] = a.rot[2] = 0.;
     a.cnt = 0;
 }
 
@@ -368,13 +379,26 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
 
     // artificial viscosity: w = (v_i - v_j).(r_i - r_j) = -(dv.d)
     const double w = -(dvx * dx + dvy * dy + dvz * dz);
+    const bool balsara = (prm.flags & SPHGPU_FLAG_BALSARA) != 0;
     double Pi = 0.;
     if (w < 0.) {
         const double rhobar = 0.5 * (pi.rho + pj.rho);
         const double csbar = 0.5 * (pi.cs + pj.cs);
         const double mu = hbar * w / (d2 + 1.e-2 * hbar * hbar);
         Pi = (-prm.av_alpha * csbar * mu + prm.av_beta * mu * mu) / rhobar;
+        if (balsara) {
+            Pi *= 0.5 * (pi.bal + pj.bal);
+        }
         acc.du += 0.5 * Pi * (-pj.m * dvg); // m_j * 0.5 * Pi * (v_i - v_j).gradW
+    }
+    if (balsara) {
+        // rot v: m_j gradW x (v_j - v_i)
+        acc.rot[0] += pj.m * (gy * dvz - gz * dvy);
+        acc.rot[1] += pj.m * (gz * dvx - gx * dvz);
+        acc.rot[2] += pj.m * (gx * dvy - gy * dvx);
+        // BalsaraSwitch::Derivative::eval returns +Pi gradW (Balsara.h:69-74) where StandardAV returns -Pi gradW
+        // (Standard.h:63-70); the drop-in reproduces the reference as it is
+        Pi = -Pi;
     }
     // pressure gradient + AV: dv_i -= m_j (P_i + P_j + Pi) gradW
     const double c = pi.P + pj.P + Pi;
@@ -489,7 +513,7 @@ SPH_HD void pairGeometry(const ParamsDev& prm, double xi, double yi, double zi, 
 /// Stage B. G = the interpolated table value g + ratio dg of entry g.k. Of pi only v, P, cs, grp are read; of pj v, m,
 /// P, cs, vol, Sr, grp. The stress sum is split: sum_j (Sr_i + Sr_j) f_j = Sr_i F + sum_j Sr_j f_j with F = sum_j f_j
 /// (acc.F, applied by finalizeParticle), which saves the target's Sr registers and two additions per pair.
-template <bool SOLID, bool CORRECTED, bool FILTER>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false>
 SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& pj, const PairGeom& g, double G, Accum& acc) {
     acc.cnt += g.valid ? 1u : 0u;
     const double mj = selectD(g.valid, pj.m, 0.);
@@ -506,9 +530,17 @@ SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& p
     // w clamped to min(w, 0) the receding pairs give mu = 0 and Pi = 0 exactly, without a branch. Q = Pi / 2.
     const double w = fmin(-t, 0.);
     const double mu = (g.hbar * w) * g.iD;
-    const double Q = mu * fma(prm.av_beta, mu, prm.av_minus_half_alpha * (pi.cs + pj.cs)) * g.irs;
+    double Q = mu * fma(prm.av_beta, mu, prm.av_minus_half_alpha * (pi.cs + pj.cs)) * g.irs;
+    if (BALSARA) {
+        Q *= 0.5 * (pi.bal + pj.bal);
+        // rot v: m_j gradW x (v_j - v_i) = (m_j s) d x dv
+        acc.rot[0] = fma(ms, dy * dvz - dz * dvy, acc.rot[0]);
+        acc.rot[1] = fma(ms, dz * dvx - dx * dvz, acc.rot[1]);
+        acc.rot[2] = fma(ms, dx * dvy - dy * dvx, acc.rot[2]);
+    }
     acc.du -= Q * mdvg;
-    const double c = fma(2., Q, pi.P + pj.P);
+    // (the Balsara-switched viscosity enters the acceleration with the opposite sign, as in Balsara.h:69-74)
+    const double c = fma(BALSARA ? -2. : 2., Q, pi.P + pj.P);
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
@@ -557,12 +589,18 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const LutPair* __restrict
     Accum& acc) {
     PairGeom g;
     pairGeometry(prm, pi.x, pi.y, pi.z, pi.h, pi.rho, pj.x, pj.y, pj.z, pj.h, pj.rho, g);
-    pairSums<SOLID, CORRECTED, FILTER>(prm, pi, pj, g, fma(g.ratio, lut2[g.k].dg, lut2[g.k].g), acc);
+    const double G = fma(g.ratio, lut2[g.k].dg, lut2[g.k].g);
+    if (prm.flags & SPHGPU_FLAG_BALSARA) {
+        pairSums<SOLID, CORRECTED, FILTER, true>(prm, pi, pj, g, G, acc);
+    } else {
+        pairSums<SOLID, CORRECTED, FILTER, false>(prm, pi, pj, g, G, acc);
+    }
 }
 
 /// Derivatives of one particle (everything IAsymmetricSolver::afterLoop leaves in the Storage for particle i).
 struct Derivs {
     double ax, ay, az, vh, du, drho, divv;
+    double rot[3];
     double dS[5];
     double gradv[6];
     double corr[6];
@@ -587,6 +625,9 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
         out.az += sxz * acc.F[0] + syz * acc.F[1] + (-sxx - syy) * acc.F[2];
     }
     out.divv = acc.divv * rhoInv;
+    out.rot[0] = acc.rot[0] * rhoInv;
+    out.rot[1] = acc.rot[1] * rhoInv;
+    out.rot[2] = acc.rot[2] * rhoInv;
     double du = acc.du;
     double trGradv = 0.;
     if (SOLID) {

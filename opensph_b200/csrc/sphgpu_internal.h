@@ -28,6 +28,7 @@ enum Field : int {
     F_C0, F_C1, F_C2, F_C3, F_C4, F_C5,       // STRAIN_RATE_CORRECTION_TENSOR
     // PredictorCorrector "predictions": copies of the highest derivatives (TimeStepping.cpp:272-282)
     F_AXP, F_AYP, F_AZP, F_DRHOP, F_DUP, F_DSP0, F_DSP1, F_DSP2, F_DSP3, F_DSP4, F_DDP,
+    F_ROTX, F_ROTY, F_ROTZ,       // VELOCITY_ROTATION (Balsara switch): result of the last evaluation, input of the next
     F_COUNT
 };
 
@@ -42,8 +43,19 @@ enum UField : int { U_NFLAWS, U_FLAG, U_MATID, U_NCNT, U_COUNT };
 // groups of shared memory although the stride is a multiple of 128 bytes. Staged copies keep t mod 8 (the chunk
 // builder aligns every staged row piece accordingly), so the same loader serves global and shared memory.
 // Fluid: the first 6 pieces + 16 bytes of padding = 7 pieces (odd stride, no swizzle needed).
-constexpr int REC_SOLID = 16; // doubles per record, solid
-constexpr int REC_FLUID = 14; // doubles per record, fluid
+// With the Balsara switch every particle also contributes its factor f: a fluid record keeps it in the padding piece
+// {f, -}; a solid record grows to nine pieces = 144 bytes {... | f, -} with an odd stride and therefore no swizzle.
+constexpr int REC_SOLID = 16;         // doubles per record, solid
+constexpr int REC_FLUID = 14;         // doubles per record, fluid
+constexpr int REC_SOLID_BALSARA = 18; // doubles per record, solid with the Balsara switch
+
+__host__ __device__ inline int recordDoubles(bool solid, bool balsara) {
+    return solid ? (balsara ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID;
+}
+/// XOR swizzle of the record with sorted / staged index t (0 for the layouts with an odd stride).
+__host__ __device__ inline uint32_t recordSwizzle(int recDoubles, uint32_t t) {
+    return recDoubles == REC_SOLID ? (t & 7u) : 0u;
+}
 
 struct GridDev {
     double lo[3];
@@ -156,7 +168,8 @@ struct sphgpu_ctx {
     sph::MaterialDev matsHost[sph::MAX_MATERIALS];
     sphgpu_material matsApi[sph::MAX_MATERIALS];
     uint32_t nMaterials = 0;
-    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false;
+    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false;
+    int recDoubles = sph::REC_FLUID; // doubles per sorted neighbour record of this context
     sph::DevicePointers d{};
     void* staging = nullptr;   // device staging for AoS <-> SoA repack (capacity * 64 B)
     // asynchronous downloads (sphgpu_download_async): results are packed into stagingDown on `stream` and leave on

@@ -48,6 +48,7 @@ static QuantityMap quantityMap(int q, int order) {
     case SPHGPU_Q_FLAG: if (order == 0) { set(1, { U_FLAG }); m.isU32 = true; } break;
     case SPHGPU_Q_NEIGHBOR_CNT: if (order == 0) { set(1, { U_NCNT }); m.isU32 = true; } break;
     case SPHGPU_Q_MATERIAL_ID: if (order == 0) { set(1, { U_MATID }); m.isU32 = true; } break;
+    case SPHGPU_Q_VELOCITY_ROTATION: if (order == 0) set(4, { F_ROTX, F_ROTY, F_ROTZ, -1 }); break;
     default: break;
     }
     return m;

@@ -35,6 +35,7 @@ const Mirror MIRRORS[] = {
     { QuantityId::STRESS_REDUCING, SPHGPU_Q_STRESS_REDUCING, 1, 0 },
     { QuantityId::VELOCITY_DIVERGENCE, SPHGPU_Q_VELOCITY_DIVERGENCE, 1, 0 },
     { QuantityId::VELOCITY_GRADIENT, SPHGPU_Q_VELOCITY_GRADIENT, 6, 0 },
+    { QuantityId::VELOCITY_ROTATION, SPHGPU_Q_VELOCITY_ROTATION, 4, 0 },
     { QuantityId::STRAIN_RATE_CORRECTION_TENSOR, SPHGPU_Q_CORRECTION_TENSOR, 6, 0 },
     { QuantityId::EPS_MIN, SPHGPU_Q_EPS_MIN, 1, 0 },
     { QuantityId::M_ZERO, SPHGPU_Q_M_ZERO, 1, 0 },

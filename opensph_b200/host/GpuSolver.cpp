@@ -3,6 +3,7 @@
 #include "objects/Exceptions.h"
 #include "quantities/IMaterial.h"
 #include "quantities/Storage.h"
+#include "sph/equations/av/Balsara.h"
 #include "sph/equations/av/Standard.h"
 #include "system/Factory.h"
 #include "system/Statistics.h"
@@ -58,13 +59,18 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     known += equations.contains<SolidStressForce>() ? 1 : 0;
     known += equations.contains<ContinuityEquation>() ? 1 : 0;
     known += equations.contains<StandardAV>() ? 1 : 0;
+    known += equations.contains<BalsaraSwitch<StandardAV>>() ? 1 : 0;
     known += equations.contains<AdaptiveSmoothingLength>() ? 1 : 0;
     known += equations.contains<ConstSmoothingLength>() ? 1 : 0;
     if (known != equations.getTermCnt()) {
         throw InvalidSetup("GpuSolver: the equation set contains a term without a GPU implementation");
     }
-    if (!equations.contains<PressureForce>() || !equations.contains<ContinuityEquation>() || !equations.contains<StandardAV>()) {
-        throw InvalidSetup("GpuSolver needs PressureForce, ContinuityEquation and StandardAV (the collision preset)");
+    if (!equations.contains<PressureForce>() || !equations.contains<ContinuityEquation>() ||
+        !(equations.contains<StandardAV>() || equations.contains<BalsaraSwitch<StandardAV>>())) {
+        throw InvalidSetup("GpuSolver needs PressureForce, ContinuityEquation and StandardAV, plain or with the Balsara switch");
+    }
+    if (equations.contains<BalsaraSwitch<StandardAV>>() && settings.get<bool>(RunSettingsId::SPH_AV_BALSARA_STORE)) {
+        throw InvalidSetup("GpuSolver: SPH_AV_BALSARA_STORE (the AV_BALSARA output quantity) is not implemented on the device");
     }
     // same check as AsymmetricSolver::sanityCheck (AsymmetricSolver.cpp:228-234)
     if (!equations.contains<AdaptiveSmoothingLength>() && !equations.contains<ConstSmoothingLength>()) {
@@ -145,6 +151,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     }
     if (settings.get<bool>(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED)) {
         cfg.flags |= SPHGPU_FLAG_SUM_ONLY_UNDAMAGED;
+    }
+    if (equations.contains<BalsaraSwitch<StandardAV>>()) {
+        cfg.flags |= SPHGPU_FLAG_BALSARA;
     }
     if (equations.contains<AdaptiveSmoothingLength>()) {
         cfg.flags |= SPHGPU_FLAG_ADAPTIVE_H;
@@ -259,6 +268,11 @@ void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives)
             check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Size>(b.id)[0], 0, n));
         }
     }
+    if (storage.has(QuantityId::VELOCITY_ROTATION)) {
+        // the Balsara factor is built from the divergence and rotation of the previous evaluation (Balsara.h:76-80)
+        check(sphgpu_upload(c, SPHGPU_Q_VELOCITY_ROTATION, 0, L, &storage.getValue<Vector>(QuantityId::VELOCITY_ROTATION)[0], 0, n));
+        check(sphgpu_upload(c, SPHGPU_Q_VELOCITY_DIVERGENCE, 0, L, &storage.getValue<Float>(QuantityId::VELOCITY_DIVERGENCE)[0], 0, n));
+    }
     if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
         check(sphgpu_upload(c, SPHGPU_Q_DEVIATORIC_STRESS, 0, L, &storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
         if (derivatives) {
@@ -298,6 +312,9 @@ void GpuSolver::downloadQuantities(Storage& storage, const bool stateToo) {
     if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
         check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 0, L, &storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
         check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 1, L, &storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+    }
+    if (storage.has(QuantityId::VELOCITY_ROTATION)) {
+        check(sphgpu_download(c, SPHGPU_Q_VELOCITY_ROTATION, 0, L, &storage.getValue<Vector>(QuantityId::VELOCITY_ROTATION)[0], 0, n));
     }
     if (storage.has(QuantityId::VELOCITY_GRADIENT)) {
         check(sphgpu_download(c, SPHGPU_Q_VELOCITY_GRADIENT, 0, L, &storage.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT)[0], 0, n));

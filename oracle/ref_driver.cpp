@@ -11,7 +11,7 @@
 // Commands
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
 //                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
-//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--criteria MASK]
+//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--criteria MASK]
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
@@ -190,6 +190,9 @@ RunSettings makeSettings(const std::string& config, const Args& args) {
     }
     if (args.has("continuity-undamaged")) { // ContinuityEnum::SUM_ONLY_UNDAMAGED (EquationTerm.cpp:302-313)
         settings.set(RunSettingsId::SPH_CONTINUITY_MODE, ContinuityEnum::SUM_ONLY_UNDAMAGED);
+    }
+    if (args.has("balsara")) { // BalsaraSwitch<StandardAV> (core/sph/equations/av/Balsara.h)
+        settings.set(RunSettingsId::SPH_AV_USE_BALSARA, true);
     }
     if (args.has("sum-all")) { // SPH_SUM_ONLY_UNDAMAGED = false: no undamaged filter
         settings.set(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED, false);
@@ -416,6 +419,7 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
         settings.get<Float>(RunSettingsId::TIMESTEPPING_MAX_INCREASE),
         double(int(settings.get<SolverEnum>(RunSettingsId::SPH_SOLVER_TYPE))),
         double(int(settings.get<TimesteppingEnum>(RunSettingsId::TIMESTEPPING_INTEGRATOR))),
+        double(settings.get<bool>(RunSettingsId::SPH_AV_USE_BALSARA)),
     };
     w.addF64("run_params", run, 1);
 

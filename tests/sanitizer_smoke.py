@@ -53,5 +53,23 @@ ext = np.ptp(i["pos"][:, :3], axis=0).max()
 snap["pos"] = snap["pos"].copy()
 snap["pos"][:, :3] += np.repeat(rng.uniform(0, 2.0 * ext, (reps, 3)), n0, axis=0)
 snap["pos"][n // 2, 3] = 4.0 * ext
-run(snap, setup, 0, "giant h")
+run(snap, setup, 0, "giant h (two-level radii)")
+snap["pos"][rng.choice(n, 1200, replace=False), 3] = 4.0 * ext
+run(snap, setup, 0, "1200 giants (degenerate single-level grid)")
+
+# a few PredictorCorrector steps with list reuse (cp.async prefetches, early-exit build kernels) and the Balsara switch
+names = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "damage", "ddamage", "reduce",
+         "eps_min", "m_zero", "growth", "n_flaws", "flag")
+small = workloads.basalt_sphere_state(6000, 5.0e4, solid=True)
+small["vel"] = small["vel"] * 40.0
+for balsara in (False, True):
+    setup = workloads.make_setup(len(small["mass"]), solid=True)
+    if balsara:
+        setup.cfg.flags |= abi.FLAG_BALSARA
+    eng = Engine(setup, len(small["mass"]))
+    eng.set_list_skin(0.04)
+    eng.upload_state(small, names)
+    dts, _, st = eng.run_pc(8, 0.01, 10.0)
+    print("run_pc 8 steps, balsara", balsara, "pairs", st.pair_count, "list builds / age / metric", eng.list_stats())
+    eng.close()
 print("SANITIZER SMOKE DONE")

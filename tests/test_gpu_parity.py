@@ -500,3 +500,42 @@ def test_async_transfers_equal_synchronous_ones(lut):
             assert np.array_equal(out[k], ref[k]), k
     a.close()
     b.close()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("config", ["collision_preset", "fluid"])
+def test_balsara_switch_against_live_reference(config, tmp_path):
+    """BalsaraSwitch<StandardAV> (core/sph/equations/av/Balsara.h). One evaluation (the factor is built
+    from the PREVIOUS evaluation's div v and rot v, so it is zero here and the viscosity is off) and five
+    PredictorCorrector steps, in which the factors are live, against the reference's own integrator."""
+    i, o = run_ref(str(tmp_path), ["--config", config, "--n", 20000, "--jitter", 18, "--balsara"])
+    setup = abi.setup_from_snapshot(i)
+    assert setup.cfg.flags & abi.FLAG_BALSARA
+    eng, stats = gpu_integrate(i, setup)
+    check_against(eng, stats, o)
+    eng.close()
+    i, o = run_ref(str(tmp_path), ["--config", config, "--n", 20000, "--steps", 5, "--balsara"])
+    setup = abi.setup_from_snapshot(i)
+    consts = abi.run_constants(i)
+    eng = Engine(setup, len(i["mass"]))
+    eng.upload_state(i, STATE_IN + ("acc", "drho", "du", "dS", "ddamage"))
+    eng.set_last_timestep(consts["initial_dt"])
+    dts = o["dt_history"]
+    for s in range(len(dts) - 1):
+        dt, _, _ = eng.step_pc(float(dts[s]), consts["max_dt"])
+        assert abs(dt - dts[s + 1]) <= 1e-9 * dts[s + 1]
+    got = eng.download_state([k for k in ("pos", "vel", "rho", "u", "S", "damage") if k in o])
+    for k, v in got.items():
+        assert_close(k, v, o[k], 1e-9, FLOOR)
+    # the switch must matter in this comparison: without it the state differs
+    plain = abi.setup_from_snapshot(i)
+    plain.cfg.flags &= ~abi.FLAG_BALSARA
+    ref = Engine(plain, len(i["mass"]))
+    ref.upload_state(i, STATE_IN + ("acc", "drho", "du", "dS", "ddamage"))
+    ref.set_last_timestep(consts["initial_dt"])
+    for s in range(len(dts) - 1):
+        ref.step_pc(float(dts[s]), consts["max_dt"])
+    other = ref.download_state(["vel"])["vel"]
+    assert np.abs(other[:, :3] - got["vel"][:, :3]).max() > 1e-6 * np.abs(got["vel"][:, :3]).max()
+    eng.close()
+    ref.close()
