@@ -331,8 +331,11 @@ def main():
     acc = eng.download_state(["acc"])["acc"][:n_owned, :3]
     h_lat = dom.h / workloads.BASALT["eta"]
     wgt = 0.5 + workloads._hash01(state["pos"][:n_owned, :3], 0.05 * h_lat, 77, 3)
+    mass = state["mass"][:n_owned]
     par = torch.tensor([float(st.pair_count)] + [float(np.sum(wgt * acc[:, k])) for k in range(3)] +
-                       [float(np.sum(np.abs(acc[:, k]))) for k in range(3)], dtype=torch.float64, device="cuda")
+                       [float(np.sum(np.abs(acc[:, k]))) for k in range(3)] +
+                       [float(np.sum(mass * acc[:, k])) for k in range(3)] + [float(np.sum(mass * np.abs(acc[:, k]))) for k in range(3)],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(par, op=dist.ReduceOp.SUM)
     par = par.tolist()
@@ -422,6 +425,9 @@ def main():
         "gpu_launches": int(launches),
         "parity": {"pair_count_global": int(round(par[0])), "acc_checksum": [par[1], par[2], par[3]],
                    "acc_abs_sum": [par[4], par[5], par[6]],
+                   "momentum_residual": [abs(par[7 + k]) / max(par[10 + k], 1e-300) for k in range(3)],
+                   "momentum_note": "|sum_i m_i a_i| / sum_i |m_i a_i| per axis over ALL particles: the pair forces are antisymmetric, so the "
+                                    "evaluation conserves linear momentum to rounding at any size (a size-independent check of the pair sums)",
                    "note": "after warm-up + 2 x steps PredictorCorrector steps; must agree across --gpus N (pair count exactly, checksum to "
                            "1e-10 of acc_abs_sum)"},
         "e2e": e2e,
@@ -443,6 +449,9 @@ def main():
         "phase_ms": {"note": "mean over %d steps run one call at a time after the timed region; %d of them rebuilt the lists" % (args.steps, phase_builds),
                      "grid_build": timings[0] / args.steps, "prologue_pack": timings[1] / args.steps,
                      "pair_stage": timings[2] / args.steps, "integrator_and_criteria": timings[3] / args.steps,
+                     "integrator_and_criteria_in_timed_region": max(step_s * 1e3 - (timings[0] + timings[1] + timings[2]) / args.steps, 0.0) if world == 1 else None,
+                     "integrator_note": "single calls run k_predict, k_correct, k_criteria; the timed region (sphgpu_run_pc) runs k_criteria and one fused "
+                                        "k_correct_predict per step (corrector of step s + predictor of step s+1: the state is read and written once)",
                      "pair_stage_parts": {"units_and_lane_order": pair_parts[0] / args.steps, "k_pair_lists": pair_parts[1] / args.steps,
                                           "k_pair_sum": pair_parts[2] / args.steps}},
     }

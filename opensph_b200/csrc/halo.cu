@@ -605,29 +605,58 @@ int sphgpu_run_pc(sphgpu_ctx* ctx, uint32_t steps, double dt, double max_dt, sph
     SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
     StepRecordDev* histDev = nullptr;
     SPH_CUDA_CHECK(cudaMalloc(&histDev, sizeof(StepRecordDev) * steps));
-    const StepStateDev init = { dt, ctx->lastDt, ctx->lastDtInit ? 1u : 0u, 0u };
+    const StepStateDev init = { dt, ctx->lastDt, ctx->lastDtInit ? 1u : 0u, 0u, dt };
     int rc = SPHGPU_OK;
     cudaError_t ce = cudaMemcpyAsync(ctx->d.stepState, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream);
     ctx->d.dtDev = &ctx->d.stepState->dt;
     ctx->launches = 0;
-    for (uint32_t s = 0; s < steps && rc == SPHGPU_OK && ce == cudaSuccess; ++s) {
-        if (s + 1 == steps) { // the events time the last step
-            ce = cudaEventRecord(ctx->ev[4], ctx->stream);
-            ctx->launches = 0;
+    // Only the derivative criterion reads what the corrector changes (values and clamped derivatives). Without it the
+    // criteria are evaluated BEFORE the corrector -- bit-identical results -- so the next time step is known when the
+    // corrector runs and the corrector of step s and the predictor of step s + 1 are one kernel (k_correct_predict).
+    const bool fused = (ctx->prm.criteria & SPHGPU_CRIT_DERIVATIVES) == 0u;
+    auto beginLastStep = [&]() { // the events time the last step
+        ce = cudaEventRecord(ctx->ev[4], ctx->stream);
+        ctx->launches = 0;
+    };
+    if (fused) {
+        if (steps == 1) {
+            beginLastStep();
         }
         rc = launchPredict(ctx, 0.);
+    }
+    for (uint32_t s = 0; s < steps && rc == SPHGPU_OK && ce == cudaSuccess; ++s) {
+        if (!fused) {
+            if (s + 1 == steps) {
+                beginLastStep();
+            }
+            rc = launchPredict(ctx, 0.);
+        }
         if (rc == SPHGPU_OK && h) {
             cudaEventRecord(ctx->ev[6], ctx->stream);
             rc = exchange(ctx); // ghosts carry the PREDICTED state
             cudaEventRecord(ctx->ev[7], ctx->stream);
         }
         if (rc == SPHGPU_OK) rc = enqueueIntegrate(ctx);
-        if (rc == SPHGPU_OK) rc = launchCorrect(ctx, 0.);
+        if (!fused) {
+            if (rc == SPHGPU_OK) rc = launchCorrect(ctx, 0.);
+        }
         if (rc == SPHGPU_OK) rc = launchCriteria(ctx);
         if (rc == SPHGPU_OK && h) {
             rc = allReduceTimestep(ctx, h, api);
         }
         if (rc == SPHGPU_OK) rc = launchFinishTimestep(ctx, max_dt, histDev, s);
+        if (fused && rc == SPHGPU_OK) {
+            if (s + 1 < steps) {
+                if (s + 2 == steps) {
+                    beginLastStep(); // (the timed step then holds the corrector of the step before instead of its own)
+                }
+                rc = launchCorrectPredict(ctx);
+            } else {
+                ctx->d.dtDev = &ctx->d.stepState->dtPrev; // k_finish_timestep has already moved on to the next step
+                rc = launchCorrect(ctx, 0.);
+                ctx->d.dtDev = &ctx->d.stepState->dt;
+            }
+        }
     }
     ctx->d.dtDev = nullptr;
     if (ce != cudaSuccess) {

@@ -53,12 +53,18 @@ __device__ __forceinline__ float4 gridRelative(const GridDev& g, double x, doubl
     return make_float4((float)(x - g.lo[0]), (float)(y - g.lo[1]), (float)(z - g.lo[2]), (float)h);
 }
 
+// 64 registers, 4 CTAs per SM: the kernel waits on its loads (ncu: long scoreboard), occupancy is what hides them. Measured
+// at 10.6 M particles: 1.11 ms with 3 CTAs, 1.01 ms with 4, 1.06 ms with 5 (spills); hoisting every load above the first
+// store made it slower (1.10 ms with 4 CTAs).
+#ifndef PROLOGUE_MIN_CTAS
+#define PROLOGUE_MIN_CTAS 4
+#endif
 // ---- prologue: EoS + rheology + damage growth, and packing of the sorted neighbour-input planes -----------
 // One thread per SORTED position t; slot i = order[t]. Reads the slot state once, writes p, cs, reduce, yielded S
 // and dD/dt back to the slot planes and the neighbour inputs (with p/rho^2, S/rho^2, m/rho precomputed) to the
 // sorted planes.
 template <bool SOLID>
-__global__ void __launch_bounds__(256) k_prologue_pack(DevicePointers d, uint32_t nActive, uint32_t nOwned, bool hasReduce,
+__global__ void __launch_bounds__(256, PROLOGUE_MIN_CTAS) k_prologue_pack(DevicePointers d, uint32_t nActive, uint32_t nOwned, bool hasReduce,
     bool hasDamage) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nActive) {

@@ -109,6 +109,7 @@ struct StepStateDev { // time-step bookkeeping of sphgpu_run_pc (MultiCriterion:
     double dt;          // step the next predict / correct will use
     double lastDt;      // MultiCriterion::lastStep
     uint32_t lastDtInit, pad;
+    double dtPrev;      // the step before `dt`: what the corrector half of k_correct_predict uses
 };
 
 struct StepRecordDev {
@@ -228,6 +229,7 @@ int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, u
 // stepping.cu
 int launchPredict(sphgpu_ctx* ctx, double dt);
 int launchCorrect(sphgpu_ctx* ctx, double dt);
+int launchCorrectPredict(sphgpu_ctx* ctx); // corrector of the step that ends + predictor of the next one (sphgpu_run_pc)
 int launchEuler(sphgpu_ctx* ctx, double dt);
 int launchCriteria(sphgpu_ctx* ctx);
 int measureFp64Peak(sphgpu_ctx* ctx, double* fmaPerSecond);

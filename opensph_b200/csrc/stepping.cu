@@ -19,6 +19,12 @@ __device__ __forceinline__ void clampFirstOrder(const MaterialDev& m, bool hasDa
     }
 }
 
+/// v dt + a dt^2/2 of the second-order predictor with the contraction spelled out: k_predict and k_correct_predict must
+/// round alike (left to the compiler, the choice of which product joins the FMA differed between the two kernels).
+__device__ __forceinline__ double secondOrderStep(double v, double a, double dt, double dt2) {
+    return fma(v, dt, __dmul_rn(a, dt2));
+}
+
 // makePredictions (TimeStepping.cpp:286-300) + storage->swap(predictions) + zeroHighestDerivatives (:331-334).
 // The derivative planes are not zeroed: integrate() overwrites every one of them.
 template <bool SOLID>
@@ -32,10 +38,10 @@ __global__ void __launch_bounds__(256) k_predict(DevicePointers d, uint32_t n, d
     const double dt2 = 0.5 * dt * dt;
     const double ax = d.f[F_AX][i], ay = d.f[F_AY][i], az = d.f[F_AZ][i];
     const double vx = d.f[F_VX][i], vy = d.f[F_VY][i], vz = d.f[F_VZ][i], vh = d.f[F_VH][i];
-    d.f[F_X][i] += vx * dt + ax * dt2;
-    d.f[F_Y][i] += vy * dt + ay * dt2;
-    d.f[F_Z][i] += vz * dt + az * dt2;
-    d.f[F_H][i] += vh * dt + 0. * dt2;
+    d.f[F_X][i] += secondOrderStep(vx, ax, dt, dt2);
+    d.f[F_Y][i] += secondOrderStep(vy, ay, dt, dt2);
+    d.f[F_Z][i] += secondOrderStep(vz, az, dt, dt2);
+    d.f[F_H][i] += secondOrderStep(vh, 0., dt, dt2);
     d.f[F_VX][i] = vx + ax * dt;
     d.f[F_VY][i] = vy + ay * dt;
     d.f[F_VZ][i] = vz + az * dt;
@@ -117,6 +123,87 @@ __global__ void __launch_bounds__(256) k_correct(DevicePointers d, uint32_t n, d
     }
 }
 
+// makeCorrections of the step that ends (time step StepStateDev::dtPrev) followed by makePredictions of the next one
+// (StepStateDev::dt) in one pass: the bodies of k_correct and k_predict back to back on registers, so the state is read and
+// written once instead of twice (512 instead of 824 bytes per solid particle). sphgpu_run_pc uses it between two steps when
+// no time-step criterion reads what the corrector changes (everything but the derivative criterion), because then the
+// criteria can be evaluated before the corrector and the next step is known when this kernel starts.
+#ifndef INTEG_MIN_CTAS
+#define INTEG_MIN_CTAS 4
+#endif
+template <bool SOLID>
+__global__ void __launch_bounds__(256, INTEG_MIN_CTAS) k_correct_predict(DevicePointers d, uint32_t n, bool hasDamage) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const MaterialDev& m = c_mats[d.u[U_MATID][i]];
+    const bool dmg = hasDamage && m.fracture != SPHGPU_FRACTURE_NONE;
+    const double dtc = d.stepState->dtPrev, dtp = d.stepState->dt; // corrector / predictor time step
+    const double dtc2 = 0.5 * dtc * dtc, dtp2 = 0.5 * dtp * dtp;
+    // Three groups, each loaded, advanced and stored before the next one starts (a store ends what the compiler may hoist,
+    // so the groups bound the number of live registers): positions and velocities, first-order scalars, stress.
+    {
+        const double a = 1. / 3., b = 0.5;
+        const double ax = d.f[F_AX][i], ay = d.f[F_AY][i], az = d.f[F_AZ][i];
+        const double ex = d.f[F_AXP][i] - ax, ey = d.f[F_AYP][i] - ay, ez = d.f[F_AZP][i] - az;
+        double x = d.f[F_X][i], y = d.f[F_Y][i], z = d.f[F_Z][i];
+        double vx = d.f[F_VX][i], vy = d.f[F_VY][i], vz = d.f[F_VZ][i];
+        const double vh = d.f[F_VH][i], h = d.f[F_H][i];
+        x -= a * ex * dtc2; // corrector, as k_correct
+        y -= a * ey * dtc2;
+        z -= a * ez * dtc2;
+        vx -= b * ex * dtc;
+        vy -= b * ey * dtc;
+        vz -= b * ez * dtc;
+        x += secondOrderStep(vx, ax, dtp, dtp2); // predictor, as k_predict
+        y += secondOrderStep(vy, ay, dtp, dtp2);
+        z += secondOrderStep(vz, az, dtp, dtp2);
+        d.f[F_X][i] = x;
+        d.f[F_Y][i] = y;
+        d.f[F_Z][i] = z;
+        d.f[F_H][i] = h + secondOrderStep(vh, 0., dtp, dtp2);
+        d.f[F_VX][i] = vx + ax * dtp;
+        d.f[F_VY][i] = vy + ay * dtp;
+        d.f[F_VZ][i] = vz + az * dtp;
+        d.f[F_AXP][i] = ax;
+        d.f[F_AYP][i] = ay;
+        d.f[F_AZP][i] = az;
+    }
+    {
+        double rho = d.f[F_RHO][i], drho = d.f[F_DRHO][i], u = d.f[F_U][i], du = d.f[F_DU][i];
+        double D = dmg ? d.f[F_D][i] : 0., dD = dmg ? d.f[F_DD][i] : 0.;
+        rho -= 0.5 * (d.f[F_DRHOP][i] - drho) * dtc;
+        u -= 0.5 * (d.f[F_DUP][i] - du) * dtc;
+        if (dmg) {
+            D -= 0.5 * (d.f[F_DDP][i] - dD) * dtc;
+        }
+        clampFirstOrder(m, dmg, rho, drho, u, du, D, dD);
+        rho += drho * dtp; // (the clamped derivatives of the corrector are the ones the predictor extrapolates with)
+        u += du * dtp;
+        D += dD * dtp;
+        clampFirstOrder(m, dmg, rho, drho, u, du, D, dD);
+        d.f[F_RHO][i] = rho;
+        d.f[F_U][i] = u;
+        d.f[F_DRHOP][i] = drho;
+        d.f[F_DUP][i] = du;
+        if (dmg) {
+            d.f[F_D][i] = D;
+            d.f[F_DDP][i] = dD;
+        }
+    }
+    if (SOLID) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double dS = d.f[F_DS0 + k][i];
+            double S = d.f[F_S0 + k][i];
+            S -= 0.5 * (d.f[F_DSP0 + k][i] - dS) * dtc;
+            d.f[F_S0 + k][i] = S + dS * dtp;
+            d.f[F_DSP0 + k][i] = dS;
+        }
+    }
+}
+
 // EulerExplicit::stepParticles after solver.integrate (TimeStepping.cpp:243-264).
 template <bool SOLID>
 __global__ void __launch_bounds__(256) k_euler(DevicePointers d, uint32_t n, double dt, bool hasDamage) {
@@ -178,6 +265,7 @@ template <bool SOLID>
 __global__ void __launch_bounds__(256) k_criteria(DevicePointers d, uint32_t n, bool hasDamage) {
     double mins[4] = { INFTY_REF, INFTY_REF, INFTY_REF, INFTY_REF };
     const uint32_t crit = c_prm.criteria;
+#pragma unroll 4 // (no stores in the loop: the loads of four particles are in flight together)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const MaterialDev& m = c_mats[d.u[U_MATID][i]];
         const double h = d.f[F_H][i];
@@ -323,6 +411,7 @@ __global__ void k_finish_timestep(DevicePointers d, double maxDt, double maxChan
         }
         st.lastDt = minStep;
     }
+    st.dtPrev = st.dt;
     st.dt = minStep;
     history[index].dt = minStep;
     history[index].criterion = minId;
@@ -365,6 +454,23 @@ int launchCorrect(sphgpu_ctx* ctx, double dt) {
     }
     const uint32_t blocks = (n + 255) / 256;
     SPH_DISPATCH_SOLID(k_correct, ctx->d, n, dt, ctx->hasDamage);
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
+int launchCorrectPredict(sphgpu_ctx* ctx) {
+    {
+        const int rcConst = ensureConstants(ctx);
+        if (rcConst != SPHGPU_OK) {
+            return rcConst;
+        }
+    }
+    const uint32_t n = ctx->n;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    const uint32_t blocks = (n + 255) / 256;
+    SPH_DISPATCH_SOLID(k_correct_predict, ctx->d, n, ctx->hasDamage);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
 }

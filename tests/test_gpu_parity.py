@@ -313,6 +313,32 @@ def test_giant_smoothing_length_costs_little_at_bench_scale():
     assert times[True] <= 2.0 * times[False], times
 
 
+def test_conservation_at_full_bench_size():
+    """Size-independent property at BASELINE's headline size (10.6 M particles, the bench workload after a few moving
+    PredictorCorrector steps): the pair forces are antisymmetric (symmetrised h, p_i/rho_i^2 + p_j/rho_j^2 + Pi_ij, the
+    undamaged-pair filter is symmetric), so sum_i m_i a_i vanishes to rounding; the neighbour relation is symmetric, so the
+    sum of the neighbour counts is even and equals the pair count of the statistics. A candidate dropped by the u16 list
+    indices, the 32-bit cell ranges or the list pool at this size would break either."""
+    from opensph_b200 import workloads
+    state = workloads.basalt_sphere_state(10_000_000)
+    n = len(state["mass"])
+    assert n > 10_000_000
+    setup = workloads.make_setup(n)
+    names = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "damage", "ddamage", "reduce",
+             "eps_min", "m_zero", "growth", "n_flaws", "flag")
+    eng = Engine(setup, n)
+    eng.upload_state(state, names)
+    _, _, st = eng.run_pc(4, 0.01, 10.0)  # the lists of step 1 are reused with moved particles
+    got = eng.download_state(["acc", "ncnt"])
+    eng.close()
+    total = int(got["ncnt"].astype(np.int64).sum())
+    assert total == st.pair_count and total % 2 == 0
+    assert 60.0 < total / n < 70.0
+    force = state["mass"][:, None] * got["acc"][:, :3]
+    residual = np.abs(force.sum(axis=0)) / np.abs(force).sum(axis=0)
+    assert np.all(residual < 1e-12), residual
+
+
 def test_batched_steps_equal_single_steps(lut):
     """sphgpu_run_pc (time step chosen on the device, one host synchronisation for the batch) against the same number
     of sphgpu_step_pc calls with the host feeding the time step back: identical dt sequence and state."""
