@@ -279,6 +279,48 @@ SPHGPU_API int sphgpu_set_last_timestep(sphgpu_ctx* ctx, double dt);
  * predict(dt) -> integrate -> correct(dt) -> criteria. No host<->device traffic except the returned scalars. */
 SPHGPU_API int sphgpu_step_pc(sphgpu_ctx* ctx, double t, double dt, double max_dt, sphgpu_stats* stats, sphgpu_timestep* out);
 
+/* ---- self-gravity --------------------------------------------------------------- */
+
+/* Replaces the IGravity object GravitySolver<TSphSolver> owns (core/sph/solvers/GravitySolver.cpp:18-30,64-99; built by
+ * Factory::getGravity, core/system/Factory.cpp:361-413): BarnesHut (core/gravity/BarnesHut.cpp:50-501) with the opening
+ * angle GRAVITY_OPENING_ANGLE and the multipole order GRAVITY_MULTIPOLE_ORDER, or -- opening_angle <= 0 --
+ * BruteForceGravity (core/gravity/BruteForceGravity.h:38-45). Close pairs use the softening kernel GravityLutKernel
+ * (core/sph/kernel/GravityKernel.h:58-86) with symmetrised smoothing lengths: lut_grad holds the lut_entries + 1 node
+ * values of its gradient table over q^2 in [0, kernel_radius^2] (Kernel.h:85-101; the last one is the Newtonian value at
+ * the edge); kernel_radius = 0 selects point particles (GravityKernelEnum::POINT_PARTICLES). leaf_size is
+ * FINDER_LEAF_SIZE (0 = the reference's default 25): nodes of at most that many particles are summed exactly when opened.
+ * Once configured, sphgpu_integrate / sphgpu_step_pc / sphgpu_run_pc add the gravitational accelerations to the SPH
+ * ones like GravitySolver::loop does. The device tree is a binary radix tree over Morton-sorted particles, not the
+ * reference's k-d tree: with opening_angle <= 0 the result equals the reference's to rounding, with an opening angle it
+ * agrees within the error of the multipole approximation (the reference's own BarnesHut tests compare against
+ * BruteForceGravity the same way, core/gravity/test/BarnesHut.cpp). Attractors (Storage::getAttractors) are not
+ * handled. Not available on decomposed runs. cfg == NULL switches gravity off. */
+typedef struct sphgpu_gravity {
+    double opening_angle;
+    int multipole_order;   /* 0, 2 or 3 (MultipoleOrder, core/gravity/Moments.h:307-312) */
+    uint32_t leaf_size;
+    double constant;       /* GRAVITY_CONSTANT */
+    double kernel_radius;
+    const double* lut_grad;
+    uint32_t lut_entries;
+    uint32_t reserved;
+} sphgpu_gravity;
+
+typedef struct sphgpu_gravity_stats {
+    uint64_t approximated; /* node x target-group interactions evaluated by multipoles (GRAVITY_NODES_APPROX) */
+    uint64_t exact;        /* particle ranges x target groups summed exactly (GRAVITY_NODES_EXACT) */
+    uint32_t nodes;        /* internal nodes of the tree (GRAVITY_NODE_COUNT) */
+    uint32_t groups;       /* target groups (the leaves the walk is run for) */
+    double gpu_ms;         /* device time of the last evaluation: keys + sort + tree + moments + walk */
+} sphgpu_gravity_stats;
+
+SPHGPU_API int sphgpu_gravity_configure(sphgpu_ctx* ctx, const sphgpu_gravity* cfg);
+/* IGravity::build + evalSelfGravity (BarnesHut.cpp:50-99) on the particles as they are on the device. accumulate != 0
+ * adds to the acceleration planes, 0 overwrites them (evalSelfGravity on a zeroed buffer). Synchronises. */
+SPHGPU_API int sphgpu_gravity_eval(sphgpu_ctx* ctx, int accumulate, sphgpu_gravity_stats* stats);
+/* Statistics of the last evaluation, e.g. the one inside sphgpu_integrate. Synchronises. */
+SPHGPU_API int sphgpu_gravity_last_stats(sphgpu_ctx* ctx, sphgpu_gravity_stats* stats);
+
 /* ---- inspection (tests) --------------------------------------------------------------------------------- */
 
 /* Neighbour lists exactly as AsymmetricSolver::loop selects them (AsymmetricSolver.cpp:174-199), CSR:

@@ -97,6 +97,41 @@ class TimeStep(C.Structure):
     _fields_ = [("dt", C.c_double), ("criterion", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
+class Gravity(C.Structure):
+    _fields_ = [
+        ("opening_angle", C.c_double), ("multipole_order", C.c_int), ("leaf_size", C.c_uint32),
+        ("constant", C.c_double), ("kernel_radius", C.c_double), ("lut_grad", C.POINTER(C.c_double)),
+        ("lut_entries", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class GravityStats(C.Structure):
+    _fields_ = [
+        ("approximated", C.c_uint64), ("exact", C.c_uint64), ("nodes", C.c_uint32), ("groups", C.c_uint32),
+        ("gpu_ms", C.c_double),
+    ]
+
+
+GRAVITY_CONSTANT = 6.67408e-11  # Constants::gravity (core/physics/Constants.h)
+
+
+def gravity_table_cubic_spline(entries: int = 40000) -> np.ndarray:
+    """Gradient table of GravityLutKernel for the cubic spline, as LutKernel<3>'s constructor fills it
+    (core/sph/kernel/Kernel.h:85-101) from GravityKernel<CubicSpline<3>>::gradImpl (core/sph/kernel/GravityKernel.h:108-121):
+    entries + 1 node values over q^2 in [0, 4]."""
+    q_sqr = np.arange(entries + 1, dtype=np.float64) / (np.float64(entries) * 0.25)
+    q = np.sqrt(q_sqr)
+    out = np.empty(entries + 1)
+    inner = q < 1.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out[inner] = (4.0 / 3.0 * q[inner] - 6.0 / 5.0 * q[inner] ** 3 + 0.5 * q_sqr[inner] ** 2) / q[inner]
+        o = ~inner
+        out[o] = (8.0 / 3.0 * q[o] - 3.0 * q_sqr[o] + 6.0 / 5.0 * q[o] ** 3 - 1.0 / 6.0 * q_sqr[o] ** 2
+                  - 1.0 / (15.0 * q_sqr[o])) / q[o]
+    out[0] = 4.0 / 3.0
+    return out
+
+
 class RunSetup:
     """Config + materials + the arrays they point into (kept alive together)."""
 

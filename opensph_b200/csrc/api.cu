@@ -286,6 +286,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaDeviceSynchronize();
     forgetConstants(ctx);
     destroyHalo(ctx);
+    destroyGravity(ctx);
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc); cudaFree(ctx->d.unitAux); cudaFree(ctx->d.unitLane); cudaFree(ctx->d.unitList);
@@ -556,6 +557,8 @@ int enqueueIntegrate(sphgpu_ctx* ctx) {
     if ((rc = launchProloguePack(ctx)) != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[2], ctx->stream));
     if ((rc = launchPair(ctx)) != SPHGPU_OK) return rc;
+    // GravitySolver::loop (GravitySolver.cpp:64-99): the gravitational accelerations join the SPH ones
+    if (ctx->gravity != nullptr && (rc = launchGravity(ctx, 1)) != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
     return SPHGPU_OK;
 }

@@ -7,3 +7,4 @@
 #include "stepping.cu"
 #include "transfer.cu"
 #include "halo.cu"
+#include "gravity.cu"

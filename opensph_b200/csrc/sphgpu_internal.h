@@ -200,6 +200,8 @@ struct sphgpu_ctx {
     uint32_t launches = 0;
     bool stateUploaded = false;
     void* halo = nullptr;      // sph::HaloState (halo.cu): NCCL communicator + exchange buffers
+    void* gravity = nullptr;   // sph::GravState (gravity.cu): self-gravity, when configured
+    double gravityConstant = 0.;
 };
 
 namespace sph {
@@ -245,5 +247,8 @@ int collectStats(sphgpu_ctx* ctx, sphgpu_stats* stats, cudaEvent_t begin, cudaEv
 int finishTimestep(sphgpu_ctx* ctx, double max_dt, sphgpu_timestep* out);
 void destroyHalo(sphgpu_ctx* ctx);
 void invalidateHalo(sphgpu_ctx* ctx); // the exchange refuses to run until sphgpu_halo_configure is called again
+// gravity.cu
+int launchGravity(sphgpu_ctx* ctx, int accumulate); // no-op unless self-gravity is configured
+void destroyGravity(sphgpu_ctx* ctx);
 
 } // namespace sph

@@ -218,6 +218,34 @@ class Engine:
         _check(self.lib.sphgpu_integrate(self._ctx, C.c_double(t), C.byref(st)))
         return st
 
+    # -- self-gravity ------------------------------------------------------------------------------------------
+    def gravity_configure(self, opening_angle: float = 0.5, order: int = 3, constant: float = abi.GRAVITY_CONSTANT,
+                          lut_grad: Optional[np.ndarray] = None, kernel_radius: float = 0.0, leaf_size: int = 0) -> None:
+        """Switches device self-gravity on (Factory::getGravity's settings); lut_grad=None selects point particles."""
+        cfg = abi.Gravity()
+        cfg.opening_angle, cfg.multipole_order, cfg.leaf_size, cfg.constant = opening_angle, order, leaf_size, constant
+        self._grav_lut = None
+        if lut_grad is not None:
+            self._grav_lut = np.ascontiguousarray(lut_grad, dtype=np.float64)
+            cfg.lut_grad = self._grav_lut.ctypes.data_as(C.POINTER(C.c_double))
+            cfg.lut_entries = len(self._grav_lut) - 1
+            cfg.kernel_radius = kernel_radius
+        _check(self.lib.sphgpu_gravity_configure(self._ctx, C.byref(cfg)))
+
+    def gravity_off(self) -> None:
+        _check(self.lib.sphgpu_gravity_configure(self._ctx, None))
+
+    def gravity_eval(self, accumulate: bool = False) -> abi.GravityStats:
+        """IGravity::build + evalSelfGravity on the device state; overwrites (or adds to) the accelerations."""
+        st = abi.GravityStats()
+        _check(self.lib.sphgpu_gravity_eval(self._ctx, C.c_int(1 if accumulate else 0), C.byref(st)))
+        return st
+
+    def gravity_last_stats(self) -> abi.GravityStats:
+        st = abi.GravityStats()
+        _check(self.lib.sphgpu_gravity_last_stats(self._ctx, C.byref(st)))
+        return st
+
     def predict(self, dt: float) -> None:
         _check(self.lib.sphgpu_step_predict(self._ctx, C.c_double(dt)))
 

@@ -15,12 +15,23 @@
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
+//   sph_ref gravity  --config C --n N [--jitter SEED] [--gravity bh|brute] [--theta X] [--order 0|2|3] [--leaf L] [--point]
+//                    [--no-lut] [--threads T] --out OUT.snap
+//       builds the Storage of config C and evaluates the reference's self-gravity on it: Factory::getGravity
+//       (core/system/Factory.cpp:361-413) -> IGravity::build + evalSelfGravity (core/gravity/BarnesHut.cpp:50-99,
+//       core/gravity/BruteForceGravity.h:38-45) on a zeroed acceleration buffer. OUT.snap holds pos, mass, grav_acc, the
+//       softening kernel's gradient table (grav_lut), grav_params {theta, order, G, kernel radius, leaf size, seconds}
+//       and, for Barnes-Hut, the moments of the root node (BarnesHut::getMoments) with the accelerations
+//       evaluateGravity (core/gravity/Moments.h:315-340) derives from them at a few distant probe points.
 //   sph_ref bench    --config C --n N --steps K --warmup W [--threads T] [--finder kd|grid] [--integrate-only] [--fixed-dt X]
 //       prints one JSON line with seconds per step of the reference CPU path.
 //
 // Snapshot format "SPHSNAP1": u32 count, then per array {char name[32]; u32 dtype(0=f64,1=u32); u32 ncomp;
 // u64 rows; payload}. All particle arrays are in the reference's own particle order.
 #include "Sph.h"
+#include "gravity/BarnesHut.h"
+#include "gravity/Moments.h"
+#include "sph/kernel/GravityKernel.h"
 #include "tests/Setup.h"
 #include <chrono>
 #include <cstdio>
@@ -567,6 +578,100 @@ int main(int argc, char** argv) {
             w.write(args.str("out", "out.snap"));
             std::cout << "{\"particles\": " << N << ", \"materials\": " << storage->getMaterialCnt() << "}"
                       << std::endl;
+        } else if (cmd == "gravity") {
+            const bool brute = args.str("gravity", "bh") == "brute";
+            const double theta = atof(args.str("theta", "0.5").c_str());
+            const int order = int(args.num("order", 3));
+            settings.set(RunSettingsId::GRAVITY_SOLVER, brute ? GravityEnum::BRUTE_FORCE : GravityEnum::BARNES_HUT)
+                .set(RunSettingsId::GRAVITY_OPENING_ANGLE, Float(theta))
+                .set(RunSettingsId::GRAVITY_MULTIPOLE_ORDER, order)
+                .set(RunSettingsId::GRAVITY_KERNEL,
+                    args.has("point") ? GravityKernelEnum::POINT_PARTICLES : GravityKernelEnum::SPH_KERNEL);
+            if (args.has("leaf")) {
+                settings.set(RunSettingsId::FINDER_LEAF_SIZE, int(args.num("leaf", 25)));
+            }
+            AutoPtr<IGravity> gravity = Factory::getGravity(settings);
+            Array<Vector> dv(N);
+            dv.fill(Vector(0._f));
+            Statistics stats;
+            const double t0 = now();
+            gravity->build(*scheduler, *storage);
+            gravity->evalSelfGravity(*scheduler, dv, stats);
+            const double seconds = now() - t0;
+            SnapWriter w;
+            ArrayView<const Vector> r = storage->getValue<Vector>(QuantityId::POSITION);
+            ArrayView<const Float> m = storage->getValue<Float>(QuantityId::MASS);
+            w.addF64("pos", vec4(r), 4);
+            w.addF64("mass", scal(m), 1);
+            w.addF64("grav_acc", vec4(dv), 4);
+            const Float G = settings.get<Float>(RunSettingsId::GRAVITY_CONSTANT);
+            double radius = 0.;
+            if (!args.has("point")) {
+                radius = GravityKernel<CubicSpline<3>>().radius();
+            }
+            if (!args.has("point") && !args.has("no-lut")) {
+                // the table GravityLutKernel holds: LutKernel<3> built from the exact gravity kernel (GravityKernel.h:40-50,
+                // Kernel.h:85-101); sampled at its own nodes, where the interpolation returns the entries themselves
+                GravityKernel<CubicSpline<3>> exact;
+                LutKernel<3> lk(exact);
+                const Size entries = 40000;
+                radius = lk.radius();
+                const Float qSqrToIdx = Float(entries) / sqr(lk.radius());
+                std::vector<double> lut(entries + 1);
+                for (Size i = 0; i <= entries; ++i) {
+                    const Float qSqr = Float(i) / qSqrToIdx;
+                    lut[i] = (i < entries) ? lk.gradImpl(qSqr) : exact.gradImpl(qSqr);
+                }
+                w.addF64("grav_lut", lut, 1);
+            }
+            w.addF64("grav_params",
+                { theta, double(order), double(G), radius, double(settings.get<int>(RunSettingsId::FINDER_LEAF_SIZE)), seconds,
+                    brute ? 1. : 0. },
+                1);
+            if (!brute) {
+                const BarnesHut* bh = dynamic_cast<const BarnesHut*>(&*gravity);
+                if (bh) {
+                    const MultipoleExpansion<3> ms = bh->getMoments(); // divided by G
+                    const TracelessMultipole<2>& q2 = ms.order<2>();
+                    const TracelessMultipole<3>& q3 = ms.order<3>();
+                    std::vector<double> mom = { ms.order<0>().value(), q2.value<0, 0>(), q2.value<1, 1>(), q2.value<0, 1>(),
+                        q2.value<0, 2>(), q2.value<1, 2>(), q3.value<0, 0, 0>(), q3.value<0, 0, 1>(), q3.value<0, 0, 2>(),
+                        q3.value<0, 1, 1>(), q3.value<0, 1, 2>(), q3.value<1, 1, 1>(), q3.value<1, 1, 2>() };
+                    w.addF64("root_moments", mom, 1);
+                    // centre of mass as BarnesHut::buildLeaf / buildInner define it (mass-weighted mean)
+                    Vector com(0._f);
+                    Float mtot = 0._f;
+                    for (Size i = 0; i < N; ++i) {
+                        com += m[i] * r[i];
+                        mtot += m[i];
+                    }
+                    com /= mtot;
+                    Float rmax = 0._f;
+                    for (Size i = 0; i < N; ++i) {
+                        rmax = max(rmax, getLength(r[i] - com));
+                    }
+                    std::vector<double> probes, field;
+                    const Vector dirs[4] = { Vector(1._f, 0.2_f, -0.3_f), Vector(-0.5_f, 1._f, 0.4_f), Vector(0.1_f, -0.7_f, 1._f),
+                        Vector(-1._f, -1._f, -1._f) };
+                    const MultipoleExpansion<3> msG = ms.multiply(G);
+                    for (int o : { 0, 2, 3 }) {
+                        for (int k = 0; k < 4; ++k) {
+                            const Vector dr = dirs[k] / getLength(dirs[k]) * (3._f + k) * rmax;
+                            const Vector a = evaluateGravity(dr, msG, MultipoleOrder(o));
+                            probes.insert(probes.end(), { com[X] + dr[X], com[Y] + dr[Y], com[Z] + dr[Z], double(o) });
+                            field.insert(field.end(), { a[X], a[Y], a[Z] });
+                        }
+                    }
+                    w.addF64("probe_pos", probes, 4);
+                    w.addF64("probe_acc", field, 3);
+                }
+                std::vector<double> st = { double(stats.get<int>(StatisticsId::GRAVITY_NODES_APPROX)),
+                    double(stats.get<int>(StatisticsId::GRAVITY_NODES_EXACT)), double(stats.get<int>(StatisticsId::GRAVITY_NODE_COUNT)) };
+                w.addF64("grav_stats", st, 1);
+            }
+            w.write(args.str("out", "gravity.snap"));
+            printf("{\"particles\": %u, \"gravity\": \"%s\", \"theta\": %g, \"order\": %d, \"seconds\": %.4f, \"threads\": %d}\n", N,
+                brute ? "brute" : "bh", theta, order, seconds, int(scheduler->getThreadCnt()));
         } else if (cmd == "bench") {
             const long steps = args.num("steps", 3), warmup = args.num("warmup", 1);
             Statistics stats;

@@ -956,3 +956,191 @@ double orc_timestep(const orc_state* s, const sphgpu_config* cfg, const sphgpu_m
     }
     return minStep;
 }
+
+/* ---- self-gravity ----------------------------------------------------------------------------------------------- */
+
+/* GravityKernel<CubicSpline<3>>::gradImpl, core/sph/kernel/GravityKernel.h:108-121. */
+static double gravity_cubic_grad(double qSqr) {
+    const double q = sqrt(qSqr);
+    if (q == 0.) {
+        return 4. / 3.;
+    } else if (q < 1.) {
+        return 1. / q * (4. / 3. * q - 6. / 5. * q * q * q + 1. / 2. * qSqr * qSqr);
+    }
+    return 1. / q * (8. / 3. * q - 3. * qSqr + 6. / 5. * q * q * q - 1. / 6. * qSqr * qSqr - 1. / (15. * qSqr));
+}
+
+/* LutKernel<3>::LutKernel(GravityKernel<CubicSpline<3>>), Kernel.h:85-101: NEntries + 1 node values over q^2. */
+void orc_build_gravity_lut(double* grad, uint32_t entries) {
+    const double radInvSqr = 1. / (2. * 2.);
+    const double qSqrToIdx = (double)entries * radInvSqr;
+    for (uint32_t i = 0; i <= entries; ++i) {
+        grad[i] = gravity_cubic_grad((double)i / qSqrToIdx);
+    }
+}
+
+/* GravityLutKernel::grad(r, h), GravityKernel.h:72-86, with LutKernel<3>::gradImpl (Kernel.h:129-144). */
+static void gravity_kernel_grad(const double r[3], double h, const double* lut, uint32_t entries, double radius, double out[3]) {
+    const double hInv = 1. / h;
+    const double sx = r[0] * hInv, sy = r[1] * hInv, sz = r[2] * hInv;
+    const double qSqr = sx * sx + sy * sy + sz * sz;
+    if (qSqr + ORC_EPS >= sqr(radius)) {
+        const double len = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        const double len3 = len * len * len;
+        out[0] = r[0] / len3;
+        out[1] = r[1] / len3;
+        out[2] = r[2] / len3;
+    } else {
+        const double floatIdx = (double)entries / sqr(radius) * qSqr;
+        const uint32_t idx1 = (uint32_t)floatIdx;
+        const double ratio = floatIdx - (double)idx1;
+        const double grad = lut[idx1] * (1. - ratio) + lut[idx1 + 1] * ratio;
+        const double f = hInv * hInv * hInv;
+        out[0] = f * r[0] * grad;
+        out[1] = f * r[1] * grad;
+        out[2] = f * r[2] * grad;
+    }
+}
+
+/* BruteForceGravity::evalImpl, BruteForceGravity.h:103-121: a_i = sum_{j != i} G m_j grad(r_j, r_i), the kernel taken
+ * at the mean smoothing length (SymmetrizeSmoothingLengths::grad, Kernel.h:640-643). */
+void orc_gravity_brute(uint32_t n, const double* pos, const double* mass, double G, const double* lut_grad, uint32_t entries,
+    double radius, double* acc) {
+#pragma omp parallel for schedule(static)
+    for (uint32_t i = 0; i < n; ++i) {
+        double a[3] = { 0., 0., 0. };
+        for (uint32_t j = 0; j < n; ++j) {
+            if (j == i) {
+                continue;
+            }
+            const double r[3] = { pos[4 * j] - pos[4 * i], pos[4 * j + 1] - pos[4 * i + 1], pos[4 * j + 2] - pos[4 * i + 2] };
+            double g[3];
+            gravity_kernel_grad(r, 0.5 * (pos[4 * j + 3] + pos[4 * i + 3]), lut_grad, entries, radius, g);
+            a[0] += mass[j] * g[0];
+            a[1] += mass[j] * g[1];
+            a[2] += mass[j] * g[2];
+        }
+        acc[3 * i] = G * a[0];
+        acc[3 * i + 1] = G * a[1];
+        acc[3 * i + 2] = G * a[2];
+    }
+}
+
+/* BarnesHut::buildLeaf, BarnesHut.cpp:393-431: com = sum m r / sum m; M2, M3 = computeMultipole<2>, <3> about com
+ * (Moments.h:166-179); reduced (traceless) multipoles computeReducedMultipole (Moments.h:92-111):
+ * Q2 = M2 - delta tr(M2) / 3, Q3_ijk = M3_ijk - (delta_ij T_k + delta_ik T_j + delta_jk T_i) / 5, T_k = M3_llk. */
+void orc_gravity_moments(uint32_t n, const double* pos, const double* mass, double* com, double* mom) {
+    double c[3] = { 0., 0., 0. }, m0 = 0.;
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            c[k] += mass[i] * pos[4 * i + k];
+        }
+        m0 += mass[i];
+    }
+    for (int k = 0; k < 3; ++k) {
+        c[k] /= m0;
+        com[k] = c[k];
+    }
+    double M2[3][3], M3[3][3][3];
+    memset(M2, 0, sizeof(M2));
+    memset(M3, 0, sizeof(M3));
+    for (uint32_t i = 0; i < n; ++i) {
+        const double d[3] = { pos[4 * i] - c[0], pos[4 * i + 1] - c[1], pos[4 * i + 2] - c[2] };
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) {
+                M2[a][b] += d[a] * d[b] * mass[i];
+                for (int e = 0; e < 3; ++e) {
+                    M3[a][b][e] += d[a] * d[b] * d[e] * mass[i];
+                }
+            }
+        }
+    }
+    const double tr = M2[0][0] + M2[1][1] + M2[2][2];
+    double T[3];
+    for (int k = 0; k < 3; ++k) {
+        T[k] = M3[0][0][k] + M3[1][1][k] + M3[2][2][k];
+    }
+    double Q2[3][3], Q3[3][3][3];
+    for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) {
+            Q2[a][b] = M2[a][b] - (a == b ? tr / 3. : 0.);
+            for (int e = 0; e < 3; ++e) {
+                Q3[a][b][e] = M3[a][b][e] - ((a == b ? T[e] : 0.) + (a == e ? T[b] : 0.) + (b == e ? T[a] : 0.)) / 5.;
+            }
+        }
+    }
+    mom[0] = m0;
+    mom[1] = Q2[0][0]; mom[2] = Q2[1][1]; mom[3] = Q2[0][1]; mom[4] = Q2[0][2]; mom[5] = Q2[1][2];
+    mom[6] = Q3[0][0][0]; mom[7] = Q3[0][0][1]; mom[8] = Q3[0][0][2]; mom[9] = Q3[0][1][1]; mom[10] = Q3[0][1][2];
+    mom[11] = Q3[1][1][1]; mom[12] = Q3[1][1][2];
+}
+
+/* evaluateGravity, Moments.h:315-340: gamma from computeGreenGamma (:22-29); per order M the acceleration
+ * gamma[M+1] dr Q0 + gamma[M] Q1 with Q0 = q . dr^M / M!, Q1 = q . dr^(M-1) / (M-1)! (computeMultipoleAcceleration
+ * :292-304, computeMultipolePotential :128-136), evaluated at dr = -(point - com). */
+void orc_gravity_multipole(const double* com, const double* mom, int order, const double* point, double* acc) {
+    double Q2[3][3], Q3[3][3][3];
+    Q2[0][0] = mom[1]; Q2[1][1] = mom[2]; Q2[2][2] = -mom[1] - mom[2];
+    Q2[0][1] = Q2[1][0] = mom[3]; Q2[0][2] = Q2[2][0] = mom[4]; Q2[1][2] = Q2[2][1] = mom[5];
+    /* the ten symmetric components from the seven independent ones (traceless in every index pair) */
+    double s[10];
+    s[0] = mom[6]; s[1] = mom[7]; s[2] = mom[8]; s[3] = mom[9]; s[4] = mom[10]; s[6] = mom[11]; s[7] = mom[12];
+    s[5] = -s[0] - s[3]; /* xzz */
+    s[8] = -s[1] - s[6]; /* yzz */
+    s[9] = -s[2] - s[7]; /* zzz */
+    for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) {
+            for (int e = 0; e < 3; ++e) {
+                const int nx = (a == 0) + (b == 0) + (e == 0), ny = (a == 1) + (b == 1) + (e == 1);
+                /* (nx, ny) -> xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz */
+                int idx;
+                if (nx == 3) idx = 0;
+                else if (nx == 2) idx = ny == 1 ? 1 : 2;
+                else if (nx == 1) idx = ny == 2 ? 3 : (ny == 1 ? 4 : 5);
+                else idx = ny == 3 ? 6 : (ny == 2 ? 7 : (ny == 1 ? 8 : 9));
+                Q3[a][b][e] = s[idx];
+            }
+        }
+    }
+    const double dr0[3] = { point[0] - com[0], point[1] - com[1], point[2] - com[2] };
+    const double invDistSqr = 1. / (dr0[0] * dr0[0] + dr0[1] * dr0[1] + dr0[2] * dr0[2]);
+    double gamma[5];
+    gamma[0] = -sqrt(invDistSqr);
+    for (int i = 1; i < 5; ++i) {
+        gamma[i] = -(2. * i - 1.) * invDistSqr * gamma[i - 1];
+    }
+    const double dr[3] = { -dr0[0], -dr0[1], -dr0[2] };
+    double a[3] = { 0., 0., 0. };
+    if (order >= 3) {
+        double q0 = 0., q1[3] = { 0., 0., 0. };
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) {
+                for (int k = 0; k < 3; ++k) {
+                    q0 += Q3[i][j][k] * dr[i] * dr[j] * dr[k] / 6.;
+                    q1[i] += Q3[i][j][k] * dr[j] * dr[k] / 2.;
+                }
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            a[k] += gamma[4] * dr[k] * q0 + gamma[3] * q1[k];
+        }
+    }
+    if (order >= 2) {
+        double q0 = 0., q1[3] = { 0., 0., 0. };
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) {
+                q0 += Q2[i][j] * dr[i] * dr[j] / 2.;
+                q1[i] += Q2[i][j] * dr[j];
+            }
+        }
+        for (int k = 0; k < 3; ++k) {
+            a[k] += gamma[3] * dr[k] * q0 + gamma[2] * q1[k];
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        a[k] += gamma[1] * dr[k] * mom[0];
+    }
+    acc[0] = a[0];
+    acc[1] = a[1];
+    acc[2] = a[2];
+}

@@ -140,3 +140,90 @@ extern "C" int hostcheck_integrate(orc_state* s, const sphgpu_config* cfg, const
     const uint64_t* off, const uint32_t* idx, int masked) {
     return masked ? dispatch<true>(s, cfg, mats, nmat, off, idx) : dispatch<false>(s, cfg, mats, nmat, off, idx);
 }
+
+// ---- self-gravity arithmetic (opensph_b200/csrc/grav_math.cuh) ------------------------------------------------------
+#include "../../opensph_b200/csrc/grav_math.cuh"
+
+/// Moments of the particle set formed the way the device tree forms them: the set is cut into `pieces` consecutive
+/// parts, each summed directly about its own centre of mass (k_grav_moments: leaf nodes), then merged pairwise with the
+/// raw-moment shift (inner nodes). Outputs the centre of mass, {M0, Q2[5], Q3[7]} and the acceleration at every probe.
+extern "C" int hostcheck_gravity_moments(uint32_t n, const double* pos, const double* mass, uint32_t pieces, double* com, double* mom,
+    uint32_t nProbes, const double* probes, int order, double* probeAcc) {
+    struct Part {
+        double c[3], m;
+        GravRaw raw;
+    };
+    std::vector<Part> parts;
+    for (uint32_t p = 0; p < pieces; ++p) {
+        const uint32_t b = (uint64_t)n * p / pieces, e = (uint64_t)n * (p + 1) / pieces;
+        if (b == e) continue;
+        Part q{};
+        for (uint32_t i = b; i < e; ++i) {
+            for (int k = 0; k < 3; ++k) q.c[k] += mass[i] * pos[4 * i + k];
+            q.m += mass[i];
+        }
+        for (int k = 0; k < 3; ++k) q.c[k] /= q.m;
+        gravRawZero(q.raw);
+        for (uint32_t i = b; i < e; ++i) {
+            gravRawAddPoint(q.raw, mass[i], pos[4 * i] - q.c[0], pos[4 * i + 1] - q.c[1], pos[4 * i + 2] - q.c[2]);
+        }
+        parts.push_back(q);
+    }
+    while (parts.size() > 1) {
+        std::vector<Part> next;
+        for (size_t k = 0; k + 1 < parts.size(); k += 2) {
+            const Part &a = parts[k], &b = parts[k + 1];
+            Part s{};
+            s.m = a.m + b.m;
+            for (int d = 0; d < 3; ++d) s.c[d] = (a.m * a.c[d] + b.m * b.c[d]) / s.m;
+            gravRawZero(s.raw);
+            gravRawAddShifted(s.raw, a.raw, a.m, a.c[0] - s.c[0], a.c[1] - s.c[1], a.c[2] - s.c[2]);
+            gravRawAddShifted(s.raw, b.raw, b.m, b.c[0] - s.c[0], b.c[1] - s.c[1], b.c[2] - s.c[2]);
+            next.push_back(s);
+        }
+        if (parts.size() & 1) next.push_back(parts.back());
+        parts.swap(next);
+    }
+    GravNode node;
+    node.cx = parts[0].c[0]; node.cy = parts[0].c[1]; node.cz = parts[0].c[2]; node.m = parts[0].m;
+    gravReduce(parts[0].raw, node);
+    com[0] = node.cx; com[1] = node.cy; com[2] = node.cz;
+    mom[0] = node.m;
+    for (int k = 0; k < 5; ++k) mom[1 + k] = node.q2[k];
+    for (int k = 0; k < 7; ++k) mom[6 + k] = node.q3[k];
+    for (uint32_t p = 0; p < nProbes; ++p) {
+        double ax = 0., ay = 0., az = 0.;
+        if (order == 0) gravNodeAccel<0>(node, probes[3 * p], probes[3 * p + 1], probes[3 * p + 2], ax, ay, az);
+        else if (order == 2) gravNodeAccel<2>(node, probes[3 * p], probes[3 * p + 1], probes[3 * p + 2], ax, ay, az);
+        else gravNodeAccel<3>(node, probes[3 * p], probes[3 * p + 1], probes[3 * p + 2], ax, ay, az);
+        probeAcc[3 * p] = ax; probeAcc[3 * p + 1] = ay; probeAcc[3 * p + 2] = az;
+    }
+    return 0;
+}
+
+/// All pairs with gravPairAccel (the walk's exact branch): acc [n*3]; masses are multiplied by G like k_grav_gather does.
+extern "C" int hostcheck_gravity_pairs(uint32_t n, const double* pos, const double* mass, double G, const double* lutGrad, uint32_t entries,
+    double radius, double* acc) {
+    GravParams prm{};
+    prm.radiusSqr = radius * radius;
+    prm.qSqrToIdx = radius > 0. ? (double)entries / prm.radiusSqr : 0.;
+    std::vector<LutPair> pairs(entries + 1);
+    if (radius > 0.) {
+        for (uint32_t k = 0; k <= entries; ++k) {
+            const double next = k < entries ? lutGrad[k + 1] : lutGrad[k];
+            pairs[k].g = lutGrad[k];
+            pairs[k].dg = next - lutGrad[k];
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        double ax = 0., ay = 0., az = 0.;
+        for (uint32_t j = 0; j < n; ++j) {
+            if (j != i) {
+                gravPairAccel(prm, pairs.data(), pos[4 * i], pos[4 * i + 1], pos[4 * i + 2], pos[4 * i + 3], pos[4 * j], pos[4 * j + 1],
+                    pos[4 * j + 2], pos[4 * j + 3], G * mass[j], ax, ay, az);
+            }
+        }
+        acc[3 * i] = ax; acc[3 * i + 1] = ay; acc[3 * i + 2] = az;
+    }
+    return 0;
+}

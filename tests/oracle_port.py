@@ -129,3 +129,44 @@ def build_lut(entries: int = 40000, radius: float = 2.0):
     val = np.zeros(entries + 1)
     lib().orc_build_lut(grad.ctypes.data_as(_D), val.ctypes.data_as(_D), C.c_uint32(entries), C.c_double(radius))
     return grad, val
+
+
+# ---- self-gravity (oracle/sph_oracle.c: orc_gravity_*) -------------------------------------------------------------
+def gravity_lut(entries: int = 40000) -> np.ndarray:
+    out = np.empty(entries + 1)
+    lib().orc_build_gravity_lut(out.ctypes.data_as(_D), C.c_uint32(entries))
+    return out
+
+
+def gravity_brute(pos: np.ndarray, mass: np.ndarray, G: float, lut_grad: Optional[np.ndarray], radius: float) -> np.ndarray:
+    """BruteForceGravity restated in C: accelerations [n, 3]."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    n = len(mass)
+    acc = np.zeros((n, 3))
+    if lut_grad is None:
+        lut_grad, radius = np.zeros(2), 0.0
+    lut_grad = np.ascontiguousarray(lut_grad, dtype=np.float64)
+    lib().orc_gravity_brute(C.c_uint32(n), pos.ctypes.data_as(_D), mass.ctypes.data_as(_D), C.c_double(G),
+                            lut_grad.ctypes.data_as(_D), C.c_uint32(len(lut_grad) - 1), C.c_double(radius),
+                            acc.ctypes.data_as(_D))
+    return acc
+
+
+def gravity_moments(pos: np.ndarray, mass: np.ndarray):
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    com, mom = np.zeros(3), np.zeros(13)
+    lib().orc_gravity_moments(C.c_uint32(len(mass)), pos.ctypes.data_as(_D), mass.ctypes.data_as(_D), com.ctypes.data_as(_D),
+                              mom.ctypes.data_as(_D))
+    return com, mom
+
+
+def gravity_multipole(com: np.ndarray, mom: np.ndarray, order: int, point: np.ndarray) -> np.ndarray:
+    com = np.ascontiguousarray(com, dtype=np.float64)
+    mom = np.ascontiguousarray(mom, dtype=np.float64)
+    point = np.ascontiguousarray(point[:3], dtype=np.float64)
+    acc = np.zeros(3)
+    lib().orc_gravity_multipole(com.ctypes.data_as(_D), mom.ctypes.data_as(_D), C.c_int(order), point.ctypes.data_as(_D),
+                                acc.ctypes.data_as(_D))
+    return acc
