@@ -1,14 +1,17 @@
 #include "GpuSolver.h"
 #include "../../include/sphgpu.h"
 #include "objects/Exceptions.h"
+#include "physics/Constants.h"
 #include "quantities/IMaterial.h"
 #include "quantities/Storage.h"
+#include "sph/kernel/GravityKernel.h"
 #include "sph/equations/av/Balsara.h"
 #include "sph/equations/av/Standard.h"
 #include "system/Factory.h"
 #include "system/Statistics.h"
 #include "system/Timer.h"
 #include "thread/Scheduler.h"
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -236,7 +239,114 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     }
     check(sphgpu_create(&cfg, mats.data(), uint32_t(mats.size()), n, n, device, &ctx));
     ctxParticleCnt = n;
+    if (deviceGravity) {
+        this->configureGravity();
+    }
     return ctx;
+}
+
+namespace {
+
+/// The table GravityLutKernel holds for the run's SPH kernel (Factory::getGravityKernel, Factory.cpp:712-735): LutKernel<3>
+/// built from the exact gravity kernel; its interpolation returns the entries themselves at the nodes, and the last
+/// node (the Newtonian value at the kernel's edge) comes from the exact kernel.
+template <typename TGravityKernel>
+void tabulateGravityKernel(const TGravityKernel& exact, std::vector<double>& lut, double& radius) {
+    const LutKernel<3> lk(exact);
+    const Size entries = 40000;
+    radius = lk.radius();
+    const Float qSqrToIdx = Float(entries) / sqr(lk.radius());
+    lut.resize(entries + 1);
+    for (Size i = 0; i < entries; ++i) {
+        lut[i] = lk.gradImpl(Float(i) / qSqrToIdx);
+    }
+    lut[entries] = exact.gradImpl(Float(entries) / qSqrToIdx);
+}
+
+bool gravityTable(const RunSettings& settings, std::vector<double>& lut, double& radius) {
+    switch (settings.get<KernelEnum>(RunSettingsId::SPH_KERNEL)) {
+    case KernelEnum::CUBIC_SPLINE:
+        tabulateGravityKernel(GravityKernel<CubicSpline<3>>(), lut, radius);
+        return true;
+    case KernelEnum::THOMAS_COUCHMAN:
+        tabulateGravityKernel(GravityKernel<ThomasCouchmanKernel<3>>(), lut, radius);
+        return true;
+    case KernelEnum::FOURTH_ORDER_SPLINE:
+        tabulateGravityKernel(getAssociatedGravityKernel(FourthOrderSpline<3>()), lut, radius);
+        return true;
+    case KernelEnum::GAUSSIAN:
+        tabulateGravityKernel(getAssociatedGravityKernel(Gaussian<3>()), lut, radius);
+        return true;
+    case KernelEnum::CORE_TRIANGLE:
+        tabulateGravityKernel(getAssociatedGravityKernel(CoreTriangle()), lut, radius);
+        return true;
+    case KernelEnum::WENDLAND_C2:
+        tabulateGravityKernel(getAssociatedGravityKernel(WendlandC2()), lut, radius);
+        return true;
+    case KernelEnum::WENDLAND_C4:
+        tabulateGravityKernel(getAssociatedGravityKernel(WendlandC4()), lut, radius);
+        return true;
+    case KernelEnum::WENDLAND_C6:
+        tabulateGravityKernel(getAssociatedGravityKernel(WendlandC6()), lut, radius);
+        return true;
+    default:
+        return false;
+    }
+}
+
+} // namespace
+
+bool GpuSolver::enableDeviceGravity() {
+    const GravityEnum id = settings.get<GravityEnum>(RunSettingsId::GRAVITY_SOLVER);
+    const GravityKernelEnum kernelId = settings.get<GravityKernelEnum>(RunSettingsId::GRAVITY_KERNEL);
+    if (id != GravityEnum::BARNES_HUT && id != GravityEnum::BRUTE_FORCE) {
+        return false;
+    }
+    if (kernelId != GravityKernelEnum::POINT_PARTICLES && kernelId != GravityKernelEnum::SPH_KERNEL) {
+        return false;
+    }
+    if (settings.get<BoundaryEnum>(RunSettingsId::DOMAIN_BOUNDARY) == BoundaryEnum::SYMMETRIC ||
+        settings.get<Float>(RunSettingsId::GRAVITY_RECOMPUTATION_PERIOD) > 0._f) {
+        return false; // SymmetricGravity / CachedGravity wrappers (Factory.cpp:401-410)
+    }
+    if (id == GravityEnum::BARNES_HUT) {
+        const int order = settings.get<int>(RunSettingsId::GRAVITY_MULTIPOLE_ORDER);
+        if (settings.get<Float>(RunSettingsId::GRAVITY_OPENING_ANGLE) > 1._f || (order != 0 && order != 2 && order != 3)) {
+            return false;
+        }
+    }
+    if (kernelId == GravityKernelEnum::SPH_KERNEL) {
+        std::vector<double> lut;
+        double radius;
+        if (!gravityTable(settings, lut, radius)) {
+            return false;
+        }
+    }
+    deviceGravity = true;
+    if (ctx) {
+        this->configureGravity();
+    }
+    return true;
+}
+
+void GpuSolver::configureGravity() {
+    sphgpu_gravity g{};
+    const bool brute = settings.get<GravityEnum>(RunSettingsId::GRAVITY_SOLVER) == GravityEnum::BRUTE_FORCE;
+    g.opening_angle = brute ? 0. : double(settings.get<Float>(RunSettingsId::GRAVITY_OPENING_ANGLE));
+    g.multipole_order = brute ? 3 : settings.get<int>(RunSettingsId::GRAVITY_MULTIPOLE_ORDER);
+    g.leaf_size = uint32_t(settings.get<int>(RunSettingsId::FINDER_LEAF_SIZE));
+    // Factory::getGravity hands GRAVITY_CONSTANT to BarnesHut only; BruteForceGravity is built with its default,
+    // Constants::gravity (Factory.cpp:384-395). The drop-in reproduces the reference as it is.
+    g.constant = brute ? double(Constants::gravity) : double(settings.get<Float>(RunSettingsId::GRAVITY_CONSTANT));
+    std::vector<double> lut;
+    double radius = 0.;
+    if (settings.get<GravityKernelEnum>(RunSettingsId::GRAVITY_KERNEL) == GravityKernelEnum::SPH_KERNEL) {
+        gravityTable(settings, lut, radius);
+        g.lut_grad = lut.data();
+        g.lut_entries = uint32_t(lut.size() - 1);
+    }
+    g.kernel_radius = radius;
+    check(sphgpu_gravity_configure(ctx, &g));
 }
 
 void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives) {
@@ -367,8 +477,15 @@ GpuGravitySolver::GpuGravitySolver(IScheduler& scheduler,
     AutoPtr<IGravity>&& gravityImpl,
     const int device)
     : scheduler(scheduler)
+    , settings(settings)
     , sph(scheduler, settings, eqs, device)
     , gravity(std::move(gravityImpl)) {
+    if (!gravity && !sph.enableDeviceGravity()) {
+        gravity = Factory::getGravity(settings);
+    }
+}
+
+void GpuGravitySolver::ensureHostGravity() {
     if (!gravity) {
         gravity = Factory::getGravity(settings);
     }
@@ -381,6 +498,32 @@ void GpuGravitySolver::create(Storage& storage, IMaterial& material) const {
 }
 
 void GpuGravitySolver::integrate(Storage& storage, Statistics& stats) {
+    ArrayView<Attractor> attractors = storage.getAttractors();
+    if (sph.hasDeviceGravity()) {
+        // SPH and gravity in one device call (sphgpu_integrate adds the gravitational accelerations, api.cu)
+        Timer timer;
+        sph.integrate(storage, stats);
+        sphgpu_gravity_stats gs{};
+        if (sphgpu_gravity_last_stats(sph.context(storage), &gs) == SPHGPU_OK) {
+            stats.set(StatisticsId::GRAVITY_EVAL_TIME, int(gs.gpu_ms));
+            stats.set(StatisticsId::GRAVITY_NODES_APPROX, int(std::min<uint64_t>(gs.approximated, 0x7fffffff)));
+            stats.set(StatisticsId::GRAVITY_NODES_EXACT, int(std::min<uint64_t>(gs.exact, 0x7fffffff)));
+            stats.set(StatisticsId::GRAVITY_NODE_COUNT, int(gs.nodes));
+        }
+        stats.set(StatisticsId::SPH_EVAL_TIME, int(timer.elapsed(TimerUnit::MILLISECOND)));
+        if (!attractors.empty()) {
+            // attractors are few: their interaction with the particles stays on the host (BarnesHut::evalAttractors,
+            // BarnesHut.cpp:101-124, needs only positions and masses, which the Storage holds)
+            this->ensureHostGravity();
+            gravity->build(scheduler, storage);
+            ArrayView<Vector> dv = storage.getD2t<Vector>(QuantityId::POSITION);
+            gravity->evalAttractors(scheduler, attractors, dv);
+            for (Size i = 0; i < dv.size(); ++i) {
+                dv[i][H] = 0._f;
+            }
+        }
+        return;
+    }
     // SPH part on the device; it overwrites the (zeroed) highest derivatives of the Storage
     Timer timer;
     sph.integrate(storage, stats);
@@ -396,7 +539,6 @@ void GpuGravitySolver::integrate(Storage& storage, Statistics& stats) {
     timer.restart();
     gravity->evalSelfGravity(scheduler, dv, stats);
     stats.set(StatisticsId::GRAVITY_EVAL_TIME, int(timer.elapsed(TimerUnit::MILLISECOND)));
-    ArrayView<Attractor> attractors = storage.getAttractors();
     gravity->evalAttractors(scheduler, attractors, dv);
     // the gravity kernels work on whole Vectors and leave a value in the H lane; the smoothing length is a first-order
     // quantity (AdaptiveSmoothingLength::finalize / ConstSmoothingLength::finalize zero it AFTER gravity in the

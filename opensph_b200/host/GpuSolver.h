@@ -55,6 +55,10 @@ private:
     /// True while the device holds a newer state than the Storage (after GpuPredictorCorrector steps).
     bool hostStale = false;
 
+    /// Self-gravity on the device (enableDeviceGravity): applied to every context this solver creates.
+    bool deviceGravity = false;
+    void configureGravity();
+
     class DeviceMirror; ///< IStorageUserData attached to the Storage: sees Storage::remove (Storage.h:126-133)
     friend class DeviceMirror;
 
@@ -83,6 +87,18 @@ public:
     /// Device context (created lazily for the storage's particle count and materials).
     sphgpu_ctx* context(const Storage& storage);
 
+    /// Adds the self-gravity Factory::getGravity(settings) describes (core/system/Factory.cpp:361-413: BarnesHut with
+    /// GRAVITY_OPENING_ANGLE / GRAVITY_MULTIPOLE_ORDER / FINDER_LEAF_SIZE or BruteForceGravity, GRAVITY_KERNEL point
+    /// particles or the softening kernel of the SPH kernel, GRAVITY_CONSTANT) to every integrate() on the device, the way
+    /// GravitySolver<TSphSolver>::loop composes them (core/sph/solvers/GravitySolver.cpp:64-99).
+    /// \return false -- and nothing changes -- if the settings ask for something the device does not implement
+    ///         (SphericalGravity, solid-sphere kernel, symmetric boundary, cached gravity, opening angle above 1).
+    bool enableDeviceGravity();
+
+    bool hasDeviceGravity() const {
+        return deviceGravity;
+    }
+
     bool isHostStale() const {
         return hostStale;
     }
@@ -106,27 +122,37 @@ private:
     void downloadQuantities(Storage& storage, const bool stateToo);
 };
 
-/// \brief GpuSolver plus the reference's own self-gravity, the composition GravitySolver<TSphSolver> performs
-///        (core/sph/solvers/GravitySolver.cpp:64-99, selected by ForceEnum::SELF_GRAVITY in Factory.cpp:300-312).
+/// \brief GpuSolver plus self-gravity, the composition GravitySolver<TSphSolver> performs
+///        (core/sph/solvers/GravitySolver.cpp:64-99, selected by ForceEnum::SELF_GRAVITY in Factory.cpp:300-312), so that
+///        setups with self-gravity -- the GUI collision preset, SimulationJobs.cpp:209-223 -- run on the device.
 ///
-/// The SPH derivatives come from the device; the gravitational accelerations are evaluated by the IGravity object of
-/// the reference (Barnes-Hut or brute force, Factory::getGravity) on the host cores and added to the acceleration
-/// buffer, so that setups with self-gravity -- the GUI collision preset, SimulationJobs.cpp:209-223 -- run with the
-/// device as their SPH part. Gravity on the device is SURVEY section 8(f) #1; until then this solver is the way to run
-/// such setups, at the cost of the host-side tree walk.
+/// By default gravity is evaluated ON THE DEVICE (GpuSolver::enableDeviceGravity: Barnes-Hut / brute force as the run
+/// settings describe it, sphgpu_gravity_configure); no particle data crosses PCIe for it and GpuPredictorCorrector keeps
+/// whole steps on the device. When the caller passes its own IGravity, when the settings ask for something the device does
+/// not implement, or when the Storage holds attractors, the accelerations come from the reference's IGravity on the host
+/// cores and are added to the acceleration buffer (the round-1 behaviour).
 class GpuGravitySolver : public ISolver {
 private:
     IScheduler& scheduler;
+    RunSettings settings;
     GpuSolver sph;
-    AutoPtr<IGravity> gravity;
+    AutoPtr<IGravity> gravity; ///< host-side gravity; null while the device evaluates it
+
+    void ensureHostGravity();
 
 public:
-    /// \param gravity Gravity implementation; nullptr selects Factory::getGravity(settings) like GravitySolver does.
+    /// \param gravity Host-side gravity implementation to use instead of the device's; nullptr selects the device path
+    ///        (falling back to Factory::getGravity(settings) on the host where the device cannot serve the settings).
     GpuGravitySolver(IScheduler& scheduler,
         const RunSettings& settings,
         const EquationHolder& eqs,
         AutoPtr<IGravity>&& gravity = nullptr,
         const int device = 0);
+
+    /// True if the gravitational accelerations are computed by the device.
+    bool gravityOnDevice() const {
+        return sph.hasDeviceGravity();
+    }
 
     ~GpuGravitySolver() override;
 

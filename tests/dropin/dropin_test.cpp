@@ -8,6 +8,7 @@
 #include "../../opensph_b200/host/GpuSolver.h"
 #include "../../opensph_b200/host/GpuOutput.h"
 #include "Sph.h"
+#include "physics/Constants.h"
 #include "sph/solvers/GravitySolver.h"
 #include <cstdio>
 #include <fstream>
@@ -279,24 +280,75 @@ int main(int argc, char** argv) {
             gs.set(RunSettingsId::SPH_SOLVER_FORCES, ForceEnum::PRESSURE | ForceEnum::SOLID_STRESS | ForceEnum::SELF_GRAVITY)
                 .set(RunSettingsId::GRAVITY_SOLVER, GravityEnum::BARNES_HUT)
                 .set(RunSettingsId::GRAVITY_OPENING_ANGLE, 0.8_f)
-                .set(RunSettingsId::GRAVITY_MULTIPOLE_ORDER, 3);
+                .set(RunSettingsId::GRAVITY_MULTIPOLE_ORDER, 3)
+                // the test body is small: a constant large enough for gravity to matter next to the SPH accelerations
+                .set(RunSettingsId::GRAVITY_CONSTANT, Float(Constants::gravity * 1.e4));
             const EquationHolder geqs = getStandardEquations(gs);
+            auto integrateWith = [&](ISolver& solver, Storage& st) {
+                st.zeroHighestDerivatives(*scheduler);
+                Statistics ss;
+                ss.set(StatisticsId::RUN_TIME, 0._f);
+                solver.integrate(st, ss);
+            };
             GravitySolver<AsymmetricSolver> refGravity(*scheduler, gs, geqs);
-            GpuGravitySolver gpuGravity(*scheduler, gs, geqs);
-            Storage ga = base->clone(VisitorEnum::ALL_BUFFERS), gb = base->clone(VisitorEnum::ALL_BUFFERS);
-            ga.zeroHighestDerivatives(*scheduler);
-            gb.zeroHighestDerivatives(*scheduler);
-            Statistics sa2, sb2;
-            sa2.set(StatisticsId::RUN_TIME, 0._f);
-            sb2.set(StatisticsId::RUN_TIME, 0._f);
-            refGravity.integrate(ga, sa2);
-            gpuGravity.integrate(gb, sb2);
-            expect(sameNeighbourCounts(ga, gb), "NEIGHBOR_CNT identical with self-gravity");
-            expect(compareStorages(ga, gb, true, "integrate() with Barnes-Hut self-gravity") <= 1.e-10,
-                "all quantities within 1e-10 (GravitySolver<AsymmetricSolver> vs GpuGravitySolver)");
-            // the gravity part is not negligible in this comparison: accelerations must differ from the SPH-only ones
-            const double diff = cmpVector(gb.getD2t<Vector>(QuantityId::POSITION), b.getD2t<Vector>(QuantityId::POSITION), 3);
-            expect(diff > 1.e-6, "gravity contributes to the accelerations");
+            Storage ga = base->clone(VisitorEnum::ALL_BUFFERS);
+            integrateWith(refGravity, ga);
+            const double gravShare = cmpVector(ga.getD2t<Vector>(QuantityId::POSITION), b.getD2t<Vector>(QuantityId::POSITION), 3);
+            expect(gravShare > 1.e-3, "gravity contributes to the accelerations");
+
+            // (a) host-side gravity handed in by the caller: the reference's own IGravity, identical tree
+            {
+                GpuGravitySolver hostGravity(*scheduler, gs, geqs, Factory::getGravity(gs));
+                expect(!hostGravity.gravityOnDevice(), "a caller-supplied IGravity stays on the host");
+                Storage gb = base->clone(VisitorEnum::ALL_BUFFERS);
+                integrateWith(hostGravity, gb);
+                expect(sameNeighbourCounts(ga, gb), "NEIGHBOR_CNT identical with self-gravity");
+                expect(compareStorages(ga, gb, true, "integrate() with host Barnes-Hut") <= 1.e-10,
+                    "all quantities within 1e-10 (GravitySolver<AsymmetricSolver> vs GpuGravitySolver with host gravity)");
+            }
+            // (b) gravity on the device, every pair exactly. (Factory::getGravity builds BruteForceGravity without
+            // GRAVITY_CONSTANT, Factory.cpp:385, so the enlarged constant would not reach it; an opening angle of 1e-3
+            // makes BarnesHut open every node instead -- the same exact pair sums on both sides.)
+            {
+                RunSettings bs = gs;
+                bs.set(RunSettingsId::GRAVITY_OPENING_ANGLE, 1.e-3_f);
+                GravitySolver<AsymmetricSolver> refBrute(*scheduler, bs, geqs);
+                GpuGravitySolver gpuBrute(*scheduler, bs, geqs);
+                expect(gpuBrute.gravityOnDevice(), "gravity runs on the device");
+                {
+                    RunSettings bf = gs;
+                    bf.set(RunSettingsId::GRAVITY_SOLVER, GravityEnum::BRUTE_FORCE);
+                    GpuGravitySolver gpuBf(*scheduler, bf, geqs);
+                    expect(gpuBf.gravityOnDevice(), "brute-force gravity runs on the device");
+                }
+                Storage gr = base->clone(VisitorEnum::ALL_BUFFERS), gb = base->clone(VisitorEnum::ALL_BUFFERS);
+                integrateWith(refBrute, gr);
+                integrateWith(gpuBrute, gb);
+                expect(compareStorages(gr, gb, true, "integrate() with exact gravity on the device") <= 1.e-10,
+                    "all quantities within 1e-10 (GravitySolver<AsymmetricSolver> vs device gravity, exact sums)");
+                // (c) device Barnes-Hut: a different tree, so it is measured like the reference's own BarnesHut tests
+                // (core/gravity/test/BarnesHut.cpp): against the exact sums, and not worse than the reference's tree
+                GpuGravitySolver gpuBh(*scheduler, gs, geqs);
+                expect(gpuBh.gravityOnDevice(), "Barnes-Hut gravity runs on the device");
+                Storage gd = base->clone(VisitorEnum::ALL_BUFFERS);
+                integrateWith(gpuBh, gd);
+                auto rms = [](ArrayView<const Vector> x, ArrayView<const Vector> y) {
+                    double num = 0., den = 0.;
+                    for (Size i = 0; i < x.size(); ++i) {
+                        for (int k = 0; k < 3; ++k) {
+                            num += sqr(x[i][k] - y[i][k]);
+                            den += sqr(y[i][k]);
+                        }
+                    }
+                    return std::sqrt(num / den);
+                };
+                const double errRef = rms(ga.getD2t<Vector>(QuantityId::POSITION), gr.getD2t<Vector>(QuantityId::POSITION));
+                const double errGpu = rms(gd.getD2t<Vector>(QuantityId::POSITION), gr.getD2t<Vector>(QuantityId::POSITION));
+                printf("  [Barnes-Hut, opening angle 0.8, octupole] rms error of the accelerations against the exact sums: reference %.3e, device %.3e\n",
+                    errRef, errGpu);
+                expect(errGpu > 0. && errGpu <= 2. * errRef, "device Barnes-Hut is as accurate as the reference's");
+                expect(sameNeighbourCounts(ga, gd), "NEIGHBOR_CNT identical with device gravity");
+            }
         }
 
         // ---- 3b. particle removal: the Storage tells the solver (IStorageUserData), the device mirror is rebuilt ----
