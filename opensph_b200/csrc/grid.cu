@@ -28,9 +28,20 @@ __device__ __forceinline__ double warpMax(double v) {
 // AdaptiveSmoothingLength::initialize (h clamp, EquationTerm.cpp:356-364) fused with the bounding-box / h_max pass and
 // with the displacement check of the list reuse (ListCtlDev): how far every particle has moved, relative to R h, and how
 // much its h has grown since the lists were built.
-__global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax, double kernelRadius) {
+/// Order-preserving map of a float to an unsigned key (atomicMin / atomicMax on floats of either sign) and back.
+__device__ __forceinline__ uint32_t floatKey(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float keyFloat(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax, double kernelRadius,
+    bool trackCells, uint32_t cellStride) {
     double lo[3] = { INFTY_REF, INFTY_REF, INFTY_REF }, hi[3] = { -INFTY_REF, -INFTY_REF, -INFTY_REF }, hm = 0.;
-    double ratio2 = 0., grow = 0., hsum = 0.;
+    double ratio2 = 0., grow = 0., hsum = 0., hNegMin0 = -INFTY_REF;
+    const uint32_t overflowCell = d.grid->ncells;
     const double gx = d.grid->lo[0], gy = d.grid->lo[1], gz = d.grid->lo[2]; // origin of the grid the lists were built on
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nActive; i += gridDim.x * blockDim.x) {
         double h = d.f[F_H][i];
@@ -55,27 +66,117 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
         const double rh0 = kernelRadius * (double)p0.w;
         ratio2 = fmax(ratio2, (ex * ex + ey * ey + ez * ez) / (rh0 * rh0));
         grow = fmax(grow, h / (double)p0.w - 1.);
+        if (trackCells) { // (cellOf belongs to the lists in use; large particles are paired directly every step)
+            const uint32_t c = d.cellOf[i];
+            if (c < overflowCell) {
+                hNegMin0 = fmax(hNegMin0, -(double)p0.w);
+                atomicMin(&d.dispA[c], floatKey(__double2float_rd(ex)));
+                atomicMin(&d.dispA[cellStride + c], floatKey(__double2float_rd(ey)));
+                atomicMin(&d.dispA[2 * cellStride + c], floatKey(__double2float_rd(ez)));
+                atomicMax(&d.dispA[3 * cellStride + c], floatKey(__double2float_ru(ex)));
+                atomicMax(&d.dispA[4 * cellStride + c], floatKey(__double2float_ru(ey)));
+                atomicMax(&d.dispA[5 * cellStride + c], floatKey(__double2float_ru(ez)));
+            }
+        }
     }
+    hNegMin0 = warpMax(hNegMin0);
     for (int o = 16; o > 0; o >>= 1) {
         hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
     }
-    __shared__ double sm[8][10];
+    __shared__ double sm[8][11];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double v[10] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm),
-        warpMax(ratio2), warpMax(grow), hsum };
+    double v[11] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm),
+        warpMax(ratio2), warpMax(grow), hsum, hNegMin0 };
     if (lane == 0) {
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < 11; ++k) {
             sm[warp][k] = v[k];
         }
     }
     __syncthreads();
-    if (threadIdx.x < 10) {
+    if (threadIdx.x < 11) {
         const int k = threadIdx.x;
         double r = sm[0][k];
         for (int w = 1; w < 8; ++w) {
             r = (k < 3) ? fmin(r, sm[w][k]) : (k == 9 ? r + sm[w][k] : fmax(r, sm[w][k]));
         }
-        d.boundsPartial[blockIdx.x * BOUNDS_STRIDE + k] = r;
+        // ([10], [11] of a block's row belong to k_hmax_small; minus the smallest build-time h goes to [12])
+        d.boundsPartial[blockIdx.x * BOUNDS_STRIDE + (k < 10 ? k : 12)] = r;
+    }
+}
+
+// ---- relative displacement since the list build (ListCtlDev) ------------------------------------------------------------
+// One pass per axis widens every cell's displacement box to the union over its window (min / max commute with the key map,
+// so the keys are never decoded here; untouched cells hold the neutral keys ~0 / 0).
+template <int AXIS, int HALF>
+__global__ void __launch_bounds__(256) k_disp_dilate(DevicePointers d, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+    uint32_t cellStride, bool trackCells) {
+    if (!trackCells) {
+        return;
+    }
+    const GridDev g = *d.grid;
+    const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
+    const int step = AXIS == 0 ? 1 : (AXIS == 1 ? dimx : dimx * dimy);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += gridDim.x * blockDim.x) {
+        const int cx = (int)(c % (uint32_t)dimx), cy = (int)((c / (uint32_t)dimx) % (uint32_t)dimy), cz = (int)(c / (uint32_t)(dimx * dimy));
+        const int pos = AXIS == 0 ? cx : (AXIS == 1 ? cy : cz), dim = AXIS == 0 ? dimx : (AXIS == 1 ? dimy : dimz);
+        const int a = max(pos - HALF, 0) - pos, b = min(pos + HALF, dim - 1) - pos;
+        uint32_t lo[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, hi[3] = { 0u, 0u, 0u };
+        for (int o = a; o <= b; ++o) {
+            const uint32_t e = (uint32_t)((int)c + o * step);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = min(lo[k], in[k * cellStride + e]);
+                hi[k] = max(hi[k], in[(3 + k) * cellStride + e]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            out[k * cellStride + c] = lo[k];
+            out[(3 + k) * cellStride + c] = hi[k];
+        }
+    }
+}
+
+/// Bound of |u_i - u_j| over the particles i of a cell and j of its window -> dispGlobal[6] (largest over all cells), and
+/// the global box of u -> dispGlobal[0..5].
+__global__ void __launch_bounds__(256) k_disp_check(DevicePointers d, const uint32_t* __restrict__ window, uint32_t cellStride, bool trackCells) {
+    if (!trackCells) {
+        return;
+    }
+    const GridDev g = *d.grid;
+    uint32_t glo[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, ghi[3] = { 0u, 0u, 0u };
+    float worst = 0.f;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += gridDim.x * blockDim.x) {
+        if (d.dispA[3 * cellStride + c] == 0u) {
+            continue; // no particle in this cell
+        }
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t ol = d.dispA[k * cellStride + c], oh = d.dispA[(3 + k) * cellStride + c];
+            const float e = fmaxf(__fsub_ru(keyFloat(oh), keyFloat(window[k * cellStride + c])),
+                __fsub_ru(keyFloat(window[(3 + k) * cellStride + c]), keyFloat(ol)));
+            s2 = __fmaf_ru(e, e, s2);
+            glo[k] = min(glo[k], ol);
+            ghi[k] = max(ghi[k], oh);
+        }
+        worst = fmaxf(worst, __fsqrt_ru(s2));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            glo[k] = min(glo[k], __shfl_xor_sync(0xffffffffu, glo[k], o));
+            ghi[k] = max(ghi[k], __shfl_xor_sync(0xffffffffu, ghi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&d.dispGlobal[6], __float_as_uint(worst)); // non-negative floats order like their bit patterns
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&d.dispGlobal[k], glo[k]);
+            atomicMax(&d.dispGlobal[3 + k], ghi[k]);
+        }
     }
 }
 
@@ -119,17 +220,18 @@ __global__ void __launch_bounds__(256) k_hmax_small(DevicePointers d, uint32_t n
 /// Reduces the partial bounds and decides whether this integrate() rebuilds the cell list / units / candidate lists (force,
 /// or the displacement metric has used up the skin; the margin covers the FP32 rounding of pos0). Every later build
 /// kernel reads ListCtlDev::rebuild and returns at once when it is 0. Also fixes the split of the search radii.
-__global__ void __launch_bounds__(256) k_grid_decide(DevicePointers d, int nPartials, uint32_t nActive, bool force, double skin) {
-    __shared__ double sm[8][10];
-    double v[10] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0., 0., 0., 0. };
+__global__ void __launch_bounds__(256) k_grid_decide(DevicePointers d, int nPartials, uint32_t nActive, bool force, double skin,
+    double kernelRadius) {
+    __shared__ double sm[8][11];
+    double v[11] = { INFTY_REF, INFTY_REF, INFTY_REF, -INFTY_REF, -INFTY_REF, -INFTY_REF, 0., 0., 0., 0., -INFTY_REF };
     for (int b = threadIdx.x; b < nPartials; b += blockDim.x) {
-        for (int k = 0; k < 10; ++k) {
-            const double p = d.boundsPartial[b * BOUNDS_STRIDE + k];
+        for (int k = 0; k < 11; ++k) {
+            const double p = d.boundsPartial[b * BOUNDS_STRIDE + (k < 10 ? k : 12)];
             v[k] = (k < 3) ? fmin(v[k], p) : (k == 9 ? v[k] + p : fmax(v[k], p));
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = 0; k < 10; ++k) {
+    for (int k = 0; k < 11; ++k) {
         if (k == 9) {
             for (int o = 16; o > 0; o >>= 1) {
                 v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
@@ -139,25 +241,45 @@ __global__ void __launch_bounds__(256) k_grid_decide(DevicePointers d, int nPart
         }
     }
     if (lane == 0) {
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < 11; ++k) {
             sm[warp][k] = v[k];
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < 11; ++k) {
             double r = sm[0][k];
             for (int w = 1; w < 8; ++w) {
                 r = (k < 3) ? fmin(r, sm[w][k]) : (k == 9 ? r + sm[w][k] : fmax(r, sm[w][k]));
             }
             // the first slots of the partial array carry the totals to k_grid_params
-            d.boundsPartial[k] = r;
+            if (k < 10) {
+                d.boundsPartial[k] = r;
+            }
             v[k] = r;
         }
         ListCtlDev ctl = *d.listCtl;
-        const double metric = 2. * sqrt(v[7]) + fmax(v[8], 0.);
+        // Relative displacement of particles that can reach each other (k_disp_check), in units of the smallest reach
+        // R h_min0, plus the largest growth of h. The FP32 copies pos0 are exact to 2^-24 of the grid extent per coordinate.
+        double metric = INFTY_REF;
+        bool farSafe = false;
+        if (!force) {
+            const GridDev g = *d.grid;
+            const double slack = 4.e-7 * g.extent;
+            const double hMin0 = -v[10];
+            const double rel = (double)__uint_as_float(d.dispGlobal[6]) + slack;
+            metric = (hMin0 > 0. ? rel / (kernelRadius * hMin0) : 0.) + fmax(v[8], 0.);
+            // pairs beyond the window were at least two cell edges apart: safe while all of u fits into 0.9 cell edges
+            double ext2 = 0.;
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t kl = d.dispGlobal[k], kh = d.dispGlobal[3 + k];
+                const double e = kh >= kl ? (double)keyFloat(kh) - (double)keyFloat(kl) : 0.;
+                ext2 += e * e;
+            }
+            farSafe = sqrt(ext2) + slack < 0.9 * g.cell;
+        }
         ctl.lastMetric = metric;
-        const bool rebuild = force || !(metric < 0.9 * skin);
+        const bool rebuild = force || !(metric < 0.9 * skin) || !farSafe;
         ctl.rebuild = rebuild ? 1u : 0u;
         if (rebuild) {
             ctl.age = 0u;
@@ -457,9 +579,27 @@ int launchGridBuild(sphgpu_ctx* ctx) {
     const uint32_t n = ctx->nActive;
     cudaStream_t st = ctx->stream;
     const bool clampH = (ctx->prm.flags & SPHGPU_FLAG_ADAPTIVE_H) != 0;
-    k_bounds<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n, clampH, ctx->prm.h_min, ctx->prm.h_max, ctx->prm.kernel_radius);
     const bool force = ctx->listsDirty || !(ctx->listSkin > 0.);
-    k_grid_decide<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, n, force, ctx->listSkin);
+    const bool track = !force; // (the first build has no cells to track)
+    const uint32_t cellStride = ctx->maxCells + 1;
+    if (track) { // neutral keys: lower bounds ~0, upper bounds 0; dispGlobal likewise, [6] = 0.f
+        SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.dispA, 0xff, sizeof(uint32_t) * 3 * (size_t)cellStride, st));
+        SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.dispA + 3 * (size_t)cellStride, 0, sizeof(uint32_t) * 3 * (size_t)cellStride, st));
+        SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.dispGlobal, 0xff, sizeof(uint32_t) * 3, st));
+        SPH_CUDA_CHECK(cudaMemsetAsync(ctx->d.dispGlobal + 3, 0, sizeof(uint32_t) * 5, st));
+    }
+    k_bounds<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n, clampH, ctx->prm.h_min, ctx->prm.h_max, ctx->prm.kernel_radius, track, cellStride);
+    if (track) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const uint32_t cb = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)ctx->maxCells + 255) / 256);
+        k_disp_dilate<0, 2><<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispA, ctx->d.dispB, cellStride, track);
+        k_disp_dilate<1, 2><<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispB, ctx->d.dispC, cellStride, track);
+        k_disp_dilate<2, 4><<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispC, ctx->d.dispB, cellStride, track);
+        k_disp_check<<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispB, cellStride, track);
+        ctx->launches += 4;
+    }
+    k_grid_decide<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, n, force, ctx->listSkin, ctx->prm.kernel_radius);
     k_hmax_small<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n);
     k_grid_params<<<1, 32, 0, st>>>(ctx->d, BOUNDS_BLOCKS, ctx->prm.kernel_radius, ctx->maxCells, ctx->listSkin > 0. ? ctx->listSkin : 0.);
     ctx->listsDirty = false;
