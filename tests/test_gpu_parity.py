@@ -479,6 +479,66 @@ def test_list_reuse_matches_rebuild_every_step(lut):
         assert_close(k, b[k], a[k], 1e-9, FLOOR)
 
 
+def test_list_reuse_relative_displacement_criterion(lut):
+    """The rebuild decision looks at the RELATIVE displacement of particles that can reach each other (per-cell displacement
+    boxes widened over the candidate stencil plus one cell, api: sphgpu_set_list_skin). Two checks:
+    (1) two bodies flying into each other -- neighbour sets between them change from step to step: NEIGHBOR_CNT after
+        every step equals the run that rebuilds every step (no neighbour may be missed);
+    (2) one body that translates fast and uniformly: no relative motion beyond the physical one, so the lists survive
+        far longer than the absolute displacement (many h) would have allowed."""
+    from opensph_b200 import workloads
+    names = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "damage", "ddamage", "reduce",
+             "eps_min", "m_zero", "growth", "n_flaws", "flag")
+    # (1) a sphere cut in two halves that approach each other at 8 km/s along x, with a little shear
+    state = workloads.basalt_sphere_state(12000)
+    h = state["pos"][0, 3]
+    left = state["pos"][:, 0] < 0.0
+    state["pos"][left, 0] -= 0.8 * h
+    state["pos"][~left, 0] += 0.8 * h
+    state["vel"][:, :3] = 0.0
+    state["vel"][left, 0], state["vel"][~left, 0] = 4000.0, -4000.0
+    state["vel"][left, 1] = 500.0
+    n = len(state["mass"])
+    setup = workloads.make_setup(n)
+    counts = {}
+    for skin in (0.0, 0.03):
+        with Engine(setup, n) as eng:
+            eng.set_list_skin(skin)
+            eng.upload_state(state, names)
+            dt, seq = 0.05, []
+            for _ in range(30):
+                dts, _, _ = eng.run_pc(1, dt, 0.1)
+                dt = float(dts[-1])
+                seq.append(eng.download_state(["ncnt"])["ncnt"].copy())
+            counts[skin] = (seq, eng.list_stats())
+    for k, (x, y) in enumerate(zip(counts[0.0][0], counts[0.03][0])):
+        assert np.array_equal(x, y), f"NEIGHBOR_CNT differs at step {k} between reused and rebuilt lists"
+    assert counts[0.0][0][-1].sum() != counts[0.0][0][0].sum(), "the halves must have come into contact"
+    assert counts[0.03][1][0] < 30, counts[0.03][1]
+    # (2) uniform translation at 30 km/s: after 20 steps of 50 ms every particle has moved ~6 h
+    state = workloads.basalt_sphere_state(12000)
+    state["vel"][:, :3] *= 0.02
+    state["vel"][:, 0] += 30000.0
+    n = len(state["mass"])
+    setup = workloads.make_setup(n)
+    with Engine(setup, n) as eng:
+        eng.set_list_skin(0.03)
+        eng.upload_state(state, names)
+        eng.run_pc(20, 0.05, 0.05)
+        moved = np.abs(eng.download_state(["pos"])["pos"][:, 0] - state["pos"][:, 0]).min() / state["pos"][0, 3]
+        rebuilds = eng.list_stats()[0]
+        a = eng.download_state(["ncnt", "acc"])
+    with Engine(setup, n) as eng:
+        eng.set_list_skin(0.0)
+        eng.upload_state(state, names)
+        eng.run_pc(20, 0.05, 0.05)
+        b = eng.download_state(["ncnt", "acc"])
+    assert moved > 3.0, moved
+    assert rebuilds <= 3, f"a uniformly translating body must keep its lists ({rebuilds} builds in 20 steps)"
+    assert np.array_equal(a["ncnt"], b["ncnt"])
+    assert_close("acc", a["acc"], b["acc"], 1e-9, FLOOR)
+
+
 def test_multi_gpu_parity_script():
     """tests/run_mgpu_parity.py (two ranks: NCCL halo exchange, batched stepping, repartition) against a single-domain run;
     needs two GPUs on the box."""
