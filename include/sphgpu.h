@@ -321,6 +321,32 @@ SPHGPU_API int sphgpu_gravity_eval(sphgpu_ctx* ctx, int accumulate, sphgpu_gravi
 /* Statistics of the last evaluation, e.g. the one inside sphgpu_integrate. Synchronises. */
 SPHGPU_API int sphgpu_gravity_last_stats(sphgpu_ctx* ctx, sphgpu_gravity_stats* stats);
 
+/* ---- initial conditions on the device --------------------------------------------------- */
+
+/* Replaces InitialConditions::addMonolithicBody (core/sph/initial/Initial.cpp:100-125) for a SphericalDomain
+ * (core/objects/geometry/Domain.cpp:10-33) filled by HexagonalPacking (core/sph/initial/Distribution.cpp:126-200,
+ * BodySettings defaults: not sorted, SPHGPU_LATTICE_CENTER = BodySettingsId::CENTER_PARTICLES) with
+ * InitialConditions::setQuantities / getMasses (Initial.cpp:288-333): positions, h = eta * lattice spacing, masses
+ * proportional to h^3 that sum to density * volume, the body flag, zero velocities and accelerations are written into
+ * the slots [first, first + count) of the context without touching host memory. Lattice points are bit-identical to the
+ * reference's; the centring shift and the mass normalisation are sums over all particles (sequential in the reference, a
+ * tree here) and agree to rounding. The remaining quantities (density, energy, stress, flaws ...) are uploaded or filled by
+ * the caller as IMaterial::create would. sphgpu_lattice_count tells how many particles the lattice has (about 6 % more
+ * than particle_count), so that the context can be created with the right capacity. */
+#define SPHGPU_LATTICE_CENTER 1u
+typedef struct sphgpu_lattice {
+    double center[3];
+    double radius;
+    uint32_t particle_count; /* BodySettingsId::PARTICLE_COUNT */
+    uint32_t flags;
+    double eta;              /* BodySettingsId::SMOOTHING_LENGTH_ETA */
+    double density;          /* BodySettingsId::DENSITY */
+    uint32_t body_flag;      /* value of QuantityId::FLAG (InitialConditions::bodyIndex) */
+    uint32_t reserved;
+} sphgpu_lattice;
+SPHGPU_API int sphgpu_lattice_count(int device, const sphgpu_lattice* cfg, uint32_t* count);
+SPHGPU_API int sphgpu_lattice_generate(sphgpu_ctx* ctx, const sphgpu_lattice* cfg, uint32_t first, uint32_t* count);
+
 /* ---- inspection (tests) --------------------------------------------------------------------------------- */
 
 /* Neighbour lists exactly as AsymmetricSolver::loop selects them (AsymmetricSolver.cpp:174-199), CSR:

@@ -112,6 +112,14 @@ class GravityStats(C.Structure):
     ]
 
 
+class Lattice(C.Structure):
+    _fields_ = [
+        ("center", C.c_double * 3), ("radius", C.c_double), ("particle_count", C.c_uint32), ("flags", C.c_uint32),
+        ("eta", C.c_double), ("density", C.c_double), ("body_flag", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+LATTICE_CENTER = 1
 GRAVITY_CONSTANT = 6.67408e-11  # Constants::gravity (core/physics/Constants.h)
 
 

@@ -8,3 +8,4 @@
 #include "transfer.cu"
 #include "halo.cu"
 #include "gravity.cu"
+#include "lattice.cu"

@@ -49,6 +49,22 @@ def _check(rc: int) -> None:
         raise SphGpuError(rc, load_library().sphgpu_last_error().decode(errors="replace"))
 
 
+def make_lattice(particle_count: int, radius: float, centre=(0.0, 0.0, 0.0), eta: float = 1.3, density: float = 2700.0,
+                 centred: bool = True, body_flag: int = 0) -> abi.Lattice:
+    lat = abi.Lattice()
+    lat.center[0], lat.center[1], lat.center[2] = centre
+    lat.radius, lat.particle_count, lat.eta, lat.density = radius, particle_count, eta, density
+    lat.flags, lat.body_flag = (abi.LATTICE_CENTER if centred else 0), body_flag
+    return lat
+
+
+def lattice_count(lat: abi.Lattice, device: int = 0) -> int:
+    """Number of particles HexagonalPacking yields for the body (sphgpu_lattice_count)."""
+    n = C.c_uint32(0)
+    _check(load_library().sphgpu_lattice_count(C.c_int(device), C.byref(lat), C.byref(n)))
+    return int(n.value)
+
+
 class Engine:
     """One device context (`sphgpu_ctx`): device-resident particle state + the hot-path kernels."""
 
@@ -217,6 +233,12 @@ class Engine:
         st = abi.Stats()
         _check(self.lib.sphgpu_integrate(self._ctx, C.c_double(t), C.byref(st)))
         return st
+
+    def lattice_generate(self, lat: abi.Lattice, first: int = 0) -> int:
+        """InitialConditions::addMonolithicBody on the device: positions, h, masses, flag of slots [first, first + count)."""
+        n = C.c_uint32(0)
+        _check(self.lib.sphgpu_lattice_generate(self._ctx, C.byref(lat), C.c_uint32(first), C.byref(n)))
+        return int(n.value)
 
     # -- self-gravity ------------------------------------------------------------------------------------------
     def gravity_configure(self, opening_angle: float = 0.5, order: int = 3, constant: float = abi.GRAVITY_CONSTANT,

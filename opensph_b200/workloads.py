@@ -4,7 +4,7 @@ fields so that every term of the collision preset does non-trivial work.
 
 Reference behaviour mirrored here (paths relative to the reference root):
   lattice           HexagonalPacking::generate, core/sph/initial/Distribution.cpp:126-200 (dx = 1.1 (V/n)^(1/3),
-                    dy = sqrt(3)/2 dx, dz = sqrt(6)/3 dx, z-outer/x-inner raster order, centred on the domain)
+                    dy = sqrt(3)/2 dx, dz = sqrt(6)/3 dx, z-outer/x-inner raster order; without the CENTER shift)
   h, masses         InitialConditions::setQuantities, core/sph/initial/Initial.cpp:308-333 (h *= eta; m ~ h^3, sum = rho0 V)
   basalt defaults   core/system/Settings.cpp:790-930
   run settings      SphJob::getDefaultSettings, core/run/jobs/SimulationJobs.cpp:195-232 (collision preset, gravity off)

@@ -1144,3 +1144,85 @@ void orc_gravity_multipole(const double* com, const double* mom, int order, cons
     acc[1] = a[1];
     acc[2] = a[2];
 }
+
+/* ---- initial conditions --------------------------------------------------------------------------------------------- */
+
+/* HexagonalPacking::generate (Distribution.cpp:126-200) inside a SphericalDomain (Domain.h:134-136), the loops of
+ * Box::iterateWithIndices (Box.h:182-195) with their running coordinate sums, the CENTER option (:186-198), then
+ * InitialConditions::setQuantities / getMasses (Initial.cpp:288-318). */
+uint32_t orc_hexagonal_sphere(uint32_t n, const double* center, double radius, int centred, double eta, double rho0, double* pos,
+    double* mass, uint32_t capacity) {
+    const double volume = 1.3333333333333333333333 * M_PI * (radius * radius * radius);
+    const double particleDensity = (double)n / volume;
+    const double h = 1. / cbrt(particleDensity);
+    const double dx = 1.1 * h;
+    const double dy = sqrt(3.) * 0.5 * dx;
+    const double dz = sqrt(6.) / 3. * dx;
+    const double lo[3] = { center[0] - radius + 0.5 * dx, center[1] - radius + 0.5 * dy, center[2] - radius + 0.5 * dz };
+    const double hi[3] = { center[0] + radius, center[1] + radius, center[2] + radius };
+    const double deltaX = 0.5 * dx;
+    const double deltaY = sqrt(3.) / 6. * dx;
+    uint32_t cnt = 0;
+    uint32_t i, j, k = 0;
+    for (double z = lo[2]; z <= hi[2]; z += dz, k++) {
+        j = 0;
+        for (double y = lo[1]; y <= hi[1]; y += dy, j++) {
+            i = 0;
+            for (double x = lo[0]; x <= hi[0]; x += dx, i++) {
+                double v[3] = { x, y, z };
+                if (k % 2 == 0) {
+                    if (j % 2 == 1) {
+                        v[0] += deltaX;
+                    }
+                } else {
+                    if (j % 2 == 0) {
+                        v[0] += deltaX;
+                    }
+                    v[1] += deltaY;
+                }
+                const double d[3] = { v[0] - center[0], v[1] - center[1], v[2] - center[2] };
+                if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= sqr(radius)) {
+                    if (pos && cnt < capacity) {
+                        pos[4 * cnt] = v[0];
+                        pos[4 * cnt + 1] = v[1];
+                        pos[4 * cnt + 2] = v[2];
+                        pos[4 * cnt + 3] = h;
+                    }
+                    cnt++;
+                }
+            }
+        }
+    }
+    if (!pos || cnt > capacity) {
+        return cnt;
+    }
+    if (centred) {
+        double com[3] = { 0., 0., 0. };
+        for (uint32_t p = 0; p < cnt; ++p) {
+            for (int a = 0; a < 3; ++a) {
+                com[a] += pos[4 * p + a];
+            }
+        }
+        for (int a = 0; a < 3; ++a) {
+            com[a] /= (double)cnt;
+        }
+        for (uint32_t p = 0; p < cnt; ++p) {
+            for (int a = 0; a < 3; ++a) {
+                pos[4 * p + a] += center[a] - com[a];
+            }
+        }
+    }
+    const double totalM = volume * rho0;
+    double prelimM = 0.;
+    for (uint32_t p = 0; p < cnt; ++p) {
+        pos[4 * p + 3] *= eta;
+        const double hp = pos[4 * p + 3];
+        mass[p] = hp * hp * hp;
+        prelimM += mass[p];
+    }
+    const double normalization = totalM / prelimM;
+    for (uint32_t p = 0; p < cnt; ++p) {
+        mass[p] *= normalization;
+    }
+    return cnt;
+}

@@ -170,3 +170,15 @@ def gravity_multipole(com: np.ndarray, mom: np.ndarray, order: int, point: np.nd
     lib().orc_gravity_multipole(com.ctypes.data_as(_D), mom.ctypes.data_as(_D), C.c_int(order), point.ctypes.data_as(_D),
                                 acc.ctypes.data_as(_D))
     return acc
+
+
+# ---- initial conditions (oracle/sph_oracle.c: orc_hexagonal_sphere) --------------------------------------------------
+def hexagonal_sphere(n: int, centre, radius: float, centred: bool = True, eta: float = 1.3, rho0: float = 2700.0):
+    """InitialConditions::addMonolithicBody (SphericalDomain, HexagonalPacking) restated in C: (pos [m, 4], mass [m])."""
+    lib().orc_hexagonal_sphere.restype = C.c_uint32
+    c = np.ascontiguousarray(centre, dtype=np.float64)
+    args = (C.c_uint32(n), c.ctypes.data_as(_D), C.c_double(radius), C.c_int(1 if centred else 0), C.c_double(eta), C.c_double(rho0))
+    m = lib().orc_hexagonal_sphere(*args, None, None, C.c_uint32(0))
+    pos, mass = np.zeros((m, 4)), np.zeros(m)
+    lib().orc_hexagonal_sphere(*args, pos.ctypes.data_as(_D), mass.ctypes.data_as(_D), C.c_uint32(m))
+    return pos, mass
