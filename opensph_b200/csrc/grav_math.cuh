@@ -156,6 +156,62 @@ SPH_HD void gravNodeAccel(const GravNode& n, double x, double y, double z, doubl
     az += fr * rz + fz;
 }
 
+/// The same expansion in single precision for the tree walk. The multipole approximation itself is good to 1e-3 .. 1e-5 of
+/// the field; rounding of 6e-8 per node does not show. FP32 runs at 64 times the FP64 rate on this device, so the far field
+/// costs next to nothing and the FP64 pipe is left to the exact particle pairs. To stay inside the FP32 range the walk works
+/// in scaled units (lengths in units of the bounding cube L, masses in units of the total mass M: every moment is <= 1)
+/// and with the unit vector n = r / d instead of high powers of r:
+///   a = m n / d^2  +  (7.5 (n.Q2 n) n - 3 Q2 n) / d^4  +  (7.5 Q3 n n - 17.5 (Q3 n n n) n) / d^5,   r = com - target.
+struct GravNodeF {
+    float rx, ry, rz, m; // centre of mass relative to the group's centre
+    float q2[5];
+    float q3[7];
+};
+
+template <int ORDER>
+SPH_HD void gravNodeAccelF(const GravNodeF& n, float ox, float oy, float oz, float& ax, float& ay, float& az) {
+    const float rx = n.rx - ox, ry = n.ry - oy, rz = n.rz - oz;
+    const float d2 = rx * rx + ry * ry + rz * rz;
+#ifdef __CUDA_ARCH__
+    const float inv = rsqrtf(d2);
+#else
+    const float inv = 1.f / sqrtf(d2);
+#endif
+    const float nx = rx * inv, ny = ry * inv, nz = rz * inv;
+    const float inv2 = inv * inv;
+    float cn = n.m * inv2; // coefficient of the unit vector
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (ORDER >= 2) {
+        const float inv4 = inv2 * inv2;
+        const float qzz = -n.q2[0] - n.q2[1];
+        const float qx = n.q2[0] * nx + n.q2[2] * ny + n.q2[3] * nz;
+        const float qy = n.q2[2] * nx + n.q2[1] * ny + n.q2[4] * nz;
+        const float qz = n.q2[3] * nx + n.q2[4] * ny + qzz * nz;
+        cn += 7.5f * inv4 * (qx * nx + qy * ny + qz * nz);
+        const float c2 = -3.f * inv4;
+        fx = c2 * qx;
+        fy = c2 * qy;
+        fz = c2 * qz;
+        if (ORDER >= 3) {
+            const float inv5 = inv4 * inv;
+            const float xxx = n.q3[0], xxy = n.q3[1], xxz = n.q3[2], xyy = n.q3[3], xyz = n.q3[4], yyy = n.q3[5], yyz = n.q3[6];
+            const float xzz = -xxx - xyy, yzz = -xxy - yyy, zzz = -xxz - yyz;
+            const float xx = nx * nx, yy = ny * ny, zz = nz * nz, xy = 2.f * nx * ny, xz = 2.f * nx * nz, yz = 2.f * ny * nz;
+            const float tx = xxx * xx + xyy * yy + xzz * zz + xxy * xy + xxz * xz + xyz * yz;
+            const float ty = xxy * xx + yyy * yy + yzz * zz + xyy * xy + xyz * xz + yyz * yz;
+            const float tz = xxz * xx + yyz * yy + zzz * zz + xyz * xy + xzz * xz + yzz * yz;
+            cn -= 17.5f * inv5 * (tx * nx + ty * ny + tz * nz);
+            const float c3 = 7.5f * inv5;
+            fx += c3 * tx;
+            fy += c3 * ty;
+            fz += c3 * tz;
+        }
+    }
+    ax += cn * nx + fx;
+    ay += cn * ny + fy;
+    az += cn * nz + fz;
+}
+
 /// Run-wide constants of the gravity path.
 struct GravParams {
     double thetaInv;       // 1 / opening angle

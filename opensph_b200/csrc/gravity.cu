@@ -13,12 +13,17 @@
 //   5. k_grav_moments  bottom-up (second arrival computes the parent): nodes of <= leafSize particles (the analogue of the
 //                      k-d tree's leaves) sum their particles directly like buildLeaf, larger nodes combine their two
 //                      children like buildInner; bounding boxes, centres of mass, opening radii, traceless moments
-//   6. k_grav_groups   target groups = the maximal nodes of <= 32 particles, in the order of the sorted particles
+//   6. target groups   the maximal nodes of <= 32 particles (marked by k_grav_moments, compacted in the order of the sorted
+//                      particles by cub::DeviceSelect)
 //   7. k_grav_walk     one warp per group, one target per lane: depth-first walk of the tree with a warp-wide stack in
 //                      shared memory, 32 nodes classified per trip with the reference's criterion for an evaluated leaf
 //                      (BarnesHut::evalNode): the opening ball of the node does not reach the group's box -> multipole
 //                      approximation, otherwise open it (or, for a leaf, sum its particles exactly). Accepted nodes and
-//                      particle ranges are staged in shared memory 32 at a time and applied to all lanes.
+//                      particle ranges are staged in shared memory 32 at a time and applied to all lanes. The exact
+//                      particle pairs are FP64 throughout; the multipole expansions of the accepted (distant) nodes are
+//                      evaluated in single precision relative to the group's centre and added to FP64 sums -- their
+//                      rounding (6e-8) is three orders below the error of the approximation itself, and the FP64 pipe,
+//                      which bounds this kernel, is left to the pairs.
 // Summation order is fixed by the tree, so results are reproducible from run to run.
 #include "grav_math.cuh"
 #include "sphgpu_internal.h"
@@ -329,12 +334,16 @@ __global__ void __launch_bounds__(128) k_grav_moments(GravDev g, GravParams prm)
             const int4 pm = g.meta[par];
             parCount = pm.w - pm.z + 1;
         }
+        // target groups: the maximal nodes of at most GRAV_GROUP particles (one per lane of the walk)
+        const bool isGroup = count <= GRAV_GROUP && parCount > GRAV_GROUP;
+        if (isGroup) {
+            g.groupAt[meta.z] = (uint32_t)cur;
+        }
         if (count <= leaf) {
-            if (parCount > leaf) { // a leaf of the gravity tree (and a target group)
+            if (parCount > leaf || isGroup) { // a leaf of the gravity tree (or a group inside one: it needs its box)
                 GravSummary s;
                 gravLeafSummary(g, meta.z, meta.w, s);
                 gravStoreNode(g, cur, s, prm, (uint32_t)count);
-                g.groupAt[meta.z] = (uint32_t)cur;
             }
         } else { // buildInner (BarnesHut.cpp:434-489)
             GravSummary a, b, s;
@@ -350,7 +359,8 @@ __global__ void __launch_bounds__(128) k_grav_moments(GravDev g, GravParams prm)
             gravRawAddShifted(s.raw, a.raw, a.m, a.com[0] - s.com[0], a.com[1] - s.com[1], a.com[2] - s.com[2]);
             gravRawAddShifted(s.raw, b.raw, b.m, b.com[0] - s.com[0], b.com[1] - s.com[1], b.com[2] - s.com[2]);
             gravStoreNode(g, cur, s, prm, (uint32_t)count);
-            // single particles hanging off a large node are groups of their own
+        }
+        if (count > GRAV_GROUP) { // single particles hanging off a larger node are groups of their own
             if (meta.x < 0) {
                 g.groupAt[~meta.x] = 0x80000000u | (uint32_t)(~meta.x);
             }
@@ -372,27 +382,49 @@ struct GravIsGroup {
 // ---- 7. the walk ----------------------------------------------------------------------------------------------------
 struct GravWarpShared {
     uint32_t stack[GRAV_STACK];
-    double nodeStage[32][16];     // 32 accepted nodes (GravNode)
+    float nodeStage[32][16];      // 32 accepted nodes (GravNodeF: relative to the group's centre, single precision)
     double partStage[5][32];      // x, y, z, h, m of a particle range
     uint32_t approx[64];          // accepted nodes waiting for a full batch
     uint2 exact[96];              // particle ranges {first, count} waiting
 };
 
+/// Applies `count` (<= 32) accepted nodes to all lanes. Lane l stages node l: centre of mass relative to the group's centre
+/// (FP64 subtraction, then single precision) and the moments; every lane then evaluates the expansion in single precision
+/// at its own offset from the group's centre and adds the batch to its FP64 sums.
 template <int ORDER>
-__device__ __forceinline__ void gravApplyNodes(const GravDev& g, GravWarpShared& w, int count, int lane, bool live, double x, double y, double z,
-    double& ax, double& ay, double& az) {
-    // cooperative load: 8 lanes fetch the 128 bytes of one node
-    const double2* src = reinterpret_cast<const double2*>(g.node);
-    double2* dst = reinterpret_cast<double2*>(&w.nodeStage[0][0]);
-    for (int e = lane; e < count * 8; e += 32) {
-        dst[e] = __ldg(src + (size_t)w.approx[e >> 3] * 8 + (e & 7));
+__device__ __forceinline__ void gravApplyNodes(const GravDev& g, GravWarpShared& w, int count, int lane, bool live, double gcx, double gcy, double gcz,
+    double invL, double invM, double accUnit, float ox, float oy, float oz, double& ax, double& ay, double& az) {
+    if (lane < count) {
+        const double* nd = reinterpret_cast<const double*>(g.node + w.approx[lane]); // GravNode: com, m, q2[5], q3[7]
+        float* dst = &w.nodeStage[lane][0];
+        dst[0] = (float)((__ldg(nd + 0) - gcx) * invL);
+        dst[1] = (float)((__ldg(nd + 1) - gcy) * invL);
+        dst[2] = (float)((__ldg(nd + 2) - gcz) * invL);
+        dst[3] = (float)(__ldg(nd + 3) * invM);
+        if (ORDER >= 2) {
+            const double s2 = invM * invL * invL, s3 = s2 * invL;
+#pragma unroll
+            for (int q = 4; q < 9; ++q) {
+                dst[q] = (float)(__ldg(nd + q) * s2);
+            }
+            if (ORDER >= 3) {
+#pragma unroll
+                for (int q = 9; q < 16; ++q) {
+                    dst[q] = (float)(__ldg(nd + q) * s3);
+                }
+            }
+        }
     }
     __syncwarp();
     if (live) {
+        float fx = 0.f, fy = 0.f, fz = 0.f;
         for (int k = 0; k < count; ++k) {
-            const GravNode& nd = *reinterpret_cast<const GravNode*>(&w.nodeStage[k][0]);
-            gravNodeAccel<ORDER>(nd, x, y, z, ax, ay, az);
+            const GravNodeF& nd = *reinterpret_cast<const GravNodeF*>(&w.nodeStage[k][0]);
+            gravNodeAccelF<ORDER>(nd, ox, oy, oz, fx, fy, fz);
         }
+        ax += (double)fx * accUnit;
+        ay += (double)fy * accUnit;
+        az += (double)fz * accUnit;
     }
     __syncwarp();
 }
@@ -426,6 +458,11 @@ __global__ void __launch_bounds__(GRAV_WARPS * 32) k_grav_walk(DevicePointers p,
     GravWarpShared& w = reinterpret_cast<GravWarpShared*>(gravSmem)[warp];
     const uint32_t nGroups = *g.groupCount;
     const uint32_t ltMask = (1u << lane) - 1u;
+    // units of the single-precision far field: the bounding cube and the total mass (GravNodeF)
+    const double invL = g.bounds[3] * (1. / 2097151.);
+    const double rootM = g.node[0].m;
+    const double invM = rootM > 0. ? 1. / rootM : 0.;
+    const double accUnit = rootM * invL * invL;
     unsigned long long nApprox = 0, nExact = 0;
     for (uint32_t gi = blockIdx.x * GRAV_WARPS + warp; gi < nGroups; gi += gridDim.x * GRAV_WARPS) {
         const uint32_t code = g.groups[gi];
@@ -456,6 +493,8 @@ __global__ void __launch_bounds__(GRAV_WARPS * 32) k_grav_walk(DevicePointers p,
             if (live) {
                 ri = g.spos[self];
             }
+            const double gcx = 0.5 * (lo[0] + hi[0]), gcy = 0.5 * (lo[1] + hi[1]), gcz = 0.5 * (lo[2] + hi[2]);
+            const float ox = (float)((ri.x - gcx) * invL), oy = (float)((ri.y - gcy) * invL), oz = (float)((ri.z - gcz) * invL);
             ax = ay = az = 0.;
             int sp = 0, nA = 0, nE = 0;
             if (lane == 0) {
@@ -527,7 +566,7 @@ __global__ void __launch_bounds__(GRAV_WARPS * 32) k_grav_walk(DevicePointers p,
                 nE += __popc(bE) + __popc(b1) + __popc(b2);
                 __syncwarp();
                 if (nA >= 32) {
-                    gravApplyNodes<ORDER>(g, w, 32, lane, live, ri.x, ri.y, ri.z, ax, ay, az);
+                    gravApplyNodes<ORDER>(g, w, 32, lane, live, gcx, gcy, gcz, invL, invM, accUnit, ox, oy, oz, ax, ay, az);
                     nApprox += 32;
                     const uint32_t keep = w.approx[32 + lane];
                     __syncwarp();
@@ -549,7 +588,7 @@ __global__ void __launch_bounds__(GRAV_WARPS * 32) k_grav_walk(DevicePointers p,
                 }
             }
             if (nA > 0) {
-                gravApplyNodes<ORDER>(g, w, nA, lane, live, ri.x, ri.y, ri.z, ax, ay, az);
+                gravApplyNodes<ORDER>(g, w, nA, lane, live, gcx, gcy, gcz, invL, invM, accUnit, ox, oy, oz, ax, ay, az);
                 nApprox += (unsigned long long)nA;
             }
             for (int k = 0; k < nE; ++k) {
