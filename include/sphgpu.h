@@ -51,8 +51,11 @@ enum {
     SPHGPU_FLAG_SUM_ONLY_UNDAMAGED = 1u << 1,   /* RunSettingsId::SPH_SUM_ONLY_UNDAMAGED                     */
     SPHGPU_FLAG_ADAPTIVE_H = 1u << 2,           /* SmoothingLengthEnum::CONTINUITY_EQUATION                  */
     SPHGPU_FLAG_SOUND_SPEED_ENFORCING = 1u << 3, /* SmoothingLengthEnum::SOUND_SPEED_ENFORCING               */
-    SPHGPU_FLAG_BALSARA = 1u << 4               /* RunSettingsId::SPH_AV_USE_BALSARA: BalsaraSwitch<StandardAV>,
+    SPHGPU_FLAG_BALSARA = 1u << 4,              /* RunSettingsId::SPH_AV_USE_BALSARA: BalsaraSwitch<StandardAV>,
                                                    core/sph/equations/av/Balsara.h:36-153                      */
+    SPHGPU_FLAG_XSPH = 1u << 5                  /* RunSettingsId::SPH_USE_XSPH: the XSph term, core/sph/equations/XSph.h:20-97;
+                                                   its epsilon is set with sphgpu_set_xsph_epsilon. Not together with
+                                                   SPHGPU_FLAG_BALSARA, not on decomposed runs                 */
 };
 enum { SPHGPU_DISCR_STANDARD = 0, SPHGPU_DISCR_BENZ_ASPHAUG = 1 };        /* DiscretizationEnum            */
 enum { SPHGPU_CONTINUITY_STANDARD = 0, SPHGPU_CONTINUITY_SUM_ONLY_UNDAMAGED = 1 }; /* ContinuityEnum       */
@@ -101,7 +104,8 @@ enum {
     SPHGPU_Q_MATERIAL_ID = 18,        /* u32  index into the materials passed to sphgpu_create; initialised from
                                          their [begin,end) ranges, must be uploaded for ghost particles      */
     SPHGPU_Q_VELOCITY_ROTATION = 19,  /* Vector {x,y,z,0}: nabla x v, input and output of the Balsara switch  */
-    SPHGPU_Q_COUNT = 20
+    SPHGPU_Q_XSPH_VELOCITIES = 20,    /* Vector {x,y,z,0}: the velocity correction the XSph term left in the velocities */
+    SPHGPU_Q_COUNT = 21
 };
 
 /* Host memory layouts understood by upload/download. */
@@ -380,6 +384,11 @@ SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
  * Default 0.03. sphgpu_list_stats: builds so far, calls served by the current lists, the metric seen by the last call
  * (values as of the last call that synchronised with the device). */
 SPHGPU_API int sphgpu_set_list_skin(sphgpu_ctx* ctx, double skin);
+/* RunSettingsId::SPH_XSPH_EPSILON of the XSph term (SPHGPU_FLAG_XSPH; XSph.h:36-38). XSph::initialize subtracts the
+ * correction of the previous evaluation from the velocities before the derivatives are evaluated, XSph::finalize adds the
+ * new one (XSph.h:69-90): sphgpu_integrate does both, so POSITION dt holds the corrected velocities between calls and
+ * SPHGPU_Q_XSPH_VELOCITIES the correction, exactly like the Storage of the reference. Default 1 (Settings.cpp). */
+SPHGPU_API int sphgpu_set_xsph_epsilon(sphgpu_ctx* ctx, double epsilon);
 SPHGPU_API int sphgpu_list_stats(sphgpu_ctx* ctx, uint32_t* rebuilds, uint32_t* age, double* metric);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
  * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the

@@ -46,6 +46,14 @@ static int validate(const sphgpu_config* cfg, const sphgpu_material* mats, uint3
     if (cfg->discretization != SPHGPU_DISCR_STANDARD) {
         return fail(SPHGPU_E_INVALID, "only DiscretizationEnum::STANDARD is implemented on the GPU path");
     }
+    if (cfg->flags & SPHGPU_FLAG_XSPH) {
+        if (!cfg->lut_value) {
+            return fail(SPHGPU_E_INVALID, "the XSph term needs the kernel value table (lut_value)");
+        }
+        if (cfg->flags & SPHGPU_FLAG_BALSARA) {
+            return fail(SPHGPU_E_INVALID, "the XSph term together with the Balsara switch is not implemented on the GPU path");
+        }
+    }
     if (!(cfg->forces & SPHGPU_FORCE_PRESSURE)) {
         return fail(SPHGPU_E_INVALID, "ForceEnum::PRESSURE is required (SolidStressForce is only added with it, StandardSets.cpp:24-33)");
     }
@@ -148,6 +156,8 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     ctx->solid = (cfg->forces & SPHGPU_FORCE_SOLID_STRESS) != 0;
     ctx->corrected = ctx->solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     ctx->balsara = (cfg->flags & SPHGPU_FLAG_BALSARA) != 0;
+    ctx->xsph = (cfg->flags & SPHGPU_FLAG_XSPH) != 0;
+    p.xsph_eps = 1.; // SPH_XSPH_EPSILON default (core/system/Settings.cpp); sphgpu_set_xsph_epsilon
     ctx->recDoubles = recordDoubles(ctx->solid, ctx->balsara);
     ctx->hasReduce = false;
     ctx->hasDamage = false;
@@ -261,6 +271,18 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         ctx->d.lut2 = lut2;
         SPH_TRY(wrap(cudaMemcpy(lut2, pairs.data(), sizeof(LutPair) * pairs.size(), cudaMemcpyHostToDevice), "LUT upload"));
     }
+    if (ctx->xsph) { // kernel values for the XSph term: LutKernel::valueImpl interpolates the same way (Kernel.h:111-127)
+        double* lutW = nullptr;
+        SPH_TRY(devAlloc(&lutW, (size_t)cfg->lut_entries + 2));
+        ctx->d.lutW = lutW;
+        SPH_TRY(wrap(cudaMemcpy(lutW, cfg->lut_value, sizeof(double) * ((size_t)cfg->lut_entries + 1), cudaMemcpyHostToDevice), "LUT upload"));
+        std::vector<LutPair> pairs((size_t)cfg->lut_entries + 1);
+        buildLutPairs(cfg->lut_value, cfg->lut_entries, pairs.data());
+        LutPair* lutW2 = nullptr;
+        SPH_TRY(devAlloc(&lutW2, pairs.size()));
+        ctx->d.lutW2 = lutW2;
+        SPH_TRY(wrap(cudaMemcpy(lutW2, pairs.data(), sizeof(LutPair) * pairs.size(), cudaMemcpyHostToDevice), "LUT upload"));
+    }
     SPH_TRY(wrap(cudaMalloc(&ctx->staging, std::max<size_t>(cap, 1) * 64), "staging"));
     // identity correction tensor and reduce = 1 by default (SolidStressForce::create, EquationTerm.cpp:215-218)
     {
@@ -299,7 +321,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
     cudaFree(ctx->d.dispA); cudaFree(ctx->d.dispB); cudaFree(ctx->d.dispC); cudaFree(ctx->d.dispGlobal);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
-    cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.statsInit); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree((void*)ctx->d.lut2); cudaFree(ctx->staging);
+    cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.statsInit); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree((void*)ctx->d.lut2); cudaFree((void*)ctx->d.lutW); cudaFree((void*)ctx->d.lutW2); cudaFree(ctx->staging);
     for (int k = 0; k < 8; ++k) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
         if (k < 4 && ctx->evPair[k]) cudaEventDestroy(ctx->evPair[k]);
@@ -646,6 +668,16 @@ int sphgpu_integrate(sphgpu_ctx* ctx, double t, sphgpu_stats* stats) {
     int rc = enqueueIntegrate(ctx);
     if (rc != SPHGPU_OK) return rc;
     return collectStats(ctx, stats, ctx->ev[0], ctx->ev[3]);
+}
+
+int sphgpu_set_xsph_epsilon(sphgpu_ctx* ctx, double epsilon) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (!ctx->xsph) return fail(SPHGPU_E_STATE, "the context was created without SPHGPU_FLAG_XSPH");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->prm.xsph_eps = epsilon;
+    forgetConstants(ctx); // uploaded again by the next call
+    return SPHGPU_OK;
 }
 
 int sphgpu_step_predict(sphgpu_ctx* ctx, double dt) {

@@ -117,8 +117,17 @@ __global__ void __launch_bounds__(256, PROLOGUE_MIN_CTAS) k_prologue_pack(Device
         d.posF[t] = pf;
         d.pos0[i] = pf; // ... and the reference point of the displacement check (k_bounds)
     }
-    rec[2 ^ sw] = make_double2(d.f[F_VX][i], d.f[F_VY][i]);
-    rec[3 ^ sw] = make_double2(d.f[F_VZ][i], rho);
+    double vx = d.f[F_VX][i], vy = d.f[F_VY][i], vz = d.f[F_VZ][i];
+    if (c_prm.flags & SPHGPU_FLAG_XSPH) { // XSph::initialize (XSph.h:69-79): take the previous correction out of the velocities
+        vx -= d.f[F_XSX][i];
+        vy -= d.f[F_XSY][i];
+        vz -= d.f[F_XSZ][i];
+        d.f[F_VX][i] = vx;
+        d.f[F_VY][i] = vy;
+        d.f[F_VZ][i] = vz;
+    }
+    rec[2 ^ sw] = make_double2(vx, vy);
+    rec[3 ^ sw] = make_double2(vz, rho);
     if (SOLID) {
         const uint32_t flag = d.u[U_FLAG][i];
         if (flag >= GROUP_FLAG_LIMIT) {
@@ -196,6 +205,16 @@ __device__ __forceinline__ void loadSortedPosition(const double* __restrict__ re
     const uint32_t sw = recordSwizzle(recDoubles, t);
     pxy = r[0 ^ sw];
     pzh = r[1 ^ sw];
+}
+
+/// XSph::finalize (XSph.h:81-90): the new correction is stored and added to the velocity (which the prologue left pure).
+__device__ __forceinline__ void storeXsph(const DevicePointers& d, uint32_t i, const double xs[3]) {
+    d.f[F_XSX][i] = xs[0];
+    d.f[F_XSY][i] = xs[1];
+    d.f[F_XSZ][i] = xs[2];
+    d.f[F_VX][i] += xs[0];
+    d.f[F_VY][i] += xs[1];
+    d.f[F_VZ][i] += xs[2];
 }
 
 template <bool SOLID, bool CORRECTED>
@@ -279,7 +298,7 @@ __device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t
                 }
                 Particle pj;
                 loadSorted<SOLID>(d, k, pj);
-                pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+                pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, d.lutW, pi, pj, dx, dy, dz, d2, hbar, acc);
             }
         }
     }
@@ -293,6 +312,9 @@ __device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t
     Derivs out;
     finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][i], d.f[F_CS][i], SOLID ? d.f[F_REDUCE][i] : 1., S, out);
     storeDerivs<SOLID, CORRECTED>(d, i, out);
+    if (c_prm.flags & SPHGPU_FLAG_XSPH) {
+        storeXsph(d, i, acc.xs);
+    }
     // neighbour statistics (AsymmetricSolver.cpp:218-225); the callers' warps are divergent here, so plain atomics
     atomicMin(&d.stats->neighMin, acc.cnt);
     atomicMax(&d.stats->neighMax, acc.cnt);
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(128) k_large_neighbours(DevicePointers d, uint
             }
             Particle pj;
             loadSorted<SOLID>(d, k, pj);
-            pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+            pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, d.lutW, pi, pj, dx, dy, dz, d2, hbar, acc);
         }
         d.accLarge[t] = acc;
     }
@@ -387,7 +409,7 @@ __global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_
             }
             Particle pj;
             loadSorted<SOLID>(d, k, pj);
-            pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, pi, pj, dx, dy, dz, d2, hbar, acc);
+            pairAccumulate<SOLID, CORRECTED, FILTER>(c_prm, d.lut, d.lutW, pi, pj, dx, dy, dz, d2, hbar, acc);
         }
         // fixed-order reduction inside the CTA: lanes by shuffle, warps through shared memory
         double* a = reinterpret_cast<double*>(&acc);
@@ -443,6 +465,9 @@ __global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_
                 Derivs out;
                 finalizeParticle<SOLID, CORRECTED>(c_prm, mat, sum, pi.h, pi.rho, d.f[F_P][i], d.f[F_CS][i], SOLID ? d.f[F_REDUCE][i] : 1., Sv, out);
                 storeDerivs<SOLID, CORRECTED>(d, i, out);
+                if (c_prm.flags & SPHGPU_FLAG_XSPH) {
+                    storeXsph(d, i, sum.xs);
+                }
                 atomicMin(&d.stats->neighMin, sum.cnt);
                 atomicMax(&d.stats->neighMax, sum.cnt);
                 atomicAdd(&d.stats->pairCount, (unsigned long long)sum.cnt);

@@ -657,8 +657,11 @@ __device__ __forceinline__ void emitList(uint32_t listOwn, uint32_t cnt, uint32_
 }
 
 /// Finalizers + stores of one target (shared with the direct variant) and the neighbour statistics of the warp.
-template <bool SOLID, bool CORRECTED>
+template <bool SOLID, bool CORRECTED, bool XSPH = false>
 __device__ __forceinline__ void finishTarget(const DevicePointers& d, const UnitLane& u, const Particle& pi, const Accum& acc) {
+    if (XSPH && u.target) { // (compile-time: the sums of the XSph term stay dead registers in the other instantiations)
+        storeXsph(d, u.slot, acc.xs);
+    }
     if (u.target) {
         const uint32_t slot = u.slot;
         const MaterialDev& mat = c_mats[d.u[U_MATID][slot]];
@@ -885,8 +888,8 @@ __device__ __forceinline__ void stageA(uint32_t stage, uint32_t k, uint32_t self
 }
 
 /// Stage B: the rest of the record and the sums.
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA>
-__device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Accum& acc) {
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH>
+__device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Accum& acc, const LutPair* lutW2) {
     using P = SumLayout<SOLID, BALSARA>;
     Particle pj;
     pj.vz = s.vz;
@@ -925,10 +928,15 @@ __device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Ac
         }
     }
     pj.m = pj.vol * pj.rho;
-    pairSums<SOLID, CORRECTED, FILTER, BALSARA>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc);
+    double W = 0.;
+    if (XSPH) { // kernel value of the XSph term: same index and weight as the gradient table
+        const double2 w = __ldg(reinterpret_cast<const double2*>(lutW2) + s.g.k);
+        W = fma(s.g.ratio, w.y, w.x);
+    }
+    pairSums<SOLID, CORRECTED, FILTER, BALSARA, XSPH>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc, W);
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH>
 __global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA>::CTAS_PER_SM)) k_pair_sum(DevicePointers d, uint32_t maxCells) {
     using P = SumLayout<SOLID, BALSARA>;
     extern __shared__ __align__(128) unsigned char smemStage[];
@@ -1051,7 +1059,7 @@ __global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA>::CTAS_PER_S
                 prefetchBlock(nextOff);
             }
             if (!fallback) {
-                finishTarget<SOLID, CORRECTED>(d, u, pi, acc); // overlaps with the copies
+                finishTarget<SOLID, CORRECTED, XSPH>(d, u, pi, acc); // overlaps with the copies
             }
             if (nextUnit >= totalUnits) {
                 break;
@@ -1100,22 +1108,22 @@ __global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA>::CTAS_PER_S
                 uint2 nxt = make_uint2(0u, 0u);
                 loadGlobalU2If(q + 4u < cnt, quads, nxt);
                 stageA<P>(stage, cur.x >> 16, selfIdx, pi, d.lut2, s1);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s0, pi, acc);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH>(s0, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
                 stageA<P>(stage, cur.y & 0xffffu, selfIdx, pi, d.lut2, s0);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s1, pi, acc);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH>(s1, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
                 stageA<P>(stage, cur.y >> 16, selfIdx, pi, d.lut2, s1);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s0, pi, acc);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH>(s0, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
                 stageA<P>(stage, nxt.x & 0xffffu, selfIdx, pi, d.lut2, s0);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA>(s1, pi, acc);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH>(s1, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
@@ -1198,9 +1206,9 @@ static int launchLists(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH>
 static int launchSumVariantB(sphgpu_ctx* ctx) {
-    auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER, BALSARA>;
+    auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER, BALSARA, XSPH>;
     static bool configured[64] = {}; // per instantiation and device; the attribute is per device function
     const size_t smem = SumLayout<SOLID, BALSARA>::bytes;
     if (!configured[ctx->device & 63]) {
@@ -1217,7 +1225,10 @@ static int launchSumVariantB(sphgpu_ctx* ctx) {
 
 template <bool SOLID, bool CORRECTED, bool FILTER>
 static int launchSumVariant(sphgpu_ctx* ctx) {
-    return ctx->balsara ? launchSumVariantB<SOLID, CORRECTED, FILTER, true>(ctx) : launchSumVariantB<SOLID, CORRECTED, FILTER, false>(ctx);
+    if (ctx->xsph) { // (not together with the Balsara switch: rejected by sphgpu_create)
+        return launchSumVariantB<SOLID, CORRECTED, FILTER, false, true>(ctx);
+    }
+    return ctx->balsara ? launchSumVariantB<SOLID, CORRECTED, FILTER, true, false>(ctx) : launchSumVariantB<SOLID, CORRECTED, FILTER, false, false>(ctx);
 }
 
 template <bool SOLID, bool CORRECTED, bool FILTER>

@@ -52,6 +52,7 @@ struct ParamsDev {
     double h_min, h_max, neigh_enforcing, neigh_lower, neigh_upper;
     uint32_t criteria, n_materials;
     double courant, derivative_factor, divergence_factor;
+    double xsph_eps; // SPH_XSPH_EPSILON (SPHGPU_FLAG_XSPH)
 };
 
 SPH_HD double sqr(double x) {
@@ -252,6 +253,7 @@ struct Accum {
     double Cm[6];
     double F[3]; // sum of the stress-weighted kernel gradients m_j gradW (pairSums): the target's own Sr is applied once
     double rot[3]; // sum m_j gradW x (v_j - v_i)  (VelocityRotation, DerivativeHelpers.h:374-395; Balsara switch only)
+    double xs[3];  // sum m_j eps (v_j - v_i) W_ij / rhobar  (XSph::Derivative, XSph.h:55-63; XSph term only)
     uint32_t cnt;
 };
 
@@ -265,6 +267,7 @@ SPH_HD void accumZero(Accum& a) {
     }
     a.F[0] = a.F[1] = a.F[2] = 0.;
     a.rot[0] = a.rot[1] = a.rot[2] = 0.;
+    a.xs[0] = a.xs[1] = a.xs[2] = 0.;
     a.cnt = 0;
 }
 
@@ -352,13 +355,13 @@ SPH_HD void unpackCsGroup(double packed, double& cs, int& grp) {
 /// One directed pair i <- j. `lut` is the (dW/dq)/q table. SOLID adds velocity gradient + stress divergence (with the
 /// undamaged filter when FILTER), CORRECTED adds the correction-tensor sums.
 template <bool SOLID, bool CORRECTED, bool FILTER>
-SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut, const Particle& pi, const Particle& pj,
-    double dx, double dy, double dz, double d2, double hbar, Accum& acc) {
+SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut, const double* __restrict__ lutW, const Particle& pi,
+    const Particle& pj, double dx, double dy, double dz, double d2, double hbar, Accum& acc) {
     acc.cnt++;
     const double hInv = 1. / hbar;
     const double hInv2 = hInv * hInv;
     const double qSqr = d2 * hInv2;
-    double G = 0.;
+    double G = 0., W = 0.;
     if (qSqr < prm.radius_sqr) {
         const double fidx = prm.q_sqr_to_idx * qSqr;
         const uint32_t k = (uint32_t)fidx;
@@ -369,6 +372,16 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
         const double g0 = lut[k], g1 = lut[k + 1];
 #endif
         G = g0 * (1. - ratio) + g1 * ratio;
+        if (prm.flags & SPHGPU_FLAG_XSPH) { // LutKernel::valueImpl (Kernel.h:111-127)
+            W = lutW[k] * (1. - ratio) + lutW[k + 1] * ratio;
+        }
+    }
+    if (prm.flags & SPHGPU_FLAG_XSPH) {
+        // XSph::Derivative::eval (XSph.h:55-63): f = eps (v_j - v_i) / rhobar W(r_i, r_j), W = hbar^-3 W(q^2); dr_i += m_j f
+        const double c = pj.m * (prm.xsph_eps * (hInv2 * hInv * W) / (0.5 * (pi.rho + pj.rho)));
+        acc.xs[0] += c * (pj.vx - pi.vx);
+        acc.xs[1] += c * (pj.vy - pi.vy);
+        acc.xs[2] += c * (pj.vz - pi.vz);
     }
     const double s = hInv2 * hInv2 * hInv * G; // h^-5 * (dW/dq)/q
     const double gx = dx * s, gy = dy * s, gz = dz * s;
@@ -513,10 +526,16 @@ SPH_HD void pairGeometry(const ParamsDev& prm, double xi, double yi, double zi, 
 /// Stage B. G = the interpolated table value g + ratio dg of entry g.k. Of pi only v, P, cs, grp are read; of pj v, m,
 /// P, cs, vol, Sr, grp. The stress sum is split: sum_j (Sr_i + Sr_j) f_j = Sr_i F + sum_j Sr_j f_j with F = sum_j f_j
 /// (acc.F, applied by finalizeParticle), which saves the target's Sr registers and two additions per pair.
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false>
-SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& pj, const PairGeom& g, double G, Accum& acc) {
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false, bool XSPH = false>
+SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& pj, const PairGeom& g, double G, Accum& acc, double W = 0.) {
     acc.cnt += g.valid ? 1u : 0u;
     const double mj = selectD(g.valid, pj.m, 0.);
+    if (XSPH) { // W = table value of the kernel at q^2; hbar^-3 = hbar^-5 hbar^2; 1 / rhobar = 2 / (rho_i + rho_j)
+        const double c = mj * ((2. * prm.xsph_eps) * W) * ((g.hInv5 * g.hbar) * g.hbar) * g.irs;
+        acc.xs[0] = fma(c, pj.vx - pi.vx, acc.xs[0]);
+        acc.xs[1] = fma(c, pj.vy - pi.vy, acc.xs[1]);
+        acc.xs[2] = fma(c, pj.vz - pi.vz, acc.xs[2]);
+    }
     const double s = g.hInv5 * G; // gradW = s d
     const double dx = g.dx, dy = g.dy, dz = g.dz;
     const double dvx = pj.vx - pi.vx, dvy = pj.vy - pi.vy, dvz = pj.vz - pi.vz;
@@ -586,11 +605,13 @@ SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& p
 /// Both stages for one pair (host formula tests).
 template <bool SOLID, bool CORRECTED, bool FILTER>
 SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const LutPair* __restrict__ lut2, const Particle& pi, const Particle& pj,
-    Accum& acc) {
+    Accum& acc, const LutPair* __restrict__ lutW2 = nullptr) {
     PairGeom g;
     pairGeometry(prm, pi.x, pi.y, pi.z, pi.h, pi.rho, pj.x, pj.y, pj.z, pj.h, pj.rho, g);
     const double G = fma(g.ratio, lut2[g.k].dg, lut2[g.k].g);
-    if (prm.flags & SPHGPU_FLAG_BALSARA) {
+    if (prm.flags & SPHGPU_FLAG_XSPH) {
+        pairSums<SOLID, CORRECTED, FILTER, false, true>(prm, pi, pj, g, G, acc, fma(g.ratio, lutW2[g.k].dg, lutW2[g.k].g));
+    } else if (prm.flags & SPHGPU_FLAG_BALSARA) {
         pairSums<SOLID, CORRECTED, FILTER, true>(prm, pi, pj, g, G, acc);
     } else {
         pairSums<SOLID, CORRECTED, FILTER, false>(prm, pi, pj, g, G, acc);
@@ -601,6 +622,7 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const LutPair* __restrict
 struct Derivs {
     double ax, ay, az, vh, du, drho, divv;
     double rot[3];
+    double xs[3];
     double dS[5];
     double gradv[6];
     double corr[6];

@@ -29,6 +29,7 @@ enum Field : int {
     // PredictorCorrector "predictions": copies of the highest derivatives (TimeStepping.cpp:272-282)
     F_AXP, F_AYP, F_AZP, F_DRHOP, F_DUP, F_DSP0, F_DSP1, F_DSP2, F_DSP3, F_DSP4, F_DDP,
     F_ROTX, F_ROTY, F_ROTZ,       // VELOCITY_ROTATION (Balsara switch): result of the last evaluation, input of the next
+    F_XSX, F_XSY, F_XSZ,          // XSPH_VELOCITIES (XSph term): the correction currently contained in the velocities
     F_COUNT
 };
 
@@ -155,6 +156,8 @@ struct DevicePointers {
     double* boundsPartial; // [BOUNDS_BLOCKS * 8]
     const double* lut;          // (dW/dq)/q table of the reference, lut_entries + 2 doubles (direct variant)
     const LutPair* lut2;        // the same table as {G[k], G[k+1] - G[k]} pairs, lut_entries + 1 entries (tiled kernels)
+    const double* lutW;         // kernel values W(q^2), lut_entries + 2 doubles (XSph term, direct variant)
+    const LutPair* lutW2;       // the same as pairs (XSph term, tiled kernels)
     GridDev* grid;
     StatsDev* stats;
     StatsDev* statsInit;       // constant {min = ~0, 0, ...}: copied over stats at the start of every integrate()
@@ -179,7 +182,7 @@ struct sphgpu_ctx {
     sph::MaterialDev matsHost[sph::MAX_MATERIALS];
     sphgpu_material matsApi[sph::MAX_MATERIALS];
     uint32_t nMaterials = 0;
-    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false;
+    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false, xsph = false;
     int recDoubles = sph::REC_FLUID; // doubles per sorted neighbour record of this context
     sph::DevicePointers d{};
     void* staging = nullptr;   // device staging for AoS <-> SoA repack (capacity * 64 B)

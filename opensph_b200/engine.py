@@ -77,6 +77,8 @@ class Engine:
         self._ctx = C.c_void_p()
         _check(self.lib.sphgpu_create(C.byref(setup.cfg), setup.materials, C.c_uint32(setup.n_materials),
                                       C.c_uint32(self.n), C.c_uint32(self.capacity), C.c_int(device), C.byref(self._ctx)))
+        if setup.cfg.flags & abi.FLAG_XSPH:
+            _check(self.lib.sphgpu_set_xsph_epsilon(self._ctx, C.c_double(getattr(setup, "xsph_eps", 1.0))))
 
     # -- lifetime ----------------------------------------------------------------------------------------------
     def close(self) -> None:

@@ -11,7 +11,7 @@
 // Commands
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
 //                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
-//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--criteria MASK]
+//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--xsph [EPS]] [--criteria MASK]
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
@@ -205,6 +205,12 @@ RunSettings makeSettings(const std::string& config, const Args& args) {
     if (args.has("balsara")) { // BalsaraSwitch<StandardAV> (core/sph/equations/av/Balsara.h)
         settings.set(RunSettingsId::SPH_AV_USE_BALSARA, true);
     }
+    if (args.has("xsph")) { // the XSph term (core/sph/equations/XSph.h), first term of getStandardEquations
+        settings.set(RunSettingsId::SPH_USE_XSPH, true);
+        if (args.str("xsph") != "1") {
+            settings.set(RunSettingsId::SPH_XSPH_EPSILON, Float(atof(args.str("xsph").c_str())));
+        }
+    }
     if (args.has("sum-all")) { // SPH_SUM_ONLY_UNDAMAGED = false: no undamaged filter
         settings.set(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED, false);
     }
@@ -357,6 +363,9 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
     if (storage.has(QuantityId::VELOCITY_GRADIENT)) {
         w.addF64("gradv", st6(storage.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT)), 6);
     }
+    if (storage.has(QuantityId::XSPH_VELOCITIES)) {
+        w.addF64("xsph", vec4(storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)), 4);
+    }
     if (storage.has(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)) {
         w.addF64("corr", st6(storage.getValue<SymmetricTensor>(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)), 6);
     }
@@ -431,6 +440,8 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
         double(int(settings.get<SolverEnum>(RunSettingsId::SPH_SOLVER_TYPE))),
         double(int(settings.get<TimesteppingEnum>(RunSettingsId::TIMESTEPPING_INTEGRATOR))),
         double(settings.get<bool>(RunSettingsId::SPH_AV_USE_BALSARA)),
+        double(settings.get<bool>(RunSettingsId::SPH_USE_XSPH)),
+        settings.get<Float>(RunSettingsId::SPH_XSPH_EPSILON),
     };
     w.addF64("run_params", run, 1);
 

@@ -97,6 +97,22 @@ static void kernel_grad(const sphgpu_config* cfg, const double* ri, const double
     }
 }
 
+/* LutKernel::valueImpl (Kernel.h:111-127) and Kernel::value with symmetrised smoothing lengths (Kernel.h:26-30,635-638) */
+static double kernel_value(const sphgpu_config* cfg, const double* ri, const double* rj) {
+    const double h = 0.5 * (ri[3] + rj[3]);
+    const double d[3] = { ri[0] - rj[0], ri[1] - rj[1], ri[2] - rj[2] };
+    const double hInv = 1. / h;
+    const double qSqr = (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) * sqr(hInv);
+    const double rad = cfg->kernel_radius;
+    if (qSqr >= sqr(rad)) {
+        return 0.;
+    }
+    const double floatIdx = (double)cfg->lut_entries * (1. / (rad * rad)) * qSqr;
+    const uint32_t idx1 = (uint32_t)floatIdx;
+    const double ratio = floatIdx - (double)idx1;
+    return hInv * hInv * hInv * (cfg->lut_value[idx1] * (1. - ratio) + cfg->lut_value[idx1 + 1] * ratio);
+}
+
 /* ---- neighbour search ------------------------------------------------------------------------------------ */
 
 typedef struct {
@@ -432,6 +448,16 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
         }
     }
 
+    /* XSph::initialize (XSph.h:69-79; the first term of getStandardEquations): remove the previous correction */
+    const int xsph = (cfg->flags & SPHGPU_FLAG_XSPH) != 0;
+    if (xsph) {
+        for (uint32_t i = 0; i < n; ++i) {
+            for (int q = 0; q < 3; ++q) {
+                s->vel[4 * (size_t)i + q] -= s->xsph[4 * (size_t)i + q];
+            }
+        }
+    }
+
     /* Accumulated buffers start zeroed (Accumulated::initialize, core/sph/equations/Accumulated.cpp:40-60) */
     for (uint32_t i = 0; i < n; ++i) {
         s->acc[4 * (size_t)i] = s->acc[4 * (size_t)i + 1] = s->acc[4 * (size_t)i + 2] = s->acc[4 * (size_t)i + 3] = 0.;
@@ -606,6 +632,23 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
                 }
                 du += s->mass[j] * heating;
             }
+            /* XSph::Derivative::eval, XSph.h:55-63 (written to its own buffer: the velocities stay pure during the loop) */
+            if (xsph) {
+                double xs[3] = { 0., 0., 0. };
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const uint32_t j = neighs[k];
+                    const double* vj = s->vel + 4 * (size_t)j;
+                    const double w = kernel_value(cfg, ri, s->pos + 4 * (size_t)j);
+                    for (int q = 0; q < 3; ++q) {
+                        const double f = s->xsph_eps * (vj[q] - vi[q]) / (0.5 * (s->rho[i] + s->rho[j])) * w;
+                        xs[q] += s->mass[j] * f;
+                    }
+                }
+                for (int q = 0; q < 3; ++q) {
+                    s->xsph[4 * (size_t)i + q] = xs[q];
+                }
+                s->xsph[4 * (size_t)i + 3] = 0.;
+            }
             s->acc[4 * (size_t)i + 0] = dv[0];
             s->acc[4 * (size_t)i + 1] = dv[1];
             s->acc[4 * (size_t)i + 2] = dv[2];
@@ -617,6 +660,15 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
     }
     grid_free(&g);
 
+    /* XSph::finalize (XSph.h:81-90): the new correction joins the velocities (the loop above read pure velocities only:
+     * every thread wrote xsph of its own particle and nobody read it) */
+    if (xsph) {
+        for (uint32_t i = 0; i < n; ++i) {
+            for (int q = 0; q < 3; ++q) {
+                s->vel[4 * (size_t)i + q] += s->xsph[4 * (size_t)i + q];
+            }
+        }
+    }
     /* afterLoop -> equations.finalize in REVERSE term order (EquationTerm.h:293-297); term order from
      * getStandardEquations (StandardSets.cpp:24-92): Pressure, SolidStress, Continuity, AV, SmoothingLength. */
     for (uint32_t i = 0; i < n; ++i) {

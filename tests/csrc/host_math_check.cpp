@@ -9,7 +9,8 @@ using namespace sph;
 
 template <bool SOLID, bool CORRECTED, bool FILTER, bool MASKED>
 static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDev>& mats, const std::vector<uint32_t>& matid,
-    const double* lut, const LutPair* lut2, const uint64_t* off, const uint32_t* idx, bool hasReduce, bool hasDamage) {
+    const double* lut, const LutPair* lut2, const double* lutW, const LutPair* lutW2, const uint64_t* off, const uint32_t* idx, bool hasReduce,
+    bool hasDamage) {
     const uint32_t n = s->n;
     std::vector<Particle> P(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -40,6 +41,9 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         }
         Particle& q = P[i];
         q.x = s->pos[4 * (size_t)i]; q.y = s->pos[4 * (size_t)i + 1]; q.z = s->pos[4 * (size_t)i + 2]; q.h = s->pos[4 * (size_t)i + 3];
+        if (prm.flags & SPHGPU_FLAG_XSPH) { // k_prologue_pack: XSph::initialize
+            for (int k = 0; k < 3; ++k) s->vel[4 * (size_t)i + k] -= s->xsph[4 * (size_t)i + k];
+        }
         q.vx = s->vel[4 * (size_t)i]; q.vy = s->vel[4 * (size_t)i + 1]; q.vz = s->vel[4 * (size_t)i + 2];
         q.m = s->mass[i]; q.rho = s->rho[i]; q.cs = cs;
         const double r2 = 1. / (q.rho * q.rho);
@@ -51,6 +55,7 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
             q.m = q.vol * q.rho;
         }
     }
+    std::vector<double> xsNew((prm.flags & SPHGPU_FLAG_XSPH) ? 3 * (size_t)n : 0);
     for (uint32_t i = 0; i < n; ++i) {
         Accum acc;
         accumZero(acc);
@@ -61,9 +66,9 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
             const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar, sq);
             if (MASKED) {
                 // the tiled kernel's branch-free body; also fed one non-neighbour per target to exercise the masking
-                pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut2, P[i], pj, acc);
+                pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut2, P[i], pj, acc, lutW2);
             } else if (valid) {
-                pairAccumulate<SOLID, CORRECTED, FILTER>(prm, lut, P[i], pj, dx, dy, dz, d2, hbar, acc);
+                pairAccumulate<SOLID, CORRECTED, FILTER>(prm, lut, lutW, P[i], pj, dx, dy, dz, d2, hbar, acc);
             }
         }
         if (MASKED) {
@@ -71,7 +76,7 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
             const double dx = P[i].x - pj.x, dy = P[i].y - pj.y, dz = P[i].z - pj.z;
             double d2, hbar, sq[4];
             const bool valid = isNeighbour(dx, dy, dz, P[i].h, pj.h, prm.kernel_radius, d2, hbar, sq);
-            if (!valid) pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut2, P[i], pj, acc);
+            if (!valid) pairAccumulateMasked<SOLID, CORRECTED, FILTER>(prm, lut2, P[i], pj, acc, lutW2);
         }
         double S[5] = { 0, 0, 0, 0, 0 };
         if (SOLID) {
@@ -82,6 +87,12 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         s->acc[4 * (size_t)i] = o.ax; s->acc[4 * (size_t)i + 1] = o.ay; s->acc[4 * (size_t)i + 2] = o.az; s->acc[4 * (size_t)i + 3] = 0.;
         s->vel[4 * (size_t)i + 3] = o.vh;
         s->du[i] = o.du; s->drho[i] = o.drho; s->divv[i] = o.divv; s->ncnt[i] = o.ncnt;
+        if (prm.flags & SPHGPU_FLAG_XSPH) { // storeXsph: XSph::finalize
+            for (int k = 0; k < 3; ++k) {
+                s->xsph[4 * (size_t)i + k] = acc.xs[k];
+                xsNew[3 * (size_t)i + k] = acc.xs[k];
+            }
+        }
         if (SOLID) {
             for (int k = 0; k < 5; ++k) s->dS[5 * (size_t)i + k] = o.dS[k];
             for (int k = 0; k < 6; ++k) s->gradv[6 * (size_t)i + k] = o.gradv[k];
@@ -89,6 +100,9 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
                 for (int k = 0; k < 6; ++k) s->corr[6 * (size_t)i + k] = o.corr[k];
             }
         }
+    }
+    for (size_t k = 0; k < xsNew.size(); ++k) {
+        s->vel[4 * (k / 3) + k % 3] += xsNew[k];
     }
 }
 
@@ -125,14 +139,26 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
     std::vector<LutPair> lutPairs(cfg->lut_entries + 1);
     buildLutPairs(cfg->lut_grad, cfg->lut_entries, lutPairs.data());
     const LutPair* lut2 = lutPairs.data();
+    // kernel values for the XSph term (api.cu uploads them the same way)
+    std::vector<double> lutWGuard;
+    std::vector<LutPair> lutWPairs;
+    if (cfg->flags & SPHGPU_FLAG_XSPH) {
+        lutWGuard.assign(cfg->lut_value, cfg->lut_value + cfg->lut_entries + 1);
+        lutWGuard.push_back(0.);
+        lutWPairs.resize(cfg->lut_entries + 1);
+        buildLutPairs(cfg->lut_value, cfg->lut_entries, lutWPairs.data());
+    }
+    const double* lutWPtr = lutWGuard.data();
+    const LutPair* lutW2 = lutWPairs.data();
+    prm.xsph_eps = s->xsph_eps;
     const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
     const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;
-    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
-    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
-    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
-    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
-    else run<true, false, false, MASKED>(s, prm, md, matid, lutPtr, lut2, off, idx, hasReduce, hasDamage);
+    if (!solid) run<false, false, false, MASKED>(s, prm, md, matid, lutPtr, lut2, lutWPtr, lutW2, off, idx, hasReduce, hasDamage);
+    else if (corrected && filter) run<true, true, true, MASKED>(s, prm, md, matid, lutPtr, lut2, lutWPtr, lutW2, off, idx, hasReduce, hasDamage);
+    else if (corrected) run<true, true, false, MASKED>(s, prm, md, matid, lutPtr, lut2, lutWPtr, lutW2, off, idx, hasReduce, hasDamage);
+    else if (filter) run<true, false, true, MASKED>(s, prm, md, matid, lutPtr, lut2, lutWPtr, lutW2, off, idx, hasReduce, hasDamage);
+    else run<true, false, false, MASKED>(s, prm, md, matid, lutPtr, lut2, lutWPtr, lutW2, off, idx, hasReduce, hasDamage);
     return 0;
 }
 

@@ -19,6 +19,9 @@ $R snapshot --config fluid --n 500 --jitter 5 --steps 3 --integrator euler --out
 $R snapshot --config gas --n 500 --jitter 9 --steps 3 --out gas_pc3.snap --no-lut
 # the library-default SymmetricSolver on the same input must agree with the asymmetric path (Solvers.cpp:178-216)
 $R snapshot --config hello --n 500 --solver sym --jitter 7 --out hello_sym_out.snap --no-lut
+# the XSph term (SPH_USE_XSPH, epsilon 0.5): one integrate() and three PredictorCorrector steps
+$R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --neighbours --in xsph_in.snap --out xsph_out.snap --no-lut
+$R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --steps 3 --out xsph_pc3.snap --no-lut
 # self-gravity (IGravity::build + evalSelfGravity on a zeroed buffer): brute force and Barnes-Hut, softened and point-like
 $R gravity --config hello --n 500 --jitter 7 --gravity brute --out gravity_brute.snap
 $R gravity --config hello --n 500 --jitter 7 --gravity bh --theta 0.5 --order 3 --no-lut --out gravity_bh.snap

@@ -21,7 +21,7 @@ class OrcState(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pad0", C.c_uint32)] + [(k, _D) for k in (
         "pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
         "eps_min", "m_zero", "growth")] + [(k, _U) for k in ("n_flaws", "flag", "ncnt")] + [(k, _D) for k in (
-        "divv", "gradv", "corr", "acc_pred", "drho_pred", "du_pred", "dS_pred", "ddamage_pred")]
+        "divv", "gradv", "corr", "acc_pred", "drho_pred", "du_pred", "dS_pred", "ddamage_pred", "xsph")] + [("xsph_eps", C.c_double)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -39,7 +39,7 @@ def lib() -> C.CDLL:
 
 
 _F64 = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
-        "eps_min", "m_zero", "growth", "divv", "gradv", "corr")
+        "eps_min", "m_zero", "growth", "divv", "gradv", "corr", "xsph")
 _U32 = ("n_flaws", "flag", "ncnt")
 _PRED = {"acc_pred": "acc", "drho_pred": "drho", "du_pred": "du", "dS_pred": "dS", "ddamage_pred": "ddamage"}
 
@@ -72,7 +72,12 @@ class OraclePort:
         self.n = n
         self.state = OrcState()
         self.state.n = n
+        if self.setup.cfg.flags & abi.FLAG_XSPH:
+            self.a.setdefault("xsph", np.zeros((n, 4)))
+        self.state.xsph_eps = self.setup.xsph_eps
         for name, _ in OrcState._fields_[2:]:
+            if name == "xsph_eps":
+                continue
             arr = self.a.get(name)
             if arr is None:
                 setattr(self.state, name, None)

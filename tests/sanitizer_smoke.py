@@ -72,4 +72,24 @@ for balsara in (False, True):
     dts, _, st = eng.run_pc(8, 0.01, 10.0)
     print("run_pc 8 steps, balsara", balsara, "pairs", st.pair_count, "list builds / age / metric", eng.list_stats())
     eng.close()
+
+# self-gravity (radix tree, bottom-up moments with arrival counters, warp-wide walk in shared memory), alone and inside
+# batched steps, and the lattice generator
+from opensph_b200.engine import lattice_count, make_lattice  # noqa: E402
+grav_lut = abi.gravity_table_cubic_spline(40000)
+for theta, order, leaf in ((0.5, 3, 0), (0.8, 2, 4), (0.0, 3, 0)):
+    setup = workloads.make_setup(len(small["mass"]), solid=True)
+    eng = Engine(setup, len(small["mass"]))
+    eng.upload_state(small, names)
+    eng.gravity_configure(theta, order, abi.GRAVITY_CONSTANT, grav_lut, 2.0, leaf)
+    gs = eng.gravity_eval()
+    dts, _, st = eng.run_pc(3, 0.01, 10.0)
+    print("gravity theta", theta, "order", order, "leaf", leaf, "node interactions", gs.approximated, "ranges", gs.exact, "groups", gs.groups)
+    eng.close()
+lat = make_lattice(3000, 5.0e4, (1.0e5, 0.0, -2.0e4))
+m = lattice_count(lat)
+eng = Engine(workloads.make_setup(m, solid=False), m)
+assert eng.lattice_generate(lat) == m
+print("lattice", m, "particles, mass sum", float(eng.download("MASS").sum()))
+eng.close()
 print("SANITIZER SMOKE DONE")
