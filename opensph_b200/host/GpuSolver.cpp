@@ -7,6 +7,7 @@
 #include "sph/kernel/GravityKernel.h"
 #include "sph/equations/av/Balsara.h"
 #include "sph/equations/av/Standard.h"
+#include "sph/equations/XSph.h"
 #include "system/Factory.h"
 #include "system/Statistics.h"
 #include "system/Timer.h"
@@ -63,6 +64,7 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     known += equations.contains<ContinuityEquation>() ? 1 : 0;
     known += equations.contains<StandardAV>() ? 1 : 0;
     known += equations.contains<BalsaraSwitch<StandardAV>>() ? 1 : 0;
+    known += equations.contains<XSph>() ? 1 : 0;
     known += equations.contains<AdaptiveSmoothingLength>() ? 1 : 0;
     known += equations.contains<ConstSmoothingLength>() ? 1 : 0;
     if (known != equations.getTermCnt()) {
@@ -71,6 +73,9 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     if (!equations.contains<PressureForce>() || !equations.contains<ContinuityEquation>() ||
         !(equations.contains<StandardAV>() || equations.contains<BalsaraSwitch<StandardAV>>())) {
         throw InvalidSetup("GpuSolver needs PressureForce, ContinuityEquation and StandardAV, plain or with the Balsara switch");
+    }
+    if (equations.contains<XSph>() && equations.contains<BalsaraSwitch<StandardAV>>()) {
+        throw InvalidSetup("GpuSolver: the XSph term together with the Balsara switch is not implemented on the device");
     }
     if (equations.contains<BalsaraSwitch<StandardAV>>() && settings.get<bool>(RunSettingsId::SPH_AV_BALSARA_STORE)) {
         throw InvalidSetup("GpuSolver: SPH_AV_BALSARA_STORE (the AV_BALSARA output quantity) is not implemented on the device");
@@ -158,6 +163,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     if (equations.contains<BalsaraSwitch<StandardAV>>()) {
         cfg.flags |= SPHGPU_FLAG_BALSARA;
     }
+    if (equations.contains<XSph>()) {
+        cfg.flags |= SPHGPU_FLAG_XSPH;
+    }
     if (equations.contains<AdaptiveSmoothingLength>()) {
         cfg.flags |= SPHGPU_FLAG_ADAPTIVE_H;
         if (hflags.has(SmoothingLengthEnum::SOUND_SPEED_ENFORCING)) {
@@ -239,6 +247,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     }
     check(sphgpu_create(&cfg, mats.data(), uint32_t(mats.size()), n, n, device, &ctx));
     ctxParticleCnt = n;
+    if (cfg.flags & SPHGPU_FLAG_XSPH) {
+        check(sphgpu_set_xsph_epsilon(ctx, settings.get<Float>(RunSettingsId::SPH_XSPH_EPSILON)));
+    }
     if (deviceGravity) {
         this->configureGravity();
     }
@@ -378,6 +389,10 @@ void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives)
             check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Size>(b.id)[0], 0, n));
         }
     }
+    if (storage.has(QuantityId::XSPH_VELOCITIES)) {
+        // the correction the previous evaluation left in the velocities (XSph::initialize takes it out again, XSph.h:69-79)
+        check(sphgpu_upload(c, SPHGPU_Q_XSPH_VELOCITIES, 0, L, &storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)[0], 0, n));
+    }
     if (storage.has(QuantityId::VELOCITY_ROTATION)) {
         // the Balsara factor is built from the divergence and rotation of the previous evaluation (Balsara.h:76-80)
         check(sphgpu_upload(c, SPHGPU_Q_VELOCITY_ROTATION, 0, L, &storage.getValue<Vector>(QuantityId::VELOCITY_ROTATION)[0], 0, n));
@@ -422,6 +437,9 @@ void GpuSolver::downloadQuantities(Storage& storage, const bool stateToo) {
     if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
         check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 0, L, &storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
         check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 1, L, &storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+    }
+    if (storage.has(QuantityId::XSPH_VELOCITIES)) {
+        check(sphgpu_download(c, SPHGPU_Q_XSPH_VELOCITIES, 0, L, &storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)[0], 0, n));
     }
     if (storage.has(QuantityId::VELOCITY_ROTATION)) {
         check(sphgpu_download(c, SPHGPU_Q_VELOCITY_ROTATION, 0, L, &storage.getValue<Vector>(QuantityId::VELOCITY_ROTATION)[0], 0, n));

@@ -390,15 +390,39 @@ int main(int argc, char** argv) {
             }
             expect(bcThrown, "a real boundary condition is rejected with InvalidSetup");
         }
+        // ---- the XSph term (SPH_USE_XSPH): two consecutive evaluations, so that the second one starts from velocities that
+        // contain the correction of the first (XSph::initialize / finalize, XSph.h:69-90)
+        {
+            RunSettings xs = settings;
+            xs.set(RunSettingsId::SPH_USE_XSPH, true).set(RunSettingsId::SPH_XSPH_EPSILON, 0.7_f);
+            const EquationHolder xeqs = getStandardEquations(xs);
+            AsymmetricSolver refX(*scheduler, xs, xeqs);
+            GpuSolver gpuX(*scheduler, xs, xeqs);
+            Storage xa = base->clone(VisitorEnum::ALL_BUFFERS), xb = base->clone(VisitorEnum::ALL_BUFFERS);
+            for (Size m = 0; m < xa.getMaterialCnt(); ++m) {
+                refX.create(xa, xa.getMaterial(m));
+                gpuX.create(xb, xb.getMaterial(m));
+            }
+            for (int pass = 0; pass < 2; ++pass) {
+                xa.zeroHighestDerivatives(*scheduler);
+                xb.zeroHighestDerivatives(*scheduler);
+                refX.integrate(xa, statsA);
+                gpuX.integrate(xb, statsA);
+            }
+            expect(compareStorages(xa, xb, true, "integrate() twice with the XSph term") <= 1.e-10, "all quantities within 1e-10 with XSph");
+            const double xe = cmpVector(xa.getValue<Vector>(QuantityId::XSPH_VELOCITIES), xb.getValue<Vector>(QuantityId::XSPH_VELOCITIES), 3);
+            printf("    %-28s %.3e\n", "XSPH_VELOCITIES", xe);
+            expect(xe <= 1.e-10, "XSPH_VELOCITIES within 1e-10");
+        }
         bool thrown = false;
         try {
             RunSettings s2 = settings;
-            s2.set(RunSettingsId::SPH_USE_XSPH, true);
+            s2.set(RunSettingsId::SPH_AV_USE_STRESS, true);
             GpuSolver bad(*scheduler, s2, getStandardEquations(s2));
         } catch (const InvalidSetup&) {
             thrown = true;
         }
-        expect(thrown, "equation set with XSph is rejected with InvalidSetup");
+        expect(thrown, "equation set with the stress AV is rejected with InvalidSetup");
         thrown = false;
         try {
             RunSettings s3 = settings;
