@@ -196,8 +196,8 @@ STEP_OUTPUTS = ("pos", "vel", "rho", "u", "S", "damage")    # the advanced state
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", dest="n", type=int, default=10_000_000, help="target particle count of the lattice (configs[3])")
     ap.add_argument("--variant", type=int, default=0)

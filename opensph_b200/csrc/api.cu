@@ -219,7 +219,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         SPH_TRY(devAlloc(&ctx->d.u[u], cap));
     }
     SPH_TRY(devAlloc(&ctx->d.rec, cap * (size_t)ctx->recDoubles));
-    ctx->maxSegs = capacity / 64 + ctx->maxCells + ctx->maxCells / 16 + 2; // units <= N / 128 + double rows + x-range cuts
+    ctx->maxSegs = capacity / 16 + ctx->maxCells + ctx->maxCells / 16 + 2; // units <= N / tile + double rows + x-range cuts
     SPH_TRY(devAlloc(&ctx->d.segStart, (size_t)ctx->maxCells + 2));
     SPH_TRY(devAlloc(&ctx->d.unitDesc, (size_t)ctx->maxSegs));
     SPH_TRY(devAlloc(&ctx->d.unitAux, (size_t)ctx->maxSegs));

@@ -31,8 +31,14 @@
 
 namespace sph {
 
-constexpr int TILE_T = 128;   // targets (threads) per work unit
-constexpr int TILE_C = 576;   // staged candidate slots per chunk (incl. the alignment gaps between row pieces)
+#ifndef SPH_TILE_T
+#define SPH_TILE_T 128
+#endif
+#ifndef SPH_TILE_C
+#define SPH_TILE_C 576
+#endif
+constexpr int TILE_T = SPH_TILE_T;   // targets (threads) per work unit
+constexpr int TILE_C = SPH_TILE_C;   // staged candidate slots per chunk (incl. the alignment gaps between row pieces)
 constexpr int LIST_CAP = 60;  // list entries per lane and block (15 quads; 63 is the null link of scheduleList)
 constexpr int UNIT_KBLOCK = 4;    // double rows (in z) interleaved in the unit order, see k_units
 constexpr int PAIRS_PER_TRIP = 2; // list entries the pair-sum kernel processes together
@@ -690,7 +696,7 @@ constexpr size_t LISTS_SMEM = (size_t)TILE_C * 16 + (size_t)(LIST_CAP + 1) * LIS
 // the pool row offset of the block AFTER it in the chain (or LIST_END): the pair-sum kernel prefetches one block ahead
 constexpr int DESC_WORDS = 16;
 
-__global__ void __launch_bounds__(TILE_T, 8) k_pair_lists(DevicePointers d, uint32_t maxCells, uint32_t poolRows, double skin) {
+__global__ void __launch_bounds__(TILE_T, 1024 / TILE_T) k_pair_lists(DevicePointers d, uint32_t maxCells, uint32_t poolRows, double skin) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float4* f4 = reinterpret_cast<float4*>(smemRaw);
     uint16_t* list = reinterpret_cast<uint16_t*>(f4 + TILE_C); // row 0 = counts + "no next block", rows 1.. = entries [entry][lane]
@@ -852,7 +858,10 @@ struct SumLayout {
     static constexpr bool SWIZZLED = S == REC_SOLID;
     static constexpr size_t bytes = (size_t)TILE_C * REC_BYTES; // 73 728 B solid (three CTAs per SM), 64 512 B fluid, 82 944 B
                                                                 // solid with the Balsara factor (two CTAs per SM)
-    static constexpr int CTAS_PER_SM = bytes > 74 * 1024 ? 2 : 3;
+    // what fits: 228 KB of shared memory per SM (per CTA 1 KB reserved + 16 B per thread + 280 B of static arrays), 64 K registers
+    static constexpr int BY_SMEM = (int)((228 * 1024) / (bytes + 1024 + 16 * TILE_T + 280));
+    static constexpr int BY_REGS = 65536 / (TILE_T * (BALSARA && SOLID ? 208 : 168));
+    static constexpr int CTAS_PER_SM = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
 };
 
 /// One list entry between the two stages of the pair body (sph_math.cuh).
@@ -1200,7 +1209,7 @@ static int launchLists(sphgpu_ctx* ctx) {
         SPH_CUDA_CHECK(cudaFuncSetAttribute(k_pair_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LISTS_SMEM));
         configured[ctx->device & 63] = true;
     }
-    k_pair_lists<<<unitGrid(ctx, 8, 8), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows, ctx->listSkin > 0. ? ctx->listSkin : 0.);
+    k_pair_lists<<<unitGrid(ctx, 1024 / TILE_T, 8), TILE_T, LISTS_SMEM, ctx->stream>>>(ctx->d, ctx->maxCells, poolRows, ctx->listSkin > 0. ? ctx->listSkin : 0.);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
