@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gravity", action="store_true", help="skip the self-gravity figure reported beside the headline")
     ap.add_argument("--fluid", action="store_true", help="fluid-only terms (BASELINE configs[4])")
     ap.add_argument("--dt-mode", choices=["criteria", "fixed"], default="criteria",
                     help="criteria: the step the preset's criteria choose (particles move); fixed: dt = 1e-6 (static lattice)")
@@ -386,6 +387,25 @@ def main():
                "what": "sphgpu_upload_async x%d -> step -> sphgpu_download_async x%d per step, pinned host buffers; the download of step k "
                        "overlaps the upload of step k+1" % (len(np_in), len(np_out))}
 
+    # Self-gravity of the same particles: not part of the headline metric (BASELINE's config has gravity
+    # off), reported beside it -- one evaluation = keys + sort + tree + moments + walk, at the GUI preset's
+    # opening angle 0.8 and at the library default 0.5, octupoles, cubic-spline softening.
+    gravity = None
+    if world == 1 and not args.no_gravity:
+        try:
+            grav_lut = __import__("opensph_b200").abi.gravity_table_cubic_spline(40000)
+            gravity = {"unit": "ms per evaluation", "particles": int(n_owned)}
+            for theta in (0.8, 0.5):
+                eng.gravity_configure(theta, 3, __import__("opensph_b200").abi.GRAVITY_CONSTANT, grav_lut, 2.0, 20)
+                eng.gravity_eval()
+                ms = sorted(eng.gravity_eval().gpu_ms for _ in range(3))[1]
+                st = eng.gravity_last_stats()
+                gravity[f"opening_angle_{theta}"] = {"ms": float(ms), "node_interactions": int(st.approximated), "exact_ranges": int(st.exact),
+                                                     "groups": int(st.groups)}
+            eng.gravity_off()
+        except Exception as e:
+            gravity = {"failed": str(e)}
+
     per_rank = None
     if world > 1:  # per-rank device-time breakdown (ms per step): grid, prologue, pair kernel, rest, of which halo exchange
         mine = torch.tensor(list(timings / args.steps) + [halo_ms / args.steps, float(n_owned)], dtype=torch.float64, device="cuda")
@@ -455,6 +475,8 @@ def main():
                      "pair_stage_parts": {"units_and_lane_order": pair_parts[0] / args.steps, "k_pair_lists": pair_parts[1] / args.steps,
                                           "k_pair_sum": pair_parts[2] / args.steps}},
     }
+    if gravity is not None:
+        out["gravity"] = gravity
     if per_rank is not None:
         out["per_rank_ms"] = {"columns": ["grid_build", "prologue_pack", "pair_kernel", "rest", "halo_exchange_in_rest", "owned_particles"],
                               "rows": per_rank}
@@ -466,6 +488,17 @@ def main():
                     "value": r["particle_updates_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
                     "sample": f"collision preset, {r['particles']} particles, 2 PredictorCorrector steps after 1 warm-up, "
                               f"AsymmetricSolver + KdTree on {r['threads']} host threads (oracle/_ref/sph_ref)"}
+            exe = os.path.join(ROOT, "oracle", "_ref", "sph_ref")
+            if gravity is not None and "failed" not in gravity and os.path.exists(exe):
+                # the reference's own Barnes-Hut (build + evalSelfGravity) on a 1 M-particle sample, all host threads
+                import tempfile
+                with tempfile.TemporaryDirectory() as tmp:
+                    line = subprocess.check_output([exe, "gravity", "--config", "preset", "--n", str(min(args.n, 1_000_000)), "--gravity", "bh",
+                                                    "--theta", "0.5", "--order", "3", "--leaf", "20", "--no-lut", "--out",
+                                                    os.path.join(tmp, "g.snap")], text=True)
+                rg = json.loads(line.strip().splitlines()[-1])
+                gravity["cpu_reference"] = {"particles": rg["particles"], "opening_angle": 0.5, "ms": 1.0e3 * rg["seconds"], "threads": rg["threads"],
+                                            "what": "BarnesHut::build + evalSelfGravity of the unmodified reference (oracle/_ref/sph_ref gravity)"}
         except Exception as e:  # the baseline is reported, never required
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     print(json.dumps(out))

@@ -229,15 +229,26 @@ struct GravParams {
 SPH_HD void gravPairAccel(const GravParams& p, const LutPair* __restrict__ lut, double xi, double yi, double zi, double hi, double xj, double yj,
     double zj, double hj, double mj, double& ax, double& ay, double& az) {
     const double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    const double d2 = dx * dx + dy * dy + dz * dz;
     const double hbar = 0.5 * (hj + hi);
+    // The reference forms q^2 = |r / hbar|^2 (GravityKernel.h:73-75). On the device the two divisions of a pair -- 1 / hbar
+    // here and 1 / |r|^3 below -- are a seeded reciprocal and a reciprocal square root with Newton steps (1-2 ulp) instead
+    // of the IEEE sequences, which cost about as much as the rest of the pair together; 1e-16 against a 1e-10 tolerance.
+#ifdef __CUDA_ARCH__
+    const double hInv = fastRcp(hbar);
+#else
     const double hInv = 1. / hbar;
-    const double sx = dx * hInv, sy = dy * hInv, sz = dz * hInv;
-    const double qSqr = sx * sx + sy * sy + sz * sz;
+#endif
+    const double qSqr = d2 * (hInv * hInv);
     double f;
     if (qSqr + (double)1.e-12f >= p.radiusSqr) {
-        const double d2 = dx * dx + dy * dy + dz * dz;
+#ifdef __CUDA_ARCH__
+        const double rInv = rsqrt(d2);
+        f = mj * (rInv * rInv * rInv);
+#else
         const double d = sqrt(d2);
         f = mj / (d2 * d);
+#endif
     } else {
         const double fidx = p.qSqrToIdx * qSqr;
         const uint32_t k = (uint32_t)fidx;
