@@ -206,13 +206,114 @@ def migrate(state: Dict[str, np.ndarray], dest: np.ndarray, world: int, rank: in
     return out
 
 
-def repartition(dom: "SlabDomain", eng, names: Sequence[str] = MIGRATE_FIELDS, adapter=None, kernel_radius: float = 2.0):
-    """Re-cuts the slabs to equal particle counts and migrates the particles that changed slab (SURVEY 8e: 're-cut every
-    m steps and migrate particles'). Host-orchestrated and rare: downloads the owned state, exchanges rows point-to-point,
-    restores the [lower band | interior | upper band] slot order, uploads, and rebuilds the halo exchange.
-    Returns (new owned state on the host, new HaloExchange)."""
+def _repartition_device(dom: "SlabDomain", eng, names: Sequence[str], kernel_radius: float):
+    """repartition() with the particle data staying in device memory: the rows are packed from the slot planes into
+    CUDA tensors (sphgpu_download_device), the new owner of every particle, the rows to send and the
+    [lower band | interior | upper band] order are computed with torch on the GPU, the rows travel over NCCL
+    (batch_isend_irecv of CUDA tensors: NVLink), and the new owned state is written back with sphgpu_upload_device.
+    Only a 4096-bin histogram and a few counts cross PCIe."""
     import torch
     import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = eng.n
+    fields = [(k,) + abi.SNAPSHOT_FIELDS[k] for k in names] + [("material_id", "MATERIAL_ID", 0)]
+    cols: Dict[str, "torch.Tensor"] = {}
+    for key, q, order in fields:
+        _, ncomp, dtype = abi.QUANTITIES[q]
+        t = torch.empty((max(n, 1), ncomp), dtype=torch.float64 if dtype == np.float64 else torch.int32, device=dev)
+        if n:
+            eng.download_device(q, order, t.data_ptr(), 0, n)
+        cols[key] = t[:n]
+    eng.synchronize()  # the packs ran on the engine's stream
+    axis = dom.axis
+    z = cols["pos"][:, axis].contiguous()
+    # global histogram of the cut coordinate -> cut planes at the count quantiles (as balanced_cut_planes)
+    bins = 4096
+    lohi = torch.stack([z.min() if n else torch.tensor(float("inf"), device=dev, dtype=torch.float64),
+                        -(z.max()) if n else torch.tensor(float("inf"), device=dev, dtype=torch.float64)])
+    dist.all_reduce(lohi, op=dist.ReduceOp.MIN)
+    lo, hi = float(lohi[0].item()), -float(lohi[1].item())
+    span = max(hi - lo, 1e-300)
+    idx = torch.clamp(((z - lo) * (bins / span)).to(torch.int64), 0, bins - 1)
+    hist = torch.bincount(idx, minlength=bins).to(torch.float64)
+    dist.all_reduce(hist)
+    hist = hist.cpu().numpy()
+    edges = lo + span * np.arange(bins + 1) / bins
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    cuts = [lo - 1e-6 * span]
+    for k in range(1, dom.world):
+        target = cum[-1] * k / dom.world
+        b = min(max(int(np.searchsorted(cum, target, side="right")) - 1, 0), bins - 1)
+        frac = (target - cum[b]) / hist[b] if hist[b] > 0 else 0.0
+        cuts.append(float(edges[b] + frac * (edges[b + 1] - edges[b])))
+    cuts.append(hi + 1e-6 * span)
+    cuts = np.array(cuts)
+    dest = torch.clamp(torch.bucketize(z, torch.tensor(cuts[1:-1], dtype=torch.float64, device=dev), right=True), 0, dom.world - 1)
+    # rows of doubles (u32 fields are exact in a double), one message per pair of ranks
+    widths = [cols[k].shape[1] for k, _, _ in fields]
+    rows = torch.cat([cols[k].to(torch.float64) for k, _, _ in fields], dim=1) if n else torch.empty((0, sum(widths)), dtype=torch.float64, device=dev)
+    mine = torch.bincount(dest, minlength=dom.world).to(torch.int64)
+    counts = [torch.zeros_like(mine) for _ in range(dom.world)]
+    dist.all_gather(counts, mine)
+    counts = torch.stack(counts).cpu().numpy()  # counts[src, dst]
+    ops, recv, keep_alive = [], {}, []
+    for peer in range(dom.world):
+        if peer == dom.rank:
+            continue
+        if counts[dom.rank, peer] > 0:
+            buf = rows[dest == peer].contiguous()
+            keep_alive.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, peer))
+        if counts[peer, dom.rank] > 0:
+            recv[peer] = torch.empty((int(counts[peer, dom.rank]), rows.shape[1]), dtype=torch.float64, device=dev)
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    rows = torch.cat([rows[dest == dom.rank]] + [recv[p] for p in sorted(recv)], dim=0)
+    # halo width from the CURRENT largest smoothing length of the whole run, then the band order
+    hmax = rows[:, 3].max().reshape(1) if len(rows) else torch.zeros(1, dtype=torch.float64, device=dev)
+    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    dom.adopt_cuts(cuts, kernel_radius * float(hmax.item()) * (1.0 + HALO_MARGIN))
+    x = rows[:, axis]
+    left = (x < dom.lo_plane + dom.halo_width) if dom.lo_plane is not None else torch.zeros(len(rows), dtype=torch.bool, device=dev)
+    right = (x >= dom.hi_plane - dom.halo_width) if dom.hi_plane is not None else torch.zeros(len(rows), dtype=torch.bool, device=dev)
+    if bool((left & right).any().item()):
+        raise ValueError("slab thinner than the halo width: use fewer ranks or more particles")
+    group = torch.where(left, 0, torch.where(right, 2, 1))
+    perm = torch.sort(group, stable=True).indices
+    rows = rows[perm]
+    dom.n_left, dom.n_right = int(left.sum().item()), int(right.sum().item())
+    n_new = len(rows)
+    if n_new > eng.capacity:
+        raise ValueError(f"rank {dom.rank}: {n_new} particles after migration exceed the engine capacity {eng.capacity}")
+    eng.set_particle_count(n_new)
+    off, keep = 0, []
+    for (key, q, order), w in zip(fields, widths):
+        _, ncomp, dtype = abi.QUANTITIES[q]
+        block = rows[:, off:off + w]
+        block = block.contiguous() if dtype == np.float64 else block.to(torch.int32).contiguous()
+        keep.append(block)
+        off += w
+    torch.cuda.current_stream().synchronize()  # the tensors are complete before the engine's stream reads them
+    for (key, q, order), block in zip(fields, keep):
+        if n_new:
+            eng.upload_device(q, order, block.data_ptr(), 0, n_new)
+    eng.synchronize()
+    halo = HaloExchange(dom, eng, None, names=tuple(names))
+    return None, halo
+
+
+def repartition(dom: "SlabDomain", eng, names: Sequence[str] = MIGRATE_FIELDS, adapter=None, kernel_radius: float = 2.0):
+    """Re-cuts the slabs to equal particle counts and migrates the particles that changed slab (SURVEY 8e: 're-cut every
+    m steps and migrate particles'): restores the [lower band | interior | upper band] slot order and rebuilds the halo
+    exchange. With NCCL and a device engine the particle rows never leave device memory (_repartition_device; the returned
+    state is None); otherwise (gloo / host engines: the CPU tests) the owned state is downloaded, exchanged point-to-point
+    and uploaded again. Returns (new owned state on the host or None, new HaloExchange)."""
+    import torch
+    import torch.distributed as dist
+    if adapter is None and dist.get_backend() == "nccl" and hasattr(eng, "download_device") and hasattr(eng, "synchronize"):
+        return _repartition_device(dom, eng, names, kernel_radius)
     state = eng.download_state([k for k in names])
     state["material_id"] = eng.download("MATERIAL_ID", 0, 0, eng.n) if hasattr(eng, "download") else np.zeros(len(state["pos"]), np.uint32)
     axis = dom.axis
@@ -270,14 +371,17 @@ class EngineAdapter:
 class HaloExchange:
     """Ghost-layer exchange between slab neighbours (rank-1, rank+1) with torch.distributed point-to-point."""
 
-    def __init__(self, dom: SlabDomain, eng, state: Dict[str, np.ndarray], adapter=None, fields=DYNAMIC_FIELDS):
+    def __init__(self, dom: SlabDomain, eng, state: Optional[Dict[str, np.ndarray]], adapter=None, fields=DYNAMIC_FIELDS, names=None):
         import torch
         import torch.distributed as dist
         self.dist, self.torch = dist, torch
         self.dom, self.eng = dom, eng
         self.adapter = adapter or EngineAdapter(eng)
-        self.n = len(state["mass"])
-        self.fields = tuple((k, c) for k, c in fields if k in state)
+        # `state` is only consulted for the particle count and for which quantities exist; a device-side repartition
+        # passes None and the names it migrated
+        have = set(state.keys()) if state is not None else set(names or ())
+        self.n = len(state["mass"]) if state is not None else eng.n
+        self.fields = tuple((k, c) for k, c in fields if k in have)
         self.width = sum(c for _, c in self.fields)
         self.left, self.right = (dom.rank - 1 if dom.rank > 0 else None), (dom.rank + 1 if dom.rank < dom.world - 1 else None)
         # how many ghosts arrive from each side: the neighbour's band facing us
@@ -293,7 +397,7 @@ class HaloExchange:
         self.recv_l = self.adapter.new_buffer(self.width * self.g_left)
         self.recv_r = self.adapter.new_buffer(self.width * self.g_right)
         self.bytes_per_exchange = 8 * self.width * (dom.n_left + dom.n_right)
-        self._static(state)
+        self._static(have)
         eng.set_active(self.n_active)
         # the per-step exchange runs inside the library (NCCL on the engine's stream) when the engine supports it
         self.native = hasattr(eng, "comm_init") and dist.get_backend() == "nccl" and self.fields == DYNAMIC_FIELDS
@@ -354,8 +458,8 @@ class HaloExchange:
         if self.g_right:
             self.adapter.unpack(fields, self.ghost_right_first, self.g_right, rr)
 
-    def _static(self, state) -> None:
-        fields = tuple((k, c) for k, c in STATIC_FIELDS if k in state)
+    def _static(self, have) -> None:
+        fields = tuple((k, c) for k, c in STATIC_FIELDS if k in have)
         if fields:
             self._run(fields)
         # Body flag and material id of the ghosts come from their owners (a ghost of another body must not pass the
@@ -367,9 +471,10 @@ class HaloExchange:
         dev = _dist_device(self.dist)
         nl, nr = self.dom.n_left, self.dom.n_right
         for q in ("FLAG", "MATERIAL_ID"):
-            own = self.eng.download(q, 0, 0, self.n).astype(np.float64) if self.n else np.zeros(0)
-            sl = torch.from_numpy(np.ascontiguousarray(own[:nl])).to(dev)
-            sr = torch.from_numpy(np.ascontiguousarray(own[self.n - nr:] if nr else own[:0])).to(dev)
+            lo_band = self.eng.download(q, 0, 0, nl).astype(np.float64) if nl else np.zeros(0)
+            hi_band = self.eng.download(q, 0, self.n - nr, nr).astype(np.float64) if nr else np.zeros(0)
+            sl = torch.from_numpy(np.ascontiguousarray(lo_band)).to(dev)
+            sr = torch.from_numpy(np.ascontiguousarray(hi_band)).to(dev)
             rl = torch.zeros(max(self.g_left, 1), dtype=torch.float64, device=dev)[: self.g_left]
             rr = torch.zeros(max(self.g_right, 1), dtype=torch.float64, device=dev)[: self.g_right]
             self._p2p(sl, sr, rl, rr)
