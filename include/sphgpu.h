@@ -351,6 +351,25 @@ typedef struct sphgpu_lattice {
 SPHGPU_API int sphgpu_lattice_count(int device, const sphgpu_lattice* cfg, uint32_t* count);
 SPHGPU_API int sphgpu_lattice_generate(sphgpu_ctx* ctx, const sphgpu_lattice* cfg, uint32_t first, uint32_t* count);
 
+/* ---- boundary condition: frozen particles ---------------------------------------------- */
+
+/* Replaces FrozenParticles::finalize (core/sph/boundary/Boundary.cpp:221-258), which the solver calls after
+ * equations.finalize and before material->finalize (AsymmetricSolver.cpp:204-224): particles whose body flag is in
+ * flag_mask (bit f = QuantityId::FLAG value f, f < 64), and -- with has_domain -- particles of a SphericalDomain that are
+ * closer to its surface than freeze_radius smoothing lengths, get all highest derivatives set to zero (acceleration,
+ * density, energy and stress derivatives; the damage derivative is the material's and stays); particles outside the
+ * domain are first projected onto its surface (SphericalDomain::project, Domain.cpp:66-85). Applied by every
+ * sphgpu_integrate / sphgpu_step_pc / sphgpu_run_pc after the derivatives are complete. cfg == NULL switches it off. */
+typedef struct sphgpu_frozen {
+    uint64_t flag_mask;
+    int has_domain;
+    int reserved;
+    double center[3];
+    double radius;
+    double freeze_radius; /* in units of the smoothing length */
+} sphgpu_frozen;
+SPHGPU_API int sphgpu_set_frozen(sphgpu_ctx* ctx, const sphgpu_frozen* cfg);
+
 /* ---- inspection (tests) --------------------------------------------------------------------------------- */
 
 /* Neighbour lists exactly as AsymmetricSolver::loop selects them (AsymmetricSolver.cpp:174-199), CSR:

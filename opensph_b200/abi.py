@@ -114,6 +114,13 @@ class GravityStats(C.Structure):
     ]
 
 
+class Frozen(C.Structure):
+    _fields_ = [
+        ("flag_mask", C.c_uint64), ("has_domain", C.c_int), ("reserved", C.c_int), ("center", C.c_double * 3),
+        ("radius", C.c_double), ("freeze_radius", C.c_double),
+    ]
+
+
 class Lattice(C.Structure):
     _fields_ = [
         ("center", C.c_double * 3), ("radius", C.c_double), ("particle_count", C.c_uint32), ("flags", C.c_uint32),

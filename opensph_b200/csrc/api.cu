@@ -586,6 +586,8 @@ int enqueueIntegrate(sphgpu_ctx* ctx) {
     if ((rc = launchPair(ctx)) != SPHGPU_OK) return rc;
     // GravitySolver::loop (GravitySolver.cpp:64-99): the gravitational accelerations join the SPH ones
     if (ctx->gravity != nullptr && (rc = launchGravity(ctx, 1)) != SPHGPU_OK) return rc;
+    // afterLoop: boundary conditions see the finished derivatives (AsymmetricSolver.cpp:216)
+    if (ctx->hasFrozen && (rc = launchFrozen(ctx)) != SPHGPU_OK) return rc;
     SPH_CUDA_CHECK(cudaEventRecord(ctx->ev[3], ctx->stream));
     return SPHGPU_OK;
 }
@@ -668,6 +670,18 @@ int sphgpu_integrate(sphgpu_ctx* ctx, double t, sphgpu_stats* stats) {
     int rc = enqueueIntegrate(ctx);
     if (rc != SPHGPU_OK) return rc;
     return collectStats(ctx, stats, ctx->ev[0], ctx->ev[3]);
+}
+
+int sphgpu_set_frozen(sphgpu_ctx* ctx, const sphgpu_frozen* cfg) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (cfg && cfg->has_domain && !(cfg->radius > 0. && cfg->freeze_radius >= 0.)) {
+        return fail(SPHGPU_E_INVALID, "frozen particles: the domain needs a positive radius and a non-negative freeze radius");
+    }
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->hasFrozen = cfg != nullptr && (cfg->flag_mask != 0ull || cfg->has_domain != 0);
+    if (cfg) ctx->frozen = *cfg;
+    return SPHGPU_OK;
 }
 
 int sphgpu_set_xsph_epsilon(sphgpu_ctx* ctx, double epsilon) {

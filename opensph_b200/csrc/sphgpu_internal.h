@@ -213,6 +213,8 @@ struct sphgpu_ctx {
     uint32_t launches = 0;
     bool stateUploaded = false;
     void* halo = nullptr;      // sph::HaloState (halo.cu): NCCL communicator + exchange buffers
+    bool hasFrozen = false;    // FrozenParticles boundary condition (sphgpu_set_frozen)
+    sphgpu_frozen frozen{};
     void* gravity = nullptr;   // sph::GravState (gravity.cu): self-gravity, when configured
     double gravityConstant = 0.;
 };
@@ -247,6 +249,7 @@ int launchCorrect(sphgpu_ctx* ctx, double dt);
 int launchCorrectPredict(sphgpu_ctx* ctx); // corrector of the step that ends + predictor of the next one (sphgpu_run_pc)
 int launchEuler(sphgpu_ctx* ctx, double dt);
 int launchCriteria(sphgpu_ctx* ctx);
+int launchFrozen(sphgpu_ctx* ctx); // FrozenParticles::finalize, when configured
 int measureFp64Peak(sphgpu_ctx* ctx, double* fmaPerSecond);
 int launchFinishTimestep(sphgpu_ctx* ctx, double maxDt, StepRecordDev* history, uint32_t index);
 // transfer.cu

@@ -492,6 +492,67 @@ int launchEuler(sphgpu_ctx* ctx, double dt) {
     return SPHGPU_OK;
 }
 
+// ---- FrozenParticles::finalize (core/sph/boundary/Boundary.cpp:221-258) ------------------------------------------------
+// Particles outside the spherical domain are projected onto its surface (SphericalDomain::project, Domain.cpp:66-85:
+// centre + unit vector * (1 - EPS) * radius); particles within `freezeRadius` smoothing lengths of the surface and particles
+// of the frozen bodies get their highest derivatives zeroed. The damage derivative belongs to material->finalize, which the
+// reference runs after the boundary condition: it stays.
+template <bool SOLID>
+__global__ void __launch_bounds__(256) k_frozen(DevicePointers d, uint32_t n, sphgpu_frozen f) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) {
+        return;
+    }
+    const uint32_t flag = d.u[U_FLAG][i];
+    bool frozen = flag < 64u && ((f.flag_mask >> flag) & 1ull) != 0ull;
+    if (f.has_domain) {
+        double x = d.f[F_X][i] - f.center[0], y = d.f[F_Y][i] - f.center[1], z = d.f[F_Z][i] - f.center[2];
+        double len2 = x * x + y * y + z * z;
+        if (!(len2 <= f.radius * f.radius)) { // SphericalDomain::isInsideImpl (Domain.h:134-136)
+            const double len = sqrt(len2);
+            const double s = 1. - (double)1.e-12f; // getNormalized(v - centre) * (1 - EPS) * radius + centre, in this order
+            x = x / len * s * f.radius + f.center[0];
+            y = y / len * s * f.radius + f.center[1];
+            z = z / len * s * f.radius + f.center[2];
+            d.f[F_X][i] = x;
+            d.f[F_Y][i] = y;
+            d.f[F_Z][i] = z;
+            x -= f.center[0];
+            y -= f.center[1];
+            z -= f.center[2];
+            len2 = x * x + y * y + z * z;
+        }
+        // getDistanceToBoundary (Domain.cpp:58-64): radius - |r - centre|
+        frozen = frozen || (f.radius - sqrt(len2) < f.freeze_radius * d.f[F_H][i]);
+    }
+    if (!frozen) {
+        return;
+    }
+    d.f[F_AX][i] = d.f[F_AY][i] = d.f[F_AZ][i] = 0.;
+    d.f[F_DRHO][i] = 0.;
+    d.f[F_DU][i] = 0.;
+    if (SOLID) {
+        for (int k = 0; k < 5; ++k) {
+            d.f[F_DS0 + k][i] = 0.;
+        }
+    }
+}
+
+int launchFrozen(sphgpu_ctx* ctx) {
+    const uint32_t n = ctx->n;
+    if (n == 0) {
+        return SPHGPU_OK;
+    }
+    if (ctx->solid) {
+        k_frozen<true><<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n, ctx->frozen);
+    } else {
+        k_frozen<false><<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d, n, ctx->frozen);
+    }
+    ctx->launches += 1;
+    SPH_CUDA_CHECK(cudaGetLastError());
+    return SPHGPU_OK;
+}
+
 int launchCriteria(sphgpu_ctx* ctx) {
     {
         const int rcConst = ensureConstants(ctx);

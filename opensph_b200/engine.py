@@ -236,6 +236,19 @@ class Engine:
         _check(self.lib.sphgpu_integrate(self._ctx, C.c_double(t), C.byref(st)))
         return st
 
+    def set_frozen(self, flags=(), domain=None) -> None:
+        """FrozenParticles boundary condition: bodies `flags` and, with domain = (centre, radius, freeze_radius), the particles
+        near the surface of that sphere keep zero highest derivatives (sphgpu_set_frozen); no arguments switch it off."""
+        f = abi.Frozen()
+        for b in flags:
+            f.flag_mask |= 1 << int(b)
+        if domain is not None:
+            centre, radius, freeze_radius = domain
+            f.has_domain = 1
+            f.center[0], f.center[1], f.center[2] = centre
+            f.radius, f.freeze_radius = radius, freeze_radius
+        _check(self.lib.sphgpu_set_frozen(self._ctx, C.byref(f) if (f.flag_mask or f.has_domain) else None))
+
     def lattice_generate(self, lat: abi.Lattice, first: int = 0) -> int:
         """InitialConditions::addMonolithicBody on the device: positions, h, masses, flag of slots [first, first + count)."""
         n = C.c_uint32(0)

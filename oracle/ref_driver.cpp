@@ -11,6 +11,7 @@
 // Commands
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
 //                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
+//                    [--frozen-flag F] [--frozen-domain RADIUS [--frozen-radius r]]
 //                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--xsph [EPS]] [--criteria MASK]
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
@@ -539,7 +540,23 @@ int main(int argc, char** argv) {
         SharedPtr<Storage> storage = makeShared<Storage>();
         makeStorage(config, n, settings, *storage);
 
-        AutoPtr<ISolver> solver = Factory::getSolver(*scheduler, settings);
+        // --frozen-flag F / --frozen-domain RADIUS [--frozen-radius r]: FrozenParticles boundary condition
+        // (core/sph/boundary/Boundary.cpp:203-258) handed to the solver like IRun::setUp would
+        AutoPtr<IBoundaryCondition> bc;
+        if (args.has("frozen-flag") || args.has("frozen-domain")) {
+            AutoPtr<FrozenParticles> frozen;
+            if (args.has("frozen-domain")) {
+                frozen = makeAuto<FrozenParticles>(makeShared<SphericalDomain>(Vector(0._f), Float(atof(args.str("frozen-domain").c_str()))),
+                    Float(atof(args.str("frozen-radius", "2").c_str())));
+            } else {
+                frozen = makeAuto<FrozenParticles>();
+            }
+            if (args.has("frozen-flag")) {
+                frozen->freeze(Size(args.num("frozen-flag", 0)));
+            }
+            bc = std::move(frozen);
+        }
+        AutoPtr<ISolver> solver = bc ? Factory::getSolver(*scheduler, settings, std::move(bc)) : Factory::getSolver(*scheduler, settings);
         for (Size i = 0; i < storage->getMaterialCnt(); ++i) {
             solver->create(*storage, storage->getMaterial(i));
         }

@@ -1278,3 +1278,44 @@ uint32_t orc_hexagonal_sphere(uint32_t n, const double* center, double radius, i
     }
     return cnt;
 }
+
+/* ---- boundary condition ------------------------------------------------------------------------------------------------ */
+
+/* FrozenParticles::finalize, Boundary.cpp:221-258; SphericalDomain::getSubset / project / getDistanceToBoundary,
+ * Domain.cpp:35-85. */
+void orc_frozen(orc_state* s, int solid, uint64_t flag_mask, int has_domain, const double* center, double radius, double freeze_radius) {
+    for (uint32_t i = 0; i < s->n; ++i) {
+        double* r = s->pos + 4 * (size_t)i;
+        int frozen = 0;
+        if (has_domain) {
+            double d[3] = { r[0] - center[0], r[1] - center[1], r[2] - center[2] };
+            if (!(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] <= sqr(radius))) {
+                const double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                for (int k = 0; k < 3; ++k) {
+                    r[k] = d[k] / len * (1. - ORC_EPS) * radius + center[k];
+                    d[k] = r[k] - center[k];
+                }
+            }
+            const double dist = radius - sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            if (dist < freeze_radius * r[3]) {
+                frozen = 1;
+            }
+        }
+        if (s->flag && s->flag[i] < 64u && ((flag_mask >> s->flag[i]) & 1ull)) {
+            frozen = 1;
+        }
+        if (!frozen) {
+            continue;
+        }
+        /* iterate<HIGHEST_DERIVATIVES>: POSITION d2t, DENSITY dt, ENERGY dt, DEVIATORIC_STRESS dt (and DAMAGE dt, which
+         * material->finalize overwrites afterwards) */
+        for (int k = 0; k < 4; ++k) {
+            s->acc[4 * (size_t)i + k] = 0.;
+        }
+        s->drho[i] = 0.;
+        s->du[i] = 0.;
+        if (solid && s->dS) {
+            memset(s->dS + 5 * (size_t)i, 0, 5 * sizeof(double));
+        }
+    }
+}

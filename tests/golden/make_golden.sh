@@ -22,6 +22,8 @@ $R snapshot --config hello --n 500 --solver sym --jitter 7 --out hello_sym_out.s
 # the XSph term (SPH_USE_XSPH, epsilon 0.5): one integrate() and three PredictorCorrector steps
 $R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --neighbours --in xsph_in.snap --out xsph_out.snap --no-lut
 $R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --steps 3 --out xsph_pc3.snap --no-lut
+# FrozenParticles boundary condition: the impactor (flag 1) frozen and everything within 0.3 h of / outside a sphere of 90 km
+$R snapshot --config collision_preset --n 500 --jitter 3 --frozen-flag 1 --frozen-domain 9e4 --frozen-radius 0.3 --out frozen_out.snap --no-lut
 # self-gravity (IGravity::build + evalSelfGravity on a zeroed buffer): brute force and Barnes-Hut, softened and point-like
 $R gravity --config hello --n 500 --jitter 7 --gravity brute --out gravity_brute.snap
 $R gravity --config hello --n 500 --jitter 7 --gravity bh --theta 0.5 --order 3 --no-lut --out gravity_bh.snap

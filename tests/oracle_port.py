@@ -93,6 +93,15 @@ class OraclePort:
     def integrate(self) -> None:
         lib().orc_integrate(*self._args())
 
+    def frozen(self, flags=(), domain=None) -> None:
+        """FrozenParticles::finalize after integrate(): bodies `flags`, domain = (centre, radius, freeze_radius)."""
+        mask = 0
+        for b in flags:
+            mask |= 1 << int(b)
+        c = np.zeros(3) if domain is None else np.ascontiguousarray(domain[0], dtype=np.float64)
+        lib().orc_frozen(C.byref(self.state), C.c_int(1 if self.setup.solid else 0), C.c_uint64(mask), C.c_int(0 if domain is None else 1),
+                         c.ctypes.data_as(_D), C.c_double(0.0 if domain is None else domain[1]), C.c_double(0.0 if domain is None else domain[2]))
+
     def predict(self, dt: float) -> None:
         lib().orc_predict(*self._args(), C.c_double(dt))
 

@@ -29,14 +29,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "sphgpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sphgpu_config),'
+    src.write_text('#include <stdio.h>\n#include "sphgpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sphgpu_config),'
                    ' sizeof(sphgpu_material), sizeof(sphgpu_stats), sizeof(sphgpu_timestep), sizeof(sphgpu_gravity),'
-                   ' sizeof(sphgpu_gravity_stats), sizeof(sphgpu_lattice));return 0;}\n')
+                   ' sizeof(sphgpu_gravity_stats), sizeof(sphgpu_lattice), sizeof(sphgpu_frozen));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(abi.Config), C.sizeof(abi.Material), C.sizeof(abi.Stats), C.sizeof(abi.TimeStep),
-                     C.sizeof(abi.Gravity), C.sizeof(abi.GravityStats), C.sizeof(abi.Lattice)]
+                     C.sizeof(abi.Gravity), C.sizeof(abi.GravityStats), C.sizeof(abi.Lattice), C.sizeof(abi.Frozen)]
 
 
 def _cuda_available():
