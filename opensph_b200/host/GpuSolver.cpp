@@ -1,6 +1,7 @@
 #include "GpuSolver.h"
 #include "../../include/sphgpu.h"
 #include "objects/Exceptions.h"
+#include "objects/geometry/Domain.h"
 #include "physics/Constants.h"
 #include "quantities/IMaterial.h"
 #include "quantities/Storage.h"
@@ -13,6 +14,8 @@
 #include "system/Timer.h"
 #include "thread/Scheduler.h"
 #include <algorithm>
+#include <set>
+#include <typeinfo>
 #include <string>
 #include <vector>
 
@@ -95,9 +98,60 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
 GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, AutoPtr<IBoundaryCondition>&& bc,
     const int device)
     : GpuSolver(scheduler, settings, eqs, device) {
-    if (bc && !dynamic_cast<NullBoundaryCondition*>(&*bc)) {
-        throw InvalidSetup("GpuSolver: boundary conditions have no device implementation (only NullBoundaryCondition)");
+    if (!bc || dynamic_cast<NullBoundaryCondition*>(&*bc)) {
+        return;
     }
+    // FrozenParticles itself (not WindTunnel, which derives from it and does more): its frozen bodies, domain and radius
+    // are protected members; a pointer to member named through a derived class reads them without touching the reference
+    struct Access : FrozenParticles {
+        static std::set<Size> FrozenParticles::*flags() {
+            return &Access::frozen;
+        }
+        static SharedPtr<IDomain> FrozenParticles::*dom() {
+            return &Access::domain;
+        }
+        static Float FrozenParticles::*rad() {
+            return &Access::radius;
+        }
+    };
+    FrozenParticles* frozen = dynamic_cast<FrozenParticles*>(&*bc);
+    if (!frozen || typeid(*frozen) != typeid(FrozenParticles)) {
+        throw InvalidSetup("GpuSolver: this boundary condition has no device implementation (NullBoundaryCondition and "
+                           "FrozenParticles have)");
+    }
+    for (const Size flag : frozen->*Access::flags()) {
+        if (flag >= 64) {
+            throw InvalidSetup("GpuSolver: FrozenParticles on the device freezes body flags below 64");
+        }
+        frozenMask |= 1ull << flag;
+    }
+    const SharedPtr<IDomain>& domain = frozen->*Access::dom();
+    if (domain) {
+        const SphericalDomain* sphere = dynamic_cast<const SphericalDomain*>(&*domain);
+        if (!sphere) {
+            throw InvalidSetup("GpuSolver: FrozenParticles on the device needs a SphericalDomain");
+        }
+        frozenDomain = true;
+        const Vector c = sphere->getCenter();
+        frozenCenter[0] = c[X];
+        frozenCenter[1] = c[Y];
+        frozenCenter[2] = c[Z];
+        frozenRadius = 0.5 * sphere->getBoundingBox().size()[X];
+        frozenFreezeRadius = frozen->*Access::rad();
+    }
+    frozenActive = frozenMask != 0 || frozenDomain;
+}
+
+void GpuSolver::configureFrozen() {
+    sphgpu_frozen f{};
+    f.flag_mask = frozenMask;
+    f.has_domain = frozenDomain ? 1 : 0;
+    for (int k = 0; k < 3; ++k) {
+        f.center[k] = frozenCenter[k];
+    }
+    f.radius = frozenRadius;
+    f.freeze_radius = frozenFreezeRadius;
+    check(sphgpu_set_frozen(ctx, &f));
 }
 
 /// Attached to the Storage (Storage::setUserData): Storage::remove tells us that particle indices changed, so the device
@@ -252,6 +306,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     }
     if (deviceGravity) {
         this->configureGravity();
+    }
+    if (frozenActive) {
+        this->configureFrozen();
     }
     return ctx;
 }

@@ -55,6 +55,13 @@ private:
     /// True while the device holds a newer state than the Storage (after GpuPredictorCorrector steps).
     bool hostStale = false;
 
+    /// FrozenParticles boundary condition taken over from the reference object handed to the constructor
+    bool frozenActive = false;
+    unsigned long long frozenMask = 0;
+    bool frozenDomain = false;
+    double frozenCenter[3] = { 0., 0., 0. }, frozenRadius = 0., frozenFreezeRadius = 0.;
+    void configureFrozen();
+
     /// Self-gravity on the device (enableDeviceGravity): applied to every context this solver creates.
     bool deviceGravity = false;
     void configureGravity();
@@ -67,8 +74,10 @@ public:
     ///        fallback), mirroring AsymmetricSolver::sanityCheck (AsymmetricSolver.cpp:228-238).
     GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, const int device = 0);
 
-    /// The signature Factory::getSolver uses (AsymmetricSolver.h:126-129). Boundary conditions have no device
-    /// implementation: anything but nullptr / NullBoundaryCondition throws InvalidSetup.
+    /// The signature Factory::getSolver uses (AsymmetricSolver.h:126-129). Boundary conditions with a device
+    /// implementation: none (nullptr / NullBoundaryCondition) and FrozenParticles (core/sph/boundary/Boundary.h:162-197) with
+    /// frozen bodies and / or a SphericalDomain -- its settings are read from the object and applied on the device after
+    /// every evaluation (sphgpu_set_frozen). Anything else throws InvalidSetup.
     GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, AutoPtr<IBoundaryCondition>&& bc,
         const int device = 0);
 

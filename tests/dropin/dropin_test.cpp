@@ -414,6 +414,34 @@ int main(int argc, char** argv) {
             printf("    %-28s %.3e\n", "XSPH_VELOCITIES", xe);
             expect(xe <= 1.e-10, "XSPH_VELOCITIES within 1e-10");
         }
+        // ---- FrozenParticles boundary condition handed to the solvers' Factory constructor ----
+        {
+            auto makeBc = [&]() {
+                Float rmax = 0._f;
+                ArrayView<const Vector> rr = base->getValue<Vector>(QuantityId::POSITION);
+                for (Size i = 0; i < rr.size(); ++i) {
+                    rmax = max(rmax, getLength(rr[i]));
+                }
+                AutoPtr<FrozenParticles> bc = makeAuto<FrozenParticles>(makeShared<SphericalDomain>(Vector(0._f), 0.9_f * rmax), 0.5_f);
+                bc->freeze(1);
+                return bc;
+            };
+            AsymmetricSolver refF(*scheduler, settings, eqs, makeBc());
+            GpuSolver gpuF(*scheduler, settings, eqs, makeBc());
+            Storage fa = base->clone(VisitorEnum::ALL_BUFFERS), fb = base->clone(VisitorEnum::ALL_BUFFERS);
+            fa.zeroHighestDerivatives(*scheduler);
+            fb.zeroHighestDerivatives(*scheduler);
+            refF.integrate(fa, statsA);
+            gpuF.integrate(fb, statsA);
+            Size frozenCnt = 0;
+            ArrayView<const Vector> dvF = fa.getD2t<Vector>(QuantityId::POSITION);
+            for (Size i = 0; i < dvF.size(); ++i) {
+                frozenCnt += (dvF[i] == Vector(0._f)) ? 1 : 0;
+            }
+            printf("  [FrozenParticles] %u of %u particles frozen\n", unsigned(frozenCnt), unsigned(dvF.size()));
+            expect(frozenCnt > 0 && frozenCnt < dvF.size(), "the boundary condition freezes some particles");
+            expect(compareStorages(fa, fb, true, "integrate() with FrozenParticles") <= 1.e-10, "all quantities within 1e-10 with FrozenParticles");
+        }
         bool thrown = false;
         try {
             RunSettings s2 = settings;
