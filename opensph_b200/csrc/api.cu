@@ -243,8 +243,6 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     SPH_TRY(devAlloc(&ctx->d.order, cap));
     SPH_TRY(devAlloc(&ctx->d.cellOf, cap));
     SPH_TRY(devAlloc(&ctx->d.dispA, 6 * ((size_t)ctx->maxCells + 1)));
-    SPH_TRY(devAlloc(&ctx->d.dispB, 6 * ((size_t)ctx->maxCells + 1)));
-    SPH_TRY(devAlloc(&ctx->d.dispC, 6 * ((size_t)ctx->maxCells + 1)));
     SPH_TRY(devAlloc(&ctx->d.dispGlobal, 8));
     SPH_TRY(devAlloc(&ctx->d.rank, cap));
     SPH_TRY(devAlloc(&ctx->d.cellStart, (size_t)ctx->maxCells + 2));
@@ -319,7 +317,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     cudaFree(ctx->d.listPool); cudaFree(ctx->d.listCursor); cudaFree(ctx->d.stepState);
     cudaFree(ctx->d.posF); cudaFree(ctx->d.pos0); cudaFree(ctx->d.accLarge); cudaFree(ctx->d.largePartial); cudaFree(ctx->d.largeCounter); cudaFree(ctx->d.listCtl); cudaFree(ctx->d.cellHmax);
     cudaFree(ctx->d.sCell); cudaFree(ctx->d.order); cudaFree(ctx->d.cellOf); cudaFree(ctx->d.rank);
-    cudaFree(ctx->d.dispA); cudaFree(ctx->d.dispB); cudaFree(ctx->d.dispC); cudaFree(ctx->d.dispGlobal);
+    cudaFree(ctx->d.dispA); cudaFree(ctx->d.dispGlobal);
     cudaFree(ctx->d.cellStart); cudaFree(ctx->d.cellCount); cudaFree(ctx->d.scanBlock); cudaFree(ctx->d.boundsPartial);
     cudaFree(ctx->d.grid); cudaFree(ctx->d.stats); cudaFree(ctx->d.statsInit); cudaFree(ctx->d.tsd); cudaFree((void*)ctx->d.lut); cudaFree((void*)ctx->d.lut2); cudaFree((void*)ctx->d.lutW); cudaFree((void*)ctx->d.lutW2); cudaFree(ctx->staging);
     for (int k = 0; k < 8; ++k) {

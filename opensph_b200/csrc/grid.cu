@@ -28,6 +28,9 @@ __device__ __forceinline__ double warpMax(double v) {
 // AdaptiveSmoothingLength::initialize (h clamp, EquationTerm.cpp:356-364) fused with the bounding-box / h_max pass and
 // with the displacement check of the list reuse (ListCtlDev): how far every particle has moved, relative to R h, and how
 // much its h has grown since the lists were built.
+// Displacement boxes of the list reuse are kept per block of 2^DISP_BX x 2^DISP_BY x 2^DISP_BZ cells.
+constexpr int DISP_BX = 2, DISP_BY = 1, DISP_BZ = 2;
+
 /// Order-preserving map of a float to an unsigned key (atomicMin / atomicMax on floats of either sign) and back.
 __device__ __forceinline__ uint32_t floatKey(float f) {
     const uint32_t b = __float_as_uint(f);
@@ -42,6 +45,8 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
     double lo[3] = { INFTY_REF, INFTY_REF, INFTY_REF }, hi[3] = { -INFTY_REF, -INFTY_REF, -INFTY_REF }, hm = 0.;
     double ratio2 = 0., grow = 0., hsum = 0., hNegMin0 = -INFTY_REF;
     const uint32_t overflowCell = d.grid->ncells;
+    const uint32_t dimx = (uint32_t)max(d.grid->dim[0], 1), dimy = (uint32_t)max(d.grid->dim[1], 1);
+    const uint32_t nbx = (dimx + (1u << DISP_BX) - 1u) >> DISP_BX, nby = (dimy + (1u << DISP_BY) - 1u) >> DISP_BY;
     const double gx = d.grid->lo[0], gy = d.grid->lo[1], gz = d.grid->lo[2]; // origin of the grid the lists were built on
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nActive; i += gridDim.x * blockDim.x) {
         double h = d.f[F_H][i];
@@ -66,16 +71,32 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
         const double rh0 = kernelRadius * (double)p0.w;
         ratio2 = fmax(ratio2, (ex * ex + ey * ey + ez * ez) / (rh0 * rh0));
         grow = fmax(grow, h / (double)p0.w - 1.);
-        if (trackCells) { // (cellOf belongs to the lists in use; large particles are paired directly every step)
+        // (cellOf belongs to the lists in use; large particles are paired directly every step)
+        uint32_t blk = 0xffffffffu;
+        if (trackCells) {
             const uint32_t c = d.cellOf[i];
             if (c < overflowCell) {
                 hNegMin0 = fmax(hNegMin0, -(double)p0.w);
-                atomicMin(&d.dispA[c], floatKey(__double2float_rd(ex)));
-                atomicMin(&d.dispA[cellStride + c], floatKey(__double2float_rd(ey)));
-                atomicMin(&d.dispA[2 * cellStride + c], floatKey(__double2float_rd(ez)));
-                atomicMax(&d.dispA[3 * cellStride + c], floatKey(__double2float_ru(ex)));
-                atomicMax(&d.dispA[4 * cellStride + c], floatKey(__double2float_ru(ey)));
-                atomicMax(&d.dispA[5 * cellStride + c], floatKey(__double2float_ru(ez)));
+                const uint32_t cx = c % dimx, cy = (c / dimx) % dimy, cz = c / (dimx * dimy);
+                blk = ((cz >> DISP_BZ) * nby + (cy >> DISP_BY)) * nbx + (cx >> DISP_BX);
+            }
+        }
+        // consecutive slots are neighbours along x on a lattice: the lanes of a warp fall into a few blocks; one set of
+        // atomics per block and warp
+        const unsigned active = __activemask();
+        const unsigned same = __match_any_sync(active, blk);
+        if (blk != 0xffffffffu) {
+            const uint32_t lx = __reduce_min_sync(same, floatKey(__double2float_rd(ex))), ly = __reduce_min_sync(same, floatKey(__double2float_rd(ey))),
+                           lz = __reduce_min_sync(same, floatKey(__double2float_rd(ez)));
+            const uint32_t ux = __reduce_max_sync(same, floatKey(__double2float_ru(ex))), uy = __reduce_max_sync(same, floatKey(__double2float_ru(ey))),
+                           uz = __reduce_max_sync(same, floatKey(__double2float_ru(ez)));
+            if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)same) - 1)) {
+                atomicMin(&d.dispA[blk], lx);
+                atomicMin(&d.dispA[cellStride + blk], ly);
+                atomicMin(&d.dispA[2 * cellStride + blk], lz);
+                atomicMax(&d.dispA[3 * cellStride + blk], ux);
+                atomicMax(&d.dispA[4 * cellStride + blk], uy);
+                atomicMax(&d.dispA[5 * cellStride + blk], uz);
             }
         }
     }
@@ -105,57 +126,42 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
 }
 
 // ---- relative displacement since the list build (ListCtlDev) ------------------------------------------------------------
-// One pass per axis widens every cell's displacement box to the union over its window (min / max commute with the key map,
-// so the keys are never decoded here; untouched cells hold the neutral keys ~0 / 0).
-template <int AXIS, int HALF>
-__global__ void __launch_bounds__(256) k_disp_dilate(DevicePointers d, const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-    uint32_t cellStride, bool trackCells) {
+/// Bound of |u_i - u_j| over the particles i of a block of cells and j of the 27 blocks around it -> dispGlobal[6] (largest
+/// over all blocks), and the global box of u -> dispGlobal[0..5]. Blocks are 4 x 2 x 4 cells (DISP_B*): one more block in
+/// every direction covers the candidate stencil (+-1 cell in x, y, +-2 in z) plus one more cell edge.
+__global__ void __launch_bounds__(256) k_disp_check(DevicePointers d, uint32_t cellStride, bool trackCells) {
     if (!trackCells) {
         return;
     }
     const GridDev g = *d.grid;
-    const int dimx = g.dim[0], dimy = g.dim[1], dimz = g.dim[2];
-    const int step = AXIS == 0 ? 1 : (AXIS == 1 ? dimx : dimx * dimy);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += gridDim.x * blockDim.x) {
-        const int cx = (int)(c % (uint32_t)dimx), cy = (int)((c / (uint32_t)dimx) % (uint32_t)dimy), cz = (int)(c / (uint32_t)(dimx * dimy));
-        const int pos = AXIS == 0 ? cx : (AXIS == 1 ? cy : cz), dim = AXIS == 0 ? dimx : (AXIS == 1 ? dimy : dimz);
-        const int a = max(pos - HALF, 0) - pos, b = min(pos + HALF, dim - 1) - pos;
-        uint32_t lo[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, hi[3] = { 0u, 0u, 0u };
-        for (int o = a; o <= b; ++o) {
-            const uint32_t e = (uint32_t)((int)c + o * step);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                lo[k] = min(lo[k], in[k * cellStride + e]);
-                hi[k] = max(hi[k], in[(3 + k) * cellStride + e]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            out[k * cellStride + c] = lo[k];
-            out[(3 + k) * cellStride + c] = hi[k];
-        }
-    }
-}
-
-/// Bound of |u_i - u_j| over the particles i of a cell and j of its window -> dispGlobal[6] (largest over all cells), and
-/// the global box of u -> dispGlobal[0..5].
-__global__ void __launch_bounds__(256) k_disp_check(DevicePointers d, const uint32_t* __restrict__ window, uint32_t cellStride, bool trackCells) {
-    if (!trackCells) {
-        return;
-    }
-    const GridDev g = *d.grid;
+    const int nbx = (g.dim[0] + (1 << DISP_BX) - 1) >> DISP_BX, nby = (g.dim[1] + (1 << DISP_BY) - 1) >> DISP_BY,
+              nbz = (g.dim[2] + (1 << DISP_BZ) - 1) >> DISP_BZ;
+    const uint32_t nBlocks = (uint32_t)(nbx * nby * nbz);
     uint32_t glo[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, ghi[3] = { 0u, 0u, 0u };
     float worst = 0.f;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncells; c += gridDim.x * blockDim.x) {
-        if (d.dispA[3 * cellStride + c] == 0u) {
-            continue; // no particle in this cell
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nBlocks; b += gridDim.x * blockDim.x) {
+        if (d.dispA[3 * cellStride + b] == 0u) {
+            continue; // no particle in this block
+        }
+        const int bx = (int)(b % (uint32_t)nbx), by = (int)((b / (uint32_t)nbx) % (uint32_t)nby), bz = (int)(b / (uint32_t)(nbx * nby));
+        uint32_t wlo[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, whi[3] = { 0u, 0u, 0u };
+        for (int z = max(bz - 1, 0); z <= min(bz + 1, nbz - 1); ++z) {
+            for (int y = max(by - 1, 0); y <= min(by + 1, nby - 1); ++y) {
+                for (int x = max(bx - 1, 0); x <= min(bx + 1, nbx - 1); ++x) {
+                    const uint32_t e = (uint32_t)((z * nby + y) * nbx + x);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { // (untouched blocks hold the neutral keys ~0 / 0)
+                        wlo[k] = min(wlo[k], d.dispA[k * cellStride + e]);
+                        whi[k] = max(whi[k], d.dispA[(3 + k) * cellStride + e]);
+                    }
+                }
+            }
         }
         float s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const uint32_t ol = d.dispA[k * cellStride + c], oh = d.dispA[(3 + k) * cellStride + c];
-            const float e = fmaxf(__fsub_ru(keyFloat(oh), keyFloat(window[k * cellStride + c])),
-                __fsub_ru(keyFloat(window[(3 + k) * cellStride + c]), keyFloat(ol)));
+            const uint32_t ol = d.dispA[k * cellStride + b], oh = d.dispA[(3 + k) * cellStride + b];
+            const float e = fmaxf(__fsub_ru(keyFloat(oh), keyFloat(wlo[k])), __fsub_ru(keyFloat(whi[k]), keyFloat(ol)));
             s2 = __fmaf_ru(e, e, s2);
             glo[k] = min(glo[k], ol);
             ghi[k] = max(ghi[k], oh);
@@ -512,18 +518,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevicePointers d, uint32_t nAct
 // in x already, so every cell ROW ends up sorted by x: the pair kernel finds the x-window a target can reach in a
 // candidate row by bisection. Also records the largest h of every cell (bound of the conservative FP32 pre-filter).
 constexpr int SORT_LOCAL = 48;
-__global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t maxCells) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= maxCells || d.listCtl->rebuild == 0u) {
-        return;
-    }
-    if (c >= d.grid->ncells) {
-        d.cellHmax[c] = 0u;
-        if (c == d.grid->ncells) {
-            d.grid->largeBegin = d.cellStart[c]; // first sorted index of the large particles
-        }
-        return;
-    }
+__device__ __forceinline__ void sortCell(const DevicePointers& d, uint32_t c) {
     const uint32_t s = d.cellStart[c], e = d.cellStart[c + 1];
     const uint32_t n = e - s;
     float hm = 0.f;
@@ -575,6 +570,30 @@ __global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t m
     }
 }
 
+__global__ void __launch_bounds__(128) k_sort_cells(DevicePointers d, uint32_t maxCells) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= maxCells || d.listCtl->rebuild == 0u) {
+        return;
+    }
+    const uint32_t ncells = d.grid->ncells;
+    if (c > ncells) {
+        d.cellHmax[c] = 0u;
+        return;
+    }
+    if (c == ncells) { // the overflow cell of the large particles
+        d.cellHmax[c] = 0u;
+        d.grid->largeBegin = d.cellStart[c]; // first sorted index of the large particles
+    } else {
+        sortCell(d, c);
+    }
+    // slot -> sorted index (the slot's rank inside its cell is no longer needed): the prologue runs over the SLOTS, reads
+    // the planes coalesced and scatters whole records
+    const uint32_t s = d.cellStart[c], e = d.cellStart[c + 1];
+    for (uint32_t a = s; a < e; ++a) {
+        d.rank[d.order[a]] = a;
+    }
+}
+
 int launchGridBuild(sphgpu_ctx* ctx) {
     const uint32_t n = ctx->nActive;
     cudaStream_t st = ctx->stream;
@@ -592,12 +611,9 @@ int launchGridBuild(sphgpu_ctx* ctx) {
     if (track) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        const uint32_t cb = (uint32_t)std::min<uint64_t>((uint64_t)sms * 8, ((uint64_t)ctx->maxCells + 255) / 256);
-        k_disp_dilate<0, 2><<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispA, ctx->d.dispB, cellStride, track);
-        k_disp_dilate<1, 2><<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispB, ctx->d.dispC, cellStride, track);
-        k_disp_dilate<2, 4><<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispC, ctx->d.dispB, cellStride, track);
-        k_disp_check<<<cb, 256, 0, st>>>(ctx->d, ctx->d.dispB, cellStride, track);
-        ctx->launches += 4;
+        const uint32_t cb = (uint32_t)std::min<uint64_t>((uint64_t)sms * 2, ((uint64_t)ctx->maxCells / 8 + 255) / 256 + 1);
+        k_disp_check<<<cb, 256, 0, st>>>(ctx->d, cellStride, track);
+        ctx->launches += 1;
     }
     k_grid_decide<<<1, 256, 0, st>>>(ctx->d, BOUNDS_BLOCKS, n, force, ctx->listSkin, ctx->prm.kernel_radius);
     k_hmax_small<<<BOUNDS_BLOCKS, 256, 0, st>>>(ctx->d, n);

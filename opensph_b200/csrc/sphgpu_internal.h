@@ -89,10 +89,10 @@ struct StatsDev {
 //     max_(i,j) |u_i - u_j| / (R h_min0)  +  max_i (h_i / h_i0 - 1)  <  skin,      u_i = r_i - r_i0,
 // with r_i0, h_i0 the values at build time (pos0) and the first maximum over all pairs that could reach each other. What
 // matters is the RELATIVE displacement of nearby particles -- a body that translates, rotates or expands smoothly keeps
-// its lists for a long time. k_bounds records the bounding box of u over the particles of every (build-time) cell,
-// k_disp_dilate_* widen it to the cells within +-2 (x, y) and +-4 (z) -- the candidate stencil plus one more cell edge --
-// k_disp_check bounds |u_i - u_j| for every cell against its window; pairs further apart than that are covered by the
-// global extent of u staying below 0.9 cell edges. k_grid_decide decides.
+// its lists for a long time. k_bounds records the bounding box of u over the particles of every block of 4 x 2 x 4
+// (build-time) cells; k_disp_check bounds |u_i - u_j| for every block against the 27 blocks around it -- which contain the
+// candidate stencil plus at least one more cell edge --; pairs further apart than that are covered by the global extent
+// of u staying below 0.9 cell edges. k_grid_decide decides.
 struct ListCtlDev {
     uint32_t rebuild;       // decision of the current integrate(): the build kernels run (1) or return at once (0)
     uint32_t age;           // integrate() calls served by the current lists after the one that built them
@@ -136,13 +136,13 @@ struct DevicePointers {
     uint32_t* largeCounter; // [LARGE_MAX] slices of a large target that have finished
     ListCtlDev* listCtl;
     uint32_t* cellHmax; // [maxCells] bit pattern of the largest (float) h inside each cell
-    // displacement boxes of the list reuse (ListCtlDev): order-preserving uint keys of floats, plane k of (maxCells + 1)
-    // entries = lower (k = 0..2) / upper (k = 3..5) bound of u_x, u_y, u_z; dispA = per cell, dispB / dispC = dilated
-    uint32_t *dispA, *dispB, *dispC;
+    // displacement boxes of the list reuse (ListCtlDev), one per block of 4 x 2 x 4 cells: order-preserving uint keys of
+    // floats, plane k of (maxCells + 1) entries = lower (k = 0..2) / upper (k = 3..5) bound of u_x, u_y, u_z
+    uint32_t* dispA;
     uint32_t* dispGlobal; // [8] global lower / upper keys of u, [6] float bits of the largest relative displacement bound
     uint32_t* order;    // sorted position -> slot
     uint32_t* cellOf;   // slot -> cell
-    uint32_t* rank;     // slot -> rank inside its cell
+    uint32_t* rank;     // slot -> rank inside its cell during the build, afterwards slot -> sorted position (inverse of order)
     uint32_t* cellStart; // [maxCells + 1] exclusive prefix of counts
     uint32_t* cellCount; // [maxCells + 1]
     uint32_t* scanBlock; // block sums of the scan
