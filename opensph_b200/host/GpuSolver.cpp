@@ -114,10 +114,14 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
             return &Access::radius;
         }
     };
+    if (typeid(*bc) == typeid(KillEscapersBoundary)) {
+        hostBc = std::move(bc);
+        return;
+    }
     FrozenParticles* frozen = dynamic_cast<FrozenParticles*>(&*bc);
     if (!frozen || typeid(*frozen) != typeid(FrozenParticles)) {
-        throw InvalidSetup("GpuSolver: this boundary condition has no device implementation (NullBoundaryCondition and "
-                           "FrozenParticles have)");
+        throw InvalidSetup("GpuSolver: this boundary condition is not implemented (NullBoundaryCondition, FrozenParticles and "
+                           "KillEscapersBoundary are)");
     }
     for (const Size flag : frozen->*Access::flags()) {
         if (flag >= 64) {
@@ -526,11 +530,17 @@ void GpuSolver::integrate(Storage& storage, Statistics& stats) {
     // what the reference's accumulate-into-zero amounts to.
     Timer timer;
     this->attachMirror(storage);
+    if (hostBc) { // beforeLoop: bc->initialize (AsymmetricSolver.cpp:143); removed particles re-create the device mirror
+        hostBc->initialize(storage);
+    }
     this->uploadQuantities(storage, false);
     sphgpu_stats st{};
     const Float t = stats.getOr<Float>(StatisticsId::RUN_TIME, 0._f);
     check(sphgpu_integrate(ctx, t, &st));
     this->downloadQuantities(storage, false);
+    if (hostBc) {
+        hostBc->finalize(storage);
+    }
     stats.set(StatisticsId::SPH_EVAL_TIME, int(timer.elapsed(TimerUnit::MILLISECOND))); // as AsymmetricSolver.cpp:92
 
     // neighbour statistics as AsymmetricSolver::afterLoop stores them (AsymmetricSolver.cpp:218-225)
@@ -648,6 +658,10 @@ public:
 GpuPredictorCorrector::GpuPredictorCorrector(const SharedPtr<Storage>& storage, const RunSettings& settings, GpuSolver& solver)
     : ITimeStepping(storage, settings, makeAuto<DeviceCriterion>(lastStep))
     , gpu(solver) {
+    if (solver.hasHostBoundary()) {
+        throw InvalidSetup("GpuPredictorCorrector: the solver's boundary condition works on the host Storage every step; use the "
+                           "reference's PredictorCorrector with this GpuSolver");
+    }
     lastStep.value = settings.get<Float>(RunSettingsId::TIMESTEPPING_INITIAL_TIMESTEP);
     lastStep.id = CriterionId::INITIAL_VALUE;
     // PredictorCorrector's constructor clears the derivatives before the first step (TimeStepping.cpp:280-281)

@@ -55,6 +55,11 @@ private:
     /// True while the device holds a newer state than the Storage (after GpuPredictorCorrector steps).
     bool hostStale = false;
 
+    /// KillEscapersBoundary handed to the constructor: it only removes particles from the Storage
+    /// (Boundary.cpp:445-454), which it does on the host at the start of integrate(); the device mirror follows through
+    /// IStorageUserData. Needs the Storage every call, so it cannot be combined with GpuPredictorCorrector.
+    AutoPtr<IBoundaryCondition> hostBc;
+
     /// FrozenParticles boundary condition taken over from the reference object handed to the constructor
     bool frozenActive = false;
     unsigned long long frozenMask = 0;
@@ -77,7 +82,8 @@ public:
     /// The signature Factory::getSolver uses (AsymmetricSolver.h:126-129). Boundary conditions with a device
     /// implementation: none (nullptr / NullBoundaryCondition) and FrozenParticles (core/sph/boundary/Boundary.h:162-197) with
     /// frozen bodies and / or a SphericalDomain -- its settings are read from the object and applied on the device after
-    /// every evaluation (sphgpu_set_frozen). Anything else throws InvalidSetup.
+    /// every evaluation (sphgpu_set_frozen) -- and KillEscapersBoundary (Boundary.h), whose removal of particles from the
+    /// Storage runs on the host at the start of integrate(). Anything else throws InvalidSetup.
     GpuSolver(IScheduler& scheduler, const RunSettings& settings, const EquationHolder& eqs, AutoPtr<IBoundaryCondition>&& bc,
         const int device = 0);
 
@@ -103,6 +109,11 @@ public:
     /// \return false -- and nothing changes -- if the settings ask for something the device does not implement
     ///         (SphericalGravity, solid-sphere kernel, symmetric boundary, cached gravity, opening angle above 1).
     bool enableDeviceGravity();
+
+    /// True if a boundary condition runs on the host inside integrate() (KillEscapersBoundary).
+    bool hasHostBoundary() const {
+        return bool(hostBc);
+    }
 
     bool hasDeviceGravity() const {
         return deviceGravity;

@@ -384,11 +384,32 @@ int main(int argc, char** argv) {
             GpuSolver viaFactorySignature(*scheduler, settings, eqs, makeAuto<NullBoundaryCondition>());
             bool bcThrown = false;
             try {
-                GpuSolver withBc(*scheduler, settings, eqs, makeAuto<KillEscapersBoundary>(makeAuto<SphericalDomain>(Vector(0._f), 1._f)));
+                GpuSolver withBc(*scheduler, settings, eqs, makeAuto<GhostParticles>(makeAuto<SphericalDomain>(Vector(0._f), 1._f), settings));
             } catch (const InvalidSetup&) {
                 bcThrown = true;
             }
-            expect(bcThrown, "a real boundary condition is rejected with InvalidSetup");
+            expect(bcThrown, "a boundary condition without an implementation (GhostParticles) is rejected with InvalidSetup");
+            // KillEscapersBoundary removes the particles outside its domain from the Storage at the start of integrate()
+            {
+                Float rmax = 0._f;
+                ArrayView<const Vector> rr = base->getValue<Vector>(QuantityId::POSITION);
+                for (Size i = 0; i < rr.size(); ++i) {
+                    rmax = max(rmax, getLength(rr[i]));
+                }
+                AsymmetricSolver refK(*scheduler, settings, eqs, makeAuto<KillEscapersBoundary>(makeShared<SphericalDomain>(Vector(0._f), 0.93_f * rmax)));
+                GpuSolver gpuK(*scheduler, settings, eqs, makeAuto<KillEscapersBoundary>(makeShared<SphericalDomain>(Vector(0._f), 0.93_f * rmax)));
+                Storage ka = base->clone(VisitorEnum::ALL_BUFFERS), kb = base->clone(VisitorEnum::ALL_BUFFERS);
+                const Size before = ka.getParticleCnt();
+                ka.zeroHighestDerivatives(*scheduler);
+                kb.zeroHighestDerivatives(*scheduler);
+                refK.integrate(ka, statsA);
+                gpuK.integrate(kb, statsA);
+                printf("  [KillEscapersBoundary] %u -> %u particles (reference), %u (GpuSolver)\n", unsigned(before), unsigned(ka.getParticleCnt()),
+                    unsigned(kb.getParticleCnt()));
+                expect(ka.getParticleCnt() < before && ka.getParticleCnt() == kb.getParticleCnt(), "escapers are removed from both Storages");
+                expect(sameNeighbourCounts(ka, kb), "NEIGHBOR_CNT identical after the removal");
+                expect(compareStorages(ka, kb, true, "integrate() with KillEscapersBoundary") <= 1.e-10, "all quantities within 1e-10 with KillEscapersBoundary");
+            }
         }
         // ---- the XSph term (SPH_USE_XSPH): two consecutive evaluations, so that the second one starts from velocities that
         // contain the correction of the first (XSph::initialize / finalize, XSph.h:69-90)
