@@ -247,6 +247,7 @@ int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, u
 int launchPredict(sphgpu_ctx* ctx, double dt);
 int launchCorrect(sphgpu_ctx* ctx, double dt);
 int launchCorrectPredict(sphgpu_ctx* ctx); // corrector of the step that ends + predictor of the next one (sphgpu_run_pc)
+int launchCorrectPredictRange(sphgpu_ctx* ctx, uint32_t first, uint32_t end); // the same for the slots [first, end)
 int launchEuler(sphgpu_ctx* ctx, double dt);
 int launchCriteria(sphgpu_ctx* ctx);
 int launchFrozen(sphgpu_ctx* ctx); // FrozenParticles::finalize, when configured

@@ -132,8 +132,10 @@ __global__ void __launch_bounds__(256) k_correct(DevicePointers d, uint32_t n, d
 #define INTEG_MIN_CTAS 4
 #endif
 template <bool SOLID>
-__global__ void __launch_bounds__(256, INTEG_MIN_CTAS) k_correct_predict(DevicePointers d, uint32_t n, bool hasDamage) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256, INTEG_MIN_CTAS) k_correct_predict(DevicePointers d, uint32_t first, uint32_t n, bool hasDamage) {
+    // particles [first, n): the whole owned range, or -- decomposed runs -- the send bands first and the interior while the
+    // bands are already on their way to the neighbours (halo.cu)
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) {
         return;
     }
@@ -458,21 +460,24 @@ int launchCorrect(sphgpu_ctx* ctx, double dt) {
     return SPHGPU_OK;
 }
 
-int launchCorrectPredict(sphgpu_ctx* ctx) {
+int launchCorrectPredictRange(sphgpu_ctx* ctx, uint32_t first, uint32_t end) {
     {
         const int rcConst = ensureConstants(ctx);
         if (rcConst != SPHGPU_OK) {
             return rcConst;
         }
     }
-    const uint32_t n = ctx->n;
-    if (n == 0) {
+    if (end <= first) {
         return SPHGPU_OK;
     }
-    const uint32_t blocks = (n + 255) / 256;
-    SPH_DISPATCH_SOLID(k_correct_predict, ctx->d, n, ctx->hasDamage);
+    const uint32_t blocks = (end - first + 255) / 256;
+    SPH_DISPATCH_SOLID(k_correct_predict, ctx->d, first, end, ctx->hasDamage);
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
+}
+
+int launchCorrectPredict(sphgpu_ctx* ctx) {
+    return launchCorrectPredictRange(ctx, 0u, ctx->n);
 }
 
 int launchEuler(sphgpu_ctx* ctx, double dt) {
