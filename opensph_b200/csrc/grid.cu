@@ -43,7 +43,7 @@ __device__ __forceinline__ float keyFloat(uint32_t k) {
 __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActive, bool clampH, double hMin, double hMax, double kernelRadius,
     bool trackCells, uint32_t cellStride) {
     double lo[3] = { INFTY_REF, INFTY_REF, INFTY_REF }, hi[3] = { -INFTY_REF, -INFTY_REF, -INFTY_REF }, hm = 0.;
-    double ratio2 = 0., grow = 0., hsum = 0., hNegMin0 = -INFTY_REF;
+    double grow = 0., hsum = 0., hNegMin0 = -INFTY_REF;
     const uint32_t overflowCell = d.grid->ncells;
     const uint32_t dimx = (uint32_t)max(d.grid->dim[0], 1), dimy = (uint32_t)max(d.grid->dim[1], 1);
     const uint32_t nbx = (dimx + (1u << DISP_BX) - 1u) >> DISP_BX, nby = (dimy + (1u << DISP_BY) - 1u) >> DISP_BY;
@@ -68,8 +68,6 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
         hsum += h;
         const float4 p0 = d.pos0[i];
         const double ex = (x - gx) - (double)p0.x, ey = (y - gy) - (double)p0.y, ez = (z - gz) - (double)p0.z;
-        const double rh0 = kernelRadius * (double)p0.w;
-        ratio2 = fmax(ratio2, (ex * ex + ey * ey + ez * ez) / (rh0 * rh0));
         grow = fmax(grow, h / (double)p0.w - 1.);
         // (cellOf belongs to the lists in use; large particles are paired directly every step)
         uint32_t blk = 0xffffffffu;
@@ -107,7 +105,7 @@ __global__ void __launch_bounds__(256) k_bounds(DevicePointers d, uint32_t nActi
     __shared__ double sm[8][11];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double v[11] = { warpMin(lo[0]), warpMin(lo[1]), warpMin(lo[2]), warpMax(hi[0]), warpMax(hi[1]), warpMax(hi[2]), warpMax(hm),
-        warpMax(ratio2), warpMax(grow), hsum, hNegMin0 };
+        0. /* (was: largest absolute displacement) */, warpMax(grow), hsum, hNegMin0 };
     if (lane == 0) {
         for (int k = 0; k < 11; ++k) {
             sm[warp][k] = v[k];

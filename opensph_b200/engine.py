@@ -16,7 +16,8 @@ import numpy as np
 
 from . import abi
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsphgpu.so")
+# (SPHGPU_LIB selects another build of the same library, e.g. one compiled with different tile parameters, for A/B runs)
+_LIB_PATH = os.environ.get("SPHGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsphgpu.so")
 _lib: Optional[C.CDLL] = None
 
 
