@@ -34,7 +34,7 @@ namespace sph {
 
 constexpr int GRAV_GROUP = 32;         // targets per group (one per lane)
 constexpr int GRAV_WARPS = 4;          // warps (groups in flight) per CTA of the walk
-constexpr int GRAV_STACK = 2048;       // stack entries per warp
+constexpr int GRAV_STACK = 1024;       // stack entries per warp (a nearly full stack is drained one node at a time, see the walk)
 constexpr uint32_t GRAV_NONE = 0xffffffffu;
 
 struct GravDev {
@@ -503,7 +503,9 @@ __global__ void __launch_bounds__(GRAV_WARPS * 32) k_grav_walk(DevicePointers p,
             sp = 1;
             __syncwarp();
             while (sp > 0) {
-                const int take = min(sp, 32);
+                // 32 nodes per trip push at most 64 children; when that might not fit, one node per trip (at most two
+                // children for one popped node): the depth-first walk then needs no more entries than the tree is deep
+                const int take = sp + 64 > GRAV_STACK ? 1 : min(sp, 32);
                 sp -= take;
                 int4 meta = make_int4(0, 0, 0, -1);
                 uint32_t nodeId = 0;
