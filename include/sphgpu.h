@@ -392,8 +392,12 @@ SPHGPU_API int sphgpu_last_halo_ms(sphgpu_ctx* ctx, double* ms);
  * be uploaded again, including MATERIAL_ID for more than one material; ghosts are dropped (n_active = n). */
 SPHGPU_API int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles);
 /* Selects the pair-kernel variant: 0 = default (candidate lists in their own kernel + tiled pair sums), 1 = direct
- * per-thread kernel, 2 = tiled kernel with both phases fused, 3 = as 0 with a tiny list pool (exercises the overflow
- * path). For A/B checks only. */
+ * per-thread kernel, 2 = every work unit through the direct per-target loop, 3 = as 0 with a tiny list pool (exercises the
+ * overflow path) -- all of them the asymmetric formulation of AsymmetricSolver::loop --, 4 = the SYMMETRIC formulation of
+ * SymmetricSolver::loop (core/sph/solvers/SymmetricSolver.cpp:104-163): particles ranked by smoothing length (makeRankH,
+ * core/objects/finders/Order.h:46-58), every pair evaluated once by its particle of higher rank (findLowerRank) and added to
+ * both particles (evalSymmetric; NeighborCountTerm, HelperTerms.h:16-47). Same results to rounding; slower (FP64 atomics),
+ * without the correction tensor (as in the reference), the Balsara switch and XSph. */
 SPHGPU_API int sphgpu_set_variant(sphgpu_ctx* ctx, int variant);
 /* Reuse of the cell list / work units / candidate lists over several steps (the reference rebuilds its finder in every
  * ISolver::integrate, AsymmetricSolver.cpp:81-84; results do not depend on this setting beyond summation order, because

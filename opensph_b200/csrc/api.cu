@@ -311,6 +311,7 @@ int sphgpu_destroy(sphgpu_ctx* ctx) {
     forgetConstants(ctx);
     destroyHalo(ctx);
     destroyGravity(ctx);
+    destroySymmetric(ctx);
     for (int f = 0; f < F_COUNT; ++f) cudaFree(ctx->d.f[f]);
     for (int u = 0; u < U_COUNT; ++u) cudaFree(ctx->d.u[u]);
     cudaFree(ctx->d.rec); cudaFree(ctx->d.segStart); cudaFree(ctx->d.unitDesc); cudaFree(ctx->d.unitAux); cudaFree(ctx->d.unitLane); cudaFree(ctx->d.unitList);
@@ -521,6 +522,11 @@ int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles) {
 
 int sphgpu_set_variant(sphgpu_ctx* ctx, int variant) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (variant < 0 || variant > 4) return fail(SPHGPU_E_INVALID, "pair-kernel variant must be 0 .. 4");
+    if (variant == 4 && (ctx->corrected || ctx->balsara || ctx->xsph)) {
+        return fail(SPHGPU_E_INVALID, "the symmetric formulation (variant 4) offers neither the correction tensor (like SymmetricSolver, "
+                                      "SymmetricSolver.cpp:41-44) nor the Balsara switch / XSph");
+    }
     if (ctx->variant != variant) {
         ctx->listsDirty = true; // variant 3 builds its lists against a different pool size
     }

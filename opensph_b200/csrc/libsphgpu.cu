@@ -4,6 +4,7 @@
 #include "grid.cu"
 #include "pair.cu"
 #include "pair_tiled.cu"
+#include "pair_symmetric.cu"
 #include "stepping.cu"
 #include "transfer.cu"
 #include "halo.cu"

@@ -606,6 +606,9 @@ int launchPair(sphgpu_ctx* ctx) {
             return rcLarge;
         }
     }
+    if (ctx->variant == 4) { // every pair once, both particles (SymmetricSolver)
+        return launchPairSymmetric(ctx);
+    }
     if (ctx->variant != 1) {
         return launchPairTiled(ctx);
     }

@@ -213,6 +213,7 @@ struct sphgpu_ctx {
     uint32_t launches = 0;
     bool stateUploaded = false;
     void* halo = nullptr;      // sph::HaloState (halo.cu): NCCL communicator + exchange buffers
+    void* symmetric = nullptr; // sph::SymState (pair_symmetric.cu): buffers of the symmetric formulation (variant 4)
     bool hasFrozen = false;    // FrozenParticles boundary condition (sphgpu_set_frozen)
     sphgpu_frozen frozen{};
     void* gravity = nullptr;   // sph::GravState (gravity.cu): self-gravity, when configured
@@ -241,6 +242,8 @@ void forgetConstants(const sphgpu_ctx* ctx);
 int launchProloguePack(sphgpu_ctx* ctx);
 int launchProloguePackPositionsOnly(sphgpu_ctx* ctx);
 int launchPair(sphgpu_ctx* ctx);
+int launchPairSymmetric(sphgpu_ctx* ctx); // pair_symmetric.cu
+void destroySymmetric(sphgpu_ctx* ctx);
 int launchNeighbourCount(sphgpu_ctx* ctx, uint32_t* countsDev);
 int launchNeighbourFill(sphgpu_ctx* ctx, const unsigned long long* offsetsDev, uint32_t* idxDev);
 // stepping.cu

@@ -146,6 +146,10 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     frozenActive = frozenMask != 0 || frozenDomain;
 }
 
+void GpuSolver::configureVariant() {
+    check(sphgpu_set_variant(ctx, pairVariant));
+}
+
 void GpuSolver::configureFrozen() {
     sphgpu_frozen f{};
     f.flag_mask = frozenMask;
@@ -313,6 +317,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     }
     if (frozenActive) {
         this->configureFrozen();
+    }
+    if (pairVariant != 0) {
+        this->configureVariant();
     }
     return ctx;
 }

@@ -55,6 +55,9 @@ private:
     /// True while the device holds a newer state than the Storage (after GpuPredictorCorrector steps).
     bool hostStale = false;
 
+    /// 0 = asymmetric kernels (default), 4 = the symmetric formulation of SymmetricSolver (sphgpu_set_variant)
+    int pairVariant = 0;
+
     /// KillEscapersBoundary handed to the constructor: it only removes particles from the Storage
     /// (Boundary.cpp:445-454), which it does on the host at the start of integrate(); the device mirror follows through
     /// IStorageUserData. Needs the Storage every call, so it cannot be combined with GpuPredictorCorrector.
@@ -66,6 +69,7 @@ private:
     bool frozenDomain = false;
     double frozenCenter[3] = { 0., 0., 0. }, frozenRadius = 0., frozenFreezeRadius = 0.;
     void configureFrozen();
+    void configureVariant();
 
     /// Self-gravity on the device (enableDeviceGravity): applied to every context this solver creates.
     bool deviceGravity = false;
@@ -109,6 +113,18 @@ public:
     /// \return false -- and nothing changes -- if the settings ask for something the device does not implement
     ///         (SphericalGravity, solid-sphere kernel, symmetric boundary, cached gravity, opening angle above 1).
     bool enableDeviceGravity();
+
+    /// Evaluates every pair once and adds it to both particles, like SymmetricSolver<3>::loop
+    /// (core/sph/solvers/SymmetricSolver.cpp:104-163: rank by smoothing length, findLowerRank, evalSymmetric), instead of
+    /// the asymmetric kernels. Same results to rounding, several times slower; not with the correction tensor (the
+    /// reference's SymmetricSolver rejects it as well), the Balsara switch or XSph (InvalidSetup at the first integrate).
+    /// Setups with SolverEnum::SYMMETRIC_SOLVER are served by the asymmetric kernels unless this is switched on.
+    void useSymmetricFormulation(const bool symmetric) {
+        pairVariant = symmetric ? 4 : 0;
+        if (ctx) {
+            this->configureVariant();
+        }
+    }
 
     /// True if a boundary condition runs on the host inside integrate() (KillEscapersBoundary).
     bool hasHostBoundary() const {

@@ -435,6 +435,23 @@ int main(int argc, char** argv) {
             printf("    %-28s %.3e\n", "XSPH_VELOCITIES", xe);
             expect(xe <= 1.e-10, "XSPH_VELOCITIES within 1e-10");
         }
+        // ---- the symmetric formulation: SymmetricSolver<3> of the reference next to GpuSolver::useSymmetricFormulation ----
+        {
+            RunSettings ss = settings;
+            ss.set(RunSettingsId::SPH_SOLVER_TYPE, SolverEnum::SYMMETRIC_SOLVER).set(RunSettingsId::SPH_STRAIN_RATE_CORRECTION_TENSOR, false);
+            const EquationHolder seqs = getStandardEquations(ss);
+            SymmetricSolver<3> refS(*scheduler, ss, seqs);
+            GpuSolver gpuS(*scheduler, ss, seqs);
+            gpuS.useSymmetricFormulation(true);
+            Storage sa2 = base->clone(VisitorEnum::ALL_BUFFERS), sb2 = base->clone(VisitorEnum::ALL_BUFFERS);
+            sa2.zeroHighestDerivatives(*scheduler);
+            sb2.zeroHighestDerivatives(*scheduler);
+            refS.integrate(sa2, statsA);
+            gpuS.integrate(sb2, statsA);
+            expect(sameNeighbourCounts(sa2, sb2), "NEIGHBOR_CNT identical (NeighborCountTerm of the SymmetricSolver vs device)");
+            expect(compareStorages(sa2, sb2, true, "SymmetricSolver<3> vs the device's symmetric formulation") <= 1.e-10,
+                "all quantities within 1e-10 (symmetric formulation)");
+        }
         // ---- FrozenParticles boundary condition handed to the solvers' Factory constructor ----
         {
             auto makeBc = [&]() {
