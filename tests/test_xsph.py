@@ -106,3 +106,21 @@ def test_gpu_xsph_is_rejected_where_it_is_not_implemented(lut):
     with pytest.raises(SphGpuError) as e:
         Engine(setup, len(i["mass"]))
     assert e.value.code == abi.E_INVALID
+
+
+@pytest.mark.gpu
+def test_gpu_xsph_batched_steps_match_golden(lut):
+    """The same three steps queued back to back (sphgpu_run_pc: fused corrector + predictor, time step fed back on the device)."""
+    from opensph_b200.engine import Engine
+    i, o = golden("xsph_in.snap"), golden("xsph_pc3.snap")
+    setup = abi.setup_from_snapshot(i, lut)
+    consts = abi.run_constants(i)
+    dts = o["dt_history"]
+    with Engine(setup, len(i["mass"])) as eng:
+        eng.upload_state(i, STATE_IN + ("acc", "drho", "du", "dS", "ddamage"))
+        eng.set_last_timestep(consts["initial_dt"])
+        hist, _, _ = eng.run_pc(len(dts) - 1, float(dts[0]), consts["max_dt"])
+        got = eng.download_state(["pos", "vel", "rho", "u", "S", "damage", "xsph"])
+    assert np.allclose(hist, dts[1:], rtol=1e-9, atol=0)
+    for k, v in got.items():
+        assert_close(k, v, o[k], 1e-9, FLOOR)
