@@ -53,9 +53,14 @@ enum {
     SPHGPU_FLAG_SOUND_SPEED_ENFORCING = 1u << 3, /* SmoothingLengthEnum::SOUND_SPEED_ENFORCING               */
     SPHGPU_FLAG_BALSARA = 1u << 4,              /* RunSettingsId::SPH_AV_USE_BALSARA: BalsaraSwitch<StandardAV>,
                                                    core/sph/equations/av/Balsara.h:36-153                      */
-    SPHGPU_FLAG_XSPH = 1u << 5                  /* RunSettingsId::SPH_USE_XSPH: the XSph term, core/sph/equations/XSph.h:20-97;
+    SPHGPU_FLAG_XSPH = 1u << 5,                 /* RunSettingsId::SPH_USE_XSPH: the XSph term, core/sph/equations/XSph.h:20-97;
                                                    its epsilon is set with sphgpu_set_xsph_epsilon. Not together with
                                                    SPHGPU_FLAG_BALSARA, not on decomposed runs                 */
+    SPHGPU_FLAG_DELTASPH = 1u << 6              /* RunSettingsId::SPH_USE_DELTASPH: DeltaSph::DensityDiffusion and
+                                                   DeltaSph::VelocityDiffusion, core/sph/equations/DeltaSph.h:12-189
+                                                   (StandardSets.cpp:64-67); coefficients: sphgpu_set_deltasph. Not together
+                                                   with SPHGPU_FLAG_BALSARA or SPHGPU_FLAG_XSPH, not on decomposed runs; with
+                                                   SPHGPU_FLAG_CORRECTION_TENSOR only for solids                  */
 };
 enum { SPHGPU_DISCR_STANDARD = 0, SPHGPU_DISCR_BENZ_ASPHAUG = 1 };        /* DiscretizationEnum            */
 enum { SPHGPU_CONTINUITY_STANDARD = 0, SPHGPU_CONTINUITY_SUM_ONLY_UNDAMAGED = 1 }; /* ContinuityEnum       */
@@ -105,7 +110,9 @@ enum {
                                          their [begin,end) ranges, must be uploaded for ghost particles      */
     SPHGPU_Q_VELOCITY_ROTATION = 19,  /* Vector {x,y,z,0}: nabla x v, input and output of the Balsara switch  */
     SPHGPU_Q_XSPH_VELOCITIES = 20,    /* Vector {x,y,z,0}: the velocity correction the XSph term left in the velocities */
-    SPHGPU_Q_COUNT = 21
+    SPHGPU_Q_DELTASPH_DENSITY_GRADIENT = 21, /* Vector {x,y,z,0}: the renormalised density gradient, output of one
+                                         evaluation and input of the next (DeltaSph.h:16-44,71-74)          */
+    SPHGPU_Q_COUNT = 22
 };
 
 /* Host memory layouts understood by upload/download. */
@@ -412,6 +419,11 @@ SPHGPU_API int sphgpu_set_list_skin(sphgpu_ctx* ctx, double skin);
  * new one (XSph.h:69-90): sphgpu_integrate does both, so POSITION dt holds the corrected velocities between calls and
  * SPHGPU_Q_XSPH_VELOCITIES the correction, exactly like the Storage of the reference. Default 1 (Settings.cpp). */
 SPHGPU_API int sphgpu_set_xsph_epsilon(sphgpu_ctx* ctx, double epsilon);
+/* RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA and SPH_VELOCITY_DIFFUSION_ALPHA of the delta-SPH terms (SPHGPU_FLAG_DELTASPH;
+ * DeltaSph.h:63-65,135-137). Every evaluation stores the renormalised density gradient sum_j m_j/rho_j (rho_j - rho_i)
+ * C_i grad W_ij in SPHGPU_Q_DELTASPH_DENSITY_GRADIENT; the density diffusion of the NEXT evaluation reads it, as the
+ * reference does through its Storage (zero before the first evaluation). Defaults 0.01, 0.01 (Settings.cpp:541-544). */
+SPHGPU_API int sphgpu_set_deltasph(sphgpu_ctx* ctx, double delta, double alpha);
 SPHGPU_API int sphgpu_list_stats(sphgpu_ctx* ctx, uint32_t* rebuilds, uint32_t* age, double* metric);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
  * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the

@@ -14,6 +14,7 @@ OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_OOM, E_STATE = 0, -1, -2, -3, -4, -5
 FORCE_PRESSURE, FORCE_SOLID_STRESS = 1, 2
 FLAG_CORRECTION_TENSOR, FLAG_SUM_ONLY_UNDAMAGED, FLAG_ADAPTIVE_H, FLAG_SOUND_SPEED_ENFORCING, FLAG_BALSARA = 1, 2, 4, 8, 16
 FLAG_XSPH = 32
+FLAG_DELTASPH = 64
 EOS_NONE, EOS_IDEAL_GAS, EOS_TILLOTSON = 0, 1, 4
 YIELD_NONE, YIELD_ELASTIC, YIELD_VON_MISES, YIELD_DUST = 0, 1, 2, 4
 FRACTURE_NONE, FRACTURE_SCALAR_GRADY_KIPP = 0, 1
@@ -43,6 +44,7 @@ QUANTITIES: Dict[str, Tuple[int, int, type]] = {
     "MATERIAL_ID": (18, 1, np.uint32),
     "VELOCITY_ROTATION": (19, 4, np.float64),
     "XSPH_VELOCITIES": (20, 4, np.float64),
+    "DELTASPH_DENSITY_GRADIENT": (21, 4, np.float64),
 }
 
 # snapshot array name -> (quantity, order)
@@ -55,6 +57,7 @@ SNAPSHOT_FIELDS: Dict[str, Tuple[str, int]] = {
     "divv": ("VELOCITY_DIVERGENCE", 0), "gradv": ("VELOCITY_GRADIENT", 0), "corr": ("CORRECTION_TENSOR", 0),
     "eps_min": ("EPS_MIN", 0), "m_zero": ("M_ZERO", 0), "growth": ("EXPLICIT_GROWTH", 0),
     "n_flaws": ("N_FLAWS", 0), "flag": ("FLAG", 0), "ncnt": ("NEIGHBOR_CNT", 0), "xsph": ("XSPH_VELOCITIES", 0),
+    "drho_grad": ("DELTASPH_DENSITY_GRADIENT", 0),
 }
 
 
@@ -162,6 +165,8 @@ class RunSetup:
         self.cfg.lut_value = self.lut_value.ctypes.data_as(C.POINTER(C.c_double))
         self.cfg.lut_entries = len(self.lut_grad) - 1
         self.xsph_eps = 1.0  # SPH_XSPH_EPSILON (used with FLAG_XSPH; Engine passes it to sphgpu_set_xsph_epsilon)
+        self.deltasph_delta = 0.01  # SPH_DENSITY_DIFFUSION_DELTA, SPH_VELOCITY_DIFFUSION_ALPHA (used with FLAG_DELTASPH;
+        self.deltasph_alpha = 0.01  # Engine passes them to sphgpu_set_deltasph)
 
     @property
     def solid(self) -> bool:
@@ -193,7 +198,8 @@ def setup_from_snapshot(snap: Dict[str, np.ndarray], lut: Dict[str, np.ndarray] 
     cfg.forces = (FORCE_PRESSURE if rp[3] else 0) | (FORCE_SOLID_STRESS if rp[4] else 0)
     cfg.flags = ((FLAG_CORRECTION_TENSOR if (rp[5] and rp[4]) else 0) | (FLAG_SUM_ONLY_UNDAMAGED if rp[6] else 0)
                  | (FLAG_ADAPTIVE_H if rp[7] else 0) | (FLAG_SOUND_SPEED_ENFORCING if rp[8] else 0)
-                 | (FLAG_BALSARA if (len(rp) > 25 and rp[25]) else 0) | (FLAG_XSPH if (len(rp) > 26 and rp[26]) else 0))
+                 | (FLAG_BALSARA if (len(rp) > 25 and rp[25]) else 0) | (FLAG_XSPH if (len(rp) > 26 and rp[26]) else 0)
+                 | (FLAG_DELTASPH if (len(rp) > 28 and rp[28]) else 0))
     cfg.continuity_mode = int(rp[9])
     cfg.discretization = int(rp[10])
     cfg.h_min, cfg.h_max = rp[11], rp[12]
@@ -218,6 +224,8 @@ def setup_from_snapshot(snap: Dict[str, np.ndarray], lut: Dict[str, np.ndarray] 
     setup = RunSetup(cfg, mats, lut["lut_grad"], lut["lut_val"])
     if len(rp) > 27:
         setup.xsph_eps = float(rp[27])
+    if len(rp) > 30:
+        setup.deltasph_delta, setup.deltasph_alpha = float(rp[29]), float(rp[30])
     return setup
 
 

@@ -54,6 +54,14 @@ static int validate(const sphgpu_config* cfg, const sphgpu_material* mats, uint3
             return fail(SPHGPU_E_INVALID, "the XSph term together with the Balsara switch is not implemented on the GPU path");
         }
     }
+    if (cfg->flags & SPHGPU_FLAG_DELTASPH) {
+        if (cfg->flags & (SPHGPU_FLAG_BALSARA | SPHGPU_FLAG_XSPH)) {
+            return fail(SPHGPU_E_INVALID, "the delta-SPH terms together with the Balsara switch or the XSph term are not implemented on the GPU path");
+        }
+        if ((cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR) && !(cfg->forces & SPHGPU_FORCE_SOLID_STRESS)) {
+            return fail(SPHGPU_E_INVALID, "the delta-SPH terms with the correction tensor need ForceEnum::SOLID_STRESS on the GPU path");
+        }
+    }
     if (!(cfg->forces & SPHGPU_FORCE_PRESSURE)) {
         return fail(SPHGPU_E_INVALID, "ForceEnum::PRESSURE is required (SolidStressForce is only added with it, StandardSets.cpp:24-33)");
     }
@@ -158,7 +166,10 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     ctx->balsara = (cfg->flags & SPHGPU_FLAG_BALSARA) != 0;
     ctx->xsph = (cfg->flags & SPHGPU_FLAG_XSPH) != 0;
     p.xsph_eps = 1.; // SPH_XSPH_EPSILON default (core/system/Settings.cpp); sphgpu_set_xsph_epsilon
-    ctx->recDoubles = recordDoubles(ctx->solid, ctx->balsara);
+    ctx->deltasph = (cfg->flags & SPHGPU_FLAG_DELTASPH) != 0;
+    p.deltasph_half_delta = 0.5 * 0.01; // SPH_DENSITY_DIFFUSION_DELTA, SPH_VELOCITY_DIFFUSION_ALPHA defaults
+    p.deltasph_half_alpha = 0.5 * 0.01; // (core/system/Settings.cpp:541-544); sphgpu_set_deltasph
+    ctx->recDoubles = recordDoubles(ctx->solid, ctx->balsara, ctx->deltasph);
     ctx->hasReduce = false;
     ctx->hasDamage = false;
     std::memset(ctx->matsHost, 0, sizeof(ctx->matsHost));
@@ -523,7 +534,7 @@ int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles) {
 int sphgpu_set_variant(sphgpu_ctx* ctx, int variant) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
     if (variant < 0 || variant > 4) return fail(SPHGPU_E_INVALID, "pair-kernel variant must be 0 .. 4");
-    if (variant == 4 && (ctx->corrected || ctx->balsara || ctx->xsph)) {
+    if (variant == 4 && (ctx->corrected || ctx->balsara || ctx->xsph || ctx->deltasph)) {
         return fail(SPHGPU_E_INVALID, "the symmetric formulation (variant 4) offers neither the correction tensor (like SymmetricSolver, "
                                       "SymmetricSolver.cpp:41-44) nor the Balsara switch / XSph");
     }
@@ -685,6 +696,17 @@ int sphgpu_set_frozen(sphgpu_ctx* ctx, const sphgpu_frozen* cfg) {
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->hasFrozen = cfg != nullptr && (cfg->flag_mask != 0ull || cfg->has_domain != 0);
     if (cfg) ctx->frozen = *cfg;
+    return SPHGPU_OK;
+}
+
+int sphgpu_set_deltasph(sphgpu_ctx* ctx, double delta, double alpha) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (!ctx->deltasph) return fail(SPHGPU_E_STATE, "the context was created without SPHGPU_FLAG_DELTASPH");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->prm.deltasph_half_delta = 0.5 * delta;
+    ctx->prm.deltasph_half_alpha = 0.5 * alpha;
+    forgetConstants(ctx); // uploaded again by the next call
     return SPHGPU_OK;
 }
 

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, PROLOGUE_MIN_CTAS) k_prologue_pack(Device
     const double rhoInv2 = 1. / (rho * rho);
     const double m = d.f[F_M][i];
     const bool balsara = (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0;
-    const int RD = recordDoubles(SOLID, balsara);
+    const int RD = recordDoublesOf(SOLID, c_prm.flags);
     double2* rec = reinterpret_cast<double2*>(d.rec + (size_t)t * RD);
     const uint32_t sw = recordSwizzle(RD, t); // XOR swizzle of the 128-byte solid record's pieces (sphgpu_internal.h)
     const double x = d.f[F_X][i], y = d.f[F_Y][i], z = d.f[F_Z][i], h = d.f[F_H][i];
@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(256, PROLOGUE_MIN_CTAS) k_prologue_pack(Device
         const double f = balsaraFactor(d.f[F_DIVV][i], d.f[F_ROTX][i], d.f[F_ROTY][i], d.f[F_ROTZ][i], cs, h);
         rec[SOLID ? 8 : 6] = make_double2(f, 0.);
     }
+    if (c_prm.flags & SPHGPU_FLAG_DELTASPH) { // the density gradient the PREVIOUS evaluation stored (DeltaSph.h:71-74)
+        rec[SOLID ? 8 : 6] = make_double2(d.f[F_DGX][i], d.f[F_DGY][i]);
+        rec[SOLID ? 9 : 7] = make_double2(d.f[F_DGZ][i], 0.);
+    }
     if (rebuild) {
         d.sCell[t] = d.cellOf[i];
     }
@@ -185,6 +189,10 @@ __device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, u
         if (recDoubles == REC_SOLID_BALSARA) {
             p.bal = r[8].x;
         }
+        if (recDoubles == REC_SOLID_DELTA) {
+            const double2 ga = r[8], gb = r[9];
+            p.gr[0] = ga.x; p.gr[1] = ga.y; p.gr[2] = gb.x;
+        }
     } else {
         const double2 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
         p.x = a.x; p.y = a.y; p.z = b.x; p.h = b.y;
@@ -192,13 +200,17 @@ __device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, u
         p.P = f.x; p.cs = f.y; p.vol = g.x;
         p.grp = 0;
         p.bal = r[6].x; // (the padding piece: the Balsara factor when the switch is on, unused otherwise)
+        if (recDoubles == REC_FLUID_DELTA) {
+            const double2 ga = r[6], gb = r[7];
+            p.gr[0] = ga.x; p.gr[1] = ga.y; p.gr[2] = gb.x;
+        }
     }
     p.m = p.vol * p.rho;
 }
 
 template <bool SOLID>
 __device__ __forceinline__ void loadSorted(const DevicePointers& d, uint32_t t, Particle& p) {
-    loadRecord<SOLID>(d.rec, t, recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0), p);
+    loadRecord<SOLID>(d.rec, t, recordDoublesOf(SOLID, c_prm.flags), p);
 }
 
 /// Position pieces {x, y}, {z, h} of the sorted record t.
@@ -233,6 +245,11 @@ __device__ __forceinline__ void storeDerivs(const DevicePointers& d, uint32_t i,
         d.f[F_ROTX][i] = o.rot[0];
         d.f[F_ROTY][i] = o.rot[1];
         d.f[F_ROTZ][i] = o.rot[2];
+    }
+    if (c_prm.flags & SPHGPU_FLAG_DELTASPH) { // read by the prologue of the NEXT evaluation only (the records hold the old one)
+        d.f[F_DGX][i] = o.dg[0];
+        d.f[F_DGY][i] = o.dg[1];
+        d.f[F_DGZ][i] = o.dg[2];
     }
     if (SOLID) {
         for (int k = 0; k < 5; ++k) {
@@ -282,7 +299,7 @@ __device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t
     const int cy = (int)((c / (uint32_t)g.dim[0]) % (uint32_t)g.dim[1]);
     const int cz = (int)(c / ((uint32_t)g.dim[0] * (uint32_t)g.dim[1]));
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-    const int RD = recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0);
+    const int RD = recordDoublesOf(SOLID, c_prm.flags);
     for (int z = max(cz - 2, 0); z <= min(cz + 2, g.dim[2] - 1); ++z) {
         for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
             const uint32_t row = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
@@ -346,7 +363,7 @@ __global__ void __launch_bounds__(128) k_large_neighbours(DevicePointers d, uint
     if (g.nLarge == 0u) {
         return;
     }
-    const int RD = recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0);
+    const int RD = recordDoublesOf(SOLID, c_prm.flags);
     // (a small grid with a stride loop: in the usual case -- no large particles -- the launch must cost next to nothing)
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < g.largeBegin; t += gridDim.x * blockDim.x) {
         Accum acc;
@@ -378,7 +395,7 @@ __global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_
     // The grid's CTAs are dealt to the large targets: target L gets S = gridDim / nLarge CTAs, each summing one slice of
     // the particles; the CTA that finishes last adds the slices' partial sums in slice order (the result does not depend
     // on which one that is) and runs the finalizers.
-    const int RD = recordDoubles(SOLID, (c_prm.flags & SPHGPU_FLAG_BALSARA) != 0);
+    const int RD = recordDoublesOf(SOLID, c_prm.flags);
     constexpr int NV = (int)(offsetof(Accum, cnt) / sizeof(double)); // doubles of Accum in front of the counter
     __shared__ double red[8][NV];
     __shared__ uint32_t redCnt[8];

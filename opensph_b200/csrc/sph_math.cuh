@@ -53,6 +53,7 @@ struct ParamsDev {
     uint32_t criteria, n_materials;
     double courant, derivative_factor, divergence_factor;
     double xsph_eps; // SPH_XSPH_EPSILON (SPHGPU_FLAG_XSPH)
+    double deltasph_half_delta, deltasph_half_alpha; // SPH_DENSITY_DIFFUSION_DELTA / 2, SPH_VELOCITY_DIFFUSION_ALPHA / 2
 };
 
 SPH_HD double sqr(double x) {
@@ -243,6 +244,7 @@ struct Particle {
     double m, rho, P, cs, vol;
     double Sr[5];
     double bal; // Balsara factor |div v| / (|div v| + |rot v| + 1e-4 cs / h) (Balsara.h:76-80); unused without the switch
+    double gr[3]; // DELTASPH_DENSITY_GRADIENT of the previous evaluation (DeltaSph.h:71-74); delta-SPH terms only
     int grp;
 };
 
@@ -254,6 +256,8 @@ struct Accum {
     double F[3]; // sum of the stress-weighted kernel gradients m_j gradW (pairSums): the target's own Sr is applied once
     double rot[3]; // sum m_j gradW x (v_j - v_i)  (VelocityRotation, DerivativeHelpers.h:374-395; Balsara switch only)
     double xs[3];  // sum m_j eps (v_j - v_i) W_ij / rhobar  (XSph::Derivative, XSph.h:55-63; XSph term only)
+    double dg[3];  // sum V_j (rho_j - rho_i) gradW  (DeltaSph::RenormalizedDensityGradient, DeltaSph.h:37-44; delta-SPH only)
+    double ddrho;  // sum V_j delta hbar cbar psi_ij . gradW  (DeltaSph::DensityDiffusion, DeltaSph.h:81-93; delta-SPH only)
     uint32_t cnt;
 };
 
@@ -268,6 +272,8 @@ SPH_HD void accumZero(Accum& a) {
     a.F[0] = a.F[1] = a.F[2] = 0.;
     a.rot[0] = a.rot[1] = a.rot[2] = 0.;
     a.xs[0] = a.xs[1] = a.xs[2] = 0.;
+    a.dg[0] = a.dg[1] = a.dg[2] = 0.;
+    a.ddrho = 0.;
     a.cnt = 0;
 }
 
@@ -419,6 +425,29 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
 
+    if (prm.flags & SPHGPU_FLAG_DELTASPH) { // DeltaSph.h:37-44, 81-93, 147-163 in the reference's own form (dr = r_j - r_i = -d)
+        bool ok = true;
+        if (SOLID && FILTER) {
+            ok = (pi.grp == pj.grp) && (pi.grp >= 0);
+        }
+        if (ok) {
+            const double drh = pj.rho - pi.rho;
+            acc.dg[0] += pj.vol * (drh * gx);
+            acc.dg[1] += pj.vol * (drh * gy);
+            acc.dg[2] += pj.vol * (drh * gz);
+            const double cbar = 0.5 * (pi.cs + pj.cs);
+            const double psx = 2. * drh * (-dx) / d2 - (pi.gr[0] + pj.gr[0]);
+            const double psy = 2. * drh * (-dy) / d2 - (pi.gr[1] + pj.gr[1]);
+            const double psz = 2. * drh * (-dz) / d2 - (pi.gr[2] + pj.gr[2]);
+            acc.ddrho += pj.vol * ((2. * prm.deltasph_half_delta) * hbar * cbar * (psx * gx + psy * gy + psz * gz));
+            const double pij = (dvx * (-dx) + dvy * (-dy) + dvz * (-dz)) / d2;
+            const double f = (2. * prm.deltasph_half_alpha) * hbar * cbar * pij;
+            acc.ax += pj.vol * (f * gx);
+            acc.ay += pj.vol * (f * gy);
+            acc.az += pj.vol * (f * gz);
+        }
+    }
+
     if (SOLID) {
         bool ok = true;
         if (FILTER) {
@@ -526,7 +555,7 @@ SPH_HD void pairGeometry(const ParamsDev& prm, double xi, double yi, double zi, 
 /// Stage B. G = the interpolated table value g + ratio dg of entry g.k. Of pi only v, P, cs, grp are read; of pj v, m,
 /// P, cs, vol, Sr, grp. The stress sum is split: sum_j (Sr_i + Sr_j) f_j = Sr_i F + sum_j Sr_j f_j with F = sum_j f_j
 /// (acc.F, applied by finalizeParticle), which saves the target's Sr registers and two additions per pair.
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false, bool XSPH = false>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false, bool XSPH = false, bool DELTA = false>
 SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& pj, const PairGeom& g, double G, Accum& acc, double W = 0.) {
     acc.cnt += g.valid ? 1u : 0u;
     const double mj = selectD(g.valid, pj.m, 0.);
@@ -563,6 +592,33 @@ SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& p
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
+    if (DELTA) {
+        // The three delta-SPH derivatives carry SUM_ONLY_UNDAMAGED (DeltaSph.h:22-24,63-64,135-136), which acts where the
+        // Storage has STRESS_REDUCING, i.e. for solids (DerivativeHelpers.h:84-91).
+        bool ok = g.valid;
+        if (SOLID && FILTER) {
+            ok = g.valid && (pi.grp == pj.grp) && (pi.grp >= 0);
+        }
+        const double vs = selectD(ok, pj.vol, 0.) * s; // V_j gradW = vs d, with d = r_i - r_j
+        const double drh = pj.rho - pi.rho;
+        // RenormalizedDensityGradient: V_j (rho_j - rho_i) gradW; the correction tensor C_i is applied once to the sum
+        const double cg = vs * drh;
+        acc.dg[0] = fma(cg, dx, acc.dg[0]);
+        acc.dg[1] = fma(cg, dy, acc.dg[1]);
+        acc.dg[2] = fma(cg, dz, acc.dg[2]);
+        // DensityDiffusion: psi = 2 (rho_j - rho_i) dr / dr^2 - (G_i + G_j) with dr = -d, so that
+        // psi . gradW = -s (2 (rho_j - rho_i) + (G_i + G_j) . d); the sum gets V_j delta hbar cbar psi . gradW
+        const double gd = (pi.gr[0] + pj.gr[0]) * dx + (pi.gr[1] + pj.gr[1]) * dy + (pi.gr[2] + pj.gr[2]) * dz;
+        const double hc = g.hbar * (pi.cs + pj.cs); // 2 hbar cbar
+        acc.ddrho -= (vs * (prm.deltasph_half_delta * hc)) * fma(2., drh, gd);
+        // VelocityDiffusion: pi_ij = (v_j - v_i) . dr / dr^2 = -t / d^2; dv_i += V_j alpha hbar cbar pi_ij gradW
+        // (the self pair is a masked candidate with d = 0: keep its reciprocal finite, vs = 0 removes it)
+        const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+        const double cv = (vs * (prm.deltasph_half_alpha * hc)) * (t * fastRcp(g.valid ? d2 : 1.));
+        acc.ax -= cv * dx;
+        acc.ay -= cv * dy;
+        acc.az -= cv * dz;
+    }
     if (SOLID) {
         bool ok = g.valid;
         if (FILTER) {
@@ -609,7 +665,9 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const LutPair* __restrict
     PairGeom g;
     pairGeometry(prm, pi.x, pi.y, pi.z, pi.h, pi.rho, pj.x, pj.y, pj.z, pj.h, pj.rho, g);
     const double G = fma(g.ratio, lut2[g.k].dg, lut2[g.k].g);
-    if (prm.flags & SPHGPU_FLAG_XSPH) {
+    if (prm.flags & SPHGPU_FLAG_DELTASPH) {
+        pairSums<SOLID, CORRECTED, FILTER, false, false, true>(prm, pi, pj, g, G, acc);
+    } else if (prm.flags & SPHGPU_FLAG_XSPH) {
         pairSums<SOLID, CORRECTED, FILTER, false, true>(prm, pi, pj, g, G, acc, fma(g.ratio, lutW2[g.k].dg, lutW2[g.k].g));
     } else if (prm.flags & SPHGPU_FLAG_BALSARA) {
         pairSums<SOLID, CORRECTED, FILTER, true>(prm, pi, pj, g, G, acc);
@@ -623,6 +681,7 @@ struct Derivs {
     double ax, ay, az, vh, du, drho, divv;
     double rot[3];
     double xs[3];
+    double dg[3]; // DELTASPH_DENSITY_GRADIENT of this evaluation (delta-SPH terms only)
     double dS[5];
     double gradv[6];
     double corr[6];
@@ -688,6 +747,14 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
         out.gradv[4] = 0.5 * (M[2] + M[6]) * rhoInv;
         out.gradv[5] = 0.5 * (M[5] + M[7]) * rhoInv;
         trGradv = out.gradv[0] + out.gradv[1] + out.gradv[2];
+        // RenormalizedDensityGradient is a CORRECTED derivative: C_i gradW summed = C_i applied to the sum (identity otherwise)
+        out.dg[0] = C[0] * acc.dg[0] + C[3] * acc.dg[1] + C[4] * acc.dg[2];
+        out.dg[1] = C[3] * acc.dg[0] + C[1] * acc.dg[1] + C[5] * acc.dg[2];
+        out.dg[2] = C[4] * acc.dg[0] + C[5] * acc.dg[1] + C[2] * acc.dg[2];
+    } else {
+        out.dg[0] = acc.dg[0];
+        out.dg[1] = acc.dg[1];
+        out.dg[2] = acc.dg[2];
     }
     // smoothing length (AdaptiveSmoothingLength::finalize / ConstSmoothingLength::finalize)
     double vh = 0.;
@@ -714,6 +781,7 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
     } else {
         out.drho = -rho * out.divv;
     }
+    out.drho += acc.ddrho; // DensityDiffusion shares the density-derivative buffer (zero without the delta-SPH terms)
     // solid stress: du += S:gradv / rho ; dS = 2 mu (gradv - tr/3 I)
     for (int k = 0; k < 5; ++k) {
         out.dS[k] = 0.;

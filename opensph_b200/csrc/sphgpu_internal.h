@@ -30,6 +30,7 @@ enum Field : int {
     F_AXP, F_AYP, F_AZP, F_DRHOP, F_DUP, F_DSP0, F_DSP1, F_DSP2, F_DSP3, F_DSP4, F_DDP,
     F_ROTX, F_ROTY, F_ROTZ,       // VELOCITY_ROTATION (Balsara switch): result of the last evaluation, input of the next
     F_XSX, F_XSY, F_XSZ,          // XSPH_VELOCITIES (XSph term): the correction currently contained in the velocities
+    F_DGX, F_DGY, F_DGZ,          // DELTASPH_DENSITY_GRADIENT (delta-SPH terms): result of the last evaluation, input of the next
     F_COUNT
 };
 
@@ -46,12 +47,21 @@ enum UField : int { U_NFLAWS, U_FLAG, U_MATID, U_NCNT, U_COUNT };
 // Fluid: the first 6 pieces + 16 bytes of padding = 7 pieces (odd stride, no swizzle needed).
 // With the Balsara switch every particle also contributes its factor f: a fluid record keeps it in the padding piece
 // {f, -}; a solid record grows to nine pieces = 144 bytes {... | f, -} with an odd stride and therefore no swizzle.
+// With the delta-SPH terms every particle contributes the density gradient G of the previous evaluation, two more pieces
+// {Gx,Gy | Gz,-} behind the regular ones plus one piece of padding to keep the stride odd: solid 11 pieces = 176 bytes,
+// fluid 9 pieces = 144 bytes.
 constexpr int REC_SOLID = 16;         // doubles per record, solid
 constexpr int REC_FLUID = 14;         // doubles per record, fluid
 constexpr int REC_SOLID_BALSARA = 18; // doubles per record, solid with the Balsara switch
+constexpr int REC_SOLID_DELTA = 22;   // doubles per record, solid with the delta-SPH terms
+constexpr int REC_FLUID_DELTA = 18;   // doubles per record, fluid with the delta-SPH terms
 
-__host__ __device__ inline int recordDoubles(bool solid, bool balsara) {
-    return solid ? (balsara ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID;
+__host__ __device__ inline int recordDoubles(bool solid, bool balsara, bool delta = false) {
+    return delta ? (solid ? REC_SOLID_DELTA : REC_FLUID_DELTA) : solid ? (balsara ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID;
+}
+/// Record size from the run flags (SPHGPU_FLAG_BALSARA / SPHGPU_FLAG_DELTASPH exclude each other).
+__host__ __device__ inline int recordDoublesOf(bool solid, uint32_t flags) {
+    return recordDoubles(solid, (flags & SPHGPU_FLAG_BALSARA) != 0, (flags & SPHGPU_FLAG_DELTASPH) != 0);
 }
 /// XOR swizzle of the record with sorted / staged index t (0 for the layouts with an odd stride).
 __host__ __device__ inline uint32_t recordSwizzle(int recDoubles, uint32_t t) {
@@ -182,7 +192,7 @@ struct sphgpu_ctx {
     sph::MaterialDev matsHost[sph::MAX_MATERIALS];
     sphgpu_material matsApi[sph::MAX_MATERIALS];
     uint32_t nMaterials = 0;
-    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false, xsph = false;
+    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false, xsph = false, deltasph = false;
     int recDoubles = sph::REC_FLUID; // doubles per sorted neighbour record of this context
     sph::DevicePointers d{};
     void* staging = nullptr;   // device staging for AoS <-> SoA repack (capacity * 64 B)

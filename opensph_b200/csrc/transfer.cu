@@ -50,6 +50,7 @@ static QuantityMap quantityMap(int q, int order) {
     case SPHGPU_Q_MATERIAL_ID: if (order == 0) { set(1, { U_MATID }); m.isU32 = true; } break;
     case SPHGPU_Q_VELOCITY_ROTATION: if (order == 0) set(4, { F_ROTX, F_ROTY, F_ROTZ, -1 }); break;
     case SPHGPU_Q_XSPH_VELOCITIES: if (order == 0) set(4, { F_XSX, F_XSY, F_XSZ, -1 }); break;
+    case SPHGPU_Q_DELTASPH_DENSITY_GRADIENT: if (order == 0) set(4, { F_DGX, F_DGY, F_DGZ, -1 }); break;
     default: break;
     }
     return m;

@@ -80,6 +80,9 @@ class Engine:
                                       C.c_uint32(self.n), C.c_uint32(self.capacity), C.c_int(device), C.byref(self._ctx)))
         if setup.cfg.flags & abi.FLAG_XSPH:
             _check(self.lib.sphgpu_set_xsph_epsilon(self._ctx, C.c_double(getattr(setup, "xsph_eps", 1.0))))
+        if setup.cfg.flags & abi.FLAG_DELTASPH:
+            _check(self.lib.sphgpu_set_deltasph(self._ctx, C.c_double(getattr(setup, "deltasph_delta", 0.01)),
+                                                C.c_double(getattr(setup, "deltasph_alpha", 0.01))))
 
     # -- lifetime ----------------------------------------------------------------------------------------------
     def close(self) -> None:

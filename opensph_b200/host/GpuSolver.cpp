@@ -8,6 +8,7 @@
 #include "sph/kernel/GravityKernel.h"
 #include "sph/equations/av/Balsara.h"
 #include "sph/equations/av/Standard.h"
+#include "sph/equations/DeltaSph.h"
 #include "sph/equations/XSph.h"
 #include "system/Factory.h"
 #include "system/Statistics.h"
@@ -68,6 +69,8 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     known += equations.contains<StandardAV>() ? 1 : 0;
     known += equations.contains<BalsaraSwitch<StandardAV>>() ? 1 : 0;
     known += equations.contains<XSph>() ? 1 : 0;
+    known += equations.contains<DeltaSph::DensityDiffusion>() ? 1 : 0;
+    known += equations.contains<DeltaSph::VelocityDiffusion>() ? 1 : 0;
     known += equations.contains<AdaptiveSmoothingLength>() ? 1 : 0;
     known += equations.contains<ConstSmoothingLength>() ? 1 : 0;
     if (known != equations.getTermCnt()) {
@@ -79,6 +82,14 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     }
     if (equations.contains<XSph>() && equations.contains<BalsaraSwitch<StandardAV>>()) {
         throw InvalidSetup("GpuSolver: the XSph term together with the Balsara switch is not implemented on the device");
+    }
+    // the delta-SPH terms come as a pair (StandardSets.cpp:64-67) and are evaluated as one device variant
+    if (equations.contains<DeltaSph::DensityDiffusion>() != equations.contains<DeltaSph::VelocityDiffusion>()) {
+        throw InvalidSetup("GpuSolver: DeltaSph::DensityDiffusion and DeltaSph::VelocityDiffusion are only implemented together");
+    }
+    if (equations.contains<DeltaSph::DensityDiffusion>() &&
+        (equations.contains<XSph>() || equations.contains<BalsaraSwitch<StandardAV>>())) {
+        throw InvalidSetup("GpuSolver: the delta-SPH terms together with XSph or the Balsara switch are not implemented on the device");
     }
     if (equations.contains<BalsaraSwitch<StandardAV>>() && settings.get<bool>(RunSettingsId::SPH_AV_BALSARA_STORE)) {
         throw InvalidSetup("GpuSolver: SPH_AV_BALSARA_STORE (the AV_BALSARA output quantity) is not implemented on the device");
@@ -228,6 +239,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     if (equations.contains<XSph>()) {
         cfg.flags |= SPHGPU_FLAG_XSPH;
     }
+    if (equations.contains<DeltaSph::DensityDiffusion>()) {
+        cfg.flags |= SPHGPU_FLAG_DELTASPH;
+    }
     if (equations.contains<AdaptiveSmoothingLength>()) {
         cfg.flags |= SPHGPU_FLAG_ADAPTIVE_H;
         if (hflags.has(SmoothingLengthEnum::SOUND_SPEED_ENFORCING)) {
@@ -311,6 +325,10 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     ctxParticleCnt = n;
     if (cfg.flags & SPHGPU_FLAG_XSPH) {
         check(sphgpu_set_xsph_epsilon(ctx, settings.get<Float>(RunSettingsId::SPH_XSPH_EPSILON)));
+    }
+    if (cfg.flags & SPHGPU_FLAG_DELTASPH) {
+        check(sphgpu_set_deltasph(ctx, settings.get<Float>(RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA),
+            settings.get<Float>(RunSettingsId::SPH_VELOCITY_DIFFUSION_ALPHA)));
     }
     if (deviceGravity) {
         this->configureGravity();
@@ -457,6 +475,11 @@ void GpuSolver::uploadQuantities(const Storage& storage, const bool derivatives)
             check(sphgpu_upload(c, b.q, 0, L, &storage.getValue<Size>(b.id)[0], 0, n));
         }
     }
+    if (storage.has(QuantityId::DELTASPH_DENSITY_GRADIENT)) {
+        // the gradient the previous evaluation stored: input of this one's density diffusion (DeltaSph.h:71-74)
+        check(sphgpu_upload(c, SPHGPU_Q_DELTASPH_DENSITY_GRADIENT, 0, L,
+            &storage.getValue<Vector>(QuantityId::DELTASPH_DENSITY_GRADIENT)[0], 0, n));
+    }
     if (storage.has(QuantityId::XSPH_VELOCITIES)) {
         // the correction the previous evaluation left in the velocities (XSph::initialize takes it out again, XSph.h:69-79)
         check(sphgpu_upload(c, SPHGPU_Q_XSPH_VELOCITIES, 0, L, &storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)[0], 0, n));
@@ -505,6 +528,10 @@ void GpuSolver::downloadQuantities(Storage& storage, const bool stateToo) {
     if (storage.has(QuantityId::DEVIATORIC_STRESS)) {
         check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 0, L, &storage.getValue<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
         check(sphgpu_download(c, SPHGPU_Q_DEVIATORIC_STRESS, 1, L, &storage.getDt<TracelessTensor>(QuantityId::DEVIATORIC_STRESS)[0], 0, n));
+    }
+    if (storage.has(QuantityId::DELTASPH_DENSITY_GRADIENT)) {
+        check(sphgpu_download(c, SPHGPU_Q_DELTASPH_DENSITY_GRADIENT, 0, L,
+            &storage.getValue<Vector>(QuantityId::DELTASPH_DENSITY_GRADIENT)[0], 0, n));
     }
     if (storage.has(QuantityId::XSPH_VELOCITIES)) {
         check(sphgpu_download(c, SPHGPU_Q_XSPH_VELOCITIES, 0, L, &storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)[0], 0, n));

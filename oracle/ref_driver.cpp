@@ -12,7 +12,7 @@
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
 //                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
 //                    [--frozen-flag F] [--frozen-domain RADIUS [--frozen-radius r]]
-//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--xsph [EPS]] [--criteria MASK]
+//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--xsph [EPS]] [--deltasph [--deltasph-delta D] [--deltasph-alpha A]] [--criteria MASK]
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
@@ -212,6 +212,15 @@ RunSettings makeSettings(const std::string& config, const Args& args) {
             settings.set(RunSettingsId::SPH_XSPH_EPSILON, Float(atof(args.str("xsph").c_str())));
         }
     }
+    if (args.has("deltasph")) { // DeltaSph::DensityDiffusion + VelocityDiffusion (core/sph/equations/DeltaSph.h; StandardSets.cpp:64-67)
+        settings.set(RunSettingsId::SPH_USE_DELTASPH, true);
+        if (args.has("deltasph-delta")) {
+            settings.set(RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA, Float(atof(args.str("deltasph-delta").c_str())));
+        }
+        if (args.has("deltasph-alpha")) {
+            settings.set(RunSettingsId::SPH_VELOCITY_DIFFUSION_ALPHA, Float(atof(args.str("deltasph-alpha").c_str())));
+        }
+    }
     if (args.has("sum-all")) { // SPH_SUM_ONLY_UNDAMAGED = false: no undamaged filter
         settings.set(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED, false);
     }
@@ -367,6 +376,9 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
     if (storage.has(QuantityId::XSPH_VELOCITIES)) {
         w.addF64("xsph", vec4(storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)), 4);
     }
+    if (storage.has(QuantityId::DELTASPH_DENSITY_GRADIENT)) {
+        w.addF64("drho_grad", vec4(storage.getValue<Vector>(QuantityId::DELTASPH_DENSITY_GRADIENT)), 4);
+    }
     if (storage.has(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)) {
         w.addF64("corr", st6(storage.getValue<SymmetricTensor>(QuantityId::STRAIN_RATE_CORRECTION_TENSOR)), 6);
     }
@@ -443,6 +455,9 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
         double(settings.get<bool>(RunSettingsId::SPH_AV_USE_BALSARA)),
         double(settings.get<bool>(RunSettingsId::SPH_USE_XSPH)),
         settings.get<Float>(RunSettingsId::SPH_XSPH_EPSILON),
+        double(settings.get<bool>(RunSettingsId::SPH_USE_DELTASPH)),
+        settings.get<Float>(RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA),
+        settings.get<Float>(RunSettingsId::SPH_VELOCITY_DIFFUSION_ALPHA),
     };
     w.addF64("run_params", run, 1);
 

@@ -458,6 +458,12 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
         }
     }
 
+    /* DeltaSph terms (core/sph/equations/DeltaSph.h; StandardSets.cpp:64-67). The new density gradient goes to the
+     * Accumulated buffer while DensityDiffusion reads the Storage values of the previous evaluation (DeltaSph.h:71-74),
+     * hence the separate array. */
+    const int deltasph = (cfg->flags & SPHGPU_FLAG_DELTASPH) != 0;
+    double* newGrad = deltasph ? (double*)calloc(4 * (size_t)n + 4, sizeof(double)) : NULL;
+
     /* Accumulated buffers start zeroed (Accumulated::initialize, core/sph/equations/Accumulated.cpp:40-60) */
     for (uint32_t i = 0; i < n; ++i) {
         s->acc[4 * (size_t)i] = s->acc[4 * (size_t)i + 1] = s->acc[4 * (size_t)i + 2] = s->acc[4 * (size_t)i + 3] = 0.;
@@ -649,6 +655,55 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
                 }
                 s->xsph[4 * (size_t)i + 3] = 0.;
             }
+            if (deltasph) {
+                const double* Gi = s->drho_grad + 4 * (size_t)i;
+                double G[3] = { 0., 0., 0. };
+                double diff = 0.;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const uint32_t j = neighs[k];
+                    if (filter && undamaged_skip(s, i, j)) { /* all three derivatives: SUM_ONLY_UNDAMAGED */
+                        continue;
+                    }
+                    const double* rj = s->pos + 4 * (size_t)j;
+                    const double* vj = s->vel + 4 * (size_t)j;
+                    const double* Gj = s->drho_grad + 4 * (size_t)j;
+                    const double* g0 = grads + 3 * k;
+                    const double vol = s->mass[j] / s->rho[j];
+                    const double drh = s->rho[j] - s->rho[i];
+                    /* RenormalizedDensityGradient::eval (DeltaSph.h:37-44) with C[i] * grad when CORRECTED
+                     * (DerivativeHelpers.h:100-107) */
+                    double gr[3] = { g0[0], g0[1], g0[2] };
+                    if (corrected) {
+                        const double* C = s->corr + 6 * (size_t)i;
+                        gr[0] = C[0] * g0[0] + C[3] * g0[1] + C[4] * g0[2];
+                        gr[1] = C[3] * g0[0] + C[1] * g0[1] + C[5] * g0[2];
+                        gr[2] = C[4] * g0[0] + C[5] * g0[1] + C[2] * g0[2];
+                    }
+                    for (int q = 0; q < 3; ++q) {
+                        G[q] += vol * (drh * gr[q]);
+                    }
+                    /* DensityDiffusion::Derivative::eval (DeltaSph.h:81-93) */
+                    const double dr[3] = { rj[0] - ri[0], rj[1] - ri[1], rj[2] - ri[2] };
+                    const double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
+                    const double hbar = 0.5 * (ri[3] + rj[3]);
+                    const double cbar = 0.5 * (s->cs[i] + s->cs[j]);
+                    double psig = 0.;
+                    for (int q = 0; q < 3; ++q) {
+                        const double psi = 2. * drh * dr[q] / dr2 - (Gi[q] + Gj[q]);
+                        psig += psi * g0[q];
+                    }
+                    diff += vol * (s->deltasph_delta * hbar * cbar * psig);
+                    /* VelocityDiffusion::Derivative::eval (DeltaSph.h:147-163) */
+                    const double pi = ((vj[0] - vi[0]) * dr[0] + (vj[1] - vi[1]) * dr[1] + (vj[2] - vi[2]) * dr[2]) / dr2;
+                    for (int q = 0; q < 3; ++q) {
+                        dv[q] += vol * (s->deltasph_alpha * hbar * cbar * pi * g0[q]);
+                    }
+                }
+                newGrad[4 * (size_t)i + 0] = G[0];
+                newGrad[4 * (size_t)i + 1] = G[1];
+                newGrad[4 * (size_t)i + 2] = G[2];
+                s->drho[i] += diff; /* the SHARED density-derivative buffer; ContinuityEquation::finalize adds to it */
+            }
             s->acc[4 * (size_t)i + 0] = dv[0];
             s->acc[4 * (size_t)i + 1] = dv[1];
             s->acc[4 * (size_t)i + 2] = dv[2];
@@ -659,6 +714,10 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
         free(grads);
     }
     grid_free(&g);
+    if (deltasph) { /* Accumulated::store: the new gradient replaces the Storage values */
+        memcpy(s->drho_grad, newGrad, sizeof(double) * 4 * (size_t)n);
+        free(newGrad);
+    }
 
     /* XSph::finalize (XSph.h:81-90): the new correction joins the velocities (the loop above read pure velocities only:
      * every thread wrote xsph of its own particle and nobody read it) */

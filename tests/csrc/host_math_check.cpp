@@ -50,6 +50,9 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         q.P = p * r2; q.vol = q.m / q.rho;
         for (int k = 0; k < 5; ++k) q.Sr[k] = S[k] * r2;
         q.grp = (hasReduce && reduce == 0.) ? -1 : (int)s->flag[i];
+        if (prm.flags & SPHGPU_FLAG_DELTASPH) { // k_prologue_pack: the gradient of the previous evaluation rides in the record
+            for (int k = 0; k < 3; ++k) q.gr[k] = s->drho_grad[4 * (size_t)i + k];
+        }
         if (MASKED) { // what the device loaders see: cs carries the group id, m is rebuilt from vol * rho
             unpackCsGroup(packCsGroup(q.cs, q.grp), q.cs, q.grp);
             q.m = q.vol * q.rho;
@@ -92,6 +95,10 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
                 s->xsph[4 * (size_t)i + k] = acc.xs[k];
                 xsNew[3 * (size_t)i + k] = acc.xs[k];
             }
+        }
+        if (prm.flags & SPHGPU_FLAG_DELTASPH) { // storeDerivs (the records P[] keep the old gradient for the other targets)
+            for (int k = 0; k < 3; ++k) s->drho_grad[4 * (size_t)i + k] = o.dg[k];
+            s->drho_grad[4 * (size_t)i + 3] = 0.;
         }
         if (SOLID) {
             for (int k = 0; k < 5; ++k) s->dS[5 * (size_t)i + k] = o.dS[k];
@@ -151,6 +158,8 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
     const double* lutWPtr = lutWGuard.data();
     const LutPair* lutW2 = lutWPairs.data();
     prm.xsph_eps = s->xsph_eps;
+    prm.deltasph_half_delta = 0.5 * s->deltasph_delta;
+    prm.deltasph_half_alpha = 0.5 * s->deltasph_alpha;
     const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
     const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;

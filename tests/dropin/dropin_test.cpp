@@ -435,6 +435,34 @@ int main(int argc, char** argv) {
             printf("    %-28s %.3e\n", "XSPH_VELOCITIES", xe);
             expect(xe <= 1.e-10, "XSPH_VELOCITIES within 1e-10");
         }
+        // ---- the delta-SPH terms (SPH_USE_DELTASPH): three consecutive evaluations, so that the density diffusion of the later
+        // ones reads the gradient stored by the one before (DeltaSph.h:37-44, 71-93)
+        {
+            RunSettings ds = settings;
+            ds.set(RunSettingsId::SPH_USE_DELTASPH, true)
+                .set(RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA, 0.1_f)
+                .set(RunSettingsId::SPH_VELOCITY_DIFFUSION_ALPHA, 0.05_f);
+            const EquationHolder deqs = getStandardEquations(ds);
+            AsymmetricSolver refD(*scheduler, ds, deqs);
+            GpuSolver gpuD(*scheduler, ds, deqs);
+            Storage da = base->clone(VisitorEnum::ALL_BUFFERS), db = base->clone(VisitorEnum::ALL_BUFFERS);
+            for (Size m = 0; m < da.getMaterialCnt(); ++m) {
+                refD.create(da, da.getMaterial(m));
+                gpuD.create(db, db.getMaterial(m));
+            }
+            for (int pass = 0; pass < 3; ++pass) {
+                da.zeroHighestDerivatives(*scheduler);
+                db.zeroHighestDerivatives(*scheduler);
+                refD.integrate(da, statsA);
+                gpuD.integrate(db, statsA);
+            }
+            expect(compareStorages(da, db, true, "integrate() three times with the delta-SPH terms") <= 1.e-10,
+                "all quantities within 1e-10 with the delta-SPH terms");
+            const double ge = cmpVector(da.getValue<Vector>(QuantityId::DELTASPH_DENSITY_GRADIENT),
+                db.getValue<Vector>(QuantityId::DELTASPH_DENSITY_GRADIENT), 3);
+            printf("    %-28s %.3e\n", "DELTASPH_DENSITY_GRADIENT", ge);
+            expect(ge <= 1.e-10, "DELTASPH_DENSITY_GRADIENT within 1e-10");
+        }
         // ---- the symmetric formulation: SymmetricSolver<3> of the reference next to GpuSolver::useSymmetricFormulation ----
         {
             RunSettings ss = settings;

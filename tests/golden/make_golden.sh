@@ -22,6 +22,11 @@ $R snapshot --config hello --n 500 --solver sym --jitter 7 --out hello_sym_out.s
 # the XSph term (SPH_USE_XSPH, epsilon 0.5): one integrate() and three PredictorCorrector steps
 $R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --neighbours --in xsph_in.snap --out xsph_out.snap --no-lut
 $R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --steps 3 --out xsph_pc3.snap --no-lut
+# the delta-SPH terms (SPH_USE_DELTASPH): one integrate() and three PredictorCorrector steps of the solid (delta 0.1, alpha 0.05),
+# three steps of the fluid with the library defaults (the in-state of the fluid run is fluid_in.snap)
+$R snapshot --config collision_preset --n 500 --jitter 3 --deltasph --deltasph-delta 0.1 --deltasph-alpha 0.05 --neighbours --in deltasph_in.snap --out deltasph_out.snap --no-lut
+$R snapshot --config collision_preset --n 500 --jitter 3 --deltasph --deltasph-delta 0.1 --deltasph-alpha 0.05 --steps 3 --out deltasph_pc3.snap --no-lut
+$R snapshot --config fluid --n 500 --jitter 5 --deltasph --steps 3 --out deltasph_fluid_pc3.snap --no-lut
 # FrozenParticles boundary condition: the impactor (flag 1) frozen and everything within 0.3 h of / outside a sphere of 90 km
 $R snapshot --config collision_preset --n 500 --jitter 3 --frozen-flag 1 --frozen-domain 9e4 --frozen-radius 0.3 --out frozen_out.snap --no-lut
 # self-gravity (IGravity::build + evalSelfGravity on a zeroed buffer): brute force and Barnes-Hut, softened and point-like

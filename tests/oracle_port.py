@@ -21,7 +21,8 @@ class OrcState(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pad0", C.c_uint32)] + [(k, _D) for k in (
         "pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
         "eps_min", "m_zero", "growth")] + [(k, _U) for k in ("n_flaws", "flag", "ncnt")] + [(k, _D) for k in (
-        "divv", "gradv", "corr", "acc_pred", "drho_pred", "du_pred", "dS_pred", "ddamage_pred", "xsph")] + [("xsph_eps", C.c_double)]
+        "divv", "gradv", "corr", "acc_pred", "drho_pred", "du_pred", "dS_pred", "ddamage_pred", "xsph")] + [("xsph_eps", C.c_double), ("drho_grad", _D),
+                                                                                     ("deltasph_delta", C.c_double), ("deltasph_alpha", C.c_double)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -39,7 +40,7 @@ def lib() -> C.CDLL:
 
 
 _F64 = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
-        "eps_min", "m_zero", "growth", "divv", "gradv", "corr", "xsph")
+        "eps_min", "m_zero", "growth", "divv", "gradv", "corr", "xsph", "drho_grad")
 _U32 = ("n_flaws", "flag", "ncnt")
 _PRED = {"acc_pred": "acc", "drho_pred": "drho", "du_pred": "du", "dS_pred": "dS", "ddamage_pred": "ddamage"}
 
@@ -75,8 +76,12 @@ class OraclePort:
         if self.setup.cfg.flags & abi.FLAG_XSPH:
             self.a.setdefault("xsph", np.zeros((n, 4)))
         self.state.xsph_eps = self.setup.xsph_eps
+        if self.setup.cfg.flags & abi.FLAG_DELTASPH:
+            self.a.setdefault("drho_grad", np.zeros((n, 4)))
+        self.state.deltasph_delta = self.setup.deltasph_delta
+        self.state.deltasph_alpha = self.setup.deltasph_alpha
         for name, _ in OrcState._fields_[2:]:
-            if name == "xsph_eps":
+            if name in ("xsph_eps", "deltasph_delta", "deltasph_alpha"):
                 continue
             arr = self.a.get(name)
             if arr is None:
