@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gravity", action="store_true", help="skip the self-gravity figure reported beside the headline")
     ap.add_argument("--fluid", action="store_true", help="fluid-only terms (BASELINE configs[4])")
+    ap.add_argument("--terms", choices=["preset", "balsara", "xsph", "deltasph"], default="preset",
+                    help="optional equation terms on top of the preset (other-workload lines, single GPU; the headline is 'preset')")
     ap.add_argument("--dt-mode", choices=["criteria", "fixed"], default="criteria",
                     help="criteria: the step the preset's criteria choose (particles move); fixed: dt = 1e-6 (static lattice)")
     ap.add_argument("--list-skin", type=float, default=None, help="skin of the candidate-list reuse (0: rebuild every step)")
@@ -244,6 +246,11 @@ def main():
     state = dom.generate_owned()
     n_owned = len(state["mass"])
     setup = workloads.make_setup(n_owned, solid=solid)
+    if args.terms != "preset":
+        if world > 1:
+            raise SystemExit("--terms needs a single GPU: these terms read results of the previous evaluation, which ghosts do not carry")
+        abi_mod = __import__("opensph_b200").abi
+        setup.cfg.flags |= {"balsara": abi_mod.FLAG_BALSARA, "xsph": abi_mod.FLAG_XSPH, "deltasph": abi_mod.FLAG_DELTASPH}[args.terms]
     eng = Engine(setup, n_owned, capacity=dom.capacity(n_owned), device=local)
     eng.set_variant(args.variant)
     if args.list_skin is not None:
@@ -428,7 +435,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": ("fluid_" if args.fluid else "collision_preset_") + str(n_lattice), "particles": int(n_total),
+        "config": {"workload": ("fluid_" if args.fluid else "collision_preset_") + str(n_lattice) + ("" if args.terms == "preset" else "+" + args.terms),
+                   "particles": int(n_total),
                    "particles_per_gpu": int(n_owned), "mean_neighbours": round(float(neigh_mean), 2), "integrator": "predictor_corrector",
                    "dt": ("chosen by the preset's criteria (Courant + divergence), initial %g, max %g; last step %.4g s" % (dt0, dt_max, dt_last))
                    if args.dt_mode == "criteria" else dt0,

@@ -330,6 +330,9 @@ __device__ __forceinline__ void directTarget(const DevicePointers& d, uint32_t t
     }
     Derivs out;
     finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][i], d.f[F_CS][i], SOLID ? d.f[F_REDUCE][i] : 1., S, out);
+    if (c_prm.flags & SPHGPU_FLAG_DELTASPH) {
+        finalizeDeltaSph<SOLID>(acc, out);
+    }
     storeDerivs<SOLID, CORRECTED>(d, i, out);
     if (c_prm.flags & SPHGPU_FLAG_XSPH) {
         storeXsph(d, i, acc.xs);
@@ -483,6 +486,9 @@ __global__ void __launch_bounds__(256) k_large_targets(DevicePointers d, uint32_
                 }
                 Derivs out;
                 finalizeParticle<SOLID, CORRECTED>(c_prm, mat, sum, pi.h, pi.rho, d.f[F_P][i], d.f[F_CS][i], SOLID ? d.f[F_REDUCE][i] : 1., Sv, out);
+                if (c_prm.flags & SPHGPU_FLAG_DELTASPH) {
+                    finalizeDeltaSph<SOLID>(sum, out);
+                }
                 storeDerivs<SOLID, CORRECTED>(d, i, out);
                 if (c_prm.flags & SPHGPU_FLAG_XSPH) {
                     storeXsph(d, i, sum.xs);

@@ -663,7 +663,7 @@ __device__ __forceinline__ void emitList(uint32_t listOwn, uint32_t cnt, uint32_
 }
 
 /// Finalizers + stores of one target (shared with the direct variant) and the neighbour statistics of the warp.
-template <bool SOLID, bool CORRECTED, bool XSPH = false>
+template <bool SOLID, bool CORRECTED, bool XSPH = false, bool DELTA = false>
 __device__ __forceinline__ void finishTarget(const DevicePointers& d, const UnitLane& u, const Particle& pi, const Accum& acc) {
     if (XSPH && u.target) { // (compile-time: the sums of the XSph term stay dead registers in the other instantiations)
         storeXsph(d, u.slot, acc.xs);
@@ -680,6 +680,9 @@ __device__ __forceinline__ void finishTarget(const DevicePointers& d, const Unit
         Derivs out;
         finalizeParticle<SOLID, CORRECTED>(c_prm, mat, acc, pi.h, pi.rho, d.f[F_P][slot], d.f[F_CS][slot], SOLID ? d.f[F_REDUCE][slot] : 1., S,
             out);
+        if (DELTA) { // (compile-time, like XSPH: the four sums of the delta-SPH terms are dead registers elsewhere)
+            finalizeDeltaSph<SOLID>(acc, out);
+        }
         storeDerivs<SOLID, CORRECTED>(d, slot, out);
     }
     neighbourStats(d, acc.cnt, u.target);
@@ -1074,7 +1077,7 @@ __global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA, DELTA>::CTA
                 prefetchBlock(nextOff);
             }
             if (!fallback) {
-                finishTarget<SOLID, CORRECTED, XSPH>(d, u, pi, acc); // overlaps with the copies
+                finishTarget<SOLID, CORRECTED, XSPH, DELTA>(d, u, pi, acc); // overlaps with the copies
             }
             if (nextUnit >= totalUnits) {
                 break;

@@ -747,15 +747,8 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
         out.gradv[4] = 0.5 * (M[2] + M[6]) * rhoInv;
         out.gradv[5] = 0.5 * (M[5] + M[7]) * rhoInv;
         trGradv = out.gradv[0] + out.gradv[1] + out.gradv[2];
-        // RenormalizedDensityGradient is a CORRECTED derivative: C_i gradW summed = C_i applied to the sum (identity otherwise)
-        out.dg[0] = C[0] * acc.dg[0] + C[3] * acc.dg[1] + C[4] * acc.dg[2];
-        out.dg[1] = C[3] * acc.dg[0] + C[1] * acc.dg[1] + C[5] * acc.dg[2];
-        out.dg[2] = C[4] * acc.dg[0] + C[5] * acc.dg[1] + C[2] * acc.dg[2];
-    } else {
-        out.dg[0] = acc.dg[0];
-        out.dg[1] = acc.dg[1];
-        out.dg[2] = acc.dg[2];
     }
+    out.dg[0] = out.dg[1] = out.dg[2] = 0.; // (finalizeDeltaSph)
     // smoothing length (AdaptiveSmoothingLength::finalize / ConstSmoothingLength::finalize)
     double vh = 0.;
     if (prm.flags & SPHGPU_FLAG_ADAPTIVE_H) {
@@ -781,7 +774,6 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
     } else {
         out.drho = -rho * out.divv;
     }
-    out.drho += acc.ddrho; // DensityDiffusion shares the density-derivative buffer (zero without the delta-SPH terms)
     // solid stress: du += S:gradv / rho ; dS = 2 mu (gradv - tr/3 I)
     for (int k = 0; k < 5; ++k) {
         out.dS[k] = 0.;
@@ -802,6 +794,25 @@ SPH_HD void finalizeParticle(const ParamsDev& prm, const MaterialDev& mat, const
         du -= p * rhoInv * out.divv;
     }
     out.du = du;
+}
+
+/// The delta-SPH part of the epilogue, after finalizeParticle (kept apart so that the gradient and diffusion sums are dead
+/// registers in the kernels without the terms). RenormalizedDensityGradient is a CORRECTED derivative: C_i gradW summed =
+/// C_i applied to the sum (out.corr: the identity without the tensor); DensityDiffusion shares the density-derivative
+/// buffer with the continuity equation (EquationTerm.cpp:289-316).
+template <bool SOLID>
+SPH_HD void finalizeDeltaSph(const Accum& acc, Derivs& out) {
+    if (SOLID) {
+        const double* C = out.corr;
+        out.dg[0] = C[0] * acc.dg[0] + C[3] * acc.dg[1] + C[4] * acc.dg[2];
+        out.dg[1] = C[3] * acc.dg[0] + C[1] * acc.dg[1] + C[5] * acc.dg[2];
+        out.dg[2] = C[4] * acc.dg[0] + C[5] * acc.dg[1] + C[2] * acc.dg[2];
+    } else {
+        out.dg[0] = acc.dg[0];
+        out.dg[1] = acc.dg[1];
+        out.dg[2] = acc.dg[2];
+    }
+    out.drho += acc.ddrho;
 }
 
 // ---- time stepping ----------------------------------------------------------------------------------------

@@ -117,7 +117,7 @@ public:
     /// Evaluates every pair once and adds it to both particles, like SymmetricSolver<3>::loop
     /// (core/sph/solvers/SymmetricSolver.cpp:104-163: rank by smoothing length, findLowerRank, evalSymmetric), instead of
     /// the asymmetric kernels. Same results to rounding, several times slower; not with the correction tensor (the
-    /// reference's SymmetricSolver rejects it as well), the Balsara switch or XSph (InvalidSetup at the first integrate).
+    /// reference's SymmetricSolver rejects it as well), the Balsara switch, XSph or the delta-SPH terms (InvalidSetup at the first integrate).
     /// Setups with SolverEnum::SYMMETRIC_SOLVER are served by the asymmetric kernels unless this is switched on.
     void useSymmetricFormulation(const bool symmetric) {
         pairVariant = symmetric ? 4 : 0;

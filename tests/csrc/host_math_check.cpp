@@ -87,6 +87,7 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         }
         Derivs o;
         finalizeParticle<SOLID, CORRECTED>(prm, mats[matid[i]], acc, P[i].h, P[i].rho, s->p[i], P[i].cs, hasReduce ? s->reduce[i] : 1., S, o);
+        if (prm.flags & SPHGPU_FLAG_DELTASPH) finalizeDeltaSph<SOLID>(acc, o);
         s->acc[4 * (size_t)i] = o.ax; s->acc[4 * (size_t)i + 1] = o.ay; s->acc[4 * (size_t)i + 2] = o.az; s->acc[4 * (size_t)i + 3] = 0.;
         s->vel[4 * (size_t)i + 3] = o.vh;
         s->du[i] = o.du; s->drho[i] = o.drho; s->divv[i] = o.divv; s->ncnt[i] = o.ncnt;
