@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gravity", action="store_true", help="skip the self-gravity figure reported beside the headline")
     ap.add_argument("--fluid", action="store_true", help="fluid-only terms (BASELINE configs[4])")
-    ap.add_argument("--terms", choices=["preset", "balsara", "xsph", "deltasph"], default="preset",
+    ap.add_argument("--terms", choices=["preset", "balsara", "xsph", "deltasph", "stressav"], default="preset",
                     help="optional equation terms on top of the preset (other-workload lines, single GPU; the headline is 'preset')")
     ap.add_argument("--dt-mode", choices=["criteria", "fixed"], default="criteria",
                     help="criteria: the step the preset's criteria choose (particles move); fixed: dt = 1e-6 (static lattice)")
@@ -250,13 +250,16 @@ def main():
         if world > 1:
             raise SystemExit("--terms needs a single GPU: these terms read results of the previous evaluation, which ghosts do not carry")
         abi_mod = __import__("opensph_b200").abi
-        setup.cfg.flags |= {"balsara": abi_mod.FLAG_BALSARA, "xsph": abi_mod.FLAG_XSPH, "deltasph": abi_mod.FLAG_DELTASPH}[args.terms]
+        setup.cfg.flags |= {"balsara": abi_mod.FLAG_BALSARA, "xsph": abi_mod.FLAG_XSPH, "deltasph": abi_mod.FLAG_DELTASPH,
+                            "stressav": abi_mod.FLAG_STRESS_AV}[args.terms]
     eng = Engine(setup, n_owned, capacity=dom.capacity(n_owned), device=local)
     eng.set_variant(args.variant)
     if args.list_skin is not None:
         eng.set_list_skin(args.list_skin)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     eng.upload_state(state, STATE_NAMES)
+    if args.terms == "stressav":  # StressAV::create: W(h, h) of the initial smoothing lengths (cubic spline: 1 / (4 pi h^3))
+        eng.upload_state({"wp": 0.25 / np.pi / state["pos"][:, 3] ** 3}, ["wp"])
     halo = decomp.HaloExchange(dom, eng, state) if world > 1 else None
     n_total = dom.total_particles(n_owned)
 

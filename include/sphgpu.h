@@ -56,11 +56,17 @@ enum {
     SPHGPU_FLAG_XSPH = 1u << 5,                 /* RunSettingsId::SPH_USE_XSPH: the XSph term, core/sph/equations/XSph.h:20-97;
                                                    its epsilon is set with sphgpu_set_xsph_epsilon. Not together with
                                                    SPHGPU_FLAG_BALSARA, not on decomposed runs                 */
-    SPHGPU_FLAG_DELTASPH = 1u << 6              /* RunSettingsId::SPH_USE_DELTASPH: DeltaSph::DensityDiffusion and
+    SPHGPU_FLAG_DELTASPH = 1u << 6,             /* RunSettingsId::SPH_USE_DELTASPH: DeltaSph::DensityDiffusion and
                                                    DeltaSph::VelocityDiffusion, core/sph/equations/DeltaSph.h:12-189
                                                    (StandardSets.cpp:64-67); coefficients: sphgpu_set_deltasph. Not together
                                                    with SPHGPU_FLAG_BALSARA or SPHGPU_FLAG_XSPH, not on decomposed runs; with
                                                    SPHGPU_FLAG_CORRECTION_TENSOR only for solids                  */
+    SPHGPU_FLAG_STRESS_AV = 1u << 7             /* RunSettingsId::SPH_AV_USE_STRESS: the artificial stress StressAV,
+                                                   core/sph/equations/av/Stress.h:10-36, Stress.cpp:8-123 (added by
+                                                   getStandardEquations, StandardSets.cpp:72-74); exponent and factor:
+                                                   sphgpu_set_stress_av. Needs ForceEnum::SOLID_STRESS and the kernel value
+                                                   table (lut_value). Not together with SPHGPU_FLAG_BALSARA, _XSPH or
+                                                   _DELTASPH, not on decomposed runs                              */
 };
 enum { SPHGPU_DISCR_STANDARD = 0, SPHGPU_DISCR_BENZ_ASPHAUG = 1 };        /* DiscretizationEnum            */
 enum { SPHGPU_CONTINUITY_STANDARD = 0, SPHGPU_CONTINUITY_SUM_ONLY_UNDAMAGED = 1 }; /* ContinuityEnum       */
@@ -112,7 +118,11 @@ enum {
     SPHGPU_Q_XSPH_VELOCITIES = 20,    /* Vector {x,y,z,0}: the velocity correction the XSph term left in the velocities */
     SPHGPU_Q_DELTASPH_DENSITY_GRADIENT = 21, /* Vector {x,y,z,0}: the renormalised density gradient, output of one
                                          evaluation and input of the next (DeltaSph.h:16-44,71-74)          */
-    SPHGPU_Q_COUNT = 22
+    SPHGPU_Q_AV_STRESS = 22,          /* SymmetricTensor: the artificial stress -(S - p I)+ every evaluation computes
+                                         (StressAV::initialize, Stress.cpp:91-109); output                   */
+    SPHGPU_Q_INTERPARTICLE_SPACING_KERNEL = 23, /* f64: W(h, h) of StressAV::create (Stress.cpp:113-121), set once from
+                                         the initial smoothing lengths; must be uploaded with SPHGPU_FLAG_STRESS_AV */
+    SPHGPU_Q_COUNT = 24
 };
 
 /* Host memory layouts understood by upload/download. */
@@ -424,6 +434,11 @@ SPHGPU_API int sphgpu_set_xsph_epsilon(sphgpu_ctx* ctx, double epsilon);
  * C_i grad W_ij in SPHGPU_Q_DELTASPH_DENSITY_GRADIENT; the density diffusion of the NEXT evaluation reads it, as the
  * reference does through its Storage (zero before the first evaluation). Defaults 0.01, 0.01 (Settings.cpp:541-544). */
 SPHGPU_API int sphgpu_set_deltasph(sphgpu_ctx* ctx, double delta, double alpha);
+/* RunSettingsId::SPH_AV_STRESS_EXPONENT and SPH_AV_STRESS_FACTOR of the artificial stress (SPHGPU_FLAG_STRESS_AV;
+ * Stress.cpp:24-27): Pi_ij = factor (W_ij / W(h_i, h_i)_0)^exponent (as_i / rho_i^2 + as_j / rho_j^2), dv_i += m_j Pi_ij grad W_ij,
+ * du_i += m_j Pi_ij (v_i - v_j) . grad W_ij / 2 over the undamaged neighbours of the same body. Defaults 4, 0.04
+ * (Settings.cpp:579-582). */
+SPHGPU_API int sphgpu_set_stress_av(sphgpu_ctx* ctx, double exponent, double factor);
 SPHGPU_API int sphgpu_list_stats(sphgpu_ctx* ctx, uint32_t* rebuilds, uint32_t* age, double* metric);
 /* Runs all subsequent work of the context on the caller's CUDA stream (a cudaStream_t passed as void*; NULL is the
  * legacy default stream 0, which is what torch.cuda.current_stream() is unless the caller changed it), so that the

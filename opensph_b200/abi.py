@@ -15,6 +15,7 @@ FORCE_PRESSURE, FORCE_SOLID_STRESS = 1, 2
 FLAG_CORRECTION_TENSOR, FLAG_SUM_ONLY_UNDAMAGED, FLAG_ADAPTIVE_H, FLAG_SOUND_SPEED_ENFORCING, FLAG_BALSARA = 1, 2, 4, 8, 16
 FLAG_XSPH = 32
 FLAG_DELTASPH = 64
+FLAG_STRESS_AV = 128
 EOS_NONE, EOS_IDEAL_GAS, EOS_TILLOTSON = 0, 1, 4
 YIELD_NONE, YIELD_ELASTIC, YIELD_VON_MISES, YIELD_DUST = 0, 1, 2, 4
 FRACTURE_NONE, FRACTURE_SCALAR_GRADY_KIPP = 0, 1
@@ -45,6 +46,8 @@ QUANTITIES: Dict[str, Tuple[int, int, type]] = {
     "VELOCITY_ROTATION": (19, 4, np.float64),
     "XSPH_VELOCITIES": (20, 4, np.float64),
     "DELTASPH_DENSITY_GRADIENT": (21, 4, np.float64),
+    "AV_STRESS": (22, 6, np.float64),
+    "INTERPARTICLE_SPACING_KERNEL": (23, 1, np.float64),
 }
 
 # snapshot array name -> (quantity, order)
@@ -57,7 +60,7 @@ SNAPSHOT_FIELDS: Dict[str, Tuple[str, int]] = {
     "divv": ("VELOCITY_DIVERGENCE", 0), "gradv": ("VELOCITY_GRADIENT", 0), "corr": ("CORRECTION_TENSOR", 0),
     "eps_min": ("EPS_MIN", 0), "m_zero": ("M_ZERO", 0), "growth": ("EXPLICIT_GROWTH", 0),
     "n_flaws": ("N_FLAWS", 0), "flag": ("FLAG", 0), "ncnt": ("NEIGHBOR_CNT", 0), "xsph": ("XSPH_VELOCITIES", 0),
-    "drho_grad": ("DELTASPH_DENSITY_GRADIENT", 0),
+    "drho_grad": ("DELTASPH_DENSITY_GRADIENT", 0), "av_stress": ("AV_STRESS", 0), "wp": ("INTERPARTICLE_SPACING_KERNEL", 0),
 }
 
 
@@ -167,6 +170,8 @@ class RunSetup:
         self.xsph_eps = 1.0  # SPH_XSPH_EPSILON (used with FLAG_XSPH; Engine passes it to sphgpu_set_xsph_epsilon)
         self.deltasph_delta = 0.01  # SPH_DENSITY_DIFFUSION_DELTA, SPH_VELOCITY_DIFFUSION_ALPHA (used with FLAG_DELTASPH;
         self.deltasph_alpha = 0.01  # Engine passes them to sphgpu_set_deltasph)
+        self.stress_av_exponent = 4.0  # SPH_AV_STRESS_EXPONENT, SPH_AV_STRESS_FACTOR (used with FLAG_STRESS_AV; Engine passes
+        self.stress_av_factor = 0.04   # them to sphgpu_set_stress_av)
 
     @property
     def solid(self) -> bool:
@@ -199,7 +204,7 @@ def setup_from_snapshot(snap: Dict[str, np.ndarray], lut: Dict[str, np.ndarray] 
     cfg.flags = ((FLAG_CORRECTION_TENSOR if (rp[5] and rp[4]) else 0) | (FLAG_SUM_ONLY_UNDAMAGED if rp[6] else 0)
                  | (FLAG_ADAPTIVE_H if rp[7] else 0) | (FLAG_SOUND_SPEED_ENFORCING if rp[8] else 0)
                  | (FLAG_BALSARA if (len(rp) > 25 and rp[25]) else 0) | (FLAG_XSPH if (len(rp) > 26 and rp[26]) else 0)
-                 | (FLAG_DELTASPH if (len(rp) > 28 and rp[28]) else 0))
+                 | (FLAG_DELTASPH if (len(rp) > 28 and rp[28]) else 0) | (FLAG_STRESS_AV if (len(rp) > 31 and rp[31]) else 0))
     cfg.continuity_mode = int(rp[9])
     cfg.discretization = int(rp[10])
     cfg.h_min, cfg.h_max = rp[11], rp[12]
@@ -226,6 +231,8 @@ def setup_from_snapshot(snap: Dict[str, np.ndarray], lut: Dict[str, np.ndarray] 
         setup.xsph_eps = float(rp[27])
     if len(rp) > 30:
         setup.deltasph_delta, setup.deltasph_alpha = float(rp[29]), float(rp[30])
+    if len(rp) > 33:
+        setup.stress_av_exponent, setup.stress_av_factor = float(rp[32]), float(rp[33])
     return setup
 
 

@@ -54,6 +54,17 @@ static int validate(const sphgpu_config* cfg, const sphgpu_material* mats, uint3
             return fail(SPHGPU_E_INVALID, "the XSph term together with the Balsara switch is not implemented on the GPU path");
         }
     }
+    if (cfg->flags & SPHGPU_FLAG_STRESS_AV) {
+        if (!(cfg->forces & SPHGPU_FORCE_SOLID_STRESS)) {
+            return fail(SPHGPU_E_INVALID, "the artificial stress needs ForceEnum::SOLID_STRESS (it is built from the deviatoric stress, Stress.cpp:91-109)");
+        }
+        if (!cfg->lut_value) {
+            return fail(SPHGPU_E_INVALID, "the artificial stress needs the kernel value table (lut_value)");
+        }
+        if (cfg->flags & (SPHGPU_FLAG_BALSARA | SPHGPU_FLAG_XSPH | SPHGPU_FLAG_DELTASPH)) {
+            return fail(SPHGPU_E_INVALID, "the artificial stress together with the Balsara switch, the XSph term or the delta-SPH terms is not implemented on the GPU path");
+        }
+    }
     if (cfg->flags & SPHGPU_FLAG_DELTASPH) {
         if (cfg->flags & (SPHGPU_FLAG_BALSARA | SPHGPU_FLAG_XSPH)) {
             return fail(SPHGPU_E_INVALID, "the delta-SPH terms together with the Balsara switch or the XSph term are not implemented on the GPU path");
@@ -169,7 +180,11 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
     ctx->deltasph = (cfg->flags & SPHGPU_FLAG_DELTASPH) != 0;
     p.deltasph_half_delta = 0.5 * 0.01; // SPH_DENSITY_DIFFUSION_DELTA, SPH_VELOCITY_DIFFUSION_ALPHA defaults
     p.deltasph_half_alpha = 0.5 * 0.01; // (core/system/Settings.cpp:541-544); sphgpu_set_deltasph
-    ctx->recDoubles = recordDoubles(ctx->solid, ctx->balsara, ctx->deltasph);
+    ctx->stressAv = (cfg->flags & SPHGPU_FLAG_STRESS_AV) != 0;
+    p.stress_av_exponent = 4.; // SPH_AV_STRESS_EXPONENT, SPH_AV_STRESS_FACTOR defaults (core/system/Settings.cpp:579-582);
+    p.stress_av_factor = 0.04; // sphgpu_set_stress_av
+    p.stress_av_int_exponent = stressAvIntExponent(p.stress_av_exponent);
+    ctx->recDoubles = recordDoubles(ctx->solid, ctx->balsara, ctx->deltasph, ctx->stressAv);
     ctx->hasReduce = false;
     ctx->hasDamage = false;
     std::memset(ctx->matsHost, 0, sizeof(ctx->matsHost));
@@ -280,7 +295,7 @@ int sphgpu_create(const sphgpu_config* cfg, const sphgpu_material* materials, ui
         ctx->d.lut2 = lut2;
         SPH_TRY(wrap(cudaMemcpy(lut2, pairs.data(), sizeof(LutPair) * pairs.size(), cudaMemcpyHostToDevice), "LUT upload"));
     }
-    if (ctx->xsph) { // kernel values for the XSph term: LutKernel::valueImpl interpolates the same way (Kernel.h:111-127)
+    if (ctx->xsph || ctx->stressAv) { // kernel values for the XSph term and the artificial stress: LutKernel::valueImpl interpolates the same way (Kernel.h:111-127)
         double* lutW = nullptr;
         SPH_TRY(devAlloc(&lutW, (size_t)cfg->lut_entries + 2));
         ctx->d.lutW = lutW;
@@ -534,7 +549,7 @@ int sphgpu_set_particle_count(sphgpu_ctx* ctx, uint32_t n_particles) {
 int sphgpu_set_variant(sphgpu_ctx* ctx, int variant) {
     if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
     if (variant < 0 || variant > 4) return fail(SPHGPU_E_INVALID, "pair-kernel variant must be 0 .. 4");
-    if (variant == 4 && (ctx->corrected || ctx->balsara || ctx->xsph || ctx->deltasph)) {
+    if (variant == 4 && (ctx->corrected || ctx->balsara || ctx->xsph || ctx->deltasph || ctx->stressAv)) {
         return fail(SPHGPU_E_INVALID, "the symmetric formulation (variant 4) offers neither the correction tensor (like SymmetricSolver, "
                                       "SymmetricSolver.cpp:41-44) nor the Balsara switch / XSph");
     }
@@ -696,6 +711,18 @@ int sphgpu_set_frozen(sphgpu_ctx* ctx, const sphgpu_frozen* cfg) {
     SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->hasFrozen = cfg != nullptr && (cfg->flag_mask != 0ull || cfg->has_domain != 0);
     if (cfg) ctx->frozen = *cfg;
+    return SPHGPU_OK;
+}
+
+int sphgpu_set_stress_av(sphgpu_ctx* ctx, double exponent, double factor) {
+    if (!ctx) return fail(SPHGPU_E_INVALID, "null context");
+    if (!ctx->stressAv) return fail(SPHGPU_E_STATE, "the context was created without SPHGPU_FLAG_STRESS_AV");
+    SPH_CUDA_CHECK(cudaSetDevice(ctx->device));
+    SPH_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->prm.stress_av_exponent = exponent;
+    ctx->prm.stress_av_factor = factor;
+    ctx->prm.stress_av_int_exponent = stressAvIntExponent(exponent);
+    forgetConstants(ctx); // uploaded again by the next call
     return SPHGPU_OK;
 }
 

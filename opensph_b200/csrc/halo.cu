@@ -465,10 +465,10 @@ int sphgpu_halo_configure(sphgpu_ctx* ctx, int left_rank, int right_rank, uint32
         return SPHGPU_E_STATE;
     }
     HaloState* h = static_cast<HaloState*>(ctx->halo);
-    if (ctx->balsara || ctx->xsph || ctx->deltasph) {
+    if (ctx->balsara || ctx->xsph || ctx->deltasph || ctx->stressAv) {
         // these terms read results of the PREVIOUS evaluation of their neighbours (div v / rot v, the velocity correction, the
-        // density gradient), which the ghost bands do not carry
-        setError("the Balsara switch, the XSph term and the delta-SPH terms are not available on decomposed runs");
+        // density gradient) or per-particle constants of their own (the spacing kernel), which the ghost bands do not carry
+        setError("the Balsara switch, the XSph term, the delta-SPH terms and the artificial stress are not available on decomposed runs");
         return SPHGPU_E_INVALID;
     }
     if ((uint64_t)ctx->n + recv_left + recv_right > ctx->capacity || send_left + send_right > ctx->n) {

@@ -65,6 +65,14 @@ __device__ __forceinline__ float4 gridRelative(const GridDev& g, double x, doubl
 // records scattered to the sorted array. (Round 1 and most of round 2 ran one thread per sorted position and GATHERED the
 // planes through `order`: a cell's particles sit on several lattice rows, so only about 60 % of every 32-byte sector was
 // used -- 0.99 ms against 0.6 ms of compulsory traffic at 10.6 M particles.)
+/// StressAV::initialize (Stress.cpp:91-109) for the total stress sigma {xx,yy,zz,xy,xz,yz}. Not inlined, and called with
+/// scalars: neither the eigen-solver's registers nor an address-taken array may weigh on the prologue of the runs without the
+/// term (passing the kernel's S[] or the DevicePointers by reference moved them to local memory: 0.94 -> 2.5 ms, measured).
+__device__ __noinline__ void avStressCold(double sxx, double syy, double szz, double sxy, double sxz, double syz, double* as) {
+    const double sigma[6] = { sxx, syy, szz, sxy, sxz, syz };
+    avStressOf(sigma, as);
+}
+
 template <bool SOLID>
 __global__ void __launch_bounds__(256, PROLOGUE_MIN_CTAS) k_prologue_pack(DevicePointers d, uint32_t nActive, uint32_t nOwned, bool hasReduce,
     bool hasDamage) {
@@ -148,6 +156,16 @@ __global__ void __launch_bounds__(256, PROLOGUE_MIN_CTAS) k_prologue_pack(Device
         const double f = balsaraFactor(d.f[F_DIVV][i], d.f[F_ROTX][i], d.f[F_ROTY][i], d.f[F_ROTZ][i], cs, h);
         rec[SOLID ? 8 : 6] = make_double2(f, 0.);
     }
+    if (SOLID && (c_prm.flags & SPHGPU_FLAG_STRESS_AV)) { // the artificial stress goes to its planes and, over rho^2, into the record
+        double as[6];
+        avStressCold(S[0] - p, S[1] - p, (-S[0] - S[1]) - p, S[2], S[3], S[4], as);
+        for (int k = 0; k < 6; ++k) {
+            d.f[F_AS0 + k][i] = as[k];
+        }
+        rec[8] = make_double2(as[0] * rhoInv2, as[1] * rhoInv2);
+        rec[9] = make_double2(as[2] * rhoInv2, as[3] * rhoInv2);
+        rec[10] = make_double2(as[4] * rhoInv2, as[5] * rhoInv2);
+    }
     if (c_prm.flags & SPHGPU_FLAG_DELTASPH) { // the density gradient the PREVIOUS evaluation stored (DeltaSph.h:71-74)
         rec[SOLID ? 8 : 6] = make_double2(d.f[F_DGX][i], d.f[F_DGY][i]);
         rec[SOLID ? 9 : 7] = make_double2(d.f[F_DGZ][i], 0.);
@@ -173,7 +191,7 @@ __global__ void __launch_bounds__(256) k_pack_positions(DevicePointers d, uint32
 
 /// Unpacks the neighbour-input record with sorted index t from global memory (layouts: sphgpu_internal.h).
 template <bool SOLID>
-__device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, uint32_t t, int recDoubles, Particle& p) {
+__device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, uint32_t t, int recDoubles, uint32_t flags, Particle& p) {
     const double2* r = reinterpret_cast<const double2*>(recBase + (size_t)t * recDoubles);
     const uint32_t sw = recordSwizzle(recDoubles, t);
     p.bal = 0.;
@@ -189,9 +207,13 @@ __device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, u
         if (recDoubles == REC_SOLID_BALSARA) {
             p.bal = r[8].x;
         }
-        if (recDoubles == REC_SOLID_DELTA) {
+        if (flags & SPHGPU_FLAG_DELTASPH) { // (the 176-byte layouts are told apart by the run flags)
             const double2 ga = r[8], gb = r[9];
             p.gr[0] = ga.x; p.gr[1] = ga.y; p.gr[2] = gb.x;
+        }
+        if (flags & SPHGPU_FLAG_STRESS_AV) {
+            const double2 aa = r[8], ab = r[9], ac = r[10];
+            p.as[0] = aa.x; p.as[1] = aa.y; p.as[2] = ab.x; p.as[3] = ab.y; p.as[4] = ac.x; p.as[5] = ac.y;
         }
     } else {
         const double2 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
@@ -200,7 +222,7 @@ __device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, u
         p.P = f.x; p.cs = f.y; p.vol = g.x;
         p.grp = 0;
         p.bal = r[6].x; // (the padding piece: the Balsara factor when the switch is on, unused otherwise)
-        if (recDoubles == REC_FLUID_DELTA) {
+        if (flags & SPHGPU_FLAG_DELTASPH) {
             const double2 ga = r[6], gb = r[7];
             p.gr[0] = ga.x; p.gr[1] = ga.y; p.gr[2] = gb.x;
         }
@@ -210,7 +232,10 @@ __device__ __forceinline__ void loadRecord(const double* __restrict__ recBase, u
 
 template <bool SOLID>
 __device__ __forceinline__ void loadSorted(const DevicePointers& d, uint32_t t, Particle& p) {
-    loadRecord<SOLID>(d.rec, t, recordDoublesOf(SOLID, c_prm.flags), p);
+    loadRecord<SOLID>(d.rec, t, recordDoublesOf(SOLID, c_prm.flags), c_prm.flags, p);
+    if (c_prm.flags & SPHGPU_FLAG_STRESS_AV) { // (read for the target only; the direct kernels are not the hot path)
+        p.wpInv = 1. / d.f[F_WP][d.order[t]];
+    }
 }
 
 /// Position pieces {x, y}, {z, h} of the sorted record t.

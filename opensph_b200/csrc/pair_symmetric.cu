@@ -296,7 +296,7 @@ static int launchSymmetricVariant(sphgpu_ctx* ctx, SymState* s) {
 
 /// Variant 4 of the pair stage (sphgpu_set_variant): called after the large-particle kernels.
 int launchPairSymmetric(sphgpu_ctx* ctx) {
-    if (ctx->corrected || ctx->balsara || ctx->xsph || ctx->deltasph) {
+    if (ctx->corrected || ctx->balsara || ctx->xsph || ctx->deltasph || ctx->stressAv) {
         setError("the symmetric formulation (variant 4) offers neither the correction tensor (like SymmetricSolver, SymmetricSolver.cpp:41-44) nor "
                  "the Balsara switch / XSph");
         return SPHGPU_E_INVALID;

@@ -854,9 +854,10 @@ __global__ void __launch_bounds__(TILE_T, 1024 / TILE_T) k_pair_lists(DevicePoin
 // (threads 0..15 also the descriptor of the next block), waits on the mbarrier and walks its list; one CTA barrier frees
 // the stage. At the end of a chain the first block of the CTA's next unit is issued BEFORE the finalizers / stores of the
 // finished unit and the loads of the next unit's targets, so those overlap with the copies.
-template <bool SOLID, bool BALSARA, bool DELTA = false>
+template <bool SOLID, bool BALSARA, bool DELTA = false, bool STRESSAV = false>
 struct SumLayout {
-    static constexpr int S = DELTA ? (SOLID ? REC_SOLID_DELTA : REC_FLUID_DELTA)
+    static constexpr int S = STRESSAV ? REC_SOLID_STRESSAV
+                             : DELTA  ? (SOLID ? REC_SOLID_DELTA : REC_FLUID_DELTA)
                                    : SOLID ? (BALSARA ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID; // doubles per staged record
     static constexpr uint32_t REC_BYTES = (uint32_t)S * 8u;
     static constexpr bool SWIZZLED = S == REC_SOLID;
@@ -865,7 +866,7 @@ struct SumLayout {
                                                                 // fluid with the delta-SPH gradient (two CTAs per SM)
     // what fits: 228 KB of shared memory per SM (per CTA 1 KB reserved + 16 B per thread + 280 B of static arrays), 64 K registers
     static constexpr int BY_SMEM = (int)((228 * 1024) / (bytes + 1024 + 16 * TILE_T + 280));
-    static constexpr int BY_REGS = 65536 / (TILE_T * (DELTA ? 255 : BALSARA && SOLID ? 208 : 168));
+    static constexpr int BY_REGS = 65536 / (TILE_T * (DELTA || STRESSAV ? 255 : BALSARA && SOLID ? 208 : 168));
     static constexpr int CTAS_PER_SM = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
 };
 
@@ -902,9 +903,9 @@ __device__ __forceinline__ void stageA(uint32_t stage, uint32_t k, uint32_t self
 }
 
 /// Stage B: the rest of the record and the sums.
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH, bool DELTA>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH, bool DELTA, bool STRESSAV>
 __device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Accum& acc, const LutPair* lutW2) {
-    using P = SumLayout<SOLID, BALSARA, DELTA>;
+    using P = SumLayout<SOLID, BALSARA, DELTA, STRESSAV>;
     Particle pj;
     pj.vz = s.vz;
     pj.rho = s.rho;
@@ -946,17 +947,21 @@ __device__ __forceinline__ void stageB(const PairSlot& s, const Particle& pi, Ac
         const double2 ga = loadSharedD2(s.rec + (SOLID ? 128u : 96u)), gb = loadSharedD2(s.rec + (SOLID ? 144u : 112u));
         pj.gr[0] = ga.x; pj.gr[1] = ga.y; pj.gr[2] = gb.x;
     }
+    if (STRESSAV) { // as / rho^2: the three pieces behind the regular ones
+        const double2 aa = loadSharedD2(s.rec + 128u), ab = loadSharedD2(s.rec + 144u), ac = loadSharedD2(s.rec + 160u);
+        pj.as[0] = aa.x; pj.as[1] = aa.y; pj.as[2] = ab.x; pj.as[3] = ab.y; pj.as[4] = ac.x; pj.as[5] = ac.y;
+    }
     double W = 0.;
-    if (XSPH) { // kernel value of the XSph term: same index and weight as the gradient table
+    if (XSPH || STRESSAV) { // kernel value (XSph term, artificial stress): same index and weight as the gradient table
         const double2 w = __ldg(reinterpret_cast<const double2*>(lutW2) + s.g.k);
         W = fma(s.g.ratio, w.y, w.x);
     }
-    pairSums<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc, W);
+    pairSums<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA, STRESSAV>(c_prm, pi, pj, s.g, fma(s.g.ratio, s.lut.y, s.lut.x), acc, W);
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH, bool DELTA>
-__global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA, DELTA>::CTAS_PER_SM)) k_pair_sum(DevicePointers d, uint32_t maxCells) {
-    using P = SumLayout<SOLID, BALSARA, DELTA>;
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH, bool DELTA, bool STRESSAV>
+__global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA, DELTA, STRESSAV>::CTAS_PER_SM)) k_pair_sum(DevicePointers d, uint32_t maxCells) {
+    using P = SumLayout<SOLID, BALSARA, DELTA, STRESSAV>;
     extern __shared__ __align__(128) unsigned char smemStage[];
     __shared__ __align__(8) uint64_t stageBar;
     __shared__ uint32_t sFirst[2][16]; // first-block descriptors of the CTA's current and next unit
@@ -1021,7 +1026,10 @@ __global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA, DELTA>::CTA
         u.target = u.live && (word & 0x40000000u) == 0u; // ghosts are neighbours only
         u.slot = u.target ? d.order[u.t] : 0xffffffffu;
         if (u.live) {
-            loadRecord<SOLID>(d.rec, u.t, P::S, pi);
+            loadRecord<SOLID>(d.rec, u.t, P::S, (DELTA ? SPHGPU_FLAG_DELTASPH : 0u) | (STRESSAV ? SPHGPU_FLAG_STRESS_AV : 0u), pi);
+            if (STRESSAV) {
+                pi.wpInv = u.target ? 1. / d.f[F_WP][u.slot] : 0.;
+            }
         } else {
             pi.x = pi.y = pi.z = 0.;
             pi.h = 1.;
@@ -1126,22 +1134,22 @@ __global__ void __launch_bounds__(TILE_T, (SumLayout<SOLID, BALSARA, DELTA>::CTA
                 uint2 nxt = make_uint2(0u, 0u);
                 loadGlobalU2If(q + 4u < cnt, quads, nxt);
                 stageA<P>(stage, cur.x >> 16, selfIdx, pi, d.lut2, s1);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA>(s0, pi, acc, d.lutW2);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA, STRESSAV>(s0, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
                 stageA<P>(stage, cur.y & 0xffffu, selfIdx, pi, d.lut2, s0);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA>(s1, pi, acc, d.lutW2);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA, STRESSAV>(s1, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
                 stageA<P>(stage, cur.y >> 16, selfIdx, pi, d.lut2, s1);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA>(s0, pi, acc, d.lutW2);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA, STRESSAV>(s0, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
                 stageA<P>(stage, nxt.x & 0xffffu, selfIdx, pi, d.lut2, s0);
-                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA>(s1, pi, acc, d.lutW2);
+                stageB<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA, STRESSAV>(s1, pi, acc, d.lutW2);
                 if (++q >= cnt) {
                     break;
                 }
@@ -1224,18 +1232,18 @@ static int launchLists(sphgpu_ctx* ctx) {
     return SPHGPU_OK;
 }
 
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH, bool DELTA = false>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA, bool XSPH, bool DELTA = false, bool STRESSAV = false>
 static int launchSumVariantB(sphgpu_ctx* ctx) {
-    auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA>;
+    auto kernel = k_pair_sum<SOLID, CORRECTED, FILTER, BALSARA, XSPH, DELTA, STRESSAV>;
     static bool configured[64] = {}; // per instantiation and device; the attribute is per device function
-    const size_t smem = SumLayout<SOLID, BALSARA, DELTA>::bytes;
+    const size_t smem = SumLayout<SOLID, BALSARA, DELTA, STRESSAV>::bytes;
     if (!configured[ctx->device & 63]) {
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SPH_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[ctx->device & 63] = true;
     }
     // many more CTAs than fit at once: the block scheduler balances the load (measured: 32 waves beat 8 by 1 %, 1 by 4 %)
-    kernel<<<unitGrid(ctx, SumLayout<SOLID, BALSARA, DELTA>::CTAS_PER_SM, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
+    kernel<<<unitGrid(ctx, SumLayout<SOLID, BALSARA, DELTA, STRESSAV>::CTAS_PER_SM, 32), TILE_T, smem, ctx->stream>>>(ctx->d, ctx->maxCells);
     ctx->launches += 1;
     SPH_CUDA_CHECK(cudaGetLastError());
     return SPHGPU_OK;
@@ -1248,6 +1256,9 @@ static int launchSumVariant(sphgpu_ctx* ctx) {
     }
     if (ctx->deltasph) { // (not together with the Balsara switch or the XSph term either)
         return launchSumVariantB<SOLID, CORRECTED, FILTER, false, false, true>(ctx);
+    }
+    if (SOLID && ctx->stressAv) { // (solids only, and on its own as well)
+        return launchSumVariantB<SOLID, CORRECTED, FILTER, false, false, false, SOLID>(ctx);
     }
     return ctx->balsara ? launchSumVariantB<SOLID, CORRECTED, FILTER, true, false>(ctx) : launchSumVariantB<SOLID, CORRECTED, FILTER, false, false>(ctx);
 }

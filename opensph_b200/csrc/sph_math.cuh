@@ -54,7 +54,14 @@ struct ParamsDev {
     double courant, derivative_factor, divergence_factor;
     double xsph_eps; // SPH_XSPH_EPSILON (SPHGPU_FLAG_XSPH)
     double deltasph_half_delta, deltasph_half_alpha; // SPH_DENSITY_DIFFUSION_DELTA / 2, SPH_VELOCITY_DIFFUSION_ALPHA / 2
+    double stress_av_exponent, stress_av_factor;     // SPH_AV_STRESS_EXPONENT, SPH_AV_STRESS_FACTOR (SPHGPU_FLAG_STRESS_AV)
+    uint32_t stress_av_int_exponent, pad0;           // the exponent if it is 1, 2, 3 or 4 (stressAvIntExponent), else 0
 };
+
+/// Small integer exponents of the artificial stress' weighting function are evaluated by multiplication.
+SPH_HD uint32_t stressAvIntExponent(double n) {
+    return n == 1. ? 1u : n == 2. ? 2u : n == 3. ? 3u : n == 4. ? 4u : 0u;
+}
 
 SPH_HD double sqr(double x) {
     return x * x;
@@ -233,6 +240,66 @@ SPH_HD double balsaraFactor(double divv, double rx, double ry, double rz, double
     return dv / (dv + rv + 1.e-4 * cs / h);
 }
 
+/// One Jacobi rotation annihilating the off-diagonal element a_pq of a symmetric 3x3 matrix; r is the third index.
+/// vp, vq: the columns p and q of the accumulated rotation.
+SPH_HD void jacobiRotate(double& app, double& aqq, double& apq, double& arp, double& arq, double vp[3], double vq[3]) {
+    if (apq == 0.) {
+        return;
+    }
+    const double theta = (aqq - app) / (2. * apq);
+    const double t = (theta >= 0. ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1.));
+    const double c = 1. / sqrt(t * t + 1.), sn = t * c;
+    app -= t * apq;
+    aqq += t * apq;
+    apq = 0.;
+    const double rp = arp, rq = arq;
+    arp = c * rp - sn * rq;
+    arq = sn * rp + c * rq;
+    for (int k = 0; k < 3; ++k) {
+        const double a = vp[k], b = vq[k];
+        vp[k] = c * a - sn * b;
+        vq[k] = sn * a + c * b;
+    }
+}
+
+/// StressAV::initialize for one particle (core/sph/equations/av/Stress.cpp:91-109): as = -V max(Lambda, 0) V^T for the
+/// eigen-decomposition sigma = V Lambda V^T of the total stress sigma = S - p I, i.e. minus its positive (tensile) part. Being
+/// a function of the tensor, the result does not depend on the eigen-solver beyond rounding: the reference runs JAMA's
+/// tred2 / tql2 (SymmetricTensor.cpp:110-272), this is cyclic Jacobi (quadratically convergent; the sweeps stop when the
+/// off-diagonal part is exactly zero, 12 at most). sigma, as: {xx,yy,zz,xy,xz,yz}.
+SPH_HD void avStressOf(const double sigma[6], double as[6]) {
+    double a00 = sigma[0], a11 = sigma[1], a22 = sigma[2], a01 = sigma[3], a02 = sigma[4], a12 = sigma[5];
+    double v0[3] = { 1., 0., 0. }, v1[3] = { 0., 1., 0. }, v2[3] = { 0., 0., 1. }; // columns of V
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        if (fabs(a01) + fabs(a02) + fabs(a12) == 0.) {
+            break;
+        }
+        jacobiRotate(a00, a11, a01, a02, a12, v0, v1); // (p, q, r) = (0, 1, 2)
+        jacobiRotate(a00, a22, a02, a01, a12, v0, v2); // (0, 2, 1)
+        jacobiRotate(a11, a22, a12, a01, a02, v1, v2); // (1, 2, 0)
+    }
+    const double l0 = fmax(a00, 0.), l1 = fmax(a11, 0.), l2 = fmax(a22, 0.);
+    as[0] = -(l0 * v0[0] * v0[0] + l1 * v1[0] * v1[0] + l2 * v2[0] * v2[0]);
+    as[1] = -(l0 * v0[1] * v0[1] + l1 * v1[1] * v1[1] + l2 * v2[1] * v2[1]);
+    as[2] = -(l0 * v0[2] * v0[2] + l1 * v1[2] * v1[2] + l2 * v2[2] * v2[2]);
+    as[3] = -(l0 * v0[0] * v0[1] + l1 * v1[0] * v1[1] + l2 * v2[0] * v2[1]);
+    as[4] = -(l0 * v0[0] * v0[2] + l1 * v1[0] * v1[2] + l2 * v2[0] * v2[2]);
+    as[5] = -(l0 * v0[1] * v0[2] + l1 * v1[1] * v1[2] + l2 * v2[1] * v2[2]);
+}
+
+/// The weighting function (W_ij / W_0)^n of the artificial stress (Stress.cpp:46-47): small integer exponents (the default is 4)
+/// by multiplication, anything else through pow.
+SPH_HD double stressAvWeight(double x, double n, uint32_t intN) {
+    const double x2 = x * x;
+    if (intN == 4u) {
+        return x2 * x2;
+    }
+    if (intN == 0u) {
+        return pow(x, n);
+    }
+    return intN == 2u ? x2 : intN == 3u ? x2 * x : x;
+}
+
 // ---- pair interaction ------------------------------------------------------------------------------------
 
 /// What one particle contributes as a neighbour. P = p/rho^2, Sr = S/rho^2, vol = m/rho, grp = body flag or -1 if the
@@ -245,6 +312,8 @@ struct Particle {
     double Sr[5];
     double bal; // Balsara factor |div v| / (|div v| + |rot v| + 1e-4 cs / h) (Balsara.h:76-80); unused without the switch
     double gr[3]; // DELTASPH_DENSITY_GRADIENT of the previous evaluation (DeltaSph.h:71-74); delta-SPH terms only
+    double as[6]; // AV_STRESS / rho^2 {xx,yy,zz,xy,xz,yz} (Stress.cpp:68-79); artificial stress only
+    double wpInv; // 1 / INTERPARTICLE_SPACING_KERNEL (Stress.cpp:113-121); artificial stress only, targets only
     int grp;
 };
 
@@ -378,7 +447,7 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
         const double g0 = lut[k], g1 = lut[k + 1];
 #endif
         G = g0 * (1. - ratio) + g1 * ratio;
-        if (prm.flags & SPHGPU_FLAG_XSPH) { // LutKernel::valueImpl (Kernel.h:111-127)
+        if (prm.flags & (SPHGPU_FLAG_XSPH | SPHGPU_FLAG_STRESS_AV)) { // LutKernel::valueImpl (Kernel.h:111-127)
             W = lutW[k] * (1. - ratio) + lutW[k + 1] * ratio;
         }
     }
@@ -424,6 +493,28 @@ SPH_HD void pairAccumulate(const ParamsDev& prm, const double* __restrict__ lut,
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
+
+    if (prm.flags & SPHGPU_FLAG_STRESS_AV) { // StressAV::Derivative::eval (Stress.cpp:44-57) in the reference's own form
+        bool ok = true;
+        if (SOLID && FILTER) {
+            ok = (pi.grp == pj.grp) && (pi.grp >= 0);
+        }
+        if (ok) {
+            const double phi = prm.stress_av_factor * stressAvWeight((hInv2 * hInv * W) * pi.wpInv, prm.stress_av_exponent, prm.stress_av_int_exponent);
+            double Pi[6];
+            for (int q = 0; q < 6; ++q) {
+                Pi[q] = phi * (pi.as[q] + pj.as[q]);
+            }
+            const double fx = Pi[0] * gx + Pi[3] * gy + Pi[4] * gz;
+            const double fy = Pi[3] * gx + Pi[1] * gy + Pi[5] * gz;
+            const double fz = Pi[4] * gx + Pi[5] * gy + Pi[2] * gz;
+            acc.ax += pj.m * fx;
+            acc.ay += pj.m * fy;
+            acc.az += pj.m * fz;
+            // heating = 1/2 (Pi (v_i - v_j)) . gradW = -1/2 (v_j - v_i) . (Pi gradW)  (Pi is symmetric)
+            acc.du -= pj.m * (0.5 * (dvx * fx + dvy * fy + dvz * fz));
+        }
+    }
 
     if (prm.flags & SPHGPU_FLAG_DELTASPH) { // DeltaSph.h:37-44, 81-93, 147-163 in the reference's own form (dr = r_j - r_i = -d)
         bool ok = true;
@@ -555,7 +646,7 @@ SPH_HD void pairGeometry(const ParamsDev& prm, double xi, double yi, double zi, 
 /// Stage B. G = the interpolated table value g + ratio dg of entry g.k. Of pi only v, P, cs, grp are read; of pj v, m,
 /// P, cs, vol, Sr, grp. The stress sum is split: sum_j (Sr_i + Sr_j) f_j = Sr_i F + sum_j Sr_j f_j with F = sum_j f_j
 /// (acc.F, applied by finalizeParticle), which saves the target's Sr registers and two additions per pair.
-template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false, bool XSPH = false, bool DELTA = false>
+template <bool SOLID, bool CORRECTED, bool FILTER, bool BALSARA = false, bool XSPH = false, bool DELTA = false, bool STRESSAV = false>
 SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& pj, const PairGeom& g, double G, Accum& acc, double W = 0.) {
     acc.cnt += g.valid ? 1u : 0u;
     const double mj = selectD(g.valid, pj.m, 0.);
@@ -592,6 +683,27 @@ SPH_HD void pairSums(const ParamsDev& prm, const Particle& pi, const Particle& p
     acc.ax -= c * mgx;
     acc.ay -= c * mgy;
     acc.az -= c * mgz;
+    if (STRESSAV) {
+        // StressAV::Derivative (Stress.cpp:44-57), SUM_ONLY_UNDAMAGED: Pi = phi (A_i + A_j) with A = as / rho^2 and
+        // phi = xi (W_ij / W_0i)^n, W_ij = hbar^-3 W(q^2) (W: the table value, 0 for a rejected candidate);
+        // dv_i += m_j Pi gradW, du_i += m_j (Pi (v_i - v_j)) . gradW / 2 = -m_j (v_j - v_i) . (Pi gradW) / 2
+        bool ok = g.valid;
+        if (SOLID && FILTER) {
+            ok = g.valid && (pi.grp == pj.grp) && (pi.grp >= 0);
+        }
+        const double w = W * ((g.hInv5 * g.hbar) * g.hbar);
+        const double phi = prm.stress_av_factor * stressAvWeight(w * pi.wpInv, prm.stress_av_exponent, prm.stress_av_int_exponent);
+        const double ps = (selectD(ok, pj.m, 0.) * s) * phi; // m_j phi gradW = ps d
+        const double a0 = pi.as[0] + pj.as[0], a1 = pi.as[1] + pj.as[1], a2 = pi.as[2] + pj.as[2];
+        const double a3 = pi.as[3] + pj.as[3], a4 = pi.as[4] + pj.as[4], a5 = pi.as[5] + pj.as[5];
+        const double fx = ps * fma(a4, dz, fma(a3, dy, a0 * dx));
+        const double fy = ps * fma(a5, dz, fma(a1, dy, a3 * dx));
+        const double fz = ps * fma(a2, dz, fma(a5, dy, a4 * dx));
+        acc.ax += fx;
+        acc.ay += fy;
+        acc.az += fz;
+        acc.du -= 0.5 * (dvx * fx + dvy * fy + dvz * fz);
+    }
     if (DELTA) {
         // The three delta-SPH derivatives carry SUM_ONLY_UNDAMAGED (DeltaSph.h:22-24,63-64,135-136), which acts where the
         // Storage has STRESS_REDUCING, i.e. for solids (DerivativeHelpers.h:84-91).
@@ -665,7 +777,9 @@ SPH_HD void pairAccumulateMasked(const ParamsDev& prm, const LutPair* __restrict
     PairGeom g;
     pairGeometry(prm, pi.x, pi.y, pi.z, pi.h, pi.rho, pj.x, pj.y, pj.z, pj.h, pj.rho, g);
     const double G = fma(g.ratio, lut2[g.k].dg, lut2[g.k].g);
-    if (prm.flags & SPHGPU_FLAG_DELTASPH) {
+    if (prm.flags & SPHGPU_FLAG_STRESS_AV) {
+        pairSums<SOLID, CORRECTED, FILTER, false, false, false, true>(prm, pi, pj, g, G, acc, fma(g.ratio, lutW2[g.k].dg, lutW2[g.k].g));
+    } else if (prm.flags & SPHGPU_FLAG_DELTASPH) {
         pairSums<SOLID, CORRECTED, FILTER, false, false, true>(prm, pi, pj, g, G, acc);
     } else if (prm.flags & SPHGPU_FLAG_XSPH) {
         pairSums<SOLID, CORRECTED, FILTER, false, true>(prm, pi, pj, g, G, acc, fma(g.ratio, lutW2[g.k].dg, lutW2[g.k].g));

@@ -31,6 +31,8 @@ enum Field : int {
     F_ROTX, F_ROTY, F_ROTZ,       // VELOCITY_ROTATION (Balsara switch): result of the last evaluation, input of the next
     F_XSX, F_XSY, F_XSZ,          // XSPH_VELOCITIES (XSph term): the correction currently contained in the velocities
     F_DGX, F_DGY, F_DGZ,          // DELTASPH_DENSITY_GRADIENT (delta-SPH terms): result of the last evaluation, input of the next
+    F_AS0, F_AS1, F_AS2, F_AS3, F_AS4, F_AS5, // AV_STRESS {xx,yy,zz,xy,xz,yz} (artificial stress): written by every prologue
+    F_WP,                         // INTERPARTICLE_SPACING_KERNEL (artificial stress): uploaded once
     F_COUNT
 };
 
@@ -50,18 +52,22 @@ enum UField : int { U_NFLAWS, U_FLAG, U_MATID, U_NCNT, U_COUNT };
 // With the delta-SPH terms every particle contributes the density gradient G of the previous evaluation, two more pieces
 // {Gx,Gy | Gz,-} behind the regular ones plus one piece of padding to keep the stride odd: solid 11 pieces = 176 bytes,
 // fluid 9 pieces = 144 bytes.
+// With the artificial stress (solids only) every particle contributes as / rho^2, three more pieces {xx,yy | zz,xy | xz,yz}:
+// 11 pieces = 176 bytes as well (the two layouts never coexist; the run flags tell them apart).
 constexpr int REC_SOLID = 16;         // doubles per record, solid
 constexpr int REC_FLUID = 14;         // doubles per record, fluid
 constexpr int REC_SOLID_BALSARA = 18; // doubles per record, solid with the Balsara switch
 constexpr int REC_SOLID_DELTA = 22;   // doubles per record, solid with the delta-SPH terms
 constexpr int REC_FLUID_DELTA = 18;   // doubles per record, fluid with the delta-SPH terms
+constexpr int REC_SOLID_STRESSAV = 22; // doubles per record, solid with the artificial stress
 
-__host__ __device__ inline int recordDoubles(bool solid, bool balsara, bool delta = false) {
-    return delta ? (solid ? REC_SOLID_DELTA : REC_FLUID_DELTA) : solid ? (balsara ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID;
+__host__ __device__ inline int recordDoubles(bool solid, bool balsara, bool delta = false, bool stressAv = false) {
+    return stressAv ? REC_SOLID_STRESSAV
+                    : delta ? (solid ? REC_SOLID_DELTA : REC_FLUID_DELTA) : solid ? (balsara ? REC_SOLID_BALSARA : REC_SOLID) : REC_FLUID;
 }
 /// Record size from the run flags (SPHGPU_FLAG_BALSARA / SPHGPU_FLAG_DELTASPH exclude each other).
 __host__ __device__ inline int recordDoublesOf(bool solid, uint32_t flags) {
-    return recordDoubles(solid, (flags & SPHGPU_FLAG_BALSARA) != 0, (flags & SPHGPU_FLAG_DELTASPH) != 0);
+    return recordDoubles(solid, (flags & SPHGPU_FLAG_BALSARA) != 0, (flags & SPHGPU_FLAG_DELTASPH) != 0, (flags & SPHGPU_FLAG_STRESS_AV) != 0);
 }
 /// XOR swizzle of the record with sorted / staged index t (0 for the layouts with an odd stride).
 __host__ __device__ inline uint32_t recordSwizzle(int recDoubles, uint32_t t) {
@@ -192,7 +198,7 @@ struct sphgpu_ctx {
     sph::MaterialDev matsHost[sph::MAX_MATERIALS];
     sphgpu_material matsApi[sph::MAX_MATERIALS];
     uint32_t nMaterials = 0;
-    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false, xsph = false, deltasph = false;
+    bool solid = false, corrected = false, filter = false, hasReduce = false, hasDamage = false, balsara = false, xsph = false, deltasph = false, stressAv = false;
     int recDoubles = sph::REC_FLUID; // doubles per sorted neighbour record of this context
     sph::DevicePointers d{};
     void* staging = nullptr;   // device staging for AoS <-> SoA repack (capacity * 64 B)

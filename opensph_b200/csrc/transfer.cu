@@ -51,6 +51,8 @@ static QuantityMap quantityMap(int q, int order) {
     case SPHGPU_Q_VELOCITY_ROTATION: if (order == 0) set(4, { F_ROTX, F_ROTY, F_ROTZ, -1 }); break;
     case SPHGPU_Q_XSPH_VELOCITIES: if (order == 0) set(4, { F_XSX, F_XSY, F_XSZ, -1 }); break;
     case SPHGPU_Q_DELTASPH_DENSITY_GRADIENT: if (order == 0) set(4, { F_DGX, F_DGY, F_DGZ, -1 }); break;
+    case SPHGPU_Q_AV_STRESS: if (order == 0) set(6, { F_AS0, F_AS1, F_AS2, F_AS3, F_AS4, F_AS5 }); break;
+    case SPHGPU_Q_INTERPARTICLE_SPACING_KERNEL: if (order == 0) set(1, { F_WP }); break;
     default: break;
     }
     return m;

@@ -83,6 +83,9 @@ class Engine:
         if setup.cfg.flags & abi.FLAG_DELTASPH:
             _check(self.lib.sphgpu_set_deltasph(self._ctx, C.c_double(getattr(setup, "deltasph_delta", 0.01)),
                                                 C.c_double(getattr(setup, "deltasph_alpha", 0.01))))
+        if setup.cfg.flags & abi.FLAG_STRESS_AV:
+            _check(self.lib.sphgpu_set_stress_av(self._ctx, C.c_double(getattr(setup, "stress_av_exponent", 4.0)),
+                                                 C.c_double(getattr(setup, "stress_av_factor", 0.04))))
 
     # -- lifetime ----------------------------------------------------------------------------------------------
     def close(self) -> None:

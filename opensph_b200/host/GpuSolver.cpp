@@ -10,6 +10,7 @@
 #include "sph/equations/av/Standard.h"
 #include "sph/equations/DeltaSph.h"
 #include "sph/equations/XSph.h"
+#include "sph/equations/av/Stress.h"
 #include "system/Factory.h"
 #include "system/Statistics.h"
 #include "system/Timer.h"
@@ -49,7 +50,8 @@ const QuantityBinding SCALARS_FIRST[] = { { QuantityId::DENSITY, SPHGPU_Q_DENSIT
 const QuantityBinding SCALARS_ZERO[] = { { QuantityId::MASS, SPHGPU_Q_MASS }, { QuantityId::PRESSURE, SPHGPU_Q_PRESSURE },
     { QuantityId::SOUND_SPEED, SPHGPU_Q_SOUND_SPEED }, { QuantityId::STRESS_REDUCING, SPHGPU_Q_STRESS_REDUCING },
     { QuantityId::EPS_MIN, SPHGPU_Q_EPS_MIN }, { QuantityId::M_ZERO, SPHGPU_Q_M_ZERO },
-    { QuantityId::EXPLICIT_GROWTH, SPHGPU_Q_EXPLICIT_GROWTH } };
+    { QuantityId::EXPLICIT_GROWTH, SPHGPU_Q_EXPLICIT_GROWTH },
+    { QuantityId::INTERPARTICLE_SPACING_KERNEL, SPHGPU_Q_INTERPARTICLE_SPACING_KERNEL } };
 const QuantityBinding INDICES[] = { { QuantityId::FLAG, SPHGPU_Q_FLAG }, { QuantityId::N_FLAWS, SPHGPU_Q_N_FLAWS } };
 
 } // namespace
@@ -71,6 +73,7 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     known += equations.contains<XSph>() ? 1 : 0;
     known += equations.contains<DeltaSph::DensityDiffusion>() ? 1 : 0;
     known += equations.contains<DeltaSph::VelocityDiffusion>() ? 1 : 0;
+    known += equations.contains<StressAV>() ? 1 : 0;
     known += equations.contains<AdaptiveSmoothingLength>() ? 1 : 0;
     known += equations.contains<ConstSmoothingLength>() ? 1 : 0;
     if (known != equations.getTermCnt()) {
@@ -90,6 +93,14 @@ GpuSolver::GpuSolver(IScheduler& scheduler, const RunSettings& settings, const E
     if (equations.contains<DeltaSph::DensityDiffusion>() &&
         (equations.contains<XSph>() || equations.contains<BalsaraSwitch<StandardAV>>())) {
         throw InvalidSetup("GpuSolver: the delta-SPH terms together with XSph or the Balsara switch are not implemented on the device");
+    }
+    if (equations.contains<StressAV>()) {
+        if (equations.contains<XSph>() || equations.contains<BalsaraSwitch<StandardAV>>() || equations.contains<DeltaSph::DensityDiffusion>()) {
+            throw InvalidSetup("GpuSolver: the artificial stress together with XSph, the Balsara switch or the delta-SPH terms is not implemented on the device");
+        }
+        if (!equations.contains<SolidStressForce>()) {
+            throw InvalidSetup("GpuSolver: the artificial stress needs SolidStressForce (it is built from the deviatoric stress)");
+        }
     }
     if (equations.contains<BalsaraSwitch<StandardAV>>() && settings.get<bool>(RunSettingsId::SPH_AV_BALSARA_STORE)) {
         throw InvalidSetup("GpuSolver: SPH_AV_BALSARA_STORE (the AV_BALSARA output quantity) is not implemented on the device");
@@ -242,6 +253,9 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     if (equations.contains<DeltaSph::DensityDiffusion>()) {
         cfg.flags |= SPHGPU_FLAG_DELTASPH;
     }
+    if (equations.contains<StressAV>()) {
+        cfg.flags |= SPHGPU_FLAG_STRESS_AV;
+    }
     if (equations.contains<AdaptiveSmoothingLength>()) {
         cfg.flags |= SPHGPU_FLAG_ADAPTIVE_H;
         if (hflags.has(SmoothingLengthEnum::SOUND_SPEED_ENFORCING)) {
@@ -325,6 +339,10 @@ sphgpu_ctx* GpuSolver::context(const Storage& storage) {
     ctxParticleCnt = n;
     if (cfg.flags & SPHGPU_FLAG_XSPH) {
         check(sphgpu_set_xsph_epsilon(ctx, settings.get<Float>(RunSettingsId::SPH_XSPH_EPSILON)));
+    }
+    if (cfg.flags & SPHGPU_FLAG_STRESS_AV) {
+        check(sphgpu_set_stress_av(ctx, settings.get<Float>(RunSettingsId::SPH_AV_STRESS_EXPONENT),
+            settings.get<Float>(RunSettingsId::SPH_AV_STRESS_FACTOR)));
     }
     if (cfg.flags & SPHGPU_FLAG_DELTASPH) {
         check(sphgpu_set_deltasph(ctx, settings.get<Float>(RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA),
@@ -538,6 +556,9 @@ void GpuSolver::downloadQuantities(Storage& storage, const bool stateToo) {
     }
     if (storage.has(QuantityId::VELOCITY_ROTATION)) {
         check(sphgpu_download(c, SPHGPU_Q_VELOCITY_ROTATION, 0, L, &storage.getValue<Vector>(QuantityId::VELOCITY_ROTATION)[0], 0, n));
+    }
+    if (storage.has(QuantityId::AV_STRESS)) { // StressAV::initialize leaves it in the Storage (Stress.cpp:91-109)
+        check(sphgpu_download(c, SPHGPU_Q_AV_STRESS, 0, L, &storage.getValue<SymmetricTensor>(QuantityId::AV_STRESS)[0], 0, n));
     }
     if (storage.has(QuantityId::VELOCITY_GRADIENT)) {
         check(sphgpu_download(c, SPHGPU_Q_VELOCITY_GRADIENT, 0, L, &storage.getValue<SymmetricTensor>(QuantityId::VELOCITY_GRADIENT)[0], 0, n));

@@ -12,7 +12,7 @@
 //   sph_ref snapshot --config C --n N [--jitter SEED] [--threads T] [--finder kd|grid] [--solver asym|sym]
 //                    [--neighbours] [--steps K] [--integrator pc|euler] [--no-lut] [--lut LUT.snap]
 //                    [--frozen-flag F] [--frozen-domain RADIUS [--frozen-radius r]]
-//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--xsph [EPS]] [--deltasph [--deltasph-delta D] [--deltasph-alpha A]] [--criteria MASK]
+//                    [--corrected 0|1] [--const-h] [--enforcing] [--continuity-undamaged] [--sum-all] [--balsara] [--xsph [EPS]] [--deltasph [--deltasph-delta D] [--deltasph-alpha A]] [--stress-av [--stress-av-exponent N] [--stress-av-factor X]] [--criteria MASK]
 //                    --in IN.snap --out OUT.snap
 //       builds the Storage of config C, writes it (state BEFORE integrate) to IN.snap, then either runs one
 //       solver.integrate() on zeroed highest derivatives (K == 0) or K time steps, and writes OUT.snap.
@@ -221,6 +221,15 @@ RunSettings makeSettings(const std::string& config, const Args& args) {
             settings.set(RunSettingsId::SPH_VELOCITY_DIFFUSION_ALPHA, Float(atof(args.str("deltasph-alpha").c_str())));
         }
     }
+    if (args.has("stress-av")) { // the artificial stress StressAV (core/sph/equations/av/Stress.cpp; StandardSets.cpp:72-74)
+        settings.set(RunSettingsId::SPH_AV_USE_STRESS, true);
+        if (args.has("stress-av-exponent")) {
+            settings.set(RunSettingsId::SPH_AV_STRESS_EXPONENT, Float(atof(args.str("stress-av-exponent").c_str())));
+        }
+        if (args.has("stress-av-factor")) {
+            settings.set(RunSettingsId::SPH_AV_STRESS_FACTOR, Float(atof(args.str("stress-av-factor").c_str())));
+        }
+    }
     if (args.has("sum-all")) { // SPH_SUM_ONLY_UNDAMAGED = false: no undamaged filter
         settings.set(RunSettingsId::SPH_SUM_ONLY_UNDAMAGED, false);
     }
@@ -376,6 +385,10 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
     if (storage.has(QuantityId::XSPH_VELOCITIES)) {
         w.addF64("xsph", vec4(storage.getValue<Vector>(QuantityId::XSPH_VELOCITIES)), 4);
     }
+    if (storage.has(QuantityId::AV_STRESS)) {
+        w.addF64("av_stress", st6(storage.getValue<SymmetricTensor>(QuantityId::AV_STRESS)), 6);
+    }
+    first("wp", nullptr, QuantityId::INTERPARTICLE_SPACING_KERNEL);
     if (storage.has(QuantityId::DELTASPH_DENSITY_GRADIENT)) {
         w.addF64("drho_grad", vec4(storage.getValue<Vector>(QuantityId::DELTASPH_DENSITY_GRADIENT)), 4);
     }
@@ -458,6 +471,9 @@ void dumpState(const Storage& storage, const RunSettings& settings, SnapWriter& 
         double(settings.get<bool>(RunSettingsId::SPH_USE_DELTASPH)),
         settings.get<Float>(RunSettingsId::SPH_DENSITY_DIFFUSION_DELTA),
         settings.get<Float>(RunSettingsId::SPH_VELOCITY_DIFFUSION_ALPHA),
+        double(settings.get<bool>(RunSettingsId::SPH_AV_USE_STRESS)),
+        settings.get<Float>(RunSettingsId::SPH_AV_STRESS_EXPONENT),
+        settings.get<Float>(RunSettingsId::SPH_AV_STRESS_FACTOR),
     };
     w.addF64("run_params", run, 1);
 

@@ -425,6 +425,53 @@ static void materials_finalize(orc_state* s, const sphgpu_material* mats, uint32
 
 /* ---- derivatives ------------------------------------------------------------------------------------------ */
 
+/* StressAV::initialize for one particle (core/sph/equations/av/Stress.cpp:91-109): sigma = S - p I is diagonalised, the positive
+ * principal stresses are negated, the negative ones dropped, and the result is rotated back: as = -V max(Lambda, 0) V^T, i.e.
+ * minus the positive part of sigma -- a function of the tensor, so any convergent symmetric eigen-solver gives the same result
+ * to rounding. The reference uses JAMA's tred2 / tql2 (SymmetricTensor.cpp:110-272); this restatement uses cyclic Jacobi
+ * rotations and is pinned on the golden vectors of the reference run. sigma, as: {xx,yy,zz,xy,xz,yz}. */
+static void av_stress_of(const double sigma[6], double as[6]) {
+    double A[3][3] = { { sigma[0], sigma[3], sigma[4] }, { sigma[3], sigma[1], sigma[5] }, { sigma[4], sigma[5], sigma[2] } };
+    double V[3][3] = { { 1., 0., 0. }, { 0., 1., 0. }, { 0., 0., 1. } };
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.) {
+            break;
+        }
+        for (int p = 0; p < 2; ++p) {
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == 0.) {
+                    continue;
+                }
+                const double theta = (A[q][q] - A[p][p]) / (2. * A[p][q]);
+                const double t = (theta >= 0. ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1.));
+                const double c = 1. / sqrt(t * t + 1.), sn = t * c;
+                const int r = 3 - p - q;
+                const double app = A[p][p], aqq = A[q][q], apq = A[p][q], arp = A[r][p], arq = A[r][q];
+                A[p][p] = app - t * apq;
+                A[q][q] = aqq + t * apq;
+                A[p][q] = A[q][p] = 0.;
+                A[r][p] = A[p][r] = c * arp - sn * arq;
+                A[r][q] = A[q][r] = sn * arp + c * arq;
+                for (int k = 0; k < 3; ++k) {
+                    const double vp = V[k][p], vq = V[k][q];
+                    V[k][p] = c * vp - sn * vq;
+                    V[k][q] = sn * vp + c * vq;
+                }
+            }
+        }
+    }
+    static const int IX[6][2] = { { 0, 0 }, { 1, 1 }, { 2, 2 }, { 0, 1 }, { 0, 2 }, { 1, 2 } };
+    for (int c = 0; c < 6; ++c) {
+        double v = 0.;
+        for (int k = 0; k < 3; ++k) {
+            const double lam = A[k][k] > 0. ? A[k][k] : 0.;
+            v -= lam * V[IX[c][0]][k] * V[IX[c][1]][k];
+        }
+        as[c] = v;
+    }
+}
+
 /* DerivativeTemplate::sum / AccelerationTemplate::sum filter, core/sph/equations/DerivativeHelpers.h:132-139 */
 static int undamaged_skip(const orc_state* s, uint32_t i, uint32_t j) {
     return s->flag[i] != s->flag[j] || s->reduce[i] == 0. || s->reduce[j] == 0.;
@@ -455,6 +502,16 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
             for (int q = 0; q < 3; ++q) {
                 s->vel[4 * (size_t)i + q] -= s->xsph[4 * (size_t)i + q];
             }
+        }
+    }
+
+    /* StressAV::initialize (Stress.cpp:91-109) on the pressure and stress the materials just left in the Storage */
+    const int stressAv = (cfg->flags & SPHGPU_FLAG_STRESS_AV) != 0;
+    if (stressAv) {
+        for (uint32_t i = 0; i < n; ++i) {
+            const double* S = s->S + 5 * (size_t)i;
+            const double sigma[6] = { S[0] - s->p[i], S[1] - s->p[i], (-S[0] - S[1]) - s->p[i], S[2], S[3], S[4] };
+            av_stress_of(sigma, s->av_stress + 6 * (size_t)i);
         }
     }
 
@@ -654,6 +711,37 @@ void orc_integrate(orc_state* s, const sphgpu_config* cfg, const sphgpu_material
                     s->xsph[4 * (size_t)i + q] = xs[q];
                 }
                 s->xsph[4 * (size_t)i + 3] = 0.;
+            }
+            /* StressAV::Derivative::eval with the STANDARD discretisation (Stress.cpp:44-57,68-79), SUM_ONLY_UNDAMAGED;
+             * AccelerationTemplate: dv_i += m_j f, du_i += m_j heating (DerivativeHelpers.h:216-227) */
+            if (stressAv) {
+                const double* ai = s->av_stress + 6 * (size_t)i;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const uint32_t j = neighs[k];
+                    if (filter && undamaged_skip(s, i, j)) {
+                        continue;
+                    }
+                    const double* aj = s->av_stress + 6 * (size_t)j;
+                    const double* vj = s->vel + 4 * (size_t)j;
+                    const double* gr = grads + 3 * k;
+                    const double w = kernel_value(cfg, ri, s->pos + 4 * (size_t)j);
+                    const double phi = s->stress_av_factor * pow(w / s->wp[i], s->stress_av_exponent);
+                    const double ri2 = sqr(s->rho[i]), rj2 = sqr(s->rho[j]);
+                    double Pi[6];
+                    for (int q = 0; q < 6; ++q) {
+                        Pi[q] = phi * (ai[q] / ri2 + aj[q] / rj2);
+                    }
+                    const double f[3] = { Pi[0] * gr[0] + Pi[3] * gr[1] + Pi[4] * gr[2], Pi[3] * gr[0] + Pi[1] * gr[1] + Pi[5] * gr[2],
+                        Pi[4] * gr[0] + Pi[5] * gr[1] + Pi[2] * gr[2] };
+                    const double a[3] = { vi[0] - vj[0], vi[1] - vj[1], vi[2] - vj[2] };
+                    const double Pa[3] = { Pi[0] * a[0] + Pi[3] * a[1] + Pi[4] * a[2], Pi[3] * a[0] + Pi[1] * a[1] + Pi[5] * a[2],
+                        Pi[4] * a[0] + Pi[5] * a[1] + Pi[2] * a[2] };
+                    const double heating = 0.5 * (Pa[0] * gr[0] + Pa[1] * gr[1] + Pa[2] * gr[2]);
+                    for (int q = 0; q < 3; ++q) {
+                        dv[q] += s->mass[j] * f[q];
+                    }
+                    du += s->mass[j] * heating;
+                }
             }
             if (deltasph) {
                 const double* Gi = s->drho_grad + 4 * (size_t)i;

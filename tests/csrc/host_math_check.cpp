@@ -50,6 +50,16 @@ static void run(orc_state* s, const ParamsDev& prm, const std::vector<MaterialDe
         q.P = p * r2; q.vol = q.m / q.rho;
         for (int k = 0; k < 5; ++k) q.Sr[k] = S[k] * r2;
         q.grp = (hasReduce && reduce == 0.) ? -1 : (int)s->flag[i];
+        if (prm.flags & SPHGPU_FLAG_STRESS_AV) { // k_prologue_pack: StressAV::initialize on the yielded stress and reduced pressure
+            const double sigma[6] = { S[0] - p, S[1] - p, (-S[0] - S[1]) - p, S[2], S[3], S[4] };
+            double as[6];
+            avStressOf(sigma, as);
+            for (int k = 0; k < 6; ++k) {
+                s->av_stress[6 * (size_t)i + k] = as[k];
+                q.as[k] = as[k] * r2;
+            }
+            q.wpInv = 1. / s->wp[i];
+        }
         if (prm.flags & SPHGPU_FLAG_DELTASPH) { // k_prologue_pack: the gradient of the previous evaluation rides in the record
             for (int k = 0; k < 3; ++k) q.gr[k] = s->drho_grad[4 * (size_t)i + k];
         }
@@ -150,7 +160,7 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
     // kernel values for the XSph term (api.cu uploads them the same way)
     std::vector<double> lutWGuard;
     std::vector<LutPair> lutWPairs;
-    if (cfg->flags & SPHGPU_FLAG_XSPH) {
+    if (cfg->flags & (SPHGPU_FLAG_XSPH | SPHGPU_FLAG_STRESS_AV)) {
         lutWGuard.assign(cfg->lut_value, cfg->lut_value + cfg->lut_entries + 1);
         lutWGuard.push_back(0.);
         lutWPairs.resize(cfg->lut_entries + 1);
@@ -161,6 +171,9 @@ static int dispatch(orc_state* s, const sphgpu_config* cfg, const sphgpu_materia
     prm.xsph_eps = s->xsph_eps;
     prm.deltasph_half_delta = 0.5 * s->deltasph_delta;
     prm.deltasph_half_alpha = 0.5 * s->deltasph_alpha;
+    prm.stress_av_exponent = s->stress_av_exponent;
+    prm.stress_av_factor = s->stress_av_factor;
+    prm.stress_av_int_exponent = stressAvIntExponent(s->stress_av_exponent);
     const bool solid = cfg->forces & SPHGPU_FORCE_SOLID_STRESS;
     const bool corrected = solid && (cfg->flags & SPHGPU_FLAG_CORRECTION_TENSOR);
     const bool filter = solid && (cfg->flags & SPHGPU_FLAG_SUM_ONLY_UNDAMAGED) && hasReduce;

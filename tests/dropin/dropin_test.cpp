@@ -508,15 +508,39 @@ int main(int argc, char** argv) {
             expect(frozenCnt > 0 && frozenCnt < dvF.size(), "the boundary condition freezes some particles");
             expect(compareStorages(fa, fb, true, "integrate() with FrozenParticles") <= 1.e-10, "all quantities within 1e-10 with FrozenParticles");
         }
+        // ---- the artificial stress (SPH_AV_USE_STRESS): two consecutive evaluations against the reference ----
+        {
+            RunSettings as = settings;
+            as.set(RunSettingsId::SPH_AV_USE_STRESS, true).set(RunSettingsId::SPH_AV_STRESS_FACTOR, 0.2_f);
+            const EquationHolder aeqs = getStandardEquations(as);
+            AsymmetricSolver refA(*scheduler, as, aeqs);
+            GpuSolver gpuA(*scheduler, as, aeqs);
+            Storage aa = base->clone(VisitorEnum::ALL_BUFFERS), ab = base->clone(VisitorEnum::ALL_BUFFERS);
+            for (Size m = 0; m < aa.getMaterialCnt(); ++m) {
+                refA.create(aa, aa.getMaterial(m));
+                gpuA.create(ab, ab.getMaterial(m));
+            }
+            for (int pass = 0; pass < 2; ++pass) {
+                aa.zeroHighestDerivatives(*scheduler);
+                ab.zeroHighestDerivatives(*scheduler);
+                refA.integrate(aa, statsA);
+                gpuA.integrate(ab, statsA);
+            }
+            expect(compareStorages(aa, ab, true, "integrate() twice with the artificial stress") <= 1.e-10,
+                "all quantities within 1e-10 with the artificial stress");
+            const double se = cmpSymmetric(aa.getValue<SymmetricTensor>(QuantityId::AV_STRESS), ab.getValue<SymmetricTensor>(QuantityId::AV_STRESS));
+            printf("    %-28s %.3e\n", "AV_STRESS", se);
+            expect(se <= 1.e-10, "AV_STRESS within 1e-10");
+        }
         bool thrown = false;
         try {
             RunSettings s2 = settings;
-            s2.set(RunSettingsId::SPH_AV_USE_STRESS, true);
+            s2.set(RunSettingsId::SPH_AV_USE_STRESS, true).set(RunSettingsId::SPH_USE_XSPH, true);
             GpuSolver bad(*scheduler, s2, getStandardEquations(s2));
         } catch (const InvalidSetup&) {
             thrown = true;
         }
-        expect(thrown, "equation set with the stress AV is rejected with InvalidSetup");
+        expect(thrown, "the artificial stress together with XSph is rejected with InvalidSetup");
         thrown = false;
         try {
             RunSettings s3 = settings;

@@ -27,6 +27,9 @@ $R snapshot --config collision_preset --n 500 --jitter 3 --xsph 0.5 --steps 3 --
 $R snapshot --config collision_preset --n 500 --jitter 3 --deltasph --deltasph-delta 0.1 --deltasph-alpha 0.05 --neighbours --in deltasph_in.snap --out deltasph_out.snap --no-lut
 $R snapshot --config collision_preset --n 500 --jitter 3 --deltasph --deltasph-delta 0.1 --deltasph-alpha 0.05 --steps 3 --out deltasph_pc3.snap --no-lut
 $R snapshot --config fluid --n 500 --jitter 5 --deltasph --steps 3 --out deltasph_fluid_pc3.snap --no-lut
+# the artificial stress (SPH_AV_USE_STRESS, factor 0.2): one integrate() and three PredictorCorrector steps
+$R snapshot --config collision_preset --n 500 --jitter 3 --stress-av --stress-av-factor 0.2 --neighbours --in stressav_in.snap --out stressav_out.snap --no-lut
+$R snapshot --config collision_preset --n 500 --jitter 3 --stress-av --stress-av-factor 0.2 --steps 3 --out stressav_pc3.snap --no-lut
 # FrozenParticles boundary condition: the impactor (flag 1) frozen and everything within 0.3 h of / outside a sphere of 90 km
 $R snapshot --config collision_preset --n 500 --jitter 3 --frozen-flag 1 --frozen-domain 9e4 --frozen-radius 0.3 --out frozen_out.snap --no-lut
 # self-gravity (IGravity::build + evalSelfGravity on a zeroed buffer): brute force and Barnes-Hut, softened and point-like

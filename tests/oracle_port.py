@@ -22,7 +22,9 @@ class OrcState(C.Structure):
         "pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
         "eps_min", "m_zero", "growth")] + [(k, _U) for k in ("n_flaws", "flag", "ncnt")] + [(k, _D) for k in (
         "divv", "gradv", "corr", "acc_pred", "drho_pred", "du_pred", "dS_pred", "ddamage_pred", "xsph")] + [("xsph_eps", C.c_double), ("drho_grad", _D),
-                                                                                     ("deltasph_delta", C.c_double), ("deltasph_alpha", C.c_double)]
+                                                                                     ("deltasph_delta", C.c_double), ("deltasph_alpha", C.c_double),
+                                                                                     ("av_stress", _D), ("wp", _D),
+                                                                                     ("stress_av_exponent", C.c_double), ("stress_av_factor", C.c_double)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -40,7 +42,7 @@ def lib() -> C.CDLL:
 
 
 _F64 = ("pos", "vel", "acc", "mass", "rho", "drho", "u", "du", "p", "cs", "S", "dS", "reduce", "damage", "ddamage",
-        "eps_min", "m_zero", "growth", "divv", "gradv", "corr", "xsph", "drho_grad")
+        "eps_min", "m_zero", "growth", "divv", "gradv", "corr", "xsph", "drho_grad", "av_stress", "wp")
 _U32 = ("n_flaws", "flag", "ncnt")
 _PRED = {"acc_pred": "acc", "drho_pred": "drho", "du_pred": "du", "dS_pred": "dS", "ddamage_pred": "ddamage"}
 
@@ -80,8 +82,12 @@ class OraclePort:
             self.a.setdefault("drho_grad", np.zeros((n, 4)))
         self.state.deltasph_delta = self.setup.deltasph_delta
         self.state.deltasph_alpha = self.setup.deltasph_alpha
+        if self.setup.cfg.flags & abi.FLAG_STRESS_AV:
+            self.a.setdefault("av_stress", np.zeros((n, 6)))
+        self.state.stress_av_exponent = self.setup.stress_av_exponent
+        self.state.stress_av_factor = self.setup.stress_av_factor
         for name, _ in OrcState._fields_[2:]:
-            if name in ("xsph_eps", "deltasph_delta", "deltasph_alpha"):
+            if name in ("xsph_eps", "deltasph_delta", "deltasph_alpha", "stress_av_exponent", "stress_av_factor"):
                 continue
             arr = self.a.get(name)
             if arr is None:

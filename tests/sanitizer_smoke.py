@@ -90,6 +90,23 @@ def section_deltasph():
             setup = abi.setup_from_snapshot(i, lut)
             setup.cfg.flags |= abi.FLAG_DELTASPH
             run(i, setup, variant, name + " delta-SPH")
+    # the artificial stress (176-byte records as well, eigen-solver in the prologue, spacing kernel per target)
+    i = golden("stressav_in.snap")
+    for variant in (0, 2, 3):
+        eng = Engine(abi.setup_from_snapshot(i, lut), len(i["mass"]))
+        eng.set_variant(variant)
+        eng.upload_state(i, STATE_IN + ("wp",))
+        st = eng.integrate()
+        print("stressav_in artificial stress variant", variant, "pairs", st.pair_count)
+        eng.close()
+    setup = workloads.make_setup(len(small["mass"]), solid=True)
+    setup.cfg.flags |= abi.FLAG_STRESS_AV
+    eng = Engine(setup, len(small["mass"]))
+    eng.upload_state(small, names)
+    eng.upload_state({"wp": 0.25 / np.pi / small["pos"][:, 3] ** 3}, ["wp"])
+    dts, _, st = eng.run_pc(4, 0.01, 10.0)
+    print("run_pc 4 steps, artificial stress, pairs", st.pair_count)
+    eng.close()
     for solid in (True, False):
         st0 = small if solid else workloads.basalt_sphere_state(6000, 5.0e4, solid=False)
         setup = workloads.make_setup(len(st0["mass"]), solid=solid)
