@@ -391,6 +391,16 @@ SPHGPU_API int sphgpu_set_frozen(sphgpu_ctx* ctx, const sphgpu_frozen* cfg);
 
 /* Neighbour lists exactly as AsymmetricSolver::loop selects them (AsymmetricSolver.cpp:174-199), CSR:
  * offsets[n_particles+1], indices ascending per particle. Pass idx == NULL to obtain only offsets. */
+/* Post::findComponents of the reference (core/post/Analysis.cpp:36-75,115-128) on the positions and smoothing lengths in the
+ * context: particles are joined along the directed relation |r_j - r_i| < h_i * radius, with SPHGPU_COMPONENTS_SEPARATE_BY_FLAG
+ * (ComponentFlag::SEPARATE_BY_FLAG) only between equal body flags. indices (host, particle_count entries) receives the
+ * component of every particle, numbered like the reference numbers them (in the order of the lowest particle index of each
+ * component), *component_count their number; bit-identical to the reference. ESCAPE_VELOCITY and SORT_BY_MASS post-process
+ * this result on the host (GpuPost::findComponents in opensph_b200/host). sweeps (may be NULL): label-propagation sweeps used.
+ * Single domain only; rebuilds the cell list (the next evaluation rebuilds its neighbour lists). */
+enum { SPHGPU_COMPONENTS_SEPARATE_BY_FLAG = 1u << 0 };
+SPHGPU_API int sphgpu_find_components(sphgpu_ctx* ctx, double radius, uint32_t flags, uint32_t* indices, uint32_t* component_count,
+    uint32_t* sweeps);
 SPHGPU_API int sphgpu_neighbour_dump(sphgpu_ctx* ctx, uint64_t* offsets, uint32_t* idx, uint64_t idx_capacity);
 /* Device-time breakdown of the last integrate call in milliseconds: [0] grid build + sort, [1] prologue + pack,
  * [2] pair kernel, [3] rest. */

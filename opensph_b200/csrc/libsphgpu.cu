@@ -10,3 +10,4 @@
 #include "halo.cu"
 #include "gravity.cu"
 #include "lattice.cu"
+#include "components.cu"

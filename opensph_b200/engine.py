@@ -321,6 +321,15 @@ class Engine:
                                               idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(idx))))
         return off, idx
 
+    def find_components(self, radius: float, separate_by_flag: bool = False) -> Tuple[np.ndarray, int, int]:
+        """Post::findComponents of the reference on the particles in the context (core/post/Analysis.cpp:36-75,115-128): returns
+        (component index of every particle, number of components, label-propagation sweeps the device needed)."""
+        idx = np.zeros(max(self.n, 1), np.uint32)
+        count, sweeps = C.c_uint32(0), C.c_uint32(0)
+        _check(self.lib.sphgpu_find_components(self._ctx, C.c_double(radius), C.c_uint32(1 if separate_by_flag else 0),
+                                               idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(count), C.byref(sweeps)))
+        return idx[:self.n], int(count.value), int(sweeps.value)
+
     def last_timings(self) -> np.ndarray:
         ms = np.zeros(4)
         _check(self.lib.sphgpu_last_timings(self._ctx, ms.ctypes.data_as(C.POINTER(C.c_double))))

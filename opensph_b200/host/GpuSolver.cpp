@@ -580,6 +580,92 @@ void GpuSolver::download(Storage& storage) {
     hostStale = false;
 }
 
+namespace {
+
+/// The checker of the second pass of Post::findComponents with ESCAPE_VELOCITY (Analysis.cpp:97-112): components whose
+/// relative speed is below their mutual escape speed belong together.
+struct BoundComponents : public Post::IComponentChecker {
+    ArrayView<const Vector> r, v;
+    ArrayView<const Float> m;
+
+    virtual bool belong(const Size i, const Size j) const override {
+        const Float dv = getLength(v[i] - v[j]);
+        const Float dr = getLength(r[i] - r[j]);
+        return dv < sqrt(2._f * Constants::gravity * (m[i] + m[j]) / dr);
+    }
+};
+
+} // namespace
+
+Size GpuSolver::findComponents(const Storage& storage, const Float particleRadius, const Flags<Post::ComponentFlag> flags,
+    Array<Size>& indices) {
+    sphgpu_ctx* c = this->context(storage);
+    const Size n = storage.getParticleCnt();
+    ArrayView<const Vector> r = storage.getValue<Vector>(QuantityId::POSITION);
+    check(sphgpu_upload(c, SPHGPU_Q_POSITION, 0, SPHGPU_LAYOUT_OPENSPH, &r[0], 0, n));
+    uint32_t deviceFlags = 0;
+    if (flags.has(Post::ComponentFlag::SEPARATE_BY_FLAG)) {
+        check(sphgpu_upload(c, SPHGPU_Q_FLAG, 0, SPHGPU_LAYOUT_OPENSPH, &storage.getValue<Size>(QuantityId::FLAG)[0], 0, n));
+        deviceFlags |= SPHGPU_COMPONENTS_SEPARATE_BY_FLAG;
+    }
+    indices.resize(n);
+    static_assert(sizeof(Size) == sizeof(uint32_t), "Size is a 32-bit index");
+    uint32_t count = 0;
+    check(sphgpu_find_components(c, particleRadius, deviceFlags, reinterpret_cast<uint32_t*>(&indices[0]), &count, nullptr));
+    Size componentCnt = count;
+
+    if (flags.has(Post::ComponentFlag::ESCAPE_VELOCITY)) {
+        // mass, barycentre, mean velocity and equivalent radius of every component, summed in particle order
+        Array<Float> masses(componentCnt), volumes(componentCnt);
+        Array<Vector> positions(componentCnt), velocities(componentCnt);
+        masses.fill(0._f);
+        volumes.fill(0._f);
+        positions.fill(Vector(0._f));
+        velocities.fill(Vector(0._f));
+        ArrayView<const Float> m = storage.getValue<Float>(QuantityId::MASS);
+        ArrayView<const Vector> v = storage.getDt<Vector>(QuantityId::POSITION);
+        for (Size i = 0; i < n; ++i) {
+            const Size k = indices[i];
+            masses[k] += m[i];
+            positions[k] += m[i] * r[i];
+            velocities[k] += m[i] * v[i];
+            volumes[k] += pow<3>(r[i][H]);
+        }
+        for (Size k = 0; k < componentCnt; ++k) {
+            positions[k] /= masses[k];
+            positions[k][H] = cbrt(3._f * volumes[k] / (4._f * PI));
+            velocities[k] /= masses[k];
+        }
+        BoundComponents bound;
+        bound.r = positions;
+        bound.v = velocities;
+        bound.m = masses;
+        Storage bodies;
+        bodies.insert<Vector>(QuantityId::POSITION, OrderEnum::ZERO, positions.clone());
+        Array<Size> merged;
+        componentCnt = Post::findComponents(bodies, 50._f, bound, merged);
+        for (Size i = 0; i < n; ++i) {
+            indices[i] = merged[indices[i]];
+        }
+    }
+    if (flags.has(Post::ComponentFlag::SORT_BY_MASS)) {
+        Array<Float> componentMass(componentCnt);
+        componentMass.fill(0._f);
+        ArrayView<const Float> m = storage.getValue<Float>(QuantityId::MASS);
+        for (Size i = 0; i < n; ++i) {
+            componentMass[indices[i]] += m[i];
+        }
+        Order byMass(componentCnt);
+        byMass.shuffle([&componentMass](const Size a, const Size b) { return componentMass[a] > componentMass[b]; });
+        const Order rank = byMass.getInverted();
+        for (Size i = 0; i < n; ++i) {
+            indices[i] = rank[indices[i]];
+        }
+    }
+    // the context now holds these positions; the next integrate() uploads its own state anyway
+    return componentCnt;
+}
+
 void GpuSolver::integrate(Storage& storage, Statistics& stats) {
     // ISolver contract: highest derivatives are zero on entry (ISolver.h:33-34); the device overwrites them, which is
     // what the reference's accumulate-into-zero amounts to.

@@ -22,6 +22,7 @@
 
 #include "gravity/IGravity.h"
 #include "io/Output.h"
+#include "post/Analysis.h"
 #include "sph/boundary/Boundary.h"
 #include "sph/equations/EquationTerm.h"
 #include "system/Settings.h"
@@ -125,6 +126,12 @@ public:
             this->configureVariant();
         }
     }
+
+    /// Post::findComponents (core/post/Analysis.cpp:115-217) with the flood over the particles on the device
+    /// (sphgpu_find_components: same components, same numbering). ComponentFlag::ESCAPE_VELOCITY merges the components found --
+    /// a problem of the size of their number -- through the reference's own public overload with a checker, SORT_BY_MASS
+    /// renumbers them by mass, both on the host exactly like the reference does.
+    Size findComponents(const Storage& storage, const Float particleRadius, const Flags<Post::ComponentFlag> flags, Array<Size>& indices);
 
     /// True if a boundary condition runs on the host inside integrate() (KillEscapersBoundary).
     bool hasHostBoundary() const {

@@ -24,6 +24,9 @@
 //       softening kernel's gradient table (grav_lut), grav_params {theta, order, G, kernel radius, leaf size, seconds}
 //       and, for Barnes-Hut, the moments of the root node (BarnesHut::getMoments) with the accelerations
 //       evaluateGravity (core/gravity/Moments.h:315-340) derives from them at a few distant probe points.
+//   sph_ref components --config C --n N [--jitter SEED] --radius X [--separate-by-flag] [--sort-by-mass] --out OUT.snap
+//       Post::findComponents (core/post/Analysis.cpp:36-75,115-217) on the particles of config C: OUT.snap holds pos, mass, flag,
+//       comp_idx and comp_params {radius, flags, component count, seconds}.
 //   sph_ref bench    --config C --n N --steps K --warmup W [--threads T] [--finder kd|grid] [--integrate-only] [--fixed-dt X]
 //       prints one JSON line with seconds per step of the reference CPU path.
 //
@@ -32,6 +35,7 @@
 #include "Sph.h"
 #include "gravity/BarnesHut.h"
 #include "gravity/Moments.h"
+#include "post/Analysis.h"
 #include "sph/kernel/GravityKernel.h"
 #include "tests/Setup.h"
 #include <chrono>
@@ -731,6 +735,31 @@ int main(int argc, char** argv) {
             w.write(args.str("out", "gravity.snap"));
             printf("{\"particles\": %u, \"gravity\": \"%s\", \"theta\": %g, \"order\": %d, \"seconds\": %.4f, \"threads\": %d}\n", N,
                 brute ? "brute" : "bh", theta, order, seconds, int(scheduler->getThreadCnt()));
+        } else if (cmd == "components") {
+            // Post::findComponents (core/post/Analysis.cpp:115-217) on the positions of the config: --radius X (in units of h),
+            // --separate-by-flag, --sort-by-mass
+            const Float radius = Float(atof(args.str("radius", "1").c_str()));
+            Flags<Post::ComponentFlag> flags = Post::ComponentFlag::OVERLAP;
+            if (args.has("separate-by-flag")) {
+                flags.set(Post::ComponentFlag::SEPARATE_BY_FLAG);
+            }
+            if (args.has("sort-by-mass")) {
+                flags.set(Post::ComponentFlag::SORT_BY_MASS);
+            }
+            Array<Size> indices;
+            const double t0 = now();
+            const Size count = Post::findComponents(*storage, radius, flags, indices);
+            const double seconds = now() - t0;
+            SnapWriter w;
+            w.addF64("pos", vec4(storage->getValue<Vector>(QuantityId::POSITION)), 4);
+            w.addF64("mass", scal(storage->getValue<Float>(QuantityId::MASS)), 1);
+            if (storage->has(QuantityId::FLAG)) {
+                w.addU32("flag", uscal(storage->getValue<Size>(QuantityId::FLAG)), 1);
+            }
+            w.addU32("comp_idx", uscal(indices), 1);
+            w.addF64("comp_params", { double(radius), double(flags.value()), double(count), seconds }, 1);
+            w.write(args.str("out", "out.snap"));
+            std::cout << "{\"particles\": " << N << ", \"components\": " << count << ", \"seconds\": " << seconds << "}" << std::endl;
         } else if (cmd == "bench") {
             const long steps = args.num("steps", 3), warmup = args.num("warmup", 1);
             Statistics stats;

@@ -1466,3 +1466,109 @@ void orc_frozen(orc_state* s, int solid, uint64_t flag_mask, int has_domain, con
         }
     }
 }
+
+/* ---- connected components ------------------------------------------------------------------- */
+
+/* Post::findComponents without ESCAPE_VELOCITY / SORT_BY_MASS = findComponentsImpl (core/post/Analysis.cpp:36-75,115-128):
+ * particles are visited in index order; an unassigned one opens the next component and floods it through a stack over the
+ * DIRECTED relation "j lies within h_index * radius of index" (IBasicFinder::findAll(index, r[index][H] * radius): distSqr <
+ * radius^2, KdTree.inl.h), restricted to equal body flags when flag != NULL (FlagComponentChecker, Analysis.cpp:84-94).
+ * A uniform grid with cells of the largest reach replaces the reference's k-d tree (same candidate sets). */
+uint32_t orc_find_components(const double* pos, uint32_t n, double radius, const uint32_t* flag, uint32_t* indices) {
+    if (n == 0) {
+        return 0;
+    }
+    double lo[3] = { pos[0], pos[1], pos[2] }, hi[3] = { pos[0], pos[1], pos[2] }, reachMax = 0.;
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int q = 0; q < 3; ++q) {
+            lo[q] = dmin(lo[q], pos[4 * (size_t)i + q]);
+            hi[q] = dmax(hi[q], pos[4 * (size_t)i + q]);
+        }
+        reachMax = dmax(reachMax, pos[4 * (size_t)i + 3] * radius);
+    }
+    int dim[3];
+    double cell = reachMax * (1. + 1.e-9);
+    for (int q = 0; q < 3; ++q) {
+        cell = dmax(cell, (hi[q] - lo[q]) / 200.); /* at most 200 cells per axis */
+    }
+    if (!(cell > 0.)) {
+        cell = 1.;
+    }
+    for (int q = 0; q < 3; ++q) {
+        dim[q] = (int)((hi[q] - lo[q]) / cell) + 1;
+    }
+    const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
+    uint32_t* start = (uint32_t*)calloc(ncell + 1, sizeof(uint32_t));
+    uint32_t* items = (uint32_t*)malloc(sizeof(uint32_t) * n);
+    uint32_t* cellOf = (uint32_t*)malloc(sizeof(uint32_t) * n);
+    for (uint32_t i = 0; i < n; ++i) {
+        int c[3];
+        for (int q = 0; q < 3; ++q) {
+            c[q] = (int)((pos[4 * (size_t)i + q] - lo[q]) / cell);
+            c[q] = c[q] < 0 ? 0 : (c[q] >= dim[q] ? dim[q] - 1 : c[q]);
+        }
+        cellOf[i] = (uint32_t)((c[2] * dim[1] + c[1]) * dim[0] + c[0]);
+        start[cellOf[i] + 1]++;
+    }
+    for (size_t c = 0; c < ncell; ++c) {
+        start[c + 1] += start[c];
+    }
+    uint32_t* fill = (uint32_t*)malloc(sizeof(uint32_t) * (ncell + 1));
+    memcpy(fill, start, sizeof(uint32_t) * (ncell + 1));
+    for (uint32_t i = 0; i < n; ++i) {
+        items[fill[cellOf[i]]++] = i;
+    }
+    free(fill);
+    const uint32_t unassigned = 0xffffffffu;
+    for (uint32_t i = 0; i < n; ++i) {
+        indices[i] = unassigned;
+    }
+    uint32_t* stack = (uint32_t*)malloc(sizeof(uint32_t) * n);
+    uint32_t componentIdx = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (indices[i] != unassigned) {
+            continue;
+        }
+        uint32_t sp = 0;
+        indices[i] = componentIdx;
+        stack[sp++] = i;
+        while (sp > 0) {
+            const uint32_t index = stack[--sp];
+            const double* ri = pos + 4 * (size_t)index;
+            const double reach = ri[3] * radius;
+            const double reachSqr = reach * reach;
+            const uint32_t c = cellOf[index];
+            const int cx = (int)(c % (uint32_t)dim[0]), cy = (int)((c / (uint32_t)dim[0]) % (uint32_t)dim[1]),
+                      cz = (int)(c / ((uint32_t)dim[0] * (uint32_t)dim[1]));
+            for (int z = cz > 0 ? cz - 1 : 0; z <= (cz + 1 < dim[2] ? cz + 1 : dim[2] - 1); ++z) {
+                for (int y = cy > 0 ? cy - 1 : 0; y <= (cy + 1 < dim[1] ? cy + 1 : dim[1] - 1); ++y) {
+                    for (int x = cx > 0 ? cx - 1 : 0; x <= (cx + 1 < dim[0] ? cx + 1 : dim[0] - 1); ++x) {
+                        const size_t cc = ((size_t)z * dim[1] + y) * dim[0] + x;
+                        for (uint32_t k = start[cc]; k < start[cc + 1]; ++k) {
+                            const uint32_t j = items[k];
+                            if (indices[j] != unassigned) {
+                                continue;
+                            }
+                            const double* rj = pos + 4 * (size_t)j;
+                            const double dx = rj[0] - ri[0], dy = rj[1] - ri[1], dz = rj[2] - ri[2];
+                            if (!(dx * dx + dy * dy + dz * dz < reachSqr)) {
+                                continue;
+                            }
+                            if (flag && flag[index] != flag[j]) {
+                                continue;
+                            }
+                            indices[j] = componentIdx;
+                            stack[sp++] = j;
+                        }
+                    }
+                }
+            }
+        }
+        componentIdx++;
+    }
+    free(stack);
+    free(cellOf);
+    free(items);
+    free(start);
+    return componentIdx;
+}

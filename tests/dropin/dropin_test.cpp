@@ -508,6 +508,32 @@ int main(int argc, char** argv) {
             expect(frozenCnt > 0 && frozenCnt < dvF.size(), "the boundary condition freezes some particles");
             expect(compareStorages(fa, fb, true, "integrate() with FrozenParticles") <= 1.e-10, "all quantities within 1e-10 with FrozenParticles");
         }
+        // ---- Post::findComponents: the reference's flood against the device's label propagation, every flag combination ----
+        {
+            GpuSolver gpuC(*scheduler, settings, getStandardEquations(settings));
+            Storage cs = base->clone(VisitorEnum::ALL_BUFFERS);
+            for (Size m = 0; m < cs.getMaterialCnt(); ++m) {
+                gpuC.create(cs, cs.getMaterial(m));
+            }
+            using Post::ComponentFlag;
+            const Flags<ComponentFlag> combos[] = { ComponentFlag::OVERLAP, ComponentFlag::SEPARATE_BY_FLAG, ComponentFlag::SORT_BY_MASS,
+                ComponentFlag::SEPARATE_BY_FLAG | ComponentFlag::SORT_BY_MASS, ComponentFlag::ESCAPE_VELOCITY,
+                ComponentFlag::ESCAPE_VELOCITY | ComponentFlag::SORT_BY_MASS };
+            for (const Float radius : { 0.45_f, 0.6_f, 1._f }) {
+                for (const Flags<ComponentFlag> f : combos) {
+                    Array<Size> ia, ib;
+                    const Size ca = Post::findComponents(cs, radius, f, ia);
+                    const Size cb = gpuC.findComponents(cs, radius, f, ib);
+                    bool same = ca == cb && ia.size() == ib.size();
+                    for (Size i = 0; same && i < ia.size(); ++i) {
+                        same = ia[i] == ib[i];
+                    }
+                    printf("  [findComponents] radius %.2f flags %u: %u components (reference), %u (GpuSolver)\n", double(radius), unsigned(f.value()),
+                        unsigned(ca), unsigned(cb));
+                    expect(same, "component indices identical to Post::findComponents");
+                }
+            }
+        }
         // ---- the artificial stress (SPH_AV_USE_STRESS): two consecutive evaluations against the reference ----
         {
             RunSettings as = settings;
