@@ -416,6 +416,22 @@ def main():
         except Exception as e:
             gravity = {"failed": str(e)}
 
+    # Connected components of the same particles (Post::findComponents): reported beside the headline as well.
+    components = None
+    if world == 1 and not args.no_gravity:
+        try:
+            eng.find_components(1.0)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                _, ccount, csweeps = eng.find_components(1.0)
+                best = min(best, time.perf_counter() - t0) if best is not None else time.perf_counter() - t0
+            components = {"unit": "ms per call", "radius": 1.0, "ms": 1.0e3 * best, "components": int(ccount), "sweeps": int(csweeps),
+                          "particles": int(n_owned),
+                          "what": "sphgpu_find_components through the C ABI, wall clock: cell list + label-propagation sweeps + indices to the host"}
+        except Exception as e:
+            components = {"failed": str(e)}
+
     per_rank = None
     if world > 1:  # per-rank device-time breakdown (ms per step): grid, prologue, pair kernel, rest, of which halo exchange
         mine = torch.tensor(list(timings / args.steps) + [halo_ms / args.steps, float(n_owned)], dtype=torch.float64, device="cuda")
@@ -488,6 +504,8 @@ def main():
     }
     if gravity is not None:
         out["gravity"] = gravity
+    if components is not None:
+        out["components"] = components
     if per_rank is not None:
         out["per_rank_ms"] = {"columns": ["grid_build", "prologue_pack", "pair_kernel", "rest", "halo_exchange_in_rest", "owned_particles"],
                               "rows": per_rank}
