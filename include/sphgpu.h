@@ -52,7 +52,9 @@ enum {
     SPHGPU_FLAG_ADAPTIVE_H = 1u << 2,           /* SmoothingLengthEnum::CONTINUITY_EQUATION                  */
     SPHGPU_FLAG_SOUND_SPEED_ENFORCING = 1u << 3, /* SmoothingLengthEnum::SOUND_SPEED_ENFORCING               */
     SPHGPU_FLAG_BALSARA = 1u << 4,              /* RunSettingsId::SPH_AV_USE_BALSARA: BalsaraSwitch<StandardAV>,
-                                                   core/sph/equations/av/Balsara.h:36-153                      */
+                                                   core/sph/equations/av/Balsara.h:36-153. Not on decomposed runs
+                                                   (sphgpu_halo_configure refuses: the ghosts do not carry the div v /
+                                                   rot v of the previous evaluation)                            */
     SPHGPU_FLAG_XSPH = 1u << 5,                 /* RunSettingsId::SPH_USE_XSPH: the XSph term, core/sph/equations/XSph.h:20-97;
                                                    its epsilon is set with sphgpu_set_xsph_epsilon. Not together with
                                                    SPHGPU_FLAG_BALSARA, not on decomposed runs                 */
@@ -241,6 +243,8 @@ SPHGPU_API int sphgpu_halo_unpack(sphgpu_ctx* ctx, uint32_t first, uint32_t coun
  *  - sphgpu_comm_init: every rank joins the communicator (collective);
  *  - sphgpu_halo_configure: neighbour ranks (-1 = none) and the sizes of the slot bands [0, send_left) and
  *    [n - send_right, n) that are sent, and of the ghost ranges [n, n + recv_left), [.., + recv_right) that are filled;
+ *    SPHGPU_E_INVALID for contexts with SPHGPU_FLAG_BALSARA / _XSPH / _DELTASPH / _STRESS_AV, whose pair terms need per-particle
+ *    results of the previous evaluation (or constants) that the bands do not carry;
  *  - sphgpu_halo_exchange: pack -> grouped ncclSend/ncclRecv -> unpack, queued on the context's stream;
  *  - sphgpu_step_pc_mgpu: predict -> halo exchange -> integrate -> correct -> criteria -> ncclAllReduce(min) of the time
  *    step, one host synchronisation per step. */
