@@ -56,6 +56,32 @@ def test_directed_relation_is_exercised_by_the_golden_vectors():
     assert (fwd & ~fwd.T).sum() > 10
 
 
+@pytest.mark.parametrize("seed,spread,radius", [(11, 1.0, 0.9), (12, 3.0, 0.55), (13, 6.0, 0.35)])
+def test_min_ancestor_labels_equal_the_flood(seed, spread, radius):
+    """The statement the device algorithm rests on (components.cu), checked without a GPU: iterating
+    label(p) = min(p, min over q -> p of label(q)) to its fixed point over the DIRECTED relation, and ranking the roots in index
+    order, reproduces the sequential flood of the reference -- numbering included."""
+    n = 1500
+    pos = random_cloud(n, seed, spread)
+    d2 = ((pos[:, None, :3] - pos[None, :, :3]) ** 2).sum(-1)
+    edge = d2 < ((pos[:, 3] * radius) ** 2)[:, None]   # edge[q, p]: p lies within the reach of q
+    assert (edge & ~edge.T).any() or spread == 1.0
+    label = np.arange(n)
+    for _ in range(n):
+        pushed = np.where(edge, label[:, None], n).min(axis=0)   # lowest label among the particles that reach p
+        new = np.minimum(label, pushed)
+        new = np.minimum(new, new[new])                          # pointer jumping: an ancestor's ancestor is an ancestor
+        if np.array_equal(new, label):
+            break
+        label = new
+    roots = np.flatnonzero(label == np.arange(n))
+    rank = np.zeros(n, np.int64)
+    rank[roots] = np.arange(len(roots))
+    ref, count = oracle_components(pos, radius)
+    assert count == len(roots) and 1 < count < n
+    assert np.array_equal(rank[label], ref)
+
+
 def engine_with_positions(pos, flag=None):
     from opensph_b200.engine import Engine
     n = len(pos)
