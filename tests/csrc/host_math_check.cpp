@@ -190,6 +190,13 @@ extern "C" int hostcheck_integrate(orc_state* s, const sphgpu_config* cfg, const
     return masked ? dispatch<true>(s, cfg, mats, nmat, off, idx) : dispatch<false>(s, cfg, mats, nmat, off, idx);
 }
 
+/// The product's artificial-stress tensor function (sph_math.cuh: avStressOf) for n tensors {xx,yy,zz,xy,xz,yz}.
+extern "C" void hostcheck_av_stress(uint32_t n, const double* sigma, double* as) {
+    for (uint32_t i = 0; i < n; ++i) {
+        avStressOf(sigma + 6 * (size_t)i, as + 6 * (size_t)i);
+    }
+}
+
 // ---- self-gravity arithmetic (opensph_b200/csrc/grav_math.cuh) ------------------------------------------------------
 #include "../../opensph_b200/csrc/grav_math.cuh"
 

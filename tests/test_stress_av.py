@@ -70,6 +70,38 @@ def test_product_stress_av_math_matches_golden(masked, lut):
         assert_close(k, st.a[k], o[k], 1e-10, FLOOR)
 
 
+def test_product_av_stress_is_minus_the_positive_part_of_the_tensor():
+    """avStressOf (Jacobi rotations) against numpy's eigh on random, degenerate, diagonal, rank-one, zero and badly scaled
+    tensors: as = -V max(Lambda, 0) V^T is a function of the tensor, whatever the eigen-solver."""
+    src = os.path.join(ROOT, "tests", "csrc", "host_math_check.cpp")
+    lib = os.path.join(ROOT, "tests", "csrc", "libhostcheck.so")
+    deps = [src, os.path.join(ROOT, "opensph_b200", "csrc", "sph_math.cuh"), os.path.join(ROOT, "opensph_b200", "csrc", "grav_math.cuh"),
+            os.path.join(ROOT, "oracle", "sph_oracle.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", src, "-o", lib])
+    hostcheck = C.CDLL(lib)
+    rng = np.random.default_rng(21)
+    mats = []
+    for _ in range(2000):
+        a = rng.normal(size=(3, 3)) * 10.0 ** rng.uniform(-3, 9)
+        mats.append(0.5 * (a + a.T))
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    for lam in ([1., 1., 1.], [2., 2., -1.], [3., -1., -1.], [0., 0., 0.], [1e9, 1e-9, -1e9], [5., 0., 0.], [-1., -2., -3.]):
+        mats.append(q @ np.diag(lam) @ q.T)          # degenerate / semi-definite / definite spectra in a rotated frame
+        mats.append(np.diag(lam))                    # and already diagonal
+    v = rng.normal(size=3)
+    mats.append(np.outer(v, v))                      # rank one
+    m = np.array(mats)
+    sig = np.ascontiguousarray(np.stack([m[:, 0, 0], m[:, 1, 1], m[:, 2, 2], m[:, 0, 1], m[:, 0, 2], m[:, 1, 2]], axis=1))
+    out = np.zeros_like(sig)
+    hostcheck.hostcheck_av_stress(C.c_uint32(len(sig)), sig.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    w, vec = np.linalg.eigh(m)
+    ref = -np.einsum("nik,nk,njk->nij", vec, np.maximum(w, 0.), vec)
+    want = np.stack([ref[:, 0, 0], ref[:, 1, 1], ref[:, 2, 2], ref[:, 0, 1], ref[:, 0, 2], ref[:, 1, 2]], axis=1)
+    scale = np.abs(sig).max(axis=1, keepdims=True) + 1e-300
+    assert np.abs(out - want).max(initial=0.) <= 0 or (np.abs(out - want) / scale).max() <= 1e-13
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_gpu_stress_av_matches_golden(variant, lut):
